@@ -1,0 +1,342 @@
+"""Synthetic NRSC-5 FM captures (cu8 I/Q at 1 488 375 S/s) with known L1 PDUs.
+
+The reference ships no modulator.  This generator inverts the receive chain
+stage by stage, so that a correct receiver returns exactly the frame bits
+generated here (recipe: SURVEY.md §8(d), each step derived from the decoder):
+
+  payload -> scramble (reference src/decode.c:279-294) -> rate-1/3 K=7
+  tail-biting encode, g=(0133,0171,0165) (decode.c:238-255, conv_dec.c:139-154)
+  -> puncture 1,1,1,1,1,0 (decode.c:263) -> inverse of interleaver I / II
+  (decode.c:296-342) -> QPSK map onto partitions (sync.c:509-536) + DBPSK
+  reference subcarriers (sync.c:96-99,169-186) -> 2x-oversampled OFDM with the
+  receiver's raised-sine pulse shape (acquire.c:322-331) -> cu8 (defines.h:93).
+
+Used by bench.py for its synthetic workload and by the tests; pure numpy.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from functools import lru_cache
+
+import numpy as np
+
+FFT = 2048
+CP = 112
+FFTCP = FFT + CP
+BLKSZ = 32
+LB_START = 1024 - 546
+UB_END = 1024 + 546
+P1_BITS = 146176
+PIDS_BITS = 80
+PM_BLOCK = 23040
+BLOCKS_PER_FRAME = 16
+SAMPLES_PER_BLOCK_CU8 = FFTCP * BLKSZ * 2  # complex cu8 samples per L1 block
+PCI_AUDIO = 0x38D8D3
+PCI_FIXED = 0x3634CE
+PM_V = np.array([10, 2, 18, 6, 14, 8, 16, 0, 12, 4, 11, 3, 19, 7, 15, 9, 17, 1, 13, 5])
+GENS_K7 = (0o133, 0o171, 0o165)
+
+
+# ----------------------------------------------------------------------------
+# bit-level pieces
+# ----------------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def pn_sequence(n: int) -> np.ndarray:
+    """The descrambler's bit sequence (reference src/decode.c:279-294)."""
+    out = np.empty((n + 7) // 8 * 8, dtype=np.uint8)
+    val = 0x3FF
+    for i in range(out.size):
+        bit = ((val >> 9) ^ val) & 1
+        val |= bit << 11
+        val >>= 1
+        out[i] = bit
+    return out[:n]
+
+
+def conv_encode_tb(u: np.ndarray, gens=GENS_K7, k: int = 7) -> np.ndarray:
+    """Tail-biting rate-1/3 encoder; returns coded[len(u), 3] in {0,1}.
+    Register convention of reference src/decode.c:243-249: newest bit at bit k-1."""
+    u = np.asarray(u, dtype=np.uint8)
+    out = np.zeros((u.size, len(gens)), dtype=np.uint8)
+    for gi, g in enumerate(gens):
+        acc = np.zeros(u.size, dtype=np.uint8)
+        for b in range(k):
+            if (g >> b) & 1:
+                acc ^= np.roll(u, (k - 1) - b)
+        out[:, gi] = acc
+    return out
+
+
+@lru_cache(maxsize=None)
+def interleaver_i_index() -> np.ndarray:
+    """Matrix index read by interleaver I for each of the 365 440 punctured P1
+    bits (reference src/decode.c:296-322 with J=20,B=16,C=36,M=1)."""
+    i = np.arange(P1_BITS * 5 // 2, dtype=np.int64)
+    J, B, C = 20, 16, 36
+    part = PM_V[i % 20]
+    block = ((i // J) + part * 7) % B
+    k = i // (J * B)
+    row = (k * 11) % 32
+    col = (k * 11 + k // (32 * 9)) % C
+    return (block * 32 + row) * (J * C) + part * C + col
+
+
+@lru_cache(maxsize=None)
+def interleaver_ii_index() -> np.ndarray:
+    """[16, 200] matrix indices for the PIDS bits of each block
+    (reference src/decode.c:324-342 with b=200, I0=365 440)."""
+    J, B, C, b, I0 = 20, 16, 36, 200, 365440
+    i = np.arange(16 * b, dtype=np.int64)
+    part = PM_V[i % 20]
+    block = i // b
+    k = ((i // J) % (b // J)) + (I0 // (J * B))
+    row = (k * 11) % 32
+    col = (k * 11 + k // (32 * 9)) % C
+    return ((block * 32 + row) * (J * C) + part * C + col).reshape(16, b)
+
+
+# ----------------------------------------------------------------------------
+# GF(256) Reed-Solomon (255,247) systematic encoder, poly 0x11d, fcr=1, prim=1
+# (decoder side: reference src/rs_decode.c, src/rs_init.c:31-133 as configured
+#  by src/frame.c:747).  The reference only declares an encoder (rs_char.h:48).
+# ----------------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def _gf_tables():
+    exp = np.zeros(512, dtype=np.int32)
+    log = np.zeros(256, dtype=np.int32)
+    sr = 1
+    for i in range(255):
+        exp[i] = sr
+        log[sr] = i
+        sr <<= 1
+        if sr & 0x100:
+            sr ^= 0x11D
+    exp[255:510] = exp[0:255]
+    return exp, log
+
+
+def _gf_mul(a: int, b: int) -> int:
+    if a == 0 or b == 0:
+        return 0
+    exp, log = _gf_tables()
+    return int(exp[log[a] + log[b]])
+
+
+@lru_cache(maxsize=None)
+def _rs_genpoly():
+    exp, _ = _gf_tables()
+    g = [1]
+    for i in range(8):
+        root = int(exp[1 + i])
+        ng = [0] * (len(g) + 1)
+        for j, c in enumerate(g):  # multiply by (x + root); g[j] is coeff of x^j
+            ng[j + 1] ^= c
+            ng[j] ^= _gf_mul(c, root)
+        g = ng
+    return g  # degree 8, g[8] == 1
+
+
+def rs_parity(msg247: bytes) -> bytes:
+    """Parity of the systematic (255,247) code; msg247[0] is the highest-degree
+    symbol.  Returns 8 bytes, highest degree first (codeword = msg + parity)."""
+    g = _rs_genpoly()
+    rem = [0] * 8  # rem[0] = coefficient of x^7
+    for m in msg247:
+        fb = m ^ rem[0]
+        rem = rem[1:] + [0]
+        if fb:
+            for j in range(8):
+                rem[j] ^= _gf_mul(fb, g[7 - j])
+    return bytes(rem)
+
+
+def audio_pdu_header(fields: bytes | None = None, rng=None) -> bytes:
+    """A valid 96-byte RS-protected L2 audio-PDU header as laid out by reference
+    src/frame.c:158-196: buf[0..7] parity, buf[8..13] header fields, rest payload.
+    Default fields: codec 0, stream 0, nop=0, hef=0, la_location=13, so the
+    reference's frame_process() consumes the header, finds no packets and stops."""
+    buf = bytearray(96)
+    if rng is not None:
+        buf[14:96] = rng.integers(0, 256, 82, dtype=np.uint8).tobytes()
+    if fields is None:
+        fields = bytes([0x00, 0x00, 0x00, 0x00, 0x00, 13])
+    buf[8:14] = fields
+    # reference block: hdr[254 - i] = buf[i]; positions 0..158 are zero padding
+    msg = bytes(159) + bytes(buf[95 - k] for k in range(88))
+    par = rs_parity(msg)  # block[247..254] = buf[7..0]
+    for k in range(8):
+        buf[7 - k] = par[k]
+    return bytes(buf)
+
+
+def build_p1_frame_bits(rng, pci: int = PCI_AUDIO, valid_header: bool = True) -> np.ndarray:
+    """146 176 descrambled frame bits exactly as handed to frame_push()
+    (reference src/frame.c:645-714): per-byte bit reversal, 24 PCI bits at
+    logical positions 116176 + 1248 h, the rest packed MSB-first into the PDU."""
+    logical = np.zeros(P1_BITS, dtype=np.uint8)
+    pci_pos = 116176 + 1248 * np.arange(24)
+    is_pci = np.zeros(P1_BITS, dtype=bool)
+    is_pci[pci_pos] = True
+    logical[pci_pos] = [(pci >> (23 - h)) & 1 for h in range(24)]
+    npdu = P1_BITS - 24
+    pdu = rng.integers(0, 256, npdu // 8, dtype=np.uint8)
+    if valid_header:
+        pdu[:96] = np.frombuffer(audio_pdu_header(rng=rng), dtype=np.uint8)
+    else:
+        # last PDU byte with unequal nibbles (no fixed-data sync, frame.c:448-456)
+        pdu[-1] = 0x12
+    logical[~is_pci] = np.unpackbits(pdu)  # MSB first
+    i = np.arange(P1_BITS)
+    phys = (i & ~7) + 7 - (i & 7)
+    bits = np.zeros(P1_BITS, dtype=np.uint8)
+    bits[phys] = logical
+    return bits
+
+
+# ----------------------------------------------------------------------------
+# reference subcarriers
+# ----------------------------------------------------------------------------
+def ref_raw_bits(bc: int, psmi: int, rsid: int) -> np.ndarray:
+    """32 raw BPSK bits of one reference subcarrier for one block, such that
+    decode_ref_fm() (reference src/sync.c:169-186) accepts it and decodes
+    block count `bc` and service mode `psmi` after DBPSK decoding."""
+    r = np.zeros(32, dtype=np.uint8)
+    fixed = {0: 0, 1: 1, 2: 0, 3: 0, 4: 0, 5: 1, 6: 1, 8: 1, 9: 0, 10: rsid >> 1,
+             11: (rsid >> 1) ^ (rsid & 1), 13: 0, 14: 0, 20: 0, 21: 1, 22: 0, 31: 0}
+    for k, v in fixed.items():
+        r[k] = v
+    r[15] = 0
+    for n, sh in zip(range(16, 20), (3, 2, 1, 0)):
+        r[n] = r[n - 1] ^ ((bc >> sh) & 1)
+    r[23] = r[24] = 0
+    for n, sh in zip(range(25, 31), (5, 4, 3, 2, 1, 0)):
+        r[n] = r[n - 1] ^ ((psmi >> sh) & 1)
+    return r
+
+
+# ----------------------------------------------------------------------------
+# capture
+# ----------------------------------------------------------------------------
+@dataclass
+class FmCapture:
+    cu8: np.ndarray                      # uint8 [2 * nsamples], I/Q interleaved
+    p1_frames: list = field(default_factory=list)    # list of uint8[146176] frame bits
+    pids_frames: list = field(default_factory=list)  # list of uint8[80], block order
+    psmi: int = 1
+    lead_in: int = 0
+
+
+@lru_cache(maxsize=None)
+def _shape2x() -> np.ndarray:
+    """Receiver pulse shape (reference src/acquire.c:322-331) sampled at 2x."""
+    j = np.arange(2 * FFTCP, dtype=np.float64)
+    s = np.ones(2 * FFTCP)
+    s[: 2 * CP] = np.sin(np.pi / 2 * j[: 2 * CP] / (2 * CP))
+    s[2 * FFT:] = np.cos(np.pi / 2 * (j[2 * FFT:] - 2 * FFT) / (2 * CP))
+    return s
+
+
+def _block_matrix_to_bins(mat_block: np.ndarray, refs: dict) -> np.ndarray:
+    """mat_block: [32 rows][20 partitions][36 cols] bits -> complex S[32, 2048]
+    in the receiver's fftshift-ed bin order (sync.c:509-536)."""
+    S = np.zeros((BLKSZ, FFT), dtype=np.complex128)
+    sym = (2.0 * mat_block.astype(np.float64) - 1.0)
+    iq = sym[:, :, 0::2] + 1j * sym[:, :, 1::2]  # [32, 20, 18]
+    for p in range(20):
+        base = LB_START + 19 * p + 1 if p < 10 else (UB_END - 190) + 19 * (p - 10) + 1
+        S[:, base:base + 18] = iq[:, p, :]
+    for b, raw in refs.items():
+        S[:, b] = (2.0 * raw.astype(np.float64) - 1.0) * (1 + 1j)
+    return S
+
+
+def make_fm_mp1(nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz: float = 0.0,
+                noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
+                tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
+                start_bc: int = 0) -> FmCapture:
+    """FM hybrid MP1 (PSMI 1) capture holding `nframes` complete L1 frames
+    followed by `tail_blocks` further blocks so the last frame flushes
+    (the reference has no flush call)."""
+    rng = np.random.default_rng(seed)
+    psmi = 1
+    nblocks = nframes * BLOCKS_PER_FRAME + tail_blocks
+    idx_i = interleaver_i_index()
+    idx_ii = interleaver_ii_index()
+    pn_p1 = pn_sequence(P1_BITS)
+    pn_pids = pn_sequence(PIDS_BITS)
+    cap = FmCapture(cu8=None, psmi=psmi, lead_in=lead_in)
+
+    nfr_total = (nblocks + start_bc + BLOCKS_PER_FRAME - 1) // BLOCKS_PER_FRAME
+    mats = []
+    for f in range(nfr_total):
+        bits = build_p1_frame_bits(rng, pci=pci, valid_header=valid_header)
+        coded = conv_encode_tb(bits ^ pn_p1).reshape(-1)          # 438528
+        keep = np.ones(coded.size, dtype=bool)
+        keep[5::6] = False
+        mat = np.zeros(16 * PM_BLOCK, dtype=np.uint8)
+        mat[idx_i] = coded[keep]
+        pids_this = []
+        for bc in range(16):
+            pb = rng.integers(0, 2, PIDS_BITS, dtype=np.uint8)
+            pc = conv_encode_tb(pb ^ pn_pids).reshape(-1)         # 240
+            k2 = np.ones(pc.size, dtype=bool)
+            k2[5::6] = False
+            mat[idx_ii[bc]] = pc[k2]
+            pids_this.append(pb)
+        mats.append((bits, pids_this, mat.reshape(16, 32, 20, 36)))
+
+    sh = _shape2x()
+    sig = np.zeros(nblocks * BLKSZ * 2 * FFTCP, dtype=np.complex128)
+    first_full = None
+    for blk in range(nblocks):
+        g = blk + start_bc
+        f, bc = divmod(g, 16)
+        bits, pids_this, mat = mats[f]
+        refs = {}
+        for i in range(11):
+            raw = ref_raw_bits(bc, psmi, (30 - i) & 3)
+            refs[LB_START + 19 * i] = raw
+            refs[UB_END - 19 * i] = raw
+        S = _block_matrix_to_bins(mat[bc], refs)
+        # receiver computes fftshift(FFT(conj(x)));  build y = conj(x) at 2x rate
+        S2 = np.zeros((BLKSZ, 2 * FFT), dtype=np.complex128)
+        fidx = (np.arange(FFT) - FFT // 2) % (2 * FFT)
+        S2[:, fidx] = S
+        y = np.fft.ifft(S2, axis=1) * (2 * FFT)
+        ysym = y[:, np.arange(2 * FFTCP) % (2 * FFT)] * sh[None, :]
+        sig[blk * BLKSZ * 2 * FFTCP:(blk + 1) * BLKSZ * 2 * FFTCP] = np.conj(ysym).reshape(-1)
+    # bookkeeping of what a receiver will output
+    for f in range(nfr_total):
+        g0 = f * 16 - start_bc
+        if g0 >= 0 and g0 + 16 <= nblocks:
+            cap.p1_frames.append(mats[f][0])
+    for blk in range(nblocks):
+        f, bc = divmod(blk + start_bc, 16)
+        cap.pids_frames.append(mats[f][1][bc])
+
+    sig *= rms_lsb / np.sqrt(np.mean(np.abs(sig) ** 2) / 2.0)
+    nlead = lead_in
+    full = np.concatenate([np.zeros(nlead, dtype=np.complex128), sig])
+    if cfo_hz != 0.0:
+        t = np.arange(full.size)
+        full *= np.exp(2j * np.pi * cfo_hz * t / 1488375.0)
+    nrng = np.random.default_rng(noise_seed)
+    sigma = noise_lsb if noise_lsb > 0 else 0.0
+    # the lead-in always carries a little noise so it is not a constant run
+    lead_sigma = max(sigma, 1.0)
+    noise = np.empty(full.size, dtype=np.complex128)
+    noise.real = nrng.standard_normal(full.size)
+    noise.imag = nrng.standard_normal(full.size)
+    scale = np.full(full.size, sigma)
+    scale[:nlead] = lead_sigma
+    full += noise * scale
+    iq = np.empty(2 * full.size, dtype=np.float64)
+    iq[0::2] = full.real
+    iq[1::2] = full.imag
+    cap.cu8 = np.clip(np.rint(iq + 127.0), 0, 255).astype(np.uint8)
+    return cap
+
+
+def pack_bits(bits: np.ndarray) -> bytes:
+    """MSB-first packing, the format of the engine's and reftap's PDU records."""
+    return np.packbits(np.asarray(bits, dtype=np.uint8)).tobytes()

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libnrsc5_ref.so")
 
-REC_FRAME, REC_PIDS, REC_SYNC, REC_LOST_SYNC, REC_MER, REC_BER, REC_HDC, REC_SOFT_PM = range(1, 9)
+REC_FRAME, REC_PIDS, REC_SYNC, REC_LOST_SYNC, REC_MER, REC_BER, REC_HDC, REC_SOFT_PM, REC_BLOCK = range(1, 10)
 MODE_FM, MODE_AM = 0, 1
 
 _lib = None
@@ -85,6 +85,9 @@ def _parse(raw: bytes) -> RefLog:
         elif ty == REC_SOFT_PM:
             bc = struct.unpack_from("<I", pay, 0)[0]
             rec = {"bc": bc, "soft": np.frombuffer(pay[4:], dtype=np.int8).copy()}
+        elif ty == REC_BLOCK:
+            st, se, ang, pr, pi, cfo, start = struct.unpack("<iifffiq", pay[:32])
+            rec = {"state": st, "samperr": se, "angle": ang, "phase": complex(pr, pi), "cfo": cfo, "start": start}
         else:
             raise ValueError(f"bad record type {ty}")
         out.records.append((ty, rec))

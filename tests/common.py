@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import json
+import lzma
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SAMPLE_CANDIDATES = [
+    os.path.join(ROOT, "oracle", "_ref", "sample.xz"),   # copied there by build(); travels to the GPU box
+    "/root/reference/support/sample.xz",
+]
+
+
+def fnv1a32(b: bytes) -> int:
+    h = 0x811C9DC5
+    for x in b:
+        h = ((h ^ x) * 0x01000193) & 0xFFFFFFFF
+    return h
+
+
+def load_sample():
+    for p in SAMPLE_CANDIDATES:
+        if os.path.exists(p):
+            return np.frombuffer(lzma.open(p).read(), dtype=np.uint8)
+    return None
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+# the synthetic parity matrix: name -> generator kwargs
+SYNTH_CASES = {
+    "mp1_clean": dict(nframes=2, seed=1234, lead_in=1777),
+    "mp1_cfo120": dict(nframes=2, seed=77, lead_in=333, cfo_hz=120.0),
+    "mp1_cfo-300_awgn12": dict(nframes=2, seed=77, lead_in=333, cfo_hz=-300.0, noise_lsb=12.0),
+    "mp1_cfo2000_awgn20": dict(nframes=2, seed=77, lead_in=333, cfo_hz=2000.0, noise_lsb=20.0),
+    "mp1_badhdr": dict(nframes=2, seed=9, lead_in=40, valid_header=False),
+}
+
+
+def summarize(log):
+    """Digest a RefLog into a JSON-able summary (order-preserving)."""
+    import reftap
+    seq = []
+    for ty, p in log.records:
+        if ty == reftap.REC_FRAME:
+            seq.append(["F", p["lc"], p["nbits"], fnv1a32(p["bits"])])
+        elif ty == reftap.REC_PIDS:
+            seq.append(["P", fnv1a32(p["bits"])])
+        elif ty == reftap.REC_SYNC:
+            seq.append(["S", round(p["freq_offset"], 3), p["psmi"]])
+        elif ty == reftap.REC_LOST_SYNC:
+            seq.append(["L"])
+        elif ty == reftap.REC_MER:
+            seq.append(["M", round(p["lower"], 4), round(p["upper"], 4)])
+        elif ty == reftap.REC_BER:
+            seq.append(["B", round(p["cber"], 7)])
+    return seq

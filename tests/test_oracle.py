@@ -1,0 +1,160 @@
+"""CPU tests pinning the oracle (the plain-C restatement in oracle/nrsc5_oracle.c)
+against (1) the committed golden vectors produced by the unmodified reference
+and (2) the reference itself (oracle/_ref/libnrsc5_ref.so) when it is present.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import common
+import port
+import reftap
+from nrsc5_b200 import synth
+
+pytestmark = pytest.mark.skipif(not port.available(), reason="oracle/_ref/liboracle.so not built (run __graft_entry__.build())")
+
+
+def _soft_fnv(log):
+    return common.fnv1a32(b"".join(p["soft"].tobytes() for p in log.of(reftap.REC_SOFT_PM)))
+
+
+@pytest.mark.parametrize("name", list(common.SYNTH_CASES))
+def test_port_matches_golden_synth(name):
+    g = common.golden("synth_fm.json")[name]
+    cap = synth.make_fm_mp1(**common.SYNTH_CASES[name])
+    if common.fnv1a32(cap.cu8[:1 << 20].tobytes()) != g["input_fnv"]:
+        pytest.skip("numpy generator stream differs from the one the golden file was made with")
+    log = port.decode(cap.cu8, want_soft=True)
+    assert common.summarize(log) == g["events"]
+    assert len(log.of(reftap.REC_SOFT_PM)) == g["soft_blocks"]
+    assert _soft_fnv(log) == g["soft_fnv"]          # soft bits bit-identical to the reference
+    # the receiver returns what the generator put in (sizes-independent round trip)
+    got = [common.fnv1a32(b) for b in log.p1_frames]
+    assert set(g["generated_p1_fnv"]) & set(got), "no generated frame was recovered"
+
+
+def test_port_matches_golden_sample():
+    raw = common.load_sample()
+    if raw is None:
+        pytest.skip("sample.xz not available")
+    g = common.golden("sample_xz.json")
+    assert common.fnv1a32(raw[:1 << 20].tobytes()) == g["input_fnv"]
+    log = port.decode(raw, want_soft=True)
+    assert common.summarize(log) == g["events"]
+    assert _soft_fnv(log) == g["soft_fnv"]
+    kinds = [e[0] for e in g["events"]]
+    # SURVEY §8c known answers
+    assert kinds.count("S") == 2 and kinds.count("L") == 1 and kinds.count("M") == 10
+    assert kinds.count("B") == 9 and kinds.count("F") == 9 and kinds.count("P") == 172
+
+
+def test_port_chunking_invariance():
+    cap = synth.make_fm_mp1(nframes=1, seed=3, lead_in=10)
+    a = port.decode(cap.cu8)
+    b = port.decode(cap.cu8, chunk=32768)
+    c = port.decode(cap.cu8, chunk=4 * 977)
+    assert common.summarize(a) == common.summarize(b) == common.summarize(c)
+
+
+@pytest.mark.skipif(not reftap.available(), reason="reference oracle not built")
+class TestAgainstReference:
+    def test_full_chain_noisy(self):
+        cap = synth.make_fm_mp1(nframes=1, seed=21, lead_in=123, cfo_hz=-150.0, noise_lsb=10.0)
+        a = reftap.decode(cap.cu8, want_soft=True)
+        b = port.decode(cap.cu8, want_soft=True)
+        ra = [r for r in a.records if r[0] != reftap.REC_HDC]
+        assert len(ra) == len(b.records)
+        for x, y in zip(ra, b.records):
+            assert x[0] == y[0]
+            if x[0] == reftap.REC_SOFT_PM:
+                assert x[1]["bc"] == y[1]["bc"] and np.array_equal(x[1]["soft"], y[1]["soft"])
+            else:
+                assert x[1] == y[1]
+
+    def test_viterbi_k7_k9(self):
+        L = reftap.lib()
+        rng = np.random.default_rng(1)
+        for n in (80, 2304, 4608):
+            soft = rng.integers(-127, 128, 3 * n, dtype=np.int8)
+            out = np.empty(n, dtype=np.uint8)
+            L.nrsc5_conv_decode_p3_p4(soft.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), n)
+            assert np.array_equal(out, port.viterbi(soft))
+        soft = rng.integers(-1, 2, 3 * 3750, dtype=np.int8)
+        out = np.empty(3750, dtype=np.uint8)
+        L.nrsc5_conv_decode_e1(soft.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), 3750)
+        assert np.array_equal(out, port.viterbi(soft, k=9, gens=(0o561, 0o657, 0o711)))
+        L.nrsc5_conv_decode_e2_e3(soft.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), 3750)
+        assert np.array_equal(out, port.viterbi(soft, k=9, gens=(0o561, 0o753, 0o711)))
+
+    def test_viterbi_saturation(self):
+        # full-scale, perfectly consistent, unpunctured input drives the int16
+        # path metrics into saturation between normalisations
+        L = reftap.lib()
+        rng = np.random.default_rng(5)
+        u = rng.integers(0, 2, 4608, dtype=np.uint8)
+        c = synth.conv_encode_tb(u).reshape(-1).astype(np.int16)
+        s = ((2 * c - 1) * 127).astype(np.int8)
+        out = np.empty(4608, dtype=np.uint8)
+        L.nrsc5_conv_decode_p3_p4(s.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), 4608)
+        assert np.array_equal(out, port.viterbi(s)) and np.array_equal(out, u)
+
+    def test_halfband(self):
+        L = reftap.lib()
+        L.firdecim_q15_create.restype = ctypes.c_void_p
+        L.halfband_q15_execute.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        taps = (ctypes.c_float * 4)(0.6062333583831787, -0.13481467962265015, 0.032919470220804214, -0.00410953676328063)
+        q = L.firdecim_q15_create(taps, 4)
+        rng = np.random.default_rng(2)
+        cu8 = rng.integers(0, 256, 4 * 5000, dtype=np.uint8)
+        cu8[:400] = 255                      # extremes
+        cu8[400:800] = 0
+        x = ((cu8.astype(np.int16) - 127) * 64).astype(np.int16)
+        out = np.empty(2 * 5000, dtype=np.int16)
+        for n in range(5000):
+            L.halfband_q15_execute(q, x[4 * n:].ctypes.data_as(ctypes.c_void_p),
+                                   out[2 * n:].ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(out, port.halfband_fm(cu8))
+
+    def test_rs_decode(self):
+        L = reftap.lib()
+        L.init_rs_char.restype = ctypes.c_void_p
+        L.decode_rs_char.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        rs = L.init_rs_char(8, 0x11D, 1, 1, 8)
+        rng = np.random.default_rng(7)
+        for t in range(1500):
+            hdr = np.frombuffer(synth.audio_pdu_header(rng=rng), dtype=np.uint8)
+            blk = np.zeros(255, dtype=np.uint8)
+            blk[254 - np.arange(96)] = hdr
+            for p in rng.choice(255 if t % 3 == 0 else 96, t % 8, replace=False):
+                blk[p if t % 3 == 0 else 254 - p] ^= rng.integers(1, 256)
+            if t % 50 == 49:
+                blk = rng.integers(0, 256, 255, dtype=np.uint8)
+            ref = blk.copy()
+            rc_ref = L.decode_rs_char(rs, ref.ctypes.data_as(ctypes.c_void_p), None, 0)
+            rc, got = port.rs_decode(blk)
+            assert rc == rc_ref and np.array_equal(ref, got)
+
+
+def test_rs_roundtrip_without_reference():
+    rng = np.random.default_rng(11)
+    for ne in range(0, 6):
+        hdr = np.frombuffer(synth.audio_pdu_header(rng=rng), dtype=np.uint8).copy()
+        bad = hdr.copy()
+        for p in rng.choice(96, ne, replace=False):
+            bad[p] ^= rng.integers(1, 256)
+        ok, fixed = port.fix_header(bad)
+        if ne <= 4:
+            assert ok == 1 and np.array_equal(fixed, hdr)
+        else:
+            assert ok == 0 or not np.array_equal(fixed, hdr)
+
+
+def test_p1_sync_lost_predicate():
+    rng = np.random.default_rng(4)
+    good = synth.build_p1_frame_bits(rng, pci=synth.PCI_AUDIO, valid_header=True)
+    assert port.p1_sync_lost(good) == (False, synth.PCI_AUDIO)
+    bad = synth.build_p1_frame_bits(rng, pci=synth.PCI_AUDIO, valid_header=False)
+    assert port.p1_sync_lost(bad) == (True, synth.PCI_AUDIO)
+    fixed = synth.build_p1_frame_bits(rng, pci=synth.PCI_FIXED, valid_header=False)
+    assert port.p1_sync_lost(fixed) == (False, synth.PCI_FIXED)
