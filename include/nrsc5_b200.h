@@ -1,0 +1,138 @@
+/* nrsc5_b200 — C ABI of the B200-native NRSC-5 FM physical-layer receive
+ * engine (libnrsc5_b200.so).  Plain pointers and sizes only.
+ *
+ * What each entry point replaces in the reference (theori-io/nrsc5 @ a5c0972):
+ *
+ *   nrsc5b_create / nrsc5b_destroy / nrsc5b_reset
+ *       input_init / input_free / input_reset      reference src/input.h:37-40,
+ *                                                   src/input.c:126-170
+ *   nrsc5b_push_cu8 (+ nrsc5b_push_cu8_device)
+ *       input_push_cu8(input_t*, const uint8_t*, uint32_t)
+ *                                                   reference src/input.h:42, src/input.c:96-117
+ *       The reference handles one stream per call; the engine takes a stream
+ *       index so that many independent channels share one GPU (BASELINE
+ *       configs 3-5).  `nbytes` counts uint8 values, as in the reference.
+ *   nrsc5b_process
+ *       the synchronous work input_push() triggers: acquire_process ->
+ *       sync_push -> decode_push_pm -> nrsc5_conv_decode_* -> descramble
+ *                                                   reference src/input.c:41-50,
+ *                                                   src/acquire.c:98-263, src/sync.c:339-610,
+ *                                                   src/decode.c:378-471, src/conv_dec.c:429-463
+ *   nrsc5b_drain
+ *       the downstream calls of the path, as records in call order:
+ *         REC_FRAME      frame_push(frame_t*, bits, len, lc)   reference src/frame.h:53
+ *         REC_PIDS       pids_frame_push(pids_t*, bits)        reference src/pids.h:98
+ *         REC_SYNC       nrsc5_report_sync                     reference src/private.h:51
+ *         REC_LOST_SYNC  nrsc5_report_lost_sync                reference src/private.h:52
+ *         REC_MER        nrsc5_report_mer                      reference src/private.h:53
+ *         REC_BER        nrsc5_report_ber                      reference src/private.h:54
+ *         REC_BLOCK      output_advance (one per 32-symbol block, before that
+ *                        block's PDUs)                          reference src/acquire.c:108
+ *   nrsc5b_set_sync_state
+ *       input_set_sync_state(input_t*, SYNC_STATE_NONE) — the L2->L3 feedback
+ *                                                   reference src/input.h:41, src/frame.c:538-539
+ *       The engine evaluates the same predicate on the GPU (RS(255,247) header
+ *       check, reference src/frame.c:158-179 + src/rs_decode.c) so batch use
+ *       needs no host round trip; a host L2 may still force the state.
+ *   nrsc5b_rs_decode
+ *       decode_rs_char(rs, data, NULL, 0) for the (255,247) code set up at
+ *                                                   reference src/frame.c:747, src/rs_decode.c:16
+ *
+ * Record stream format (identical to the test oracle's): u32 type, u32
+ * payload_len, payload padded to 4 bytes.  Frame bits are packed MSB-first.
+ *
+ * All functions return 0 on success, a negative NRSC5B_E* code otherwise.
+ * The engine never falls back to a CPU path: without a CUDA device
+ * nrsc5b_create() fails with NRSC5B_ENODEV.
+ */
+#ifndef NRSC5_B200_H
+#define NRSC5_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRSC5B_MODE_FM 0
+
+enum {
+    NRSC5B_OK = 0,
+    NRSC5B_ENODEV = -1,   /* no CUDA device / CUDA error at creation */
+    NRSC5B_EINVAL = -2,
+    NRSC5B_ENOMEM = -3,
+    NRSC5B_ECUDA = -4,
+    NRSC5B_EFULL = -5,    /* input buffer of that stream cannot take the push */
+};
+
+enum {
+    NRSC5B_REC_FRAME = 1,     /* u32 lc, u32 nbits, packed bits            */
+    NRSC5B_REC_PIDS = 2,      /* 10 bytes                                  */
+    NRSC5B_REC_SYNC = 3,      /* f32 freq_offset, i32 psmi                 */
+    NRSC5B_REC_LOST_SYNC = 4,
+    NRSC5B_REC_MER = 5,       /* f32 lower, f32 upper                      */
+    NRSC5B_REC_BER = 6,       /* f32 cber                                  */
+    NRSC5B_REC_SOFT_PM = 8,   /* u32 bc, 23040 int8 (only when enabled)    */
+    NRSC5B_REC_BLOCK = 9,     /* i32 state_in, i32 samperr, f32 angle, f32 ph_re, f32 ph_im, i32 cfo, i64 start */
+};
+
+typedef struct nrsc5b_engine nrsc5b_engine_t;
+
+typedef struct {
+    int device;                 /* CUDA device ordinal                                  */
+    int nstreams;               /* independent channels on this GPU                     */
+    int mode;                   /* NRSC5B_MODE_FM                                       */
+    size_t input_capacity;      /* bytes of cu8 each stream can hold on the device      */
+    size_t log_capacity;        /* bytes of output records per stream between drains    */
+    int emit_soft;              /* also emit REC_SOFT_PM (debug / parity taps)          */
+} nrsc5b_config_t;
+
+int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg);
+void nrsc5b_destroy(nrsc5b_engine_t *e);
+int nrsc5b_reset(nrsc5b_engine_t *e, int stream);          /* stream < 0: all */
+
+/* Use this CUDA stream (a cudaStream_t cast to void*) for all engine work; NULL = legacy default. */
+int nrsc5b_set_cuda_stream(nrsc5b_engine_t *e, void *cuda_stream);
+
+/* Append cu8 I/Q (host memory; staged through pinned memory, asynchronous H2D). nbytes % 4 == 0. */
+int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
+/* Append cu8 I/Q that already lives in device memory (device-to-device copy). */
+int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void *dev_buf, size_t nbytes);
+/* Point every stream at an existing device buffer [nstreams][stride] holding nbytes valid bytes each (no copy). */
+int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_buf, size_t stride, size_t nbytes);
+
+/* Run every 32-symbol block for which all streams' buffered samples suffice. Asynchronous. */
+int nrsc5b_process(nrsc5b_engine_t *e);
+/* Wait for the GPU and copy the records of `stream` produced since the last drain.
+ * Returns the number of bytes written (>= 0) or a negative error; *needed gets the full size. */
+long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_t cap, size_t *needed);
+/* Wait for the GPU without draining. */
+int nrsc5b_synchronize(nrsc5b_engine_t *e);
+
+int nrsc5b_set_sync_state(nrsc5b_engine_t *e, int stream, int state);   /* 0 none, 1 coarse, 2 fine */
+
+typedef struct {
+    uint64_t blocks;          /* 32-symbol blocks processed (all streams)       */
+    uint64_t samples;         /* cu8 complex samples consumed (all streams)     */
+    uint64_t p1_frames;       /* P1 frames decoded                              */
+    uint64_t kernel_launches; /* kernels launched by the engine                 */
+} nrsc5b_stats_t;
+int nrsc5b_get_stats(nrsc5b_engine_t *e, nrsc5b_stats_t *st);
+
+/* ---- single-stage entry points (kernel-level parity tests, host buffers) ---- */
+/* cu8 -> Q15 -> halfband /2 from zero history: out[2*npairs] int16 (reference src/firdecim_q15.c:137-165) */
+int nrsc5b_halfband_fm(int device, const uint8_t *cu8, size_t npairs, int16_t *out_ri);
+/* batch of tail-biting K=7 rate-1/3 Viterbi decodes: in[nframes][3*len] int8 -> out[nframes][len] bits (one per byte) */
+int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int len, int nframes);
+/* batch RS(255,247) decode in place; rc[n] = corrections or -1 (reference src/rs_decode.c:16) */
+int nrsc5b_rs_decode(int device, uint8_t *blocks255, int *rc, int nblocks);
+/* 2048-point forward complex FFT of nffts rows (float2 interleaved), natural order, for numerics tests */
+int nrsc5b_fft2048(int device, const float *in, float *out, int nffts);
+
+const char *nrsc5b_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRSC5_B200_H */

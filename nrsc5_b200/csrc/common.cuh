@@ -1,0 +1,163 @@
+// Shared definitions for the nrsc5_b200 CUDA engine (sm_100a).
+//
+// Vocabulary follows the reference domain: a *stream* is one independent
+// radio channel (one nrsc5_t in the reference); a *block* is 32 OFDM symbols
+// (reference src/defines.h:20); an L1 *frame* is 16 blocks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nb {
+
+constexpr int NFFT = 2048;
+constexpr int NCP = 112;
+constexpr int NSYM = NFFT + NCP;            // 2160 decimated samples per OFDM symbol
+constexpr int BLK = 32;                     // symbols per block
+constexpr int NACQ = NSYM * (BLK + 1);      // 71280: acquisition window (reference src/acquire.h:12)
+constexpr int LB0 = NFFT / 2 - 546;         // 478
+constexpr int UB1 = NFFT / 2 + 546;         // 1570
+constexpr int PW = 19;
+constexpr int MAXPART = 14;
+constexpr int SIDE = MAXPART * PW + 1;      // 267 bins kept per sideband (reference src/sync.c:785-789)
+constexpr int NBINS = 2 * SIDE;             // 534
+constexpr int PM_BLOCK = 23040;
+constexpr int P1_LEN = 146176;
+constexpr int P1_ENC = P1_LEN * 5 / 2;      // 365440
+constexpr int P1_VIT = P1_LEN * 3;          // 438528
+constexpr int P1_STEPS = P1_LEN + 64;       // tail-biting: 32 pre-roll + 32 post-roll
+constexpr int PIDS_LEN = 80;
+constexpr int ST_NONE = 0, ST_COARSE = 1, ST_FINE = 2;
+
+// record types (include/nrsc5_b200.h)
+constexpr uint32_t REC_FRAME = 1, REC_PIDS = 2, REC_SYNC = 3, REC_LOST_SYNC = 4, REC_MER = 5,
+                   REC_BER = 6, REC_SOFT_PM = 8, REC_BLOCK = 9;
+
+// bin index inside the compact 534-bin spectrum kept per symbol
+__host__ __device__ inline int compact_of_bin(int b)   // b in fftshift-ed coordinates
+{
+    if (b >= LB0 && b < LB0 + SIDE) return b - LB0;
+    if (b > UB1 - SIDE && b <= UB1) return SIDE + (b - (UB1 - SIDE + 1));
+    return -1;
+}
+
+// Per-stream persistent state.  One instance per stream in device memory.
+struct StreamState {
+    // input cursor
+    long long in_avail;        // cu8 complex samples available from absolute index 0
+    long long start;           // decimated index of the acquisition window's first sample
+    // acquisition (reference src/acquire.h:24-28)
+    float prev_angle;
+    float2 phase;
+    int keep_extra;
+    int cfo;
+    int state;
+    // feedback from sync (reference src/sync.h:21-22)
+    int samperr;
+    float angle;
+    // sync (reference src/sync.h:13-31)
+    int psmi, cfo_wait, bc, mer_cnt;
+    float err_lb, err_ub;
+    // decode
+    int started_pm;
+    // per-block hand-off prep -> demod -> sync
+    int active;                // this step has a full window for the stream
+    int blk_samperr;
+    int blk_state_in;
+    float theta;               // NCO step, radians per decimated sample
+    float2 phase0;             // NCO phase at the first sample of the block
+    // P1 hand-off sync -> p1 kernel
+    int p1_ready;
+    int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
+    // output log cursor
+    unsigned log_len;
+    unsigned log_overflow;
+    unsigned long long blocks_done;
+    unsigned long long frames_done;
+    // history of the coarse band-pass FIR: the last 31 samples it was fed
+    short bp_hist[31][2];
+    short pad_[2];
+};
+
+struct EngineDims {
+    int nstreams;
+    size_t in_stride;          // bytes between streams in the cu8 buffer
+    size_t log_cap;            // bytes of log per stream
+    int emit_soft;
+};
+
+// Pointers to all device arrays, passed by value to kernels.
+struct DevPtrs {
+    const uint8_t *iq;         // [S][in_stride] cu8
+    StreamState *st;           // [S]
+    float *cfreq;              // [S][2048]
+    float *cphase;             // [S][2048]
+    float2 *nco;               // [S][2160]  window * exp(j*theta*j)
+    float2 *bins;              // [S][32][534]
+    int8_t *pm;                // [S][16][23040]
+    short2 *ydec;              // [S][71280]   decimated window (coarse acquisition scratch)
+    float2 *tbuf;              // [S][71280]   band-passed window (coarse acquisition scratch)
+    int8_t *vit_in;            // [S][438528]
+    uint2 *vit_dec;            // [S][146240]
+    uint8_t *p1_bits;          // [S][146176]  decoded bits, one per byte
+    uint8_t *log;              // [S][log_cap]
+    const float *shape;        // [2160]
+    const float2 *twid;        // [2048]  exp(-2*pi*i*k/2048)
+    const uint32_t *p1_lut;    // [365440] interleaver I gather index
+    const uint8_t *pn;         // [146176] descrambler sequence
+};
+
+// ---- log writer: one CTA owns a stream's log at any time ----
+__device__ inline uint8_t *log_reserve(const DevPtrs &p, const EngineDims &d, int s, uint32_t type, uint32_t plen)
+{
+    StreamState &st = p.st[s];
+    uint32_t need = 8 + ((plen + 3) & ~3u);
+    if ((size_t)st.log_len + need > d.log_cap) {
+        st.log_overflow = 1;
+        return nullptr;
+    }
+    uint8_t *w = p.log + (size_t)s * d.log_cap + st.log_len;
+    reinterpret_cast<uint32_t *>(w)[0] = type;
+    reinterpret_cast<uint32_t *>(w)[1] = plen;
+    st.log_len += need;
+    return w + 8;
+}
+
+// cu8 byte of absolute input sample n (component c); before the stream start
+// the decimator window holds zeros, i.e. byte 127 (reference src/firdecim_q15.c:33)
+__device__ __forceinline__ int q15_of_u8(int v) { return (v - 127) * 64; }
+
+// halfband decimator output y[d] for one stream (reference src/firdecim_q15.c:137-151,
+// taps int16{-134,1078,-4417,19864}): exact integer arithmetic.
+__device__ __forceinline__ short2 halfband_at(const uint8_t *iq, long long d)
+{
+    // y[d] = x[2d-7] + sum_k ((x[2d-14+2k] + x[2d-2k]) * tap_k) >> 15
+    const int tap[4] = { -134, 1078, -4417, 19864 };
+    long long n0 = 2 * d - 14;
+    int accr = 0, acci = 0;
+    if (n0 >= 0) {
+        const uint8_t *b = iq + 2 * n0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int ar = q15_of_u8(b[4 * k]) + q15_of_u8(b[2 * (14 - 2 * k)]);
+            int ai = q15_of_u8(b[4 * k + 1]) + q15_of_u8(b[2 * (14 - 2 * k) + 1]);
+            accr = (short)(accr + ((ar * tap[k]) >> 15));
+            acci = (short)(acci + ((ai * tap[k]) >> 15));
+        }
+        accr = (short)(accr + q15_of_u8(b[14]));
+        acci = (short)(acci + q15_of_u8(b[15]));
+    } else {
+        auto rd = [&](long long n, int c) -> int { return n < 0 ? 0 : q15_of_u8(iq[2 * n + c]); };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int ar = rd(n0 + 2 * k, 0) + rd(n0 + 14 - 2 * k, 0);
+            int ai = rd(n0 + 2 * k, 1) + rd(n0 + 14 - 2 * k, 1);
+            accr = (short)(accr + ((ar * tap[k]) >> 15));
+            acci = (short)(acci + ((ai * tap[k]) >> 15));
+        }
+        accr = (short)(accr + rd(n0 + 7, 0));
+        acci = (short)(acci + rd(n0 + 7, 1));
+    }
+    return make_short2((short)accr, (short)acci);
+}
+
+}  // namespace nb

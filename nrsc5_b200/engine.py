@@ -1,0 +1,224 @@
+"""ctypes binding of libnrsc5_b200.so (include/nrsc5_b200.h).
+
+Mirrors the reference's own Python binding style (reference support/nrsc5.py:
+a ctypes CDLL with thin methods); there is deliberately no CPU fallback: if
+the CUDA library is missing or no GPU is present, constructing an Engine raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+REC_FRAME, REC_PIDS, REC_SYNC, REC_LOST_SYNC, REC_MER, REC_BER = 1, 2, 3, 4, 5, 6
+REC_SOFT_PM, REC_BLOCK = 8, 9
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("nstreams", ctypes.c_int), ("mode", ctypes.c_int),
+                ("input_capacity", ctypes.c_size_t), ("log_capacity", ctypes.c_size_t),
+                ("emit_soft", ctypes.c_int)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("blocks", ctypes.c_uint64), ("samples", ctypes.c_uint64),
+                ("p1_frames", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libnrsc5_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libnrsc5_b200.so; raises EngineError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise EngineError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = ctypes.CDLL(p)
+    vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    L.nrsc5b_version.restype = ctypes.c_char_p
+    L.nrsc5b_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_Config)]
+    L.nrsc5b_destroy.argtypes = [vp]
+    L.nrsc5b_destroy.restype = None
+    L.nrsc5b_reset.argtypes = [vp, ci]
+    L.nrsc5b_set_cuda_stream.argtypes = [vp, vp]
+    L.nrsc5b_push_cu8.argtypes = [vp, ci, vp, sz]
+    L.nrsc5b_push_cu8_device.argtypes = [vp, ci, vp, sz]
+    L.nrsc5b_attach_device_input.argtypes = [vp, vp, sz, sz]
+    L.nrsc5b_process.argtypes = [vp]
+    L.nrsc5b_synchronize.argtypes = [vp]
+    L.nrsc5b_drain.argtypes = [vp, ci, vp, sz, ctypes.POINTER(sz)]
+    L.nrsc5b_drain.restype = ctypes.c_long
+    L.nrsc5b_set_sync_state.argtypes = [vp, ci, ci]
+    L.nrsc5b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.nrsc5b_halfband_fm.argtypes = [ci, vp, sz, vp]
+    L.nrsc5b_viterbi_k7.argtypes = [ci, vp, vp, ci, ci]
+    L.nrsc5b_rs_decode.argtypes = [ci, vp, vp, ci]
+    L.nrsc5b_fft2048.argtypes = [ci, vp, vp, ci]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc < 0:
+        names = {-1: "ENODEV (no CUDA device; no CPU path exists)", -2: "EINVAL", -3: "ENOMEM", -4: "ECUDA", -5: "EFULL"}
+        raise EngineError(f"{what} failed: {names.get(rc, rc)}")
+    return rc
+
+
+def parse_records(raw: bytes):
+    """Decode the engine's record stream into (type, dict) tuples."""
+    out = []
+    off, n = 0, len(raw)
+    while off < n:
+        ty, plen = struct.unpack_from("<II", raw, off)
+        pay = raw[off + 8: off + 8 + plen]
+        off += 8 + ((plen + 3) & ~3)
+        if ty == REC_FRAME:
+            lc, nbits = struct.unpack_from("<II", pay, 0)
+            rec = {"lc": lc, "nbits": nbits, "bits": bytes(pay[8:])}
+        elif ty == REC_PIDS:
+            rec = {"bits": bytes(pay[:10])}
+        elif ty == REC_SYNC:
+            f, psmi = struct.unpack("<fi", pay)
+            rec = {"freq_offset": f, "psmi": psmi}
+        elif ty == REC_LOST_SYNC:
+            rec = {}
+        elif ty == REC_MER:
+            lo, up = struct.unpack("<ff", pay)
+            rec = {"lower": lo, "upper": up}
+        elif ty == REC_BER:
+            rec = {"cber": struct.unpack("<f", pay)[0]}
+        elif ty == REC_SOFT_PM:
+            rec = {"bc": struct.unpack_from("<I", pay, 0)[0], "soft": np.frombuffer(pay[4:], dtype=np.int8).copy()}
+        elif ty == REC_BLOCK:
+            st, se, ang, pr, pi, cfo, start = struct.unpack("<iifffiq", pay[:32])
+            rec = {"state": st, "samperr": se, "angle": ang, "phase": complex(pr, pi), "cfo": cfo, "start": start}
+        else:
+            raise EngineError(f"corrupt record stream (type {ty} at {off})")
+        out.append((ty, rec))
+    return out
+
+
+class Engine:
+    """Many independent FM channels decoded on one GPU.
+
+    push_cu8()/process()/drain() mirror input_push_cu8() and the downstream
+    frame_push / pids_frame_push / nrsc5_report_* calls of the reference
+    (see include/nrsc5_b200.h for the file:line map).
+    """
+
+    def __init__(self, nstreams: int, input_capacity: int, device: int = 0, log_capacity: int = 1 << 20,
+                 emit_soft: bool = False):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        cfg = _Config(device, nstreams, 0, input_capacity, log_capacity, int(emit_soft))
+        _check(self._L.nrsc5b_create(ctypes.byref(self._h), ctypes.byref(cfg)), "nrsc5b_create")
+        self.nstreams = nstreams
+        self._log_cap = log_capacity + 64
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._L.nrsc5b_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_cuda_stream(self, stream_ptr: int):
+        _check(self._L.nrsc5b_set_cuda_stream(self._h, ctypes.c_void_p(stream_ptr)), "set_cuda_stream")
+
+    def reset(self, stream: int = -1):
+        _check(self._L.nrsc5b_reset(self._h, stream), "nrsc5b_reset")
+
+    def push_cu8(self, stream: int, samples):
+        """samples: uint8 numpy array / bytes (host) — length counts uint8 values, multiple of 4."""
+        a = np.ascontiguousarray(np.frombuffer(samples, dtype=np.uint8) if isinstance(samples, (bytes, bytearray)) else samples,
+                                 dtype=np.uint8)
+        _check(self._L.nrsc5b_push_cu8(self._h, stream, a.ctypes.data, a.size), "nrsc5b_push_cu8")
+
+    def push_cu8_device(self, stream: int, dev_ptr: int, nbytes: int):
+        _check(self._L.nrsc5b_push_cu8_device(self._h, stream, ctypes.c_void_p(dev_ptr), nbytes), "nrsc5b_push_cu8_device")
+
+    def attach_device_input(self, dev_ptr: int, stride: int, nbytes: int):
+        _check(self._L.nrsc5b_attach_device_input(self._h, ctypes.c_void_p(dev_ptr), stride, nbytes), "attach_device_input")
+
+    def process(self):
+        _check(self._L.nrsc5b_process(self._h), "nrsc5b_process")
+
+    def synchronize(self):
+        _check(self._L.nrsc5b_synchronize(self._h), "nrsc5b_synchronize")
+
+    def drain_raw(self, stream: int) -> bytes:
+        need = ctypes.c_size_t(0)
+        buf = ctypes.create_string_buffer(self._log_cap)
+        n = self._L.nrsc5b_drain(self._h, stream, buf, self._log_cap, ctypes.byref(need))
+        _check(n, "nrsc5b_drain")
+        return buf.raw[:n]
+
+    def drain(self, stream: int):
+        return parse_records(self.drain_raw(stream))
+
+    def set_sync_state(self, stream: int, state: int):
+        _check(self._L.nrsc5b_set_sync_state(self._h, stream, state), "nrsc5b_set_sync_state")
+
+    def stats(self) -> Stats:
+        st = Stats()
+        _check(self._L.nrsc5b_get_stats(self._h, ctypes.byref(st)), "nrsc5b_get_stats")
+        return st
+
+
+# ---- single-stage helpers (parity tests) ----
+def halfband_fm(cu8: np.ndarray, device: int = 0) -> np.ndarray:
+    a = np.ascontiguousarray(cu8, dtype=np.uint8)
+    n = a.size // 4
+    out = np.empty(2 * n, dtype=np.int16)
+    _check(load_library().nrsc5b_halfband_fm(device, a.ctypes.data, n, out.ctypes.data), "nrsc5b_halfband_fm")
+    return out
+
+
+def viterbi_k7(soft: np.ndarray, length: int, device: int = 0) -> np.ndarray:
+    s = np.ascontiguousarray(soft, dtype=np.int8)
+    nframes = s.size // (3 * length)
+    out = np.empty(nframes * length, dtype=np.uint8)
+    _check(load_library().nrsc5b_viterbi_k7(device, s.ctypes.data, out.ctypes.data, length, nframes), "nrsc5b_viterbi_k7")
+    return out.reshape(nframes, length)
+
+
+def rs_decode(blocks: np.ndarray, device: int = 0):
+    b = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 255).copy()
+    rc = np.empty(b.shape[0], dtype=np.int32)
+    _check(load_library().nrsc5b_rs_decode(device, b.ctypes.data, rc.ctypes.data, b.shape[0]), "nrsc5b_rs_decode")
+    return rc, b
+
+
+def fft2048(x: np.ndarray, device: int = 0) -> np.ndarray:
+    a = np.ascontiguousarray(x, dtype=np.complex64).reshape(-1, 2048)
+    out = np.empty_like(a)
+    _check(load_library().nrsc5b_fft2048(device, a.ctypes.data, out.ctypes.data, a.shape[0]), "nrsc5b_fft2048")
+    return out

@@ -1,0 +1,120 @@
+"""GPU parity tests of the whole hot path through the C ABI: cu8 in, L1 PDUs and
+events out, against the CPU oracle and the committed golden vectors."""
+import numpy as np
+import pytest
+
+import common
+import port
+import reftap
+import nrsc5_b200
+from nrsc5_b200 import engine as eng
+from nrsc5_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_engine(cu8_list, chunk=None, emit_soft=False, log_capacity=8 << 20):
+    cap = max(c.size for c in cu8_list) + 4096
+    with nrsc5_b200.Engine(nstreams=len(cu8_list), input_capacity=cap, log_capacity=log_capacity,
+                           emit_soft=emit_soft) as e:
+        if chunk is None:
+            for s, c in enumerate(cu8_list):
+                e.push_cu8(s, c[: c.size & ~3])
+            e.process()
+            return [e.drain(s) for s in range(len(cu8_list))]
+        outs = [[] for _ in cu8_list]
+        n = max(c.size for c in cu8_list)
+        for off in range(0, n, chunk):
+            for s, c in enumerate(cu8_list):
+                piece = c[off: off + chunk]
+                if piece.size:
+                    e.push_cu8(s, piece[: piece.size & ~3])
+            e.process()
+            for s in range(len(cu8_list)):
+                outs[s] += e.drain(s)
+        return outs
+
+
+def pdus(recs):
+    p1 = [r["bits"] for t, r in recs if t == eng.REC_FRAME and r["lc"] == 0]
+    pids = [r["bits"] for t, r in recs if t == eng.REC_PIDS]
+    return p1, pids
+
+
+def kinds(recs):
+    m = {eng.REC_FRAME: "F", eng.REC_PIDS: "P", eng.REC_SYNC: "S", eng.REC_LOST_SYNC: "L", eng.REC_MER: "M", eng.REC_BER: "B"}
+    return [m[t] for t, _ in recs if t in m]
+
+
+def oracle_kinds(log):
+    return [e[0] for e in common.summarize(log)]
+
+
+@pytest.mark.parametrize("name", list(common.SYNTH_CASES))
+def test_synth_pdus_bit_exact(name):
+    cap = synth.make_fm_mp1(**common.SYNTH_CASES[name])
+    ref = port.decode(cap.cu8, want_soft=True)
+    recs = run_engine([cap.cu8], emit_soft=True)[0]
+    p1, pids = pdus(recs)
+    assert p1 == ref.p1_frames                   # L1 P1 PDUs, bit-exact
+    assert pids == ref.pids_frames               # PIDS PDUs, bit-exact
+    assert kinds(recs) == oracle_kinds(ref)      # same events in the same order
+    # events carrying floats: tolerance (FFT arithmetic differs from the reference's FFT)
+    for (a, b) in zip([r for t, r in recs if t == eng.REC_SYNC], ref.of(reftap.REC_SYNC)):
+        assert a["psmi"] == b["psmi"] and abs(a["freq_offset"] - b["freq_offset"]) < 0.05
+    for (a, b) in zip([r for t, r in recs if t == eng.REC_BER], ref.of(reftap.REC_BER)):
+        assert abs(a["cber"] - b["cber"]) < 2e-4
+    for (a, b) in zip([r for t, r in recs if t == eng.REC_MER], ref.of(reftap.REC_MER)):
+        assert abs(a["lower"] - b["lower"]) < 0.05 and abs(a["upper"] - b["upper"]) < 0.05
+    # soft bits: <= 0.1 % may differ, by at most 1
+    sa = [r["soft"] for t, r in recs if t == eng.REC_SOFT_PM]
+    sb = [p["soft"] for p in ref.of(reftap.REC_SOFT_PM)]
+    assert len(sa) == len(sb)
+    fine = [(x, y) for x, y in zip(sa, sb)][2:]          # skip the blocks right after acquisition
+    if fine:
+        x = np.concatenate([a for a, _ in fine]).astype(np.int16)
+        y = np.concatenate([b for _, b in fine]).astype(np.int16)
+        assert np.abs(x - y).max() <= 2
+        assert np.mean(x != y) < 2e-3
+    # golden file (made by the unmodified reference)
+    g = common.golden("synth_fm.json")[name]
+    if common.fnv1a32(cap.cu8[:1 << 20].tobytes()) == g["input_fnv"]:
+        gold_frames = [e[3] for e in g["events"] if e[0] == "F"]
+        assert [common.fnv1a32(b) for b in p1] == gold_frames
+
+
+def test_chunked_push_matches_single_push():
+    cap = synth.make_fm_mp1(nframes=1, seed=3, lead_in=10)
+    a = run_engine([cap.cu8])[0]
+    b = run_engine([cap.cu8], chunk=32768 * 8)[0]
+    assert pdus(a) == pdus(b) and kinds(a) == kinds(b)
+
+
+def test_multi_stream_independent():
+    caps = [synth.make_fm_mp1(nframes=1, seed=100 + i, lead_in=37 * i + 5, cfo_hz=40.0 * i) for i in range(5)]
+    outs = run_engine([c.cu8 for c in caps])
+    for c, recs in zip(caps, outs):
+        ref = port.decode(c.cu8)
+        assert pdus(recs) == (ref.p1_frames, ref.pids_frames)
+        got = [common.fnv1a32(b) for b in pdus(recs)[0]]
+        assert common.fnv1a32(synth.pack_bits(c.p1_frames[-1])) in got      # round trip
+
+
+def test_sample_xz_bit_exact():
+    raw = common.load_sample()
+    if raw is None:
+        pytest.skip("sample.xz not available on this box")
+    g = common.golden("sample_xz.json")
+    recs = run_engine([raw], log_capacity=16 << 20)[0]
+    p1, pids = pdus(recs)
+    gold_p1 = [e[3] for e in g["events"] if e[0] == "F"]
+    gold_pids = [e[1] for e in g["events"] if e[0] == "P"]
+    assert [common.fnv1a32(b) for b in p1] == gold_p1
+    assert [common.fnv1a32(b) for b in pids] == gold_pids
+    assert kinds(recs) == [e[0] for e in g["events"]]
+
+
+def test_no_gpu_error_is_loud(monkeypatch):
+    # the product path has no CPU fallback: an invalid device must raise
+    with pytest.raises(nrsc5_b200.EngineError):
+        nrsc5_b200.Engine(nstreams=1, input_capacity=4096, device=99)

@@ -1,0 +1,84 @@
+"""GPU parity tests, stage by stage, through the C ABI (libnrsc5_b200.so)
+against the CPU oracle (oracle/nrsc5_oracle.c)."""
+import numpy as np
+import pytest
+
+import port
+from nrsc5_b200 import engine as eng
+from nrsc5_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_halfband_bit_exact():
+    rng = np.random.default_rng(0)
+    cu8 = rng.integers(0, 256, 4 * 200000, dtype=np.uint8)
+    cu8[:4000] = 255
+    cu8[4000:8000] = 0
+    cu8[8000:12000:2] = 255
+    assert np.array_equal(eng.halfband_fm(cu8), port.halfband_fm(cu8))
+
+
+def test_fft2048_matches_fp64():
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((8, 2048)) + 1j * rng.standard_normal((8, 2048))).astype(np.complex64)
+    x[0] = 0
+    x[0, 1] = 1
+    got = eng.fft2048(x)
+    ref = np.fft.fft(x.astype(np.complex128), axis=1)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err        # fp32 FFT: ~log2(N)*eps relative
+
+
+@pytest.mark.parametrize("length", [80, 2304, 4608])
+def test_viterbi_random_soft_bit_exact(length):
+    rng = np.random.default_rng(length)
+    nframes = 6
+    soft = rng.integers(-127, 128, (nframes, 3 * length), dtype=np.int8)
+    soft[:, 5::6] = 0
+    got = eng.viterbi_k7(soft, length)
+    for f in range(nframes):
+        assert np.array_equal(got[f], port.viterbi(soft[f]))
+
+
+def test_viterbi_saturating_and_noisy():
+    rng = np.random.default_rng(3)
+    length = 4608
+    u = rng.integers(0, 2, length, dtype=np.uint8)
+    c = synth.conv_encode_tb(u).reshape(-1).astype(np.int16)
+    full = ((2 * c - 1) * 127).astype(np.int8)             # drives int16 metrics into saturation
+    noisy = np.clip((2 * c - 1) * 40 + rng.normal(0, 45, c.size), -127, 127).astype(np.int8)
+    soft = np.stack([full, noisy])
+    got = eng.viterbi_k7(soft, length)
+    assert np.array_equal(got[0], port.viterbi(full)) and np.array_equal(got[0], u)
+    assert np.array_equal(got[1], port.viterbi(noisy))
+
+
+def test_viterbi_p1_length_bit_exact():
+    rng = np.random.default_rng(4)
+    length = 146176
+    u = rng.integers(0, 2, length, dtype=np.uint8)
+    c = synth.conv_encode_tb(u).reshape(-1).astype(np.int16)
+    soft = np.clip((2 * c - 1) * 30 + rng.normal(0, 40, c.size), -127, 127).astype(np.int8)
+    soft[5::6] = 0
+    got = eng.viterbi_k7(soft[None, :], length)[0]
+    assert np.array_equal(got, port.viterbi(soft))
+
+
+def test_rs_decode_bit_exact():
+    rng = np.random.default_rng(5)
+    blocks = []
+    for t in range(600):
+        hdr = np.frombuffer(synth.audio_pdu_header(rng=rng), dtype=np.uint8)
+        blk = np.zeros(255, dtype=np.uint8)
+        blk[254 - np.arange(96)] = hdr
+        for p in rng.choice(255 if t % 3 == 0 else 96, t % 8, replace=False):
+            blk[p if t % 3 == 0 else 254 - p] ^= rng.integers(1, 256)
+        if t % 25 == 24:
+            blk = rng.integers(0, 256, 255, dtype=np.uint8)
+        blocks.append(blk)
+    blocks = np.stack(blocks)
+    rc, fixed = eng.rs_decode(blocks)
+    for i in range(blocks.shape[0]):
+        rc_ref, ref = port.rs_decode(blocks[i])
+        assert rc[i] == rc_ref and np.array_equal(fixed[i], ref), i
