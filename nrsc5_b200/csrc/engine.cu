@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(DevPtrs p, EngineDims d)
             int *wi = reinterpret_cast<int *>(w);
             float *wf = reinterpret_cast<float *>(w);
             wi[0] = state_in; wi[1] = samperr; wf[2] = angle; wf[3] = ph.x; wf[4] = ph.y; wi[5] = st.cfo;
-            *reinterpret_cast<long long *>(w + 24) = st.start;
+            wi[6] = (int)(unsigned)(st.start & 0xffffffffLL);
+            wi[7] = (int)(st.start >> 32);
         }
     }
     __syncthreads();
@@ -416,16 +417,23 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
         __syncthreads();
         __shared__ int sh_do_search;
         if (t == 0) {
-            unsigned good = 0, seen_bc[16], seen_ps[64];
-            for (int i = 0; i < 16; i++) seen_bc[i] = 0;
-            for (int i = 0; i < 64; i++) seen_ps[i] = 0;
+            unsigned good = 0;
             for (int r = 0; r < 2 * MAXREF; r++)
-                if (sm.ref_ok[r]) { good++; seen_bc[sm.ref_bc[r]]++; seen_ps[sm.ref_psmi[r]]++; }
+                if (sm.ref_ok[r]) good++;
             sh_do_search = 0;
             if (good >= 4) {
+                // strict majorities; the PSMI majority is only looked for among 0..15 (sync.c:396)
                 int mbc = -1, mps = -1;
-                for (int v = 0; v < 16; v++) if (seen_bc[v] > good / 2) mbc = v;
-                for (int v = 0; v < 16; v++) if (seen_ps[v] > good / 2) mps = v;     // 0..15 only (sync.c:396)
+                for (int v = 0; v < 16; v++) {
+                    unsigned nbc = 0, nps = 0;
+                    for (int r = 0; r < 2 * MAXREF; r++) {
+                        if (!sm.ref_ok[r]) continue;
+                        nbc += sm.ref_bc[r] == v;
+                        nps += sm.ref_psmi[r] == v;
+                    }
+                    if (nbc > good / 2) mbc = v;
+                    if (nps > good / 2) mps = v;
+                }
                 if (mbc >= 0 && mps >= 0) {
                     st.bc = mbc;
                     st.psmi = mps;
@@ -459,14 +467,13 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
                 __syncwarp();
                 int found = 0;
                 if (lane == 0) {
-                    unsigned votes[BLK];
-                    for (int k = 0; k < BLK; k++) votes[k] = 0;
-                    for (int r = 0; r < 22; r++)
-                        if (sm.offs[r] >= 0) votes[sm.offs[r]]++;
                     int best = -1;
                     unsigned bestn = 0;
-                    for (int k = 0; k < BLK; k++)
-                        if (votes[k] > bestn) { best = k; bestn = votes[k]; }
+                    for (int k = 0; k < BLK; k++) {
+                        unsigned nv = 0;
+                        for (int r = 0; r < 22; r++) nv += sm.offs[r] == k;
+                        if (nv > bestn) { best = k; bestn = nv; }
+                    }
                     if (best >= 0 && bestn >= 3) {
                         st.keep_extra = ((BLK - best) % BLK) * NSYM;
                         st.cfo += cfo;
@@ -645,6 +652,9 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
                 // P1 bookkeeping (decode.c:383-390)
                 if (bc == 0) st.started_pm = 1;
                 if (st.started_pm && bc == 15) st.p1_ready = 1;
+#ifdef NB_DEBUG
+                { uint8_t *w2 = log_reserve(p, d, s, 10, 12); if (w2) { int *wi = (int*)w2; wi[0] = bc; wi[1] = st.started_pm; wi[2] = st.p1_ready; } }
+#endif
                 st.bc = (bc + 1) % 16;
             }
         }
@@ -673,6 +683,10 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1(DevPtrs p, EngineDims d)
 {
     const int s = blockIdx.x, t = threadIdx.x;
     StreamState &st = p.st[s];
+#ifdef NB_DEBUG
+    if (t == 0) { uint8_t *w2 = log_reserve(p, d, s, 11, 4); if (w2) *(int*)w2 = st.p1_ready; }
+    __syncthreads();
+#endif
     if (!st.p1_ready) return;
     __shared__ uint8_t tb_map[TB_NCHUNK][64];
     __shared__ uint8_t tb_end[TB_NCHUNK];

@@ -109,6 +109,8 @@ def parse_records(raw: bytes):
         elif ty == REC_BLOCK:
             st, se, ang, pr, pi, cfo, start = struct.unpack("<iifffiq", pay[:32])
             rec = {"state": st, "samperr": se, "angle": ang, "phase": complex(pr, pi), "cfo": cfo, "start": start}
+        elif ty in (10, 11):
+            rec = {"dbg": struct.unpack("<%di" % (plen // 4), pay)}
         else:
             raise EngineError(f"corrupt record stream (type {ty} at {off})")
         out.append((ty, rec))

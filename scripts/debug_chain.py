@@ -49,3 +49,8 @@ gpi = [r["bits"] for t, r in recs if t == eng.REC_PIDS]
 print("PIDS equal", gpi == ref.pids_frames, len(gpi), len(ref.pids_frames), sum(a != b for a, b in zip(gpi, ref.pids_frames)))
 for k, t in [("S", eng.REC_SYNC), ("M", eng.REC_MER), ("B", eng.REC_BER)]:
     print(k, [r for tt, r in recs if tt == t][:4], [p for tt, p in ref.records if tt == t][:4])
+dbg = [(t, r["dbg"]) for t, r in recs if t in (10, 11)]
+if dbg:
+    print("debug records:")
+    for i in range(0, min(len(dbg), 80), 2):
+        print("  ", dbg[i:i + 2])
