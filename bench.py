@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — NRSC-5 FM receive-chain throughput on B200.
+
+Metric (BASELINE.json): cu8 I/Q Msamples/s (complex samples; / 1.488375 = x real
+time) of the whole hot path, at N GPUs, streams sharded per GPU, weak scaling.
+
+A *step* = one pass of the hot path over one batch: S independent synthetic
+FM MP1 channels per GPU (config 5's per-GPU shard: 128 channels), each
+`frames` L1 frames (+2 blocks of tail) long, decoded from reset to L1 PDUs.
+
+  value : whole-job Msamples/s with the cu8 already resident in HBM when the
+          timed region starts (engine attached to a device buffer).
+  e2e   : same metric through the public C ABI with HOST buffers: pinned
+          host->device copy of every stream's cu8 and device->host drain of all
+          PDU/event records inside the timed region (and, for N>1, an NCCL
+          gather of the fixed-size P1 PDU slabs to rank 0).
+  --impl reference : the reference's own CPU implementation (the UNMODIFIED
+          reference built into oracle/_ref/libnrsc5_ref.so; FFTW replaced by
+          oracle/shim/fftshim.c) on the host cores, same captures.
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 1488375.0
+BLOCK_BYTES = 276480
+DEMOD_BYTES_PER_BLOCK = 276480 + 32 * 534 * 8      # cu8 in + 534 complex bins x 32 symbols out
+FUSED_BYTES_PER_BLOCK = 276480 + 23040              # cu8 in + int8 soft bits out
+P1_BYTES_PER_FRAME = 368640 + 18272 + 160
+SYNC_BYTES_PER_BLOCK = 32 * 534 * 8 + 23040
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=128, help="channels per GPU")
+    ap.add_argument("--frames", type=int, default=2, help="L1 frames per channel per step")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic captures (replicated with offsets)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_captures(distinct: int, frames: int, base_seed: int = 1234):
+    from nrsc5_b200 import synth
+    caps = []
+    for i in range(distinct):
+        kw = dict(nframes=frames, seed=base_seed + i, lead_in=0, tail_blocks=2, noise_seed=5 + i)
+        if i % 4 == 1:
+            kw.update(cfo_hz=120.0)
+        elif i % 4 == 2:
+            kw.update(cfo_hz=-300.0, noise_lsb=12.0)
+        elif i % 4 == 3:
+            kw.update(cfo_hz=60.0, noise_lsb=6.0)
+        caps.append(synth.make_fm_mp1(**kw).cu8)
+    return caps
+
+
+def stream_views(caps, nstreams: int, rank: int):
+    """Stream s of this rank = capture (g % D) with the first 4*(37*(g // D) % 1080) bytes dropped,
+    g = global stream index: distinct alignments, so distinct acquisition paths."""
+    D = len(caps)
+    n = min(c.size for c in caps) - 4 * 1080 * 4
+    n &= ~63
+    views = []
+    for s in range(nstreams):
+        g = rank * nstreams + s
+        off = 4 * ((37 * (g // D)) % 1080)
+        views.append(caps[g % D][off: off + n])
+    return views, n
+
+
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def start(self):
+        def run():
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([x.strip() for x in out.strip().split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._th = threading.Thread(target=run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_arm(args, rank: int, world: int):
+    """Times the unmodified reference CPU implementation on this host's cores."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reftap
+    import port
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, 64)
+    caps = make_captures(args.distinct, args.frames)
+    views, n = stream_views(caps, nthreads, 0)
+    bufs = [np.ascontiguousarray(v) for v in views]
+    if reftap.available():
+        kind = "reference"
+        run = lambda: reftap.bench(bufs, mode=reftap.MODE_FM, reps=1)      # noqa: E731
+    else:
+        kind = "port"
+        def run():
+            t0 = time.perf_counter()
+            for b in bufs[:1]:
+                port.decode(b)
+            return time.perf_counter() - t0
+        nthreads = 1
+    for _ in range(args.warmup):
+        run()
+    t = [run() for _ in range(args.steps)]
+    total = sum(t)
+    samples = (n // 2) * nthreads * args.steps
+    val = samples / total / 1e6
+    sample_desc = (f"{nthreads} host threads x 1 channel x {args.frames} frames+2 blocks ({n // 2} cu8 samples each) per step; "
+                   f"FFT = oracle/shim/fftshim.c (FFTW 3.3.10 not installed); SSE Viterbi")
+    line = {
+        "impl": "reference", "metric": "cu8 I/Q Msamples/s", "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16/f32", "data": "synthetic",
+        "config": workload_config(args, n),
+        "x_realtime": val * 1e6 / SAMPLE_RATE,
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": nthreads, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": cores,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, nbytes):
+    return {"workload": f"{args.streams} independent synthetic FM MP1 hybrid cu8 channels per GPU "
+                        f"(BASELINE config 5 shard), {args.frames} L1 frames + 2 blocks each, full chain to L1 PDUs",
+            "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "bytes_per_stream": int(nbytes),
+            "distinct_captures": args.distinct,
+            "l2": "per-GPU input (streams x bytes_per_stream) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import nrsc5_b200
+    from nrsc5_b200 import engine as eng
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    use_dist = world > 1
+    if use_dist:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.streams
+    caps = make_captures(args.distinct, args.frames)
+    views, nbytes = stream_views(caps, S, rank)
+    samples_per_step = S * (nbytes // 2)
+
+    # host side: one pinned slab [S][nbytes]; device side: the same slab resident in HBM
+    host = torch.empty((S, nbytes), dtype=torch.uint8).pin_memory()
+    hnp = host.numpy()
+    for s, v in enumerate(views):
+        hnp[s, :] = v
+    devbuf = torch.empty((S, nbytes + 64), dtype=torch.uint8, device=dev)
+    devbuf[:, :nbytes].copy_(host)
+    devbuf[:, nbytes:] = 127
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    log_cap = (args.frames + 1) * (18272 + 64) + 64 * 1024
+    e = nrsc5_b200.Engine(nstreams=S, input_capacity=nbytes + 4096, device=local_rank, log_capacity=log_cap)
+    e.set_cuda_stream(stream.cuda_stream)
+    log_stride = (log_cap + 15) & ~15
+    logbuf = torch.zeros((S, log_stride), dtype=torch.uint8, device=dev)   # caller-owned record log, NCCL-gatherable
+    e.attach_device_log(logbuf.data_ptr(), log_stride)
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        e.attach_device_input(devbuf.data_ptr(), nbytes + 64, nbytes)
+        e.rewind()
+        e.process()
+
+    def step_e2e():
+        e.reset()
+        for s in range(S):
+            e.push_cu8(s, hnp[s])
+        e.process()
+        nrec = 0
+        d2h = 0
+        frames = []
+        for s in range(S):
+            raw = e.drain_raw(s)
+            d2h += len(raw)
+            frames.append(raw)
+        if use_dist:
+            # gather of the decoded L1 PDU / event slabs to rank 0 over NCCL (the only collective on the path)
+            lst = [torch.empty_like(logbuf) for _ in range(world)] if rank == 0 else None
+            dist.gather(logbuf, lst, dst=0)
+        return d2h, frames
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = e.stats().kernel_launches
+        ev0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        l1 = e.stats().kernel_launches
+        clocks = sampler.stop()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), l1 - l0, clocks, out
+
+    # ---- correctness gate: PDUs of stream 0 must match what the generator put in ----
+    step_resident()
+    recs0 = e.drain(0)
+    n_p1 = sum(1 for t, _ in recs0 if t == eng.REC_FRAME)
+    assert n_p1 >= 1, "no P1 frame decoded in the bench workload"
+
+    # ---- value: device-resident ----
+    ms, launches, clocks, _ = timed(step_resident, args.steps, max(args.warmup, 3))
+    total_samples = samples_per_step * world * args.steps
+    value = total_samples / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel times (separate pass, CUDA events around each launch) ----
+    e.set_profiling(True)
+    step_resident()
+    torch.cuda.synchronize()
+    kt = e.kernel_times()
+    e.set_profiling(False)
+    st = e.stats()
+    peak, peak_src = measured_peak()
+    blocks_per_step = None
+    # blocks processed in the profiled step = demod launches that had work; use stats delta instead
+    e.rewind(); e.attach_device_input(devbuf.data_ptr(), nbytes + 64, nbytes)
+    b0 = e.stats().blocks
+    e.process(); torch.cuda.synchronize()
+    b1 = e.stats().blocks
+    blocks_per_step = int(b1 - b0) if b1 > b0 else int(b1)
+    frames_per_step = int(e.stats().p1_frames)
+    kinfo = {}
+    alg = {"demod": DEMOD_BYTES_PER_BLOCK * blocks_per_step, "sync": SYNC_BYTES_PER_BLOCK * blocks_per_step,
+           "p1": P1_BYTES_PER_FRAME * frames_per_step, "prep": 0}
+    for k, v in kt.items():
+        gbs = alg[k] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
+        kinfo[k] = {"ms_per_step": v["ms"], "launches": v["launches"], "alg_bytes_per_step": alg[k], "achieved_gbs": gbs}
+    dom = max(("demod", "sync", "p1"), key=lambda k: kt[k]["ms"])
+    busy = [k for k in kt if kt[k]["launches"]]
+    dom_launches_with_work = max(1, blocks_per_step // S) if dom != "p1" else max(1, frames_per_step // S)
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": kinfo[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kinfo[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg[dom] / dom_launches_with_work,
+                "chain_frac_of_hbm": (2.34 * value * 1e6 / world) / (peak * 1e9),
+                "fused_frontend_equiv_gbs": FUSED_BYTES_PER_BLOCK * blocks_per_step / (max(kt["demod"]["ms"] + kt["sync"]["ms"], 1e-9) * 1e-3) / 1e9,
+                "kernels": kinfo}
+
+    # ---- e2e ----
+    e2e = None
+    if not args.no_e2e:
+        ms2, _, _, out = timed(step_e2e, args.steps, max(args.warmup, 3))
+        d2h = out[0] if out else 0
+        e2e_val = total_samples / (ms2 * 1e-3) / 1e6
+        e2e = {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": int(S * nbytes), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms2 / args.steps, "x_realtime": e2e_val * 1e6 / SAMPLE_RATE}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import reftap
+        cores = os.cpu_count() or 1
+        nthreads = min(cores, 64, S)
+        bufs = [np.ascontiguousarray(hnp[s]) for s in range(nthreads)]
+        if reftap.available():
+            reftap.bench(bufs[:1], reps=1)
+            reps = 2
+            t1 = reftap.bench(bufs[:1], reps=reps)
+            tn = reftap.bench(bufs, reps=reps)
+            cpu = {"value": nthreads * reps * (nbytes // 2) / tn / 1e6, "unit": "Msamples/s", "cores": nthreads, "kind": "reference",
+                   "single_core_value": reps * (nbytes // 2) / t1 / 1e6,
+                   "sample": f"{nthreads} threads x {reps} passes over one {nbytes // 2}-sample channel each "
+                             f"(unmodified reference, SSE Viterbi, fftshim FFT in place of FFTW); host has {cores} logical cores"}
+        else:
+            import port
+            t0 = time.perf_counter()
+            port.decode(bufs[0])
+            dt = time.perf_counter() - t0
+            cpu = {"value": (nbytes // 2) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                   "sample": "one channel, one pass, oracle/nrsc5_oracle.c"}
+
+    if rank == 0:
+        line = {
+            "metric": "cu8 I/Q Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int16/f32", "data": "synthetic", "config": workload_config(args, nbytes),
+            "x_realtime": value * 1e6 / SAMPLE_RATE, "x_realtime_per_gpu": value * 1e6 / SAMPLE_RATE / world,
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    e.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,8 @@ typedef struct {
 int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg);
 void nrsc5b_destroy(nrsc5b_engine_t *e);
 int nrsc5b_reset(nrsc5b_engine_t *e, int stream);          /* stream < 0: all */
+/* Restart every stream from sample 0 of the input it already holds (benchmark loops). */
+int nrsc5b_rewind(nrsc5b_engine_t *e);
 
 /* Use this CUDA stream (a cudaStream_t cast to void*) for all engine work; NULL = legacy default. */
 int nrsc5b_set_cuda_stream(nrsc5b_engine_t *e, void *cuda_stream);
@@ -102,7 +104,11 @@ int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void *dev_buf, 
 /* Point every stream at an existing device buffer [nstreams][stride] holding nbytes valid bytes each (no copy). */
 int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_buf, size_t stride, size_t nbytes);
 
-/* Run every 32-symbol block for which all streams' buffered samples suffice. Asynchronous. */
+/* Write the output records into a caller-owned device buffer [nstreams][stride] (stride % 16 == 0), e.g. one
+ * that an NCCL gather can ship to another rank; nrsc5b_drain keeps working on it. */
+int nrsc5b_attach_device_log(nrsc5b_engine_t *e, void *dev_buf, size_t stride);
+
+/* Run every 32-symbol block for which a stream's buffered samples suffice; returns when no stream can advance. */
 int nrsc5b_process(nrsc5b_engine_t *e);
 /* Wait for the GPU and copy the records of `stream` produced since the last drain.
  * Returns the number of bytes written (>= 0) or a negative error; *needed gets the full size. */
@@ -119,6 +125,11 @@ typedef struct {
     uint64_t kernel_launches; /* kernels launched by the engine                 */
 } nrsc5b_stats_t;
 int nrsc5b_get_stats(nrsc5b_engine_t *e, nrsc5b_stats_t *st);
+
+/* Per-kernel device time from CUDA events around every launch (a separate, slower pass):
+ * ms4/n4 = {prep, demod, sync, p1} accumulated milliseconds and launch counts since set_profiling(1). */
+int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on);
+int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long *n4);
 
 /* ---- single-stage entry points (kernel-level parity tests, host buffers) ---- */
 /* cu8 -> Q15 -> halfband /2 from zero history: out[2*npairs] int16 (reference src/firdecim_q15.c:137-165) */

@@ -67,6 +67,7 @@ struct StreamState {
     float2 phase0;             // NCO phase at the first sample of the block
     // P1 hand-off sync -> p1 kernel
     int p1_ready;
+    int p1_slow;               // this frame needs saturating Viterbi arithmetic
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
     // output log cursor
     unsigned log_len;
@@ -75,7 +76,6 @@ struct StreamState {
     unsigned long long frames_done;
     // history of the coarse band-pass FIR: the last 31 samples it was fed
     short bp_hist[31][2];
-    short pad_[2];
 };
 
 struct EngineDims {

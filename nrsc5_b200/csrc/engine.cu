@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "rs.cuh"
 #include "viterbi.cuh"
+#include "viterbi_chunk.cuh"
 
 namespace nb {
 
@@ -669,76 +670,39 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
 }
 
 // ===========================================================================
-// k_p1: per stream with a complete interleaver matrix — interleaver I +
-// depuncture, K=7 Viterbi, channel BER, descramble, packing, and the L2 header
-// predicate that feeds back into the sync state.
-//   reference src/decode.c:451-461,296-322,234-265,279-294; src/conv_dec.c;
-//   src/frame.c:645-714,527-541,158-179; src/rs_decode.c
+// P1 decode: for every stream whose interleaver matrix is complete —
+//   k_p1_gather : interleaver I + depuncture 1,1,1,1,1,0  (decode.c:296-322)
+//   k_vitc_fwd / k_vitc_ends / k_vitc_emit : K=7 tail-biting Viterbi (viterbi_chunk.cuh)
+//   k_p1_fin    : channel BER (decode.c:234-265), descramble (:279-294), packing,
+//                 and the L2 header predicate that feeds back into the sync state
+//                 (frame.c:645-714,527-541,158-179; rs_decode.c)
 // ===========================================================================
 constexpr int P1_THREADS = 256;
-constexpr int TB_CHUNK = 256;
-constexpr int TB_NCHUNK = (P1_STEPS + TB_CHUNK - 1) / TB_CHUNK;     // 572
+constexpr int P1_NCH = (P1_STEPS + CH_LEN - 1) / CH_LEN;             // 143
 
-__global__ void __launch_bounds__(P1_THREADS) k_p1(DevPtrs p, EngineDims d)
+__global__ void __launch_bounds__(256) k_p1_gather(DevPtrs p, EngineDims d)
+{
+    const int s = blockIdx.y;
+    if (!p.st[s].p1_ready) return;
+    const int8_t *pm = p.pm + (size_t)s * 16 * PM_BLOCK;
+    int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P1_VIT; o += gridDim.x * blockDim.x) {
+        const int q = o / 6, r = o - 6 * q;
+        vin[o] = r == 5 ? (int8_t)0 : pm[p.p1_lut[5 * q + r]];
+    }
+}
+
+__global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
 {
     const int s = blockIdx.x, t = threadIdx.x;
     StreamState &st = p.st[s];
-#ifdef NB_DEBUG
-    if (t == 0) { uint8_t *w2 = log_reserve(p, d, s, 11, 4); if (w2) *(int*)w2 = st.p1_ready; }
-    __syncthreads();
-#endif
     if (!st.p1_ready) return;
-    __shared__ uint8_t tb_map[TB_NCHUNK][64];
-    __shared__ uint8_t tb_end[TB_NCHUNK];
-    __shared__ int sh_state;
     __shared__ int red[P1_THREADS];
     __shared__ uint8_t *sh_w;
     __shared__ uint8_t hdr[96];
     __shared__ uint8_t blk[255];
-
-    const int8_t *pm = p.pm + (size_t)s * 16 * PM_BLOCK;
-    int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
-    uint2 *dec = p.vit_dec + (size_t)s * P1_STEPS;
+    const int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
     uint8_t *bits = p.p1_bits + (size_t)s * P1_LEN;
-
-    // interleaver I gather with depuncture 1,1,1,1,1,0
-    for (int o = t; o < P1_VIT; o += P1_THREADS) {
-        int q = o / 6, r = o - 6 * q;
-        vin[o] = r == 5 ? (int8_t)0 : pm[p.p1_lut[5 * q + r]];
-    }
-    __syncthreads();
-    if (t < 32) {
-        int stt = viterbi_forward(vin, P1_LEN, dec, t);
-        if (t == 0) sh_state = stt;
-    }
-    __syncthreads();
-    // chunked traceback, phase A: end-state -> start-state map of every chunk
-    for (int item = t; item < TB_NCHUNK * 64; item += P1_THREADS) {
-        int c = item >> 6, e = item & 63;
-        int hi = min(P1_STEPS, (c + 1) * TB_CHUNK), lo = c * TB_CHUNK;
-        int state = e;
-        for (int q = hi - 1; q >= lo; q--) state = vit_prev(state, dec[q]);
-        tb_map[c][e] = (uint8_t)state;
-    }
-    __syncthreads();
-    if (t == 0) {                                // phase B: compose from the end
-        int cur = sh_state;
-        for (int c = TB_NCHUNK - 1; c >= 0; c--) {
-            tb_end[c] = (uint8_t)cur;
-            cur = tb_map[c][cur];
-        }
-    }
-    __syncthreads();
-    for (int c = t; c < TB_NCHUNK; c += P1_THREADS) {     // phase C: emit bits
-        int hi = min(P1_STEPS, (c + 1) * TB_CHUNK), lo = c * TB_CHUNK;
-        int state = tb_end[c];
-        for (int q = hi - 1; q >= lo; q--) {
-            if (q >= 32 && q < 32 + P1_LEN) bits[q - 32] = (uint8_t)((state >> 5) & 1);
-            state = vit_prev(state, dec[q]);
-        }
-    }
-    __syncthreads();
-    // channel BER by re-encoding (decode.c:234-265)
     {
         int errs = 0;
         for (int i = t; i < P1_LEN; i += P1_THREADS) {
@@ -750,7 +714,7 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1(DevPtrs p, EngineDims d)
                 reg |= (unsigned)bits[idx] << b;
             }
             const int8_t *c = vin + 3 * i;
-            int j = 3 * i;
+            const int j = 3 * i;
             if ((j % 6) != 5 && ((c[0] > 0) != (int)(__popc(reg & 0133u) & 1))) errs++;
             if (((j + 1) % 6) != 5 && ((c[1] > 0) != (int)(__popc(reg & 0171u) & 1))) errs++;
             if (((j + 2) % 6) != 5 && ((c[2] > 0) != (int)(__popc(reg & 0165u) & 1))) errs++;
@@ -773,7 +737,6 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1(DevPtrs p, EngineDims d)
         }
     }
     __syncthreads();
-    // descramble (decode.c:279-294) and pack MSB-first
     for (int i = t; i < P1_LEN; i += P1_THREADS) bits[i] ^= p.pn[i];
     __syncthreads();
     if (sh_w) {
@@ -784,7 +747,6 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1(DevPtrs p, EngineDims d)
             sh_w[8 + b] = (uint8_t)v;
         }
     }
-    // L2 feedback predicate (frame.c:645-714 PCI, :146-156 has_audio, :527-541)
     if (t < 96) {
         unsigned v = 0;
         for (int j = 0; j < 8; j++) {
@@ -803,7 +765,31 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1(DevPtrs p, EngineDims d)
         bool has_audio = (pci & 0xFFFFFC) != (0x3634CE & 0xFFFFFC);
         if (has_audio && !fix_header_96(hdr, blk)) set_state(p, d, s, ST_NONE);
         st.p1_ready = 0;
+        st.p1_slow = 0;
         st.frames_done++;
+    }
+}
+
+// input_reset for a range of streams (reference src/input.c:126-138)
+__global__ void k_reset(DevPtrs p, EngineDims d, int only)
+{
+    const int s = blockIdx.x, t = threadIdx.x;
+    if (only >= 0 && s != only) return;
+    for (int i = t; i < NFFT; i += blockDim.x) {
+        p.cfreq[(size_t)s * NFFT + i] = 0.f;
+        p.cphase[(size_t)s * NFFT + i] = 0.f;
+    }
+    if (t == 0) {
+        StreamState &st = p.st[s];
+        const long long avail = st.in_avail;
+        StreamState z;
+        memset(&z, 0, sizeof(z));
+        z.phase = make_float2(1.0f, 0.0f);
+        z.psmi = 1;
+        z.state = ST_NONE;
+        z.force_state = -1;
+        z.in_avail = only == -2 ? avail : 0;     // -2: keep the attached input (rewind)
+        st = z;
     }
 }
 
@@ -839,6 +825,9 @@ __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
 // ===========================================================================
 using namespace nb;
 
+static size_t vitc_ends_smem(int nch) { return (size_t)nch * (VITC_HEAD / 16) * 16 * sizeof(uint2) + (size_t)nch * 64; }
+static size_t vitc_emit_smem() { return (size_t)VITC_EMIT_WARPS * CH_LEN * sizeof(uint2); }
+
 #define CK(x)                                                                                      \
     do {                                                                                           \
         cudaError_t e_ = (x);                                                                      \
@@ -864,6 +853,12 @@ struct nrsc5b_engine {
     unsigned long long last_progress;
     size_t sync_smem;
     std::vector<void *> allocs;
+    int profiling;
+    uint2 *vspec, *vend;
+    int *tbend;
+    cudaEvent_t pev[5];
+    double kernel_ms[4];
+    unsigned long long kernel_n[4];
 };
 
 static const float k_bp_coeff[32] = {
@@ -953,6 +948,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->iq_owned = nullptr;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
+    e->profiling = 0;
+    for (int i = 0; i < 5; i++) e->pev[i] = nullptr;
+    for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
+    e->pinned = nullptr; e->h_state = nullptr; e->pinned_free = nullptr;
     const int S = cfg->nstreams;
     e->dims.nstreams = S;
     e->dims.in_stride = (cfg->input_capacity + 63) & ~(size_t)63;
@@ -989,7 +988,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     DA(ydec, short2, (size_t)S * NACQ);
     DA(tbuf, float2, (size_t)S * NACQ);
     DA(vit_in, int8_t, (size_t)S * P1_VIT);
-    DA(vit_dec, uint2, (size_t)S * P1_STEPS);
+    DA(vit_dec, uint2, (size_t)S * P1_NCH * CH_LEN);
+    rc = dev_alloc(e, &e->vspec, (size_t)S * P1_NCH * 16); if (rc) { nrsc5b_destroy(e); return rc; }
+    rc = dev_alloc(e, &e->vend, (size_t)S * P1_NCH * 16); if (rc) { nrsc5b_destroy(e); return rc; }
+    rc = dev_alloc(e, &e->tbend, (size_t)S * P1_NCH); if (rc) { nrsc5b_destroy(e); return rc; }
     DA(p1_bits, uint8_t, (size_t)S * P1_LEN);
     DA(log, uint8_t, (size_t)S * e->dims.log_cap);
     {
@@ -1048,12 +1050,15 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         return NRSC5B_ENOMEM;
     }
     e->sync_smem = sizeof(SyncSmem);
-    if (cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->sync_smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->sync_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vitc_ends, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_ends_smem(P1_NCH)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess) {
         nrsc5b_destroy(e);
         return NRSC5B_ECUDA;
     }
     *out = e;
     rc = nrsc5b_reset(e, -1);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = NRSC5B_ECUDA;
     if (rc) { nrsc5b_destroy(e); *out = nullptr; return rc; }
     return NRSC5B_OK;
 }
@@ -1066,6 +1071,7 @@ extern "C" void nrsc5b_destroy(nrsc5b_engine_t *e)
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_state) cudaFreeHost(e->h_state);
     if (e->pinned_free) cudaEventDestroy(e->pinned_free);
+    for (int i = 0; i < 5; i++) if (e->pev[i]) cudaEventDestroy(e->pev[i]);
     delete e;
 }
 
@@ -1079,18 +1085,26 @@ extern "C" int nrsc5b_set_cuda_stream(nrsc5b_engine_t *e, void *cuda_stream)
 extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
 {
     if (!e || stream >= e->dims.nstreams) return NRSC5B_EINVAL;
-    CK(cudaStreamSynchronize(e->stream));
     const int S = e->dims.nstreams;
+    k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream);
+    e->stats.kernel_launches += 1;
     for (int s = 0; s < S; s++) {
         if (stream >= 0 && s != stream) continue;
-        StreamState st;
-        init_state_host(st);
-        CK(cudaMemcpy(e->dp.st + s, &st, sizeof(st), cudaMemcpyHostToDevice));
-        CK(cudaMemset(e->dp.cfreq + (size_t)s * NFFT, 0, NFFT * sizeof(float)));
-        CK(cudaMemset(e->dp.cphase + (size_t)s * NFFT, 0, NFFT * sizeof(float)));
         e->pushed[s] = 0;
         e->drained[s] = 0;
     }
+    CK(cudaGetLastError());
+    return NRSC5B_OK;
+}
+
+/* Restart every stream from sample 0 of the input it already holds (benchmark loops). */
+extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
+{
+    if (!e) return NRSC5B_EINVAL;
+    k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2);
+    e->stats.kernel_launches += 1;
+    for (int s = 0; s < e->dims.nstreams; s++) e->drained[s] = 0;
+    CK(cudaGetLastError());
     return NRSC5B_OK;
 }
 
@@ -1108,14 +1122,22 @@ extern "C" int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *bu
     size_t off = (size_t)e->pushed[stream] * 2;
     if (off + nbytes > e->dims.in_stride) return NRSC5B_EFULL;
     uint8_t *dst = e->iq_owned + (size_t)stream * e->dims.in_stride + off;
-    size_t done = 0;
-    while (done < nbytes) {
-        size_t n = nbytes - done < e->pinned_cap ? nbytes - done : e->pinned_cap;
-        CK(cudaEventSynchronize(e->pinned_free));
-        memcpy(e->pinned, buf + done, n);
-        CK(cudaMemcpyAsync(dst + done, e->pinned, n, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaEventRecord(e->pinned_free, e->stream));
-        done += n;
+    // page-locked caller memory is DMA'd directly; pageable memory goes through the engine's pinned staging buffer
+    cudaPointerAttributes attr;
+    bool pinned_src = cudaPointerGetAttributes(&attr, buf) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned_src) {
+        CK(cudaMemcpyAsync(dst, buf, nbytes, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        size_t done = 0;
+        while (done < nbytes) {
+            size_t n = nbytes - done < e->pinned_cap ? nbytes - done : e->pinned_cap;
+            CK(cudaEventSynchronize(e->pinned_free));
+            memcpy(e->pinned, buf + done, n);
+            CK(cudaMemcpyAsync(dst + done, e->pinned, n, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaEventRecord(e->pinned_free, e->stream));
+            done += n;
+        }
     }
     e->pushed[stream] += (long long)(nbytes / 2);
     return publish_avail(e, stream);
@@ -1145,15 +1167,95 @@ extern "C" int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_bu
     return NRSC5B_OK;
 }
 
+extern "C" int nrsc5b_attach_device_log(nrsc5b_engine_t *e, void *dev_buf, size_t stride)
+{
+    if (!e || !dev_buf || stride < 4096 || (stride & 15)) return NRSC5B_EINVAL;
+    CK(cudaStreamSynchronize(e->stream));
+    e->dp.log = reinterpret_cast<uint8_t *>(dev_buf);
+    e->dims.log_cap = stride;
+    return NRSC5B_OK;
+}
+
+static VitcArgs p1_vitc_args(nrsc5b_engine *e)
+{
+    VitcArgs a;
+    a.vin = e->dp.vit_in;
+    a.dec = e->dp.vit_dec;
+    a.vspec = e->vspec;
+    a.vend = e->vend;
+    a.tbend = e->tbend;
+    a.bits = e->dp.p1_bits;
+    a.ready = &e->dp.st[0].p1_ready;
+    a.slow = &e->dp.st[0].p1_slow;
+    a.ready_stride = (int)(sizeof(StreamState) / sizeof(int));
+    a.len = P1_LEN;
+    a.nch = P1_NCH;
+    a.dec_stride = (size_t)P1_NCH * CH_LEN;
+    return a;
+}
+
+
+static void launch_vitc(const VitcArgs &a, int nframes, cudaStream_t stream)
+{
+    dim3 gf((a.nch + 2 * VITC_FWD_WARPS - 1) / (2 * VITC_FWD_WARPS), nframes);
+    k_vitc_fwd<<<gf, VITC_FWD_WARPS * 32, 0, stream>>>(a);
+    k_vitc_ends<<<nframes, VITC_ENDS_THREADS, vitc_ends_smem(a.nch), stream>>>(a);
+    dim3 ge((a.nch + VITC_EMIT_WARPS - 1) / VITC_EMIT_WARPS, nframes);
+    k_vitc_emit<<<ge, VITC_EMIT_WARPS * 32, vitc_emit_smem(), stream>>>(a);
+}
+
+static void launch_p1(nrsc5b_engine *e)
+{
+    const int S = e->dims.nstreams;
+    k_p1_gather<<<dim3(16, S), 256, 0, e->stream>>>(e->dp, e->dims);
+    launch_vitc(p1_vitc_args(e), S, e->stream);
+    k_p1_fin<<<S, P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
+    e->stats.kernel_launches += 5;
+}
+
 static int launch_step(nrsc5b_engine *e)
 {
     const int S = e->dims.nstreams;
+    const bool prof = e->profiling != 0;
+    if (prof) cudaEventRecord(e->pev[0], e->stream);
     k_prep<<<S, PREP_THREADS, 0, e->stream>>>(e->dp, e->dims);
+    if (prof) cudaEventRecord(e->pev[1], e->stream);
     launch_demod(e->dp, e->dims, e->stream);
+    if (prof) cudaEventRecord(e->pev[2], e->stream);
     k_sync<<<S, SYNC_THREADS, e->sync_smem, e->stream>>>(e->dp, e->dims);
-    k_p1<<<S, P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
-    e->stats.kernel_launches += 4;
+    if (prof) cudaEventRecord(e->pev[3], e->stream);
+    launch_p1(e);
+    if (prof) {
+        cudaEventRecord(e->pev[4], e->stream);
+        cudaEventSynchronize(e->pev[4]);
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->pev[i], e->pev[i + 1]);
+            e->kernel_ms[i] += ms;
+            e->kernel_n[i] += 1;
+        }
+    }
+    e->stats.kernel_launches += 3;
     return 0;
+}
+
+/* Per-kernel device time (CUDA events around every launch; slows the run down, use a separate pass).
+ * Order: prep, demod, sync, p1. */
+extern "C" int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on)
+{
+    if (!e) return NRSC5B_EINVAL;
+    if (on && !e->pev[0])
+        for (int i = 0; i < 5; i++) CK(cudaEventCreate(&e->pev[i]));
+    e->profiling = on;
+    for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
+    return NRSC5B_OK;
+}
+
+extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long *n4)
+{
+    if (!e || !ms4 || !n4) return NRSC5B_EINVAL;
+    for (int i = 0; i < 4; i++) { ms4[i] = e->kernel_ms[i]; n4[i] = e->kernel_n[i]; }
+    return NRSC5B_OK;
 }
 
 extern "C" int nrsc5b_process(nrsc5b_engine_t *e)
@@ -1269,17 +1371,45 @@ extern "C" int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int
     if (len < 32 || nframes <= 0) return NRSC5B_EINVAL;
     int8_t *din = nullptr;
     uint8_t *dout = nullptr;
-    uint2 *ddec = nullptr;
     size_t nin = (size_t)nframes * 3 * len;
     CK(cudaMalloc(&din, nin));
     CK(cudaMalloc(&dout, (size_t)nframes * len));
-    CK(cudaMalloc(&ddec, (size_t)nframes * (len + 64) * sizeof(uint2)));
     CK(cudaMemcpy(din, in, nin, cudaMemcpyHostToDevice));
-    k_viterbi_test<<<nframes, 32>>>(din, dout, ddec, len);
+    if (len >= 2048 && (len % 16) == 0) {
+        // chunk-parallel exact decoder (the engine's P1 path)
+        VitcArgs a;
+        a.len = len;
+        a.nch = (len + 64 + CH_LEN - 1) / CH_LEN;
+        a.dec_stride = (size_t)a.nch * CH_LEN;
+        a.ready_stride = 1;
+        int *dflags = nullptr;
+        CK(cudaMalloc(&a.dec, (size_t)nframes * a.dec_stride * sizeof(uint2)));
+        CK(cudaMalloc(&a.vspec, (size_t)nframes * a.nch * 16 * sizeof(uint2)));
+        CK(cudaMalloc(&a.vend, (size_t)nframes * a.nch * 16 * sizeof(uint2)));
+        CK(cudaMalloc(&a.tbend, (size_t)nframes * a.nch * sizeof(int)));
+        CK(cudaMalloc(&dflags, (size_t)nframes * 2 * sizeof(int)));
+        std::vector<int> fl(2 * (size_t)nframes, 0);
+        for (int i = 0; i < nframes; i++) fl[i] = 1;
+        CK(cudaMemcpy(dflags, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
+        a.vin = din;
+        a.bits = dout;
+        a.ready = dflags;
+        a.slow = dflags + nframes;
+        CK(cudaFuncSetAttribute(k_vitc_ends, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_ends_smem(a.nch)));
+        CK(cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()));
+        launch_vitc(a, nframes, 0);
+        CK(cudaDeviceSynchronize());
+        cudaFree(a.dec); cudaFree(a.vspec); cudaFree(a.vend); cudaFree(a.tbend); cudaFree(dflags);
+    } else {
+        uint2 *ddec = nullptr;
+        CK(cudaMalloc(&ddec, (size_t)nframes * (len + 64) * sizeof(uint2)));
+        k_viterbi_test<<<nframes, 32>>>(din, dout, ddec, len);
+        CK(cudaDeviceSynchronize());
+        cudaFree(ddec);
+    }
     CK(cudaMemcpy(out, dout, (size_t)nframes * len, cudaMemcpyDeviceToHost));
     cudaFree(din);
     cudaFree(dout);
-    cudaFree(ddec);
     return NRSC5B_OK;
 }
 

@@ -56,10 +56,14 @@ def load_library():
     L.nrsc5b_destroy.argtypes = [vp]
     L.nrsc5b_destroy.restype = None
     L.nrsc5b_reset.argtypes = [vp, ci]
+    L.nrsc5b_rewind.argtypes = [vp]
+    L.nrsc5b_set_profiling.argtypes = [vp, ci]
+    L.nrsc5b_get_kernel_times.argtypes = [vp, vp, vp]
     L.nrsc5b_set_cuda_stream.argtypes = [vp, vp]
     L.nrsc5b_push_cu8.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_push_cu8_device.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_attach_device_input.argtypes = [vp, vp, sz, sz]
+    L.nrsc5b_attach_device_log.argtypes = [vp, vp, sz]
     L.nrsc5b_process.argtypes = [vp]
     L.nrsc5b_synchronize.argtypes = [vp]
     L.nrsc5b_drain.argtypes = [vp, ci, vp, sz, ctypes.POINTER(sz)]
@@ -158,6 +162,19 @@ class Engine:
     def reset(self, stream: int = -1):
         _check(self._L.nrsc5b_reset(self._h, stream), "nrsc5b_reset")
 
+    def rewind(self):
+        _check(self._L.nrsc5b_rewind(self._h), "nrsc5b_rewind")
+
+    def set_profiling(self, on: bool):
+        _check(self._L.nrsc5b_set_profiling(self._h, int(on)), "nrsc5b_set_profiling")
+
+    def kernel_times(self):
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_ulonglong * 4)()
+        _check(self._L.nrsc5b_get_kernel_times(self._h, ms, n), "nrsc5b_get_kernel_times")
+        names = ("prep", "demod", "sync", "p1")
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
+
     def push_cu8(self, stream: int, samples):
         """samples: uint8 numpy array / bytes (host) — length counts uint8 values, multiple of 4."""
         a = np.ascontiguousarray(np.frombuffer(samples, dtype=np.uint8) if isinstance(samples, (bytes, bytearray)) else samples,
@@ -169,6 +186,10 @@ class Engine:
 
     def attach_device_input(self, dev_ptr: int, stride: int, nbytes: int):
         _check(self._L.nrsc5b_attach_device_input(self._h, ctypes.c_void_p(dev_ptr), stride, nbytes), "attach_device_input")
+
+    def attach_device_log(self, dev_ptr: int, stride: int):
+        _check(self._L.nrsc5b_attach_device_log(self._h, ctypes.c_void_p(dev_ptr), stride), "attach_device_log")
+        self._log_cap = stride + 64
 
     def process(self):
         _check(self._L.nrsc5b_process(self._h), "nrsc5b_process")
