@@ -68,6 +68,9 @@ struct StreamState {
     // P1 hand-off sync -> p1 kernel
     int p1_ready;
     int p1_slow;               // this frame needs saturating Viterbi arithmetic
+    unsigned p1_rec;           // log offset of the reserved BER payload (FRAME record follows)
+    int p1_errs;               // channel bit errors counted so far
+    int p1_done;               // k_p1_fin CTAs finished
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
     // output log cursor
     unsigned log_len;
@@ -98,7 +101,7 @@ struct DevPtrs {
     float2 *tbuf;              // [S][71280]   band-passed window (coarse acquisition scratch)
     int8_t *vit_in;            // [S][438528]
     uint2 *vit_dec;            // [S][146240]
-    uint8_t *p1_bits;          // [S][146176]  decoded bits, one per byte
+    uint32_t *p1_bits;         // [S][146176/32] decoded (still scrambled) bits, bit k of word w = frame bit 32w+k
     uint8_t *log;              // [S][log_cap]
     const float *shape;        // [2160]
     const float2 *twid;        // [2048]  exp(-2*pi*i*k/2048)

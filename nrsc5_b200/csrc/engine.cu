@@ -260,12 +260,13 @@ struct SyncSmem {
     float phs[2 * MAXREF][BLK];                 // Costas phase per reference and symbol
     float smag[2 * MAXREF];
     float part_lb[BLK], part_ub[BLK];
+    float mer_lb[8][BLK], mer_ub[8][BLK];
     float2 zero_row[BLK];
     float tmp_phs[32][BLK];                     // scratch phases for the CFO search
     int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
     int offs[32];
     int8_t vit[PIDS_LEN * 3];
-    uint2 dec[PIDS_LEN + 64];
+    uint2 dec[PIDS_LEN + 64];                    // 9 groups x 16 lanes of decision history
     float mult_lb, mult_ub;
     int flag;
 };
@@ -282,21 +283,21 @@ __device__ void costas_row(float2 *z, int zstride, float *phs, float &cfreq, flo
     const signed char pat[BLK] = { -1, 1, -1, -1, -1, 1, 1, 0, 1, -1, 0, 0, 0, -1, -1, 0,
                                    0, 0, 0, 0, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1 };
     const float cfo_freq = (float)(2 * M_PI * cfo * NCP / NFFT);
+    const float PI_F = 3.14159274101257324f;                  // smallest float above pi: (ph > M_PI) <=> (ph >= PI_F)
     float f = cfreq, ph = cphase;
     for (int n = 0; n < BLK; n++) {
-        float2 v = z[n * zstride];
-        float2 v2 = cmulf(v, v);
-        float2 e2 = cexp_j(-(2.0f * ph));
-        float2 w = cmulf(v2, e2);
-        float error = atan2f(w.y, w.x) * 0.5f;
+        const float2 v = z[n * zstride];
+        // u = v * exp(-j*ph); the loop error arg(v^2 * exp(-2j*ph)) / 2 equals arg(u^2) / 2
+        const float2 u = cmulf(v, cexp_j(-ph));
+        const float error = atan2f((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y) * 0.5f;
         phs[n] = ph;
-        z[n * zstride] = cmulf(v, cexp_j(-ph));
+        z[n * zstride] = u;
         f += beta * error;
         if (f > 0.5f) f = 0.5f;
         if (f < -0.5f) f = -0.5f;
         ph += (f + cfo_freq) + (alpha * error);
-        if ((double)ph > M_PI) ph = (float)((double)ph - 2 * M_PI);
-        if ((double)ph < -M_PI) ph = (float)((double)ph + 2 * M_PI);
+        if (ph >= PI_F) ph = (float)((double)ph - 2 * M_PI);
+        if (ph <= -PI_F) ph = (float)((double)ph + 2 * M_PI);
     }
     float x = 0;
     for (int n = 0; n < BLK; n++) x += z[n * zstride].x * (float)pat[n];
@@ -550,18 +551,27 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
             }
         }
         __syncthreads();
-        // modulation error per symbol, then combined in symbol order (sync.c:465-488)
-        if (t < BLK) {
+        // modulation error (sync.c:465-488): 8 threads per symbol take the partitions round-robin, the
+        // partial sums are then combined in a fixed order (per symbol, then over symbols)
+        {
+            const int n = t & (BLK - 1), g = t >> 5;           // SYNC_THREADS == 8 * BLK
             float e_lb = 0, e_ub = 0;
-            for (int i = 0; i < ppb; i++)
+            for (int i = g; i < ppb; i += SYNC_THREADS / BLK)
                 for (int j = 1; j < PW; j++) {
-                    float2 c = sm.z[compact_of_bin(LB0 + PW * i + j) * ZLD + t];
+                    float2 c = sm.z[compact_of_bin(LB0 + PW * i + j) * ZLD + n];
                     float dx = (c.x >= 0 ? 1.0f : -1.0f) - c.x, dy = (c.y >= 0 ? 1.0f : -1.0f) - c.y;
                     e_lb += dx * dx + dy * dy;
-                    c = sm.z[compact_of_bin(UB1 - PW * i - PW + j) * ZLD + t];
+                    c = sm.z[compact_of_bin(UB1 - PW * i - PW + j) * ZLD + n];
                     dx = (c.x >= 0 ? 1.0f : -1.0f) - c.x; dy = (c.y >= 0 ? 1.0f : -1.0f) - c.y;
                     e_ub += dx * dx + dy * dy;
                 }
+            sm.mer_lb[g][n] = e_lb;
+            sm.mer_ub[g][n] = e_ub;
+        }
+        __syncthreads();
+        if (t < BLK) {
+            float e_lb = 0, e_ub = 0;
+            for (int g = 0; g < SYNC_THREADS / BLK; g++) { e_lb += sm.mer_lb[g][t]; e_ub += sm.mer_ub[g][t]; }
             sm.part_lb[t] = e_lb;
             sm.part_ub[t] = e_ub;
         }
@@ -593,13 +603,16 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
         {
             int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
             const float mlb = sm.mult_lb, mub = sm.mult_ub;
-            for (int o = t; o < PM_BLOCK; o += SYNC_THREADS) {
-                int n = o / 720, rem = o - n * 720;
-                int part = rem / 36, c = rem - part * 36;
-                int j = 1 + (c >> 1);
-                int b = part < 10 ? LB0 + PW * part + j : (UB1 - 10 * PW) + PW * (part - 10) + j;
-                float2 v = sm.z[compact_of_bin(b) * ZLD + n];
-                pm[o] = soft_demap((c & 1) ? v.y : v.x, part < 10 ? mlb : mub);
+            for (int col = t; col < 720; col += SYNC_THREADS) {      // one matrix column per thread, all 32 symbols
+                const int part = col / 36, c = col - part * 36;
+                const int j = 1 + (c >> 1);
+                const int b = part < 10 ? LB0 + PW * part + j : (UB1 - 10 * PW) + PW * (part - 10) + j;
+                const float2 *zc = &sm.z[compact_of_bin(b) * ZLD];
+                const float mult = part < 10 ? mlb : mub;
+                for (int n = 0; n < BLK; n++) {
+                    const float2 v = zc[n];
+                    pm[n * 720 + col] = soft_demap((c & 1) ? v.y : v.x, mult);
+                }
             }
         }
         __syncthreads();
@@ -635,8 +648,26 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
         }
         __syncthreads();
         if (t < 32) {
-            int state = viterbi_forward(sm.vit, PIDS_LEN, sm.dec, t);
+            // both half-warps decode the same 80-bit frame (the packed kernel works on two chunks per warp);
+            // FM PIDS soft bits are punctured 1,1,1,1,1,0, so the int16 metrics cannot saturate
+            const int l = t & 15;
+            VitHalf<false> vh;
+            vh.init(l);
+            vitc_run<false>(vh, sm.vit, PIDS_LEN, PIDS_LEN + 64, 0, PIDS_LEN + 64, 0, sm.dec, t < 16, l);
             __syncwarp();
+            // first maximum in state order; lane l holds states 2l, 2l+32 (E) and 2l+1, 2l+33 (O)
+            int v = (short)(vh.E & 0xffff), state = 2 * l;
+            const int w1 = (short)(vh.O & 0xffff);
+            if (w1 > v) { v = w1; state = 2 * l + 1; }
+            int v2 = (short)(vh.E >> 16), idx2 = 2 * l + 32;
+            const int w3 = (short)(vh.O >> 16);
+            if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
+            if (v2 > v) { v = v2; state = idx2; }
+#pragma unroll
+            for (int o = 8; o; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, state, o, 16);
+                if (ov > v || (ov == v && oi < state)) { v = ov; state = oi; }
+            }
             if (t == 0) {
                 uint8_t pk[10];
                 for (int i = 0; i < 10; i++) pk[i] = 0;
@@ -646,7 +677,7 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
                         int bit = ((state >> 5) & 1) ^ p.pn[i];
                         pk[i >> 3] |= (uint8_t)(bit << (7 - (i & 7)));
                     }
-                    state = vit_prev(state, sm.dec[q]);
+                    state = vitc_prev_head(state, sm.dec, q);
                 }
                 uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
                 if (w) for (int i = 0; i < 10; i++) w[i] = pk[i];
@@ -683,7 +714,20 @@ constexpr int P1_NCH = (P1_STEPS + CH_LEN - 1) / CH_LEN;             // 143
 __global__ void __launch_bounds__(256) k_p1_gather(DevPtrs p, EngineDims d)
 {
     const int s = blockIdx.y;
-    if (!p.st[s].p1_ready) return;
+    StreamState &st = p.st[s];
+    if (!st.p1_ready) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // reserve the BER and FRAME records now so that they keep their place in the stream's record order
+        uint8_t *w = log_reserve(p, d, s, REC_BER, 4);
+        uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8);
+        st.p1_rec = (w && fw) ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+        if (fw) {
+            reinterpret_cast<uint32_t *>(fw)[0] = 0;            // P1 logical channel
+            reinterpret_cast<uint32_t *>(fw)[1] = P1_LEN;
+        }
+        st.p1_errs = 0;
+        st.p1_done = 0;
+    }
     const int8_t *pm = p.pm + (size_t)s * 16 * PM_BLOCK;
     int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P1_VIT; o += gridDim.x * blockDim.x) {
@@ -692,77 +736,84 @@ __global__ void __launch_bounds__(256) k_p1_gather(DevPtrs p, EngineDims d)
     }
 }
 
+constexpr int FIN_BYTES = 1024;                                      // packed PDU bytes per CTA
+constexpr int FIN_CTAS = (P1_LEN / 8 + FIN_BYTES - 1) / FIN_BYTES;   // 18
+
+__device__ __forceinline__ unsigned p1_bit(const uint32_t *bw, int i)
+{
+    return (bw[i >> 5] >> (i & 31)) & 1u;
+}
+
 __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
 {
-    const int s = blockIdx.x, t = threadIdx.x;
+    const int s = blockIdx.y, t = threadIdx.x;
     StreamState &st = p.st[s];
     if (!st.p1_ready) return;
     __shared__ int red[P1_THREADS];
-    __shared__ uint8_t *sh_w;
+    __shared__ int sh_last;
     __shared__ uint8_t hdr[96];
     __shared__ uint8_t blk[255];
     const int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
-    uint8_t *bits = p.p1_bits + (size_t)s * P1_LEN;
-    {
-        int errs = 0;
-        for (int i = t; i < P1_LEN; i += P1_THREADS) {
-            unsigned reg = 0;
+    const uint32_t *bw = p.p1_bits + (size_t)s * (P1_LEN / 32);
+    uint8_t *rec = st.p1_rec == 0xffffffffu ? nullptr : p.log + (size_t)s * d.log_cap + st.p1_rec;
+    uint8_t *frame = rec ? rec + 4 + 8 + 8 : nullptr;                // BER payload (4) | FRAME header (8) | lc,nbits (8) | bytes
+    const int byte0 = blockIdx.x * FIN_BYTES, byte1 = min(P1_LEN / 8, byte0 + FIN_BYTES);
+    int errs = 0;
+    for (int bi = byte0 + t; bi < byte1; bi += P1_THREADS) {
+        // 14 decoded bits around this byte: bits 8*bi-6 .. 8*bi+7 (tail-biting wrap at the frame start)
+        unsigned win = 0;
 #pragma unroll
-            for (int b = 0; b < 7; b++) {
-                int idx = i - 6 + b;
-                if (idx < 0) idx += P1_LEN;
-                reg |= (unsigned)bits[idx] << b;
-            }
+        for (int k = 0; k < 14; k++) {
+            int idx = 8 * bi - 6 + k;
+            if (idx < 0) idx += P1_LEN;
+            win |= p1_bit(bw, idx) << k;
+        }
+        unsigned packed = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = 8 * bi + k;
+            const unsigned reg = (win >> k) & 0x7f;              // bits i-6 .. i, newest at bit 6 (decode.c:243-249)
             const int8_t *c = vin + 3 * i;
             const int j = 3 * i;
             if ((j % 6) != 5 && ((c[0] > 0) != (int)(__popc(reg & 0133u) & 1))) errs++;
             if (((j + 1) % 6) != 5 && ((c[1] > 0) != (int)(__popc(reg & 0171u) & 1))) errs++;
             if (((j + 2) % 6) != 5 && ((c[2] > 0) != (int)(__popc(reg & 0165u) & 1))) errs++;
+            packed |= (((win >> (k + 6)) & 1u) ^ p.pn[i]) << (7 - k);   // descramble (decode.c:279-294), MSB first
         }
-        red[t] = errs;
+        if (frame) frame[bi] = (uint8_t)packed;
+    }
+    red[t] = errs;
+    __syncthreads();
+    for (int o = P1_THREADS / 2; o; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
         __syncthreads();
-        for (int o = P1_THREADS / 2; o; o >>= 1) {
-            if (t < o) red[t] += red[t + o];
-            __syncthreads();
-        }
     }
     if (t == 0) {
-        float ber = (float)red[0] / (float)P1_ENC;
-        uint8_t *w = log_reserve(p, d, s, REC_BER, 4);
-        if (w) *reinterpret_cast<float *>(w) = ber;
-        sh_w = log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8);
-        if (sh_w) {
-            reinterpret_cast<uint32_t *>(sh_w)[0] = 0;          // P1 logical channel
-            reinterpret_cast<uint32_t *>(sh_w)[1] = P1_LEN;
-        }
+        atomicAdd(&st.p1_errs, red[0]);
+        __threadfence();
+        sh_last = atomicAdd(&st.p1_done, 1) == FIN_CTAS - 1;
     }
     __syncthreads();
-    for (int i = t; i < P1_LEN; i += P1_THREADS) bits[i] ^= p.pn[i];
-    __syncthreads();
-    if (sh_w) {
-        for (int b = t; b < P1_LEN / 8; b += P1_THREADS) {
-            unsigned v = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) v |= (unsigned)bits[8 * b + j] << (7 - j);
-            sh_w[8 + b] = (uint8_t)v;
-        }
-    }
+    if (!sh_last) return;
+    // last CTA of this stream: BER record, and the L2 feedback predicate
+    // (frame.c:645-714 PCI, :146-156 has_audio, :527-541 header RS check)
+    __threadfence();
     if (t < 96) {
-        unsigned v = 0;
-        for (int j = 0; j < 8; j++) {
-            unsigned i = 8u * t + j;
-            v |= (unsigned)bits[(i & ~7u) + 7 - (i & 7)] << (7 - j);
-        }
-        hdr[t] = (uint8_t)v;
+        // PDU byte n of frame_push() is the bit-reversed packed byte n (the reference swaps the bit order per byte)
+        unsigned v = frame ? frame[t] : 0;
+        hdr[t] = (uint8_t)(__brev(v) >> 24);
     }
     __syncthreads();
     if (t == 0) {
+        if (rec) *reinterpret_cast<float *>(rec) = (float)atomicAdd(&st.p1_errs, 0) / (float)P1_ENC;
         unsigned pci = 0;
         for (int h = 0; h < 24; h++) {
-            unsigned i = 116176u + 1248u * h;
-            pci |= (unsigned)bits[(i & ~7u) + 7 - (i & 7)] << (23 - h);
+            const unsigned i = 116176u + 1248u * h;
+            const unsigned phys = (i & ~7u) + 7 - (i & 7);
+            const unsigned bit = (p1_bit(bw, (int)phys) ^ p.pn[phys]) & 1u;
+            pci |= bit << (23 - h);
         }
-        bool has_audio = (pci & 0xFFFFFC) != (0x3634CE & 0xFFFFFC);
+        const bool has_audio = (pci & 0xFFFFFC) != (0x3634CE & 0xFFFFFC);
         if (has_audio && !fix_header_96(hdr, blk)) set_state(p, d, s, ST_NONE);
         st.p1_ready = 0;
         st.p1_slow = 0;
@@ -825,8 +876,7 @@ __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
 // ===========================================================================
 using namespace nb;
 
-static size_t vitc_ends_smem(int nch) { return (size_t)nch * (VITC_HEAD / 16) * 16 * sizeof(uint2) + (size_t)nch * 64; }
-static size_t vitc_emit_smem() { return (size_t)VITC_EMIT_WARPS * CH_LEN * sizeof(uint2); }
+static size_t vitc_emit_smem() { return (size_t)VITC_EMIT_WARPS * VITC_EMIT_STEPS * sizeof(uint2); }
 
 #define CK(x)                                                                                      \
     do {                                                                                           \
@@ -855,7 +905,7 @@ struct nrsc5b_engine {
     std::vector<void *> allocs;
     int profiling;
     uint2 *vspec, *vend;
-    int *tbend;
+    int *tbend, *hstate;
     cudaEvent_t pev[5];
     double kernel_ms[4];
     unsigned long long kernel_n[4];
@@ -992,7 +1042,8 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     rc = dev_alloc(e, &e->vspec, (size_t)S * P1_NCH * 16); if (rc) { nrsc5b_destroy(e); return rc; }
     rc = dev_alloc(e, &e->vend, (size_t)S * P1_NCH * 16); if (rc) { nrsc5b_destroy(e); return rc; }
     rc = dev_alloc(e, &e->tbend, (size_t)S * P1_NCH); if (rc) { nrsc5b_destroy(e); return rc; }
-    DA(p1_bits, uint8_t, (size_t)S * P1_LEN);
+    rc = dev_alloc(e, &e->hstate, (size_t)S * P1_NCH); if (rc) { nrsc5b_destroy(e); return rc; }
+    DA(p1_bits, uint32_t, (size_t)S * (P1_LEN / 32));
     DA(log, uint8_t, (size_t)S * e->dims.log_cap);
     {
         // tables
@@ -1051,7 +1102,6 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     }
     e->sync_smem = sizeof(SyncSmem);
     if (cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->sync_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vitc_ends, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_ends_smem(P1_NCH)) != cudaSuccess ||
         cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess) {
         nrsc5b_destroy(e);
         return NRSC5B_ECUDA;
@@ -1183,8 +1233,9 @@ static VitcArgs p1_vitc_args(nrsc5b_engine *e)
     a.dec = e->dp.vit_dec;
     a.vspec = e->vspec;
     a.vend = e->vend;
+    a.hstate = e->hstate;
     a.tbend = e->tbend;
-    a.bits = e->dp.p1_bits;
+    a.bitsw = e->dp.p1_bits;
     a.ready = &e->dp.st[0].p1_ready;
     a.slow = &e->dp.st[0].p1_slow;
     a.ready_stride = (int)(sizeof(StreamState) / sizeof(int));
@@ -1199,7 +1250,7 @@ static void launch_vitc(const VitcArgs &a, int nframes, cudaStream_t stream)
 {
     dim3 gf((a.nch + 2 * VITC_FWD_WARPS - 1) / (2 * VITC_FWD_WARPS), nframes);
     k_vitc_fwd<<<gf, VITC_FWD_WARPS * 32, 0, stream>>>(a);
-    k_vitc_ends<<<nframes, VITC_ENDS_THREADS, vitc_ends_smem(a.nch), stream>>>(a);
+    k_vitc_ends<<<nframes, 32, 0, stream>>>(a);
     dim3 ge((a.nch + VITC_EMIT_WARPS - 1) / VITC_EMIT_WARPS, nframes);
     k_vitc_emit<<<ge, VITC_EMIT_WARPS * 32, vitc_emit_smem(), stream>>>(a);
 }
@@ -1209,7 +1260,7 @@ static void launch_p1(nrsc5b_engine *e)
     const int S = e->dims.nstreams;
     k_p1_gather<<<dim3(16, S), 256, 0, e->stream>>>(e->dp, e->dims);
     launch_vitc(p1_vitc_args(e), S, e->stream);
-    k_p1_fin<<<S, P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
+    k_p1_fin<<<dim3(FIN_CTAS, S), P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
     e->stats.kernel_launches += 5;
 }
 
@@ -1375,7 +1426,7 @@ extern "C" int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int
     CK(cudaMalloc(&din, nin));
     CK(cudaMalloc(&dout, (size_t)nframes * len));
     CK(cudaMemcpy(din, in, nin, cudaMemcpyHostToDevice));
-    if (len >= 2048 && (len % 16) == 0) {
+    if (len >= 2048 && (len % 32) == 0) {
         // chunk-parallel exact decoder (the engine's P1 path)
         VitcArgs a;
         a.len = len;
@@ -1387,19 +1438,25 @@ extern "C" int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int
         CK(cudaMalloc(&a.vspec, (size_t)nframes * a.nch * 16 * sizeof(uint2)));
         CK(cudaMalloc(&a.vend, (size_t)nframes * a.nch * 16 * sizeof(uint2)));
         CK(cudaMalloc(&a.tbend, (size_t)nframes * a.nch * sizeof(int)));
+        CK(cudaMalloc(&a.hstate, (size_t)nframes * a.nch * sizeof(int)));
+        uint32_t *dbw = nullptr;
+        CK(cudaMalloc(&dbw, (size_t)nframes * (len / 32) * sizeof(uint32_t)));
         CK(cudaMalloc(&dflags, (size_t)nframes * 2 * sizeof(int)));
         std::vector<int> fl(2 * (size_t)nframes, 0);
         for (int i = 0; i < nframes; i++) fl[i] = 1;
         CK(cudaMemcpy(dflags, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
         a.vin = din;
-        a.bits = dout;
+        a.bitsw = dbw;
         a.ready = dflags;
         a.slow = dflags + nframes;
-        CK(cudaFuncSetAttribute(k_vitc_ends, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_ends_smem(a.nch)));
         CK(cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()));
         launch_vitc(a, nframes, 0);
+        {
+            size_t nb = (size_t)nframes * len;
+            k_vitc_unpack<<<(unsigned)((nb + 255) / 256), 256>>>(dbw, dout, nb);
+        }
         CK(cudaDeviceSynchronize());
-        cudaFree(a.dec); cudaFree(a.vspec); cudaFree(a.vend); cudaFree(a.tbend); cudaFree(dflags);
+        cudaFree(a.dec); cudaFree(a.vspec); cudaFree(a.vend); cudaFree(a.tbend); cudaFree(a.hstate); cudaFree(dflags); cudaFree(dbw);
     } else {
         uint2 *ddec = nullptr;
         CK(cudaMalloc(&ddec, (size_t)nframes * (len + 64) * sizeof(uint2)));

@@ -25,6 +25,7 @@ namespace nb {
 constexpr int CH_LEN = 1024;
 constexpr int CH_WARM = 256;
 constexpr int VITC_NORM = 32767 / (3 * 127) - 7;                 // 79
+constexpr int VITC_HEAD_STEPS = 128;
 
 __device__ __forceinline__ unsigned vadd16(unsigned a, unsigned b)
 {
@@ -130,7 +131,8 @@ struct VitHalf {
 // values of this half's frame; dec = that frame's decision array.
 template <bool SAT>
 __device__ inline void vitc_run(VitHalf<SAT> &vh, const int8_t *__restrict__ vin, int len, int total,
-                                int s_from, int nsteps, int s_store, uint2 *__restrict__ dec, bool store_ok, int l)
+                                int s_from, int nsteps, int s_store, uint2 *__restrict__ dec, bool store_ok, int l,
+                                uint2 *head = nullptr)
 {
     const unsigned hmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
     for (int base = 0; base < nsteps; base += 16) {
@@ -154,16 +156,21 @@ __device__ inline void vitc_run(VitHalf<SAT> &vh, const int8_t *__restrict__ vin
         const int g0 = s_from + base;                    // groups are 16-aligned by construction
         if (store_ok && n == 16 && g0 >= s_store && g0 < total)
             dec[(size_t)(g0 >> 4) * 16 + l] = make_uint2(vh.accA, vh.accB);
+        if (head && g0 >= s_store && g0 < s_store + VITC_HEAD_STEPS)      // first steps of the chunk, kept on chip
+            head[((g0 - s_store) >> 4) * 16 + l] = make_uint2(vh.accA, vh.accB);
     }
 }
 
 // ===========================================================================
-// Kernels.  A "frame" f has 3*len soft values at vin + f*3*len, total = len+64
-// trellis steps, nch = ceil(total / CH_LEN) chunks, and per-frame work areas:
-//   dec   [nch*CH_LEN]   uint2  decision history (layout above)
-//   vspec [nch][16]      uint2  metrics (E,O per lane) at each chunk start, speculative
-//   vend  [nch][16]      uint2  metrics at each chunk end
-//   tbend [nch]          int    survivor state after the last step of each chunk
+// Kernels.  A "frame" f has 3*len soft values at vin + f*3*len (len % 32 == 0),
+// total = len+64 trellis steps, nch = ceil(total / CH_LEN) chunks, and per-frame
+// work areas:
+//   dec    [nch*CH_LEN + VITC_HEAD] uint2  decision history (layout above)
+//   vspec  [nch][16]      uint2  metrics (E,O per lane) at each chunk start, speculative
+//   vend   [nch][16]      uint2  metrics at each chunk end
+//   hstate [nch]          int    state at the chunk's lower boundary found by the merge trace (-1: no merge)
+//   tbend  [nch]          int    survivor state after the last step of each chunk
+//   bitsw  [len/32]       u32    decoded bits, bit k of word w = frame bit 32w+k
 // ready[f*ready_stride] != 0 selects the frames to decode; slow[f*ready_stride]
 // is set when a frame must use saturating arithmetic.
 // ===========================================================================
@@ -172,8 +179,9 @@ struct VitcArgs {
     uint2 *dec;
     uint2 *vspec;
     uint2 *vend;
+    int *hstate;
     int *tbend;
-    uint8_t *bits;          // [len] decoded bits per frame, one per byte
+    uint32_t *bitsw;
     const int *ready;
     int *slow;
     int ready_stride;       // in ints
@@ -183,12 +191,22 @@ struct VitcArgs {
 };
 
 constexpr int VITC_FWD_WARPS = 4;                      // 8 chunks per CTA
+constexpr int VITC_HEAD = VITC_HEAD_STEPS;               // look-back that makes all 64 survivors merge (checked, not assumed)
+
+__device__ __forceinline__ int vitc_prev_head(int state, const uint2 *hd, int q)
+{
+    const int ll = state & 15, qq = state >> 4;
+    const uint2 w = hd[(q >> 4) * 16 + ll];
+    const unsigned word = (qq & 2) ? w.y : w.x;
+    return ((state << 1) & 62) | (int)((word >> (((qq & 1) << 4) + (q & 15))) & 1u);
+}
 
 __global__ void __launch_bounds__(VITC_FWD_WARPS * 32) k_vitc_fwd(VitcArgs a)
 {
     const int f = blockIdx.y;
     if (!a.ready[(size_t)f * a.ready_stride]) return;
     __shared__ int sh_flag;
+    __shared__ uint2 sh_head[2 * VITC_FWD_WARPS][VITC_HEAD];      // first VITC_HEAD steps of each chunk
     const int t = threadIdx.x, lane = t & 31, l = lane & 15, half = lane >> 4, warp = t >> 5;
     const int total = a.len + 64;
     const int8_t *vin = a.vin + (size_t)f * 3 * a.len;
@@ -229,8 +247,29 @@ __global__ void __launch_bounds__(VITC_FWD_WARPS * 32) k_vitc_fwd(VitcArgs a)
     // warm-up from zero metrics (chunk 0 replays zero soft values: the true initial condition)
     vitc_run<false>(vh, vin, a.len, total, cc * CH_LEN - CH_WARM, CH_WARM, 0, dec, false, l);
     if (valid) a.vspec[((size_t)f * a.nch + cc) * 16 + l] = make_uint2(vh.E, vh.O);
-    vitc_run<false>(vh, vin, a.len, total, cc * CH_LEN, CH_LEN, cc * CH_LEN, dec, valid, l);
+    uint2 *head = sh_head[warp * 2 + half];
+    vitc_run<false>(vh, vin, a.len, total, cc * CH_LEN, CH_LEN, cc * CH_LEN, dec, valid, l, head);
     if (valid) a.vend[((size_t)f * a.nch + cc) * 16 + l] = make_uint2(vh.E, vh.O);
+    __syncwarp();
+    // merge trace over the chunk head: every survivor at step lo+VITC_HEAD-1 walked back to the chunk's
+    // lower boundary; if all 64 agree, that state lies on the final path whatever happens later
+    {
+        const int n = min(VITC_HEAD, total - cc * CH_LEN);
+        int first = -1;
+        bool same = true;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int state = l + 16 * r;
+            for (int q = n - 1; q >= 0; q--) state = vitc_prev_head(state, head, q);
+            if (r == 0) first = state;
+            same &= state == first;
+        }
+        const int ref = __shfl_sync(0xffffffffu, first, 0, 16);
+        same &= first == ref;
+        const unsigned hm = half ? 0xffff0000u : 0x0000ffffu;
+        const bool all = (__ballot_sync(0xffffffffu, same) & hm) == hm;
+        if (valid && l == 0) a.hstate[(size_t)f * a.nch + cc] = all ? ref : -1;
+    }
 }
 
 __device__ __forceinline__ bool vitc_same_shape(uint2 x, uint2 y)
@@ -245,114 +284,88 @@ __device__ __forceinline__ bool vitc_same_shape(uint2 x, uint2 y)
     return __all_sync(0xffffffffu, ok);
 }
 
-constexpr int VITC_HEAD = 128;                         // steps of every chunk head staged for the merge trace
-constexpr int VITC_ENDS_THREADS = 256;
-
-__device__ __forceinline__ int vitc_prev_head(int state, const uint2 *hd, int q)
+// One warp per frame: accept / repair the speculative chunks, pick the end state,
+// and fix the survivor state at every chunk boundary.
+__global__ void __launch_bounds__(32) k_vitc_ends(VitcArgs a)
 {
-    const int ll = state & 15, qq = state >> 4;
-    const uint2 w = hd[(q >> 4) * 16 + ll];
-    const unsigned word = (qq & 2) ? w.y : w.x;
-    return ((state << 1) & 62) | (int)((word >> (((qq & 1) << 4) + (q & 15))) & 1u);
-}
-
-// One CTA per frame: accept / repair the speculative chunks, pick the end state,
-// and find the survivor state at every chunk boundary.  Dynamic shared memory:
-// nch * (VITC_HEAD/16) * 16 uint2  +  nch * 64 bytes.
-__global__ void __launch_bounds__(VITC_ENDS_THREADS) k_vitc_ends(VitcArgs a)
-{
-    extern __shared__ __align__(16) unsigned char vitc_smem[];
     const int f = blockIdx.x;
     if (!a.ready[(size_t)f * a.ready_stride]) return;
-    const int t = threadIdx.x, lane = t & 31, l = lane & 15;
+    const int t = threadIdx.x, l = t & 15;
     const int total = a.len + 64, nch = a.nch;
-    constexpr int gper = VITC_HEAD / 16;
-    uint2 *heads = reinterpret_cast<uint2 *>(vitc_smem);                          // [nch][gper][16]
-    uint8_t *mstate = vitc_smem + (size_t)nch * gper * 16 * sizeof(uint2);        // [nch][64]
     const int8_t *vin = a.vin + (size_t)f * 3 * a.len;
     uint2 *dec = a.dec + (size_t)f * a.dec_stride;
-    uint2 *vspec = a.vspec + (size_t)f * nch * 16, *vend = a.vend + (size_t)f * nch * 16;
-    int *tbend = a.tbend + (size_t)f * nch;
+    const uint2 *vspec = a.vspec + (size_t)f * nch * 16, *vend = a.vend + (size_t)f * nch * 16;
+    int *tbend = a.tbend + (size_t)f * nch, *hstate = a.hstate + (size_t)f * nch;
 
-    if (t < 32) {
-        uint2 cur;
-        if (a.slow[(size_t)f * a.ready_stride]) {
-            // exact saturating arithmetic, sequential over the whole frame
-            VitHalf<true> vs;
-            vs.init(l);
-            vitc_run<true>(vs, vin, a.len, total, 0, total, 0, dec, true, l);
-            cur = make_uint2(vs.E, vs.O);
-        } else {
-            cur = vend[l];
-            for (int c = 1; c < nch; c++) {
-                const uint2 sp = vspec[(size_t)c * 16 + l];
-                if (vitc_same_shape(cur, sp)) {
-                    cur = vend[(size_t)c * 16 + l];
-                } else {                               // speculation missed: redo this chunk from the true metrics
-                    VitHalf<false> vh;
-                    vh.init(l);
-                    vh.E = cur.x;
-                    vh.O = cur.y;
-                    vitc_run<false>(vh, vin, a.len, total, c * CH_LEN, CH_LEN, c * CH_LEN, dec, true, l);
-                    cur = make_uint2(vh.E, vh.O);
-                }
+    uint2 cur;
+    if (a.slow[(size_t)f * a.ready_stride]) {
+        // exact saturating arithmetic, sequential over the whole frame
+        VitHalf<true> vs;
+        vs.init(l);
+        vitc_run<true>(vs, vin, a.len, total, 0, total, 0, dec, true, l);
+        cur = make_uint2(vs.E, vs.O);
+        for (int c = t; c < nch; c += 32) hstate[c] = -1;
+    } else {
+        cur = vend[l];
+        uint2 sp_next = vspec[(size_t)(nch > 1 ? 1 : 0) * 16 + l], ve_next = vend[(size_t)(nch > 1 ? 1 : 0) * 16 + l];
+        for (int c = 1; c < nch; c++) {
+            const uint2 sp = sp_next, ve = ve_next;
+            if (c + 1 < nch) {                         // prefetch the next chunk's vectors
+                sp_next = vspec[(size_t)(c + 1) * 16 + l];
+                ve_next = vend[(size_t)(c + 1) * 16 + l];
+            }
+            if (vitc_same_shape(cur, sp)) {
+                cur = ve;
+            } else {                                   // speculation missed: redo this chunk from the true metrics
+                VitHalf<false> vh;
+                vh.init(l);
+                vh.E = cur.x;
+                vh.O = cur.y;
+                vitc_run<false>(vh, vin, a.len, total, c * CH_LEN, CH_LEN, c * CH_LEN, dec, true, l);
+                cur = make_uint2(vh.E, vh.O);
+                if (t == 0) hstate[c] = -1;            // its merge trace was made on discarded decisions
             }
         }
-        // first maximum in state order (reference src/conv_dec.c:310-317); lane l holds states 2l, 2l+32, 2l+1, 2l+33
-        int v = (short)(cur.x & 0xffff), idx = 2 * l;
-        const int w1 = (short)(cur.y & 0xffff);
-        if (w1 > v) { v = w1; idx = 2 * l + 1; }
-        int v2 = (short)(cur.x >> 16), idx2 = 2 * l + 32;
-        const int w3 = (short)(cur.y >> 16);
-        if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
-        if (v2 > v) { v = v2; idx = idx2; }                // equal values: the lower state index (idx) stays
+    }
+    // first maximum in state order (reference src/conv_dec.c:310-317); lane l holds states 2l, 2l+32, 2l+1, 2l+33
+    int v = (short)(cur.x & 0xffff), idx = 2 * l;
+    const int w1 = (short)(cur.y & 0xffff);
+    if (w1 > v) { v = w1; idx = 2 * l + 1; }
+    int v2 = (short)(cur.x >> 16), idx2 = 2 * l + 32;
+    const int w3 = (short)(cur.y >> 16);
+    if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
+    if (v2 > v) { v = v2; idx = idx2; }                    // equal values: the lower state index stays
 #pragma unroll
-        for (int o = 8; o; o >>= 1) {
-            const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, idx, o, 16);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        if (t == 0) tbend[nch - 1] = idx;
+    for (int o = 8; o; o >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, idx, o, 16);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
     }
-    __syncthreads();                                        // decision repairs above are visible to the CTA
-    // stage the first VITC_HEAD steps of every chunk
-    for (int i = t; i < nch * gper * 16; i += VITC_ENDS_THREADS) {
-        const int c = i / (gper * 16), r = i - c * gper * 16;
-        heads[i] = dec[((size_t)c * (CH_LEN / 16)) * 16 + r];
-    }
-    __syncthreads();
-    // merge trace: walk all 64 survivors back over a chunk head; they land on the state at the chunk boundary
-    for (int item = t; item < (nch - 1) * 64; item += VITC_ENDS_THREADS) {
-        const int c = 1 + (item >> 6), e = item & 63;
-        const int n = min(VITC_HEAD, total - c * CH_LEN);
-        int state = e;
-        const uint2 *hd = heads + (size_t)c * gper * 16;
-        for (int q = n - 1; q >= 0; q--) state = vitc_prev_head(state, hd, q);
-        mstate[c * 64 + e] = (uint8_t)state;
-    }
-    __syncthreads();
-    for (int c = 1 + t; c < nch; c += VITC_ENDS_THREADS) {
-        const int m0 = mstate[c * 64];
-        bool merged = true;
-        for (int e = 1; e < 64; e++) merged &= mstate[c * 64 + e] == m0;
-        tbend[c - 1] = merged ? m0 : -1;
-    }
-    __syncthreads();
-    // rare: some head did not merge within VITC_HEAD steps -> walk back from the next known boundary
+    __syncwarp();
+    __threadfence_block();
     if (t == 0) {
-        for (int c = nch - 2; c >= 0; c--) {
-            if (tbend[c] >= 0) continue;
-            int state = tbend[c + 1];
-            const int hi = min(total, (c + 2) * CH_LEN), lo = (c + 1) * CH_LEN;
-            for (int q = hi - 1; q >= lo; q--) state = vitc_prev(state, dec, q);
-            tbend[c] = state;
+        tbend[nch - 1] = idx;
+        for (int c = nch - 1; c >= 1; c--) {
+            int hs = hstate[c];
+            if (hs < 0) {                              // rare: walk the whole chunk back from its known end state
+                int state = tbend[c];
+                const int hi = min(total, (c + 1) * CH_LEN), lo = c * CH_LEN;
+                for (int q = hi - 1; q >= lo; q--) state = vitc_prev(state, dec, q);
+                hs = state;
+            }
+            tbend[c - 1] = hs;
         }
     }
 }
 
-constexpr int VITC_EMIT_WARPS = 8;                     // one warp per chunk
+constexpr int VITC_EMIT_WARPS = 4;                     // one warp per chunk
+constexpr int VITC_EMIT_STEPS = CH_LEN + VITC_HEAD;    // staged decisions per chunk
 
-// Emit the decoded bits of every chunk from its known end state.  Dynamic shared
-// memory: VITC_EMIT_WARPS * CH_LEN * sizeof(uint2).
+// Emit the decoded bits of a chunk from its known end state.  The chunk is cut
+// into 32 segments of 32 steps, one per lane; each lane *guesses* its segment's
+// end state by walking an arbitrary survivor back over the VITC_HEAD steps that
+// follow the segment, emits its 32 bits, and the guesses are then checked
+// against the neighbouring segment's start state from the (known) chunk end
+// downwards; a wrong guess is repaired by re-walking that segment.
 __global__ void __launch_bounds__(VITC_EMIT_WARPS * 32) k_vitc_emit(VitcArgs a)
 {
     extern __shared__ __align__(16) unsigned char vitc_smem[];
@@ -362,30 +375,57 @@ __global__ void __launch_bounds__(VITC_EMIT_WARPS * 32) k_vitc_emit(VitcArgs a)
     const int c = blockIdx.x * VITC_EMIT_WARPS + warp;
     if (c >= a.nch) return;
     const int total = a.len + 64;
-    uint2 *sd = reinterpret_cast<uint2 *>(vitc_smem) + (size_t)warp * CH_LEN;
+    uint2 *sd = reinterpret_cast<uint2 *>(vitc_smem) + (size_t)warp * VITC_EMIT_STEPS;
     const uint2 *dec = a.dec + (size_t)f * a.dec_stride + (size_t)c * CH_LEN;
-    const int lo = c * CH_LEN, hi = min(total, lo + CH_LEN);
-    const int n = hi - lo;
-    for (int i = lane; i < n; i += 32) sd[i] = dec[i];
+    const int lo = c * CH_LEN;
+    const int n = min(total - lo, CH_LEN);             // steps of this chunk
+    const int nst = min(total - lo, VITC_EMIT_STEPS);  // staged steps (incl. look-ahead into the next chunk)
+    for (int i = lane; i < nst; i += 32) sd[i] = dec[i];
     __syncwarp();
-    uint8_t *bits = a.bits + (size_t)f * a.len;
-    // lane 0 walks the survivor; 32 decoded bits at a time are handed to the warp for a coalesced store
-    int state = a.tbend[(size_t)f * a.nch + c];
-    for (int top = n; top > 0; top -= 32) {
-        unsigned word = 0;                              // bit k = decoded bit of step (lo + top - 32 + k)
-        if (lane == 0) {
-            for (int k = 31; k >= 0; k--) {
-                const int q = top - 32 + k;
-                if (q < 0) break;
-                word |= (unsigned)((state >> 5) & 1) << k;
-                state = vitc_prev_head(state, sd, q);
-            }
+    const int true_end = a.tbend[(size_t)f * a.nch + c];
+    const int seg_end = 32 * lane + 31;                // local step index of this lane's last step
+    const bool have = 32 * lane < n;
+    auto walk = [&](int state, int from, int to) {     // state after local step `from` -> state after step `to`-... down to > to
+        for (int q = from; q > to; q--) state = vitc_prev_head(state, sd, q);
+        return state;
+    };
+    int g;                                             // state after local step seg_end
+    if (!have) g = 0;
+    else if (seg_end == n - 1) g = true_end;
+    else if (seg_end + VITC_HEAD >= nst) g = walk(true_end, n - 1, seg_end);      // frame end inside the look-ahead (last chunk)
+    else g = walk(0, seg_end + VITC_HEAD, seg_end);                               // guess
+    unsigned word = 0;
+    int b = 0;                                         // state before the segment's first step
+    auto emit = [&](int gstate) {
+        int state = gstate;
+        unsigned w = 0;
+        for (int k = 31; k >= 0; k--) {
+            w |= (unsigned)((state >> 5) & 1) << k;
+            state = vitc_prev_head(state, sd, 32 * lane + k);
         }
-        word = __shfl_sync(0xffffffffu, word, 0);
-        const int q = top - 32 + lane;
-        const int sidx = lo + q - 32;                   // bit index in the frame
-        if (q >= 0 && sidx >= 0 && sidx < a.len) bits[sidx] = (uint8_t)((word >> lane) & 1u);
+        word = w;
+        b = state;
+    };
+    if (have) emit(g);
+    // verification from the chunk end downwards
+    const int nseg = (n + 31) / 32;
+    for (;;) {
+        const int bnext = __shfl_down_sync(0xffffffffu, b, 1);
+        const bool bad = have && lane < nseg - 1 && g != bnext;
+        const unsigned m = __ballot_sync(0xffffffffu, bad);
+        if (!m) break;
+        const int jj = 31 - __clz(m);                  // highest wrong segment: its right neighbour is already final
+        if (lane == jj) { g = bnext; emit(g); }
     }
+    const int widx = (lo >> 5) + lane - 1;             // frame bit 32*widx = step lo + 32*lane - 32
+    if (have && widx >= 0 && widx < a.len / 32) a.bitsw[(size_t)f * (a.len / 32) + widx] = word;
+}
+
+// bits (one per byte) from the packed words — used by the stage-level test entry point
+__global__ void k_vitc_unpack(const uint32_t *bitsw, uint8_t *out, size_t nbits)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nbits) out[i] = (uint8_t)((bitsw[i >> 5] >> (i & 31)) & 1u);
 }
 
 }  // namespace nb
