@@ -71,6 +71,9 @@ struct StreamState {
     unsigned p1_rec;           // log offset of the reserved BER payload (FRAME record follows)
     int p1_errs;               // channel bit errors counted so far
     int p1_done;               // k_p1_fin CTAs finished
+    int pids_pending;          // a PIDS frame (block pids_bc) waits to be decoded into the log slot pids_rec
+    int pids_bc;
+    unsigned pids_rec;
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
     // output log cursor
     unsigned log_len;

@@ -265,8 +265,6 @@ struct SyncSmem {
     float tmp_phs[32][BLK];                     // scratch phases for the CFO search
     int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
     int offs[32];
-    int8_t vit[PIDS_LEN * 3];
-    uint2 dec[PIDS_LEN + 64];                    // 9 groups x 16 lanes of decision history
     float mult_lb, mult_ub;
     int flag;
 };
@@ -353,8 +351,13 @@ __device__ __forceinline__ float half_pi_wrap(float a, float b)        // sync.c
 
 __device__ __forceinline__ int8_t soft_demap(float x, float mult)      // sync.c:69-73
 {
-    float c = fmaxf(fminf(x, 1.0f), -1.0f);
-    return (int8_t)lroundf(c * mult);
+    // lroundf semantics (round half away from zero) without the libm call: |v| <= 127 so v - trunc(v) is exact
+    const float v = fmaxf(fminf(x, 1.0f), -1.0f) * mult;
+    int r = __float2int_rz(v);
+    const float f = v - (float)r;
+    if (f >= 0.5f) r++;
+    else if (f <= -0.5f) r--;
+    return (int8_t)r;
 }
 
 __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
@@ -374,9 +377,22 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
     // stage the block's 32x534 spectrum as [bin][symbol]
     {
         const float2 *src = p.bins + (size_t)s * BLK * NBINS;
-        for (int i = t; i < BLK * NBINS; i += SYNC_THREADS) {
-            int sym = i / NBINS, ci = i - sym * NBINS;
-            sm.z[ci * ZLD + sym] = src[i];
+        constexpr int NEL = BLK * NBINS, U = 6;                   // 17088 = 256 * 66 + 192
+        for (int i0 = t; i0 < NEL; i0 += SYNC_THREADS * U) {
+            float2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * SYNC_THREADS;
+                if (i < NEL) v[u] = __ldg(&src[i]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * SYNC_THREADS;
+                if (i < NEL) {
+                    const int sym = i / NBINS, ci = i - sym * NBINS;
+                    sm.z[ci * ZLD + sym] = v[u];
+                }
+            }
         }
         if (t < BLK) sm.zero_row[t] = make_float2(0.f, 0.f);
     }
@@ -518,9 +534,9 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
             for (int k = 1; k < PW; k++) {
                 float fa = (float)k * m19, fb = (float)(PW - k) * m0;
                 float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
-                float den = c * c + dd * dd;
+                const float rden = 19.0f / (c * c + dd * dd);
                 // (19 + 19j) / (c + j dd)
-                float2 C = make_float2((19.0f * c + 19.0f * dd) / den, (19.0f * c - 19.0f * dd) / den);
+                float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
                 zc[k * ZLD] = cmulf(zc[k * ZLD], C);
             }
         }
@@ -629,66 +645,18 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
             }
             __syncthreads();
         }
-        // PIDS: interleaver II + depuncture (decode.c:324-342), Viterbi, descramble
-        {
-            const int8_t *pmall = p.pm + (size_t)s * 16 * PM_BLOCK;
-            const int8_t PMV[20] = { 10, 2, 18, 6, 14, 8, 16, 0, 12, 4, 11, 3, 19, 7, 15, 9, 17, 1, 13, 5 };
-            for (int o = t; o < PIDS_LEN * 3; o += SYNC_THREADS) {
-                int8_t v = 0;
-                if (o % 6 != 5) {
-                    unsigned i = (unsigned)bc * 200 + (unsigned)(o - o / 6);
-                    unsigned part = (unsigned)PMV[i % 20];
-                    unsigned block = i / 200;
-                    unsigned k = (i / 20) % 10 + P1_ENC / 320;
-                    unsigned row = (k * 11) % 32, col = (k * 11 + k / 288) % 36;
-                    v = pmall[(block * 32 + row) * 720 + part * 36 + col];
-                }
-                sm.vit[o] = v;
-            }
-        }
-        __syncthreads();
-        if (t < 32) {
-            // both half-warps decode the same 80-bit frame (the packed kernel works on two chunks per warp);
-            // FM PIDS soft bits are punctured 1,1,1,1,1,0, so the int16 metrics cannot saturate
-            const int l = t & 15;
-            VitHalf<false> vh;
-            vh.init(l);
-            vitc_run<false>(vh, sm.vit, PIDS_LEN, PIDS_LEN + 64, 0, PIDS_LEN + 64, 0, sm.dec, t < 16, l);
-            __syncwarp();
-            // first maximum in state order; lane l holds states 2l, 2l+32 (E) and 2l+1, 2l+33 (O)
-            int v = (short)(vh.E & 0xffff), state = 2 * l;
-            const int w1 = (short)(vh.O & 0xffff);
-            if (w1 > v) { v = w1; state = 2 * l + 1; }
-            int v2 = (short)(vh.E >> 16), idx2 = 2 * l + 32;
-            const int w3 = (short)(vh.O >> 16);
-            if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
-            if (v2 > v) { v = v2; state = idx2; }
-#pragma unroll
-            for (int o = 8; o; o >>= 1) {
-                const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, state, o, 16);
-                if (ov > v || (ov == v && oi < state)) { v = ov; state = oi; }
-            }
-            if (t == 0) {
-                uint8_t pk[10];
-                for (int i = 0; i < 10; i++) pk[i] = 0;
-                for (int q = PIDS_LEN + 63; q >= 0; q--) {
-                    if (q >= 32 && q < 32 + PIDS_LEN) {
-                        int i = q - 32;
-                        int bit = ((state >> 5) & 1) ^ p.pn[i];
-                        pk[i >> 3] |= (uint8_t)(bit << (7 - (i & 7)));
-                    }
-                    state = vitc_prev_head(state, sm.dec, q);
-                }
-                uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
-                if (w) for (int i = 0; i < 10; i++) w[i] = pk[i];
-                // P1 bookkeeping (decode.c:383-390)
-                if (bc == 0) st.started_pm = 1;
-                if (st.started_pm && bc == 15) st.p1_ready = 1;
-#ifdef NB_DEBUG
-                { uint8_t *w2 = log_reserve(p, d, s, 10, 12); if (w2) { int *wi = (int*)w2; wi[0] = bc; wi[1] = st.started_pm; wi[2] = st.p1_ready; } }
-#endif
-                st.bc = (bc + 1) % 16;
-            }
+        // PIDS (decode.c:463-471): the 80-bit frame of this block is decoded by the next demodulator launch
+        // (k_demod, symbol-0 CTA) so that its ~150 serial trellis steps stay off this kernel's critical
+        // path; the record slot is reserved here to keep the stream's record order.
+        if (t == 0) {
+            uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
+            st.pids_rec = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+            st.pids_bc = bc;
+            st.pids_pending = 1;
+            // P1 bookkeeping (decode.c:383-390)
+            if (bc == 0) st.started_pm = 1;
+            if (st.started_pm && bc == 15) st.p1_ready = 1;
+            st.bc = (bc + 1) % 16;
         }
     }
     __syncthreads();
@@ -1312,19 +1280,30 @@ extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned
 extern "C" int nrsc5b_process(nrsc5b_engine_t *e)
 {
     if (!e) return NRSC5B_EINVAL;
-    // Every block consumes at least 2160*31 decimated samples, so the number of
-    // steps any stream can still take is bounded by its buffered samples; run
-    // them in batches and stop when a whole batch made no progress.
+    // Each block advances a stream's window by 69120 +- a few decimated samples, so the number of
+    // blocks a stream can still take follows from its buffered samples and its window start.  Launch
+    // that many steps, look at the device-side progress counter, and stop after a batch (always at
+    // least one trailing step, which also flushes the deferred PIDS decode) made no progress.
+    const int S = e->dims.nstreams;
     for (;;) {
-        const int batch = 16;
+        CK(cudaMemcpyAsync(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        long long most = 0;
+        for (int s = 0; s < S; s++) {
+            const long long avail_dec = e->pushed[s] / 2, start = e->h_state[s].start;
+            if (avail_dec >= start + NACQ) {
+                long long n = (avail_dec - start - NACQ) / (NSYM * BLK + 80) + 1;
+                if (n > most) most = n;
+            }
+        }
+        const int batch = (int)(most < 1 ? 1 : (most > 256 ? 256 : most));
         for (int i = 0; i < batch; i++) launch_step(e);
         unsigned long long prog = 0;
         CK(cudaMemcpyFromSymbolAsync(&prog, g_progress, sizeof(prog), 0, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
-        unsigned long long delta = prog - e->last_progress;
+        const unsigned long long delta = prog - e->last_progress;
         e->last_progress = prog;
-        e->stats.blocks += delta;
         if (delta == 0) break;
     }
     return NRSC5B_OK;

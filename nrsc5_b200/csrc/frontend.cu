@@ -12,6 +12,7 @@
 // bins (the FFT is linear), instead of the reference's per-sample recurrence.
 #include "common.cuh"
 #include "fft.cuh"
+#include "viterbi_pack.cuh"
 
 namespace nb {
 
@@ -42,10 +43,77 @@ __device__ __forceinline__ float2 sample_at(const uint32_t *sw, int j)
     return make_float2((float)ar * sc, (float)ai * -sc);      // conj(x)/32767, acquire.c:160-161
 }
 
+// PIDS frame of the block the sync kernel just finished: interleaver II + depuncture
+// (reference src/decode.c:324-342), K=7 tail-biting Viterbi (src/conv_dec.c), descramble
+// (src/decode.c:279-294).  Run by the symbol-0 CTA of the next demodulator launch.
+__device__ void pids_decode(const DevPtrs &p, const EngineDims &d, int s, int t)
+{
+    __shared__ int8_t vit[PIDS_LEN * 3];
+    __shared__ uint2 dec[PIDS_LEN + 64];                     // 9 groups x 16 lanes of decision history
+    StreamState &st = p.st[s];
+    const int bc = st.pids_bc;
+    const int8_t *pmall = p.pm + (size_t)s * 16 * PM_BLOCK;
+    const int8_t PMV[20] = { 10, 2, 18, 6, 14, 8, 16, 0, 12, 4, 11, 3, 19, 7, 15, 9, 17, 1, 13, 5 };
+    for (int o = t; o < PIDS_LEN * 3; o += FFT_THREADS) {
+        int8_t v = 0;
+        if (o % 6 != 5) {
+            unsigned i = (unsigned)bc * 200 + (unsigned)(o - o / 6);
+            unsigned part = (unsigned)PMV[i % 20];
+            unsigned block = i / 200;
+            unsigned k = (i / 20) % 10 + P1_ENC / 320;
+            unsigned row = (k * 11) % 32, col = (k * 11 + k / 288) % 36;
+            v = pmall[(block * 32 + row) * 720 + part * 36 + col];
+        }
+        vit[o] = v;
+    }
+    __syncthreads();
+    if (t < 32) {
+        // both half-warps decode the same frame (the packed kernel works on two chunks per warp); FM PIDS
+        // soft bits are punctured 1,1,1,1,1,0, so the int16 metrics cannot saturate
+        const int l = t & 15;
+        VitHalf<false> vh;
+        vh.init(l);
+        vitc_run<false>(vh, vit, PIDS_LEN, PIDS_LEN + 64, 0, PIDS_LEN + 64, 0, dec, t < 16, l);
+        __syncwarp();
+        // first maximum in state order; lane l holds states 2l, 2l+32 (E) and 2l+1, 2l+33 (O)
+        int v = (short)(vh.E & 0xffff), state = 2 * l;
+        const int w1 = (short)(vh.O & 0xffff);
+        if (w1 > v) { v = w1; state = 2 * l + 1; }
+        int v2 = (short)(vh.E >> 16), idx2 = 2 * l + 32;
+        const int w3 = (short)(vh.O >> 16);
+        if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
+        if (v2 > v) { v = v2; state = idx2; }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, state, o, 16);
+            if (ov > v || (ov == v && oi < state)) { v = ov; state = oi; }
+        }
+        if (t == 0) {
+            uint8_t pk[10];
+            for (int i = 0; i < 10; i++) pk[i] = 0;
+            for (int q = PIDS_LEN + 63; q >= 0; q--) {
+                if (q >= 32 && q < 32 + PIDS_LEN) {
+                    const int i = q - 32;
+                    const int bit = ((state >> 5) & 1) ^ p.pn[i];
+                    pk[i >> 3] |= (uint8_t)(bit << (7 - (i & 7)));
+                }
+                state = vitc_prev_head(state, dec, q);
+            }
+            if (st.pids_rec != 0xffffffffu) {
+                uint8_t *w = p.log + (size_t)s * d.log_cap + st.pids_rec;
+                for (int i = 0; i < 10; i++) w[i] = pk[i];
+            }
+            st.pids_pending = 0;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(FFT_THREADS) k_demod(DevPtrs p, EngineDims d)
 {
     const int s = blockIdx.y, sym = blockIdx.x, t = threadIdx.x;
     const StreamState &st = p.st[s];
+    if (sym == 0 && st.pids_pending) pids_decode(p, d, s, t);      // previous block's PIDS frame (block-uniform branch)
     if (!st.active) return;
 
     __shared__ __align__(16) uint8_t in[IN_BYTES];
