@@ -105,6 +105,8 @@ struct DevPtrs {
     int8_t *vit_in;            // [S][438528]
     uint2 *vit_dec;            // [S][146240]
     uint32_t *p1_bits;         // [S][146176/32] decoded (still scrambled) bits, bit k of word w = frame bit 32w+k
+    uint2 *vspec, *vend;       // [S][143][16] chunk boundary metrics of the P1 Viterbi
+    int *hstate, *tbend;       // [S][143]
     uint8_t *log;              // [S][log_cap]
     const float *shape;        // [2160]
     const float2 *twid;        // [2048]  exp(-2*pi*i*k/2048)

@@ -360,13 +360,9 @@ __device__ __forceinline__ int8_t soft_demap(float x, float mult)      // sync.c
     return (int8_t)r;
 }
 
-__global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
+__device__ void sync_block(const DevPtrs &p, const EngineDims &d, SyncSmem &sm, int s, int t)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
-    const int s = blockIdx.x, t = threadIdx.x;
     StreamState &st = p.st[s];
-    if (!st.active) return;
 
     float *cfreq = p.cfreq + (size_t)s * NFFT;
     float *cphase = p.cphase + (size_t)s * NFFT;
@@ -668,6 +664,14 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
     }
 }
 
+__global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
+    const int s = blockIdx.x, t = threadIdx.x;
+    if (p.st[s].active) sync_block(p, d, sm, s, t);
+}
+
 // ===========================================================================
 // P1 decode: for every stream whose interleaver matrix is complete —
 //   k_p1_gather : interleaver I + depuncture 1,1,1,1,1,0  (decode.c:296-322)
@@ -789,6 +793,27 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     }
 }
 
+__host__ __device__ inline VitcArgs p1_vitc_args(const DevPtrs &dp)
+{
+    VitcArgs a;
+    a.vin = dp.vit_in;
+    a.dec = dp.vit_dec;
+    a.vspec = dp.vspec;
+    a.vend = dp.vend;
+    a.hstate = dp.hstate;
+    a.tbend = dp.tbend;
+    a.bitsw = dp.p1_bits;
+    a.ready = &dp.st[0].p1_ready;
+    a.slow = &dp.st[0].p1_slow;
+    a.ready_stride = (int)(sizeof(StreamState) / sizeof(int));
+    a.len = P1_LEN;
+    a.nch = P1_NCH;
+    a.dec_stride = (size_t)P1_NCH * CH_LEN;
+    return a;
+}
+
+constexpr size_t VITC_EMIT_SMEM = (size_t)VITC_EMIT_WARPS * VITC_EMIT_STEPS * sizeof(uint2);
+
 // input_reset for a range of streams (reference src/input.c:126-138)
 __global__ void k_reset(DevPtrs p, EngineDims d, int only)
 {
@@ -844,7 +869,7 @@ __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
 // ===========================================================================
 using namespace nb;
 
-static size_t vitc_emit_smem() { return (size_t)VITC_EMIT_WARPS * VITC_EMIT_STEPS * sizeof(uint2); }
+static size_t vitc_emit_smem() { return VITC_EMIT_SMEM; }
 
 #define CK(x)                                                                                      \
     do {                                                                                           \
@@ -872,8 +897,6 @@ struct nrsc5b_engine {
     size_t sync_smem;
     std::vector<void *> allocs;
     int profiling;
-    uint2 *vspec, *vend;
-    int *tbend, *hstate;
     cudaEvent_t pev[5];
     double kernel_ms[4];
     unsigned long long kernel_n[4];
@@ -1007,10 +1030,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     DA(tbuf, float2, (size_t)S * NACQ);
     DA(vit_in, int8_t, (size_t)S * P1_VIT);
     DA(vit_dec, uint2, (size_t)S * P1_NCH * CH_LEN);
-    rc = dev_alloc(e, &e->vspec, (size_t)S * P1_NCH * 16); if (rc) { nrsc5b_destroy(e); return rc; }
-    rc = dev_alloc(e, &e->vend, (size_t)S * P1_NCH * 16); if (rc) { nrsc5b_destroy(e); return rc; }
-    rc = dev_alloc(e, &e->tbend, (size_t)S * P1_NCH); if (rc) { nrsc5b_destroy(e); return rc; }
-    rc = dev_alloc(e, &e->hstate, (size_t)S * P1_NCH); if (rc) { nrsc5b_destroy(e); return rc; }
+    DA(vspec, uint2, (size_t)S * P1_NCH * 16);
+    DA(vend, uint2, (size_t)S * P1_NCH * 16);
+    DA(tbend, int, (size_t)S * P1_NCH);
+    DA(hstate, int, (size_t)S * P1_NCH);
     DA(p1_bits, uint32_t, (size_t)S * (P1_LEN / 32));
     DA(log, uint8_t, (size_t)S * e->dims.log_cap);
     {
@@ -1194,26 +1217,6 @@ extern "C" int nrsc5b_attach_device_log(nrsc5b_engine_t *e, void *dev_buf, size_
     return NRSC5B_OK;
 }
 
-static VitcArgs p1_vitc_args(nrsc5b_engine *e)
-{
-    VitcArgs a;
-    a.vin = e->dp.vit_in;
-    a.dec = e->dp.vit_dec;
-    a.vspec = e->vspec;
-    a.vend = e->vend;
-    a.hstate = e->hstate;
-    a.tbend = e->tbend;
-    a.bitsw = e->dp.p1_bits;
-    a.ready = &e->dp.st[0].p1_ready;
-    a.slow = &e->dp.st[0].p1_slow;
-    a.ready_stride = (int)(sizeof(StreamState) / sizeof(int));
-    a.len = P1_LEN;
-    a.nch = P1_NCH;
-    a.dec_stride = (size_t)P1_NCH * CH_LEN;
-    return a;
-}
-
-
 static void launch_vitc(const VitcArgs &a, int nframes, cudaStream_t stream)
 {
     dim3 gf((a.nch + 2 * VITC_FWD_WARPS - 1) / (2 * VITC_FWD_WARPS), nframes);
@@ -1227,12 +1230,12 @@ static void launch_p1(nrsc5b_engine *e)
 {
     const int S = e->dims.nstreams;
     k_p1_gather<<<dim3(16, S), 256, 0, e->stream>>>(e->dp, e->dims);
-    launch_vitc(p1_vitc_args(e), S, e->stream);
+    launch_vitc(p1_vitc_args(e->dp), S, e->stream);
     k_p1_fin<<<dim3(FIN_CTAS, S), P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
     e->stats.kernel_launches += 5;
 }
 
-static int launch_step(nrsc5b_engine *e)
+static int launch_step(nrsc5b_engine *e, bool with_p1)
 {
     const int S = e->dims.nstreams;
     const bool prof = e->profiling != 0;
@@ -1243,7 +1246,7 @@ static int launch_step(nrsc5b_engine *e)
     if (prof) cudaEventRecord(e->pev[2], e->stream);
     k_sync<<<S, SYNC_THREADS, e->sync_smem, e->stream>>>(e->dp, e->dims);
     if (prof) cudaEventRecord(e->pev[3], e->stream);
-    launch_p1(e);
+    if (with_p1) launch_p1(e);
     if (prof) {
         cudaEventRecord(e->pev[4], e->stream);
         cudaEventSynchronize(e->pev[4]);
@@ -1296,8 +1299,25 @@ extern "C" int nrsc5b_process(nrsc5b_engine_t *e)
                 if (n > most) most = n;
             }
         }
-        const int batch = (int)(most < 1 ? 1 : (most > 256 ? 256 : most));
-        for (int i = 0; i < batch; i++) launch_step(e);
+        // The P1 decode kernels are only launched in the steps where a stream can complete its 16-block
+        // interleaver matrix.  With the states just read back this is predictable for up to 15 steps: a
+        // stream in FINE sync reaches block count 15 at a known step (a superset if it runs out of
+        // samples or loses sync first), and a stream that is not in FINE sync now cannot finish a frame
+        // in fewer than 16 blocks.  The last step of every batch launches them unconditionally, which
+        // also covers streams that stalled with a frame pending.
+        const int batch = (int)(most < 1 ? 1 : (most > 15 ? 15 : most));
+        unsigned p1_steps = 0;
+        for (int s = 0; s < S; s++) {
+            const StreamState &hs = e->h_state[s];
+            if (hs.p1_ready) p1_steps |= 1u;
+            if (hs.state != ST_FINE) continue;
+            for (int i = 0; i < batch; i++) {
+                const int bc = (hs.bc + i) & 15;
+                if (bc == 15 && (hs.started_pm || i >= ((16 - hs.bc) & 15))) p1_steps |= 1u << i;
+            }
+        }
+        p1_steps |= 1u << (batch - 1);
+        for (int i = 0; i < batch; i++) launch_step(e, e->profiling || ((p1_steps >> i) & 1u));
         unsigned long long prog = 0;
         CK(cudaMemcpyFromSymbolAsync(&prog, g_progress, sizeof(prog), 0, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));

@@ -111,7 +111,9 @@ __device__ void pids_decode(const DevPtrs &p, const EngineDims &d, int s, int t)
 
 __global__ void __launch_bounds__(FFT_THREADS) k_demod(DevPtrs p, EngineDims d)
 {
-    const int s = blockIdx.y, sym = blockIdx.x, t = threadIdx.x;
+    // blockIdx.x = stream, blockIdx.y = symbol: the symbol-0 CTAs (which also carry the deferred PIDS
+    // decode) are scheduled first
+    const int s = blockIdx.x, sym = blockIdx.y, t = threadIdx.x;
     const StreamState &st = p.st[s];
     if (sym == 0 && st.pids_pending) pids_decode(p, d, s, t);      // previous block's PIDS frame (block-uniform branch)
     if (!st.active) return;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_demod(DevPtrs p, EngineDims d)
 
 void launch_demod(const DevPtrs &p, const EngineDims &d, cudaStream_t stream)
 {
-    dim3 grid(BLK, d.nstreams);
+    dim3 grid(d.nstreams, BLK);
     k_demod<<<grid, FFT_THREADS, 0, stream>>>(p, d);
 }
 
