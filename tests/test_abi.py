@@ -1,0 +1,57 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/nrsc5_b200.h declares, and fails
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import nrsc5_b200
+from nrsc5_b200 import engine as eng
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nrsc5_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nrsc5b_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = nrsc5_b200.load_library()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/nrsc5_b200.h but not exported"
+    assert b"sm_100a" in L.nrsc5b_version()
+
+
+def test_sass_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", nrsc5_b200.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nrsc5_b200.EngineError):
+        nrsc5_b200.Engine(nstreams=1, input_capacity=1 << 16)
+    import numpy as np
+    with pytest.raises(nrsc5_b200.EngineError):
+        eng.halfband_fm(np.zeros(64, dtype=np.uint8))
+
+
+def test_record_parser_roundtrip():
+    import struct
+    raw = b""
+    raw += struct.pack("<II", eng.REC_SYNC, 8) + struct.pack("<fi", 12.5, 1)
+    raw += struct.pack("<II", eng.REC_PIDS, 10) + bytes(range(10)) + b"\0\0"
+    raw += struct.pack("<II", eng.REC_FRAME, 8 + 3) + struct.pack("<II", 0, 24) + b"\x01\x02\x03" + b"\0"
+    raw += struct.pack("<II", eng.REC_LOST_SYNC, 0)
+    recs = eng.parse_records(raw)
+    assert [t for t, _ in recs] == [eng.REC_SYNC, eng.REC_PIDS, eng.REC_FRAME, eng.REC_LOST_SYNC]
+    assert recs[0][1]["psmi"] == 1 and recs[2][1]["bits"] == b"\x01\x02\x03"
