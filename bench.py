@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=128, help="channels per GPU")
-    ap.add_argument("--frames", type=int, default=2, help="L1 frames per channel per step")
+    ap.add_argument("--frames", type=int, default=4, help="L1 frames per channel per step (SURVEY §8d config 5: 4)")
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic captures (replicated with offsets)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -87,35 +87,53 @@ def stream_views(caps, nstreams: int, rank: int):
 
 
 class ClockSampler:
+    """Samples SM clocks / throttle reasons with one streaming `nvidia-smi -lms` process (the recipe's
+    clocks line in B200_PROFILING.md); only the samples taken between mark_begin() and stop() count."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
     def __init__(self, index: int):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self.t_begin = None
+        self._proc = None
         self._th = None
 
     def start(self):
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                           "--format=csv,noheader,nounits", "-lms", "50"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
+            return
+
         def run():
-            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap")
-            while not self._stop.is_set():
-                try:
-                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                    self.rows.append([x.strip() for x in out.strip().split(",")])
-                except Exception:
-                    pass
-                self._stop.wait(0.2)
+            for line in self._proc.stdout:
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.strip().split(",")]))
         self._th = threading.Thread(target=run, daemon=True)
         self._th.start()
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
     def stop(self):
-        self._stop.set()
-        if self._th:
-            self._th.join(timeout=6)
+        t_end = time.perf_counter()
+        if self._proc:
+            time.sleep(0.06)
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=3)
+            except Exception:
+                self._proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if self.t_begin is None or (self.t_begin <= ts <= t_end + 0.1)]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-1:]]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -225,7 +243,7 @@ def main():
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
-    log_cap = (args.frames + 1) * (18272 + 64) + 64 * 1024
+    log_cap = (args.frames + 1) * (18272 + 64) + 96 * 1024
     e = nrsc5_b200.Engine(nstreams=S, input_capacity=nbytes + 4096, device=local_rank, log_capacity=log_cap)
     e.set_cuda_stream(stream.cuda_stream)
     log_stride = (log_cap + 15) & ~15
@@ -242,12 +260,22 @@ def main():
         e.rewind()
         e.process()
 
+    E2E_CHUNKS = 4                                # input arrives in 4 pushes per channel; copy k+1 overlaps compute k
+    cuts = [((nbytes * k // E2E_CHUNKS) & ~3) for k in range(E2E_CHUNKS + 1)]
+
     def step_e2e():
         e.reset()
-        for s in range(S):
-            e.push_cu8(s, hnp[s])
-        e.process()
-        nrec = 0
+
+        def push(k):
+            for s in range(S):
+                e.push_cu8(s, hnp[s, cuts[k]:cuts[k + 1]])
+        push(0)
+        for k in range(E2E_CHUNKS):
+            if k + 1 < E2E_CHUNKS:
+                push(k + 1)                       # asynchronous, on the engine's copy stream
+                e.process_available()             # works on what has landed while chunk k+1 is in flight
+            else:
+                e.process()
         d2h = 0
         frames = []
         for s in range(S):
@@ -261,11 +289,12 @@ def main():
         return d2h, frames
 
     def timed(fn, steps, warmup):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.mark_begin()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = e.stats().kernel_launches
         ev0.record(stream)

@@ -110,6 +110,9 @@ int nrsc5b_attach_device_log(nrsc5b_engine_t *e, void *dev_buf, size_t stride);
 
 /* Run every 32-symbol block for which a stream's buffered samples suffice; returns when no stream can advance. */
 int nrsc5b_process(nrsc5b_engine_t *e);
+/* Same, but does not wait for input copies still in flight (pushes are asynchronous): lets the next
+ * nrsc5b_push_cu8 overlap with this call's compute.  A later nrsc5b_process() picks up the rest. */
+int nrsc5b_process_available(nrsc5b_engine_t *e);
 /* Wait for the GPU and copy the records of `stream` produced since the last drain.
  * Returns the number of bytes written (>= 0) or a negative error; *needed gets the full size. */
 long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_t cap, size_t *needed);

@@ -885,12 +885,16 @@ struct nrsc5b_engine {
     EngineDims dims;
     DevPtrs dp;
     cudaStream_t stream;
+    cudaStream_t copy_stream;          // host->device input copies overlap with compute on `stream`
     uint8_t *iq_owned;                 // engine-owned cu8 buffer (null when attached)
     std::vector<long long> pushed;     // complex cu8 samples pushed per stream
     std::vector<unsigned> drained;     // log bytes already handed out per stream
     uint8_t *pinned;                   // staging for pushes
     size_t pinned_cap;
     cudaEvent_t pinned_free;
+    long long *avail_ring;             // pinned, 4096 entries
+    unsigned avail_pos;
+    cudaEvent_t reset_done;            // copy stream waits for resets issued on the compute stream
     StreamState *h_state;              // pinned mirror for read-back
     nrsc5b_stats_t stats;
     unsigned long long last_progress;
@@ -986,13 +990,14 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     if (!e) return NRSC5B_ENOMEM;
     e->cfg = *cfg;
     e->stream = 0;
+    e->copy_stream = nullptr;
     e->iq_owned = nullptr;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
     e->profiling = 0;
     for (int i = 0; i < 5; i++) e->pev[i] = nullptr;
     for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
-    e->pinned = nullptr; e->h_state = nullptr; e->pinned_free = nullptr;
+    e->pinned = nullptr; e->h_state = nullptr; e->pinned_free = nullptr; e->avail_ring = nullptr; e->avail_pos = 0; e->reset_done = nullptr;
     const int S = cfg->nstreams;
     e->dims.nstreams = S;
     e->dims.in_stride = (cfg->input_capacity + 63) & ~(size_t)63;
@@ -1085,8 +1090,11 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     }
 #undef DA
     e->pinned_cap = 8u << 20;
+    if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { nrsc5b_destroy(e); return NRSC5B_ECUDA; }
     if (cudaMallocHost((void **)&e->pinned, e->pinned_cap) != cudaSuccess ||
         cudaMallocHost((void **)&e->h_state, sizeof(StreamState) * S) != cudaSuccess ||
+        cudaMallocHost((void **)&e->avail_ring, sizeof(long long) * 4096) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->reset_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->pinned_free, cudaEventDisableTiming) != cudaSuccess) {
         nrsc5b_destroy(e);
         return NRSC5B_ENOMEM;
@@ -1111,7 +1119,10 @@ extern "C" void nrsc5b_destroy(nrsc5b_engine_t *e)
     for (void *q : e->allocs) cudaFree(q);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_state) cudaFreeHost(e->h_state);
+    if (e->avail_ring) cudaFreeHost(e->avail_ring);
+    if (e->reset_done) cudaEventDestroy(e->reset_done);
     if (e->pinned_free) cudaEventDestroy(e->pinned_free);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 5; i++) if (e->pev[i]) cudaEventDestroy(e->pev[i]);
     delete e;
 }
@@ -1127,7 +1138,10 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
 {
     if (!e || stream >= e->dims.nstreams) return NRSC5B_EINVAL;
     const int S = e->dims.nstreams;
+    CK(cudaStreamSynchronize(e->copy_stream));       // no input copy of the old contents may still be in flight
     k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream);
+    CK(cudaEventRecord(e->reset_done, e->stream));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->reset_done, 0));
     e->stats.kernel_launches += 1;
     for (int s = 0; s < S; s++) {
         if (stream >= 0 && s != stream) continue;
@@ -1149,11 +1163,14 @@ extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
     return NRSC5B_OK;
 }
 
-static int publish_avail(nrsc5b_engine *e, int s)
+static int publish_avail(nrsc5b_engine *e, int s, cudaStream_t on)
 {
-    long long v = e->pushed[s];
-    CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(e->dp.st + s) + offsetof(StreamState, in_avail), &v, sizeof(v),
-                       cudaMemcpyHostToDevice, e->stream));
+    // staged through a small pinned ring so that the asynchronous copy has a stable source
+    if (e->avail_pos && (e->avail_pos & 4095) == 0) CK(cudaStreamSynchronize(on));   // ring wrap: let pending copies drain
+    long long *slot = e->avail_ring + (e->avail_pos++ & 4095);
+    *slot = e->pushed[s];
+    CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(e->dp.st + s) + offsetof(StreamState, in_avail), slot, sizeof(*slot),
+                       cudaMemcpyHostToDevice, on));
     return 0;
 }
 
@@ -1168,20 +1185,21 @@ extern "C" int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *bu
     bool pinned_src = cudaPointerGetAttributes(&attr, buf) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned_src) {
-        CK(cudaMemcpyAsync(dst, buf, nbytes, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(dst, buf, nbytes, cudaMemcpyHostToDevice, e->copy_stream));
     } else {
         size_t done = 0;
         while (done < nbytes) {
             size_t n = nbytes - done < e->pinned_cap ? nbytes - done : e->pinned_cap;
             CK(cudaEventSynchronize(e->pinned_free));
             memcpy(e->pinned, buf + done, n);
-            CK(cudaMemcpyAsync(dst + done, e->pinned, n, cudaMemcpyHostToDevice, e->stream));
-            CK(cudaEventRecord(e->pinned_free, e->stream));
+            CK(cudaMemcpyAsync(dst + done, e->pinned, n, cudaMemcpyHostToDevice, e->copy_stream));
+            CK(cudaEventRecord(e->pinned_free, e->copy_stream));
             done += n;
         }
     }
     e->pushed[stream] += (long long)(nbytes / 2);
-    return publish_avail(e, stream);
+    // published on the copy stream, i.e. after the samples themselves have landed
+    return publish_avail(e, stream, e->copy_stream);
 }
 
 extern "C" int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void *dev_buf, size_t nbytes)
@@ -1192,7 +1210,7 @@ extern "C" int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void
     CK(cudaMemcpyAsync(e->iq_owned + (size_t)stream * e->dims.in_stride + off, dev_buf, nbytes,
                        cudaMemcpyDeviceToDevice, e->stream));
     e->pushed[stream] += (long long)(nbytes / 2);
-    return publish_avail(e, stream);
+    return publish_avail(e, stream, e->stream);
 }
 
 extern "C" int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_buf, size_t stride, size_t nbytes)
@@ -1202,7 +1220,7 @@ extern "C" int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_bu
     e->dims.in_stride = stride;
     for (int s = 0; s < e->dims.nstreams; s++) {
         e->pushed[s] = (long long)(nbytes / 2);
-        int rc = publish_avail(e, s);
+        int rc = publish_avail(e, s, e->stream);
         if (rc) return rc;
     }
     return NRSC5B_OK;
@@ -1280,7 +1298,7 @@ extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned
     return NRSC5B_OK;
 }
 
-extern "C" int nrsc5b_process(nrsc5b_engine_t *e)
+static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
 {
     if (!e) return NRSC5B_EINVAL;
     // Each block advances a stream's window by 69120 +- a few decimated samples, so the number of
@@ -1324,10 +1342,17 @@ extern "C" int nrsc5b_process(nrsc5b_engine_t *e)
         CK(cudaGetLastError());
         const unsigned long long delta = prog - e->last_progress;
         e->last_progress = prog;
-        if (delta == 0) break;
+        if (delta == 0) {
+            // samples pushed asynchronously may still have been in flight: wait for them once, then retry
+            if (!wait_for_copies || cudaStreamQuery(e->copy_stream) == cudaSuccess) break;
+            CK(cudaStreamSynchronize(e->copy_stream));
+        }
     }
     return NRSC5B_OK;
 }
+
+extern "C" int nrsc5b_process(nrsc5b_engine_t *e) { return process_impl(e, true); }
+extern "C" int nrsc5b_process_available(nrsc5b_engine_t *e) { return process_impl(e, false); }
 
 extern "C" int nrsc5b_synchronize(nrsc5b_engine_t *e)
 {

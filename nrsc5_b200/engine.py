@@ -65,6 +65,7 @@ def load_library():
     L.nrsc5b_attach_device_input.argtypes = [vp, vp, sz, sz]
     L.nrsc5b_attach_device_log.argtypes = [vp, vp, sz]
     L.nrsc5b_process.argtypes = [vp]
+    L.nrsc5b_process_available.argtypes = [vp]
     L.nrsc5b_synchronize.argtypes = [vp]
     L.nrsc5b_drain.argtypes = [vp, ci, vp, sz, ctypes.POINTER(sz)]
     L.nrsc5b_drain.restype = ctypes.c_long
@@ -193,6 +194,9 @@ class Engine:
 
     def process(self):
         _check(self._L.nrsc5b_process(self._h), "nrsc5b_process")
+
+    def process_available(self):
+        _check(self._L.nrsc5b_process_available(self._h), "nrsc5b_process_available")
 
     def synchronize(self):
         _check(self._L.nrsc5b_synchronize(self._h), "nrsc5b_synchronize")
