@@ -78,6 +78,10 @@ struct StreamState {
     // output log cursor
     unsigned log_len;
     unsigned log_overflow;
+    // task-queue flags of the persistent front-end kernel (front.cuh)
+    unsigned long long q_prepped;   // rounds whose prep is published
+    unsigned long long q_synced;    // rounds completely processed
+    int q_cnt;                      // demod tasks of the current round that have finished
     unsigned long long blocks_done;
     unsigned long long frames_done;
     // history of the coarse band-pass FIR: the last 31 samples it was fed

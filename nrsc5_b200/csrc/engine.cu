@@ -18,659 +18,12 @@
 #include "rs.cuh"
 #include "viterbi.cuh"
 #include "viterbi_chunk.cuh"
+#include "front.cuh"
 
 namespace nb {
 
-void launch_demod(const DevPtrs &p, const EngineDims &d, cudaStream_t stream);
 void launch_fft_test(const float2 *in, float2 *out, const float2 *twid, int nffts, cudaStream_t stream);
 void launch_halfband_test(const uint8_t *cu8, long long npairs, short2 *out, cudaStream_t stream);
-
-__device__ unsigned long long g_progress;      // bumped by every stream that processed a block
-
-__constant__ int c_compat_mode[64];
-__constant__ short c_bp_tap[32];               // coarse band-pass taps, tap[i] pairs w[i] and w[32-i]
-
-// complex helpers with the reference's (gcc, no FMA) evaluation order
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
-{
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cexp_j(float a)       // cexpf(I*a)
-{
-    float s, c;
-    sincosf(a, &s, &c);
-    return make_float2(c, s);
-}
-
-__device__ __forceinline__ int partitions_per_band(int psmi)
-{
-    switch (c_compat_mode[psmi & 63]) {
-    case 2: return 11;
-    case 3: return 12;
-    case 5: case 6: case 11: return 14;
-    default: return 10;
-    }
-}
-
-// input_set_sync_state (reference src/input.c:172-188)
-__device__ void set_state(const DevPtrs &p, const EngineDims &d, int s, int ns)
-{
-    StreamState &st = p.st[s];
-    if (st.state == ns) return;
-    if (st.state == ST_FINE) log_reserve(p, d, s, REC_LOST_SYNC, 0);
-    if (ns == ST_FINE) {
-        float fo = (float)(((double)st.prev_angle - 2 * M_PI * st.cfo) * 744187.5 / (2 * M_PI * NFFT));
-        uint8_t *w = log_reserve(p, d, s, REC_SYNC, 8);
-        if (w) {
-            reinterpret_cast<float *>(w)[0] = fo;
-            reinterpret_cast<int *>(w)[1] = st.psmi;
-        }
-    }
-    st.state = ns;
-}
-
-// ===========================================================================
-// k_prep: per stream, decide whether a full 33-symbol window is buffered, run
-// coarse acquisition when not in FINE, and publish the block's NCO.
-//   reference src/acquire.c:98-168 (+ src/sync.c:769-777, src/firdecim_q15.c:95-109,154-158)
-// ===========================================================================
-constexpr int PREP_THREADS = 512;
-
-__global__ void __launch_bounds__(PREP_THREADS) k_prep(DevPtrs p, EngineDims d)
-{
-    const int s = blockIdx.x, t = threadIdx.x;
-    StreamState &st = p.st[s];
-    __shared__ int sh_active;
-    __shared__ float2 sums[NSYM];
-    __shared__ float red_mag[PREP_THREADS];
-    __shared__ int red_idx[PREP_THREADS];
-    __shared__ float2 red_v[PREP_THREADS];
-    __shared__ int sh_samperr;
-    __shared__ float sh_angle;
-
-    if (t == 0) {
-        if (st.force_state >= 0) {
-            set_state(p, d, s, st.force_state);
-            st.force_state = -1;
-        }
-        int act = st.in_avail >= 2 * (st.start + NACQ);
-        st.active = act;
-        sh_active = act;
-        if (act) atomicAdd(&g_progress, 1ull);
-    }
-    __syncthreads();
-    if (!sh_active) return;
-
-    const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
-    const int state_in = st.state;
-
-    if (state_in != ST_FINE) {
-        short2 *y = p.ydec + (size_t)s * NACQ;
-        float2 *tb = p.tbuf + (size_t)s * NACQ;
-        for (int i = t; i < NACQ; i += PREP_THREADS) y[i] = halfband_at(iq, st.start + i);
-        __syncthreads();
-        // 32-tap symmetric Q15 band-pass; history = last 31 samples of the previous coarse window
-        for (int i = t; i < NACQ; i += PREP_THREADS) {
-            auto at = [&](int pos) -> short2 {
-                if (pos >= 0) return y[pos];
-                return make_short2(st.bp_hist[31 + pos][0], st.bp_hist[31 + pos][1]);
-            };
-            short accr = 0, acci = 0;
-#pragma unroll 5
-            for (int k = 1; k < 16; k++) {
-                short2 a = at(i - 31 + k), b = at(i - 31 + 32 - k);
-                accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
-                acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
-            }
-            short2 c = at(i - 31 + 16);
-            accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
-            acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
-            tb[i] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
-        }
-        __syncthreads();
-        if (t < 31) {
-            short2 v = y[NACQ - 31 + t];
-            st.bp_hist[t][0] = v.x;
-            st.bp_hist[t][1] = v.y;
-        }
-        // cyclic-prefix correlation per sample offset (acquire.c:129-134)
-        for (int i = t; i < NSYM; i += PREP_THREADS) {
-            float2 acc = make_float2(0.f, 0.f);
-            for (int j = 0; j < BLK; j++) {
-                float2 a = tb[i + j * NSYM], b = tb[i + j * NSYM + NFFT];
-                float2 bc = make_float2(b.x, -b.y);
-                float2 pr = cmulf(a, bc);
-                acc.x += pr.x;
-                acc.y += pr.y;
-            }
-            sums[i] = acc;
-        }
-        __syncthreads();
-        // pulse-shaped sliding sum and arg-max (acquire.c:136-151)
-        float best = -1.0f;
-        int besti = 0;
-        float2 bestv = make_float2(0.f, 0.f);
-        for (int i = t; i < NSYM; i += PREP_THREADS) {
-            float2 v = make_float2(0.f, 0.f);
-            for (int j = 0; j < NCP; j++) {
-                int q = i + j;
-                if (q >= NSYM) q -= NSYM;
-                float2 sm = sums[q];
-                float a = p.shape[j], b = p.shape[j + NFFT];
-                v.x += (sm.x * a) * b;
-                v.y += (sm.y * a) * b;
-            }
-            float mag = v.x * v.x + v.y * v.y;
-            if (mag > best) { best = mag; besti = i; bestv = v; }
-        }
-        red_mag[t] = best; red_idx[t] = besti; red_v[t] = bestv;
-        __syncthreads();
-        for (int o = PREP_THREADS / 2; o; o >>= 1) {
-            if (t < o) {
-                float m2 = red_mag[t + o];
-                int i2 = red_idx[t + o];
-                if (m2 > red_mag[t] || (m2 == red_mag[t] && i2 < red_idx[t])) {
-                    red_mag[t] = m2; red_idx[t] = i2; red_v[t] = red_v[t + o];
-                }
-            }
-            __syncthreads();
-        }
-        if (t == 0) {
-            float2 mv = red_v[0];
-            float2 w = cmulf(mv, cexp_j(-st.prev_angle));
-            float angle_diff = atan2f(w.y, w.x);
-            float factor = (st.prev_angle != 0.0f) ? 0.25f : 1.0f;
-            float angle = st.prev_angle + (angle_diff * factor);
-            st.prev_angle = angle;
-            sh_angle = angle;
-            sh_samperr = (red_idx[0] + NSYM - 15) % NSYM;
-            if (st.state == ST_NONE) st.state = ST_COARSE;
-        }
-    } else if (t == 0) {
-        sh_samperr = NSYM / 2 + st.samperr;
-        st.samperr = 0;
-        float angle = st.prev_angle + (-st.angle);
-        st.angle = 0;
-        st.prev_angle = angle;
-        sh_angle = angle;
-    }
-    __syncthreads();
-
-    const int samperr = sh_samperr;
-    const int adj = NSYM / 2 - samperr;
-    if (adj != 0) {                                            // sync_adjust, sync.c:769-777
-        float *cp = p.cphase + (size_t)s * NFFT;
-        for (int i = t; i < SIDE; i += PREP_THREADS) {
-            int bl = LB0 + i, bu = UB1 - i;
-            cp[bl] = (float)((double)cp[bl] - (double)(adj * (bl - NFFT / 2) * 2) * M_PI / NFFT);
-            cp[bu] = (float)((double)cp[bu] - (double)(adj * (bu - NFFT / 2) * 2) * M_PI / NFFT);
-        }
-    }
-    __shared__ float sh_theta;
-    if (t == 0) {
-        float angle = sh_angle;
-        angle = (float)((double)angle - 2 * M_PI * st.cfo);
-        float pre = (float)(-adj) * angle / (float)NFFT;
-        float2 ph = cmulf(st.phase, cexp_j(pre));
-        float theta = angle / (float)NFFT;
-        st.phase0 = ph;
-        st.theta = theta;
-        st.blk_samperr = samperr;
-        st.blk_state_in = state_in;
-        sh_theta = theta;
-        // NCO phase after the 32 symbols of this block (acquire.c:250-252, closed form)
-        double sn, cs;
-        sincos((double)theta * (double)(NSYM * BLK), &sn, &cs);
-        float2 pe = cmulf(ph, make_float2((float)cs, (float)sn));
-        float nrm = sqrtf(pe.x * pe.x + pe.y * pe.y);
-        st.phase = make_float2(pe.x / nrm, pe.y / nrm);
-        uint8_t *w = log_reserve(p, d, s, REC_BLOCK, 32);
-        if (w) {
-            int *wi = reinterpret_cast<int *>(w);
-            float *wf = reinterpret_cast<float *>(w);
-            wi[0] = state_in; wi[1] = samperr; wf[2] = angle; wf[3] = ph.x; wf[4] = ph.y; wi[5] = st.cfo;
-            wi[6] = (int)(unsigned)(st.start & 0xffffffffLL);
-            wi[7] = (int)(st.start >> 32);
-        }
-    }
-    __syncthreads();
-    {
-        const float theta = sh_theta;
-        float2 *nco = p.nco + (size_t)s * NSYM;
-        for (int j = t; j < NSYM; j += PREP_THREADS) {
-            float2 e = cexp_j(theta * (float)j);
-            float w = (j < NCP || j >= NFFT) ? p.shape[j] : 1.0f;
-            nco[j] = make_float2(e.x * w, e.y * w);
-        }
-    }
-}
-
-// ===========================================================================
-// k_sync: per stream and block — Costas loops on the reference subcarriers,
-// COARSE->FINE decision, channel equalisation, timing/phase feedback, MER,
-// soft demapping and the PIDS decode.      reference src/sync.c:90-610,
-// src/decode.c:378-391,463-471
-// ===========================================================================
-constexpr int SYNC_THREADS = 256;
-constexpr int ZLD = 33;                         // padded symbols-per-bin stride in shared memory
-constexpr int MAXREF = 15;                      // reference subcarriers per sideband (14 partitions + 1)
-
-struct SyncSmem {
-    float2 z[NBINS * ZLD];                      // [bin][symbol]
-    float phs[2 * MAXREF][BLK];                 // Costas phase per reference and symbol
-    float smag[2 * MAXREF];
-    float part_lb[BLK], part_ub[BLK];
-    float mer_lb[8][BLK], mer_ub[8][BLK];
-    float2 zero_row[BLK];
-    float tmp_phs[32][BLK];                     // scratch phases for the CFO search
-    int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
-    int offs[32];
-    float mult_lb, mult_ub;
-    int flag;
-};
-
-__device__ __forceinline__ int ref_bin(int slot, int nref)      // slot < nref: lower, else upper
-{
-    return slot < MAXREF ? LB0 + PW * slot : UB1 - PW * (slot - MAXREF);
-}
-
-// adjust_ref (sync.c:90-130) on one row of 32 symbols
-__device__ void costas_row(float2 *z, int zstride, float *phs, float &cfreq, float &cphase, int cfo,
-                           float alpha, float beta)
-{
-    const signed char pat[BLK] = { -1, 1, -1, -1, -1, 1, 1, 0, 1, -1, 0, 0, 0, -1, -1, 0,
-                                   0, 0, 0, 0, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1 };
-    const float cfo_freq = (float)(2 * M_PI * cfo * NCP / NFFT);
-    const float PI_F = 3.14159274101257324f;                  // smallest float above pi: (ph > M_PI) <=> (ph >= PI_F)
-    float f = cfreq, ph = cphase;
-    for (int n = 0; n < BLK; n++) {
-        const float2 v = z[n * zstride];
-        // u = v * exp(-j*ph); the loop error arg(v^2 * exp(-2j*ph)) / 2 equals arg(u^2) / 2
-        const float2 u = cmulf(v, cexp_j(-ph));
-        const float error = atan2f((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y) * 0.5f;
-        phs[n] = ph;
-        z[n * zstride] = u;
-        f += beta * error;
-        if (f > 0.5f) f = 0.5f;
-        if (f < -0.5f) f = -0.5f;
-        ph += (f + cfo_freq) + (alpha * error);
-        if (ph >= PI_F) ph = (float)((double)ph - 2 * M_PI);
-        if (ph <= -PI_F) ph = (float)((double)ph + 2 * M_PI);
-    }
-    float x = 0;
-    for (int n = 0; n < BLK; n++) x += z[n * zstride].x * (float)pat[n];
-    if (x < 0) {
-        for (int n = 0; n < BLK; n++) {
-            phs[n] = (float)((double)phs[n] + M_PI);
-            float2 v = z[n * zstride];
-            z[n * zstride] = make_float2(v.x * -1.0f, v.y * -1.0f);
-        }
-        ph = (float)((double)ph + M_PI);
-    }
-    cfreq = f;
-    cphase = ph;
-}
-
-__device__ __forceinline__ int needle_bit(int n, unsigned rsid)       // -1 = don't care (sync.c:171-174)
-{
-    const signed char base[BLK] = { 0, 1, 0, 0, 0, 1, 1, -1, 1, 0, 0, 0, -1, 0, 0, -1,
-                                    -1, -1, -1, -1, 0, 1, 0, -1, -1, -1, -1, -1, -1, -1, -1, 0 };
-    if (n == 10) return (int)(rsid >> 1);
-    if (n == 11) return (int)((rsid >> 1) ^ (rsid & 1));
-    return base[n];
-}
-
-// find_ref_fm (sync.c:188-207): cyclic offset of the sync pattern, also trying the inverted bits
-__device__ int ref_find(const float2 *z, int zstride, unsigned rsid)
-{
-    unsigned raw = 0;
-    for (int n = 0; n < BLK; n++)
-        if (!(z[n * zstride].x <= 0)) raw |= 1u << n;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int n = 0; n < BLK; n++) {
-            int i;
-            for (i = 0; i < BLK; i++) {
-                int nb_ = needle_bit(i, rsid);
-                if (nb_ < 0) continue;
-                if (nb_ != (int)((raw >> ((n + i) & 31)) & 1)) break;
-            }
-            if (i == BLK) return n;
-        }
-        raw = ~raw;
-    }
-    return -1;
-}
-
-__device__ __forceinline__ float half_pi_wrap(float a, float b)        // sync.c:284-290
-{
-    float dd = a - b;
-    while ((double)dd > M_PI / 2) dd = (float)((double)dd - M_PI);
-    while ((double)dd < -M_PI / 2) dd = (float)((double)dd + M_PI);
-    return dd;
-}
-
-__device__ __forceinline__ int8_t soft_demap(float x, float mult)      // sync.c:69-73
-{
-    // lroundf semantics (round half away from zero) without the libm call: |v| <= 127 so v - trunc(v) is exact
-    const float v = fmaxf(fminf(x, 1.0f), -1.0f) * mult;
-    int r = __float2int_rz(v);
-    const float f = v - (float)r;
-    if (f >= 0.5f) r++;
-    else if (f <= -0.5f) r--;
-    return (int8_t)r;
-}
-
-__device__ void sync_block(const DevPtrs &p, const EngineDims &d, SyncSmem &sm, int s, int t)
-{
-    StreamState &st = p.st[s];
-
-    float *cfreq = p.cfreq + (size_t)s * NFFT;
-    float *cphase = p.cphase + (size_t)s * NFFT;
-    const float loop_bw = 0.05f, damping = 0.70710678f;
-    const float denom = 1 + (2 * damping * loop_bw) + (loop_bw * loop_bw);
-    const float alpha = (4 * damping * loop_bw) / denom, beta = (4 * loop_bw * loop_bw) / denom;
-
-    // stage the block's 32x534 spectrum as [bin][symbol]
-    {
-        const float2 *src = p.bins + (size_t)s * BLK * NBINS;
-        constexpr int NEL = BLK * NBINS, U = 6;                   // 17088 = 256 * 66 + 192
-        for (int i0 = t; i0 < NEL; i0 += SYNC_THREADS * U) {
-            float2 v[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + u * SYNC_THREADS;
-                if (i < NEL) v[u] = __ldg(&src[i]);
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + u * SYNC_THREADS;
-                if (i < NEL) {
-                    const int sym = i / NBINS, ci = i - sym * NBINS;
-                    sm.z[ci * ZLD + sym] = v[u];
-                }
-            }
-        }
-        if (t < BLK) sm.zero_row[t] = make_float2(0.f, 0.f);
-    }
-    __syncthreads();
-
-    int ppb = partitions_per_band(st.psmi);
-    int nref = ppb + 1;
-    // Costas loop on every reference subcarrier (sync.c:359-363)
-    if (t < 2 * MAXREF) {
-        int side = t / MAXREF, i = t - side * MAXREF;
-        if (i < nref) {
-            int b = ref_bin(t, nref);
-            costas_row(&sm.z[compact_of_bin(b) * ZLD], 1, sm.phs[t], cfreq[b], cphase[b], 0, alpha, beta);
-        }
-    }
-    __syncthreads();
-
-    if (st.state == ST_COARSE) {                 // sync.c:366-421
-        if (t < 2 * MAXREF) {
-            int side = t / MAXREF, i = t - side * MAXREF;
-            sm.ref_ok[t] = 0;
-            if (i < nref) {
-                const float2 *z = &sm.z[compact_of_bin(ref_bin(t, nref)) * ZLD];
-                unsigned rsid = (unsigned)(30 - i) & 3;
-                bool ok = true;
-                unsigned raw = 0;
-                for (int n = 0; n < BLK; n++) {
-                    int nbit = needle_bit(n, rsid);
-                    int pos = z[n].x > 0 ? 1 : 0;
-                    if (nbit >= 0 && nbit != pos) ok = false;
-                    if (!(z[n].x <= 0)) raw |= 1u << n;
-                }
-                unsigned dd = raw ^ (raw << 1);              // DBPSK decode, prev = 0 (sync.c:138-148)
-                auto bit = [&](int n) { return (dd >> n) & 1u; };
-                sm.ref_ok[t] = ok;
-                sm.ref_bc[t] = (int)(bit(16) << 3 | bit(17) << 2 | bit(18) << 1 | bit(19));
-                sm.ref_psmi[t] = (int)(bit(25) << 5 | bit(26) << 4 | bit(27) << 3 | bit(28) << 2 | bit(29) << 1 | bit(30));
-            }
-        }
-        __syncthreads();
-        __shared__ int sh_do_search;
-        if (t == 0) {
-            unsigned good = 0;
-            for (int r = 0; r < 2 * MAXREF; r++)
-                if (sm.ref_ok[r]) good++;
-            sh_do_search = 0;
-            if (good >= 4) {
-                // strict majorities; the PSMI majority is only looked for among 0..15 (sync.c:396)
-                int mbc = -1, mps = -1;
-                for (int v = 0; v < 16; v++) {
-                    unsigned nbc = 0, nps = 0;
-                    for (int r = 0; r < 2 * MAXREF; r++) {
-                        if (!sm.ref_ok[r]) continue;
-                        nbc += sm.ref_bc[r] == v;
-                        nps += sm.ref_psmi[r] == v;
-                    }
-                    if (nbc > good / 2) mbc = v;
-                    if (nps > good / 2) mps = v;
-                }
-                if (mbc >= 0 && mps >= 0) {
-                    st.bc = mbc;
-                    st.psmi = mps;
-                    set_state(p, d, s, ST_FINE);
-                    st.started_pm = 0;                   // decode_reset (decode.c:556-565)
-                }
-            } else if (st.cfo_wait == 0) {
-                sh_do_search = 1;
-            } else {
-                st.cfo_wait--;
-            }
-        }
-        __syncthreads();
-        if (sh_do_search && t < 32) {            // detect_cfo (sync.c:292-337), warp 0
-            const int lane = t;
-            for (int cfo = -2 * PW; cfo < 2 * PW; cfo++) {
-                int off = -1;
-                if (lane < 22) {
-                    int i = lane >> 1, upper = lane & 1;
-                    int b = upper ? cfo + UB1 - i * PW : cfo + LB0 + i * PW;
-                    int ci = compact_of_bin(b);
-                    float2 *row = ci >= 0 ? &sm.z[ci * ZLD] : sm.zero_row;
-                    costas_row(row, 1, sm.tmp_phs[lane], cfreq[b], cphase[b], cfo, alpha, beta);
-                    off = ref_find(row, 1, (unsigned)(30 - i) & 3);
-                    for (int n = 0; n < BLK; n++)            // reset_ref (sync.c:132-136)
-                        row[n] = cmulf(row[n], cexp_j(sm.tmp_phs[lane][n]));
-                    if (ci < 0)
-                        for (int n = 0; n < BLK; n++) row[n] = make_float2(0.f, 0.f);
-                }
-                sm.offs[lane] = off;
-                __syncwarp();
-                int found = 0;
-                if (lane == 0) {
-                    int best = -1;
-                    unsigned bestn = 0;
-                    for (int k = 0; k < BLK; k++) {
-                        unsigned nv = 0;
-                        for (int r = 0; r < 22; r++) nv += sm.offs[r] == k;
-                        if (nv > bestn) { best = k; bestn = nv; }
-                    }
-                    if (best >= 0 && bestn >= 3) {
-                        st.keep_extra = ((BLK - best) % BLK) * NSYM;
-                        st.cfo += cfo;
-                        st.cfo_wait = 8;
-                        found = 1;
-                    }
-                }
-                found = __shfl_sync(0xffffffffu, found, 0);
-                if (found) break;
-            }
-        }
-        __syncthreads();
-        ppb = partitions_per_band(st.psmi);      // psmi may have changed with the FINE decision
-        nref = ppb + 1;
-    }
-
-    if (st.state == ST_FINE) {
-        // reference amplitude per subcarrier (calc_smag, sync.c:254-261)
-        if (t < 2 * MAXREF) {
-            int side = t / MAXREF, i = t - side * MAXREF;
-            if (i < nref) {
-                const float2 *z = &sm.z[compact_of_bin(ref_bin(t, nref)) * ZLD];
-                float sum = 0;
-                for (int n = 0; n < BLK; n++) sum += fabsf(z[n].x);
-                sm.smag[t] = sum / BLK;
-            }
-        }
-        __syncthreads();
-        // adjust_data (sync.c:263-282): one thread per (partition, symbol)
-        for (int item = t; item < 2 * ppb * BLK; item += SYNC_THREADS) {
-            int n = item & (BLK - 1), pp = item >> 5;
-            int upper = pp >= ppb, i = upper ? pp - ppb : pp;
-            int lo_bin, slot_lo, slot_hi;
-            if (!upper) { lo_bin = LB0 + PW * i; slot_lo = i; slot_hi = i + 1; }
-            else { lo_bin = UB1 - PW * i - PW; slot_lo = MAXREF + i + 1; slot_hi = MAXREF + i; }
-            float m0 = sm.smag[slot_lo], m19 = sm.smag[slot_hi];
-            float2 up = cexp_j(sm.phs[slot_hi][n]);
-            float2 lp = cexp_j(sm.phs[slot_lo][n]);
-            float2 *zc = &sm.z[compact_of_bin(lo_bin) * ZLD + n];
-            for (int k = 1; k < PW; k++) {
-                float fa = (float)k * m19, fb = (float)(PW - k) * m0;
-                float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
-                const float rden = 19.0f / (c * c + dd * dd);
-                // (19 + 19j) / (c + j dd)
-                float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
-                zc[k * ZLD] = cmulf(zc[k * ZLD], C);
-            }
-        }
-        // timing / phase feedback (sync.c:426-463)
-        if (t == 0) {
-            float samperr = 0, angle = 0, sum_xy = 0, sum_x2 = 0;
-            for (int i = 0; i < ppb; i++) {
-                samperr += half_pi_wrap(sm.phs[i][0], sm.phs[i + 1][0]);
-                samperr += half_pi_wrap(sm.phs[MAXREF + i + 1][0], sm.phs[MAXREF + i][0]);
-            }
-            samperr = (float)((double)(samperr / (float)(ppb * 2) * (float)NFFT / (float)PW) / (2 * M_PI));
-            for (int i = 0; i <= ppb; i++) {
-                float x, y;
-                x = (float)(LB0 + PW * i - NFFT / 2);
-                y = cfreq[LB0 + PW * i];
-                angle += y; sum_xy += x * y; sum_x2 += x * x;
-                x = (float)(UB1 - PW * i - NFFT / 2);
-                y = cfreq[UB1 - PW * i];
-                angle += y; sum_xy += x * y; sum_x2 += x * x;
-            }
-            samperr = (float)((double)samperr - (double)((sum_xy / sum_x2) * (float)NFFT) / (2 * M_PI) * BLK);
-            st.samperr = (int)roundf(samperr);
-            angle /= (float)((ppb + 1) * 2);
-            st.angle = angle;
-            for (int i = 0; i <= ppb; i++) {
-                cfreq[LB0 + PW * i] -= angle;
-                cfreq[UB1 - PW * i] -= angle;
-            }
-        }
-        __syncthreads();
-        // modulation error (sync.c:465-488): 8 threads per symbol take the partitions round-robin, the
-        // partial sums are then combined in a fixed order (per symbol, then over symbols)
-        {
-            const int n = t & (BLK - 1), g = t >> 5;           // SYNC_THREADS == 8 * BLK
-            float e_lb = 0, e_ub = 0;
-            for (int i = g; i < ppb; i += SYNC_THREADS / BLK)
-                for (int j = 1; j < PW; j++) {
-                    float2 c = sm.z[compact_of_bin(LB0 + PW * i + j) * ZLD + n];
-                    float dx = (c.x >= 0 ? 1.0f : -1.0f) - c.x, dy = (c.y >= 0 ? 1.0f : -1.0f) - c.y;
-                    e_lb += dx * dx + dy * dy;
-                    c = sm.z[compact_of_bin(UB1 - PW * i - PW + j) * ZLD + n];
-                    dx = (c.x >= 0 ? 1.0f : -1.0f) - c.x; dy = (c.y >= 0 ? 1.0f : -1.0f) - c.y;
-                    e_ub += dx * dx + dy * dy;
-                }
-            sm.mer_lb[g][n] = e_lb;
-            sm.mer_ub[g][n] = e_ub;
-        }
-        __syncthreads();
-        if (t < BLK) {
-            float e_lb = 0, e_ub = 0;
-            for (int g = 0; g < SYNC_THREADS / BLK; g++) { e_lb += sm.mer_lb[g][t]; e_ub += sm.mer_ub[g][t]; }
-            sm.part_lb[t] = e_lb;
-            sm.part_ub[t] = e_ub;
-        }
-        __syncthreads();
-        if (t == 0) {
-            float e_lb = 0, e_ub = 0;
-            for (int n = 0; n < BLK; n++) { e_lb += sm.part_lb[n]; e_ub += sm.part_ub[n]; }
-            st.err_lb += e_lb;
-            st.err_ub += e_ub;
-            if (++st.mer_cnt == 16) {
-                float signal = (float)(2 * BLK * (ppb * 18) * st.mer_cnt);
-                uint8_t *w = log_reserve(p, d, s, REC_MER, 8);
-                if (w) {
-                    reinterpret_cast<float *>(w)[0] = 10 * log10f(signal / st.err_lb);
-                    reinterpret_cast<float *>(w)[1] = 10 * log10f(signal / st.err_ub);
-                }
-                st.mer_cnt = 0;
-                st.err_lb = 0;
-                st.err_ub = 0;
-            }
-            const float mer_lb = 2.0f * BLK * (float)(ppb * 18) / e_lb;
-            const float mer_ub = 2.0f * BLK * (float)(ppb * 18) / e_ub;
-            sm.mult_lb = fmaxf(fminf(mer_lb * 10, 127.0f), 1.0f);
-            sm.mult_ub = fmaxf(fminf(mer_ub * 10, 127.0f), 1.0f);
-        }
-        __syncthreads();
-        // soft demap of the primary-main partitions (sync.c:509-536) into the interleaver matrix
-        const int bc = st.bc;
-        {
-            int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
-            const float mlb = sm.mult_lb, mub = sm.mult_ub;
-            for (int col = t; col < 720; col += SYNC_THREADS) {      // one matrix column per thread, all 32 symbols
-                const int part = col / 36, c = col - part * 36;
-                const int j = 1 + (c >> 1);
-                const int b = part < 10 ? LB0 + PW * part + j : (UB1 - 10 * PW) + PW * (part - 10) + j;
-                const float2 *zc = &sm.z[compact_of_bin(b) * ZLD];
-                const float mult = part < 10 ? mlb : mub;
-                for (int n = 0; n < BLK; n++) {
-                    const float2 v = zc[n];
-                    pm[n * 720 + col] = soft_demap((c & 1) ? v.y : v.x, mult);
-                }
-            }
-        }
-        __syncthreads();
-        if (d.emit_soft) {
-            __shared__ uint8_t *sh_w;
-            if (t == 0) {
-                sh_w = log_reserve(p, d, s, REC_SOFT_PM, 4 + PM_BLOCK);
-                if (sh_w) *reinterpret_cast<uint32_t *>(sh_w) = (uint32_t)bc;
-            }
-            __syncthreads();
-            if (sh_w) {
-                const int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
-                for (int o = t; o < PM_BLOCK; o += SYNC_THREADS) sh_w[4 + o] = (uint8_t)pm[o];
-            }
-            __syncthreads();
-        }
-        // PIDS (decode.c:463-471): the 80-bit frame of this block is decoded by the next demodulator launch
-        // (k_demod, symbol-0 CTA) so that its ~150 serial trellis steps stay off this kernel's critical
-        // path; the record slot is reserved here to keep the stream's record order.
-        if (t == 0) {
-            uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
-            st.pids_rec = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
-            st.pids_bc = bc;
-            st.pids_pending = 1;
-            // P1 bookkeeping (decode.c:383-390)
-            if (bc == 0) st.started_pm = 1;
-            if (st.started_pm && bc == 15) st.p1_ready = 1;
-            st.bc = (bc + 1) % 16;
-        }
-    }
-    __syncthreads();
-    if (t == 0) {                                // window overlap carry (acquire.c:259-262)
-        int keep = NSYM + (NSYM / 2 - st.blk_samperr) + st.keep_extra;
-        st.keep_extra = 0;
-        st.start += NACQ - keep;
-        st.blocks_done++;
-    }
-}
-
-__global__ void __launch_bounds__(SYNC_THREADS) k_sync(DevPtrs p, EngineDims d)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
-    const int s = blockIdx.x, t = threadIdx.x;
-    if (p.st[s].active) sync_block(p, d, sm, s, t);
-}
 
 // ===========================================================================
 // P1 decode: for every stream whose interleaver matrix is complete —
@@ -815,7 +168,7 @@ __host__ __device__ inline VitcArgs p1_vitc_args(const DevPtrs &dp)
 constexpr size_t VITC_EMIT_SMEM = (size_t)VITC_EMIT_WARPS * VITC_EMIT_STEPS * sizeof(uint2);
 
 // input_reset for a range of streams (reference src/input.c:126-138)
-__global__ void k_reset(DevPtrs p, EngineDims d, int only)
+__global__ void k_reset(DevPtrs p, EngineDims d, int only, unsigned long long round0)
 {
     const int s = blockIdx.x, t = threadIdx.x;
     if (only >= 0 && s != only) return;
@@ -833,6 +186,8 @@ __global__ void k_reset(DevPtrs p, EngineDims d, int only)
         z.state = ST_NONE;
         z.force_state = -1;
         z.in_avail = only == -2 ? avail : 0;     // -2: keep the attached input (rewind)
+        z.q_prepped = round0;
+        z.q_synced = round0;
         st = z;
     }
 }
@@ -898,7 +253,10 @@ struct nrsc5b_engine {
     StreamState *h_state;              // pinned mirror for read-back
     nrsc5b_stats_t stats;
     unsigned long long last_progress;
-    size_t sync_smem;
+    unsigned long long round0;         // rounds launched so far (task-queue epoch)
+    int front_grid;                    // resident CTAs of k_front
+    unsigned *d_ticket;
+    int *d_error;
     std::vector<void *> allocs;
     int profiling;
     cudaEvent_t pev[5];
@@ -994,6 +352,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->iq_owned = nullptr;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
+    e->round0 = 0;
     e->profiling = 0;
     for (int i = 0; i < 5; i++) e->pev[i] = nullptr;
     for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
@@ -1099,11 +458,20 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         nrsc5b_destroy(e);
         return NRSC5B_ENOMEM;
     }
-    e->sync_smem = sizeof(SyncSmem);
-    if (cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->sync_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess) {
-        nrsc5b_destroy(e);
-        return NRSC5B_ECUDA;
+    {
+        const int smem = (int)sizeof(FrontSmem);
+        int per_sm = 0, dev = cfg->device, sms = 0;
+        if (cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, smem) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm < 1 ||
+            cudaGetSymbolAddress((void **)&e->d_ticket, g_ticket) != cudaSuccess ||
+            cudaGetSymbolAddress((void **)&e->d_error, g_error) != cudaSuccess) {
+            nrsc5b_destroy(e);
+            return NRSC5B_ECUDA;
+        }
+        // every CTA must be resident at once: the task queue lets CTAs wait for work held by other CTAs
+        e->front_grid = per_sm * sms;
     }
     *out = e;
     rc = nrsc5b_reset(e, -1);
@@ -1139,7 +507,7 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
     if (!e || stream >= e->dims.nstreams) return NRSC5B_EINVAL;
     const int S = e->dims.nstreams;
     CK(cudaStreamSynchronize(e->copy_stream));       // no input copy of the old contents may still be in flight
-    k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream);
+    k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream, e->round0);
     CK(cudaEventRecord(e->reset_done, e->stream));
     CK(cudaStreamWaitEvent(e->copy_stream, e->reset_done, 0));
     e->stats.kernel_launches += 1;
@@ -1156,7 +524,7 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
 extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
 {
     if (!e) return NRSC5B_EINVAL;
-    k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2);
+    k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2, e->round0);
     e->stats.kernel_launches += 1;
     for (int s = 0; s < e->dims.nstreams; s++) e->drained[s] = 0;
     CK(cudaGetLastError());
@@ -1253,34 +621,31 @@ static void launch_p1(nrsc5b_engine *e)
     e->stats.kernel_launches += 5;
 }
 
-static int launch_step(nrsc5b_engine *e, bool with_p1)
+// nrounds rounds of the front end for every stream (one persistent launch), then — if asked — the P1 decode
+static int launch_rounds(nrsc5b_engine *e, int nrounds, bool with_p1)
 {
-    const int S = e->dims.nstreams;
     const bool prof = e->profiling != 0;
+    CK(cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned), e->stream));
     if (prof) cudaEventRecord(e->pev[0], e->stream);
-    k_prep<<<S, PREP_THREADS, 0, e->stream>>>(e->dp, e->dims);
+    k_front<<<e->front_grid, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, e->round0, nrounds);
+    e->round0 += (unsigned long long)nrounds;
+    e->stats.kernel_launches += 1;
     if (prof) cudaEventRecord(e->pev[1], e->stream);
-    launch_demod(e->dp, e->dims, e->stream);
-    if (prof) cudaEventRecord(e->pev[2], e->stream);
-    k_sync<<<S, SYNC_THREADS, e->sync_smem, e->stream>>>(e->dp, e->dims);
-    if (prof) cudaEventRecord(e->pev[3], e->stream);
     if (with_p1) launch_p1(e);
     if (prof) {
-        cudaEventRecord(e->pev[4], e->stream);
-        cudaEventSynchronize(e->pev[4]);
-        for (int i = 0; i < 4; i++) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, e->pev[i], e->pev[i + 1]);
-            e->kernel_ms[i] += ms;
-            e->kernel_n[i] += 1;
-        }
+        cudaEventRecord(e->pev[2], e->stream);
+        cudaEventSynchronize(e->pev[2]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->pev[0], e->pev[1]);
+        e->kernel_ms[1] += ms; e->kernel_n[1] += 1;
+        cudaEventElapsedTime(&ms, e->pev[1], e->pev[2]);
+        e->kernel_ms[3] += ms; e->kernel_n[3] += with_p1 ? 1 : 0;
     }
-    e->stats.kernel_launches += 3;
     return 0;
 }
 
 /* Per-kernel device time (CUDA events around every launch; slows the run down, use a separate pass).
- * Order: prep, demod, sync, p1. */
+ * Slots: [1] = the fused front-end kernel k_front, [3] = the P1 decode group; [0],[2] unused. */
 extern "C" int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on)
 {
     if (!e) return NRSC5B_EINVAL;
@@ -1335,11 +700,23 @@ static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
             }
         }
         p1_steps |= 1u << (batch - 1);
-        for (int i = 0; i < batch; i++) launch_step(e, e->profiling || ((p1_steps >> i) & 1u));
+        for (int i0 = 0; i0 < batch; ) {                      // one persistent launch up to each P1 step
+            int i1 = i0;
+            while (!((p1_steps >> i1) & 1u)) i1++;
+            int rc = launch_rounds(e, i1 - i0 + 1, true);
+            if (rc) return rc;
+            i0 = i1 + 1;
+        }
         unsigned long long prog = 0;
+        int err = 0;
         CK(cudaMemcpyFromSymbolAsync(&prog, g_progress, sizeof(prog), 0, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(&err, e->d_error, sizeof(err), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
+        if (err) {
+            fprintf(stderr, "nrsc5_b200: front-end task queue timed out\n");
+            return NRSC5B_ECUDA;
+        }
         const unsigned long long delta = prog - e->last_progress;
         e->last_progress = prog;
         if (delta == 0) {

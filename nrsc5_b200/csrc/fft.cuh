@@ -8,9 +8,17 @@ namespace nb {
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex multiply with explicit fused multiply-adds (this header is also used by translation units
+// built with -fmad=false)
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
+}
+// barrier over one 128-thread half of a CTA (id 1 or 2), or the whole CTA (id 0)
+__device__ __forceinline__ void bar_sync(int id)
+{
+    if (id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory");
 }
 __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }   // * (-j)
 
@@ -69,7 +77,7 @@ constexpr int FFT_SMEM_ELEMS = 16 * FFT_LD;        // 2064 float2
 // q = t + 128*h, h = 0..1, k3 = 0..7.  `buf` is FFT_SMEM_ELEMS float2 of
 // shared memory; `twid[m] = exp(-2*pi*i*m/2048)`.
 __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float2 *buf,
-                                              const float2 *__restrict__ twid, int t)
+                                              const float2 *__restrict__ twid, int t, int bar = 0)
 {
     // pass 1: DFT-16 over n1, twiddle W^(r*k1), store A[k1][r]
     fft16(v);
@@ -79,7 +87,7 @@ __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float
         if (k1) x = cmul(x, __ldg(&twid[t * k1]));
         buf[k1 * FFT_LD + t] = x;
     }
-    __syncthreads();
+    bar_sync(bar);
     // pass 2: thread (k1, n3): DFT-16 over n2, twiddle W^(16*n3*k2)
     {
         const int k1 = t & 15, n3 = t >> 4;
@@ -87,7 +95,7 @@ __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float
 #pragma unroll
         for (int n2 = 0; n2 < 16; n2++) u[n2] = buf[k1 * FFT_LD + n2 * 8 + n3];
         fft16(u);
-        __syncthreads();
+        bar_sync(bar);
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             float2 x = u[k2];
@@ -95,7 +103,7 @@ __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float
             buf[n3 * 256 + k2 * 16 + k1] = x;
         }
     }
-    __syncthreads();
+    bar_sync(bar);
     // pass 3: DFT-8 over n3 for q = k1 + 16*k2
 #pragma unroll
     for (int h = 0; h < 2; h++) {

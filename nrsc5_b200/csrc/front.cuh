@@ -1,0 +1,886 @@
+// The fused, persistent front-end kernel: for every stream and every 32-symbol
+// block it runs
+//
+//   prep   window check, coarse acquisition when not in FINE sync, feedback, NCO      (acquire.c:98-168)
+//   demod  cu8 -> halfband -> NCO/window/fold -> 2048-pt FFT -> 534 bins, 32 symbols  (input.c:52-94,
+//                                                   firdecim_q15.c:137-165, acquire.c:237-257, sync.c:779-790)
+//   sync   Costas, COARSE->FINE vote / CFO search, equalise, feedback, MER, soft demap (sync.c:90-610)
+//   pids   the previous block's PIDS frame                                            (decode.c:463-471)
+//
+// as *tasks* taken from one ticket counter.  A task is (round r, stream s, k), k = 0..15, and covers
+// OFDM symbols 2k and 2k+1 of the stream's block in that round (two 128-thread halves of the CTA, one
+// symbol each).  Task k = 0 first waits for the stream's previous round to be synced, decodes the
+// pending PIDS frame and runs `prep`; tasks k > 0 wait for that prep.  The CTA that finishes the
+// stream's 16th task runs `sync` for the block.  Tickets are handed out in (r, s, k) order and every
+// CTA of the (fully resident) grid only ever waits for work with a smaller ticket, so the scheme cannot
+// deadlock; other streams' tasks fill the SMs while one stream's 32-step Costas recurrences run.
+//
+// This translation unit is compiled with -fmad=false and -dlcm=cg: float expressions keep the
+// reference's evaluation order wherever a discrete decision depends on them, and plain global loads
+// bypass the (non-coherent) L1 so that data produced by another CTA in an earlier task is never read
+// stale.  Read-only tables and the input samples use __ldg.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+#include "viterbi_pack.cuh"
+
+namespace nb {
+
+constexpr int FRONT_THREADS = 256;
+constexpr int TASKS_PER_BLOCK = BLK / 2;           // 16 tasks of two symbols
+constexpr int MAXREF = 15;                         // reference subcarriers per sideband (14 partitions + 1)
+constexpr int IN_BYTES = 4 * NSYM + 28 + 16 + 16;  // staged cu8 bytes per symbol (+ alignment slack) = 8700
+constexpr int IN_STRIDE = 8704;
+
+__device__ unsigned long long g_progress;          // bumped by every stream that processed a block
+__device__ unsigned g_ticket;                      // task queue head (reset by the host before each launch)
+__device__ int g_error;                            // set if a wait timed out (never expected)
+
+__constant__ int c_compat_mode[64];
+__constant__ short c_bp_tap[32];                   // coarse band-pass taps, tap[i] pairs w[i] and w[32-i]
+
+// complex helpers with the reference's (gcc, no FMA) evaluation order
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cexp_j(float a)       // cexpf(I*a)
+{
+    float s, c;
+    sincosf(a, &s, &c);
+    return make_float2(c, s);
+}
+
+__device__ __forceinline__ int partitions_per_band(int psmi)
+{
+    switch (c_compat_mode[psmi & 63]) {
+    case 2: return 11;
+    case 3: return 12;
+    case 5: case 6: case 11: return 14;
+    default: return 10;
+    }
+}
+
+// input_set_sync_state (reference src/input.c:172-188)
+__device__ void set_state(const DevPtrs &p, const EngineDims &d, int s, int ns)
+{
+    StreamState &st = p.st[s];
+    if (st.state == ns) return;
+    if (st.state == ST_FINE) log_reserve(p, d, s, REC_LOST_SYNC, 0);
+    if (ns == ST_FINE) {
+        float fo = (float)(((double)st.prev_angle - 2 * M_PI * st.cfo) * 744187.5 / (2 * M_PI * NFFT));
+        uint8_t *w = log_reserve(p, d, s, REC_SYNC, 8);
+        if (w) {
+            reinterpret_cast<float *>(w)[0] = fo;
+            reinterpret_cast<int *>(w)[1] = st.psmi;
+        }
+    }
+    st.state = ns;
+}
+
+// ---------------------------------------------------------------------------
+// shared memory: one buffer, reinterpreted per task phase
+// ---------------------------------------------------------------------------
+struct DemodSmem {
+    uint8_t in[2][IN_STRIDE];                      // staged cu8 of the two symbols
+    float2 buf[2][FFT_SMEM_ELEMS];                 // FFT exchange buffers
+    float2 symphase[2];
+};
+struct PrepSmem {
+    float2 sums[NSYM];
+    float red_mag[FRONT_THREADS];
+    int red_idx[FRONT_THREADS];
+    float2 red_v[FRONT_THREADS];
+};
+struct SyncSmem {
+    float2 zref[2 * MAXREF][BLK];                  // reference carriers after their Costas loop
+    float phs[2 * MAXREF][BLK];                    // Costas phase per reference and symbol
+    float smag[2 * MAXREF];
+    float err_lb[2 * MAXPART][BLK], err_ub[2 * MAXPART][BLK];   // per (partition, symbol) error sums
+    float part_lb[BLK], part_ub[BLK];
+    float2 rows[22][BLK];                          // CFO search: working rows
+    float tmp_phs[22][BLK];
+    int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
+    int offs[32];
+    float mult_lb, mult_ub;
+    int do_search;
+};
+struct PidsSmem {
+    int8_t vit[PIDS_LEN * 3];
+    uint2 dec[PIDS_LEN + 64];
+};
+union FrontSmem {
+    DemodSmem demod;
+    PrepSmem prep;
+    SyncSmem sync;
+    PidsSmem pids;
+};
+
+// ---------------------------------------------------------------------------
+// pids: interleaver II + depuncture (decode.c:324-342), K=7 Viterbi, descramble (decode.c:279-294)
+// ---------------------------------------------------------------------------
+__device__ void front_pids(const DevPtrs &p, const EngineDims &d, int s, PidsSmem &sm, int t)
+{
+    StreamState &st = p.st[s];
+    const int bc = st.pids_bc;
+    const int8_t *pmall = p.pm + (size_t)s * 16 * PM_BLOCK;
+    const int8_t PMV[20] = { 10, 2, 18, 6, 14, 8, 16, 0, 12, 4, 11, 3, 19, 7, 15, 9, 17, 1, 13, 5 };
+    for (int o = t; o < PIDS_LEN * 3; o += FRONT_THREADS) {
+        int8_t v = 0;
+        if (o % 6 != 5) {
+            unsigned i = (unsigned)bc * 200 + (unsigned)(o - o / 6);
+            unsigned part = (unsigned)PMV[i % 20];
+            unsigned block = i / 200;
+            unsigned k = (i / 20) % 10 + P1_ENC / 320;
+            unsigned row = (k * 11) % 32, col = (k * 11 + k / 288) % 36;
+            v = pmall[(block * 32 + row) * 720 + part * 36 + col];
+        }
+        sm.vit[o] = v;
+    }
+    __syncthreads();
+    if (t < 32) {
+        // both half-warps decode the same frame (the packed kernel works on two chunks per warp); FM PIDS
+        // soft bits are punctured 1,1,1,1,1,0, so the int16 metrics cannot saturate
+        const int l = t & 15;
+        VitHalf<false> vh;
+        vh.init(l);
+        vitc_run<false>(vh, sm.vit, PIDS_LEN, PIDS_LEN + 64, 0, PIDS_LEN + 64, 0, sm.dec, t < 16, l);
+        __syncwarp();
+        // first maximum in state order; lane l holds states 2l, 2l+32 (E) and 2l+1, 2l+33 (O)
+        int v = (short)(vh.E & 0xffff), state = 2 * l;
+        const int w1 = (short)(vh.O & 0xffff);
+        if (w1 > v) { v = w1; state = 2 * l + 1; }
+        int v2 = (short)(vh.E >> 16), idx2 = 2 * l + 32;
+        const int w3 = (short)(vh.O >> 16);
+        if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
+        if (v2 > v) { v = v2; state = idx2; }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, state, o, 16);
+            if (ov > v || (ov == v && oi < state)) { v = ov; state = oi; }
+        }
+        if (t == 0) {
+            uint8_t pk[10];
+            for (int i = 0; i < 10; i++) pk[i] = 0;
+            for (int q = PIDS_LEN + 63; q >= 0; q--) {
+                if (q >= 32 && q < 32 + PIDS_LEN) {
+                    const int i = q - 32;
+                    const int bit = ((state >> 5) & 1) ^ __ldg(&p.pn[i]);
+                    pk[i >> 3] |= (uint8_t)(bit << (7 - (i & 7)));
+                }
+                state = vitc_prev_head(state, sm.dec, q);
+            }
+            if (st.pids_rec != 0xffffffffu) {
+                uint8_t *w = p.log + (size_t)s * d.log_cap + st.pids_rec;
+                for (int i = 0; i < 10; i++) w[i] = pk[i];
+            }
+            st.pids_pending = 0;
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// prep (reference src/acquire.c:98-168, src/sync.c:769-777, src/firdecim_q15.c:95-109,154-158)
+// ---------------------------------------------------------------------------
+__device__ void front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, int t)
+{
+    StreamState &st = p.st[s];
+    __shared__ int sh_active, sh_samperr;
+    __shared__ float sh_angle;
+    if (t == 0) {
+        if (st.force_state >= 0) {
+            set_state(p, d, s, st.force_state);
+            st.force_state = -1;
+        }
+        const int act = st.in_avail >= 2 * (st.start + NACQ);
+        st.active = act;
+        sh_active = act;
+        if (act) atomicAdd(&g_progress, 1ull);
+    }
+    __syncthreads();
+    if (!sh_active) return;
+
+    const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
+    const int state_in = st.state;
+    if (state_in != ST_FINE) {
+        short2 *y = p.ydec + (size_t)s * NACQ;
+        float2 *tb = p.tbuf + (size_t)s * NACQ;
+        const long long start = st.start;
+        for (int i = t; i < NACQ; i += FRONT_THREADS) y[i] = halfband_at(iq, start + i);
+        __syncthreads();
+        // 32-tap symmetric Q15 band-pass; history = last 31 samples of the previous coarse window
+        for (int i = t; i < NACQ; i += FRONT_THREADS) {
+            auto at = [&](int pos) -> short2 {
+                if (pos >= 0) return y[pos];
+                return make_short2(st.bp_hist[31 + pos][0], st.bp_hist[31 + pos][1]);
+            };
+            short accr = 0, acci = 0;
+#pragma unroll 5
+            for (int k = 1; k < 16; k++) {
+                short2 a = at(i - 31 + k), b = at(i - 31 + 32 - k);
+                accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
+                acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
+            }
+            short2 c = at(i - 31 + 16);
+            accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
+            acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
+            tb[i] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
+        }
+        __syncthreads();
+        if (t < 31) {
+            short2 v = y[NACQ - 31 + t];
+            st.bp_hist[t][0] = v.x;
+            st.bp_hist[t][1] = v.y;
+        }
+        // cyclic-prefix correlation per sample offset (acquire.c:129-134)
+        for (int i = t; i < NSYM; i += FRONT_THREADS) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int j = 0; j < BLK; j++) {
+                float2 a = tb[i + j * NSYM], b = tb[i + j * NSYM + NFFT];
+                float2 pr = cmulf(a, make_float2(b.x, -b.y));
+                acc.x += pr.x;
+                acc.y += pr.y;
+            }
+            sm.sums[i] = acc;
+        }
+        __syncthreads();
+        // pulse-shaped sliding sum and arg-max (acquire.c:136-151)
+        float best = -1.0f;
+        int besti = 0;
+        float2 bestv = make_float2(0.f, 0.f);
+        for (int i = t; i < NSYM; i += FRONT_THREADS) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int j = 0; j < NCP; j++) {
+                int q = i + j;
+                if (q >= NSYM) q -= NSYM;
+                const float2 sv = sm.sums[q];
+                const float a = __ldg(&p.shape[j]), b = __ldg(&p.shape[j + NFFT]);
+                v.x += (sv.x * a) * b;
+                v.y += (sv.y * a) * b;
+            }
+            const float mag = v.x * v.x + v.y * v.y;
+            if (mag > best) { best = mag; besti = i; bestv = v; }
+        }
+        sm.red_mag[t] = best; sm.red_idx[t] = besti; sm.red_v[t] = bestv;
+        __syncthreads();
+        for (int o = FRONT_THREADS / 2; o; o >>= 1) {
+            if (t < o) {
+                const float m2 = sm.red_mag[t + o];
+                const int i2 = sm.red_idx[t + o];
+                if (m2 > sm.red_mag[t] || (m2 == sm.red_mag[t] && i2 < sm.red_idx[t])) {
+                    sm.red_mag[t] = m2; sm.red_idx[t] = i2; sm.red_v[t] = sm.red_v[t + o];
+                }
+            }
+            __syncthreads();
+        }
+        if (t == 0) {
+            const float2 w = cmulf(sm.red_v[0], cexp_j(-st.prev_angle));
+            const float angle_diff = atan2f(w.y, w.x);
+            const float factor = (st.prev_angle != 0.0f) ? 0.25f : 1.0f;
+            const float angle = st.prev_angle + (angle_diff * factor);
+            st.prev_angle = angle;
+            sh_angle = angle;
+            sh_samperr = (sm.red_idx[0] + NSYM - 15) % NSYM;
+            if (st.state == ST_NONE) st.state = ST_COARSE;
+        }
+    } else if (t == 0) {
+        sh_samperr = NSYM / 2 + st.samperr;
+        st.samperr = 0;
+        const float angle = st.prev_angle + (-st.angle);
+        st.angle = 0;
+        st.prev_angle = angle;
+        sh_angle = angle;
+    }
+    __syncthreads();
+
+    const int samperr = sh_samperr;
+    const int adj = NSYM / 2 - samperr;
+    if (adj != 0) {                                            // sync_adjust, sync.c:769-777
+        float *cp = p.cphase + (size_t)s * NFFT;
+        for (int i = t; i < SIDE; i += FRONT_THREADS) {
+            const int bl = LB0 + i, bu = UB1 - i;
+            cp[bl] = (float)((double)cp[bl] - (double)(adj * (bl - NFFT / 2) * 2) * M_PI / NFFT);
+            cp[bu] = (float)((double)cp[bu] - (double)(adj * (bu - NFFT / 2) * 2) * M_PI / NFFT);
+        }
+    }
+    if (t == 0) {
+        float angle = sh_angle;
+        angle = (float)((double)angle - 2 * M_PI * st.cfo);
+        const float pre = (float)(-adj) * angle / (float)NFFT;
+        const float2 ph = cmulf(st.phase, cexp_j(pre));
+        const float theta = angle / (float)NFFT;
+        st.phase0 = ph;
+        st.theta = theta;
+        st.blk_samperr = samperr;
+        st.blk_state_in = state_in;
+        // NCO phase after the 32 symbols of this block (acquire.c:250-252, closed form)
+        double sn, cs;
+        sincos((double)theta * (double)(NSYM * BLK), &sn, &cs);
+        const float2 pe = cmulf(ph, make_float2((float)cs, (float)sn));
+        const float nrm = sqrtf(pe.x * pe.x + pe.y * pe.y);
+        st.phase = make_float2(pe.x / nrm, pe.y / nrm);
+        uint8_t *w = log_reserve(p, d, s, REC_BLOCK, 32);
+        if (w) {
+            int *wi = reinterpret_cast<int *>(w);
+            float *wf = reinterpret_cast<float *>(w);
+            wi[0] = state_in; wi[1] = samperr; wf[2] = angle; wf[3] = ph.x; wf[4] = ph.y; wi[5] = st.cfo;
+            wi[6] = (int)(unsigned)(st.start & 0xffffffffLL);
+            wi[7] = (int)(st.start >> 32);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// demod: one OFDM symbol per 128-thread half of the CTA
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 sample_at(const uint32_t *sw, int j)
+{
+    // sw points at the 32-bit word holding input samples (2*base-14, 2*base-13); word q of output j
+    // holds samples m = 2q (low half) and m = 2q+1 (high half) of the 15-sample halfband window
+    uint32_t w[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) w[q] = sw[j + q];
+    const int tap[4] = { -134, 1078, -4417, 19864 };
+    int ar = 0, ai = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t a = w[k], b = w[7 - k];
+        const int sr = (int)(a & 0xff) + (int)(b & 0xff) - 254;
+        const int si = (int)((a >> 8) & 0xff) + (int)((b >> 8) & 0xff) - 254;
+        // ((64*sr) * tap) >> 15  ==  (sr * tap) >> 9   (exact)
+        ar += (sr * tap[k]) >> 9;
+        ai += (si * tap[k]) >> 9;
+    }
+    ar += ((int)((w[3] >> 16) & 0xff) - 127) * 64;
+    ai += ((int)(w[3] >> 24) - 127) * 64;
+    const float sc = 1.0f / 32767.0f;
+    return make_float2((float)ar * sc, (float)ai * -sc);      // conj(x)/32767, acquire.c:160-161
+}
+
+__device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sym, DemodSmem &sm, int half, int tl,
+                            long long start, int samperr, float theta, float2 phase0)
+{
+    uint8_t *in = sm.in[half];
+    float2 *buf = sm.buf[half];
+    const int bar = 1 + half;                            // named barrier of this 128-thread half
+    const long long base = start + samperr + (long long)NSYM * sym;
+    const long long b0 = 4 * base - 28;                  // first needed cu8 byte (may be < 0 at stream start)
+    const long long b0a = b0 & ~15LL;
+    const int off = (int)(b0 - b0a);
+    const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
+    {
+        const int nvec = (off + 4 * NSYM + 28 + 15) / 16;
+        uint4 *dst = reinterpret_cast<uint4 *>(in);
+        for (int v = tl; v < nvec; v += 128) {
+            const long long a = b0a + 16LL * v;
+            dst[v] = a >= 0 ? __ldg(reinterpret_cast<const uint4 *>(iq + a))
+                            : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+        }
+    }
+    if (tl == 0) {
+        double sn, cs;
+        sincos((double)theta * (double)(NSYM * sym), &sn, &cs);
+        sm.symphase[half] = cmul(phase0, make_float2((float)cs, (float)sn));
+    }
+    bar_sync(bar);
+
+    // NCO in closed form: exp(j*theta*j), j = n1*128 + tl, advanced by exp(j*theta*128) per n1
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(in + off);
+    float2 ph = cexp_j(theta * (float)tl);
+    const float2 step = cexp_j(theta * 128.0f);
+    float2 v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int j = n1 * 128 + tl;
+        float2 x = cmul(sample_at(sw, j), ph);
+        if (n1 == 0 && tl < NCP) {                        // raised-sine head (acquire.c:243-244)
+            const float w = __ldg(&p.shape[tl]);
+            x = make_float2(x.x * w, x.y * w);
+        }
+        v[n1] = x;
+        ph = cmul(ph, step);
+    }
+    if (tl < NCP) {                                       // fold the windowed tail onto the head (acquire.c:247-248)
+        const int j = NFFT + tl;
+        const float w = __ldg(&p.shape[j]);
+        const float2 x = cmul(sample_at(sw, j), ph);      // ph is now exp(j*theta*(2048+tl))
+        v[0] = cadd(v[0], make_float2(x.x * w, x.y * w));
+    }
+    float2 out[2][8];
+    fft2048_block(v, out, buf, p.twid, tl, bar);
+
+    float2 *dst = p.bins + ((size_t)s * BLK + sym) * NBINS;
+    const float2 sp = sm.symphase[half];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) {
+            const int k = tl + 128 * h + 256 * k3;        // natural-order bin
+            const int b = (k + NFFT / 2) & (NFFT - 1);    // fftshift (defines.h:123-138)
+            const int ci = compact_of_bin(b);
+            if (ci >= 0) dst[ci] = cmul(out[h][k3], sp);
+        }
+}
+
+// ---------------------------------------------------------------------------
+// sync (reference src/sync.c)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ref_bin(int slot)                // slot < MAXREF: lower sideband, else upper
+{
+    return slot < MAXREF ? LB0 + PW * slot : UB1 - PW * (slot - MAXREF);
+}
+
+// adjust_ref (sync.c:90-130) on one row of 32 symbols
+__device__ void costas_row(float2 *z, float *phs, float &cfreq, float &cphase, int cfo, float alpha, float beta)
+{
+    const signed char pat[BLK] = { -1, 1, -1, -1, -1, 1, 1, 0, 1, -1, 0, 0, 0, -1, -1, 0,
+                                   0, 0, 0, 0, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1 };
+    const float cfo_freq = (float)(2 * M_PI * cfo * NCP / NFFT);
+    const float PI_F = 3.14159274101257324f;                  // smallest float above pi: (ph > M_PI) <=> (ph >= PI_F)
+    float f = cfreq, ph = cphase;
+    for (int n = 0; n < BLK; n++) {
+        const float2 v = z[n];
+        // u = v * exp(-j*ph); the loop error arg(v^2 * exp(-2j*ph)) / 2 equals arg(u^2) / 2
+        const float2 u = cmulf(v, cexp_j(-ph));
+        const float error = atan2f((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y) * 0.5f;
+        phs[n] = ph;
+        z[n] = u;
+        f += beta * error;
+        if (f > 0.5f) f = 0.5f;
+        if (f < -0.5f) f = -0.5f;
+        ph += (f + cfo_freq) + (alpha * error);
+        if (ph >= PI_F) ph = (float)((double)ph - 2 * M_PI);
+        if (ph <= -PI_F) ph = (float)((double)ph + 2 * M_PI);
+    }
+    float x = 0;
+    for (int n = 0; n < BLK; n++) x += z[n].x * (float)pat[n];
+    if (x < 0) {
+        for (int n = 0; n < BLK; n++) {
+            phs[n] = (float)((double)phs[n] + M_PI);
+            z[n] = make_float2(z[n].x * -1.0f, z[n].y * -1.0f);
+        }
+        ph = (float)((double)ph + M_PI);
+    }
+    cfreq = f;
+    cphase = ph;
+}
+
+__device__ __forceinline__ int needle_bit(int n, unsigned rsid)       // -1 = don't care (sync.c:171-174)
+{
+    const signed char base[BLK] = { 0, 1, 0, 0, 0, 1, 1, -1, 1, 0, 0, 0, -1, 0, 0, -1,
+                                    -1, -1, -1, -1, 0, 1, 0, -1, -1, -1, -1, -1, -1, -1, -1, 0 };
+    if (n == 10) return (int)(rsid >> 1);
+    if (n == 11) return (int)((rsid >> 1) ^ (rsid & 1));
+    return base[n];
+}
+
+// find_ref_fm (sync.c:188-207): cyclic offset of the sync pattern, also trying the inverted bits
+__device__ int ref_find(const float2 *z, unsigned rsid)
+{
+    unsigned raw = 0;
+    for (int n = 0; n < BLK; n++)
+        if (!(z[n].x <= 0)) raw |= 1u << n;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int n = 0; n < BLK; n++) {
+            int i;
+            for (i = 0; i < BLK; i++) {
+                const int nb_ = needle_bit(i, rsid);
+                if (nb_ < 0) continue;
+                if (nb_ != (int)((raw >> ((n + i) & 31)) & 1)) break;
+            }
+            if (i == BLK) return n;
+        }
+        raw = ~raw;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ float half_pi_wrap(float a, float b)        // sync.c:284-290
+{
+    float dd = a - b;
+    while ((double)dd > M_PI / 2) dd = (float)((double)dd - M_PI);
+    while ((double)dd < -M_PI / 2) dd = (float)((double)dd + M_PI);
+    return dd;
+}
+
+__device__ __forceinline__ int8_t soft_demap(float x, float mult)      // sync.c:69-73
+{
+    // lroundf semantics (round half away from zero) without the libm call: |v| <= 127 so v - trunc(v) is exact
+    const float v = fmaxf(fminf(x, 1.0f), -1.0f) * mult;
+    int r = __float2int_rz(v);
+    const float f = v - (float)r;
+    if (f >= 0.5f) r++;
+    else if (f <= -0.5f) r--;
+    return (int8_t)r;
+}
+
+__device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSmem &sm, int t)
+{
+    StreamState &st = p.st[s];
+    float *cfreq = p.cfreq + (size_t)s * NFFT;
+    float *cphase = p.cphase + (size_t)s * NFFT;
+    float2 *bins = p.bins + (size_t)s * BLK * NBINS;          // [symbol][534]
+    const float loop_bw = 0.05f, damping = 0.70710678f;
+    const float denom = 1 + (2 * damping * loop_bw) + (loop_bw * loop_bw);
+    const float alpha = (4 * damping * loop_bw) / denom, beta = (4 * loop_bw * loop_bw) / denom;
+
+    int ppb = partitions_per_band(st.psmi);
+    int nref = ppb + 1;
+    // reference carriers -> shared memory, then one Costas loop per carrier (sync.c:359-363)
+    for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
+        const int slot = i >> 5, n = i & 31;
+        const int ii = slot < MAXREF ? slot : slot - MAXREF;
+        if (ii < nref) sm.zref[slot][n] = bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))];
+    }
+    __syncthreads();
+    if (t < 2 * MAXREF) {
+        const int i = t < MAXREF ? t : t - MAXREF;
+        if (i < nref) {
+            const int b = ref_bin(t);
+            costas_row(sm.zref[t], sm.phs[t], cfreq[b], cphase[b], 0, alpha, beta);
+        }
+    }
+    __syncthreads();
+
+    if (st.state == ST_COARSE) {                 // sync.c:366-421
+        if (t < 2 * MAXREF) {
+            const int i = t < MAXREF ? t : t - MAXREF;
+            sm.ref_ok[t] = 0;
+            if (i < nref) {
+                const float2 *z = sm.zref[t];
+                const unsigned rsid = (unsigned)(30 - i) & 3;
+                bool ok = true;
+                unsigned raw = 0;
+                for (int n = 0; n < BLK; n++) {
+                    const int nbit = needle_bit(n, rsid);
+                    const int pos = z[n].x > 0 ? 1 : 0;
+                    if (nbit >= 0 && nbit != pos) ok = false;
+                    if (!(z[n].x <= 0)) raw |= 1u << n;
+                }
+                const unsigned dd = raw ^ (raw << 1);        // DBPSK decode, prev = 0 (sync.c:138-148)
+                auto bit = [&](int n) { return (dd >> n) & 1u; };
+                sm.ref_ok[t] = ok;
+                sm.ref_bc[t] = (int)(bit(16) << 3 | bit(17) << 2 | bit(18) << 1 | bit(19));
+                sm.ref_psmi[t] = (int)(bit(25) << 5 | bit(26) << 4 | bit(27) << 3 | bit(28) << 2 | bit(29) << 1 | bit(30));
+            }
+        }
+        __syncthreads();
+        if (t == 0) {
+            unsigned good = 0;
+            for (int r = 0; r < 2 * MAXREF; r++)
+                if (sm.ref_ok[r]) good++;
+            sm.do_search = 0;
+            if (good >= 4) {
+                // strict majorities; the PSMI majority is only looked for among 0..15 (sync.c:396)
+                int mbc = -1, mps = -1;
+                for (int v = 0; v < 16; v++) {
+                    unsigned nbc = 0, nps = 0;
+                    for (int r = 0; r < 2 * MAXREF; r++) {
+                        if (!sm.ref_ok[r]) continue;
+                        nbc += sm.ref_bc[r] == v;
+                        nps += sm.ref_psmi[r] == v;
+                    }
+                    if (nbc > good / 2) mbc = v;
+                    if (nps > good / 2) mps = v;
+                }
+                if (mbc >= 0 && mps >= 0) {
+                    st.bc = mbc;
+                    st.psmi = mps;
+                    set_state(p, d, s, ST_FINE);
+                    st.started_pm = 0;                   // decode_reset (decode.c:556-565)
+                }
+            } else if (st.cfo_wait == 0) {
+                sm.do_search = 1;
+            } else {
+                st.cfo_wait--;
+            }
+        }
+        __syncthreads();
+        if (sm.do_search) {                      // detect_cfo (sync.c:292-337)
+            // the rows the search works on live in global memory; first give it the Costas-rotated references
+            for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
+                const int slot = i >> 5, n = i & 31;
+                const int ii = slot < MAXREF ? slot : slot - MAXREF;
+                if (ii < nref) bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))] = sm.zref[slot][n];
+            }
+            __syncthreads();
+            if (t < 32) {
+                const int lane = t;
+                for (int cfo = -2 * PW; cfo < 2 * PW; cfo++) {
+                    int off = -1;
+                    if (lane < 22) {
+                        const int i = lane >> 1, upper = lane & 1;
+                        const int b = upper ? cfo + UB1 - i * PW : cfo + LB0 + i * PW;
+                        const int ci = compact_of_bin(b);
+                        float2 *row = sm.rows[lane];
+                        for (int n = 0; n < BLK; n++)
+                            row[n] = ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f);
+                        costas_row(row, sm.tmp_phs[lane], cfreq[b], cphase[b], cfo, alpha, beta);
+                        off = ref_find(row, (unsigned)(30 - i) & 3);
+                        if (ci >= 0)
+                            for (int n = 0; n < BLK; n++)    // reset_ref (sync.c:132-136)
+                                bins[(size_t)n * NBINS + ci] = cmulf(row[n], cexp_j(sm.tmp_phs[lane][n]));
+                    }
+                    sm.offs[lane] = off;
+                    __syncwarp();
+                    int found = 0;
+                    if (lane == 0) {
+                        int best = -1;
+                        unsigned bestn = 0;
+                        for (int k = 0; k < BLK; k++) {
+                            unsigned nv = 0;
+                            for (int r = 0; r < 22; r++) nv += sm.offs[r] == k;
+                            if (nv > bestn) { best = k; bestn = nv; }
+                        }
+                        if (best >= 0 && bestn >= 3) {
+                            st.keep_extra = ((BLK - best) % BLK) * NSYM;
+                            st.cfo += cfo;
+                            st.cfo_wait = 8;
+                            found = 1;
+                        }
+                    }
+                    found = __shfl_sync(0xffffffffu, found, 0);
+                    __syncwarp();
+                    if (found) break;
+                }
+            }
+        }
+        __syncthreads();
+        ppb = partitions_per_band(st.psmi);      // psmi may have changed with the FINE decision
+        nref = ppb + 1;
+    }
+
+    if (st.state == ST_FINE) {
+        // reference amplitude per subcarrier (calc_smag, sync.c:254-261)
+        if (t < 2 * MAXREF) {
+            const int i = t < MAXREF ? t : t - MAXREF;
+            if (i < nref) {
+                float sum = 0;
+                for (int n = 0; n < BLK; n++) sum += fabsf(sm.zref[t][n].x);
+                sm.smag[t] = sum / BLK;
+            }
+        }
+        __syncthreads();
+        // adjust_data (sync.c:263-282) + squared error to the nearest QPSK point (sync.c:465-488):
+        // one thread per (partition, symbol); the equalised carriers go back to `bins`
+        for (int item = t; item < 2 * ppb * BLK; item += FRONT_THREADS) {
+            const int n = item & (BLK - 1), pp = item >> 5;
+            const int upper = pp >= ppb, i = upper ? pp - ppb : pp;
+            int lo_bin, slot_lo, slot_hi;
+            if (!upper) { lo_bin = LB0 + PW * i; slot_lo = i; slot_hi = i + 1; }
+            else { lo_bin = UB1 - PW * i - PW; slot_lo = MAXREF + i + 1; slot_hi = MAXREF + i; }
+            const float m0 = sm.smag[slot_lo], m19 = sm.smag[slot_hi];
+            const float2 up = cexp_j(sm.phs[slot_hi][n]);
+            const float2 lp = cexp_j(sm.phs[slot_lo][n]);
+            float2 *zc = bins + (size_t)n * NBINS + compact_of_bin(lo_bin);
+            float e = 0;
+            for (int k = 1; k < PW; k++) {
+                const float fa = (float)k * m19, fb = (float)(PW - k) * m0;
+                const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
+                const float rden = 19.0f / (c * c + dd * dd);
+                // (19 + 19j) / (c + j dd)
+                const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
+                const float2 v = cmulf(zc[k], C);
+                zc[k] = v;
+                const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
+                e += dx * dx + dy * dy;
+            }
+            if (!upper) sm.err_lb[i][n] = e;
+            else sm.err_ub[i][n] = e;
+        }
+        // timing / phase feedback (sync.c:426-463)
+        if (t == 0) {
+            float samperr = 0, angle = 0, sum_xy = 0, sum_x2 = 0;
+            for (int i = 0; i < ppb; i++) {
+                samperr += half_pi_wrap(sm.phs[i][0], sm.phs[i + 1][0]);
+                samperr += half_pi_wrap(sm.phs[MAXREF + i + 1][0], sm.phs[MAXREF + i][0]);
+            }
+            samperr = (float)((double)(samperr / (float)(ppb * 2) * (float)NFFT / (float)PW) / (2 * M_PI));
+            for (int i = 0; i <= ppb; i++) {
+                float x, y;
+                x = (float)(LB0 + PW * i - NFFT / 2);
+                y = cfreq[LB0 + PW * i];
+                angle += y; sum_xy += x * y; sum_x2 += x * x;
+                x = (float)(UB1 - PW * i - NFFT / 2);
+                y = cfreq[UB1 - PW * i];
+                angle += y; sum_xy += x * y; sum_x2 += x * x;
+            }
+            samperr = (float)((double)samperr - (double)((sum_xy / sum_x2) * (float)NFFT) / (2 * M_PI) * BLK);
+            st.samperr = (int)roundf(samperr);
+            angle /= (float)((ppb + 1) * 2);
+            st.angle = angle;
+            for (int i = 0; i <= ppb; i++) {
+                cfreq[LB0 + PW * i] -= angle;
+                cfreq[UB1 - PW * i] -= angle;
+            }
+        }
+        __syncthreads();
+        // modulation error: combine per symbol (over partitions), then over symbols — a fixed order
+        if (t < BLK) {
+            float e_lb = 0, e_ub = 0;
+            for (int i = 0; i < ppb; i++) { e_lb += sm.err_lb[i][t]; e_ub += sm.err_ub[i][t]; }
+            sm.part_lb[t] = e_lb;
+            sm.part_ub[t] = e_ub;
+        }
+        __syncthreads();
+        if (t == 0) {
+            float e_lb = 0, e_ub = 0;
+            for (int n = 0; n < BLK; n++) { e_lb += sm.part_lb[n]; e_ub += sm.part_ub[n]; }
+            st.err_lb += e_lb;
+            st.err_ub += e_ub;
+            if (++st.mer_cnt == 16) {
+                const float signal = (float)(2 * BLK * (ppb * 18) * st.mer_cnt);
+                uint8_t *w = log_reserve(p, d, s, REC_MER, 8);
+                if (w) {
+                    reinterpret_cast<float *>(w)[0] = 10 * log10f(signal / st.err_lb);
+                    reinterpret_cast<float *>(w)[1] = 10 * log10f(signal / st.err_ub);
+                }
+                st.mer_cnt = 0;
+                st.err_lb = 0;
+                st.err_ub = 0;
+            }
+            const float mer_lb = 2.0f * BLK * (float)(ppb * 18) / e_lb;
+            const float mer_ub = 2.0f * BLK * (float)(ppb * 18) / e_ub;
+            sm.mult_lb = fmaxf(fminf(mer_lb * 10, 127.0f), 1.0f);
+            sm.mult_ub = fmaxf(fminf(mer_ub * 10, 127.0f), 1.0f);
+        }
+        __syncthreads();
+        // soft demap of the primary-main partitions (sync.c:509-536) into the interleaver matrix
+        const int bc = st.bc;
+        int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
+        {
+            const float mlb = sm.mult_lb, mub = sm.mult_ub;
+            for (int o = t; o < PM_BLOCK; o += FRONT_THREADS) {
+                const int n = o / 720, col = o - n * 720;
+                const int part = col / 36, c = col - part * 36;
+                const int j = 1 + (c >> 1);
+                const int b = part < 10 ? LB0 + PW * part + j : (UB1 - 10 * PW) + PW * (part - 10) + j;
+                const float2 v = bins[(size_t)n * NBINS + compact_of_bin(b)];
+                pm[o] = soft_demap((c & 1) ? v.y : v.x, part < 10 ? mlb : mub);
+            }
+        }
+        __syncthreads();
+        if (d.emit_soft) {
+            __shared__ uint8_t *sh_w;
+            if (t == 0) {
+                sh_w = log_reserve(p, d, s, REC_SOFT_PM, 4 + PM_BLOCK);
+                if (sh_w) *reinterpret_cast<uint32_t *>(sh_w) = (uint32_t)bc;
+            }
+            __syncthreads();
+            if (sh_w)
+                for (int o = t; o < PM_BLOCK; o += FRONT_THREADS) sh_w[4 + o] = (uint8_t)pm[o];
+            __syncthreads();
+        }
+        // PIDS (decode.c:463-471): decoded by the stream's first task of the next round; the record slot is
+        // reserved here to keep the stream's record order
+        if (t == 0) {
+            uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
+            st.pids_rec = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+            st.pids_bc = bc;
+            st.pids_pending = 1;
+            // P1 bookkeeping (decode.c:383-390)
+            if (bc == 0) st.started_pm = 1;
+            if (st.started_pm && bc == 15) st.p1_ready = 1;
+            st.bc = (bc + 1) % 16;
+        }
+    }
+    __syncthreads();
+    if (t == 0) {                                // window overlap carry (acquire.c:259-262)
+        const int keep = NSYM + (NSYM / 2 - st.blk_samperr) + st.keep_extra;
+        st.keep_extra = 0;
+        st.start += NACQ - keep;
+        st.blocks_done++;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the persistent kernel
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *a)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(a);
+}
+
+// wait until *flag >= target; gives up (and flags an error) instead of hanging the GPU
+__device__ bool wait_flag(const unsigned long long *flag, unsigned long long target)
+{
+    unsigned spins = 0;
+    while (ld_volatile(flag) < target) {
+        __nanosleep(spins < 64 ? 32 : 256);
+        if (++spins > (1u << 24)) {              // several seconds
+            atomicExch(&g_error, 1);
+            return false;
+        }
+        if (*reinterpret_cast<volatile int *>(&g_error)) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(FRONT_THREADS) k_front(DevPtrs p, EngineDims d, unsigned long long round0, int nrounds)
+{
+    extern __shared__ __align__(16) unsigned char front_smem_raw[];
+    FrontSmem &sm = *reinterpret_cast<FrontSmem *>(front_smem_raw);
+    __shared__ unsigned sh_ticket;
+    __shared__ int sh_ok, sh_last;
+    const int t = threadIdx.x, half = t >> 7, tl = t & 127;
+    const int S = d.nstreams;
+    const unsigned total = (unsigned)nrounds * (unsigned)S * TASKS_PER_BLOCK;
+
+    for (;;) {
+        if (t == 0) sh_ticket = atomicAdd(&g_ticket, 1u);
+        __syncthreads();
+        const unsigned ticket = sh_ticket;
+        if (ticket >= total) break;
+        const int r = (int)(ticket / ((unsigned)S * TASKS_PER_BLOCK));
+        const unsigned rem = ticket - (unsigned)r * S * TASKS_PER_BLOCK;
+        const int s = (int)(rem / TASKS_PER_BLOCK), k = (int)(rem % TASKS_PER_BLOCK);
+        const unsigned long long round = round0 + (unsigned long long)r;
+        StreamState &st = p.st[s];
+
+        if (k == 0) {
+            if (t == 0) sh_ok = wait_flag(&st.q_synced, round);       // the previous block of this stream is done
+            __syncthreads();
+            if (!sh_ok) break;
+            __threadfence();
+            if (st.pids_pending) front_pids(p, d, s, sm.pids, t);
+            front_prep(p, d, s, sm.prep, t);
+            __threadfence();                                           // every thread publishes its writes ...
+            __syncthreads();
+            if (t == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long *>(&st.q_prepped) = round + 1;   // ... before the flag
+            }
+        } else {
+            if (t == 0) sh_ok = wait_flag(&st.q_prepped, round + 1);
+            __syncthreads();
+            if (!sh_ok) break;
+            __threadfence();
+        }
+        if (st.active)
+            front_demod(p, d, s, 2 * k + half, sm.demod, half, tl, st.start, st.blk_samperr, st.theta, st.phase0);
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            const int old = atomicAdd(&st.q_cnt, 1);
+            sh_last = old == TASKS_PER_BLOCK - 1;
+            if (sh_last) st.q_cnt = 0;
+        }
+        __syncthreads();
+        if (sh_last) {
+            __threadfence();
+            if (st.active) front_sync(p, d, s, sm.sync, t);
+            __threadfence();
+            __syncthreads();
+            if (t == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long *>(&st.q_synced) = round + 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace nb

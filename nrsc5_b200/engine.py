@@ -173,8 +173,8 @@ class Engine:
         ms = (ctypes.c_double * 4)()
         n = (ctypes.c_ulonglong * 4)()
         _check(self._L.nrsc5b_get_kernel_times(self._h, ms, n), "nrsc5b_get_kernel_times")
-        names = ("prep", "demod", "sync", "p1")
-        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
+        # slot 1 = the fused persistent front-end kernel (k_front), slot 3 = the P1 decode kernel group
+        return {"front": {"ms": ms[1], "launches": int(n[1])}, "p1": {"ms": ms[3], "launches": int(n[3])}}
 
     def push_cu8(self, stream: int, samples):
         """samples: uint8 numpy array / bytes (host) — length counts uint8 values, multiple of 4."""
