@@ -78,10 +78,6 @@ struct StreamState {
     // output log cursor
     unsigned log_len;
     unsigned log_overflow;
-    // task-queue flags of the persistent front-end kernel (front.cuh)
-    unsigned long long q_prepped;   // rounds whose prep is published
-    unsigned long long q_synced;    // rounds completely processed
-    int q_cnt;                      // demod tasks of the current round that have finished
     unsigned long long blocks_done;
     unsigned long long frames_done;
     // history of the coarse band-pass FIR: the last 31 samples it was fed
@@ -113,7 +109,7 @@ struct DevPtrs {
     int *hstate, *tbend;       // [S][143]
     uint8_t *log;              // [S][log_cap]
     const float *shape;        // [2160]
-    const float2 *twid;        // [2048]  exp(-2*pi*i*k/2048)
+    const float2 *twid;        // [FFT_TW] twiddle tables of fft2048_block (fft.cuh)
     const uint32_t *p1_lut;    // [365440] interleaver I gather index
     const uint8_t *pn;         // [146176] descrambler sequence
 };
@@ -147,18 +143,20 @@ __device__ __forceinline__ short2 halfband_at(const uint8_t *iq, long long d)
     long long n0 = 2 * d - 14;
     int accr = 0, acci = 0;
     if (n0 >= 0) {
+        // input samples may land (asynchronous copies) while a kernel runs: read them through L2 only
         const uint8_t *b = iq + 2 * n0;
+        auto ld = [&](int i) -> int { return q15_of_u8(__ldcg(b + i)); };
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int ar = q15_of_u8(b[4 * k]) + q15_of_u8(b[2 * (14 - 2 * k)]);
-            int ai = q15_of_u8(b[4 * k + 1]) + q15_of_u8(b[2 * (14 - 2 * k) + 1]);
+            int ar = ld(4 * k) + ld(2 * (14 - 2 * k));
+            int ai = ld(4 * k + 1) + ld(2 * (14 - 2 * k) + 1);
             accr = (short)(accr + ((ar * tap[k]) >> 15));
             acci = (short)(acci + ((ai * tap[k]) >> 15));
         }
-        accr = (short)(accr + q15_of_u8(b[14]));
-        acci = (short)(acci + q15_of_u8(b[15]));
+        accr = (short)(accr + ld(14));
+        acci = (short)(acci + ld(15));
     } else {
-        auto rd = [&](long long n, int c) -> int { return n < 0 ? 0 : q15_of_u8(iq[2 * n + c]); };
+        auto rd = [&](long long n, int c) -> int { return n < 0 ? 0 : q15_of_u8(__ldcg(iq + 2 * n + c)); };
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             int ar = rd(n0 + 2 * k, 0) + rd(n0 + 14 - 2 * k, 0);

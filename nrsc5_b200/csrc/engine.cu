@@ -168,7 +168,7 @@ __host__ __device__ inline VitcArgs p1_vitc_args(const DevPtrs &dp)
 constexpr size_t VITC_EMIT_SMEM = (size_t)VITC_EMIT_WARPS * VITC_EMIT_STEPS * sizeof(uint2);
 
 // input_reset for a range of streams (reference src/input.c:126-138)
-__global__ void k_reset(DevPtrs p, EngineDims d, int only, unsigned long long round0)
+__global__ void k_reset(DevPtrs p, EngineDims d, int only)
 {
     const int s = blockIdx.x, t = threadIdx.x;
     if (only >= 0 && s != only) return;
@@ -186,8 +186,6 @@ __global__ void k_reset(DevPtrs p, EngineDims d, int only, unsigned long long ro
         z.state = ST_NONE;
         z.force_state = -1;
         z.in_avail = only == -2 ? avail : 0;     // -2: keep the attached input (rewind)
-        z.q_prepped = round0;
-        z.q_synced = round0;
         st = z;
     }
 }
@@ -253,10 +251,6 @@ struct nrsc5b_engine {
     StreamState *h_state;              // pinned mirror for read-back
     nrsc5b_stats_t stats;
     unsigned long long last_progress;
-    unsigned long long round0;         // rounds launched so far (task-queue epoch)
-    int front_grid;                    // resident CTAs of k_front
-    unsigned *d_ticket;
-    int *d_error;
     std::vector<void *> allocs;
     int profiling;
     cudaEvent_t pev[5];
@@ -316,11 +310,16 @@ static int dev_alloc(nrsc5b_engine *e, T **ptr, size_t count, bool zero = true)
 
 static std::vector<float2> make_twiddles()
 {
-    std::vector<float2> tw(NFFT);
-    for (int k = 0; k < NFFT; k++) {
-        double a = -2.0 * M_PI * (double)k / (double)NFFT;
-        tw[k] = make_float2((float)cos(a), (float)sin(a));
-    }
+    // fft.cuh layout: tw1[k1*128 + t] = W^(t*k1), then tw2[k2*8 + n3] = W^(16*n3*k2)
+    std::vector<float2> tw(FFT_TW);
+    auto w = [](int m) {
+        double a = -2.0 * M_PI * (double)(m % NFFT) / (double)NFFT;
+        return make_float2((float)cos(a), (float)sin(a));
+    };
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int t = 0; t < 128; t++) tw[k1 * 128 + t] = w(t * k1);
+    for (int k2 = 0; k2 < 16; k2++)
+        for (int n3 = 0; n3 < 8; n3++) tw[FFT_TW1 + k2 * 8 + n3] = w(16 * n3 * k2);
     return tw;
 }
 
@@ -352,7 +351,6 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->iq_owned = nullptr;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
-    e->round0 = 0;
     e->profiling = 0;
     for (int i = 0; i < 5; i++) e->pev[i] = nullptr;
     for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
@@ -415,9 +413,9 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         dp.shape = dshape;
         std::vector<float2> tw = make_twiddles();
         float2 *dtw = nullptr;
-        rc = dev_alloc(e, &dtw, NFFT);
+        rc = dev_alloc(e, &dtw, FFT_TW);
         if (rc) { nrsc5b_destroy(e); return rc; }
-        cudaMemcpy(dtw, tw.data(), NFFT * sizeof(float2), cudaMemcpyHostToDevice);
+        cudaMemcpy(dtw, tw.data(), FFT_TW * sizeof(float2), cudaMemcpyHostToDevice);
         dp.twid = dtw;
         static const int PMV[20] = { 10, 2, 18, 6, 14, 8, 16, 0, 12, 4, 11, 3, 19, 7, 15, 9, 17, 1, 13, 5 };
         std::vector<uint32_t> lut(P1_ENC);
@@ -458,20 +456,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         nrsc5b_destroy(e);
         return NRSC5B_ENOMEM;
     }
-    {
-        const int smem = (int)sizeof(FrontSmem);
-        int per_sm = 0, dev = cfg->device, sms = 0;
-        if (cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, smem) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm < 1 ||
-            cudaGetSymbolAddress((void **)&e->d_ticket, g_ticket) != cudaSuccess ||
-            cudaGetSymbolAddress((void **)&e->d_error, g_error) != cudaSuccess) {
-            nrsc5b_destroy(e);
-            return NRSC5B_ECUDA;
-        }
-        // every CTA must be resident at once: the task queue lets CTAs wait for work held by other CTAs
-        e->front_grid = per_sm * sms;
+    if (cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess) {
+        nrsc5b_destroy(e);
+        return NRSC5B_ECUDA;
     }
     *out = e;
     rc = nrsc5b_reset(e, -1);
@@ -507,7 +495,7 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
     if (!e || stream >= e->dims.nstreams) return NRSC5B_EINVAL;
     const int S = e->dims.nstreams;
     CK(cudaStreamSynchronize(e->copy_stream));       // no input copy of the old contents may still be in flight
-    k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream, e->round0);
+    k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream);
     CK(cudaEventRecord(e->reset_done, e->stream));
     CK(cudaStreamWaitEvent(e->copy_stream, e->reset_done, 0));
     e->stats.kernel_launches += 1;
@@ -524,7 +512,7 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
 extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
 {
     if (!e) return NRSC5B_EINVAL;
-    k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2, e->round0);
+    k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2);
     e->stats.kernel_launches += 1;
     for (int s = 0; s < e->dims.nstreams; s++) e->drained[s] = 0;
     CK(cudaGetLastError());
@@ -621,17 +609,18 @@ static void launch_p1(nrsc5b_engine *e)
     e->stats.kernel_launches += 5;
 }
 
-// nrounds rounds of the front end for every stream (one persistent launch), then — if asked — the P1 decode
-static int launch_rounds(nrsc5b_engine *e, int nrounds, bool with_p1)
+// One pass: every stream runs its front end up to its next frame boundary (at most BLOCKS_PER_PASS blocks,
+// one persistent CTA per stream), then the P1 decode of the streams that completed an interleaver matrix.
+constexpr int BLOCKS_PER_PASS = 16;
+
+static int launch_pass(nrsc5b_engine *e)
 {
     const bool prof = e->profiling != 0;
-    CK(cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned), e->stream));
     if (prof) cudaEventRecord(e->pev[0], e->stream);
-    k_front<<<e->front_grid, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, e->round0, nrounds);
-    e->round0 += (unsigned long long)nrounds;
+    k_stream<<<e->dims.nstreams, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS);
     e->stats.kernel_launches += 1;
     if (prof) cudaEventRecord(e->pev[1], e->stream);
-    if (with_p1) launch_p1(e);
+    launch_p1(e);
     if (prof) {
         cudaEventRecord(e->pev[2], e->stream);
         cudaEventSynchronize(e->pev[2]);
@@ -639,13 +628,13 @@ static int launch_rounds(nrsc5b_engine *e, int nrounds, bool with_p1)
         cudaEventElapsedTime(&ms, e->pev[0], e->pev[1]);
         e->kernel_ms[1] += ms; e->kernel_n[1] += 1;
         cudaEventElapsedTime(&ms, e->pev[1], e->pev[2]);
-        e->kernel_ms[3] += ms; e->kernel_n[3] += with_p1 ? 1 : 0;
+        e->kernel_ms[3] += ms; e->kernel_n[3] += 1;
     }
     return 0;
 }
 
 /* Per-kernel device time (CUDA events around every launch; slows the run down, use a separate pass).
- * Slots: [1] = the fused front-end kernel k_front, [3] = the P1 decode group; [0],[2] unused. */
+ * Slots: [1] = the stream-resident front-end kernel k_stream, [3] = the P1 decode group; [0],[2] unused. */
 extern "C" int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on)
 {
     if (!e) return NRSC5B_EINVAL;
@@ -666,57 +655,32 @@ extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned
 static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
 {
     if (!e) return NRSC5B_EINVAL;
-    // Each block advances a stream's window by 69120 +- a few decimated samples, so the number of
-    // blocks a stream can still take follows from its buffered samples and its window start.  Launch
-    // that many steps, look at the device-side progress counter, and stop after a batch (always at
-    // least one trailing step, which also flushes the deferred PIDS decode) made no progress.
+    // Each block advances a stream's window by 69120 +- a few decimated samples, and a pass takes a stream
+    // through at most one frame boundary, so the number of passes the buffered samples can need follows
+    // from the host-side sample counts.  Enqueue that many, look at the device-side progress counter, and
+    // stop after a batch (always ending with a pass that also flushes the deferred PIDS decode) made no
+    // progress.  Surplus passes find nothing to do and cost a few microseconds.
     const int S = e->dims.nstreams;
+    bool first = true;
     for (;;) {
-        CK(cudaMemcpyAsync(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        long long most = 0;
-        for (int s = 0; s < S; s++) {
-            const long long avail_dec = e->pushed[s] / 2, start = e->h_state[s].start;
-            if (avail_dec >= start + NACQ) {
-                long long n = (avail_dec - start - NACQ) / (NSYM * BLK + 80) + 1;
+        int passes = 1;
+        if (first) {
+            long long most = 0;
+            for (int s = 0; s < S; s++) {
+                const long long n = e->pushed[s] / 2 / (NSYM * BLK - 80) + 1;
                 if (n > most) most = n;
             }
+            passes = (int)(most / BLOCKS_PER_PASS) + 2;
+            first = false;
         }
-        // The P1 decode kernels are only launched in the steps where a stream can complete its 16-block
-        // interleaver matrix.  With the states just read back this is predictable for up to 15 steps: a
-        // stream in FINE sync reaches block count 15 at a known step (a superset if it runs out of
-        // samples or loses sync first), and a stream that is not in FINE sync now cannot finish a frame
-        // in fewer than 16 blocks.  The last step of every batch launches them unconditionally, which
-        // also covers streams that stalled with a frame pending.
-        const int batch = (int)(most < 1 ? 1 : (most > 15 ? 15 : most));
-        unsigned p1_steps = 0;
-        for (int s = 0; s < S; s++) {
-            const StreamState &hs = e->h_state[s];
-            if (hs.p1_ready) p1_steps |= 1u;
-            if (hs.state != ST_FINE) continue;
-            for (int i = 0; i < batch; i++) {
-                const int bc = (hs.bc + i) & 15;
-                if (bc == 15 && (hs.started_pm || i >= ((16 - hs.bc) & 15))) p1_steps |= 1u << i;
-            }
-        }
-        p1_steps |= 1u << (batch - 1);
-        for (int i0 = 0; i0 < batch; ) {                      // one persistent launch up to each P1 step
-            int i1 = i0;
-            while (!((p1_steps >> i1) & 1u)) i1++;
-            int rc = launch_rounds(e, i1 - i0 + 1, true);
+        for (int i = 0; i < passes; i++) {
+            int rc = launch_pass(e);
             if (rc) return rc;
-            i0 = i1 + 1;
         }
         unsigned long long prog = 0;
-        int err = 0;
         CK(cudaMemcpyFromSymbolAsync(&prog, g_progress, sizeof(prog), 0, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaMemcpyAsync(&err, e->d_error, sizeof(err), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
-        if (err) {
-            fprintf(stderr, "nrsc5_b200: front-end task queue timed out\n");
-            return NRSC5B_ECUDA;
-        }
         const unsigned long long delta = prog - e->last_progress;
         e->last_progress = prog;
         if (delta == 0) {
@@ -896,9 +860,9 @@ extern "C" int nrsc5b_fft2048(int device, const float *in, float *out, int nffts
     size_t n = (size_t)nffts * NFFT;
     CK(cudaMalloc(&di, n * sizeof(float2)));
     CK(cudaMalloc(&dout, n * sizeof(float2)));
-    CK(cudaMalloc(&dtw, NFFT * sizeof(float2)));
+    CK(cudaMalloc(&dtw, FFT_TW * sizeof(float2)));
     std::vector<float2> tw = make_twiddles();
-    CK(cudaMemcpy(dtw, tw.data(), NFFT * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtw, tw.data(), FFT_TW * sizeof(float2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(di, in, n * sizeof(float2), cudaMemcpyHostToDevice));
     launch_fft_test(di, dout, dtw, nffts, 0);
     CK(cudaMemcpy(out, dout, n * sizeof(float2), cudaMemcpyDeviceToHost));

@@ -72,19 +72,25 @@ constexpr int FFT_THREADS = 128;
 constexpr int FFT_LD = 129;                        // padded leading dimension of the pass-1 layout
 constexpr int FFT_SMEM_ELEMS = 16 * FFT_LD;        // 2064 float2
 
+// twiddle tables of fft2048_block: tw1[k1*128 + t] = W^(t*k1) (16 x 128), tw2[k2*8 + n3] = W^(16*n3*k2)
+// (16 x 8), W = exp(-2*pi*i/2048): laid out so that a warp's loads are consecutive (tw1) or a two-address
+// broadcast (tw2), from shared or global memory alike
+constexpr int FFT_TW1 = 16 * 128, FFT_TW2 = 16 * 8, FFT_TW = FFT_TW1 + FFT_TW2;
+
 // 2048-point FFT by 128 threads.  On entry thread r holds x[n1*128 + r] in
 // v[n1], n1 = 0..15.  On exit thread t holds X[q + 256*k3] in out[h][k3] for
 // q = t + 128*h, h = 0..1, k3 = 0..7.  `buf` is FFT_SMEM_ELEMS float2 of
-// shared memory; `twid[m] = exp(-2*pi*i*m/2048)`.
+// shared memory; `tw` = the FFT_TW-entry twiddle table above.
 __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float2 *buf,
-                                              const float2 *__restrict__ twid, int t, int bar = 0)
+                                              const float2 *__restrict__ tw, int t, int bar = 0)
 {
+    const float2 *tw2 = tw + FFT_TW1;
     // pass 1: DFT-16 over n1, twiddle W^(r*k1), store A[k1][r]
     fft16(v);
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) {
         float2 x = v[k1];
-        if (k1) x = cmul(x, __ldg(&twid[t * k1]));
+        if (k1) x = cmul(x, tw[k1 * 128 + t]);
         buf[k1 * FFT_LD + t] = x;
     }
     bar_sync(bar);
@@ -99,7 +105,7 @@ __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             float2 x = u[k2];
-            if (k2) x = cmul(x, __ldg(&twid[16 * n3 * k2]));
+            if (k2) x = cmul(x, tw2[k2 * 8 + n3]);
             buf[n3 * 256 + k2 * 16 + k1] = x;
         }
     }

@@ -1,24 +1,19 @@
-// The fused, persistent front-end kernel: for every stream and every 32-symbol
-// block it runs
+// The stream-resident front end: ONE persistent CTA per stream (k_stream) runs, block after block,
 //
+//   pids   the previous block's PIDS frame                                            (decode.c:463-471)
 //   prep   window check, coarse acquisition when not in FINE sync, feedback, NCO      (acquire.c:98-168)
 //   demod  cu8 -> halfband -> NCO/window/fold -> 2048-pt FFT -> 534 bins, 32 symbols  (input.c:52-94,
 //                                                   firdecim_q15.c:137-165, acquire.c:237-257, sync.c:779-790)
 //   sync   Costas, COARSE->FINE vote / CFO search, equalise, feedback, MER, soft demap (sync.c:90-610)
-//   pids   the previous block's PIDS frame                                            (decode.c:463-471)
 //
-// as *tasks* taken from one ticket counter.  A task is (round r, stream s, k), k = 0..15, and covers
-// OFDM symbols 2k and 2k+1 of the stream's block in that round (two 128-thread halves of the CTA, one
-// symbol each).  Task k = 0 first waits for the stream's previous round to be synced, decodes the
-// pending PIDS frame and runs `prep`; tasks k > 0 wait for that prep.  The CTA that finishes the
-// stream's 16th task runs `sync` for the block.  Tickets are handed out in (r, s, k) order and every
-// CTA of the (fully resident) grid only ever waits for work with a smaller ticket, so the scheme cannot
-// deadlock; other streams' tasks fill the SMs while one stream's 32-step Costas recurrences run.
+// until the stream runs out of buffered samples, completes an L1 frame (the P1 decode kernels must run
+// before the next block: their RS header check feeds back into the sync state, frame.c:538) or has done
+// `max_blocks` blocks.  The block-to-block feedback (timing error, phase) never leaves the SM; streams
+// share nothing, so there are no inter-CTA flags, fences or queues.  The 1024 threads form 8 teams of
+// 128; a team demodulates one OFDM symbol at a time (4 passes per 32-symbol block).
 //
-// This translation unit is compiled with -fmad=false and -dlcm=cg: float expressions keep the
-// reference's evaluation order wherever a discrete decision depends on them, and plain global loads
-// bypass the (non-coherent) L1 so that data produced by another CTA in an earlier task is never read
-// stale.  Read-only tables and the input samples use __ldg.
+// This translation unit is compiled with -fmad=false: float expressions keep the reference's
+// evaluation order wherever a discrete decision depends on them.
 #pragma once
 #include "common.cuh"
 #include "fft.cuh"
@@ -26,15 +21,13 @@
 
 namespace nb {
 
-constexpr int FRONT_THREADS = 256;
-constexpr int TASKS_PER_BLOCK = BLK / 2;           // 16 tasks of two symbols
+constexpr int FRONT_THREADS = 1024;
+constexpr int TEAMS = FRONT_THREADS / 128;         // symbol teams of 128 threads
 constexpr int MAXREF = 15;                         // reference subcarriers per sideband (14 partitions + 1)
 constexpr int IN_BYTES = 4 * NSYM + 28 + 16 + 16;  // staged cu8 bytes per symbol (+ alignment slack) = 8700
 constexpr int IN_STRIDE = 8704;
 
 __device__ unsigned long long g_progress;          // bumped by every stream that processed a block
-__device__ unsigned g_ticket;                      // task queue head (reset by the host before each launch)
-__device__ int g_error;                            // set if a wait timed out (never expected)
 
 __constant__ int c_compat_mode[64];
 __constant__ short c_bp_tap[32];                   // coarse band-pass taps, tap[i] pairs w[i] and w[32-i]
@@ -82,10 +75,11 @@ __device__ void set_state(const DevPtrs &p, const EngineDims &d, int s, int ns)
 // shared memory: one buffer, reinterpreted per task phase
 // ---------------------------------------------------------------------------
 struct DemodSmem {
-    uint8_t in[2][IN_STRIDE];                      // staged cu8 of the two symbols
-    float2 buf[2][FFT_SMEM_ELEMS];                 // FFT exchange buffers
-    float2 symphase[2];
+    // per team: the FFT exchange buffer; the symbol's staged cu8 (IN_STRIDE bytes) aliases its start
+    float2 buf[TEAMS][FFT_SMEM_ELEMS];
+    float2 symphase[TEAMS];
 };
+static_assert(IN_STRIDE <= FFT_SMEM_ELEMS * sizeof(float2), "staged input must fit in the FFT buffer");
 struct PrepSmem {
     float2 sums[NSYM];
     float red_mag[FRONT_THREADS];
@@ -109,11 +103,15 @@ struct PidsSmem {
     int8_t vit[PIDS_LEN * 3];
     uint2 dec[PIDS_LEN + 64];
 };
-union FrontSmem {
-    DemodSmem demod;
-    PrepSmem prep;
-    SyncSmem sync;
-    PidsSmem pids;
+struct FrontSmem {
+    float2 tw[FFT_TW];                             // FFT twiddle tables (fft.cuh)
+    float2 nco[NSYM];                              // window[j] * exp(j*theta*j) of the current block
+    union {
+        DemodSmem demod;
+        PrepSmem prep;
+        SyncSmem sync;
+        PidsSmem pids;
+    } u;
 };
 
 // ---------------------------------------------------------------------------
@@ -183,23 +181,26 @@ __device__ void front_pids(const DevPtrs &p, const EngineDims &d, int s, PidsSme
 // ---------------------------------------------------------------------------
 // prep (reference src/acquire.c:98-168, src/sync.c:769-777, src/firdecim_q15.c:95-109,154-158)
 // ---------------------------------------------------------------------------
-__device__ void front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, int t)
+// Returns false (uniformly) when the stream has no complete 33-symbol window buffered.
+__device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, float2 *nco, int t)
 {
     StreamState &st = p.st[s];
     __shared__ int sh_active, sh_samperr;
-    __shared__ float sh_angle;
+    __shared__ float sh_angle, sh_theta;
     if (t == 0) {
         if (st.force_state >= 0) {
             set_state(p, d, s, st.force_state);
             st.force_state = -1;
         }
-        const int act = st.in_avail >= 2 * (st.start + NACQ);
+        // in_avail is advanced by asynchronous copies while this kernel runs
+        const long long avail = *reinterpret_cast<volatile long long *>(&st.in_avail);
+        const int act = avail >= 2 * (st.start + NACQ);
         st.active = act;
         sh_active = act;
         if (act) atomicAdd(&g_progress, 1ull);
     }
     __syncthreads();
-    if (!sh_active) return;
+    if (!sh_active) return false;
 
     const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
     const int state_in = st.state;
@@ -312,6 +313,7 @@ __device__ void front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
         const float theta = angle / (float)NFFT;
         st.phase0 = ph;
         st.theta = theta;
+        sh_theta = theta;
         st.blk_samperr = samperr;
         st.blk_state_in = state_in;
         // NCO phase after the 32 symbols of this block (acquire.c:250-252, closed form)
@@ -330,6 +332,21 @@ __device__ void front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
         }
     }
     __syncthreads();
+    // NCO of this block in closed form, with the pulse shape folded in (acquire.c:243-252):
+    // nco[j] = shape[j] * exp(j*theta*j); the per-symbol phase is applied to the kept bins
+    {
+        const float theta = sh_theta;
+        for (int j = t; j < NSYM; j += FRONT_THREADS) {
+            float2 e = cexp_j(theta * (float)j);
+            if (j < NCP || j >= NFFT) {
+                const float w = __ldg(&p.shape[j]);
+                e = make_float2(e.x * w, e.y * w);
+            }
+            nco[j] = e;
+        }
+    }
+    __syncthreads();
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -359,23 +376,25 @@ __device__ __forceinline__ float2 sample_at(const uint32_t *sw, int j)
     return make_float2((float)ar * sc, (float)ai * -sc);      // conj(x)/32767, acquire.c:160-161
 }
 
-__device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sym, DemodSmem &sm, int half, int tl,
-                            long long start, int samperr, float theta, float2 phase0)
+__device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sym, DemodSmem &sm, const float2 *nco,
+                            const float2 *tw, int half, int tl, long long start, int samperr, float theta, float2 phase0)
 {
-    uint8_t *in = sm.in[half];
     float2 *buf = sm.buf[half];
-    const int bar = 1 + half;                            // named barrier of this 128-thread half
+    uint8_t *in = reinterpret_cast<uint8_t *>(buf);
+    const int bar = 1 + half;                            // named barrier of this 128-thread team
     const long long base = start + samperr + (long long)NSYM * sym;
     const long long b0 = 4 * base - 28;                  // first needed cu8 byte (may be < 0 at stream start)
     const long long b0a = b0 & ~15LL;
     const int off = (int)(b0 - b0a);
     const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
+    bar_sync(bar);                                       // the team has read the previous symbol's FFT buffer
     {
         const int nvec = (off + 4 * NSYM + 28 + 15) / 16;
         uint4 *dst = reinterpret_cast<uint4 *>(in);
         for (int v = tl; v < nvec; v += 128) {
             const long long a = b0a + 16LL * v;
-            dst[v] = a >= 0 ? __ldg(reinterpret_cast<const uint4 *>(iq + a))
+            // through L2 only: samples may have landed after an earlier (partial) read of the same line
+            dst[v] = a >= 0 ? __ldcg(reinterpret_cast<const uint4 *>(iq + a))
                             : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
         }
     }
@@ -385,34 +404,25 @@ __device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sy
         sm.symphase[half] = cmul(phase0, make_float2((float)cs, (float)sn));
     }
     bar_sync(bar);
+    const float2 sp = sm.symphase[half];
 
-    // NCO in closed form: exp(j*theta*j), j = n1*128 + tl, advanced by exp(j*theta*128) per n1
+    // rotate by the block's NCO table (window folded in); j = n1*128 + tl
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(in + off);
-    float2 ph = cexp_j(theta * (float)tl);
-    const float2 step = cexp_j(theta * 128.0f);
     float2 v[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
         const int j = n1 * 128 + tl;
-        float2 x = cmul(sample_at(sw, j), ph);
-        if (n1 == 0 && tl < NCP) {                        // raised-sine head (acquire.c:243-244)
-            const float w = __ldg(&p.shape[tl]);
-            x = make_float2(x.x * w, x.y * w);
-        }
-        v[n1] = x;
-        ph = cmul(ph, step);
+        v[n1] = cmul(sample_at(sw, j), nco[j]);
     }
     if (tl < NCP) {                                       // fold the windowed tail onto the head (acquire.c:247-248)
         const int j = NFFT + tl;
-        const float w = __ldg(&p.shape[j]);
-        const float2 x = cmul(sample_at(sw, j), ph);      // ph is now exp(j*theta*(2048+tl))
-        v[0] = cadd(v[0], make_float2(x.x * w, x.y * w));
+        v[0] = cadd(v[0], cmul(sample_at(sw, j), nco[j]));
     }
+    bar_sync(bar);                                        // every thread is done with the staged input
     float2 out[2][8];
-    fft2048_block(v, out, buf, p.twid, tl, bar);
+    fft2048_block(v, out, buf, tw, tl, bar);
 
     float2 *dst = p.bins + ((size_t)s * BLK + sym) * NBINS;
-    const float2 sp = sm.symphase[half];
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
@@ -796,89 +806,32 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
 }
 
 // ---------------------------------------------------------------------------
-// the persistent kernel
+// the stream-resident kernel: grid = streams, one CTA each
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *a)
-{
-    return *reinterpret_cast<const volatile unsigned long long *>(a);
-}
-
-// wait until *flag >= target; gives up (and flags an error) instead of hanging the GPU
-__device__ bool wait_flag(const unsigned long long *flag, unsigned long long target)
-{
-    unsigned spins = 0;
-    while (ld_volatile(flag) < target) {
-        __nanosleep(spins < 64 ? 32 : 256);
-        if (++spins > (1u << 24)) {              // several seconds
-            atomicExch(&g_error, 1);
-            return false;
-        }
-        if (*reinterpret_cast<volatile int *>(&g_error)) return false;
-    }
-    return true;
-}
-
-__global__ void __launch_bounds__(FRONT_THREADS) k_front(DevPtrs p, EngineDims d, unsigned long long round0, int nrounds)
+__global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDims d, int max_blocks)
 {
     extern __shared__ __align__(16) unsigned char front_smem_raw[];
     FrontSmem &sm = *reinterpret_cast<FrontSmem *>(front_smem_raw);
-    __shared__ unsigned sh_ticket;
-    __shared__ int sh_ok, sh_last;
-    const int t = threadIdx.x, half = t >> 7, tl = t & 127;
-    const int S = d.nstreams;
-    const unsigned total = (unsigned)nrounds * (unsigned)S * TASKS_PER_BLOCK;
+    const int t = threadIdx.x, team = t >> 7, tl = t & 127;
+    const int s = blockIdx.x;
+    StreamState &st = p.st[s];
+    for (int i = t; i < FFT_TW; i += FRONT_THREADS) sm.tw[i] = __ldg(&p.twid[i]);
+    __syncthreads();
 
-    for (;;) {
-        if (t == 0) sh_ticket = atomicAdd(&g_ticket, 1u);
+    for (int nb = 0; nb < max_blocks; nb++) {
+        // a completed interleaver matrix is decoded (and its header checked) before the next block
+        if (st.p1_ready) break;
+        if (st.pids_pending) front_pids(p, d, s, sm.u.pids, t);
+        if (!front_prep(p, d, s, sm.u.prep, sm.nco, t)) break;
+        const long long start = st.start;
+        const int samperr = st.blk_samperr;
+        const float theta = st.theta;
+        const float2 phase0 = st.phase0;
+#pragma unroll 1
+        for (int pass = 0; pass < BLK / TEAMS; pass++)
+            front_demod(p, d, s, pass * TEAMS + team, sm.u.demod, sm.nco, sm.tw, team, tl, start, samperr, theta, phase0);
         __syncthreads();
-        const unsigned ticket = sh_ticket;
-        if (ticket >= total) break;
-        const int r = (int)(ticket / ((unsigned)S * TASKS_PER_BLOCK));
-        const unsigned rem = ticket - (unsigned)r * S * TASKS_PER_BLOCK;
-        const int s = (int)(rem / TASKS_PER_BLOCK), k = (int)(rem % TASKS_PER_BLOCK);
-        const unsigned long long round = round0 + (unsigned long long)r;
-        StreamState &st = p.st[s];
-
-        if (k == 0) {
-            if (t == 0) sh_ok = wait_flag(&st.q_synced, round);       // the previous block of this stream is done
-            __syncthreads();
-            if (!sh_ok) break;
-            __threadfence();
-            if (st.pids_pending) front_pids(p, d, s, sm.pids, t);
-            front_prep(p, d, s, sm.prep, t);
-            __threadfence();                                           // every thread publishes its writes ...
-            __syncthreads();
-            if (t == 0) {
-                __threadfence();
-                *reinterpret_cast<volatile unsigned long long *>(&st.q_prepped) = round + 1;   // ... before the flag
-            }
-        } else {
-            if (t == 0) sh_ok = wait_flag(&st.q_prepped, round + 1);
-            __syncthreads();
-            if (!sh_ok) break;
-            __threadfence();
-        }
-        if (st.active)
-            front_demod(p, d, s, 2 * k + half, sm.demod, half, tl, st.start, st.blk_samperr, st.theta, st.phase0);
-        __threadfence();
-        __syncthreads();
-        if (t == 0) {
-            __threadfence();
-            const int old = atomicAdd(&st.q_cnt, 1);
-            sh_last = old == TASKS_PER_BLOCK - 1;
-            if (sh_last) st.q_cnt = 0;
-        }
-        __syncthreads();
-        if (sh_last) {
-            __threadfence();
-            if (st.active) front_sync(p, d, s, sm.sync, t);
-            __threadfence();
-            __syncthreads();
-            if (t == 0) {
-                __threadfence();
-                *reinterpret_cast<volatile unsigned long long *>(&st.q_synced) = round + 1;
-            }
-        }
+        front_sync(p, d, s, sm.u.sync, t);
         __syncthreads();
     }
 }
