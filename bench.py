@@ -328,6 +328,9 @@ def main():
     torch.cuda.synchronize()
     kt = e.kernel_times()
     e.set_profiling(False)
+    # where the front-end kernel's SM time goes: average microseconds per stream-block and phase
+    clk_mhz = 1965.0
+    phases = {k: {"us_per_call": (c / n / clk_mhz) if n else 0.0, "calls": n} for k, (c, n) in e.phase_cycles().items()}
     st = e.stats()
     peak, peak_src = measured_peak()
     blocks_per_step = None
@@ -338,6 +341,7 @@ def main():
     b1 = e.stats().blocks
     blocks_per_step = int(b1 - b0) if b1 > b0 else int(b1)
     frames_per_step = int(e.stats().p1_frames)
+    p1_fallbacks = int(e.stats().p1_fallbacks)
     kinfo = {}
     # algorithmic bytes: fused front end 299 520 B per stream-block (276 480 B cu8 in + 23 040 B
     # int8 soft bits out); P1 decode group 387 072 B per L1 frame
@@ -351,7 +355,8 @@ def main():
                 "frac": kinfo[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom] / max(1, kt[dom]["launches"]),
                 "chain_frac_of_hbm": (2.34 * value * 1e6 / world) / (peak * 1e9),
-                "kernels": kinfo}
+                "kernels": kinfo, "front_phases_at_1965MHz": phases,
+                "p1_frames_per_step": frames_per_step, "p1_fast_path_fallbacks": p1_fallbacks}
 
     # ---- e2e ----
     e2e = None

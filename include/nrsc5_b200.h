@@ -126,19 +126,27 @@ typedef struct {
     uint64_t samples;         /* cu8 complex samples consumed (all streams)     */
     uint64_t p1_frames;       /* P1 frames decoded                              */
     uint64_t kernel_launches; /* kernels launched by the engine                 */
+    uint64_t p1_fallbacks;    /* P1 frames the fast Viterbi handed to the exact fallback kernels */
 } nrsc5b_stats_t;
 int nrsc5b_get_stats(nrsc5b_engine_t *e, nrsc5b_stats_t *st);
 
 /* Per-kernel device time from CUDA events around every launch (a separate, slower pass):
- * ms4/n4 = {prep, demod, sync, p1} accumulated milliseconds and launch counts since set_profiling(1). */
+ * ms4/n4: slot 1 = the front-end kernel (k_stream), slot 3 = the P1 decode group; slots 0, 2 unused. */
 int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on);
 int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long *n4);
+
+/* SM cycles spent by the stream-resident front-end kernel per phase, summed over streams since the last reset /
+ * rewind: cyc6/n6 = {pids flush, prep with coarse acquisition, prep in fine sync, demod (32 symbols),
+ * sync+demap of a block that started in fine sync, sync of any other block (vote / CFO search)}. */
+int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc6, unsigned long long *n6);
 
 /* ---- single-stage entry points (kernel-level parity tests, host buffers) ---- */
 /* cu8 -> Q15 -> halfband /2 from zero history: out[2*npairs] int16 (reference src/firdecim_q15.c:137-165) */
 int nrsc5b_halfband_fm(int device, const uint8_t *cu8, size_t npairs, int16_t *out_ri);
 /* batch of tail-biting K=7 rate-1/3 Viterbi decodes: in[nframes][3*len] int8 -> out[nframes][len] bits (one per byte) */
 int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int len, int nframes);
+/* same; *fallbacks = frames the register-resident fast path handed to the exact fallback kernels */
+int nrsc5b_viterbi_k7_ex(int device, const int8_t *in, uint8_t *out, int len, int nframes, int *fallbacks);
 /* batch RS(255,247) decode in place; rc[n] = corrections or -1 (reference src/rs_decode.c:16) */
 int nrsc5b_rs_decode(int device, uint8_t *blocks255, int *rc, int nblocks);
 /* 2048-point forward complex FFT of nffts rows (float2 interleaved), natural order, for numerics tests */

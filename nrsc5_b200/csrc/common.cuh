@@ -68,18 +68,24 @@ struct StreamState {
     // P1 hand-off sync -> p1 kernel
     int p1_ready;
     int p1_slow;               // this frame needs saturating Viterbi arithmetic
+    int p1_retry;              // the register-resident fast path could not prove its result: use the exact fallback kernels
     unsigned p1_rec;           // log offset of the reserved BER payload (FRAME record follows)
     int p1_errs;               // channel bit errors counted so far
     int p1_done;               // k_p1_fin CTAs finished
-    int pids_pending;          // a PIDS frame (block pids_bc) waits to be decoded into the log slot pids_rec
-    int pids_bc;
-    unsigned pids_rec;
+    int pids_pending;          // PIDS frames (of blocks pids_bc[]) waiting to be decoded into the log slots pids_rec[];
+    int pids_bc[16];           // k_stream decodes them together, one warp each, before it exits
+    unsigned pids_rec[16];
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
     // output log cursor
     unsigned log_len;
     unsigned log_overflow;
     unsigned long long blocks_done;
     unsigned long long frames_done;
+    unsigned long long p1_fallbacks;    // P1 frames decoded by the exact fallback Viterbi
+    // SM cycles spent per phase of k_stream (thread 0's clock): pids flush, prep with acquisition, prep in FINE,
+    // demod, sync of a block that started in FINE, sync of any other block (vote / CFO search)
+    unsigned long long ph_cyc[6];
+    unsigned long long ph_n[6];
     // history of the coarse band-pass FIR: the last 31 samples it was fed
     short bp_hist[31][2];
 };
@@ -105,13 +111,16 @@ struct DevPtrs {
     int8_t *vit_in;            // [S][438528]
     uint2 *vit_dec;            // [S][146240]
     uint32_t *p1_bits;         // [S][146176/32] decoded (still scrambled) bits, bit k of word w = frame bit 32w+k
-    uint2 *vspec, *vend;       // [S][143][16] chunk boundary metrics of the P1 Viterbi
+    uint2 *vspec, *vend;       // [S][143][16] chunk boundary metrics of the fallback P1 Viterbi
     int *hstate, *tbend;       // [S][143]
+    uint32_t *v64_spec, *v64_end;   // [S][V64 chunks][32] chunk boundary metrics of the fast P1 Viterbi
+    int *v64_endstate;         // [S]
     uint8_t *log;              // [S][log_cap]
     const float *shape;        // [2160]
     const float2 *twid;        // [FFT_TW] twiddle tables of fft2048_block (fft.cuh)
     const uint32_t *p1_lut;    // [365440] interleaver I gather index
-    const uint8_t *pn;         // [146176] descrambler sequence
+    const uint8_t *pn;         // [146176] descrambler sequence, one bit per byte
+    const uint32_t *pnw;       // [146176/32] the same, packed (bit i of word i/32)
 };
 
 // ---- log writer: one CTA owns a stream's log at any time ----

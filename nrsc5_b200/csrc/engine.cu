@@ -18,6 +18,7 @@
 #include "rs.cuh"
 #include "viterbi.cuh"
 #include "viterbi_chunk.cuh"
+#include "viterbi64.cuh"
 #include "front.cuh"
 
 namespace nb {
@@ -36,12 +37,21 @@ void launch_halfband_test(const uint8_t *cu8, long long npairs, short2 *out, cud
 constexpr int P1_THREADS = 256;
 constexpr int P1_NCH = (P1_STEPS + CH_LEN - 1) / CH_LEN;             // 143
 
+// Interleaver I as a row-wise pass: all P1 soft bits that come from matrix row r of the 16 blocks
+// (decode.c:296-322: row = 11k % 32, k = i / 320) are the 320-bit groups k = 3r % 32 + 32m.  A CTA stages
+// those 16 x 720 bytes with coalesced loads and writes each group's 384 depunctured bytes contiguously;
+// inside a group the source offset (block, partition) depends on the position only, the column on k only.
+__constant__ uint16_t c_p1_src[320];                                   // (block * 720 + partition * 36) of position w
+
 __global__ void __launch_bounds__(256) k_p1_gather(DevPtrs p, EngineDims d)
 {
-    const int s = blockIdx.y;
+    const int s = blockIdx.y, r = blockIdx.x, t = threadIdx.x;
     StreamState &st = p.st[s];
     if (!st.p1_ready) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __shared__ __align__(16) int8_t rows[16 * 720];
+    __shared__ uint16_t src[320];
+    for (int i = t; i < 320; i += 256) src[i] = c_p1_src[i];
+    if (r == 0 && t == 0) {
         // reserve the BER and FRAME records now so that they keep their place in the stream's record order
         uint8_t *w = log_reserve(p, d, s, REC_BER, 4);
         uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8);
@@ -52,12 +62,28 @@ __global__ void __launch_bounds__(256) k_p1_gather(DevPtrs p, EngineDims d)
         }
         st.p1_errs = 0;
         st.p1_done = 0;
+        st.p1_retry = 0;
     }
     const int8_t *pm = p.pm + (size_t)s * 16 * PM_BLOCK;
-    int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P1_VIT; o += gridDim.x * blockDim.x) {
-        const int q = o / 6, r = o - 6 * q;
-        vin[o] = r == 5 ? (int8_t)0 : pm[p.p1_lut[5 * q + r]];
+    for (int v = t; v < 16 * 45; v += 256) {
+        const int blk = v / 45, q = v - blk * 45;
+        reinterpret_cast<uint4 *>(rows)[v] = *reinterpret_cast<const uint4 *>(pm + (size_t)(blk * 32 + r) * 720 + 16 * q);
+    }
+    __syncthreads();
+    uint32_t *vout = reinterpret_cast<uint32_t *>(p.vit_in + (size_t)s * P1_VIT);
+    const int k0 = (3 * r) & 31;                                        // 11 * 3 = 1 (mod 32)
+    for (int item = t; item < 36 * 96; item += 256) {
+        const int m = item / 96, wq = item - m * 96;
+        const int k = k0 + 32 * m;
+        if (k >= P1_ENC / 320) break;
+        const int col = (11 * k + k / 288) % 36;
+        uint32_t word = 0;
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            const int o = 4 * wq + bb, q = o / 6, r6 = o - 6 * q;
+            if (r6 != 5) word |= (uint32_t)(uint8_t)rows[src[5 * q + r6] + col] << (8 * bb);
+        }
+        vout[96 * k + wq] = word;
     }
 }
 
@@ -69,6 +95,8 @@ __device__ __forceinline__ unsigned p1_bit(const uint32_t *bw, int i)
     return (bw[i >> 5] >> (i & 31)) & 1u;
 }
 
+__constant__ uint32_t c_spread3[256];                                 // bit k of the index -> bit 3k
+
 __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
 {
     const int s = blockIdx.y, t = threadIdx.x;
@@ -78,6 +106,9 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     __shared__ int sh_last;
     __shared__ uint8_t hdr[96];
     __shared__ uint8_t blk[255];
+    __shared__ uint32_t spread[256];
+    spread[t] = c_spread3[t];
+    __syncthreads();
     const int8_t *vin = p.vit_in + (size_t)s * P1_VIT;
     const uint32_t *bw = p.p1_bits + (size_t)s * (P1_LEN / 32);
     uint8_t *rec = st.p1_rec == 0xffffffffu ? nullptr : p.log + (size_t)s * d.log_cap + st.p1_rec;
@@ -85,27 +116,43 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     const int byte0 = blockIdx.x * FIN_BYTES, byte1 = min(P1_LEN / 8, byte0 + FIN_BYTES);
     int errs = 0;
     for (int bi = byte0 + t; bi < byte1; bi += P1_THREADS) {
-        // 14 decoded bits around this byte: bits 8*bi-6 .. 8*bi+7 (tail-biting wrap at the frame start)
-        unsigned win = 0;
-#pragma unroll
-        for (int k = 0; k < 14; k++) {
-            int idx = 8 * bi - 6 + k;
-            if (idx < 0) idx += P1_LEN;
-            win |= p1_bit(bw, idx) << k;
+        // 14 decoded bits around this byte: frame bits 8*bi-6 .. 8*bi+7 (tail-biting wrap at the frame start)
+        unsigned win;
+        {
+            const int i0 = 8 * bi - 6;
+            if (i0 >= 0) {
+                const int w0 = i0 >> 5;
+                const uint32_t lo = bw[w0], hi = (w0 + 1 < P1_LEN / 32) ? bw[w0 + 1] : 0u;
+                win = __funnelshift_r(lo, hi, i0 & 31) & 0x3fffu;
+            } else {
+                win = (bw[P1_LEN / 32 - 1] >> 26) | ((bw[0] & 0xffu) << 6);
+            }
         }
-        unsigned packed = 0;
+        // re-encode (decode.c:243-249): the register of bit i holds bits i-6..i, newest at bit 6; code bit of
+        // polynomial g for the byte's 8 bits at once = XOR over the taps of g of (win >> tap)
+        const unsigned e0 = (win ^ (win >> 1) ^ (win >> 3) ^ (win >> 4) ^ (win >> 6)) & 0xffu;      // 0133
+        const unsigned e1 = (win ^ (win >> 3) ^ (win >> 4) ^ (win >> 5) ^ (win >> 6)) & 0xffu;      // 0171
+        const unsigned e2 = (win ^ (win >> 2) ^ (win >> 4) ^ (win >> 5) ^ (win >> 6)) & 0xffu;      // 0165
+        const unsigned enc24 = spread[e0] | (spread[e1] << 1) | (spread[e2] << 2);
+        // signs of the 24 soft values of these 8 bits: bit m = (soft[24*bi + m] > 0)
+        unsigned pos24 = 0;
+        const uint2 *q = reinterpret_cast<const uint2 *>(vin + 24 * (size_t)bi);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int i = 8 * bi + k;
-            const unsigned reg = (win >> k) & 0x7f;              // bits i-6 .. i, newest at bit 6 (decode.c:243-249)
-            const int8_t *c = vin + 3 * i;
-            const int j = 3 * i;
-            if ((j % 6) != 5 && ((c[0] > 0) != (int)(__popc(reg & 0133u) & 1))) errs++;
-            if (((j + 1) % 6) != 5 && ((c[1] > 0) != (int)(__popc(reg & 0171u) & 1))) errs++;
-            if (((j + 2) % 6) != 5 && ((c[2] > 0) != (int)(__popc(reg & 0165u) & 1))) errs++;
-            packed |= (((win >> (k + 6)) & 1u) ^ p.pn[i]) << (7 - k);   // descramble (decode.c:279-294), MSB first
+        for (int h = 0; h < 3; h++) {
+            const uint2 v = q[h];
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                const unsigned x = g ? v.y : v.x;
+                const unsigned nz = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;          // bit 7 of a byte: byte != 0
+                const unsigned ps = ((nz & ~x) >> 7) & 0x01010101u;                 // byte > 0
+                pos24 |= ((ps * 0x01020408u) >> 24) << (8 * h + 4 * g);
+            }
         }
-        if (frame) frame[bi] = (uint8_t)packed;
+        // channel bit errors on the unpunctured positions (decode.c:234-259); every 6th soft value is a puncture
+        errs += __popc((enc24 ^ pos24) & 0x7df7dfu);
+        // descramble (decode.c:279-294) and pack MSB first
+        const unsigned bits8 = ((win >> 6) & 0xffu) ^ ((p.pnw[bi >> 2] >> (8 * (bi & 3))) & 0xffu);
+        if (frame) frame[bi] = (uint8_t)(__brev(bits8) >> 24);
     }
     red[t] = errs;
     __syncthreads();
@@ -125,7 +172,7 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     __threadfence();
     if (t < 96) {
         // PDU byte n of frame_push() is the bit-reversed packed byte n (the reference swaps the bit order per byte)
-        unsigned v = frame ? frame[t] : 0;
+        unsigned v = frame ? __ldcg(frame + t) : 0;
         hdr[t] = (uint8_t)(__brev(v) >> 24);
     }
     __syncthreads();
@@ -135,13 +182,15 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
         for (int h = 0; h < 24; h++) {
             const unsigned i = 116176u + 1248u * h;
             const unsigned phys = (i & ~7u) + 7 - (i & 7);
-            const unsigned bit = (p1_bit(bw, (int)phys) ^ p.pn[phys]) & 1u;
+            const unsigned bit = (p1_bit(bw, (int)phys) ^ (p.pnw[phys >> 5] >> (phys & 31))) & 1u;
             pci |= bit << (23 - h);
         }
         const bool has_audio = (pci & 0xFFFFFC) != (0x3634CE & 0xFFFFFC);
         if (has_audio && !fix_header_96(hdr, blk)) set_state(p, d, s, ST_NONE);
+        if (st.p1_retry) st.p1_fallbacks++;
         st.p1_ready = 0;
         st.p1_slow = 0;
+        st.p1_retry = 0;
         st.frames_done++;
     }
 }
@@ -156,11 +205,30 @@ __host__ __device__ inline VitcArgs p1_vitc_args(const DevPtrs &dp)
     a.hstate = dp.hstate;
     a.tbend = dp.tbend;
     a.bitsw = dp.p1_bits;
-    a.ready = &dp.st[0].p1_ready;
+    a.ready = &dp.st[0].p1_retry;      // the fallback only decodes what the fast path gave up on
     a.slow = &dp.st[0].p1_slow;
     a.ready_stride = (int)(sizeof(StreamState) / sizeof(int));
     a.len = P1_LEN;
     a.nch = P1_NCH;
+    a.dec_stride = (size_t)P1_NCH * CH_LEN;
+    return a;
+}
+
+__host__ __device__ inline V64Args p1_v64_args(const DevPtrs &dp, int ch)
+{
+    V64Args a;
+    a.vin = dp.vit_in;
+    a.dec = dp.vit_dec;
+    a.vspec = dp.v64_spec;
+    a.vend = dp.v64_end;
+    a.endstate = dp.v64_endstate;
+    a.bitsw = dp.p1_bits;
+    a.ready = &dp.st[0].p1_ready;
+    a.retry = &dp.st[0].p1_retry;
+    a.stride = (int)(sizeof(StreamState) / sizeof(int));
+    a.len = P1_LEN;
+    a.ch = ch;
+    a.nch = (P1_STEPS + ch - 1) / ch;
     a.dec_stride = (size_t)P1_NCH * CH_LEN;
     return a;
 }
@@ -252,6 +320,7 @@ struct nrsc5b_engine {
     nrsc5b_stats_t stats;
     unsigned long long last_progress;
     std::vector<void *> allocs;
+    int v64_ch;                        // chunk length of the fast P1 Viterbi (chosen from the stream count)
     int profiling;
     cudaEvent_t pev[5];
     double kernel_ms[4];
@@ -293,6 +362,14 @@ static int upload_tables(int device)
     short taps[32];
     for (int i = 0; i < 32; i++) taps[i] = (short)(k_bp_coeff[31 - i] * 32767.0f);
     CK(cudaMemcpyToSymbol(c_bp_tap, taps, sizeof(taps)));
+    unsigned pn80[3] = { 0, 0, 0 }, reg = 0x3ff;       // descrambler LFSR (reference src/decode.c:279-294)
+    for (int i = 0; i < 80; i++) {
+        const unsigned b = ((reg >> 9) ^ reg) & 1;
+        reg |= b << 11;
+        reg >>= 1;
+        pn80[i >> 5] |= b << (i & 31);
+    }
+    CK(cudaMemcpyToSymbol(c_pn80, pn80, sizeof(pn80)));
     done_for = device;
     return 0;
 }
@@ -397,6 +474,23 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     DA(tbend, int, (size_t)S * P1_NCH);
     DA(hstate, int, (size_t)S * P1_NCH);
     DA(p1_bits, uint32_t, (size_t)S * (P1_LEN / 32));
+    {
+        // fast Viterbi: one thread per chunk; pick the chunk length so that the warps of all streams' frames
+        // make one wave over the GPU's warp schedulers (4 per SM)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        int wpf = (4 * sms) / S;
+        if (wpf < 1) wpf = 1;
+        if (wpf > 18) wpf = 18;
+        int ch = (P1_STEPS + 32 * wpf - 1) / (32 * wpf);
+        ch = (ch + 31) & ~31;
+        if (ch < 256) ch = 256;
+        e->v64_ch = ch;
+        const size_t nch = (size_t)(P1_STEPS + ch - 1) / ch;
+        DA(v64_spec, uint32_t, (size_t)S * nch * 32);
+        DA(v64_end, uint32_t, (size_t)S * nch * 32);
+        DA(v64_endstate, int, (size_t)S);
+    }
     DA(log, uint8_t, (size_t)S * e->dims.log_cap);
     {
         // tables
@@ -426,6 +520,14 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
             unsigned row = (k * 11) % 32, col = (k * 11 + k / 288) % 36;
             lut[i] = (block * 32 + row) * 720 + part * 36 + col;
         }
+        {
+            uint16_t src[320];
+            for (int w = 0; w < 320; w++) {
+                const int part = PMV[w % 20], blk = (w / 20 + 7 * part) % 16;
+                src[w] = (uint16_t)(blk * 720 + part * 36);
+            }
+            cudaMemcpyToSymbol(c_p1_src, src, sizeof(src));
+        }
         uint32_t *dlut = nullptr;
         rc = dev_alloc(e, &dlut, P1_ENC);
         if (rc) { nrsc5b_destroy(e); return rc; }
@@ -444,6 +546,21 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         if (rc) { nrsc5b_destroy(e); return rc; }
         cudaMemcpy(dpn, pn.data(), P1_LEN, cudaMemcpyHostToDevice);
         dp.pn = dpn;
+        std::vector<uint32_t> pnw(P1_LEN / 32, 0u);
+        for (int i = 0; i < P1_LEN; i++) pnw[i >> 5] |= (uint32_t)pn[i] << (i & 31);
+        uint32_t *dpnw = nullptr;
+        rc = dev_alloc(e, &dpnw, P1_LEN / 32);
+        if (rc) { nrsc5b_destroy(e); return rc; }
+        cudaMemcpy(dpnw, pnw.data(), pnw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        dp.pnw = dpnw;
+        {
+            uint32_t sp[256];
+            for (int v = 0; v < 256; v++) {
+                sp[v] = 0;
+                for (int k = 0; k < 8; k++) sp[v] |= (uint32_t)((v >> k) & 1) << (3 * k);
+            }
+            cudaMemcpyToSymbol(c_spread3, sp, sizeof(sp));
+        }
     }
 #undef DA
     e->pinned_cap = 8u << 20;
@@ -457,7 +574,8 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         return NRSC5B_ENOMEM;
     }
     if (cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess) {
+        cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_v64_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V64_EMIT_SMEM) != cudaSuccess) {
         nrsc5b_destroy(e);
         return NRSC5B_ECUDA;
     }
@@ -600,13 +718,22 @@ static void launch_vitc(const VitcArgs &a, int nframes, cudaStream_t stream)
     k_vitc_emit<<<ge, VITC_EMIT_WARPS * 32, vitc_emit_smem(), stream>>>(a);
 }
 
+static void launch_v64(const V64Args &a, int nframes, cudaStream_t stream)
+{
+    k_v64_fwd<<<dim3((a.nch + V64_FWD_THREADS - 1) / V64_FWD_THREADS, nframes), V64_FWD_THREADS, 0, stream>>>(a);
+    k_v64_check<<<nframes, V64_CHECK_THREADS, 0, stream>>>(a);
+    const int nwin = (a.len + 64 + V64_WIN - 1) / V64_WIN;
+    k_v64_emit<<<dim3((nwin + V64_EMIT_WARPS - 1) / V64_EMIT_WARPS, nframes), V64_EMIT_WARPS * 32, V64_EMIT_SMEM, stream>>>(a);
+}
+
 static void launch_p1(nrsc5b_engine *e)
 {
     const int S = e->dims.nstreams;
-    k_p1_gather<<<dim3(16, S), 256, 0, e->stream>>>(e->dp, e->dims);
-    launch_vitc(p1_vitc_args(e->dp), S, e->stream);
+    k_p1_gather<<<dim3(32, S), 256, 0, e->stream>>>(e->dp, e->dims);
+    launch_v64(p1_v64_args(e->dp, e->v64_ch), S, e->stream);      // fast path ...
+    launch_vitc(p1_vitc_args(e->dp), S, e->stream);               // ... exact fallback for the frames it flagged
     k_p1_fin<<<dim3(FIN_CTAS, S), P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
-    e->stats.kernel_launches += 5;
+    e->stats.kernel_launches += 8;
 }
 
 // One pass: every stream runs its front end up to its next frame boundary (at most BLOCKS_PER_PASS blocks,
@@ -642,6 +769,19 @@ extern "C" int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on)
         for (int i = 0; i < 5; i++) CK(cudaEventCreate(&e->pev[i]));
     e->profiling = on;
     for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
+    return NRSC5B_OK;
+}
+
+extern "C" int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc5, unsigned long long *n5)
+{
+    // six slots (see StreamState::ph_cyc)
+    if (!e || !cyc5 || !n5) return NRSC5B_EINVAL;
+    CK(cudaStreamSynchronize(e->stream));
+    const int S = e->dims.nstreams;
+    CK(cudaMemcpy(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; i++) { cyc5[i] = 0; n5[i] = 0; }
+    for (int s = 0; s < S; s++)
+        for (int i = 0; i < 6; i++) { cyc5[i] += e->h_state[s].ph_cyc[i]; n5[i] += e->h_state[s].ph_n[i]; }
     return NRSC5B_OK;
 }
 
@@ -739,13 +879,15 @@ extern "C" int nrsc5b_get_stats(nrsc5b_engine_t *e, nrsc5b_stats_t *out)
     CK(cudaStreamSynchronize(e->stream));
     const int S = e->dims.nstreams;
     CK(cudaMemcpy(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost));
-    unsigned long long frames = 0, samples = 0, blocks = 0;
+    unsigned long long frames = 0, samples = 0, blocks = 0, fb = 0;
     for (int s = 0; s < S; s++) {
+        fb += e->h_state[s].p1_fallbacks;
         frames += e->h_state[s].frames_done;
         blocks += e->h_state[s].blocks_done;
         samples += (unsigned long long)(2 * e->h_state[s].start);
     }
     e->stats.p1_frames = frames;
+    e->stats.p1_fallbacks = fb;
     e->stats.blocks = blocks;
     e->stats.samples = samples;
     *out = e->stats;
@@ -780,7 +922,20 @@ extern "C" int nrsc5b_halfband_fm(int device, const uint8_t *cu8, size_t npairs,
     return NRSC5B_OK;
 }
 
+static int viterbi_k7_impl(int device, const int8_t *in, uint8_t *out, int len, int nframes, int *fallbacks);
+
 extern "C" int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int len, int nframes)
+{
+    return viterbi_k7_impl(device, in, out, len, nframes, nullptr);
+}
+
+/* Same, and reports how many frames the register-resident fast path handed to the exact fallback kernels. */
+extern "C" int nrsc5b_viterbi_k7_ex(int device, const int8_t *in, uint8_t *out, int len, int nframes, int *fallbacks)
+{
+    return viterbi_k7_impl(device, in, out, len, nframes, fallbacks);
+}
+
+static int viterbi_k7_impl(int device, const int8_t *in, uint8_t *out, int len, int nframes, int *fallbacks)
 {
     int rc = use_device(device);
     if (rc) return rc;
@@ -792,36 +947,59 @@ extern "C" int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int
     CK(cudaMalloc(&dout, (size_t)nframes * len));
     CK(cudaMemcpy(din, in, nin, cudaMemcpyHostToDevice));
     if (len >= 2048 && (len % 32) == 0) {
-        // chunk-parallel exact decoder (the engine's P1 path)
+        // the engine's P1 path: register-resident fast decoder, then the exact fallback for flagged frames
+        const int total = len + 64;
+        int *dflags = nullptr;                       // [ready | slow | retry] x nframes
+        CK(cudaMalloc(&dflags, (size_t)nframes * 3 * sizeof(int)));
+        std::vector<int> fl(3 * (size_t)nframes, 0);
+        for (int i = 0; i < nframes; i++) fl[i] = 1;
+        CK(cudaMemcpy(dflags, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
+        uint32_t *dbw = nullptr;
+        CK(cudaMalloc(&dbw, (size_t)nframes * (len / 32) * sizeof(uint32_t)));
         VitcArgs a;
         a.len = len;
-        a.nch = (len + 64 + CH_LEN - 1) / CH_LEN;
+        a.nch = (total + CH_LEN - 1) / CH_LEN;
         a.dec_stride = (size_t)a.nch * CH_LEN;
         a.ready_stride = 1;
-        int *dflags = nullptr;
         CK(cudaMalloc(&a.dec, (size_t)nframes * a.dec_stride * sizeof(uint2)));
         CK(cudaMalloc(&a.vspec, (size_t)nframes * a.nch * 16 * sizeof(uint2)));
         CK(cudaMalloc(&a.vend, (size_t)nframes * a.nch * 16 * sizeof(uint2)));
         CK(cudaMalloc(&a.tbend, (size_t)nframes * a.nch * sizeof(int)));
         CK(cudaMalloc(&a.hstate, (size_t)nframes * a.nch * sizeof(int)));
-        uint32_t *dbw = nullptr;
-        CK(cudaMalloc(&dbw, (size_t)nframes * (len / 32) * sizeof(uint32_t)));
-        CK(cudaMalloc(&dflags, (size_t)nframes * 2 * sizeof(int)));
-        std::vector<int> fl(2 * (size_t)nframes, 0);
-        for (int i = 0; i < nframes; i++) fl[i] = 1;
-        CK(cudaMemcpy(dflags, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
         a.vin = din;
         a.bitsw = dbw;
-        a.ready = dflags;
+        a.ready = dflags + 2 * nframes;              // the fallback decodes the frames flagged `retry`
         a.slow = dflags + nframes;
+        V64Args b;
+        b.vin = din;
+        b.dec = a.dec;
+        b.bitsw = dbw;
+        b.ready = dflags;
+        b.retry = dflags + 2 * nframes;
+        b.stride = 1;
+        b.len = len;
+        b.ch = len >= 16384 ? 1024 : 256;
+        b.nch = (total + b.ch - 1) / b.ch;
+        b.dec_stride = a.dec_stride;
+        CK(cudaMalloc(&b.vspec, (size_t)nframes * b.nch * 32 * sizeof(uint32_t)));
+        CK(cudaMalloc(&b.vend, (size_t)nframes * b.nch * 32 * sizeof(uint32_t)));
+        CK(cudaMalloc(&b.endstate, (size_t)nframes * sizeof(int)));
         CK(cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()));
+        CK(cudaFuncSetAttribute(k_v64_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V64_EMIT_SMEM));
+        launch_v64(b, nframes, 0);
         launch_vitc(a, nframes, 0);
         {
             size_t nb = (size_t)nframes * len;
             k_vitc_unpack<<<(unsigned)((nb + 255) / 256), 256>>>(dbw, dout, nb);
         }
         CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(fl.data(), dflags, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        if (fallbacks) {
+            *fallbacks = 0;
+            for (int i = 0; i < nframes; i++) *fallbacks += fl[2 * (size_t)nframes + i] != 0;
+        }
         cudaFree(a.dec); cudaFree(a.vspec); cudaFree(a.vend); cudaFree(a.tbend); cudaFree(a.hstate); cudaFree(dflags); cudaFree(dbw);
+        cudaFree(b.vspec); cudaFree(b.vend); cudaFree(b.endstate);
     } else {
         uint2 *ddec = nullptr;
         CK(cudaMalloc(&ddec, (size_t)nframes * (len + 64) * sizeof(uint2)));

@@ -30,6 +30,7 @@ constexpr int IN_STRIDE = 8704;
 __device__ unsigned long long g_progress;          // bumped by every stream that processed a block
 
 __constant__ int c_compat_mode[64];
+__constant__ unsigned c_pn80[3];                   // first 80 bits of the descrambler sequence (bit i of word i/32)
 __constant__ short c_bp_tap[32];                   // coarse band-pass taps, tap[i] pairs w[i] and w[32-i]
 
 // complex helpers with the reference's (gcc, no FMA) evaluation order
@@ -86,22 +87,29 @@ struct PrepSmem {
     int red_idx[FRONT_THREADS];
     float2 red_v[FRONT_THREADS];
 };
+struct PidsSmem {
+    int8_t vit[PIDS_LEN * 3];
+    uint2 dec[PIDS_LEN + 64];
+};
+constexpr int EQ_LD = BLK + 1;                      // padded row of the equalisation buffer (bank-conflict free)
+constexpr int EQ_ROWS = MAXPART * (PW - 1);         // data carriers of one sideband
 struct SyncSmem {
     float2 zref[2 * MAXREF][BLK];                  // reference carriers after their Costas loop
     float phs[2 * MAXREF][BLK];                    // Costas phase per reference and symbol
+    float2 eph[2 * MAXREF][BLK];                   // exp(j*phs)
     float smag[2 * MAXREF];
-    float err_lb[2 * MAXPART][BLK], err_ub[2 * MAXPART][BLK];   // per (partition, symbol) error sums
-    float part_lb[BLK], part_ub[BLK];
+    float cfq[2 * MAXREF];                         // Costas frequency of every reference after the block
+    float2 eq[EQ_ROWS][EQ_LD];                     // one sideband's data carriers [partition*18 + k-1][symbol]
+    float eerr[EQ_ROWS][EQ_LD];                    // their squared distance to the nearest QPSK point
+    float err_part[MAXPART][BLK];                  // per (partition, symbol) error sums
+    float part_sum[BLK];
     float2 rows[22][BLK];                          // CFO search: working rows
     float tmp_phs[22][BLK];
     int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
     int offs[32];
-    float mult_lb, mult_ub;
+    float mult[2];
+    float angle;
     int do_search;
-};
-struct PidsSmem {
-    int8_t vit[PIDS_LEN * 3];
-    uint2 dec[PIDS_LEN + 64];
 };
 struct FrontSmem {
     float2 tw[FFT_TW];                             // FFT twiddle tables (fft.cuh)
@@ -110,20 +118,21 @@ struct FrontSmem {
         DemodSmem demod;
         PrepSmem prep;
         SyncSmem sync;
-        PidsSmem pids;
+        PidsSmem pidsq[16];
     } u;
 };
 
 // ---------------------------------------------------------------------------
 // pids: interleaver II + depuncture (decode.c:324-342), K=7 Viterbi, descramble (decode.c:279-294)
 // ---------------------------------------------------------------------------
-__device__ void front_pids(const DevPtrs &p, const EngineDims &d, int s, PidsSmem &sm, int t)
+// One warp decodes pending PIDS frame `e` of the stream into its reserved log slot.
+__device__ void pids_decode_warp(const DevPtrs &p, const EngineDims &d, int s, int e, PidsSmem &sm, int lane)
 {
-    StreamState &st = p.st[s];
-    const int bc = st.pids_bc;
+    const StreamState &st = p.st[s];
+    const int bc = st.pids_bc[e];
     const int8_t *pmall = p.pm + (size_t)s * 16 * PM_BLOCK;
     const int8_t PMV[20] = { 10, 2, 18, 6, 14, 8, 16, 0, 12, 4, 11, 3, 19, 7, 15, 9, 17, 1, 13, 5 };
-    for (int o = t; o < PIDS_LEN * 3; o += FRONT_THREADS) {
+    for (int o = lane; o < PIDS_LEN * 3; o += 32) {
         int8_t v = 0;
         if (o % 6 != 5) {
             unsigned i = (unsigned)bc * 200 + (unsigned)(o - o / 6);
@@ -135,47 +144,53 @@ __device__ void front_pids(const DevPtrs &p, const EngineDims &d, int s, PidsSme
         }
         sm.vit[o] = v;
     }
-    __syncthreads();
-    if (t < 32) {
-        // both half-warps decode the same frame (the packed kernel works on two chunks per warp); FM PIDS
-        // soft bits are punctured 1,1,1,1,1,0, so the int16 metrics cannot saturate
-        const int l = t & 15;
-        VitHalf<false> vh;
-        vh.init(l);
-        vitc_run<false>(vh, sm.vit, PIDS_LEN, PIDS_LEN + 64, 0, PIDS_LEN + 64, 0, sm.dec, t < 16, l);
-        __syncwarp();
-        // first maximum in state order; lane l holds states 2l, 2l+32 (E) and 2l+1, 2l+33 (O)
-        int v = (short)(vh.E & 0xffff), state = 2 * l;
-        const int w1 = (short)(vh.O & 0xffff);
-        if (w1 > v) { v = w1; state = 2 * l + 1; }
-        int v2 = (short)(vh.E >> 16), idx2 = 2 * l + 32;
-        const int w3 = (short)(vh.O >> 16);
-        if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
-        if (v2 > v) { v = v2; state = idx2; }
+    __syncwarp();
+    // both half-warps decode the same frame (the packed kernel works on two chunks per warp); FM PIDS
+    // soft bits are punctured 1,1,1,1,1,0, so the int16 metrics cannot saturate
+    const int l = lane & 15;
+    VitHalf<false> vh;
+    vh.init(l);
+    vitc_run<false>(vh, sm.vit, PIDS_LEN, PIDS_LEN + 64, 0, PIDS_LEN + 64, 0, sm.dec, lane < 16, l);
+    __syncwarp();
+    // first maximum in state order; lane l holds states 2l, 2l+32 (E) and 2l+1, 2l+33 (O)
+    int v = (short)(vh.E & 0xffff), state = 2 * l;
+    const int w1 = (short)(vh.O & 0xffff);
+    if (w1 > v) { v = w1; state = 2 * l + 1; }
+    int v2 = (short)(vh.E >> 16), idx2 = 2 * l + 32;
+    const int w3 = (short)(vh.O >> 16);
+    if (w3 > v2) { v2 = w3; idx2 = 2 * l + 33; }
+    if (v2 > v) { v = v2; state = idx2; }
 #pragma unroll
-        for (int o = 8; o; o >>= 1) {
-            const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, state, o, 16);
-            if (ov > v || (ov == v && oi < state)) { v = ov; state = oi; }
+    for (int o = 8; o; o >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, v, o, 16), oi = __shfl_xor_sync(0xffffffffu, state, o, 16);
+        if (ov > v || (ov == v && oi < state)) { v = ov; state = oi; }
+    }
+    if (lane == 0) {
+        uint8_t pk[10];
+        for (int i = 0; i < 10; i++) pk[i] = 0;
+        for (int q = PIDS_LEN + 63; q >= 0; q--) {
+            if (q >= 32 && q < 32 + PIDS_LEN) {
+                const int i = q - 32;
+                const int bit = ((state >> 5) & 1) ^ (int)((c_pn80[i >> 5] >> (i & 31)) & 1u);
+                pk[i >> 3] |= (uint8_t)(bit << (7 - (i & 7)));
+            }
+            state = vitc_prev_head(state, sm.dec, q);
         }
-        if (t == 0) {
-            uint8_t pk[10];
-            for (int i = 0; i < 10; i++) pk[i] = 0;
-            for (int q = PIDS_LEN + 63; q >= 0; q--) {
-                if (q >= 32 && q < 32 + PIDS_LEN) {
-                    const int i = q - 32;
-                    const int bit = ((state >> 5) & 1) ^ __ldg(&p.pn[i]);
-                    pk[i >> 3] |= (uint8_t)(bit << (7 - (i & 7)));
-                }
-                state = vitc_prev_head(state, sm.dec, q);
-            }
-            if (st.pids_rec != 0xffffffffu) {
-                uint8_t *w = p.log + (size_t)s * d.log_cap + st.pids_rec;
-                for (int i = 0; i < 10; i++) w[i] = pk[i];
-            }
-            st.pids_pending = 0;
+        if (st.pids_rec[e] != 0xffffffffu) {
+            uint8_t *w = p.log + (size_t)s * d.log_cap + st.pids_rec[e];
+            for (int i = 0; i < 10; i++) w[i] = pk[i];
         }
     }
+}
+
+// decode every pending PIDS frame of the stream (at most 16), one warp each
+__device__ void front_pids_flush(const DevPtrs &p, const EngineDims &d, int s, PidsSmem *sm, int t)
+{
+    StreamState &st = p.st[s];
+    const int n = st.pids_pending, warp = t >> 5;
+    if (warp < n) pids_decode_warp(p, d, s, warp, sm[warp], t & 31);
     __syncthreads();
+    if (t == 0) st.pids_pending = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -549,7 +564,11 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         const int i = t < MAXREF ? t : t - MAXREF;
         if (i < nref) {
             const int b = ref_bin(t);
-            costas_row(sm.zref[t], sm.phs[t], cfreq[b], cphase[b], 0, alpha, beta);
+            float f = cfreq[b], ph = cphase[b];
+            costas_row(sm.zref[t], sm.phs[t], f, ph, 0, alpha, beta);
+            cfreq[b] = f;
+            cphase[b] = ph;
+            sm.cfq[t] = f;
         }
     }
     __syncthreads();
@@ -663,7 +682,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
     }
 
     if (st.state == ST_FINE) {
-        // reference amplitude per subcarrier (calc_smag, sync.c:254-261)
+        // reference amplitude per subcarrier (calc_smag, sync.c:254-261) and exp(j*phase) per (reference, symbol)
         if (t < 2 * MAXREF) {
             const int i = t < MAXREF ? t : t - MAXREF;
             if (i < nref) {
@@ -672,36 +691,13 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 sm.smag[t] = sum / BLK;
             }
         }
-        __syncthreads();
-        // adjust_data (sync.c:263-282) + squared error to the nearest QPSK point (sync.c:465-488):
-        // one thread per (partition, symbol); the equalised carriers go back to `bins`
-        for (int item = t; item < 2 * ppb * BLK; item += FRONT_THREADS) {
-            const int n = item & (BLK - 1), pp = item >> 5;
-            const int upper = pp >= ppb, i = upper ? pp - ppb : pp;
-            int lo_bin, slot_lo, slot_hi;
-            if (!upper) { lo_bin = LB0 + PW * i; slot_lo = i; slot_hi = i + 1; }
-            else { lo_bin = UB1 - PW * i - PW; slot_lo = MAXREF + i + 1; slot_hi = MAXREF + i; }
-            const float m0 = sm.smag[slot_lo], m19 = sm.smag[slot_hi];
-            const float2 up = cexp_j(sm.phs[slot_hi][n]);
-            const float2 lp = cexp_j(sm.phs[slot_lo][n]);
-            float2 *zc = bins + (size_t)n * NBINS + compact_of_bin(lo_bin);
-            float e = 0;
-            for (int k = 1; k < PW; k++) {
-                const float fa = (float)k * m19, fb = (float)(PW - k) * m0;
-                const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
-                const float rden = 19.0f / (c * c + dd * dd);
-                // (19 + 19j) / (c + j dd)
-                const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
-                const float2 v = cmulf(zc[k], C);
-                zc[k] = v;
-                const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
-                e += dx * dx + dy * dy;
-            }
-            if (!upper) sm.err_lb[i][n] = e;
-            else sm.err_ub[i][n] = e;
+        for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
+            const int slot = i >> 5, n = i & 31;
+            const int ii = slot < MAXREF ? slot : slot - MAXREF;
+            if (ii < nref) sm.eph[slot][n] = cexp_j(sm.phs[slot][n]);
         }
-        // timing / phase feedback (sync.c:426-463)
-        if (t == 0) {
+        // timing / phase feedback (sync.c:426-463), one thread of the last warp while the others equalise
+        if (t == FRONT_THREADS - 1) {
             float samperr = 0, angle = 0, sum_xy = 0, sum_x2 = 0;
             for (int i = 0; i < ppb; i++) {
                 samperr += half_pi_wrap(sm.phs[i][0], sm.phs[i + 1][0]);
@@ -711,35 +707,98 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             for (int i = 0; i <= ppb; i++) {
                 float x, y;
                 x = (float)(LB0 + PW * i - NFFT / 2);
-                y = cfreq[LB0 + PW * i];
+                y = sm.cfq[i];
                 angle += y; sum_xy += x * y; sum_x2 += x * x;
                 x = (float)(UB1 - PW * i - NFFT / 2);
-                y = cfreq[UB1 - PW * i];
+                y = sm.cfq[MAXREF + i];
                 angle += y; sum_xy += x * y; sum_x2 += x * x;
             }
             samperr = (float)((double)samperr - (double)((sum_xy / sum_x2) * (float)NFFT) / (2 * M_PI) * BLK);
             st.samperr = (int)roundf(samperr);
             angle /= (float)((ppb + 1) * 2);
             st.angle = angle;
-            for (int i = 0; i <= ppb; i++) {
-                cfreq[LB0 + PW * i] -= angle;
-                cfreq[UB1 - PW * i] -= angle;
+            sm.angle = angle;
+        }
+        __syncthreads();
+        if (t < 2 * MAXREF) {
+            const int i = t < MAXREF ? t : t - MAXREF;
+            if (i < nref) cfreq[ref_bin(t)] = sm.cfq[t] - sm.angle;
+        }
+        const int bc = st.bc;
+        int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
+        const int rows = ppb * (PW - 1);
+        float e_sb[2] = { 0.f, 0.f };
+        // one sideband at a time: stage its data carriers as [carrier][symbol], equalise (adjust_data,
+        // sync.c:263-282), squared error to the nearest QPSK point (sync.c:465-488), soft demap (sync.c:509-536)
+        for (int sb = 0; sb < 2; sb++) {
+            for (int idx = t; idx < rows * BLK; idx += FRONT_THREADS) {
+                const int n = idx / rows, r = idx - n * rows;
+                const int i = r / (PW - 1), k = r - i * (PW - 1) + 1;
+                const int ci = sb == 0 ? PW * i + k : (NBINS - 1 - PW) - PW * i + k;
+                sm.eq[r][n] = bins[(size_t)n * NBINS + ci];
             }
+            __syncthreads();
+            for (int idx = t; idx < rows * BLK; idx += FRONT_THREADS) {
+                const int r = idx >> 5, n = idx & (BLK - 1);
+                const int i = r / (PW - 1), k = r - i * (PW - 1) + 1;
+                int slot_lo, slot_hi;
+                if (sb == 0) { slot_lo = i; slot_hi = i + 1; }
+                else { slot_lo = MAXREF + i + 1; slot_hi = MAXREF + i; }
+                const float m0 = sm.smag[slot_lo], m19 = sm.smag[slot_hi];
+                const float2 up = sm.eph[slot_hi][n], lp = sm.eph[slot_lo][n];
+                const float fa = (float)k * m19, fb = (float)(PW - k) * m0;
+                const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
+                const float rden = 19.0f / (c * c + dd * dd);
+                // (19 + 19j) / (c + j dd)
+                const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
+                const float2 v = cmulf(sm.eq[r][n], C);
+                sm.eq[r][n] = v;
+                const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
+                sm.eerr[r][n] = dx * dx + dy * dy;
+            }
+            __syncthreads();
+            // error sums in a fixed order: carriers of a partition, partitions of a symbol, symbols
+            for (int item = t; item < ppb * BLK; item += FRONT_THREADS) {
+                const int n = item & (BLK - 1), i = item >> 5;
+                float e = 0;
+                for (int k = 0; k < PW - 1; k++) e += sm.eerr[i * (PW - 1) + k][n];
+                sm.err_part[i][n] = e;
+            }
+            __syncthreads();
+            if (t < BLK) {
+                float e = 0;
+                for (int i = 0; i < ppb; i++) e += sm.err_part[i][t];
+                sm.part_sum[t] = e;
+            }
+            __syncthreads();
+            if (t == 0) {
+                float e = 0;
+                for (int n = 0; n < BLK; n++) e += sm.part_sum[n];
+                e_sb[sb] = e;
+                const float mer = 2.0f * BLK * (float)(ppb * 18) / e;
+                sm.mult[sb] = fmaxf(fminf(mer * 10, 127.0f), 1.0f);
+            }
+            __syncthreads();
+            // soft demap of the 10 primary-main partitions of this sideband into the interleaver matrix,
+            // four soft bits (two carriers) per thread
+            {
+                const float mult = sm.mult[sb];
+                for (int item = t; item < BLK * 10 * 9; item += FRONT_THREADS) {
+                    const int n = item / 90, rem = item - n * 90;
+                    const int part = rem / 9, c4 = rem - part * 9;
+                    // sideband partition `part` in demap order: lower = partition index, upper = reversed storage order
+                    const int r = (sb == 0 ? part : 9 - part) * (PW - 1) + 2 * c4;
+                    const float2 a = sm.eq[r][n], b = sm.eq[r + 1][n];
+                    const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
+                                       ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
+                    *reinterpret_cast<uint32_t *>(pm + n * 720 + (sb * 10 + part) * 36 + 4 * c4) = w;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // modulation error: combine per symbol (over partitions), then over symbols — a fixed order
-        if (t < BLK) {
-            float e_lb = 0, e_ub = 0;
-            for (int i = 0; i < ppb; i++) { e_lb += sm.err_lb[i][t]; e_ub += sm.err_ub[i][t]; }
-            sm.part_lb[t] = e_lb;
-            sm.part_ub[t] = e_ub;
-        }
-        __syncthreads();
         if (t == 0) {
-            float e_lb = 0, e_ub = 0;
-            for (int n = 0; n < BLK; n++) { e_lb += sm.part_lb[n]; e_ub += sm.part_ub[n]; }
-            st.err_lb += e_lb;
-            st.err_ub += e_ub;
+            st.err_lb += e_sb[0];
+            st.err_ub += e_sb[1];
             if (++st.mer_cnt == 16) {
                 const float signal = (float)(2 * BLK * (ppb * 18) * st.mer_cnt);
                 uint8_t *w = log_reserve(p, d, s, REC_MER, 8);
@@ -751,29 +810,10 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 st.err_lb = 0;
                 st.err_ub = 0;
             }
-            const float mer_lb = 2.0f * BLK * (float)(ppb * 18) / e_lb;
-            const float mer_ub = 2.0f * BLK * (float)(ppb * 18) / e_ub;
-            sm.mult_lb = fmaxf(fminf(mer_lb * 10, 127.0f), 1.0f);
-            sm.mult_ub = fmaxf(fminf(mer_ub * 10, 127.0f), 1.0f);
         }
-        __syncthreads();
-        // soft demap of the primary-main partitions (sync.c:509-536) into the interleaver matrix
-        const int bc = st.bc;
-        int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
-        {
-            const float mlb = sm.mult_lb, mub = sm.mult_ub;
-            for (int o = t; o < PM_BLOCK; o += FRONT_THREADS) {
-                const int n = o / 720, col = o - n * 720;
-                const int part = col / 36, c = col - part * 36;
-                const int j = 1 + (c >> 1);
-                const int b = part < 10 ? LB0 + PW * part + j : (UB1 - 10 * PW) + PW * (part - 10) + j;
-                const float2 v = bins[(size_t)n * NBINS + compact_of_bin(b)];
-                pm[o] = soft_demap((c & 1) ? v.y : v.x, part < 10 ? mlb : mub);
-            }
-        }
-        __syncthreads();
         if (d.emit_soft) {
             __shared__ uint8_t *sh_w;
+            __syncthreads();
             if (t == 0) {
                 sh_w = log_reserve(p, d, s, REC_SOFT_PM, 4 + PM_BLOCK);
                 if (sh_w) *reinterpret_cast<uint32_t *>(sh_w) = (uint32_t)bc;
@@ -783,13 +823,14 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 for (int o = t; o < PM_BLOCK; o += FRONT_THREADS) sh_w[4 + o] = (uint8_t)pm[o];
             __syncthreads();
         }
-        // PIDS (decode.c:463-471): decoded by the stream's first task of the next round; the record slot is
-        // reserved here to keep the stream's record order
+        // PIDS (decode.c:463-471): the frames of a pass are decoded together when k_stream exits; the record
+        // slot is reserved here to keep the stream's record order
         if (t == 0) {
             uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
-            st.pids_rec = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
-            st.pids_bc = bc;
-            st.pids_pending = 1;
+            const int e = st.pids_pending;
+            st.pids_rec[e] = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+            st.pids_bc[e] = bc;
+            st.pids_pending = e + 1;
             // P1 bookkeeping (decode.c:383-390)
             if (bc == 0) st.started_pm = 1;
             if (st.started_pm && bc == 15) st.p1_ready = 1;
@@ -818,11 +859,21 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
     for (int i = t; i < FFT_TW; i += FRONT_THREADS) sm.tw[i] = __ldg(&p.twid[i]);
     __syncthreads();
 
+    if (max_blocks > 16) max_blocks = 16;             // the PIDS queue (and its interleaver matrix rows) hold 16 blocks
     for (int nb = 0; nb < max_blocks; nb++) {
         // a completed interleaver matrix is decoded (and its header checked) before the next block
         if (st.p1_ready) break;
-        if (st.pids_pending) front_pids(p, d, s, sm.u.pids, t);
+        long long c0 = clock64();
+        auto lap = [&](int ph) {
+            if (t == 0) {
+                const long long c1 = clock64();
+                st.ph_cyc[ph] += (unsigned long long)(c1 - c0);
+                st.ph_n[ph]++;
+                c0 = c1;
+            }
+        };
         if (!front_prep(p, d, s, sm.u.prep, sm.nco, t)) break;
+        lap(st.blk_state_in == ST_FINE ? 2 : 1);
         const long long start = st.start;
         const int samperr = st.blk_samperr;
         const float theta = st.theta;
@@ -831,8 +882,19 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
         for (int pass = 0; pass < BLK / TEAMS; pass++)
             front_demod(p, d, s, pass * TEAMS + team, sm.u.demod, sm.nco, sm.tw, team, tl, start, samperr, theta, phase0);
         __syncthreads();
+        lap(3);
         front_sync(p, d, s, sm.u.sync, t);
         __syncthreads();
+        lap(st.blk_state_in == ST_FINE ? 4 : 5);
+    }
+    __syncthreads();
+    if (st.pids_pending) {
+        const long long c0 = clock64();
+        front_pids_flush(p, d, s, sm.u.pidsq, t);
+        if (t == 0) {
+            st.ph_cyc[0] += (unsigned long long)(clock64() - c0);
+            st.ph_n[0]++;
+        }
     }
 }
 

@@ -30,7 +30,8 @@ class _Config(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("blocks", ctypes.c_uint64), ("samples", ctypes.c_uint64),
-                ("p1_frames", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64)]
+                ("p1_frames", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
+                ("p1_fallbacks", ctypes.c_uint64)]
 
 
 def lib_path() -> str:
@@ -59,6 +60,7 @@ def load_library():
     L.nrsc5b_rewind.argtypes = [vp]
     L.nrsc5b_set_profiling.argtypes = [vp, ci]
     L.nrsc5b_get_kernel_times.argtypes = [vp, vp, vp]
+    L.nrsc5b_get_phase_cycles.argtypes = [vp, vp, vp]
     L.nrsc5b_set_cuda_stream.argtypes = [vp, vp]
     L.nrsc5b_push_cu8.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_push_cu8_device.argtypes = [vp, ci, vp, sz]
@@ -73,6 +75,7 @@ def load_library():
     L.nrsc5b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.nrsc5b_halfband_fm.argtypes = [ci, vp, sz, vp]
     L.nrsc5b_viterbi_k7.argtypes = [ci, vp, vp, ci, ci]
+    L.nrsc5b_viterbi_k7_ex.argtypes = [ci, vp, vp, ci, ci, ctypes.POINTER(ci)]
     L.nrsc5b_rs_decode.argtypes = [ci, vp, vp, ci]
     L.nrsc5b_fft2048.argtypes = [ci, vp, vp, ci]
     _lib = L
@@ -173,8 +176,16 @@ class Engine:
         ms = (ctypes.c_double * 4)()
         n = (ctypes.c_ulonglong * 4)()
         _check(self._L.nrsc5b_get_kernel_times(self._h, ms, n), "nrsc5b_get_kernel_times")
-        # slot 1 = the fused persistent front-end kernel (k_front), slot 3 = the P1 decode kernel group
+        # slot 1 = the stream-resident front-end kernel (k_stream), slot 3 = the P1 decode kernel group
         return {"front": {"ms": ms[1], "launches": int(n[1])}, "p1": {"ms": ms[3], "launches": int(n[3])}}
+
+    def phase_cycles(self):
+        """SM cycles per phase of k_stream summed over streams: {name: (cycles, count)}."""
+        c = (ctypes.c_ulonglong * 6)()
+        n = (ctypes.c_ulonglong * 6)()
+        _check(self._L.nrsc5b_get_phase_cycles(self._h, c, n), "nrsc5b_get_phase_cycles")
+        names = ["pids_flush", "prep_acquire", "prep_fine", "demod", "sync_fine", "sync_acquire"]
+        return {k: (int(c[i]), int(n[i])) for i, k in enumerate(names)}
 
     def push_cu8(self, stream: int, samples):
         """samples: uint8 numpy array / bytes (host) — length counts uint8 values, multiple of 4."""
@@ -229,12 +240,17 @@ def halfband_fm(cu8: np.ndarray, device: int = 0) -> np.ndarray:
     return out
 
 
-def viterbi_k7(soft: np.ndarray, length: int, device: int = 0) -> np.ndarray:
+def viterbi_k7(soft: np.ndarray, length: int, device: int = 0, want_fallbacks: bool = False):
+    """Batch of tail-biting K=7 decodes.  With want_fallbacks also returns how many frames the fast
+    register-resident path handed to the exact fallback kernels."""
     s = np.ascontiguousarray(soft, dtype=np.int8)
     nframes = s.size // (3 * length)
     out = np.empty(nframes * length, dtype=np.uint8)
-    _check(load_library().nrsc5b_viterbi_k7(device, s.ctypes.data, out.ctypes.data, length, nframes), "nrsc5b_viterbi_k7")
-    return out.reshape(nframes, length)
+    fb = ctypes.c_int(0)
+    _check(load_library().nrsc5b_viterbi_k7_ex(device, s.ctypes.data, out.ctypes.data, length, nframes, ctypes.byref(fb)),
+           "nrsc5b_viterbi_k7_ex")
+    out = out.reshape(nframes, length)
+    return (out, fb.value) if want_fallbacks else out
 
 
 def rs_decode(blocks: np.ndarray, device: int = 0):
