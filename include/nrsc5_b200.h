@@ -116,6 +116,9 @@ int nrsc5b_process_available(nrsc5b_engine_t *e);
 /* Wait for the GPU and copy the records of `stream` produced since the last drain.
  * Returns the number of bytes written (>= 0) or a negative error; *needed gets the full size. */
 long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_t cap, size_t *needed);
+/* nrsc5b_drain for every stream in one call: stream s's records land at out + s*out_stride, sizes[s] bytes.
+ * Returns NRSC5B_EFULL (and drains nothing) if a stream's records exceed out_stride. */
+int nrsc5b_drain_all(nrsc5b_engine_t *e, uint8_t *out, size_t out_stride, size_t *sizes);
 /* Wait for the GPU without draining. */
 int nrsc5b_synchronize(nrsc5b_engine_t *e);
 
@@ -136,9 +139,14 @@ int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on);
 int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long *n4);
 
 /* SM cycles spent by the stream-resident front-end kernel per phase, summed over streams since the last reset /
- * rewind: cyc6/n6 = {pids flush, prep with coarse acquisition, prep in fine sync, demod (32 symbols),
- * sync+demap of a block that started in fine sync, sync of any other block (vote / CFO search)}. */
-int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc6, unsigned long long *n6);
+ * rewind: cyc12/n12 = {pids flush, prep with coarse acquisition, prep in fine sync, demod (32 symbols),
+ * sync+demap of a block that started in fine sync, sync of any other block (vote / CFO search)} followed
+ * by six sub-phases of the fine-sync slot {reference gather, Costas loops, tables + feedback, staging,
+ * equalise + error sums, demap + bookkeeping}. */
+int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12, unsigned long long *n12);
+
+/* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops); 0 = default. */
+int nrsc5b_debug_set(int flags);
 
 /* ---- single-stage entry points (kernel-level parity tests, host buffers) ---- */
 /* cu8 -> Q15 -> halfband /2 from zero history: out[2*npairs] int16 (reference src/firdecim_q15.c:137-165) */

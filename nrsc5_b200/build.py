@@ -15,11 +15,10 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = (["-DNB_DEBUG"] if os.environ.get("NB_DEBUG") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 # (source, extra flags).  engine.cu keeps the reference's float operation order in the acquisition /
-# sync arithmetic, so FMA contraction is off there (the FFT uses explicit FMAs), and its plain global
-# loads bypass L1 because the persistent front-end kernel passes data between CTAs through L2.
+# sync arithmetic, so FMA contraction is off there (the FFT uses explicit FMAs).
 UNITS = [
     ("frontend.cu", []),
-    ("engine.cu", ["-fmad=false", "-Xptxas", "-dlcm=cg"]),
+    ("engine.cu", ["-fmad=false"]),
 ]
 
 

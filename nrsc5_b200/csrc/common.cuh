@@ -86,6 +86,9 @@ struct StreamState {
     // demod, sync of a block that started in FINE, sync of any other block (vote / CFO search)
     unsigned long long ph_cyc[6];
     unsigned long long ph_n[6];
+    // sub-phases of a FINE block's sync: reference gather, Costas loops, amplitude/phase tables + feedback,
+    // staging, equalise + error sums, demap + bookkeeping
+    unsigned long long sy_cyc[6];
     // history of the coarse band-pass FIR: the last 31 samples it was fed
     short bp_hist[31][2];
 };

@@ -772,16 +772,25 @@ extern "C" int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on)
     return NRSC5B_OK;
 }
 
+extern "C" int nrsc5b_debug_set(int flags)
+{
+    CK(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(flags)));
+    return NRSC5B_OK;
+}
+
 extern "C" int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc5, unsigned long long *n5)
 {
-    // six slots (see StreamState::ph_cyc)
+    // twelve slots (see StreamState::ph_cyc, sy_cyc)
     if (!e || !cyc5 || !n5) return NRSC5B_EINVAL;
     CK(cudaStreamSynchronize(e->stream));
     const int S = e->dims.nstreams;
     CK(cudaMemcpy(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 6; i++) { cyc5[i] = 0; n5[i] = 0; }
-    for (int s = 0; s < S; s++)
+    for (int i = 0; i < 12; i++) { cyc5[i] = 0; n5[i] = 0; }
+    for (int s = 0; s < S; s++) {
         for (int i = 0; i < 6; i++) { cyc5[i] += e->h_state[s].ph_cyc[i]; n5[i] += e->h_state[s].ph_n[i]; }
+        // slots 6..11: sub-phases of the FINE sync (same call count as slot 4, approximately)
+        for (int i = 0; i < 6; i++) { cyc5[6 + i] += e->h_state[s].sy_cyc[i]; n5[6 + i] += e->h_state[s].ph_n[4]; }
+    }
     return NRSC5B_OK;
 }
 
@@ -862,6 +871,34 @@ extern "C" long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_
     e->drained[stream] = 0;
     if (st.log_overflow) fprintf(stderr, "nrsc5_b200: stream %d output log overflowed (raise log_capacity)\n", stream);
     return (long)avail;
+}
+
+/* All streams at once: records of stream s go to out + s*out_stride, their byte count to sizes[s].  One
+ * device->host copy of the stream states, then one asynchronous copy per stream and a single wait. */
+extern "C" int nrsc5b_drain_all(nrsc5b_engine_t *e, uint8_t *out, size_t out_stride, size_t *sizes)
+{
+    if (!e || !out || !sizes) return NRSC5B_EINVAL;
+    const int S = e->dims.nstreams;
+    CK(cudaMemcpyAsync(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = NRSC5B_OK;
+    for (int s = 0; s < S; s++) {
+        const size_t avail = e->h_state[s].log_len - e->drained[s];
+        sizes[s] = avail;
+        if (avail > out_stride) { rc = NRSC5B_EFULL; sizes[s] = 0; continue; }
+        if (avail)
+            CK(cudaMemcpyAsync(out + (size_t)s * out_stride, e->dp.log + (size_t)s * e->dims.log_cap + e->drained[s], avail,
+                               cudaMemcpyDeviceToHost, e->stream));
+        if (e->h_state[s].log_overflow) fprintf(stderr, "nrsc5_b200: stream %d output log overflowed (raise log_capacity)\n", s);
+    }
+    if (rc == NRSC5B_OK) {
+        // rewind every log (strided 4-byte writes of zero into the states)
+        CK(cudaMemset2DAsync(reinterpret_cast<uint8_t *>(e->dp.st) + offsetof(StreamState, log_len), sizeof(StreamState), 0,
+                             sizeof(unsigned), S, e->stream));
+        for (int s = 0; s < S; s++) e->drained[s] = 0;
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return rc;
 }
 
 extern "C" int nrsc5b_set_sync_state(nrsc5b_engine_t *e, int stream, int state)

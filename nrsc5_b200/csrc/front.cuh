@@ -27,6 +27,7 @@ constexpr int MAXREF = 15;                         // reference subcarriers per 
 constexpr int IN_BYTES = 4 * NSYM + 28 + 16 + 16;  // staged cu8 bytes per symbol (+ alignment slack) = 8700
 constexpr int IN_STRIDE = 8704;
 
+__device__ int g_dbg;                              // experiment switches (nrsc5b_debug_set), 0 in production
 __device__ unsigned long long g_progress;          // bumped by every stream that processed a block
 
 __constant__ int c_compat_mode[64];
@@ -91,20 +92,28 @@ struct PidsSmem {
     int8_t vit[PIDS_LEN * 3];
     uint2 dec[PIDS_LEN + 64];
 };
+constexpr int ZS = 32;                              // row stride of the per-reference arrays (>= 2 * MAXREF)
 constexpr int EQ_LD = BLK + 1;                      // padded row of the equalisation buffer (bank-conflict free)
-constexpr int EQ_ROWS = MAXPART * (PW - 1);         // data carriers of one sideband
+constexpr int EQ_MAXPART = 12;                      // partitions per sideband the equaliser stages (MP1..MP3, MP11 excluded)
+constexpr int EQ_ROWS = 2 * EQ_MAXPART * (PW - 1);  // data carriers of both sidebands
 struct SyncSmem {
-    float2 zref[2 * MAXREF][BLK];                  // reference carriers after their Costas loop
-    float phs[2 * MAXREF][BLK];                    // Costas phase per reference and symbol
+    // reference carriers after their Costas loop and the loop's phase, [symbol][reference slot]: the threads
+    // of a warp each walk one reference, symbol by symbol, so the slot index must be the contiguous one
+    float2 zref[BLK][ZS];
+    float phs[BLK][ZS];
     float2 eph[2 * MAXREF][BLK];                   // exp(j*phs)
     float smag[2 * MAXREF];
     float cfq[2 * MAXREF];                         // Costas frequency of every reference after the block
-    float2 eq[EQ_ROWS][EQ_LD];                     // one sideband's data carriers [partition*18 + k-1][symbol]
-    float eerr[EQ_ROWS][EQ_LD];                    // their squared distance to the nearest QPSK point
-    float err_part[MAXPART][BLK];                  // per (partition, symbol) error sums
-    float part_sum[BLK];
-    float2 rows[22][BLK];                          // CFO search: working rows
-    float tmp_phs[22][BLK];
+    union {
+        float2 eq[EQ_ROWS][EQ_LD];                 // data carriers [sideband*rows + partition*18 + k-1][symbol]
+        struct {                                   // CFO search (never at the same time as the equaliser)
+            float2 rows[BLK][ZS];                  // working rows, [symbol][lane]
+            float tmp_phs[BLK][ZS];
+        } srch;
+    };
+    float wred[FRONT_THREADS / 32][2];             // per-warp error sums (lower, upper sideband)
+    float fb_w[2][MAXREF], fb_xy[2][MAXREF + 1];   // feedback terms (phase differences, bin * frequency)
+    float4 rowc[EQ_ROWS];                          // per carrier row: k*|upper ref|, (19-k)*|lower ref|, slots
     int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
     int offs[32];
     float mult[2];
@@ -458,33 +467,42 @@ __device__ __forceinline__ int ref_bin(int slot)                // slot < MAXREF
 }
 
 // adjust_ref (sync.c:90-130) on one row of 32 symbols
-__device__ void costas_row(float2 *z, float *phs, float &cfreq, float &cphase, int cfo, float alpha, float beta)
+__device__ __forceinline__ void costas_row(float2 *z, float *phs, int zs, float &cfreq, float &cphase, int cfo, float alpha, float beta)
 {
-    const signed char pat[BLK] = { -1, 1, -1, -1, -1, 1, 1, 0, 1, -1, 0, 0, 0, -1, -1, 0,
-                                   0, 0, 0, 0, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1 };
+    // sync pattern -1, 1, -1, -1, -1, 1, 1, 0, 1, -1, 0, 0, 0, -1, -1, 0, 0, 0, 0, 0, -1, 1, -1, 0 x8, -1 as bit masks
+    const unsigned pat_pos = (1u << 1) | (1u << 5) | (1u << 6) | (1u << 8) | (1u << 21);
+    const unsigned pat_neg = (1u << 0) | (1u << 2) | (1u << 3) | (1u << 4) | (1u << 9) | (1u << 13) | (1u << 14) | (1u << 20) |
+                             (1u << 22) | (1u << 31);
     const float cfo_freq = (float)(2 * M_PI * cfo * NCP / NFFT);
     const float PI_F = 3.14159274101257324f;                  // smallest float above pi: (ph > M_PI) <=> (ph >= PI_F)
+    const float TWO_PI_HI = 6.28318548202514648f, TWO_PI_LO = -1.74845553e-07f;
     float f = cfreq, ph = cphase;
+    // (kept rolled: one warp runs this alone, straight-line code would be bound by instruction fetch)
+#pragma unroll 1
     for (int n = 0; n < BLK; n++) {
-        const float2 v = z[n];
+        const float2 v = z[n * zs];
         // u = v * exp(-j*ph); the loop error arg(v^2 * exp(-2j*ph)) / 2 equals arg(u^2) / 2
         const float2 u = cmulf(v, cexp_j(-ph));
         const float error = atan2f((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y) * 0.5f;
-        phs[n] = ph;
-        z[n] = u;
+        phs[n * zs] = ph;
+        z[n * zs] = u;
         f += beta * error;
         if (f > 0.5f) f = 0.5f;
         if (f < -0.5f) f = -0.5f;
         ph += (f + cfo_freq) + (alpha * error);
-        if (ph >= PI_F) ph = (float)((double)ph - 2 * M_PI);
-        if (ph <= -PI_F) ph = (float)((double)ph + 2 * M_PI);
+        // (float)((double)ph -+ 2*pi) without double arithmetic on the serial path: 2*pi = HI + LO, the first
+        // step is exact (Sterbenz), the second rounds once
+        if (ph >= PI_F) ph = (ph - TWO_PI_HI) - TWO_PI_LO;
+        if (ph <= -PI_F) ph = (ph + TWO_PI_HI) + TWO_PI_LO;
     }
     float x = 0;
-    for (int n = 0; n < BLK; n++) x += z[n].x * (float)pat[n];
+#pragma unroll 4
+    for (int n = 0; n < BLK; n++) x += z[n * zs].x * (float)((int)((pat_pos >> n) & 1u) - (int)((pat_neg >> n) & 1u));
     if (x < 0) {
+#pragma unroll 4
         for (int n = 0; n < BLK; n++) {
-            phs[n] = (float)((double)phs[n] + M_PI);
-            z[n] = make_float2(z[n].x * -1.0f, z[n].y * -1.0f);
+            phs[n * zs] = (float)((double)phs[n * zs] + M_PI);
+            z[n * zs] = make_float2(z[n * zs].x * -1.0f, z[n * zs].y * -1.0f);
         }
         ph = (float)((double)ph + M_PI);
     }
@@ -502,11 +520,11 @@ __device__ __forceinline__ int needle_bit(int n, unsigned rsid)       // -1 = do
 }
 
 // find_ref_fm (sync.c:188-207): cyclic offset of the sync pattern, also trying the inverted bits
-__device__ int ref_find(const float2 *z, unsigned rsid)
+__device__ int ref_find(const float2 *z, int zs, unsigned rsid)
 {
     unsigned raw = 0;
     for (int n = 0; n < BLK; n++)
-        if (!(z[n].x <= 0)) raw |= 1u << n;
+        if (!(z[n * zs].x <= 0)) raw |= 1u << n;
     for (int pass = 0; pass < 2; pass++) {
         for (int n = 0; n < BLK; n++) {
             int i;
@@ -553,40 +571,66 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
 
     int ppb = partitions_per_band(st.psmi);
     int nref = ppb + 1;
+    long long sy0 = clock64();
+    const bool sy_on = st.state == ST_FINE;
+    auto sylap = [&](int k) {
+        if (t == 0 && sy_on) {
+            const long long c1 = clock64();
+            st.sy_cyc[k] += (unsigned long long)(c1 - sy0);
+            sy0 = c1;
+        }
+    };
+    // data carriers of both sidebands -> shared memory as [carrier][symbol] (coalesced reads along the carriers)
+    auto stage_eq = [&](int first, int stride) {
+        const int rows = min(ppb, EQ_MAXPART) * (PW - 1), rows2 = 2 * rows;
+#pragma unroll 4
+        for (int idx = first; idx < rows2 * BLK; idx += stride) {
+            const int n = idx / rows2, r = idx - n * rows2;
+            const int sb = r >= rows, rr = sb ? r - rows : r;
+            const int i = rr / (PW - 1), k = rr - i * (PW - 1) + 1;
+            const int ci = sb == 0 ? PW * i + k : (NBINS - 1 - PW) - PW * i + k;
+            sm.eq[r][n] = bins[(size_t)n * NBINS + ci];
+        }
+    };
+    const bool pre_staged = st.state == ST_FINE && !(g_dbg & 1);   // partitions known: stage while warp 0 runs the Costas loops
     // reference carriers -> shared memory, then one Costas loop per carrier (sync.c:359-363)
-    for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
-        const int slot = i >> 5, n = i & 31;
+    for (int i = t; i < ZS * BLK; i += FRONT_THREADS) {
+        const int slot = i & (ZS - 1), n = i / ZS;
         const int ii = slot < MAXREF ? slot : slot - MAXREF;
-        if (ii < nref) sm.zref[slot][n] = bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))];
+        if (slot < 2 * MAXREF && ii < nref) sm.zref[n][slot] = bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))];
     }
     __syncthreads();
+    sylap(0);
     if (t < 2 * MAXREF) {
         const int i = t < MAXREF ? t : t - MAXREF;
         if (i < nref) {
             const int b = ref_bin(t);
             float f = cfreq[b], ph = cphase[b];
-            costas_row(sm.zref[t], sm.phs[t], f, ph, 0, alpha, beta);
+            costas_row(&sm.zref[0][t], &sm.phs[0][t], ZS, f, ph, 0, alpha, beta);
             cfreq[b] = f;
             cphase[b] = ph;
             sm.cfq[t] = f;
         }
+    } else if (t >= 32 && pre_staged) {
+        stage_eq(t - 32, FRONT_THREADS - 32);
     }
     __syncthreads();
+    sylap(1);
 
     if (st.state == ST_COARSE) {                 // sync.c:366-421
         if (t < 2 * MAXREF) {
             const int i = t < MAXREF ? t : t - MAXREF;
             sm.ref_ok[t] = 0;
             if (i < nref) {
-                const float2 *z = sm.zref[t];
+                const float2 *z = &sm.zref[0][t];
                 const unsigned rsid = (unsigned)(30 - i) & 3;
                 bool ok = true;
                 unsigned raw = 0;
                 for (int n = 0; n < BLK; n++) {
                     const int nbit = needle_bit(n, rsid);
-                    const int pos = z[n].x > 0 ? 1 : 0;
+                    const int pos = z[n * ZS].x > 0 ? 1 : 0;
                     if (nbit >= 0 && nbit != pos) ok = false;
-                    if (!(z[n].x <= 0)) raw |= 1u << n;
+                    if (!(z[n * ZS].x <= 0)) raw |= 1u << n;
                 }
                 const unsigned dd = raw ^ (raw << 1);        // DBPSK decode, prev = 0 (sync.c:138-148)
                 auto bit = [&](int n) { return (dd >> n) & 1u; };
@@ -632,7 +676,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
                 const int slot = i >> 5, n = i & 31;
                 const int ii = slot < MAXREF ? slot : slot - MAXREF;
-                if (ii < nref) bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))] = sm.zref[slot][n];
+                if (ii < nref) bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))] = sm.zref[n][slot];
             }
             __syncthreads();
             if (t < 32) {
@@ -643,14 +687,14 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                         const int i = lane >> 1, upper = lane & 1;
                         const int b = upper ? cfo + UB1 - i * PW : cfo + LB0 + i * PW;
                         const int ci = compact_of_bin(b);
-                        float2 *row = sm.rows[lane];
+                        float2 *row = &sm.srch.rows[0][lane];
                         for (int n = 0; n < BLK; n++)
-                            row[n] = ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f);
-                        costas_row(row, sm.tmp_phs[lane], cfreq[b], cphase[b], cfo, alpha, beta);
-                        off = ref_find(row, (unsigned)(30 - i) & 3);
+                            row[n * ZS] = ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f);
+                        costas_row(row, &sm.srch.tmp_phs[0][lane], ZS, cfreq[b], cphase[b], cfo, alpha, beta);
+                        off = ref_find(row, ZS, (unsigned)(30 - i) & 3);
                         if (ci >= 0)
                             for (int n = 0; n < BLK; n++)    // reset_ref (sync.c:132-136)
-                                bins[(size_t)n * NBINS + ci] = cmulf(row[n], cexp_j(sm.tmp_phs[lane][n]));
+                                bins[(size_t)n * NBINS + ci] = cmulf(row[n * ZS], cexp_j(sm.srch.tmp_phs[n][lane]));
                     }
                     sm.offs[lane] = off;
                     __syncwarp();
@@ -687,37 +731,50 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             const int i = t < MAXREF ? t : t - MAXREF;
             if (i < nref) {
                 float sum = 0;
-                for (int n = 0; n < BLK; n++) sum += fabsf(sm.zref[t][n].x);
+                for (int n = 0; n < BLK; n++) sum += fabsf(sm.zref[n][t].x);
                 sm.smag[t] = sum / BLK;
             }
         }
         for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
             const int slot = i >> 5, n = i & 31;
             const int ii = slot < MAXREF ? slot : slot - MAXREF;
-            if (ii < nref) sm.eph[slot][n] = cexp_j(sm.phs[slot][n]);
+            if (ii < nref) sm.eph[slot][n] = cexp_j(sm.phs[n][slot]);
         }
-        // timing / phase feedback (sync.c:426-463), one thread of the last warp while the others equalise
-        if (t == FRONT_THREADS - 1) {
-            float samperr = 0, angle = 0, sum_xy = 0, sum_x2 = 0;
-            for (int i = 0; i < ppb; i++) {
-                samperr += half_pi_wrap(sm.phs[i][0], sm.phs[i + 1][0]);
-                samperr += half_pi_wrap(sm.phs[MAXREF + i + 1][0], sm.phs[MAXREF + i][0]);
+        // timing / phase feedback (sync.c:426-463) on the last warp: the terms are computed in parallel, then
+        // summed by one lane in the reference's order (same values, same rounding as the sequential loop)
+        if (t >= FRONT_THREADS - 32) {
+            const int lane = t & 31;
+            if (lane < ppb) {
+                sm.fb_w[0][lane] = half_pi_wrap(sm.phs[0][lane], sm.phs[0][lane + 1]);
+                sm.fb_w[1][lane] = half_pi_wrap(sm.phs[0][MAXREF + lane + 1], sm.phs[0][MAXREF + lane]);
             }
-            samperr = (float)((double)(samperr / (float)(ppb * 2) * (float)NFFT / (float)PW) / (2 * M_PI));
-            for (int i = 0; i <= ppb; i++) {
-                float x, y;
-                x = (float)(LB0 + PW * i - NFFT / 2);
-                y = sm.cfq[i];
-                angle += y; sum_xy += x * y; sum_x2 += x * x;
-                x = (float)(UB1 - PW * i - NFFT / 2);
-                y = sm.cfq[MAXREF + i];
-                angle += y; sum_xy += x * y; sum_x2 += x * x;
+            if (lane <= ppb) {
+                sm.fb_xy[0][lane] = (float)(LB0 + PW * lane - NFFT / 2) * sm.cfq[lane];
+                sm.fb_xy[1][lane] = (float)(UB1 - PW * lane - NFFT / 2) * sm.cfq[MAXREF + lane];
             }
-            samperr = (float)((double)samperr - (double)((sum_xy / sum_x2) * (float)NFFT) / (2 * M_PI) * BLK);
-            st.samperr = (int)roundf(samperr);
-            angle /= (float)((ppb + 1) * 2);
-            st.angle = angle;
-            sm.angle = angle;
+            __syncwarp();
+            if (lane == 31) {
+                float samperr = 0, angle = 0, sum_xy = 0, sum_x2 = 0;
+                for (int i = 0; i < ppb; i++) {
+                    samperr += sm.fb_w[0][i];
+                    samperr += sm.fb_w[1][i];
+                }
+                // x / (2 pi) as a multiplication by the double reciprocal: the result is rounded to float anyway
+                const double inv_2pi = 1.0 / (2 * M_PI);
+                samperr = (float)((double)(samperr / (float)(ppb * 2) * (float)NFFT / (float)PW) * inv_2pi);
+                for (int i = 0; i <= ppb; i++) {
+                    float x;
+                    x = (float)(LB0 + PW * i - NFFT / 2);
+                    angle += sm.cfq[i]; sum_xy += sm.fb_xy[0][i]; sum_x2 += x * x;
+                    x = (float)(UB1 - PW * i - NFFT / 2);
+                    angle += sm.cfq[MAXREF + i]; sum_xy += sm.fb_xy[1][i]; sum_x2 += x * x;
+                }
+                samperr = (float)((double)samperr - (double)((sum_xy / sum_x2) * (float)NFFT) * inv_2pi * BLK);
+                st.samperr = (int)roundf(samperr);
+                angle /= (float)((ppb + 1) * 2);
+                st.angle = angle;
+                sm.angle = angle;
+            }
         }
         __syncthreads();
         if (t < 2 * MAXREF) {
@@ -726,76 +783,81 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         }
         const int bc = st.bc;
         int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
-        const int rows = ppb * (PW - 1);
-        float e_sb[2] = { 0.f, 0.f };
-        // one sideband at a time: stage its data carriers as [carrier][symbol], equalise (adjust_data,
-        // sync.c:263-282), squared error to the nearest QPSK point (sync.c:465-488), soft demap (sync.c:509-536)
-        for (int sb = 0; sb < 2; sb++) {
-            for (int idx = t; idx < rows * BLK; idx += FRONT_THREADS) {
-                const int n = idx / rows, r = idx - n * rows;
-                const int i = r / (PW - 1), k = r - i * (PW - 1) + 1;
-                const int ci = sb == 0 ? PW * i + k : (NBINS - 1 - PW) - PW * i + k;
-                sm.eq[r][n] = bins[(size_t)n * NBINS + ci];
-            }
-            __syncthreads();
-            for (int idx = t; idx < rows * BLK; idx += FRONT_THREADS) {
-                const int r = idx >> 5, n = idx & (BLK - 1);
-                const int i = r / (PW - 1), k = r - i * (PW - 1) + 1;
-                int slot_lo, slot_hi;
-                if (sb == 0) { slot_lo = i; slot_hi = i + 1; }
-                else { slot_lo = MAXREF + i + 1; slot_hi = MAXREF + i; }
-                const float m0 = sm.smag[slot_lo], m19 = sm.smag[slot_hi];
-                const float2 up = sm.eph[slot_hi][n], lp = sm.eph[slot_lo][n];
-                const float fa = (float)k * m19, fb = (float)(PW - k) * m0;
-                const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
-                const float rden = 19.0f / (c * c + dd * dd);
-                // (19 + 19j) / (c + j dd)
-                const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
-                const float2 v = cmulf(sm.eq[r][n], C);
-                sm.eq[r][n] = v;
-                const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
-                sm.eerr[r][n] = dx * dx + dy * dy;
-            }
-            __syncthreads();
-            // error sums in a fixed order: carriers of a partition, partitions of a symbol, symbols
-            for (int item = t; item < ppb * BLK; item += FRONT_THREADS) {
-                const int n = item & (BLK - 1), i = item >> 5;
-                float e = 0;
-                for (int k = 0; k < PW - 1; k++) e += sm.eerr[i * (PW - 1) + k][n];
-                sm.err_part[i][n] = e;
-            }
-            __syncthreads();
-            if (t < BLK) {
-                float e = 0;
-                for (int i = 0; i < ppb; i++) e += sm.err_part[i][t];
-                sm.part_sum[t] = e;
-            }
-            __syncthreads();
-            if (t == 0) {
-                float e = 0;
-                for (int n = 0; n < BLK; n++) e += sm.part_sum[n];
-                e_sb[sb] = e;
-                const float mer = 2.0f * BLK * (float)(ppb * 18) / e;
-                sm.mult[sb] = fmaxf(fminf(mer * 10, 127.0f), 1.0f);
-            }
-            __syncthreads();
-            // soft demap of the 10 primary-main partitions of this sideband into the interleaver matrix,
-            // four soft bits (two carriers) per thread
-            {
-                const float mult = sm.mult[sb];
-                for (int item = t; item < BLK * 10 * 9; item += FRONT_THREADS) {
-                    const int n = item / 90, rem = item - n * 90;
-                    const int part = rem / 9, c4 = rem - part * 9;
-                    // sideband partition `part` in demap order: lower = partition index, upper = reversed storage order
-                    const int r = (sb == 0 ? part : 9 - part) * (PW - 1) + 2 * c4;
-                    const float2 a = sm.eq[r][n], b = sm.eq[r + 1][n];
-                    const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
-                                       ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
-                    *reinterpret_cast<uint32_t *>(pm + n * 720 + (sb * 10 + part) * 36 + 4 * c4) = w;
-                }
-            }
-            __syncthreads();
+        // (service modes with 14 partitions per sideband are equalised on their outer 12 only: not supported)
+        const int rows = min(ppb, EQ_MAXPART) * (PW - 1), rows2 = 2 * rows;
+        sylap(2);
+        if (!pre_staged) stage_eq(t, FRONT_THREADS);
+        // per carrier row: the two interpolation weights and the reference slots on either side
+        for (int r = t; r < rows2; r += FRONT_THREADS) {
+            const int sb = r >= rows, rr = sb ? r - rows : r;
+            const int i = rr / (PW - 1), k = rr - i * (PW - 1) + 1;
+            int slot_lo, slot_hi;
+            if (sb == 0) { slot_lo = i; slot_hi = i + 1; }
+            else { slot_lo = MAXREF + i + 1; slot_hi = MAXREF + i; }
+            sm.rowc[r] = make_float4((float)k * sm.smag[slot_hi], (float)(PW - k) * sm.smag[slot_lo],
+                                     __int_as_float(slot_hi), __int_as_float(slot_lo));
         }
+        __syncthreads();
+        sylap(3);
+        // equalise (adjust_data, sync.c:263-282) and squared error to the nearest QPSK point (sync.c:465-488)
+        float e_lb = 0.f, e_ub = 0.f;
+        for (int idx = t; idx < rows2 * BLK; idx += FRONT_THREADS) {
+            const int r = idx >> 5, n = idx & (BLK - 1);
+            const float4 rc = sm.rowc[r];
+            const float fa = rc.x, fb = rc.y;
+            const float2 up = sm.eph[__float_as_int(rc.z)][n], lp = sm.eph[__float_as_int(rc.w)][n];
+            const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
+            const float rden = __fdividef(19.0f, c * c + dd * dd);
+            // (19 + 19j) / (c + j dd)
+            const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
+            const float2 v = cmulf(sm.eq[r][n], C);
+            sm.eq[r][n] = v;
+            const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
+            const float e = dx * dx + dy * dy;
+            if (r >= rows) e_ub += e;
+            else e_lb += e;
+        }
+        // modulation error per sideband: a fixed-shape tree (thread, warp shuffle, warp 0)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            e_lb += __shfl_xor_sync(0xffffffffu, e_lb, o);
+            e_ub += __shfl_xor_sync(0xffffffffu, e_ub, o);
+        }
+        if ((t & 31) == 0) { sm.wred[t >> 5][0] = e_lb; sm.wred[t >> 5][1] = e_ub; }
+        __syncthreads();
+        float e_sb[2] = { 0.f, 0.f };
+        if (t < 32) {
+            float a = sm.wred[t][0], b = sm.wred[t][1];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (t == 0) {
+                e_sb[0] = a;
+                e_sb[1] = b;
+                const float mer_lb = 2.0f * BLK * (float)(ppb * 18) / a, mer_ub = 2.0f * BLK * (float)(ppb * 18) / b;
+                sm.mult[0] = fmaxf(fminf(mer_lb * 10, 127.0f), 1.0f);
+                sm.mult[1] = fmaxf(fminf(mer_ub * 10, 127.0f), 1.0f);
+            }
+        }
+        __syncthreads();
+        sylap(4);
+        // soft demap (sync.c:509-536) of the 10 primary-main partitions of each sideband into the interleaver
+        // matrix, four soft bits (two carriers) per thread
+        for (int item = t; item < BLK * 20 * 9; item += FRONT_THREADS) {
+            const int n = item / 180, rem = item - n * 180;
+            const int part = rem / 9, c4 = rem - part * 9;             // part 0..19 in demap order
+            const int sb = part >= 10;
+            // lower sideband: partition index; upper: the reference walks them upwards, storage is downwards
+            const int r = (sb ? rows + (19 - part) * (PW - 1) : part * (PW - 1)) + 2 * c4;
+            const float mult = sm.mult[sb];
+            const float2 a = sm.eq[r][n], b = sm.eq[r + 1][n];
+            const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
+                               ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
+            *reinterpret_cast<uint32_t *>(pm + n * 720 + part * 36 + 4 * c4) = w;
+        }
+        __syncthreads();
         if (t == 0) {
             st.err_lb += e_sb[0];
             st.err_ub += e_sb[1];
@@ -844,6 +906,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         st.start += NACQ - keep;
         st.blocks_done++;
     }
+    sylap(5);
 }
 
 // ---------------------------------------------------------------------------

@@ -71,6 +71,7 @@ def load_library():
     L.nrsc5b_synchronize.argtypes = [vp]
     L.nrsc5b_drain.argtypes = [vp, ci, vp, sz, ctypes.POINTER(sz)]
     L.nrsc5b_drain.restype = ctypes.c_long
+    L.nrsc5b_drain_all.argtypes = [vp, vp, sz, vp]
     L.nrsc5b_set_sync_state.argtypes = [vp, ci, ci]
     L.nrsc5b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.nrsc5b_halfband_fm.argtypes = [ci, vp, sz, vp]
@@ -181,10 +182,12 @@ class Engine:
 
     def phase_cycles(self):
         """SM cycles per phase of k_stream summed over streams: {name: (cycles, count)}."""
-        c = (ctypes.c_ulonglong * 6)()
-        n = (ctypes.c_ulonglong * 6)()
+        c = (ctypes.c_ulonglong * 12)()
+        n = (ctypes.c_ulonglong * 12)()
         _check(self._L.nrsc5b_get_phase_cycles(self._h, c, n), "nrsc5b_get_phase_cycles")
-        names = ["pids_flush", "prep_acquire", "prep_fine", "demod", "sync_fine", "sync_acquire"]
+        names = ["pids_flush", "prep_acquire", "prep_fine", "demod", "sync_fine", "sync_acquire",
+                 "sync_fine.gather", "sync_fine.costas", "sync_fine.tables_feedback", "sync_fine.stage",
+                 "sync_fine.equalise", "sync_fine.demap_tail"]
         return {k: (int(c[i]), int(n[i])) for i, k in enumerate(names)}
 
     def push_cu8(self, stream: int, samples):
@@ -221,6 +224,17 @@ class Engine:
 
     def drain(self, stream: int):
         return parse_records(self.drain_raw(stream))
+
+    def drain_all_raw(self, out: np.ndarray = None):
+        """Records of every stream in one call; `out` = optional (pinned) uint8 array [nstreams, stride]."""
+        if out is None:
+            out = np.empty((self.nstreams, self._log_cap), dtype=np.uint8)
+        sizes = (ctypes.c_size_t * self.nstreams)()
+        _check(self._L.nrsc5b_drain_all(self._h, out.ctypes.data, out.strides[0], sizes), "nrsc5b_drain_all")
+        return [out[s, :sizes[s]] for s in range(self.nstreams)]
+
+    def drain_all(self):
+        return [parse_records(r.tobytes()) for r in self.drain_all_raw()]
 
     def set_sync_state(self, stream: int, state: int):
         _check(self._L.nrsc5b_set_sync_state(self._h, stream, state), "nrsc5b_set_sync_state")
