@@ -310,6 +310,7 @@ struct nrsc5b_engine {
     uint8_t *iq_owned;                 // engine-owned cu8 buffer (null when attached)
     std::vector<long long> pushed;     // complex cu8 samples pushed per stream
     std::vector<unsigned> drained;     // log bytes already handed out per stream
+    uint8_t *trim_scratch;             // bounce buffer of trim_stream (allocated on first use)
     uint8_t *pinned;                   // staging for pushes
     size_t pinned_cap;
     cudaEvent_t pinned_free;
@@ -426,6 +427,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->stream = 0;
     e->copy_stream = nullptr;
     e->iq_owned = nullptr;
+    e->trim_scratch = nullptr;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
     e->profiling = 0;
@@ -648,10 +650,50 @@ static int publish_avail(nrsc5b_engine *e, int s, cudaStream_t on)
     return 0;
 }
 
+__global__ void k_trim_state(DevPtrs p, int s, long long drop)
+{
+    p.st[s].start -= drop;
+    p.st[s].in_avail -= 2 * drop;
+}
+
+// Discards the samples a stream's window has moved past (everything more than 64 decimated samples before
+// the window start), so that an endless stream fits a fixed input buffer.  Synchronous; only called when a
+// push would not fit.
+static int trim_stream(nrsc5b_engine *e, int s)
+{
+    CK(cudaStreamSynchronize(e->copy_stream));
+    CK(cudaStreamSynchronize(e->stream));
+    StreamState st;
+    CK(cudaMemcpy(&st, e->dp.st + s, sizeof(st), cudaMemcpyDeviceToHost));
+    long long drop = (st.start - 64) & ~7LL;                  // decimated samples; 32-byte granularity in cu8
+    if (st.start < 72 || drop <= 0) return 0;
+    const size_t off = 4 * (size_t)drop, have = 2 * (size_t)e->pushed[s];
+    if (off >= have) return 0;
+    const size_t rem = have - off;
+    uint8_t *base = e->iq_owned + (size_t)s * e->dims.in_stride;
+    if (!e->trim_scratch) {
+        void *q = nullptr;
+        if (cudaMalloc(&q, e->dims.in_stride) != cudaSuccess) return NRSC5B_ENOMEM;
+        e->allocs.push_back(q);
+        e->trim_scratch = reinterpret_cast<uint8_t *>(q);
+    }
+    CK(cudaMemcpyAsync(e->trim_scratch, base + off, rem, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(base, e->trim_scratch, rem, cudaMemcpyDeviceToDevice, e->stream));
+    k_trim_state<<<1, 1, 0, e->stream>>>(e->dp, s, drop);
+    e->pushed[s] -= 2 * drop;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 extern "C" int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes)
 {
     if (!e || stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned) return NRSC5B_EINVAL;
     size_t off = (size_t)e->pushed[stream] * 2;
+    if (off + nbytes > e->dims.in_stride) {
+        int rc = trim_stream(e, stream);                       // make room: drop what the window has passed
+        if (rc) return rc;
+        off = (size_t)e->pushed[stream] * 2;
+    }
     if (off + nbytes > e->dims.in_stride) return NRSC5B_EFULL;
     uint8_t *dst = e->iq_owned + (size_t)stream * e->dims.in_stride + off;
     // page-locked caller memory is DMA'd directly; pageable memory goes through the engine's pinned staging buffer

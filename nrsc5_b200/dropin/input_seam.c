@@ -1,0 +1,207 @@
+/* The seven input_* functions of the reference (src/input.c:96-188, declared src/input.h:37-43) on top of
+ * the B200 engine's C ABI (include/nrsc5_b200.h).  Linked with the reference's unmodified host-side
+ * sources this gives a libnrsc5.so whose public API, event order and callback threading are the
+ * reference's: input_push_cu8() pushes the samples to the GPU, runs what they complete, and replays the
+ * engine's records - in the reference's call order - into frame_push() / pids_frame_push() /
+ * nrsc5_report_*() / output_advance() on the calling thread before it returns.
+ */
+#include "config.h"
+
+#include <assert.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "defines.h"
+#include "input.h"
+#include "private.h"
+
+#include "nrsc5_b200.h"
+
+#define INPUT_CAPACITY (8u << 20)       /* cu8 bytes buffered on the GPU (one 33-symbol window is 285 KB) */
+#define RECORDS_CAPACITY (4u << 20)
+
+static void fail(const char *what, int rc)
+{
+    fprintf(stderr, "libnrsc5 (B200): %s failed (%d); there is no CPU path\n", what, rc);
+    abort();
+}
+
+void input_set_sync_state(input_t *st, unsigned int new_state)
+{
+    /* reference src/input.c:172-188 for what the host side sees; the engine keeps the real state */
+    if (st->sync_state == new_state)
+        return;
+    if (st->sync_state == SYNC_STATE_FINE)
+        nrsc5_report_lost_sync(st->radio);
+    st->sync_state = new_state;
+    if (st->in_frame_push && st->engine)
+    {
+        /* frame.c:539 (L2 saw an audio frame whose header fails RS): the engine applies the same predicate
+         * on the GPU; forcing the state covers the cases where the two disagree */
+        int rc = nrsc5b_set_sync_state(st->engine, 0, (int)new_state);
+        if (rc) fail("nrsc5b_set_sync_state", rc);
+    }
+}
+
+static void unpack_bits(const uint8_t *packed, size_t nbits, uint8_t *bits)
+{
+    for (size_t i = 0; i < nbits; i++)
+        bits[i] = (packed[i >> 3] >> (7 - (i & 7))) & 1;
+}
+
+static void replay(input_t *st, const uint8_t *rec, size_t n)
+{
+    size_t off = 0;
+    while (off + 8 <= n)
+    {
+        uint32_t type, plen;
+        memcpy(&type, rec + off, 4);
+        memcpy(&plen, rec + off + 4, 4);
+        const uint8_t *pay = rec + off + 8;
+        off += 8 + ((plen + 3) & ~3u);
+        switch (type)
+        {
+        case NRSC5B_REC_BLOCK:                       /* acquire.c:108 */
+            output_advance(st->output);
+            break;
+        case NRSC5B_REC_SYNC:                        /* sync.c:403-409, input.c:180-186 */
+        {
+            float freq_offset;
+            int psmi;
+            memcpy(&freq_offset, pay, 4);
+            memcpy(&psmi, pay + 4, 4);
+            if (st->sync_state == SYNC_STATE_FINE)
+                nrsc5_report_lost_sync(st->radio);
+            st->sync_state = SYNC_STATE_FINE;
+            nrsc5_report_sync(st->radio, freq_offset, psmi, -1, -1, -1, -1);
+            pids_init(&st->pids, st);                /* decode_reset, decode.c:556-565 */
+            frame_reset(&st->frame);
+            break;
+        }
+        case NRSC5B_REC_LOST_SYNC:                   /* already reported if frame.c asked for it */
+            if (st->sync_state == SYNC_STATE_FINE)
+                nrsc5_report_lost_sync(st->radio);
+            st->sync_state = SYNC_STATE_NONE;
+            break;
+        case NRSC5B_REC_MER:                         /* sync.c:490-497 */
+        {
+            float lo, up;
+            memcpy(&lo, pay, 4);
+            memcpy(&up, pay + 4, 4);
+            nrsc5_report_mer(st->radio, lo, up);
+            break;
+        }
+        case NRSC5B_REC_BER:                         /* decode.c:458 */
+        {
+            float cber;
+            memcpy(&cber, pay, 4);
+            nrsc5_report_ber(st->radio, cber);
+            break;
+        }
+        case NRSC5B_REC_PIDS:                        /* decode.c:471 */
+            unpack_bits(pay, 80, st->bits);
+            pids_frame_push(&st->pids, st->bits);
+            break;
+        case NRSC5B_REC_FRAME:                       /* decode.c:460 */
+        {
+            uint32_t lc, nbits;
+            memcpy(&lc, pay, 4);
+            memcpy(&nbits, pay + 4, 4);
+            unpack_bits(pay + 8, nbits, st->bits);
+            st->in_frame_push = 1;
+            frame_push(&st->frame, st->bits, nbits, (logical_channel_t)lc);
+            st->in_frame_push = 0;
+            break;
+        }
+        default:
+            break;
+        }
+    }
+}
+
+void input_push_cu8(input_t *st, const uint8_t *buf, const uint32_t len)
+{
+    nrsc5_report_iq(st->radio, buf, len);            /* input.c:101 */
+    assert(len % 4 == 0);
+    uint32_t done = 0;
+    while (done < len)
+    {
+        /* at most a block's worth per round, so that L2's sync-loss verdict (frame.c:538) always lands
+         * before the engine starts the following block, as in the reference */
+        uint32_t n = len - done;
+        if (n > 65536) n = 65536;
+        int rc = nrsc5b_push_cu8(st->engine, 0, buf + done, n);
+        if (rc) fail("nrsc5b_push_cu8", rc);
+        rc = nrsc5b_process(st->engine);
+        if (rc) fail("nrsc5b_process", rc);
+        size_t need = 0;
+        long got = nrsc5b_drain(st->engine, 0, st->records, st->records_cap, &need);
+        if (got < 0) fail("nrsc5b_drain", (int)got);
+        replay(st, st->records, (size_t)got);
+        done += n;
+    }
+}
+
+void input_push_cs16(input_t *st, const int16_t *buf, const uint32_t len)
+{
+    (void)st; (void)buf; (void)len;
+    fprintf(stderr, "libnrsc5 (B200): cs16 input (AM, or pre-decimated FM) is not on the accelerated path yet\n");
+    abort();
+}
+
+void input_reset(input_t *st)
+{
+    /* input.c:126-138 */
+    if (st->sync_state == SYNC_STATE_FINE)
+        nrsc5_report_lost_sync(st->radio);
+    st->sync_state = SYNC_STATE_NONE;
+    int rc = nrsc5b_reset(st->engine, 0);
+    if (rc) fail("nrsc5b_reset", rc);
+    pids_init(&st->pids, st);
+    frame_reset(&st->frame);
+}
+
+void input_init(input_t *st, nrsc5_t *radio, output_t *output)
+{
+    memset(st, 0, sizeof(*st));
+    st->radio = radio;
+    st->output = output;
+    st->sync_state = SYNC_STATE_NONE;
+
+    nrsc5b_config_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const char *dev = getenv("NRSC5_B200_DEVICE");
+    cfg.device = dev ? atoi(dev) : 0;
+    cfg.nstreams = 1;
+    cfg.mode = NRSC5B_MODE_FM;
+    cfg.input_capacity = INPUT_CAPACITY;
+    cfg.log_capacity = RECORDS_CAPACITY;
+    int rc = nrsc5b_create(&st->engine, &cfg);
+    if (rc) fail("nrsc5b_create", rc);
+    st->records_cap = RECORDS_CAPACITY + 64;
+    st->records = malloc(st->records_cap);
+    st->bits = malloc(P1_FRAME_LEN_FM);
+    if (!st->records || !st->bits) fail("malloc", -1);
+
+    frame_init(&st->frame, st);
+    input_reset(st);
+}
+
+void input_set_mode(input_t *st)
+{
+    if (st->radio->mode != NRSC5_MODE_FM)
+    {
+        fprintf(stderr, "libnrsc5 (B200): AM is not on the accelerated path yet\n");
+        abort();
+    }
+    input_reset(st);
+}
+
+void input_free(input_t *st)
+{
+    frame_free(&st->frame);
+    nrsc5b_destroy(st->engine);
+    free(st->records);
+    free(st->bits);
+}

@@ -1,0 +1,52 @@
+"""The drop-in libnrsc5.so (reference host side + our input seam + the B200 engine) driven through the
+reference's PUBLIC API must deliver the events the unmodified reference delivers - same kinds, same order,
+identical HDC audio packets - on support/sample.xz (golden: tests/golden/api_sample_xz.json, made by
+tests/golden/make_golden_api.py with the unmodified reference)."""
+import os
+import subprocess
+
+import pytest
+
+import common
+import nrsc5_api
+
+DROPIN = os.path.join(common.ROOT, "nrsc5_b200", "dropin", "_build", "libnrsc5.so")
+PUBLIC_API = ["nrsc5_get_version", "nrsc5_service_data_type_name", "nrsc5_program_type_name", "nrsc5_open",
+              "nrsc5_open_file", "nrsc5_open_pipe", "nrsc5_open_rtltcp", "nrsc5_close", "nrsc5_start", "nrsc5_stop",
+              "nrsc5_set_mode", "nrsc5_set_bias_tee", "nrsc5_set_direct_sampling", "nrsc5_set_freq_correction",
+              "nrsc5_get_frequency", "nrsc5_set_frequency", "nrsc5_get_gain", "nrsc5_set_gain", "nrsc5_set_auto_gain",
+              "nrsc5_set_callback", "nrsc5_pipe_samples_cu8", "nrsc5_pipe_samples_cs16"]
+
+
+def test_dropin_exports_the_public_api():
+    if not os.path.exists(DROPIN):
+        pytest.skip("drop-in not built (needs the reference tree at build time)")
+    out = subprocess.run(["nm", "-D", "--defined-only", DROPIN], capture_output=True, text=True).stdout
+    names = {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+    for n in PUBLIC_API:
+        assert n in names, n
+    # and none of the reference's hot-path translation units were linked in
+    for n in ("acquire_process", "sync_push", "decode_push_pm", "nrsc5_conv_decode_p1", "firdecim_q15_create"):
+        assert n not in names, n
+
+
+@pytest.mark.gpu
+def test_dropin_events_match_reference_on_sample_xz():
+    if not os.path.exists(DROPIN):
+        pytest.skip("drop-in not built")
+    raw = common.load_sample()
+    if raw is None:
+        pytest.skip("sample.xz not available on this box")
+    g = common.golden("api_sample_xz.json")
+    got = nrsc5_api.run(DROPIN, raw.tobytes())
+    want = g["events"]
+    assert [e[0] for e in got] == [e[0] for e in want]                  # kinds and order
+    for a, b in zip(got, want):
+        if a[0] == "HDC":
+            assert a == b                                               # program, length, payload digest
+        elif a[0] == "SYNC":
+            assert a[2:] == b[2:] and abs(a[1] - b[1]) < 0.05
+        elif a[0] == "MER":
+            assert abs(a[1] - b[1]) < 0.05 and abs(a[2] - b[2]) < 0.05
+        elif a[0] == "BER":
+            assert abs(a[1] - b[1]) < 2e-4
