@@ -26,6 +26,13 @@ constexpr int P1_ENC = P1_LEN * 5 / 2;      // 365440
 constexpr int P1_VIT = P1_LEN * 3;          // 438528
 constexpr int P1_STEPS = P1_LEN + 64;       // tail-biting: 32 pre-roll + 32 post-roll
 constexpr int PIDS_LEN = 80;
+constexpr int P3_LEN = 4608;                // P3 frame bits in MP3/MP11 (reference src/defines.h:53)
+constexpr int P3_VIT = P3_LEN * 3;          // 13824
+constexpr int PX1_BLOCK = 4608;             // PX1 soft bits per block (2 partitions per sideband)
+constexpr int IV_N = 147456;                // span of interleaver IV (reference src/decode.c:350)
+constexpr int PX_RING = 2 * IV_N;
+constexpr int P3_SLOTS = 8;                 // P3 frames per stream and pass (one per two blocks)
+constexpr int P3_DEC_STRIDE = 5120;         // decisions per frame: 5 fallback chunks of 1024 >= 4608 + 64
 constexpr int ST_NONE = 0, ST_COARSE = 1, ST_FINE = 2;
 
 // record types (include/nrsc5_b200.h)
@@ -75,6 +82,12 @@ struct StreamState {
     int pids_pending;          // PIDS frames (of blocks pids_bc[]) waiting to be decoded into the log slots pids_rec[];
     int pids_bc[16];           // k_stream decodes them together, one warp each, before it exits
     unsigned pids_rec[16];
+    // P3 (MP3/MP11 PX1 partitions): convolutional interleaver IV bookkeeping (reference src/decode.c:344-414)
+    long long px_total;        // PX1 soft bits taken in since the interleaver (re)started
+    int px_started;
+    int p3_pending;            // P3 frames waiting for the decode kernels that follow k_stream
+    long long p3_k0[8];        // interleaver position of each frame's first soft bit
+    unsigned p3_rec[8];        // log offset of each frame's reserved FRAME record
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
     // output log cursor
     unsigned log_len;
@@ -118,6 +131,16 @@ struct DevPtrs {
     int *hstate, *tbend;       // [S][143]
     uint32_t *v64_spec, *v64_end;   // [S][V64 chunks][32] chunk boundary metrics of the fast P1 Viterbi
     int *v64_endstate;         // [S]
+    int8_t *px_ring;           // [S][2 * IV_N] PX1 soft bits in arrival order (the last two interleaver spans)
+    const uint32_t *iv_delay;  // [IV_N] interleaver IV: output m comes from the input iv_delay[m] positions earlier
+    int8_t *p3_vin;            // [S][8][13824] deinterleaved + depunctured P3 soft bits
+    uint2 *p3_dec;             // [S][8][P3_DEC_STRIDE] survivor decisions
+    uint32_t *p3_spec, *p3_end;     // [S][8][P3 chunks][32] fast Viterbi chunk boundary metrics
+    int *p3_endstate;          // [S][8]
+    uint2 *p3_fspec, *p3_fend; // [S][8][5][16] fallback Viterbi
+    int *p3_fhstate, *p3_ftbend;    // [S][8][5]
+    uint32_t *p3_bits;         // [S][8][144] decoded (still scrambled) bits
+    int *p3_flags;             // [S][8][4] ready, slow, retry, -
     uint8_t *log;              // [S][log_cap]
     const float *shape;        // [2160]
     const float2 *twid;        // [FFT_TW] twiddle tables of fft2048_block (fft.cuh)

@@ -52,14 +52,7 @@ __global__ void __launch_bounds__(256) k_p1_gather(DevPtrs p, EngineDims d)
     __shared__ uint16_t src[320];
     for (int i = t; i < 320; i += 256) src[i] = c_p1_src[i];
     if (r == 0 && t == 0) {
-        // reserve the BER and FRAME records now so that they keep their place in the stream's record order
-        uint8_t *w = log_reserve(p, d, s, REC_BER, 4);
-        uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8);
-        st.p1_rec = (w && fw) ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
-        if (fw) {
-            reinterpret_cast<uint32_t *>(fw)[0] = 0;            // P1 logical channel
-            reinterpret_cast<uint32_t *>(fw)[1] = P1_LEN;
-        }
+        // (the BER and FRAME records were reserved by the block's sync, in record order)
         st.p1_errs = 0;
         st.p1_done = 0;
         st.p1_retry = 0;
@@ -230,6 +223,95 @@ __host__ __device__ inline V64Args p1_v64_args(const DevPtrs &dp, int ch)
     a.ch = ch;
     a.nch = (P1_STEPS + ch - 1) / ch;
     a.dec_stride = (size_t)P1_NCH * CH_LEN;
+    return a;
+}
+
+// ===========================================================================
+// P3 decode (MP3/MP11): for every P3 frame the pass queued (decode_push_px1, reference src/decode.c:393-414) -
+//   k_p3_gather : interleaver IV as a gather through its delay table + depuncture 1,0,1,1,0,1 (decode.c:344-376)
+//   the same Viterbi kernels as P1 (4608-bit frames: fast path with 256-step chunks, exact fallback)
+//   k_p3_fin    : descramble (decode.c:279-294) and pack into the frame's reserved record
+// P3 frames feed nothing back into the receiver (frame.c:535-540 only acts on P1), so they can wait for
+// the end of the pass.
+// ===========================================================================
+__global__ void __launch_bounds__(256) k_p3_gather(DevPtrs p, EngineDims d)
+{
+    const int s = blockIdx.y, slot = blockIdx.x, t = threadIdx.x;
+    const StreamState &st = p.st[s];
+    int *fl = p.p3_flags + ((size_t)s * P3_SLOTS + slot) * 4;
+    const bool on = slot < st.p3_pending;
+    if (t == 0) { fl[0] = on; fl[1] = 0; fl[2] = 0; }
+    if (!on) return;
+    const long long k0 = st.p3_k0[slot];
+    const int8_t *ring = p.px_ring + (size_t)s * PX_RING;
+    uint32_t *vout = reinterpret_cast<uint32_t *>(p.p3_vin + ((size_t)s * P3_SLOTS + slot) * P3_VIT);
+    // 12 outputs = 8 transmitted soft bits: positions 0 2 3 5 | 6 8 9 11 of each dozen, zeros in between
+    for (int g = t; g < P3_VIT / 12; g += 256) {
+        int8_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const long long k = k0 + 8 * g + i;
+            const long long j = k - (long long)__ldg(&p.iv_delay[k % IV_N]);
+            v[i] = ring[j % PX_RING];
+        }
+        auto b = [&](int i) { return (uint32_t)(uint8_t)v[i]; };
+        vout[3 * g + 0] = b(0) | (b(1) << 16) | (b(2) << 24);
+        vout[3 * g + 1] = (b(3) << 8) | (b(4) << 16);
+        vout[3 * g + 2] = b(5) | (b(6) << 8) | (b(7) << 24);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_p3_fin(DevPtrs p, EngineDims d)
+{
+    const int s = blockIdx.y, slot = blockIdx.x, t = threadIdx.x;
+    const StreamState &st = p.st[s];
+    if (slot >= st.p3_pending) return;
+    const unsigned rec = st.p3_rec[slot];
+    if (rec == 0xffffffffu) return;
+    uint8_t *frame = p.log + (size_t)s * d.log_cap + rec + 8;          // past lc, nbits
+    const uint32_t *bw = p.p3_bits + ((size_t)s * P3_SLOTS + slot) * (P3_LEN / 32);
+    for (int w = t; w < P3_LEN / 32; w += 128) {
+        const uint32_t x = bw[w] ^ p.pnw[w];                            // the descrambler restarts with every frame
+        // MSB-first bytes
+        reinterpret_cast<uint32_t *>(frame)[w] = __brev(__byte_perm(x, 0, 0x0123));
+    }
+}
+
+__host__ __device__ inline V64Args p3_v64_args(const DevPtrs &dp)
+{
+    V64Args a;
+    a.vin = dp.p3_vin;
+    a.dec = dp.p3_dec;
+    a.vspec = dp.p3_spec;
+    a.vend = dp.p3_end;
+    a.endstate = dp.p3_endstate;
+    a.bitsw = dp.p3_bits;
+    a.ready = dp.p3_flags;
+    a.retry = dp.p3_flags + 2;
+    a.stride = 4;
+    a.len = P3_LEN;
+    a.ch = 256;
+    a.nch = (P3_LEN + 64 + 255) / 256;
+    a.dec_stride = P3_DEC_STRIDE;
+    return a;
+}
+
+__host__ __device__ inline VitcArgs p3_vitc_args(const DevPtrs &dp)
+{
+    VitcArgs a;
+    a.vin = dp.p3_vin;
+    a.dec = dp.p3_dec;
+    a.vspec = dp.p3_fspec;
+    a.vend = dp.p3_fend;
+    a.hstate = dp.p3_fhstate;
+    a.tbend = dp.p3_ftbend;
+    a.bitsw = dp.p3_bits;
+    a.ready = dp.p3_flags + 2;         // the fallback only decodes what the fast path gave up on
+    a.slow = dp.p3_flags + 1;
+    a.ready_stride = 4;
+    a.len = P3_LEN;
+    a.nch = (P3_LEN + 64 + CH_LEN - 1) / CH_LEN;
+    a.dec_stride = P3_DEC_STRIDE;
     return a;
 }
 
@@ -493,6 +575,21 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         DA(v64_end, uint32_t, (size_t)S * nch * 32);
         DA(v64_endstate, int, (size_t)S);
     }
+    {
+        const size_t F = (size_t)S * P3_SLOTS;
+        DA(px_ring, int8_t, (size_t)S * PX_RING);
+        DA(p3_vin, int8_t, F * P3_VIT);
+        DA(p3_dec, uint2, F * P3_DEC_STRIDE);
+        DA(p3_spec, uint32_t, F * 19 * 32);
+        DA(p3_end, uint32_t, F * 19 * 32);
+        DA(p3_endstate, int, F);
+        DA(p3_fspec, uint2, F * 5 * 16);
+        DA(p3_fend, uint2, F * 5 * 16);
+        DA(p3_fhstate, int, F * 5);
+        DA(p3_ftbend, int, F * 5);
+        DA(p3_bits, uint32_t, F * (P3_LEN / 32));
+        DA(p3_flags, int, F * 4);
+    }
     DA(log, uint8_t, (size_t)S * e->dims.log_cap);
     {
         // tables
@@ -529,6 +626,24 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
                 src[w] = (uint16_t)(blk * 720 + part * 36);
             }
             cudaMemcpyToSymbol(c_p1_src, src, sizeof(src));
+        }
+        {
+            // interleaver IV (decode.c:344-376, MP3/MP11: J=4, B=32, C=36, M=2): output m reads internal[A(m)]
+            // before input m is stored at internal[m]; as a delay: m - A(m) if A(m) < m, else one span more
+            std::vector<uint32_t> dl(IV_N);
+            unsigned pt[4] = { 0, 0, 0, 0 };
+            for (unsigned m = 0; m < (unsigned)IV_N; m++) {
+                const unsigned part = (m / 2) % 4, pti = pt[part]++;
+                const unsigned block = (pti + part * 7 - 1151 * (pti / 1152)) % 32;
+                const unsigned row = ((11 * pti) % 1152) / 36, col = (pti * 11) % 36;
+                const unsigned A = (block * 32 + row) * 144 + part * 36 + col;
+                dl[m] = A < m ? m - A : m - A + IV_N;
+            }
+            uint32_t *ddl = nullptr;
+            rc = dev_alloc(e, &ddl, IV_N);
+            if (rc) { nrsc5b_destroy(e); return rc; }
+            cudaMemcpy(ddl, dl.data(), dl.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+            dp.iv_delay = ddl;
         }
         uint32_t *dlut = nullptr;
         rc = dev_alloc(e, &dlut, P1_ENC);
@@ -775,6 +890,12 @@ static void launch_p1(nrsc5b_engine *e)
     launch_v64(p1_v64_args(e->dp, e->v64_ch), S, e->stream);      // fast path ...
     launch_vitc(p1_vitc_args(e->dp), S, e->stream);               // ... exact fallback for the frames it flagged
     k_p1_fin<<<dim3(FIN_CTAS, S), P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
+    e->stats.kernel_launches += 8;
+    // P3 frames (streams in MP3/MP11 queue up to 8 per pass; the kernels find nothing to do otherwise)
+    k_p3_gather<<<dim3(P3_SLOTS, S), 256, 0, e->stream>>>(e->dp, e->dims);
+    launch_v64(p3_v64_args(e->dp), S * P3_SLOTS, e->stream);
+    launch_vitc(p3_vitc_args(e->dp), S * P3_SLOTS, e->stream);
+    k_p3_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims);
     e->stats.kernel_launches += 8;
 }
 

@@ -663,6 +663,8 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     st.psmi = mps;
                     set_state(p, d, s, ST_FINE);
                     st.started_pm = 0;                   // decode_reset (decode.c:556-565)
+                    st.px_total = 0;
+                    st.px_started = 0;
                 }
             } else if (st.cfo_wait == 0) {
                 sm.do_search = 1;
@@ -721,8 +723,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             }
         }
         __syncthreads();
-        ppb = partitions_per_band(st.psmi);      // psmi may have changed with the FINE decision
-        nref = ppb + 1;
+        // (partitions_per_band stays what it was at entry even if the vote changed psmi, sync.c:343-357)
     }
 
     if (st.state == ST_FINE) {
@@ -857,6 +858,36 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                                ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
             *reinterpret_cast<uint32_t *>(pm + n * 720 + part * 36 + 4 * c4) = w;
         }
+        // PX1 (sync.c:552-573; MP3/MP11): two more partitions per sideband go to the convolutional interleaver's
+        // store in arrival order.  The mode is looked up afresh here, so the block that reaches FINE sync demaps
+        // them although it did not equalise them (its partition count was fixed at entry).
+        const int cm = c_compat_mode[st.psmi & 63];
+        const bool has_px1 = cm == 3 || cm == 11;
+        if (has_px1 && (st.px_started || (bc & 1) == 0)) {       // decode_push_px1, decode.c:393-399
+            int8_t *ring = p.px_ring + (size_t)s * PX_RING;
+            const long long T = st.px_total;
+            const int eqparts = rows / (PW - 1);
+            for (int item = t; item < BLK * 36; item += FRONT_THREADS) {
+                const int n = item / 36, rem = item - n * 36;
+                const int q = rem / 9, c4 = rem - q * 9;         // q: lower 10, lower 11, upper 11, upper 10 (from the band edge)
+                const int sb = q >= 2, i = (q == 0 || q == 3) ? 10 : 11;
+                float2 a, b;
+                if (i < eqparts) {
+                    const int r = (sb ? rows : 0) + i * (PW - 1) + 2 * c4;
+                    a = sm.eq[r][n];
+                    b = sm.eq[r + 1][n];
+                } else {
+                    const int ci = (sb == 0 ? PW * i : (NBINS - 1 - PW) - PW * i) + 1 + 2 * c4;
+                    a = bins[(size_t)n * NBINS + ci];
+                    b = bins[(size_t)n * NBINS + ci + 1];
+                }
+                const float mult = sm.mult[sb];
+                const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
+                                   ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
+                const long long pos = (T + n * 144 + q * 36 + 4 * c4) % PX_RING;
+                *reinterpret_cast<uint32_t *>(ring + pos) = w;
+            }
+        }
         __syncthreads();
         if (t == 0) {
             st.err_lb += e_sb[0];
@@ -893,9 +924,39 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             st.pids_rec[e] = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
             st.pids_bc[e] = bc;
             st.pids_pending = e + 1;
-            // P1 bookkeeping (decode.c:383-390)
+            // P1 bookkeeping (decode.c:383-390); the BER and FRAME records are reserved now so that they keep
+            // their place in the stream's record order (decode.c:458-460)
             if (bc == 0) st.started_pm = 1;
-            if (st.started_pm && bc == 15) st.p1_ready = 1;
+            if (st.started_pm && bc == 15) {
+                uint8_t *bw = log_reserve(p, d, s, REC_BER, 4);
+                uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8);
+                st.p1_rec = (bw && fw) ? (unsigned)(bw - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+                if (fw) {
+                    reinterpret_cast<uint32_t *>(fw)[0] = 0;            // P1 logical channel
+                    reinterpret_cast<uint32_t *>(fw)[1] = P1_LEN;
+                }
+                st.p1_ready = 1;
+            }
+            // P3 bookkeeping (decode_push_px1, decode.c:393-414): every second block closes a 9216-bit span of
+            // the interleaver; once a whole span of 147456 bits has gone through it yields a frame
+            if (has_px1) {
+                if ((bc & 1) == 0) st.px_started = 1;
+                if (st.px_started) {
+                    st.px_total += PX1_BLOCK;
+                    const long long k0 = st.px_total - 2 * PX1_BLOCK;
+                    if ((bc & 1) && k0 >= IV_N && st.p3_pending < P3_SLOTS) {
+                        uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P3_LEN / 8);
+                        const int e3 = st.p3_pending;
+                        st.p3_k0[e3] = k0;
+                        st.p3_rec[e3] = fw ? (unsigned)(fw - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+                        if (fw) {
+                            reinterpret_cast<uint32_t *>(fw)[0] = 1;        // P3 logical channel
+                            reinterpret_cast<uint32_t *>(fw)[1] = P3_LEN;
+                        }
+                        st.p3_pending = e3 + 1;
+                    }
+                }
+            }
             st.bc = (bc + 1) % 16;
         }
     }
@@ -923,6 +984,8 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
     __syncthreads();
 
     if (max_blocks > 16) max_blocks = 16;             // the PIDS queue (and its interleaver matrix rows) hold 16 blocks
+    if (t == 0) st.p3_pending = 0;                    // decoded by the kernels that followed the previous pass
+    __syncthreads();
     for (int nb = 0; nb < max_blocks; nb++) {
         // a completed interleaver matrix is decoded (and its header checked) before the next block
         if (st.p1_ready) break;

@@ -7,7 +7,9 @@ generated here (recipe: SURVEY.md §8(d), each step derived from the decoder):
   payload -> scramble (reference src/decode.c:279-294) -> rate-1/3 K=7
   tail-biting encode, g=(0133,0171,0165) (decode.c:238-255, conv_dec.c:139-154)
   -> puncture 1,1,1,1,1,0 (decode.c:263) -> inverse of interleaver I / II
-  (decode.c:296-342) -> QPSK map onto partitions (sync.c:509-536) + DBPSK
+  (decode.c:296-342); for MP3 also P3: puncture 1,0,1,1,0,1 and the inverse of
+  the convolutional interleaver IV (decode.c:344-376) onto the PX1 partitions
+  (sync.c:552-573) -> QPSK map onto partitions (sync.c:509-536) + DBPSK
   reference subcarriers (sync.c:96-99,169-186) -> 2x-oversampled OFDM with the
   receiver's raised-sine pulse shape (acquire.c:322-331) -> cu8 (defines.h:93).
 
@@ -222,8 +224,55 @@ class FmCapture:
     cu8: np.ndarray                      # uint8 [2 * nsamples], I/Q interleaved
     p1_frames: list = field(default_factory=list)    # list of uint8[146176] frame bits
     pids_frames: list = field(default_factory=list)  # list of uint8[80], block order
+    p3_frames: list = field(default_factory=list)    # MP3: list of uint8[4608] the receiver will output
     psmi: int = 1
     lead_in: int = 0
+
+
+# ----------------------------------------------------------------------------
+# P3 (MP3): convolutional interleaver IV
+# ----------------------------------------------------------------------------
+P3_BITS = 4608
+PX1_BLOCK = 4608                      # PX1 soft bits per block in MP3 (2 partitions per sideband)
+IV_N = 147456                         # interleaver IV span: 16 P3 frames = 32 blocks
+
+
+@lru_cache(maxsize=None)
+def interleaver_iv_delay() -> np.ndarray:
+    """D[m]: the deinterleaver's output m (mod IV_N) is the input it received D[m] positions earlier,
+    1 <= D <= IV_N (reference src/decode.c:344-376 for MP3/MP11: J=4, B=32, C=36, M=2): it reads
+    internal[A(m)] before it stores input m at internal[m]."""
+    J, B, C, M = 4, 32, 36, 2
+    bk_bits, bk_adj = 32 * C, 32 * C - 1
+    m = np.arange(IV_N, dtype=np.int64)
+    part = (m // M) % J
+    pti = np.empty(IV_N, dtype=np.int64)
+    for pp in range(J):
+        sel = part == pp
+        pti[sel] = np.arange(int(sel.sum()))
+    block = (pti + part * 7 - bk_adj * (pti // bk_bits)) % B
+    row = ((11 * pti) % bk_bits) // C
+    col = (pti * 11) % C
+    A = (block * 32 + row) * (J * C) + part * C + col
+    return np.where(A < m, m - A, m - A + IV_N)
+
+
+def build_p3_frame_bits(rng) -> np.ndarray:
+    """4608 descrambled P3 frame bits as handed to frame_push() (frame.c:658-662: PCI at logical bits
+    120 + 184 h); PCI says fixed data only and the last byte rules out a fixed-data sync (frame.c:448-456)."""
+    logical = np.zeros(P3_BITS, dtype=np.uint8)
+    pci_pos = 120 + 184 * np.arange(24)
+    is_pci = np.zeros(P3_BITS, dtype=bool)
+    is_pci[pci_pos] = True
+    logical[pci_pos] = [(PCI_FIXED >> (23 - h)) & 1 for h in range(24)]
+    pdu = rng.integers(0, 256, (P3_BITS - 24) // 8, dtype=np.uint8)
+    pdu[-1] = 0x12
+    logical[~is_pci] = np.unpackbits(pdu)
+    i = np.arange(P3_BITS)
+    phys = (i & ~7) + 7 - (i & 7)
+    bits = np.zeros(P3_BITS, dtype=np.uint8)
+    bits[phys] = logical
+    return bits
 
 
 @lru_cache(maxsize=None)
@@ -250,15 +299,28 @@ def _block_matrix_to_bins(mat_block: np.ndarray, refs: dict) -> np.ndarray:
     return S
 
 
-def make_fm_mp1(nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz: float = 0.0,
-                noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
-                tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
-                start_bc: int = 0) -> FmCapture:
-    """FM hybrid MP1 (PSMI 1) capture holding `nframes` complete L1 frames
+def make_fm_mp1(**kw) -> FmCapture:
+    """FM hybrid MP1 (PSMI 1), see make_fm."""
+    return make_fm(psmi=1, **kw)
+
+
+def make_fm_mp3(**kw) -> FmCapture:
+    """FM extended hybrid MP3 (PSMI 3): 13 reference subcarriers and 12 partitions per sideband, P3 on the
+    two PX1 partitions per sideband.  P3 frames only come out after the interleaver has filled
+    (16 P3 frames = 2 L1 frames), so use nframes >= 3."""
+    return make_fm(psmi=3, **kw)
+
+
+def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz: float = 0.0,
+            noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
+            tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
+            start_bc: int = 0) -> FmCapture:
+    """FM capture (PSMI 1 or 3) holding `nframes` complete L1 frames
     followed by `tail_blocks` further blocks so the last frame flushes
     (the reference has no flush call)."""
+    assert psmi in (1, 3)
     rng = np.random.default_rng(seed)
-    psmi = 1
+    nref = 11 if psmi == 1 else 13
     nblocks = nframes * BLOCKS_PER_FRAME + tail_blocks
     idx_i = interleaver_i_index()
     idx_ii = interleaver_ii_index()
@@ -285,6 +347,30 @@ def make_fm_mp1(nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz:
             pids_this.append(pb)
         mats.append((bits, pids_this, mat.reshape(16, 32, 20, 36)))
 
+    # P3 (MP3): the deinterleaver starts with the first even block it sees and hands out frame c (inputs of
+    # blocks 2c, 2c+1 counted from there) once 16 frames have gone in; transmit stream position j carries the
+    # punctured coded bit of output position k = j + D[k mod N]
+    px1 = None
+    if psmi == 3:
+        first_even = start_bc % 2                     # blocks before it carry PX1 bits nobody reads
+        ncalls = (nblocks - first_even) // 2
+        D = interleaver_iv_delay()
+        prng = np.random.default_rng(seed + 7919)
+        px1 = prng.integers(0, 2, nblocks * PX1_BLOCK, dtype=np.uint8)
+        tx = px1[first_even * PX1_BLOCK:]
+        pn_p3 = pn_sequence(P3_BITS)
+        keep3 = np.tile(np.array([1, 0, 1, 1, 0, 1], dtype=bool), P3_BITS * 3 // 6)
+        for c in range(ncalls):
+            fb = build_p3_frame_bits(prng)
+            u = conv_encode_tb(fb ^ pn_p3).reshape(-1)[keep3]          # 9216 transmitted bits
+            k = c * 2 * PX1_BLOCK + np.arange(2 * PX1_BLOCK, dtype=np.int64)
+            j = k - D[k % IV_N]
+            ok = j >= 0
+            tx[j[ok]] = u[ok]
+            if c >= IV_N // (2 * PX1_BLOCK):
+                cap.p3_frames.append(fb)
+        px1 = px1.reshape(nblocks, BLKSZ, 4, 18, 2)   # [block][symbol][lower q0, lower q1, upper q0, upper q1][carrier][re, im]
+
     sh = _shape2x()
     sig = np.zeros(nblocks * BLKSZ * 2 * FFTCP, dtype=np.complex128)
     first_full = None
@@ -293,11 +379,16 @@ def make_fm_mp1(nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz:
         f, bc = divmod(g, 16)
         bits, pids_this, mat = mats[f]
         refs = {}
-        for i in range(11):
+        for i in range(nref):
             raw = ref_raw_bits(bc, psmi, (30 - i) & 3)
             refs[LB_START + 19 * i] = raw
             refs[UB_END - 19 * i] = raw
         S = _block_matrix_to_bins(mat[bc], refs)
+        if px1 is not None:                           # PX1 partitions (sync.c:552-573)
+            symx = 2.0 * px1[blk].astype(np.float64) - 1.0
+            iqx = symx[..., 0] + 1j * symx[..., 1]    # [32, 4, 18]
+            for q, base in enumerate((LB_START + 190 + 1, LB_START + 209 + 1, UB_END - 228 + 1, UB_END - 209 + 1)):
+                S[:, base:base + 18] = iqx[:, q, :]
         # receiver computes fftshift(FFT(conj(x)));  build y = conj(x) at 2x rate
         S2 = np.zeros((BLKSZ, 2 * FFT), dtype=np.complex128)
         fidx = (np.arange(FFT) - FFT // 2) % (2 * FFT)

@@ -720,8 +720,8 @@ static unsigned demap_span(orc_t *o, int8_t *dst, unsigned n, unsigned first, un
 static void sync_block_fm(orc_t *o)                                 /* sync.c:339-610 */
 {
     int ppb;
-    const int cm = compat_mode[o->psmi];
-    switch (cm) {
+    /* partitions_per_band is fixed at entry (sync.c:343-357) even if the vote below changes psmi ... */
+    switch (compat_mode[o->psmi]) {
     case 2: ppb = 11; break;
     case 3: ppb = 12; break;
     case 5: case 6: case 11: ppb = 14; break;
@@ -814,6 +814,9 @@ static void sync_block_fm(orc_t *o)                                 /* sync.c:33
     const float mult_lb = fmaxf(fminf(mer_lb * 10, 127), 1);
     const float mult_ub = fmaxf(fminf(mer_ub * 10, 127), 1);
 
+    /* ... while the PX1/PX2 demap looks psmi up again (sync.c:537,552,574): in the block that reaches FINE
+     * sync the new mode's extra partitions are demapped although they were not equalised */
+    const int cm = compat_mode[o->psmi];
     int8_t pm[PM_BLOCK], px1[P3_LEN_MAX], px2[P3_LEN_MAX];
     unsigned n_pm = 0, n_px1 = 0, n_px2 = 0;
     for (unsigned n = 0; n < BLK; n++) {

@@ -43,6 +43,10 @@ SYNTH_CASES = {
 }
 
 
+# MP3 (extended hybrid: 12 partitions per sideband, P3 on the PX1 partitions through interleaver IV)
+MP3_CASE = dict(nframes=4, seed=11, lead_in=300, tail_blocks=2)
+
+
 def summarize(log):
     """Digest a RefLog into a JSON-able summary (order-preserving)."""
     import reftap

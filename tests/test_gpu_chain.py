@@ -83,6 +83,22 @@ def test_synth_pdus_bit_exact(name):
         assert [common.fnv1a32(b) for b in p1] == gold_frames
 
 
+def test_mp3_p1_pids_p3_bit_exact():
+    """FM MP3: P1, PIDS and P3 (PX1 partitions -> interleaver IV -> Viterbi) PDUs and the record order."""
+    cap = synth.make_fm_mp3(**common.MP3_CASE)
+    ref = port.decode(cap.cu8)
+    recs = run_engine([cap.cu8])[0]
+    frames = [(r["lc"], r["nbits"], r["bits"]) for t, r in recs if t == eng.REC_FRAME]
+    want = [(p["lc"], p["nbits"], p["bits"]) for t, p in ref.records if t == reftap.REC_FRAME]
+    assert frames == want
+    assert sum(1 for f in frames if f[0] == 1) >= 8
+    assert pdus(recs)[1] == ref.pids_frames
+    assert kinds(recs) == oracle_kinds(ref)
+    g = common.golden("synth_mp3.json")
+    if common.fnv1a32(cap.cu8[:1 << 20].tobytes()) == g["input_fnv"]:
+        assert [common.fnv1a32(b) for _, _, b in frames] == [e[3] for e in g["events"] if e[0] == "F"]
+
+
 def test_chunked_push_matches_single_push():
     cap = synth.make_fm_mp1(nframes=1, seed=3, lead_in=10)
     a = run_engine([cap.cu8])[0]

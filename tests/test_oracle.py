@@ -34,6 +34,20 @@ def test_port_matches_golden_synth(name):
     assert set(g["generated_p1_fnv"]) & set(got), "no generated frame was recovered"
 
 
+def test_port_matches_golden_mp3():
+    """MP3: 12 partitions per sideband, PX1 demap (incl. the unequalised block that reaches FINE sync),
+    interleaver IV, P3 frames - everything the unmodified reference put into the golden file."""
+    g = common.golden("synth_mp3.json")
+    cap = synth.make_fm_mp3(**common.MP3_CASE)
+    if common.fnv1a32(cap.cu8[:1 << 20].tobytes()) != g["input_fnv"]:
+        pytest.skip("numpy generator stream differs from the one the golden file was made with")
+    log = port.decode(cap.cu8, want_soft=True)
+    assert common.summarize(log) == g["events"]
+    assert _soft_fnv(log) == g["soft_fnv"]
+    p3 = [common.fnv1a32(p["bits"]) for t, p in log.records if t == reftap.REC_FRAME and p["lc"] == 1]
+    assert len(p3) >= 8 and set(p3) <= set(g["generated_p3_fnv"])     # round trip: only generated frames come out
+
+
 def test_port_matches_golden_sample():
     raw = common.load_sample()
     if raw is None:
