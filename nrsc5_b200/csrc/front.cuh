@@ -26,6 +26,7 @@ constexpr int TEAMS = FRONT_THREADS / 128;         // symbol teams of 128 thread
 constexpr int MAXREF = 15;                         // reference subcarriers per sideband (14 partitions + 1)
 constexpr int IN_BYTES = 4 * NSYM + 28 + 16 + 16;  // staged cu8 bytes per symbol (+ alignment slack) = 8700
 constexpr int IN_STRIDE = 8704;
+constexpr int ACQ_TILE = 4096;                     // decimated samples per acquisition tile
 
 __device__ int g_dbg;                              // experiment switches (nrsc5b_debug_set), 0 in production
 __device__ unsigned long long g_progress;          // bumped by every stream that processed a block
@@ -83,6 +84,8 @@ struct DemodSmem {
 };
 static_assert(IN_STRIDE <= FFT_SMEM_ELEMS * sizeof(float2), "staged input must fit in the FFT buffer");
 struct PrepSmem {
+    uint32_t words[ACQ_TILE + 40];                 // cu8 of one acquisition tile (+ 7 words of halfband, 31 of FIR history)
+    short2 ytile[ACQ_TILE + 32];                   // its halfband outputs, preceded by the 31 the band-pass looks back on
     float2 sums[NSYM];
     float red_mag[FRONT_THREADS];
     int red_idx[FRONT_THREADS];
@@ -107,15 +110,15 @@ struct SyncSmem {
     union {
         float2 eq[EQ_ROWS][EQ_LD];                 // data carriers [sideband*rows + partition*18 + k-1][symbol]
         struct {                                   // CFO search (never at the same time as the equaliser)
-            float2 rows[BLK][ZS];                  // working rows, [symbol][lane]
-            float tmp_phs[BLK][ZS];
+            int offs[76][22];                      // block offset found by every (trial, carrier), -1 = none
+            int verdict[76];                       // winning block offset of a trial, -1 = trial failed
+            int winner;
         } srch;
     };
     float wred[FRONT_THREADS / 32][2];             // per-warp error sums (lower, upper sideband)
     float fb_w[2][MAXREF], fb_xy[2][MAXREF + 1];   // feedback terms (phase differences, bin * frequency)
     float4 rowc[EQ_ROWS];                          // per carrier row: k*|upper ref|, (19-k)*|lower ref|, slots
     int ref_ok[2 * MAXREF], ref_bc[2 * MAXREF], ref_psmi[2 * MAXREF];
-    int offs[32];
     float mult[2];
     float angle;
     int do_search;
@@ -205,6 +208,26 @@ __device__ void front_pids_flush(const DevPtrs &p, const EngineDims &d, int s, P
 // ---------------------------------------------------------------------------
 // prep (reference src/acquire.c:98-168, src/sync.c:769-777, src/firdecim_q15.c:95-109,154-158)
 // ---------------------------------------------------------------------------
+// Halfband decimator output (reference src/firdecim_q15.c:137-151, taps int16{-134,1078,-4417,19864}) from the
+// eight 32-bit words that hold its 15 input samples: word q = cu8 samples 2q (low half) and 2q+1 (high half).
+// Exact integer arithmetic: ((64*s) * tap) >> 15 == (s * tap) >> 9.
+__device__ __forceinline__ int2 halfband_words(const uint32_t *w)
+{
+    const int tap[4] = { -134, 1078, -4417, 19864 };
+    int ar = 0, ai = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t a = w[k], b = w[7 - k];
+        const int sr = (int)(a & 0xff) + (int)(b & 0xff) - 254;
+        const int si = (int)((a >> 8) & 0xff) + (int)((b >> 8) & 0xff) - 254;
+        ar += (sr * tap[k]) >> 9;
+        ai += (si * tap[k]) >> 9;
+    }
+    ar += ((int)((w[3] >> 16) & 0xff) - 127) * 64;
+    ai += ((int)(w[3] >> 24) - 127) * 64;
+    return make_int2(ar, ai);
+}
+
 // Returns false (uniformly) when the stream has no complete 33-symbol window buffered.
 __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, float2 *nco, int t)
 {
@@ -229,34 +252,49 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
     const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
     const int state_in = st.state;
     if (state_in != ST_FINE) {
-        short2 *y = p.ydec + (size_t)s * NACQ;
         float2 *tb = p.tbuf + (size_t)s * NACQ;
         const long long start = st.start;
-        for (int i = t; i < NACQ; i += FRONT_THREADS) y[i] = halfband_at(iq, start + i);
-        __syncthreads();
-        // 32-tap symmetric Q15 band-pass; history = last 31 samples of the previous coarse window
-        for (int i = t; i < NACQ; i += FRONT_THREADS) {
-            auto at = [&](int pos) -> short2 {
-                if (pos >= 0) return y[pos];
-                return make_short2(st.bp_hist[31 + pos][0], st.bp_hist[31 + pos][1]);
-            };
-            short accr = 0, acci = 0;
-#pragma unroll 5
-            for (int k = 1; k < 16; k++) {
-                short2 a = at(i - 31 + k), b = at(i - 31 + 32 - k);
-                accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
-                acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
+        const uint32_t *iqw = reinterpret_cast<const uint32_t *>(iq);
+        // the 71280-sample window in tiles: cu8 words -> shared memory (coalesced), halfband /2 (input.c:52-94),
+        // 32-tap symmetric Q15 band-pass (acquire.c:120-127, firdecim_q15.c:95-109) -> float window in `tb`
+        for (int i0 = 0; i0 < NACQ; i0 += ACQ_TILE) {
+            const int L = min(ACQ_TILE, NACQ - i0);
+            const long long w0 = start + i0 - 38;                 // word of halfband output i0-31's first input
+            for (int v = t; v < L + 38; v += FRONT_THREADS) {
+                const long long a = w0 + v;
+                // before the stream starts the decimator sees zeros = byte 127; through L2 only (asynchronous pushes)
+                sm.words[v] = a >= 0 ? __ldcg(iqw + a) : 0x7f7f7f7fu;
             }
-            short2 c = at(i - 31 + 16);
-            accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
-            acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
-            tb[i] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
-        }
-        __syncthreads();
-        if (t < 31) {
-            short2 v = y[NACQ - 31 + t];
-            st.bp_hist[t][0] = v.x;
-            st.bp_hist[t][1] = v.y;
+            __syncthreads();
+            for (int k = t; k < L + 31; k += FRONT_THREADS) {
+                if (i0 == 0 && k < 31) {                          // history: the last 31 outputs of the previous window
+                    sm.ytile[k] = make_short2(st.bp_hist[k][0], st.bp_hist[k][1]);
+                } else {
+                    const int2 h = halfband_words(sm.words + k);
+                    sm.ytile[k] = make_short2((short)h.x, (short)h.y);
+                }
+            }
+            __syncthreads();
+            for (int j = t; j < L; j += FRONT_THREADS) {
+                const short2 *yy = sm.ytile + j;                  // yy[k] = y[i - 31 + k]
+                short accr = 0, acci = 0;
+#pragma unroll 5
+                for (int k = 1; k < 16; k++) {
+                    const short2 a = yy[k], b = yy[32 - k];
+                    accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
+                    acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
+                }
+                const short2 c = yy[16];
+                accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
+                acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
+                tb[i0 + j] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
+            }
+            if (i0 + L == NACQ && t < 31) {                       // keep the window's last 31 outputs as history
+                const short2 v = sm.ytile[L + t];
+                st.bp_hist[t][0] = v.x;
+                st.bp_hist[t][1] = v.y;
+            }
+            __syncthreads();
         }
         // cyclic-prefix correlation per sample offset (acquire.c:129-134)
         for (int i = t; i < NSYM; i += FRONT_THREADS) {
@@ -378,26 +416,13 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float2 sample_at(const uint32_t *sw, int j)
 {
-    // sw points at the 32-bit word holding input samples (2*base-14, 2*base-13); word q of output j
-    // holds samples m = 2q (low half) and m = 2q+1 (high half) of the 15-sample halfband window
+    // sw points at the 32-bit word holding input samples (2*base-14, 2*base-13): output j uses words j..j+7
     uint32_t w[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) w[q] = sw[j + q];
-    const int tap[4] = { -134, 1078, -4417, 19864 };
-    int ar = 0, ai = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t a = w[k], b = w[7 - k];
-        const int sr = (int)(a & 0xff) + (int)(b & 0xff) - 254;
-        const int si = (int)((a >> 8) & 0xff) + (int)((b >> 8) & 0xff) - 254;
-        // ((64*sr) * tap) >> 15  ==  (sr * tap) >> 9   (exact)
-        ar += (sr * tap[k]) >> 9;
-        ai += (si * tap[k]) >> 9;
-    }
-    ar += ((int)((w[3] >> 16) & 0xff) - 127) * 64;
-    ai += ((int)(w[3] >> 24) - 127) * 64;
+    const int2 h = halfband_words(w);
     const float sc = 1.0f / 32767.0f;
-    return make_float2((float)ar * sc, (float)ai * -sc);      // conj(x)/32767, acquire.c:160-161
+    return make_float2((float)h.x * sc, (float)h.y * -sc);    // conj(x)/32767, acquire.c:160-161
 }
 
 __device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sym, DemodSmem &sm, const float2 *nco,
@@ -674,51 +699,90 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         }
         __syncthreads();
         if (sm.do_search) {                      // detect_cfo (sync.c:292-337)
-            // the rows the search works on live in global memory; first give it the Costas-rotated references
-            for (int i = t; i < 2 * MAXREF * BLK; i += FRONT_THREADS) {
-                const int slot = i >> 5, n = i & 31;
+            // The reference tries the 76 integer offsets one after the other; each trial runs the Costas loop on
+            // 22 carriers (cfo + the reference positions), looks for the sync pattern and puts the carriers back,
+            // and the first offset with three agreeing block positions wins.  A trial only touches the state of
+            // its own 22 bins, and two trials share a bin only if they are 19 apart - so every BIN has its own
+            // short chain of trials (at most 4), and the chains of different bins are independent.  One thread
+            // per bin walks its chain on a private copy (snapshots in the acquisition scratch), the winner is
+            // picked exactly as the reference does, and only the snapshots up to the winner are committed.
+            // First give the search the Costas-rotated references (adjust_ref has already run on them).
+            for (int i = t; i < ZS * BLK; i += FRONT_THREADS) {
+                const int slot = i & (ZS - 1), n = i / ZS;
                 const int ii = slot < MAXREF ? slot : slot - MAXREF;
-                if (ii < nref) bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))] = sm.zref[n][slot];
+                if (slot < 2 * MAXREF && ii < nref) bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))] = sm.zref[n][slot];
+            }
+            for (int i = t; i < 76 * 22; i += FRONT_THREADS) sm.srch.offs[i / 22][i % 22] = -1;
+            __syncthreads();
+            constexpr int SB_BINS = 2 * PW * 2 + 10 * PW;                  // 266 bins a sideband's trials can touch
+            constexpr int NSB = 2 * SB_BINS;
+            float2 *snap = p.tbuf + (size_t)s * NACQ;                     // [4][32][NSB] row snapshots
+            float *sphs = reinterpret_cast<float *>(p.ydec + (size_t)s * NACQ);   // [32][NSB] Costas phases
+            float fs[4], phsn[4];
+            int cfo_of[4], nq = 0, ci = -1, b = 0;
+            if (t < NSB) {
+                const int upper = t >= SB_BINS;
+                b = upper ? (UB1 - 10 * PW - 2 * PW) + (t - SB_BINS) : (LB0 - 2 * PW) + t;
+                ci = compact_of_bin(b);
+                float f = cfreq[b], ph = cphase[b];
+                // trials touching this bin, in increasing cfo: lower cfo = b - LB0 - 19 i, upper cfo = b - UB1 + 19 i
+                for (int step = 0; step <= 10; step++) {
+                    const int i = upper ? step : 10 - step;
+                    const int cfo = upper ? b - UB1 + PW * i : b - LB0 - PW * i;
+                    if (cfo < -2 * PW || cfo >= 2 * PW) continue;
+                    float2 *row = snap + (size_t)nq * BLK * NSB + t;
+                    const float2 *src = nq ? snap + (size_t)(nq - 1) * BLK * NSB + t : nullptr;
+                    for (int n = 0; n < BLK; n++)
+                        row[(size_t)n * NSB] = nq ? src[(size_t)n * NSB]
+                                                  : (ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f));
+                    costas_row(row, sphs + t, NSB, f, ph, cfo, alpha, beta);
+                    sm.srch.offs[cfo + 2 * PW][2 * i + upper] = ref_find(row, NSB, (unsigned)(30 - i) & 3);
+                    for (int n = 0; n < BLK; n++)            // reset_ref (sync.c:132-136)
+                        row[(size_t)n * NSB] = cmulf(row[(size_t)n * NSB], cexp_j(sphs[(size_t)n * NSB + t]));
+                    fs[nq] = f;
+                    phsn[nq] = ph;
+                    cfo_of[nq] = cfo;
+                    nq++;
+                }
             }
             __syncthreads();
-            if (t < 32) {
-                const int lane = t;
-                for (int cfo = -2 * PW; cfo < 2 * PW; cfo++) {
-                    int off = -1;
-                    if (lane < 22) {
-                        const int i = lane >> 1, upper = lane & 1;
-                        const int b = upper ? cfo + UB1 - i * PW : cfo + LB0 + i * PW;
-                        const int ci = compact_of_bin(b);
-                        float2 *row = &sm.srch.rows[0][lane];
-                        for (int n = 0; n < BLK; n++)
-                            row[n * ZS] = ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f);
-                        costas_row(row, &sm.srch.tmp_phs[0][lane], ZS, cfreq[b], cphase[b], cfo, alpha, beta);
-                        off = ref_find(row, ZS, (unsigned)(30 - i) & 3);
-                        if (ci >= 0)
-                            for (int n = 0; n < BLK; n++)    // reset_ref (sync.c:132-136)
-                                bins[(size_t)n * NBINS + ci] = cmulf(row[n * ZS], cexp_j(sm.srch.tmp_phs[n][lane]));
+            // every trial's verdict (sync.c:320-336), then the first successful trial
+            if (t < 76) {
+                int best = -1;
+                unsigned bestn = 0;
+                for (int k = 0; k < BLK; k++) {
+                    unsigned nv = 0;
+                    for (int r = 0; r < 22; r++) nv += sm.srch.offs[t][r] == k;
+                    if (nv > bestn) { best = k; bestn = nv; }
+                }
+                sm.srch.verdict[t] = (best >= 0 && bestn >= 3) ? best : -1;
+            }
+            __syncthreads();
+            if (t == 0) {
+                int win = 1 << 20;                            // no winner: every trial ran
+                for (int c = 0; c < 76; c++)
+                    if (sm.srch.verdict[c] >= 0) { win = c - 2 * PW; break; }
+                sm.srch.winner = win;
+                if (win < (1 << 20)) {
+                    st.keep_extra = ((BLK - sm.srch.verdict[win + 2 * PW]) % BLK) * NSYM;
+                    st.cfo += win;
+                    st.cfo_wait = 8;
+                }
+            }
+            __syncthreads();
+            if (t < NSB) {
+                // commit what the sequential search would have left behind: the last trial <= the winner
+                const int win = sm.srch.winner;
+                int q = -1;
+                for (int k = 0; k < nq; k++)
+                    if (cfo_of[k] <= win) q = k;
+                if (q >= 0) {
+                    cfreq[b] = fs[q];
+                    cphase[b] = phsn[q];
+                    if (ci >= 0) {
+                        const float2 *row = snap + (size_t)q * BLK * NSB + t;
+                        for (int n = 0; n < BLK; n++) bins[(size_t)n * NBINS + ci] = row[(size_t)n * NSB];
                     }
-                    sm.offs[lane] = off;
-                    __syncwarp();
-                    int found = 0;
-                    if (lane == 0) {
-                        int best = -1;
-                        unsigned bestn = 0;
-                        for (int k = 0; k < BLK; k++) {
-                            unsigned nv = 0;
-                            for (int r = 0; r < 22; r++) nv += sm.offs[r] == k;
-                            if (nv > bestn) { best = k; bestn = nv; }
-                        }
-                        if (best >= 0 && bestn >= 3) {
-                            st.keep_extra = ((BLK - best) % BLK) * NSYM;
-                            st.cfo += cfo;
-                            st.cfo_wait = 8;
-                            found = 1;
-                        }
-                    }
-                    found = __shfl_sync(0xffffffffu, found, 0);
-                    __syncwarp();
-                    if (found) break;
                 }
             }
         }
