@@ -726,23 +726,30 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 ci = compact_of_bin(b);
                 float f = cfreq[b], ph = cphase[b];
                 // trials touching this bin, in increasing cfo: lower cfo = b - LB0 - 19 i, upper cfo = b - UB1 + 19 i
+                int ref_i[4];
                 for (int step = 0; step <= 10; step++) {
                     const int i = upper ? step : 10 - step;
                     const int cfo = upper ? b - UB1 + PW * i : b - LB0 - PW * i;
-                    if (cfo < -2 * PW || cfo >= 2 * PW) continue;
-                    float2 *row = snap + (size_t)nq * BLK * NSB + t;
-                    const float2 *src = nq ? snap + (size_t)(nq - 1) * BLK * NSB + t : nullptr;
+                    if (cfo >= -2 * PW && cfo < 2 * PW && nq < 4) {
+                        ref_i[nq] = i;
+                        cfo_of[nq] = cfo;
+                        nq++;
+                    }
+                }
+                // (the lanes of a warp walk their chains in step: trial q of every bin together)
+                for (int q = 0; q < nq; q++) {
+                    const int i = ref_i[q], cfo = cfo_of[q];
+                    float2 *row = snap + (size_t)q * BLK * NSB + t;
+                    const float2 *src = q ? snap + (size_t)(q - 1) * BLK * NSB + t : nullptr;
                     for (int n = 0; n < BLK; n++)
-                        row[(size_t)n * NSB] = nq ? src[(size_t)n * NSB]
-                                                  : (ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f));
+                        row[(size_t)n * NSB] = q ? src[(size_t)n * NSB]
+                                                 : (ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f));
                     costas_row(row, sphs + t, NSB, f, ph, cfo, alpha, beta);
                     sm.srch.offs[cfo + 2 * PW][2 * i + upper] = ref_find(row, NSB, (unsigned)(30 - i) & 3);
                     for (int n = 0; n < BLK; n++)            // reset_ref (sync.c:132-136)
                         row[(size_t)n * NSB] = cmulf(row[(size_t)n * NSB], cexp_j(sphs[(size_t)n * NSB + t]));
-                    fs[nq] = f;
-                    phsn[nq] = ph;
-                    cfo_of[nq] = cfo;
-                    nq++;
+                    fs[q] = f;
+                    phsn[q] = ph;
                 }
             }
             __syncthreads();
