@@ -106,6 +106,32 @@ def test_chunked_push_matches_single_push():
     assert pdus(a) == pdus(b) and kinds(a) == kinds(b)
 
 
+def test_drain_all_equals_per_stream_drain():
+    caps = [synth.make_fm_mp1(nframes=1, seed=200 + i, lead_in=11 * i + 3) for i in range(3)]
+    cap = max(c.cu8.size for c in caps) + 4096
+    outs = []
+    for use_all in (False, True):
+        with nrsc5_b200.Engine(nstreams=3, input_capacity=cap, log_capacity=4 << 20) as e:
+            for s, c in enumerate(caps):
+                e.push_cu8(s, c.cu8[: c.cu8.size & ~3])
+            e.process()
+            outs.append(e.drain_all() if use_all else [e.drain(s) for s in range(3)])
+    assert [[(t, r.get("bits")) for t, r in x] for x in outs[0]] == [[(t, r.get("bits")) for t, r in x] for x in outs[1]]
+
+
+def test_endless_stream_is_trimmed_to_the_input_buffer():
+    """Pushing more than the device buffer holds: the engine drops what the window has passed."""
+    cap = synth.make_fm_mp1(nframes=1, seed=31, lead_in=100)
+    whole = run_engine([cap.cu8])[0]
+    with nrsc5_b200.Engine(nstreams=1, input_capacity=1 << 20, log_capacity=4 << 20) as e:     # 1 MB < 4.7 MB capture
+        recs = []
+        for off in range(0, cap.cu8.size & ~3, 1 << 18):
+            e.push_cu8(0, cap.cu8[off: min(off + (1 << 18), cap.cu8.size & ~3)])
+            e.process()
+            recs += e.drain(0)
+    assert pdus(recs) == pdus(whole) and kinds(recs) == kinds(whole)
+
+
 def test_multi_stream_independent():
     caps = [synth.make_fm_mp1(nframes=1, seed=100 + i, lead_in=37 * i + 5, cfo_hz=40.0 * i) for i in range(5)]
     outs = run_engine([c.cu8 for c in caps])

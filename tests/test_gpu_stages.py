@@ -54,6 +54,28 @@ def test_viterbi_saturating_and_noisy():
     assert np.array_equal(got[1], port.viterbi(noisy))
 
 
+def test_viterbi_fast_path_and_fallback_agree():
+    """The register-resident fast path proves its result or hands the frame to the exact fallback: encoded
+    (even noisy) frames stay on the fast path, the saturating frame and pure noise must fall back - and every
+    result equals the sequential decoder's."""
+    rng = np.random.default_rng(8)
+    length = 4608
+    u = rng.integers(0, 2, length, dtype=np.uint8)
+    c = synth.conv_encode_tb(u).reshape(-1).astype(np.int16)
+    clean = ((2 * c - 1) * 60).astype(np.int8)
+    clean[5::6] = 0
+    noisy = np.clip((2 * c - 1) * 40 + rng.normal(0, 40, c.size), -127, 127).astype(np.int8)
+    noisy[5::6] = 0
+    got, fb = eng.viterbi_k7(np.stack([clean, noisy]), length, want_fallbacks=True)
+    assert fb == 0
+    assert np.array_equal(got[0], u) and np.array_equal(got[1], port.viterbi(noisy))
+    full = ((2 * c - 1) * 127).astype(np.int8)               # could saturate the reference's int16 metrics
+    rnd = rng.integers(-127, 128, 3 * length).astype(np.int8)
+    got, fb = eng.viterbi_k7(np.stack([full, rnd]), length, want_fallbacks=True)
+    assert fb >= 1
+    assert np.array_equal(got[0], port.viterbi(full)) and np.array_equal(got[1], port.viterbi(rnd))
+
+
 def test_viterbi_p1_length_bit_exact():
     rng = np.random.default_rng(4)
     length = 146176
