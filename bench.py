@@ -271,14 +271,16 @@ def main():
     def step_e2e():
         e.reset()
 
-        def push(k):
-            for s in range(S):
-                e.push_cu8(s, hnp[s, cuts[k]:cuts[k + 1]])
+        def push(k):                              # one strided copy: chunk k of every channel
+            e.push_cu8_all(host.data_ptr() + cuts[k], nbytes, cuts[k + 1] - cuts[k])
         push(0)
+        tok = e.push_fence()
         for k in range(E2E_CHUNKS):
             if k + 1 < E2E_CHUNKS:
                 push(k + 1)                       # asynchronous, on the engine's copy stream
-                e.process_available()             # works on what has landed while chunk k+1 is in flight
+                nxt = e.push_fence()
+                e.process_fence(tok)              # chunk k as soon as it has landed, while chunk k+1 is in flight
+                tok = nxt
             else:
                 e.process()
         frames = e.drain_all_raw(host_log_np)         # every stream's records: one state copy + one copy per stream

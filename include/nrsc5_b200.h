@@ -99,6 +99,9 @@ int nrsc5b_set_cuda_stream(nrsc5b_engine_t *e, void *cuda_stream);
 
 /* Append cu8 I/Q (host memory; staged through pinned memory, asynchronous H2D). nbytes % 4 == 0. */
 int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
+/* Append `nbytes` to EVERY stream from one page-locked host slab (stream s at host + s*host_stride) with a single
+ * strided copy; the streams must hold equally many samples (batch ingest of equally paced channels). */
+int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size_t host_stride, size_t nbytes);
 /* Append cu8 I/Q that already lives in device memory (device-to-device copy). */
 int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void *dev_buf, size_t nbytes);
 /* Point every stream at an existing device buffer [nstreams][stride] holding nbytes valid bytes each (no copy). */
@@ -113,6 +116,10 @@ int nrsc5b_process(nrsc5b_engine_t *e);
 /* Same, but does not wait for input copies still in flight (pushes are asynchronous): lets the next
  * nrsc5b_push_cu8 overlap with this call's compute.  A later nrsc5b_process() picks up the rest. */
 int nrsc5b_process_available(nrsc5b_engine_t *e);
+/* Overlapping transfer and compute: nrsc5b_push_fence() marks "everything pushed so far" and returns a token;
+ * nrsc5b_process_fence(token) processes exactly that as soon as it has landed, while later pushes keep copying. */
+int nrsc5b_push_fence(nrsc5b_engine_t *e);
+int nrsc5b_process_fence(nrsc5b_engine_t *e, int token);
 /* Wait for the GPU and copy the records of `stream` produced since the last drain.
  * Returns the number of bytes written (>= 0) or a negative error; *needed gets the full size. */
 long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_t cap, size_t *needed);

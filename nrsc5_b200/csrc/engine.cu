@@ -108,7 +108,11 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     uint8_t *frame = rec ? rec + 4 + 8 + 8 : nullptr;                // BER payload (4) | FRAME header (8) | lc,nbits (8) | bytes
     const int byte0 = blockIdx.x * FIN_BYTES, byte1 = min(P1_LEN / 8, byte0 + FIN_BYTES);
     int errs = 0;
-    for (int bi = byte0 + t; bi < byte1; bi += P1_THREADS) {
+    static_assert(FIN_BYTES % P1_THREADS == 0, "whole iterations");
+#pragma unroll
+    for (int it = 0; it < FIN_BYTES / P1_THREADS; it++) {          // independent iterations: their loads overlap
+        const int bi = byte0 + t + it * P1_THREADS;
+        if (bi >= byte1) break;
         // 14 decoded bits around this byte: frame bits 8*bi-6 .. 8*bi+7 (tail-biting wrap at the frame start)
         unsigned win;
         {
@@ -396,9 +400,13 @@ struct nrsc5b_engine {
     uint8_t *pinned;                   // staging for pushes
     size_t pinned_cap;
     cudaEvent_t pinned_free;
+    long long *avail_rows;             // pinned, 16 x S entries (nrsc5b_push_cu8_all), allocated on first use
+    unsigned avail_rows_pos;
     long long *avail_ring;             // pinned, 4096 entries
     unsigned avail_pos;
     cudaEvent_t reset_done;            // copy stream waits for resets issued on the compute stream
+    cudaEvent_t fence[64];             // push fences (nrsc5b_push_fence), created on first use
+    unsigned fence_next;
     StreamState *h_state;              // pinned mirror for read-back
     nrsc5b_stats_t stats;
     unsigned long long last_progress;
@@ -510,6 +518,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->copy_stream = nullptr;
     e->iq_owned = nullptr;
     e->trim_scratch = nullptr;
+    e->avail_rows = nullptr;
+    e->avail_rows_pos = 0;
+    for (int i = 0; i < 64; i++) e->fence[i] = nullptr;
+    e->fence_next = 0;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
     e->profiling = 0;
@@ -711,7 +723,9 @@ extern "C" void nrsc5b_destroy(nrsc5b_engine_t *e)
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_state) cudaFreeHost(e->h_state);
     if (e->avail_ring) cudaFreeHost(e->avail_ring);
+    if (e->avail_rows) cudaFreeHost(e->avail_rows);
     if (e->reset_done) cudaEventDestroy(e->reset_done);
+    for (int i = 0; i < 64; i++) if (e->fence[i]) cudaEventDestroy(e->fence[i]);
     if (e->pinned_free) cudaEventDestroy(e->pinned_free);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 5; i++) if (e->pev[i]) cudaEventDestroy(e->pev[i]);
@@ -831,6 +845,29 @@ extern "C" int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *bu
     e->pushed[stream] += (long long)(nbytes / 2);
     // published on the copy stream, i.e. after the samples themselves have landed
     return publish_avail(e, stream, e->copy_stream);
+}
+
+/* The same number of bytes for every stream from one page-locked host slab (stream s at host + s*host_stride):
+ * a single strided copy and a single publication of the new sample counts instead of one pair per stream. */
+extern "C" int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size_t host_stride, size_t nbytes)
+{
+    if (!e || !host || (nbytes & 3) || !e->iq_owned || nbytes > host_stride) return NRSC5B_EINVAL;
+    const int S = e->dims.nstreams;
+    for (int s = 1; s < S; s++)
+        if (e->pushed[s] != e->pushed[0]) return NRSC5B_EINVAL;          // streams must be in step
+    size_t off = (size_t)e->pushed[0] * 2;
+    if (off + nbytes > e->dims.in_stride) return NRSC5B_EFULL;
+    CK(cudaMemcpy2DAsync(e->iq_owned + off, e->dims.in_stride, host, host_stride, nbytes, S, cudaMemcpyHostToDevice,
+                         e->copy_stream));
+    // publish: one strided copy of the new count into every stream's state, after the samples
+    if (!e->avail_rows && cudaMallocHost((void **)&e->avail_rows, sizeof(long long) * 16 * S) != cudaSuccess) return NRSC5B_ENOMEM;
+    if (e->avail_rows_pos && (e->avail_rows_pos & 15) == 0) CK(cudaStreamSynchronize(e->copy_stream));   // rows recycled
+    long long *row = e->avail_rows + (size_t)(e->avail_rows_pos++ & 15) * S;
+    for (int s = 0; s < S; s++) row[s] = e->pushed[0] + (long long)(nbytes / 2);
+    CK(cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(e->dp.st) + offsetof(StreamState, in_avail), sizeof(StreamState), row,
+                         sizeof(long long), sizeof(long long), S, cudaMemcpyHostToDevice, e->copy_stream));
+    for (int s = 0; s < S; s++) e->pushed[s] += (long long)(nbytes / 2);
+    return NRSC5B_OK;
 }
 
 extern "C" int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void *dev_buf, size_t nbytes)
@@ -1002,6 +1039,26 @@ static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
         }
     }
     return NRSC5B_OK;
+}
+
+/* A fence behind everything pushed so far (pushes are asynchronous copies on the engine's copy stream).
+ * Returns a token >= 0 for nrsc5b_process_fence; tokens are recycled after 64 newer fences. */
+extern "C" int nrsc5b_push_fence(nrsc5b_engine_t *e)
+{
+    if (!e) return NRSC5B_EINVAL;
+    const unsigned slot = e->fence_next++ & 63;
+    if (!e->fence[slot]) CK(cudaEventCreateWithFlags(&e->fence[slot], cudaEventDisableTiming));
+    CK(cudaEventRecord(e->fence[slot], e->copy_stream));
+    return (int)slot;
+}
+
+/* Processes what had been pushed when the fence was taken, as soon as it has landed - later pushes keep
+ * copying meanwhile (the way to overlap host->device transfer with compute). */
+extern "C" int nrsc5b_process_fence(nrsc5b_engine_t *e, int token)
+{
+    if (!e || token < 0 || token >= 64 || !e->fence[token]) return NRSC5B_EINVAL;
+    CK(cudaStreamWaitEvent(e->stream, e->fence[token], 0));
+    return process_impl(e, false);
 }
 
 extern "C" int nrsc5b_process(nrsc5b_engine_t *e) { return process_impl(e, true); }

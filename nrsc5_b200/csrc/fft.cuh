@@ -48,6 +48,21 @@ __device__ __forceinline__ void fft8(float2 *v)
     v[3] = cadd(e3, w3); v[7] = csub(e3, w3);
 }
 
+// outputs 1, 2, 5, 6 only of the 8-point DFT of v (same arithmetic as fft8 for those outputs)
+__device__ __forceinline__ void fft8_kept(const float2 *v, float2 &x1, float2 &x2, float2 &x5, float2 &x6)
+{
+    // even/odd 4-point DFTs, outputs 1 and 2 each
+    const float2 et0 = cadd(v[0], v[4]), et1 = csub(v[0], v[4]), et2 = cadd(v[2], v[6]), et3 = mul_mj(csub(v[2], v[6]));
+    const float2 ot0 = cadd(v[1], v[5]), ot1 = csub(v[1], v[5]), ot2 = cadd(v[3], v[7]), ot3 = mul_mj(csub(v[3], v[7]));
+    const float2 e1 = cadd(et1, et3), e2 = csub(et0, et2);
+    const float2 o1 = cadd(ot1, ot3), o2 = csub(ot0, ot2);
+    const float h = 0.70710678118654752440f;
+    const float2 w1 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));      // o1 * (1-j)/sqrt2
+    const float2 w2 = mul_mj(o2);
+    x1 = cadd(e1, w1); x5 = csub(e1, w1);
+    x2 = cadd(e2, w2); x6 = csub(e2, w2);
+}
+
 // in-place 16-point DFT, natural order in and out
 __device__ __forceinline__ void fft16(float2 *v)
 {
@@ -81,6 +96,8 @@ constexpr int FFT_TW1 = 16 * 128, FFT_TW2 = 16 * 8, FFT_TW = FFT_TW1 + FFT_TW2;
 // v[n1], n1 = 0..15.  On exit thread t holds X[q + 256*k3] in out[h][k3] for
 // q = t + 128*h, h = 0..1, k3 = 0..7.  `buf` is FFT_SMEM_ELEMS float2 of
 // shared memory; `tw` = the FFT_TW-entry twiddle table above.
+// KEPT_ONLY: the last pass only produces out[h][1,2,5,6] (the bins the receiver keeps); the rest is garbage.
+template <bool KEPT_ONLY = false>
 __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float2 *buf,
                                               const float2 *__restrict__ tw, int t, int bar = 0)
 {
@@ -116,7 +133,15 @@ __device__ __forceinline__ void fft2048_block(float2 *v, float2 (*out)[8], float
         const int q = t + 128 * h;
 #pragma unroll
         for (int n3 = 0; n3 < 8; n3++) out[h][n3] = buf[n3 * 256 + q];
-        fft8(out[h]);
+        if (KEPT_ONLY) {
+            // the receiver keeps bins 478..744 and 1304..1570 of the shifted spectrum (sync.c:785-789): natural
+            // bins 280..546 and 1502..1768, i.e. only k3 = 1, 2, 5, 6 of X[q + 256*k3]
+            float2 x1, x2, x5, x6;
+            fft8_kept(out[h], x1, x2, x5, x6);
+            out[h][1] = x1; out[h][2] = x2; out[h][5] = x5; out[h][6] = x6;
+        } else {
+            fft8(out[h]);
+        }
     }
 }
 

@@ -469,18 +469,20 @@ __device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sy
     }
     bar_sync(bar);                                        // every thread is done with the staged input
     float2 out[2][8];
-    fft2048_block(v, out, buf, tw, tl, bar);
+    fft2048_block<true>(v, out, buf, tw, tl, bar);
 
+    // kept bins (sync.c:785-789, fftshift defines.h:123-138): with q = tl + 128 h and natural bin k = q + 256 k3,
+    //   k3 = 5 (q >= 222) -> compact q - 222,  k3 = 6 (q <= 232) -> q + 34      (lower sideband, bins 478..744)
+    //   k3 = 1 (q >= 24)  -> compact q + 243,  k3 = 2 (q <= 34)  -> q + 499     (upper sideband, bins 1304..1570)
     float2 *dst = p.bins + ((size_t)s * BLK + sym) * NBINS;
 #pragma unroll
-    for (int h = 0; h < 2; h++)
-#pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) {
-            const int k = tl + 128 * h + 256 * k3;        // natural-order bin
-            const int b = (k + NFFT / 2) & (NFFT - 1);    // fftshift (defines.h:123-138)
-            const int ci = compact_of_bin(b);
-            if (ci >= 0) dst[ci] = cmul(out[h][k3], sp);
-        }
+    for (int h = 0; h < 2; h++) {
+        const int q = tl + 128 * h;
+        if (q >= 222) dst[q - 222] = cmul(out[h][5], sp);
+        if (q <= 232) dst[q + 34] = cmul(out[h][6], sp);
+        if (q >= 24) dst[q + 243] = cmul(out[h][1], sp);
+        if (q <= 34) dst[q + 499] = cmul(out[h][2], sp);
+    }
 }
 
 // ---------------------------------------------------------------------------

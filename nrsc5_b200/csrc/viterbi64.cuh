@@ -277,7 +277,10 @@ __global__ void __launch_bounds__(V64_CHECK_THREADS) k_v64_check(V64Args a)
 // ---------------------------------------------------------------------------
 constexpr int V64_EMIT_WARPS = 4;
 constexpr int V64_EMIT_STEPS = V64_WIN + V64_HEAD;
-constexpr size_t V64_EMIT_SMEM = (size_t)V64_EMIT_WARPS * V64_EMIT_STEPS * sizeof(uint2);
+// staged decisions are padded by one word per 32 steps: the lanes walk segments 32 steps apart at the same time
+constexpr int V64_EMIT_LD = V64_EMIT_STEPS + V64_EMIT_STEPS / 32 + 1;
+constexpr size_t V64_EMIT_SMEM = (size_t)V64_EMIT_WARPS * V64_EMIT_LD * sizeof(uint2);
+__device__ __forceinline__ int v64_pad(int q) { return q + (q >> 5); }
 
 __global__ void __launch_bounds__(V64_EMIT_WARPS * 32) k_v64_emit(V64Args a)
 {
@@ -289,14 +292,14 @@ __global__ void __launch_bounds__(V64_EMIT_WARPS * 32) k_v64_emit(V64Args a)
     const int w = blockIdx.x * V64_EMIT_WARPS + warp;
     const int lo = w * V64_WIN;
     if (lo >= total) return;
-    uint2 *sd = reinterpret_cast<uint2 *>(v64_smem) + (size_t)warp * V64_EMIT_STEPS;
+    uint2 *sd = reinterpret_cast<uint2 *>(v64_smem) + (size_t)warp * V64_EMIT_LD;
     const uint2 *dec = a.dec + (size_t)f * a.dec_stride + lo;
     const int n = min(total - lo, V64_WIN);             // steps of this window
     const int nst = min(total - lo, V64_EMIT_STEPS);    // staged steps (incl. look-ahead)
-    for (int i = lane; i < nst; i += 32) sd[i] = dec[i];
+    for (int i = lane; i < nst; i += 32) sd[v64_pad(i)] = dec[i];
     __syncwarp();
     auto walk = [&](int state, int from, int to) {      // state after local step `from` -> state after local step `to`
-        for (int q = from; q > to; q--) state = v64_prev(state, sd[q]);
+        for (int q = from; q > to; q--) state = v64_prev(state, sd[v64_pad(q)]);
         return state;
     };
     // the window's end state: the frame's end state for the last window, otherwise the state all survivors
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(V64_EMIT_WARPS * 32) k_v64_emit(V64Args a)
         for (int look = min(V64_HEAD / 2, nst - n); ; look = nst - n) {
             int e0 = lane, e1 = lane + 32;
             for (int q = n + look - 1; q > n - 1; q--) {
-                const uint2 w = sd[q];
+                const uint2 w = sd[v64_pad(q)];
                 e0 = v64_prev(e0, w);
                 e1 = v64_prev(e1, w);
             }
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(V64_EMIT_WARPS * 32) k_v64_emit(V64Args a)
         unsigned ww = 0;
         for (int k = 31; k >= 0; k--) {
             ww |= (unsigned)((state >> 5) & 1) << k;
-            state = v64_prev(state, sd[32 * lane + k]);
+            state = v64_prev(state, sd[33 * lane + k]);
         }
         word = ww;
         b = state;

@@ -64,10 +64,13 @@ def load_library():
     L.nrsc5b_set_cuda_stream.argtypes = [vp, vp]
     L.nrsc5b_push_cu8.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_push_cu8_device.argtypes = [vp, ci, vp, sz]
+    L.nrsc5b_push_cu8_all.argtypes = [vp, vp, sz, sz]
     L.nrsc5b_attach_device_input.argtypes = [vp, vp, sz, sz]
     L.nrsc5b_attach_device_log.argtypes = [vp, vp, sz]
     L.nrsc5b_process.argtypes = [vp]
     L.nrsc5b_process_available.argtypes = [vp]
+    L.nrsc5b_push_fence.argtypes = [vp]
+    L.nrsc5b_process_fence.argtypes = [vp, ci]
     L.nrsc5b_synchronize.argtypes = [vp]
     L.nrsc5b_drain.argtypes = [vp, ci, vp, sz, ctypes.POINTER(sz)]
     L.nrsc5b_drain.restype = ctypes.c_long
@@ -211,6 +214,16 @@ class Engine:
 
     def process_available(self):
         _check(self._L.nrsc5b_process_available(self._h), "nrsc5b_process_available")
+
+    def push_cu8_all(self, host_ptr: int, host_stride: int, nbytes: int):
+        """nbytes for every stream from one page-locked slab (stream s at host_ptr + s*host_stride)."""
+        _check(self._L.nrsc5b_push_cu8_all(self._h, ctypes.c_void_p(host_ptr), host_stride, nbytes), "nrsc5b_push_cu8_all")
+
+    def push_fence(self) -> int:
+        return _check(self._L.nrsc5b_push_fence(self._h), "nrsc5b_push_fence")
+
+    def process_fence(self, token: int):
+        _check(self._L.nrsc5b_process_fence(self._h, token), "nrsc5b_process_fence")
 
     def synchronize(self):
         _check(self._L.nrsc5b_synchronize(self._h), "nrsc5b_synchronize")
