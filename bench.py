@@ -353,9 +353,18 @@ def main():
         gbs = alg[k] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
         kinfo[k] = {"ms_per_step": v["ms"], "launches": v["launches"], "alg_bytes_per_step": alg[k], "achieved_gbs": gbs}
     dom = max(("front", "p1"), key=lambda k: kt[k]["ms"])
-    roofline = {"bound": "hbm", "kernel": "k_front (fused prep+halfband+NCO+FFT+sync+demap, persistent)" if dom == "front" else "P1 decode group",
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture, scaled to this run's
+    # average launch (bytes per stream-block x stream-blocks per launch)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if dom == "front" and os.path.exists(tp):
+        tj = json.load(open(tp))
+        per_block = (tj["k_stream"]["dram_read_bytes"] + tj["k_stream"]["dram_write_bytes"]) / tj["k_stream"]["stream_blocks"]
+        traffic = per_block * blocks_per_step / max(1, kt[dom]["launches"])
+        traffic_src = tj["source"]
+    roofline = {"bound": "hbm", "kernel": "k_stream (stream-resident front end: prep+halfband+NCO+FFT+sync+demap)" if dom == "front" else "P1 decode group",
                 "achieved": kinfo[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kinfo[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kinfo[dom]["achieved_gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom] / max(1, kt[dom]["launches"]),
                 "chain_frac_of_hbm": (2.34 * value * 1e6 / world) / (peak * 1e9),
                 "kernels": kinfo, "front_phases_at_1965MHz": phases,

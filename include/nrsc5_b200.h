@@ -6,9 +6,12 @@
  *   nrsc5b_create / nrsc5b_destroy / nrsc5b_reset
  *       input_init / input_free / input_reset      reference src/input.h:37-40,
  *                                                   src/input.c:126-170
- *   nrsc5b_push_cu8 (+ nrsc5b_push_cu8_device)
+ *   nrsc5b_push_cu8 (+ nrsc5b_push_cu8_device, nrsc5b_push_cu8_all)
  *       input_push_cu8(input_t*, const uint8_t*, uint32_t)
  *                                                   reference src/input.h:42, src/input.c:96-117
+ *   nrsc5b_push_cs16
+ *       input_push_cs16(input_t*, const int16_t*, uint32_t)   (FM: samples already at 744 187.5 S/s)
+ *                                                   reference src/input.h:43, src/input.c:119-124
  *       The reference handles one stream per call; the engine takes a stream
  *       index so that many independent channels share one GPU (BASELINE
  *       configs 3-5).  `nbytes` counts uint8 values, as in the reference.
@@ -86,6 +89,8 @@ typedef struct {
     size_t input_capacity;      /* bytes of cu8 each stream can hold on the device      */
     size_t log_capacity;        /* bytes of output records per stream between drains    */
     int emit_soft;              /* also emit REC_SOFT_PM (debug / parity taps)          */
+    int input_cs16;             /* 0: cu8 I/Q at 1 488 375 S/s (nrsc5b_push_cu8); 1: cs16 at 744 187.5 S/s,
+                                   i.e. already decimated (nrsc5b_push_cs16), as input_push_cs16 takes it */
 } nrsc5b_config_t;
 
 int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg);
@@ -99,6 +104,9 @@ int nrsc5b_set_cuda_stream(nrsc5b_engine_t *e, void *cuda_stream);
 
 /* Append cu8 I/Q (host memory; staged through pinned memory, asynchronous H2D). nbytes % 4 == 0. */
 int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
+/* Append cs16 I/Q (engines created with input_cs16 = 1): nvalues counts int16 values, as in the reference
+ * (input_push_cs16, reference src/input.c:119-124; nvalues % 2 == 0). */
+int nrsc5b_push_cs16(nrsc5b_engine_t *e, int stream, const int16_t *buf, size_t nvalues);
 /* Append `nbytes` to EVERY stream from one page-locked host slab (stream s at host + s*host_stride) with a single
  * strided copy; the streams must hold equally many samples (batch ingest of equally paced channels). */
 int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size_t host_stride, size_t nbytes);

@@ -111,6 +111,7 @@ struct EngineDims {
     size_t in_stride;          // bytes between streams in the cu8 buffer
     size_t log_cap;            // bytes of log per stream
     int emit_soft;
+    int cs16;                  // input is cs16 at the decimated rate: 4 bytes per sample, no halfband
 };
 
 // Pointers to all device arrays, passed by value to kernels.

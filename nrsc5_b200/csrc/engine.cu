@@ -533,6 +533,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->dims.in_stride = (cfg->input_capacity + 63) & ~(size_t)63;
     e->dims.log_cap = cfg->log_capacity ? ((cfg->log_capacity + 15) & ~(size_t)15) : (1u << 20);
     e->dims.emit_soft = cfg->emit_soft;
+    e->dims.cs16 = cfg->input_cs16 ? 1 : 0;
     e->pushed.assign(S, 0);
     e->drained.assign(S, 0);
     int rc = upload_tables(cfg->device);
@@ -814,7 +815,23 @@ static int trim_stream(nrsc5b_engine *e, int s)
     return 0;
 }
 
+static int push_bytes(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
+
 extern "C" int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes)
+{
+    if (!e || e->dims.cs16) return NRSC5B_EINVAL;
+    return push_bytes(e, stream, buf, nbytes);
+}
+
+/* cs16: 4 bytes per (already decimated) complex sample; the engine counts input in 2-byte units either way, so
+ * a cs16 sample counts like the two cu8 samples it stands for */
+extern "C" int nrsc5b_push_cs16(nrsc5b_engine_t *e, int stream, const int16_t *buf, size_t nvalues)
+{
+    if (!e || !e->dims.cs16 || (nvalues & 1)) return NRSC5B_EINVAL;
+    return push_bytes(e, stream, reinterpret_cast<const uint8_t *>(buf), 2 * nvalues);
+}
+
+static int push_bytes(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes)
 {
     if (!e || stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned) return NRSC5B_EINVAL;
     size_t off = (size_t)e->pushed[stream] * 2;

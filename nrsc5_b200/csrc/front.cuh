@@ -263,12 +263,15 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
             for (int v = t; v < L + 38; v += FRONT_THREADS) {
                 const long long a = w0 + v;
                 // before the stream starts the decimator sees zeros = byte 127; through L2 only (asynchronous pushes)
-                sm.words[v] = a >= 0 ? __ldcg(iqw + a) : 0x7f7f7f7fu;
+                sm.words[v] = a >= 0 ? __ldcg(iqw + a) : (d.cs16 ? 0u : 0x7f7f7f7fu);
             }
             __syncthreads();
             for (int k = t; k < L + 31; k += FRONT_THREADS) {
                 if (i0 == 0 && k < 31) {                          // history: the last 31 outputs of the previous window
                     sm.ytile[k] = make_short2(st.bp_hist[k][0], st.bp_hist[k][1]);
+                } else if (d.cs16) {                              // already decimated: the sample itself
+                    const uint32_t w = sm.words[k + 7];
+                    sm.ytile[k] = make_short2((short)(w & 0xffff), (short)(w >> 16));
                 } else {
                     const int2 h = halfband_words(sm.words + k);
                     sm.ytile[k] = make_short2((short)h.x, (short)h.y);
@@ -425,6 +428,12 @@ __device__ __forceinline__ float2 sample_at(const uint32_t *sw, int j)
     return make_float2((float)h.x * sc, (float)h.y * -sc);    // conj(x)/32767, acquire.c:160-161
 }
 
+__device__ __forceinline__ float2 sample_cs16(uint32_t w)
+{
+    const float sc = 1.0f / 32767.0f;
+    return make_float2((float)(short)(w & 0xffff) * sc, (float)(short)(w >> 16) * -sc);   // conj(x)/32767
+}
+
 __device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sym, DemodSmem &sm, const float2 *nco,
                             const float2 *tw, int half, int tl, long long start, int samperr, float theta, float2 phase0)
 {
@@ -458,14 +467,26 @@ __device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sy
     // rotate by the block's NCO table (window folded in); j = n1*128 + tl
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(in + off);
     float2 v[16];
+    if (d.cs16) {                                         // cs16 input: word j+7 is sample j of the symbol
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        const int j = n1 * 128 + tl;
-        v[n1] = cmul(sample_at(sw, j), nco[j]);
-    }
-    if (tl < NCP) {                                       // fold the windowed tail onto the head (acquire.c:247-248)
-        const int j = NFFT + tl;
-        v[0] = cadd(v[0], cmul(sample_at(sw, j), nco[j]));
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int j = n1 * 128 + tl;
+            v[n1] = cmul(sample_cs16(sw[j + 7]), nco[j]);
+        }
+        if (tl < NCP) {
+            const int j = NFFT + tl;
+            v[0] = cadd(v[0], cmul(sample_cs16(sw[j + 7]), nco[j]));
+        }
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const int j = n1 * 128 + tl;
+            v[n1] = cmul(sample_at(sw, j), nco[j]);
+        }
+        if (tl < NCP) {                                   // fold the windowed tail onto the head (acquire.c:247-248)
+            const int j = NFFT + tl;
+            v[0] = cadd(v[0], cmul(sample_at(sw, j), nco[j]));
+        }
     }
     bar_sync(bar);                                        // every thread is done with the staged input
     float2 out[2][8];

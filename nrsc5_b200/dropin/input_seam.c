@@ -120,34 +120,77 @@ static void replay(input_t *st, const uint8_t *rec, size_t n)
     }
 }
 
+static void engine_open(input_t *st, int cs16)
+{
+    if (st->engine && st->engine_cs16 == cs16)
+        return;
+    /* the reference accepts cu8 and cs16 pushes on one handle; the engine is built for one format, so a
+     * change of format starts a new engine (= input_reset) */
+    if (st->engine)
+        nrsc5b_destroy(st->engine);
+    nrsc5b_config_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const char *dev = getenv("NRSC5_B200_DEVICE");
+    cfg.device = dev ? atoi(dev) : 0;
+    cfg.nstreams = 1;
+    cfg.mode = NRSC5B_MODE_FM;
+    cfg.input_capacity = INPUT_CAPACITY;
+    cfg.log_capacity = RECORDS_CAPACITY;
+    cfg.input_cs16 = cs16;
+    int rc = nrsc5b_create(&st->engine, &cfg);
+    if (rc) fail("nrsc5b_create", rc);
+    st->engine_cs16 = cs16;
+}
+
+static void run_and_replay(input_t *st)
+{
+    int rc = nrsc5b_process(st->engine);
+    if (rc) fail("nrsc5b_process", rc);
+    size_t need = 0;
+    long got = nrsc5b_drain(st->engine, 0, st->records, st->records_cap, &need);
+    if (got < 0) fail("nrsc5b_drain", (int)got);
+    replay(st, st->records, (size_t)got);
+}
+
 void input_push_cu8(input_t *st, const uint8_t *buf, const uint32_t len)
 {
     nrsc5_report_iq(st->radio, buf, len);            /* input.c:101 */
     assert(len % 4 == 0);
+    engine_open(st, 0);
     uint32_t done = 0;
     while (done < len)
     {
-        /* at most a block's worth per round, so that L2's sync-loss verdict (frame.c:538) always lands
+        /* at most a quarter block per round, so that L2's sync-loss verdict (frame.c:538) always lands
          * before the engine starts the following block, as in the reference */
         uint32_t n = len - done;
         if (n > 65536) n = 65536;
         int rc = nrsc5b_push_cu8(st->engine, 0, buf + done, n);
         if (rc) fail("nrsc5b_push_cu8", rc);
-        rc = nrsc5b_process(st->engine);
-        if (rc) fail("nrsc5b_process", rc);
-        size_t need = 0;
-        long got = nrsc5b_drain(st->engine, 0, st->records, st->records_cap, &need);
-        if (got < 0) fail("nrsc5b_drain", (int)got);
-        replay(st, st->records, (size_t)got);
+        run_and_replay(st);
         done += n;
     }
 }
 
 void input_push_cs16(input_t *st, const int16_t *buf, const uint32_t len)
 {
-    (void)st; (void)buf; (void)len;
-    fprintf(stderr, "libnrsc5 (B200): cs16 input (AM, or pre-decimated FM) is not on the accelerated path yet\n");
-    abort();
+    /* input.c:119-124: FM samples that are already at 744 187.5 S/s; len counts int16 values */
+    assert(len % 2 == 0);
+    if (st->radio->mode != NRSC5_MODE_FM)
+    {
+        fprintf(stderr, "libnrsc5 (B200): AM is not on the accelerated path yet\n");
+        abort();
+    }
+    engine_open(st, 1);
+    uint32_t done = 0;
+    while (done < len)
+    {
+        uint32_t n = len - done;
+        if (n > 32768) n = 32768;
+        int rc = nrsc5b_push_cs16(st->engine, 0, buf + done, n);
+        if (rc) fail("nrsc5b_push_cs16", rc);
+        run_and_replay(st);
+        done += n;
+    }
 }
 
 void input_reset(input_t *st)
@@ -169,16 +212,7 @@ void input_init(input_t *st, nrsc5_t *radio, output_t *output)
     st->output = output;
     st->sync_state = SYNC_STATE_NONE;
 
-    nrsc5b_config_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    const char *dev = getenv("NRSC5_B200_DEVICE");
-    cfg.device = dev ? atoi(dev) : 0;
-    cfg.nstreams = 1;
-    cfg.mode = NRSC5B_MODE_FM;
-    cfg.input_capacity = INPUT_CAPACITY;
-    cfg.log_capacity = RECORDS_CAPACITY;
-    int rc = nrsc5b_create(&st->engine, &cfg);
-    if (rc) fail("nrsc5b_create", rc);
+    engine_open(st, 0);
     st->records_cap = RECORDS_CAPACITY + 64;
     st->records = malloc(st->records_cap);
     st->bits = malloc(P1_FRAME_LEN_FM);

@@ -25,7 +25,7 @@ class EngineError(RuntimeError):
 class _Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("nstreams", ctypes.c_int), ("mode", ctypes.c_int),
                 ("input_capacity", ctypes.c_size_t), ("log_capacity", ctypes.c_size_t),
-                ("emit_soft", ctypes.c_int)]
+                ("emit_soft", ctypes.c_int), ("input_cs16", ctypes.c_int)]
 
 
 class Stats(ctypes.Structure):
@@ -63,6 +63,7 @@ def load_library():
     L.nrsc5b_get_phase_cycles.argtypes = [vp, vp, vp]
     L.nrsc5b_set_cuda_stream.argtypes = [vp, vp]
     L.nrsc5b_push_cu8.argtypes = [vp, ci, vp, sz]
+    L.nrsc5b_push_cs16.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_push_cu8_device.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_push_cu8_all.argtypes = [vp, vp, sz, sz]
     L.nrsc5b_attach_device_input.argtypes = [vp, vp, sz, sz]
@@ -138,10 +139,10 @@ class Engine:
     """
 
     def __init__(self, nstreams: int, input_capacity: int, device: int = 0, log_capacity: int = 1 << 20,
-                 emit_soft: bool = False):
+                 emit_soft: bool = False, input_cs16: bool = False):
         self._L = load_library()
         self._h = ctypes.c_void_p()
-        cfg = _Config(device, nstreams, 0, input_capacity, log_capacity, int(emit_soft))
+        cfg = _Config(device, nstreams, 0, input_capacity, log_capacity, int(emit_soft), int(input_cs16))
         _check(self._L.nrsc5b_create(ctypes.byref(self._h), ctypes.byref(cfg)), "nrsc5b_create")
         self.nstreams = nstreams
         self._log_cap = log_capacity + 64
@@ -214,6 +215,11 @@ class Engine:
 
     def process_available(self):
         _check(self._L.nrsc5b_process_available(self._h), "nrsc5b_process_available")
+
+    def push_cs16(self, stream: int, samples):
+        """samples: int16 numpy array (I, Q interleaved, 744 187.5 S/s); an engine made with input_cs16=True."""
+        a = np.ascontiguousarray(samples, dtype=np.int16)
+        _check(self._L.nrsc5b_push_cs16(self._h, stream, a.ctypes.data, a.size), "nrsc5b_push_cs16")
 
     def push_cu8_all(self, host_ptr: int, host_stride: int, nbytes: int):
         """nbytes for every stream from one page-locked slab (stream s at host_ptr + s*host_stride)."""

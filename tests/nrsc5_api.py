@@ -24,13 +24,15 @@ def fnv1a32(b: bytes) -> int:
     return h
 
 
-def run(lib_path: str, cu8: bytes, chunk: int = 32768):
+def run(lib_path: str, cu8: bytes, chunk: int = 32768, cs16: bool = False):
     """Decode `cu8` through the public API in `chunk`-byte pushes (main.c:1097-1119 uses 32768);
-    returns the event digest list, IQ events left out."""
+    returns the event digest list, IQ events left out.  With cs16=True the bytes are int16 I/Q at the
+    decimated rate and go through nrsc5_pipe_samples_cs16 (whose length counts int16 values)."""
     L = ctypes.CDLL(lib_path)
     L.nrsc5_open_pipe.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
     L.nrsc5_set_callback.argtypes = [ctypes.c_void_p, CALLBACK, ctypes.c_void_p]
     L.nrsc5_pipe_samples_cu8.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint]
+    L.nrsc5_pipe_samples_cs16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint]
     L.nrsc5_close.argtypes = [ctypes.c_void_p]
     events = []
 
@@ -64,6 +66,9 @@ def run(lib_path: str, cu8: bytes, chunk: int = 32768):
     base = ctypes.addressof(buf)
     for off in range(0, len(cu8), chunk):
         n = min(chunk, len(cu8) - off)
-        L.nrsc5_pipe_samples_cu8(h, base + off, n)
+        if cs16:
+            L.nrsc5_pipe_samples_cs16(h, base + off, n // 2)
+        else:
+            L.nrsc5_pipe_samples_cu8(h, base + off, n)
     L.nrsc5_close(h)
     return events

@@ -50,3 +50,20 @@ def test_dropin_events_match_reference_on_sample_xz():
             assert abs(a[1] - b[1]) < 0.05 and abs(a[2] - b[2]) < 0.05
         elif a[0] == "BER":
             assert abs(a[1] - b[1]) < 2e-4
+
+
+@pytest.mark.gpu
+def test_dropin_cs16_pipe_matches_reference_events():
+    """nrsc5_pipe_samples_cs16 (input_push_cs16): the exactly decimated sample.xz must produce the events of
+    the cu8 capture (the chain after the decimator is the same)."""
+    if not os.path.exists(DROPIN):
+        pytest.skip("drop-in not built")
+    raw = common.load_sample()
+    if raw is None:
+        pytest.skip("sample.xz not available on this box")
+    from nrsc5_b200 import engine as eng
+    cs16 = eng.halfband_fm(raw[: raw.size & ~3])
+    got = nrsc5_api.run(DROPIN, cs16.tobytes(), chunk=32768, cs16=True)
+    want = common.golden("api_sample_xz.json")["events"]
+    assert [e[0] for e in got] == [e[0] for e in want]
+    assert [e for e in got if e[0] == "HDC"] == [e for e in want if e[0] == "HDC"]
