@@ -1006,6 +1006,18 @@ size_t orc_log_size(const orc_t *o) { return o->log.len; }
 const uint8_t *orc_log_data(const orc_t *o) { return o->log.p; }
 void orc_log_clear(orc_t *o) { o->log.len = 0; }
 
+/* mirrors input_push_cs16 (reference src/input.c:119-124): FM samples already at 744 187.5 S/s go straight
+ * to the acquisition window; nvalues counts int16 values */
+void orc_push_cs16(orc_t *o, const int16_t *buf, size_t nvalues)
+{
+    for (size_t n = 0; n + 1 < nvalues; n += 2) {
+        o->win_r[o->fill] = buf[n];
+        o->win_i[o->fill] = buf[n + 1];
+        if (++o->fill == NACQ)
+            process_window(o);
+    }
+}
+
 void orc_push_cu8(orc_t *o, const uint8_t *buf, size_t nbytes)
 {
     for (size_t n = 0; n + 3 < nbytes; n += 4) {

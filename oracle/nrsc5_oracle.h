@@ -40,6 +40,8 @@ void orc_want_soft(orc_t *o, int on);
 void orc_want_blocks(orc_t *o, int on);
 /* mirrors input_push_cu8 (reference src/input.c:96); nbytes % 4 == 0 */
 void orc_push_cu8(orc_t *o, const uint8_t *buf, size_t nbytes);
+/* mirrors input_push_cs16 (reference src/input.c:119); nvalues % 2 == 0 */
+void orc_push_cs16(orc_t *o, const int16_t *buf, size_t nvalues);
 size_t orc_log_size(const orc_t *o);
 const uint8_t *orc_log_data(const orc_t *o);
 void orc_log_clear(orc_t *o);

@@ -27,6 +27,7 @@ def lib():
         L.orc_want_soft.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_want_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_push_cu8.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.orc_push_cs16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.orc_log_size.restype = ctypes.c_size_t
         L.orc_log_size.argtypes = [ctypes.c_void_p]
         L.orc_log_data.restype = ctypes.c_void_p
@@ -46,19 +47,23 @@ def lib():
 
 
 def decode(cu8: np.ndarray, chunk: int = 0, want_soft=False, want_blocks=False) -> RefLog:
+    """cu8 (uint8) capture, or cs16 (int16, already decimated) capture."""
     L = lib()
-    a = np.ascontiguousarray(cu8, dtype=np.uint8)
-    n = a.size & ~3
+    is_cs16 = np.asarray(cu8).dtype == np.int16
+    a = np.ascontiguousarray(cu8, dtype=np.int16 if is_cs16 else np.uint8)
+    n = a.size & (~1 if is_cs16 else ~3)
     o = L.orc_new()
     try:
         L.orc_want_soft(o, int(want_soft))
         L.orc_want_blocks(o, int(want_blocks))
+        push = L.orc_push_cs16 if is_cs16 else L.orc_push_cu8
+        item = 2 if is_cs16 else 1
         if chunk <= 0:
-            L.orc_push_cu8(o, a.ctypes.data, n)
+            push(o, a.ctypes.data, n)
         else:
             chunk &= ~3
             for off in range(0, n, chunk):
-                L.orc_push_cu8(o, a.ctypes.data + off, min(chunk, n - off))
+                push(o, a.ctypes.data + off * item, min(chunk, n - off))
         raw = ctypes.string_at(L.orc_log_data(o), L.orc_log_size(o))
     finally:
         L.orc_free(o)
