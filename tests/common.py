@@ -47,6 +47,13 @@ SYNTH_CASES = {
 MP3_CASE = dict(nframes=4, seed=11, lead_in=300, tail_blocks=2)
 
 
+# AM hybrid MA1, cs16 (the reference is the only decoder of these so far; CUDA rows: SURVEY §8 a21)
+AM_CASES = {
+    "ma1_clean": dict(nframes=10, seed=3, lead_in=500),
+    "ma1_cfo_awgn": dict(nframes=10, seed=4, lead_in=777, cfo_hz=1.5, noise_lsb=8.0),
+}
+
+
 def summarize(log):
     """Digest a RefLog into a JSON-able summary (order-preserving)."""
     import reftap
