@@ -46,6 +46,15 @@ size_t orc_log_size(const orc_t *o);
 const uint8_t *orc_log_data(const orc_t *o);
 void orc_log_clear(orc_t *o);
 
+/* ---- AM (hybrid MA1), oracle/nrsc5_oracle_am.c: cs16 at 46 511.72 S/s in, same record stream out ---- */
+typedef struct orc_am orc_am_t;
+orc_am_t *orc_am_new(void);
+void orc_am_free(orc_am_t *o);
+/* mirrors input_push_cs16 in AM mode (reference src/input.c:119); nvalues % 2 == 0 */
+void orc_am_push_cs16(orc_am_t *o, const int16_t *buf, size_t nvalues);
+size_t orc_am_log_size(const orc_am_t *o);
+const uint8_t *orc_am_log_data(const orc_am_t *o);
+
 /* ---- stage-level functions (pure; for kernel-by-kernel parity tests) ---- */
 /* cu8 -> Q15 -> halfband /2 from a zero history; n_out = npairs */
 void orc_halfband_fm(const uint8_t *cu8, size_t npairs, int16_t *out_ri);

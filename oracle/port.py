@@ -32,6 +32,13 @@ def lib():
         L.orc_log_size.argtypes = [ctypes.c_void_p]
         L.orc_log_data.restype = ctypes.c_void_p
         L.orc_log_data.argtypes = [ctypes.c_void_p]
+        L.orc_am_new.restype = ctypes.c_void_p
+        L.orc_am_free.argtypes = [ctypes.c_void_p]
+        L.orc_am_push_cs16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.orc_am_log_size.restype = ctypes.c_size_t
+        L.orc_am_log_size.argtypes = [ctypes.c_void_p]
+        L.orc_am_log_data.restype = ctypes.c_void_p
+        L.orc_am_log_data.argtypes = [ctypes.c_void_p]
         L.orc_halfband_fm.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
         L.orc_viterbi.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                   ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
@@ -67,6 +74,25 @@ def decode(cu8: np.ndarray, chunk: int = 0, want_soft=False, want_blocks=False) 
         raw = ctypes.string_at(L.orc_log_data(o), L.orc_log_size(o))
     finally:
         L.orc_free(o)
+    return _parse(raw)
+
+
+def decode_am(cs16: np.ndarray, chunk: int = 0) -> RefLog:
+    """AM hybrid MA1 capture (int16 I/Q at 46 511.72 S/s) through oracle/nrsc5_oracle_am.c."""
+    L = lib()
+    a = np.ascontiguousarray(cs16, dtype=np.int16)
+    n = a.size & ~1
+    o = L.orc_am_new()
+    try:
+        if chunk <= 0:
+            L.orc_am_push_cs16(o, a.ctypes.data, n)
+        else:
+            chunk &= ~1
+            for off in range(0, n, chunk):
+                L.orc_am_push_cs16(o, a.ctypes.data + 2 * off, min(chunk, n - off))
+        raw = ctypes.string_at(L.orc_am_log_data(o), L.orc_am_log_size(o))
+    finally:
+        L.orc_am_free(o)
     return _parse(raw)
 
 
