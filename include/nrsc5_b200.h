@@ -59,6 +59,7 @@ extern "C" {
 #endif
 
 #define NRSC5B_MODE_FM 0
+#define NRSC5B_MODE_AM 1      /* hybrid MA1, cs16 input at 46 511.72 S/s only (input_cs16 = 1); first, unoptimised path */
 
 enum {
     NRSC5B_OK = 0,
@@ -85,7 +86,7 @@ typedef struct nrsc5b_engine nrsc5b_engine_t;
 typedef struct {
     int device;                 /* CUDA device ordinal                                  */
     int nstreams;               /* independent channels on this GPU                     */
-    int mode;                   /* NRSC5B_MODE_FM                                       */
+    int mode;                   /* NRSC5B_MODE_FM or NRSC5B_MODE_AM                     */
     size_t input_capacity;      /* bytes of cu8 each stream can hold on the device      */
     size_t log_capacity;        /* bytes of output records per stream between drains    */
     int emit_soft;              /* also emit REC_SOFT_PM (debug / parity taps)          */

@@ -1,0 +1,757 @@
+// AM (hybrid MA1) receive chain: first CUDA path.  One WARP per stream runs the whole chain block after block
+// (k_am): coarse acquisition, carrier-phase tracking, 256-point OFDM demodulation, reference-carrier search,
+// training-symbol equalisation, QAM/QPSK slicing, PIDS, interleaver MA1 with the diversity delay, K=9
+// tail-biting Viterbi (E1/E2/E3), descramble, L1 PDUs.
+//
+//   reference: src/acquire.c:98-263 (AM branches), src/sync.c:37-88,208-252,612-767, src/decode.c:67-231,
+//              234-277,474-554, src/conv_dec.c (K=9), src/frame.c:645-714,527-541 (sync-loss predicate)
+//
+// The code is written so that it also compiles for the host with ONE lane (AM_HD functions, lane-strided
+// loops with AM_SYNC() between dependent phases): tests/am_host.cu runs exactly these functions on the CPU
+// against the oracle before the GPU ever sees them.  AM rates are tiny (46.5 kS/s per stream), so this first
+// version favours a line-by-line correspondence with the reference's order of operations over speed; the
+// K=9 add-compare-select and the FFT butterflies are spread over the lanes, everything sequential in the
+// reference (phase recurrences, arg-max scans, reductions) is computed redundantly by every lane.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <cuda_runtime.h>
+
+#if defined(__CUDA_ARCH__)
+#define AM_SYNC() __syncwarp()
+#else
+#define AM_SYNC() ((void)0)
+#endif
+#define AM_HD __host__ __device__
+// input samples may land (asynchronous pushes) while a kernel runs: on the device they are read through L2 only
+#if defined(__CUDA_ARCH__)
+#define AM_LDIN(ptr) __ldcg(ptr)
+#else
+#define AM_LDIN(ptr) (*(ptr))
+#endif
+
+namespace nbam {
+
+constexpr int FFT = 256, CP = 14, SYM = FFT + CP, BLK = 32, NACQ = SYM * (BLK + 1);
+constexpr int CENTER = 128, REF_IDX = 1, PIDS_INNER = 27, PIDS_OUTER = 53, INNER_START = 2, MIDDLE_START = 28,
+              OUTER_START = 57, MAX_IDX = 81, PW = 25;
+constexpr int P1_LEN = 3750, P3_LEN = 24000, PIDS_LEN = 80, DIVERSITY = 18000 * 3;
+constexpr int ST_NONE = 0, ST_COARSE = 1, ST_FINE = 2;
+constexpr int VIT_MAX_STEPS = P3_LEN + 64;
+constexpr uint32_t REC_FRAME = 1, REC_PIDS = 2, REC_SYNC = 3, REC_LOST_SYNC = 4, REC_BER = 6;
+constexpr double PI = 3.14159265358979323846;
+
+struct Lanes {
+    int lane, n;
+};
+
+// ---- complex helpers in the reference's (gcc, no FMA) evaluation order ----
+AM_HD inline float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+AM_HD inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+AM_HD inline float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+AM_HD inline float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+AM_HD inline float2 cexpj(float a)
+{
+    float s, c;
+    sincosf(a, &s, &c);
+    return make_float2(c, s);
+}
+AM_HD inline float cabs2(float2 a) { return hypotf(a.x, a.y); }
+AM_HD inline float carg(float2 a) { return atan2f(a.y, a.x); }
+// complex division the way libgcc's __divsc3 does it (Smith's algorithm)
+AM_HD inline float2 cdiv(float2 a, float2 b)
+{
+    float ratio, denom;
+    if (fabsf(b.x) < fabsf(b.y)) {
+        ratio = b.x / b.y;
+        denom = (b.x * ratio) + b.y;
+        return make_float2(((a.x * ratio) + a.y) / denom, ((a.y * ratio) - a.x) / denom);
+    }
+    ratio = b.y / b.x;
+    denom = (b.y * ratio) + b.x;
+    return make_float2(((a.y * ratio) + a.x) / denom, (a.y - (a.x * ratio)) / denom);
+}
+
+// Per-stream scalars (reference src/acquire.h, src/sync.h, src/decode.h).
+struct AmState {
+    long long in_avail;        // cs16 complex samples available from absolute index 0 (advanced by the host)
+    long long start;           // sample index of the acquisition window's first sample
+    float prev_angle;
+    float2 phase;
+    int keep_extra, cfo, state;
+    int psmi, pli, hppi, aabi, rdbi, cfo_wait, samperr;
+    unsigned bc, offset_history;
+    float angle;
+    int am_errors, am_diversity_wait;
+    unsigned log_len, log_overflow;
+    unsigned long long blocks_done;
+    short bp_hist[31][2];      // the coarse band-pass filter's last 31 inputs
+};
+
+// Per-stream arrays.
+struct AmWork {
+    float2 buf[NACQ];
+    float2 sums[SYM];
+    float2 fft[FFT];
+    float2 spec[FFT];                          // one demodulated symbol, fftshift-ed
+    float2 bins[FFT][BLK];
+    uint8_t buffer_pl[PW * BLK * 8], buffer_pu[PW * BLK * 8], buffer_s[PW * BLK * 8], buffer_t[PW * BLK * 8];
+    uint8_t bl[18000], bu[18000], ml[DIVERSITY + 18000], mu[DIVERSITY + 18000], el[12000], eu[24000];
+    uint8_t p1_am[8 * 9000], p3_am[36000];
+    int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN * 3], vit_pids[PIDS_LEN * 3];
+    uint8_t out[P3_LEN + 8];
+    short pm[2][256];
+    uint8_t dec[(size_t)VIT_MAX_STEPS * 32];   // survivor bits, see viterbi_k9
+    float2 mult[4][PW];
+    uint8_t sym_pl[BLK * PW], sym_pu[BLK * PW], sym_s[BLK * PW], sym_t[BLK * PW], sym_pids[2 * BLK];
+};
+
+struct AmTables {
+    float shape[SYM];
+    float2 tw[FFT / 2];        // exp(-2*pi*i*k/256)
+    short bp_tap[32];          // coarse band-pass taps, reversed and truncated like src/firdecim_q15.c:37-41
+    uint8_t brev[FFT];         // bit reversal of 8 bits
+    uint8_t pn[P3_LEN + 8];    // descrambler sequence
+};
+
+struct AmIo {
+    const int16_t *iq;         // this stream's cs16 samples, I/Q interleaved
+    uint8_t *log;
+    unsigned log_cap;
+};
+
+// ---- records ----
+// Every lane calls this with identical arguments (each keeps its own copy of the cursor); lane 0 writes.
+AM_HD inline uint8_t *log_reserve(AmState &st, const AmIo &io, Lanes L, uint32_t type, uint32_t plen)
+{
+    const uint32_t need = 8 + ((plen + 3) & ~3u);
+    if ((size_t)st.log_len + need > io.log_cap) {
+        st.log_overflow = 1;
+        return nullptr;
+    }
+    uint8_t *w = io.log + st.log_len;
+    if (L.lane == 0) {
+        uint32_t hdr[2] = { type, plen };
+        memcpy(w, hdr, 8);
+        memset(w + 8, 0, need - 8);
+    }
+    st.log_len += need;
+    return w + 8;
+}
+
+// All lanes call this with identical arguments; lane 0 writes.  `st` is every lane's private copy.
+AM_HD inline void emit_frame(AmState &st, const AmIo &io, Lanes L, const uint8_t *bits, unsigned len, unsigned lc)
+{
+    uint8_t *w = log_reserve(st, io, L, REC_FRAME, 8 + (len + 7) / 8);
+    if (w && L.lane == 0) {
+        uint32_t hdr[2] = { lc, len };
+        memcpy(w, hdr, 8);
+        for (unsigned i = 0; i < len; i++) w[8 + (i >> 3)] |= (uint8_t)((bits[i] & 1) << (7 - (i & 7)));
+    }
+}
+
+AM_HD inline void set_state(AmState &st, const AmIo &io, Lanes L, int ns)       // input.c:172-188
+{
+    if (st.state == ns) return;
+    if (st.state == ST_FINE) log_reserve(st, io, L, REC_LOST_SYNC, 0);
+    if (ns == ST_FINE) {
+        float fo = (float)(((double)st.prev_angle - 2 * PI * st.cfo) * 46511.71875 / (2 * PI * FFT));
+        uint8_t *w = log_reserve(st, io, L, REC_SYNC, 8);
+        if (w && L.lane == 0) {
+            memcpy(w, &fo, 4);
+            int32_t psmi = st.psmi;
+            memcpy(w + 4, &psmi, 4);
+        }
+    }
+    st.state = ns;
+}
+
+// ---- K=9 tail-biting Viterbi, rate 1/3 (reference src/conv_dec.c:359-453 with src/conv_gen.h) ----
+// int16 metrics, minimum subtracted when step % 77 == 0, survivor = odd predecessor unless the even one is
+// strictly better, first maximum at the end, 32 steps of pre- and post-roll.  Lane l owns butterflies
+// 4l..4l+3; byte dec[step*32 + l] holds the survivor bits of new states 4l..4l+3 (low nibble) and
+// 128+4l..128+4l+3 (high nibble).
+AM_HD inline int parity9(unsigned v)
+{
+    v ^= v >> 8;
+    v ^= v >> 4;
+    v ^= v >> 2;
+    v ^= v >> 1;
+    return (int)(v & 1u);
+}
+AM_HD inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+
+AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out, int len, unsigned g0, unsigned g1, unsigned g2)
+{
+    const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
+    for (int i = L.lane; i < 256; i += L.n) w.pm[0][i] = 0;
+    AM_SYNC();
+    int cur = 0;
+    int j = len - 32;
+    for (int s = 0; s < steps; s++, j++) {
+        if (j == len) j = 0;
+        const int q0 = in[3 * j], q1 = in[3 * j + 1], q2 = in[3 * j + 2];
+        const short *pmv = w.pm[cur];
+        short *nxt = w.pm[cur ^ 1];
+        for (int l = L.lane; l < 32; l += L.n) {
+            unsigned d = 0;
+            for (int q = 0; q < 4; q++) {
+                const int b = 4 * l + q;
+                const unsigned reg = (unsigned)b << 1;
+                const int m = q0 * (parity9(reg & g0) ? 1 : -1) + q1 * (parity9(reg & g1) ? 1 : -1) + q2 * (parity9(reg & g2) ? 1 : -1);
+                const int a0 = sat16(pmv[2 * b] + m), a1 = sat16(pmv[2 * b + 1] - m);
+                const int c0 = sat16(pmv[2 * b] - m), c1 = sat16(pmv[2 * b + 1] + m);
+                if (a0 > a1) nxt[b] = (short)a0;
+                else { nxt[b] = (short)a1; d |= 1u << q; }
+                if (c0 > c1) nxt[b + 128] = (short)c0;
+                else { nxt[b + 128] = (short)c1; d |= 16u << q; }
+            }
+            w.dec[(size_t)s * 32 + l] = (uint8_t)d;
+        }
+        AM_SYNC();
+        if (s % interval == 0) {
+            int mn = nxt[0];
+            for (int i = 1; i < 256; i++) mn = nxt[i] < mn ? nxt[i] : mn;     // every lane scans: same value
+            AM_SYNC();
+            for (int i = L.lane; i < 256; i += L.n) nxt[i] = (short)sat16(nxt[i] - mn);
+            AM_SYNC();
+        }
+        cur ^= 1;
+    }
+    // first maximum wins (conv_dec.c:310-317); every lane walks back, lane-strided writes of the output
+    const short *pmv = w.pm[cur];
+    int best = -1;
+    unsigned state = 0;
+    for (int i = 0; i < 256; i++)
+        if (pmv[i] > best) { best = pmv[i]; state = (unsigned)i; }
+    for (int s = steps - 1; s >= 0; s--) {
+        const unsigned byte = w.dec[(size_t)s * 32 + ((state & 127) >> 2)];
+        const unsigned bit = (byte >> ((state & 3) + (state >= 128 ? 4 : 0))) & 1u;
+        if (s >= 32 && s < 32 + len && ((s - 32) % L.n) == L.lane) out[s - 32] = (uint8_t)((state >> 7) & 1);
+        state = ((state << 1) & 254u) | bit;
+    }
+    AM_SYNC();
+}
+
+AM_HD inline void descramble(const AmTables &tb, Lanes L, uint8_t *bits, int len)     // decode.c:279-294
+{
+    for (int i = L.lane; i < len; i += L.n) bits[i] ^= tb.pn[i];
+    AM_SYNC();
+}
+
+AM_HD inline int bit_errors(const int8_t *coded, const uint8_t *decoded, unsigned len, unsigned g0, unsigned g1, unsigned g2,
+                            const uint8_t *punct, int plen)                             // decode.c:234-259
+{
+    const unsigned k = 9, gens[3] = { g0, g1, g2 };
+    unsigned r = 0, errors = 0;
+    for (unsigned i = 0; i < k - 1; i++) r = ((r >> 1) | ((unsigned)decoded[len - (k - 1) + i] << (k - 1))) & 0xffffu;
+    for (unsigned i = 0, j = 0; i < len; i++, j += 3) {
+        r = ((r >> 1) | ((unsigned)decoded[i] << (k - 1))) & 0xffffu;
+        for (unsigned g = 0; g < 3; g++)
+            if (punct[(j + g) % plen] && ((coded[j + g] > 0) != parity9(r & gens[g]))) errors++;
+    }
+    return (int)errors;
+}
+
+// ---- decode (reference src/decode.c) ----
+AM_HD inline int bit_map(const uint8_t *matrix, int b, int k, int p)                    // decode.c:67-72
+{
+    const int col = (9 * k) % 25;
+    const int row = (11 * col + 16 * (k / 25) + 11 * (k / 50)) % 32;
+    return (matrix[PW * (b * BLK + row) + col] >> p) & 1;
+}
+
+AM_HD inline void interleaver_ma1(AmWork &w, Lanes L)                                  // decode.c:74-231 (MA1)
+{
+    const int bl_delay[3] = { 2, 1, 5 }, ml_delay[3] = { 11, 6, 7 }, bu_delay[3] = { 10, 8, 9 }, mu_delay[3] = { 4, 3, 0 };
+    const int el_delay[2] = { 0, 1 }, eu_delay[4] = { 2, 3, 5, 4 };
+    for (int n = L.lane; n < 18000; n += L.n) {
+        w.bl[n] = (uint8_t)bit_map(w.buffer_pl, n / 2250, (n + n / 750 + 1) % 750, n % 3);
+        w.ml[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_pl, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
+        w.bu[n] = (uint8_t)bit_map(w.buffer_pu, n / 2250, (n + n / 750) % 750, n % 3);
+        w.mu[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_pu, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
+    }
+    for (int n = L.lane; n < 12000; n += L.n)
+        w.el[n] = (uint8_t)bit_map(w.buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2);
+    for (int n = L.lane; n < 24000; n += L.n)
+        w.eu[n] = (uint8_t)bit_map(w.buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4);
+    AM_SYNC();
+    for (int i = L.lane; i < 6000; i += L.n) {
+        for (int j = 0; j < 3; j++) {
+            w.p1_am[i * 12 + bl_delay[j]] = w.bl[i * 3 + j];
+            w.p1_am[i * 12 + ml_delay[j]] = w.ml[i * 3 + j];
+            w.p1_am[i * 12 + bu_delay[j]] = w.bu[i * 3 + j];
+            w.p1_am[i * 12 + mu_delay[j]] = w.mu[i * 3 + j];
+        }
+        for (int j = 0; j < 2; j++) w.p3_am[i * 6 + el_delay[j]] = w.el[i * 2 + j];
+        for (int j = 0; j < 4; j++) w.p3_am[i * 6 + eu_delay[j]] = w.eu[i * 4 + j];
+    }
+    AM_SYNC();
+    // the main bits move three frames towards the front (memmove of 54000 entries, in three non-overlapping steps)
+    for (int step = 0; step < 3; step++) {
+        for (int i = L.lane; i < 18000; i += L.n) {
+            w.ml[step * 18000 + i] = w.ml[(step + 1) * 18000 + i];
+            w.mu[step * 18000 + i] = w.mu[(step + 1) * 18000 + i];
+        }
+        AM_SYNC();
+    }
+    // depuncture: kept positions of every 15 (P1) / 6 (P3) code bits (decode.c:186-212)
+    for (int i = L.lane; i < 8 * P1_LEN * 3; i += L.n) {
+        const int r = i % 15, base = (i / 15) * 12;
+        const int before = r - (r > 1) - (r > 4) - (r > 7);
+        w.vit_p1[i] = (r == 1 || r == 4 || r == 7) ? 0 : (w.p1_am[base + before] ? 1 : -1);
+    }
+    for (int i = L.lane; i < P3_LEN * 3; i += L.n) {
+        const int r = i % 6, base = (i / 6) * 3;
+        const int before = r - (r > 1);
+        w.vit_p3[i] = (r == 1 || r == 4 || r == 5) ? 0 : (w.p3_am[base + before] ? 1 : -1);
+    }
+    AM_SYNC();
+}
+
+AM_HD inline void process_pids(AmState &st, AmWork &w, const AmTables &tb, const AmIo &io, Lanes L)   // decode.c:474-505
+{
+    const int il_delay[12] = { 0, 1, 12, 13, 6, 5, 18, 17, 11, 7, 23, 19 };
+    const int iu_delay[12] = { 2, 4, 14, 16, 3, 8, 15, 20, 9, 10, 21, 22 };
+    const uint8_t *sbit = w.sym_pids;
+    const int pids1_disabled = (st.psmi == 1) && st.rdbi;
+    for (int n = L.lane; n < 120; n += L.n) {
+        const int p = n % 4, i = n / 12, j = n % 12;
+        int k = (n + (n / 60) + 11) % 30;
+        int row = (11 * (k + (k / 15)) + 3) % 32;
+        const int il = (sbit[row * 2] >> p) & 1;
+        k = (n + (n / 60)) % 30;
+        row = (11 * (k + (k / 15)) + 3) % 32;
+        const int iu = (sbit[row * 2 + 1] >> p) & 1;
+        w.vit_pids[i * 24 + il_delay[j]] = pids1_disabled ? 0 : (il ? 1 : -1);
+        w.vit_pids[i * 24 + iu_delay[j]] = iu ? 1 : -1;
+    }
+    AM_SYNC();
+    viterbi_k9(w, L, w.vit_pids, w.out, PIDS_LEN, 0561, 0753, 0711);
+    descramble(tb, L, w.out, PIDS_LEN);
+    uint8_t *rec = log_reserve(st, io, L, REC_PIDS, 10);
+    if (rec && L.lane == 0)
+        for (int i = 0; i < PIDS_LEN; i++) rec[i >> 3] |= (uint8_t)(w.out[i] << (7 - (i & 7)));
+    AM_SYNC();
+}
+
+// frame.c:645-714 (PCI), :146-156, :527-541 + rs: an AM P1 PDU that announces audio but whose first header
+// fails RS(255,247) sends the receiver back to acquisition.  `fix_header` is supplied by the caller
+// (csrc/rs.cuh on the device, the same algorithm on the host).
+template <typename FixHeader>
+AM_HD inline int p1_sync_lost(const uint8_t *bits, FixHeader fix_header)
+{
+    uint8_t pdu[96];
+    unsigned h = 0, j = 0, nb = 0, val = 0;
+    uint32_t pci = 0;
+    for (int i = 0; i < 96; i++) pdu[i] = 0;
+    for (unsigned i = 0; i < (unsigned)P1_LEN && nb < 96; i++) {
+        const unsigned byte_start = (i >> 3) << 3;
+        const unsigned byte_len = (P1_LEN - byte_start < 8) ? P1_LEN - byte_start : 8;
+        const unsigned bit = bits[byte_start + byte_len - 1 - (i & 7)];
+        if (i >= 120 && ((i - 120) % 160) == 0 && h < 22) {
+            pci |= bit << (23 - h);
+            ++h;
+        } else {
+            val |= bit << (7 - j);
+            if (++j == 8) {
+                pdu[nb++] = (uint8_t)val;
+                val = 0;
+                j = 0;
+            }
+        }
+    }
+    // the PCI bits all lie behind the first 96 PDU bytes?  No: they start at bit 120 - collect the rest of them
+    for (unsigned hh = h; hh < 22; hh++) {
+        const unsigned i = 120 + 160 * hh;
+        const unsigned byte_start = (i >> 3) << 3;
+        const unsigned byte_len = (P1_LEN - byte_start < 8) ? P1_LEN - byte_start : 8;
+        pci |= (uint32_t)bits[byte_start + byte_len - 1 - (i & 7)] << (23 - hh);
+    }
+    if ((pci & 0xFFFFFC) == (0x3634CE & 0xFFFFFC)) return 0;              // fixed data only: no audio
+    return !fix_header(pdu);
+}
+
+template <typename FixHeader>
+AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, const AmIo &io, Lanes L, unsigned bc,
+                                FixHeader fix_header)                                   // decode.c:507-554
+{
+    const uint8_t punct_e1[15] = { 1, 0, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1 }, punct_e2[6] = { 1, 0, 1, 1, 0, 0 };
+    if (bc == 0) st.am_errors = 0;
+    if (st.am_diversity_wait == 0) {
+        const int8_t *v = w.vit_p1 + bc * P1_LEN * 3;
+        viterbi_k9(w, L, v, w.out, P1_LEN, 0561, 0657, 0711);
+        st.am_errors += bit_errors(v, w.out, P1_LEN, 0561, 0657, 0711, punct_e1, 15);
+        AM_SYNC();
+        descramble(tb, L, w.out, P1_LEN);
+        emit_frame(st, io, L, w.out, P1_LEN, 0);
+        if (p1_sync_lost(w.out, fix_header)) set_state(st, io, L, ST_NONE);              // inside frame_push, frame.c:538
+        AM_SYNC();
+        if (bc == 7) {
+            unsigned total = 8 * 9000;
+            if (!st.rdbi) {
+                total += 36000;
+                viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711);
+                st.am_errors += bit_errors(w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711, punct_e2, 6);
+                AM_SYNC();
+                descramble(tb, L, w.out, P3_LEN);
+                emit_frame(st, io, L, w.out, P3_LEN, 1);
+                AM_SYNC();
+            }
+            const float cber = (float)st.am_errors / (float)total;
+            uint8_t *rec = log_reserve(st, io, L, REC_BER, 4);
+            if (rec && L.lane == 0) memcpy(rec, &cber, 4);
+        }
+    }
+    if (bc == 7) {
+        interleaver_ma1(w, L);
+        if (st.am_diversity_wait > 0) st.am_diversity_wait--;
+    }
+}
+
+// ---- sync (reference src/sync.c) ----
+AM_HD inline uint8_t gray4(float f) { return f < -1 ? 0 : f < 0 ? 2 : f < 1 ? 3 : 1; }
+AM_HD inline uint8_t gray8(float f)
+{
+    return f < -3 ? 0 : f < -2 ? 4 : f < -1 ? 6 : f < 0 ? 2 : f < 1 ? 3 : f < 2 ? 7 : f < 3 ? 5 : 1;
+}
+AM_HD inline uint8_t qpsk(float2 c) { return (uint8_t)((c.x < 0 ? 0 : 1) | (c.y < 0 ? 0 : 2)); }
+AM_HD inline uint8_t qam16(float2 c) { return (uint8_t)(gray4(c.x) | (gray4(c.y) << 2)); }
+AM_HD inline uint8_t qam64(float2 c) { return (uint8_t)(gray8(c.x) | (gray8(c.y) << 3)); }
+
+AM_HD inline float phase_diff(float a, float b)                                         // sync.c:284-290
+{
+    float diff = a - b;
+    while ((double)diff > PI / 2) diff = (float)((double)diff - PI);
+    while ((double)diff < -PI / 2) diff = (float)((double)diff + PI);
+    return diff;
+}
+
+AM_HD inline int needle_am(int n)                                                       // sync.c:210-212
+{
+    const signed char nd[32] = { 0, 1, 1, 0, 0, 1, 0, -1, -1, 1, -1, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1, 1, 1,
+                                 -1, -1, -1, -1, -1, -1, -1, -1, -1 };
+    return nd[n];
+}
+
+AM_HD inline int find_block_am(AmState &st, const AmWork &w, unsigned ref)              // sync.c:208-237
+{
+    unsigned char data[BLK];
+    for (int n = 0; n < BLK; n++) {
+        data[n] = w.bins[ref][n].y <= 0 ? 0 : 1;
+        if ((needle_am(n) >= 0) && (data[n] != needle_am(n))) return -1;
+    }
+    if (data[7] ^ data[8]) return -1;
+    if (data[10] ^ data[11] ^ data[12] ^ data[13]) return -1;
+    if (data[15] ^ data[16] ^ data[17] ^ data[18] ^ data[19] ^ data[20]) return -1;
+    if (data[23] ^ data[24] ^ data[25] ^ data[26] ^ data[27] ^ data[28] ^ data[29] ^ data[30] ^ data[31]) return -1;
+    const int bc = (data[17] << 2) | (data[18] << 1) | data[19];
+    if (bc == 0) {
+        st.psmi = (data[26] << 4) | (data[27] << 3) | (data[28] << 2) | (data[29] << 1) | data[30];
+        st.pli = data[7];
+        st.hppi = data[11];
+        st.aabi = data[12];
+        st.rdbi = data[15];
+    }
+    return bc;
+}
+
+AM_HD inline int find_ref_am(const AmWork &w, unsigned ref)                             // sync.c:239-252, :150-167
+{
+    unsigned char data[BLK];
+    for (int n = 0; n < BLK; n++) data[n] = w.bins[ref][n].y <= 0 ? 0 : 1;
+    for (int n = 0; n < BLK; n++) {
+        int i;
+        for (i = 0; i < 23; i++) {
+            if (needle_am(i) < 0) continue;
+            if (needle_am(i) != data[(n + i) % BLK]) break;
+        }
+        if (i == 23) return n;
+    }
+    return -1;
+}
+
+template <typename FixHeader>
+AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const AmIo &io, Lanes L, FixHeader fix_header)
+{
+    // sync.c:616-633: mirror the lower sideband, fold it onto the upper one up to the outer PIDS carrier
+    for (int i = REF_IDX + L.lane; i <= MAX_IDX; i += L.n)
+        for (int n = 0; n < BLK; n++) {
+            const float2 v = w.bins[CENTER - i][n];
+            w.bins[CENTER - i][n] = make_float2(-v.x, v.y);                              // -conj
+        }
+    AM_SYNC();
+    for (int i = REF_IDX + L.lane; i <= PIDS_OUTER; i += L.n)
+        for (int n = 0; n < BLK; n++) w.bins[CENTER + i][n] = cadd(w.bins[CENTER + i][n], w.bins[CENTER - i][n]);
+    AM_SYNC();
+
+    if (st.state == ST_COARSE && st.cfo_wait == 0) {                                     // sync.c:635-647
+        const int offset = find_ref_am(w, CENTER + REF_IDX);
+        if (offset > 0) {
+            st.keep_extra = ((BLK - offset) % BLK) * SYM;
+            st.cfo_wait = 8;
+        }
+    } else {
+        st.cfo_wait--;
+    }
+    if (st.state == ST_COARSE) {                                                         // sync.c:649-666
+        const int bc = find_block_am(st, w, CENTER + REF_IDX);
+        if (bc == -1) st.offset_history = 0;
+        else st.offset_history = (st.offset_history << 4) | (unsigned)bc;
+        if ((st.offset_history & 0xffff) == 0x5670) {
+            st.bc = 0;
+            set_state(st, io, L, ST_FINE);
+            st.am_errors = 0;                                                            // decode_reset, decode.c:556-565
+            st.am_diversity_wait = 4;
+            st.offset_history = 0;
+        }
+    }
+    if (st.state != ST_FINE) return;
+
+    // PIDS carriers (sync.c:668-685): equalise with the training symbols of rows 8 and 24, slice
+    {
+        const float2 tr = make_float2(2 * 1.5f, 2 * -0.5f);
+        const float2 m1 = cdiv(tr, cadd(w.bins[CENTER + PIDS_INNER][8], w.bins[CENTER + PIDS_INNER][24]));
+        const float2 m2 = cdiv(tr, cadd(w.bins[CENTER + PIDS_OUTER][8], w.bins[CENTER + PIDS_OUTER][24]));
+        AM_SYNC();
+        for (int n = L.lane; n < BLK; n += L.n) {
+            w.bins[CENTER + PIDS_INNER][n] = cmul(w.bins[CENTER + PIDS_INNER][n], m1);
+            w.sym_pids[2 * n] = qam16(w.bins[CENTER + PIDS_INNER][n]);
+            w.bins[CENTER + PIDS_OUTER][n] = cmul(w.bins[CENTER + PIDS_OUTER][n], m2);
+            w.sym_pids[2 * n + 1] = qam16(w.bins[CENTER + PIDS_OUTER][n]);
+        }
+        AM_SYNC();
+    }
+    process_pids(st, w, tb, io, L);
+
+    // partitions (sync.c:687-717): per column the two training rows give the equaliser tap
+    for (int col = L.lane; col < PW; col += L.n) {
+        const int t1 = (5 + 11 * col) % 32, t2 = (21 + 11 * col) % 32;
+        w.mult[0][col] = cdiv(make_float2(2 * 2.5f, 2 * -2.5f), cadd(w.bins[CENTER - OUTER_START - col][t1], w.bins[CENTER - OUTER_START - col][t2]));
+        w.mult[1][col] = cdiv(make_float2(2 * 2.5f, 2 * -2.5f), cadd(w.bins[CENTER + OUTER_START + col][t1], w.bins[CENTER + OUTER_START + col][t2]));
+        w.mult[2][col] = cdiv(make_float2(2 * 1.5f, 2 * -0.5f), cadd(w.bins[CENTER + MIDDLE_START + col][t1], w.bins[CENTER + MIDDLE_START + col][t2]));
+        w.mult[3][col] = cdiv(make_float2(2 * -0.5f, 2 * 0.5f), cadd(w.bins[CENTER + INNER_START + col][t1], w.bins[CENTER + INNER_START + col][t2]));
+    }
+    AM_SYNC();
+    {
+        float samperr = 0;
+        for (int col = 1; col < PW; col++) {
+            samperr += phase_diff(carg(w.mult[0][col]), carg(w.mult[0][col - 1]));
+            samperr += phase_diff(carg(w.mult[1][col]), carg(w.mult[1][col - 1]));
+        }
+        samperr = (float)((double)(samperr / (2 * (PW - 1)) * FFT) / (2 * PI));
+        st.samperr = (int)roundf(samperr);
+    }
+    for (int idx = L.lane; idx < BLK * PW; idx += L.n) {                                 // sync.c:725-754
+        const int n = idx / PW, col = idx - n * PW;
+        float2 v;
+        v = cmul(w.bins[CENTER - OUTER_START - col][n], w.mult[0][col]);
+        w.bins[CENTER - OUTER_START - col][n] = v;
+        w.sym_pl[idx] = qam64(v);
+        v = cmul(w.bins[CENTER + OUTER_START + col][n], w.mult[1][col]);
+        w.bins[CENTER + OUTER_START + col][n] = v;
+        w.sym_pu[idx] = qam64(v);
+        v = cmul(w.bins[CENTER + MIDDLE_START + col][n], w.mult[2][col]);
+        w.bins[CENTER + MIDDLE_START + col][n] = v;
+        w.sym_s[idx] = qam16(v);
+        v = cmul(w.bins[CENTER + INNER_START + col][n], w.mult[3][col]);
+        w.bins[CENTER + INNER_START + col][n] = v;
+        w.sym_t[idx] = qpsk(v);
+    }
+    AM_SYNC();
+    for (int i = L.lane; i < BLK * PW; i += L.n) {                                        // decode_push_pl_pu_s_t, decode.c:439-449
+        w.buffer_pl[st.bc * BLK * PW + i] = w.sym_pl[i];
+        w.buffer_pu[st.bc * BLK * PW + i] = w.sym_pu[i];
+        w.buffer_s[st.bc * BLK * PW + i] = w.sym_s[i];
+        w.buffer_t[st.bc * BLK * PW + i] = w.sym_t[i];
+    }
+    AM_SYNC();
+    process_p1_p3(st, w, tb, io, L, st.bc, fix_header);
+    st.bc = (st.bc + 1) % 8;
+}
+
+// ---- acquisition and demodulation (reference src/acquire.c) ----
+AM_HD inline float2 input_at(const AmIo &io, long long n)            // cq15_to_cf, defines.h:106-109 (no conjugate in AM)
+{
+    return make_float2((float)AM_LDIN(io.iq + 2 * n) / 32767.0f, (float)AM_LDIN(io.iq + 2 * n + 1) / 32767.0f);
+}
+
+// 256-point forward FFT of w.fft in place, result in natural order (radix-2, lanes share the butterflies)
+AM_HD inline void fft256(AmWork &w, const AmTables &tb, Lanes L)
+{
+    for (int i = L.lane; i < FFT; i += L.n) {
+        const int r = tb.brev[i];
+        if (r > i) {
+            const float2 t = w.fft[i];
+            w.fft[i] = w.fft[r];
+            w.fft[r] = t;
+        }
+    }
+    AM_SYNC();
+    for (int half = 1; half < FFT; half <<= 1) {
+        const int tstep = FFT / (2 * half);
+        for (int b = L.lane; b < FFT / 2; b += L.n) {
+            const int grp = b / half, k = b - grp * half;
+            const int i0 = grp * 2 * half + k, i1 = i0 + half;
+            const float2 t = cmul(w.fft[i1], tb.tw[k * tstep]);
+            const float2 u = w.fft[i0];
+            w.fft[i0] = cadd(u, t);
+            w.fft[i1] = make_float2(u.x - t.x, u.y - t.y);
+        }
+        AM_SYNC();
+    }
+}
+
+// one OFDM symbol: rotate by the running phase, window, fold, shift by 121, FFT, fftshift (acquire.c:178-195,237-256)
+AM_HD inline void symbol_fft(AmWork &w, const AmTables &tb, Lanes L, int sym, int samperr, float2 &phase, float2 inc)
+{
+    const int offset = (FFT - CP) / 2;
+    // the phase recurrence is sequential: every lane runs it, each lane writes its share of the FFT input;
+    // the folded tail (j >= 256) adds onto entries written by the same lane (same residue of j mod 256 mod n?)
+    // - not in general, so the tail is added in a second sweep after a barrier
+    float2 ph = phase;
+    for (int j = 0; j < FFT; ++j) {
+        if ((j % L.n) == L.lane) {
+            const float2 sample = cmul(ph, w.buf[sym * SYM + j + samperr]);
+            w.fft[(j + offset) % FFT] = j < CP ? cscale(sample, tb.shape[j]) : sample;
+        }
+        ph = cmul(ph, inc);
+    }
+    AM_SYNC();
+    for (int j = FFT; j < SYM; ++j) {
+        if (((j - FFT) % L.n) == L.lane) {
+            const float2 sample = cmul(ph, w.buf[sym * SYM + j + samperr]);
+            const int idx = (j + offset) % FFT;
+            w.fft[idx] = cadd(w.fft[idx], cscale(sample, tb.shape[j]));
+        }
+        ph = cmul(ph, inc);
+    }
+    {
+        const float a = cabs2(ph);
+        phase = make_float2(ph.x / a, ph.y / a);
+    }
+    AM_SYNC();
+    fft256(w, tb, L);
+    for (int i = L.lane; i < FFT; i += L.n) w.spec[i] = w.fft[(i + FFT / 2) % FFT];       // fftshift, defines.h:123-138
+    AM_SYNC();
+}
+
+template <typename FixHeader>
+AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, const AmIo &io, Lanes L, FixHeader fix_header)
+{
+    int samperr = 0;
+    float angle, angle_diff;
+    const long long start = st.start;
+
+    if (st.state == ST_FINE) {                                                            // acquire.c:110-119
+        samperr = SYM / 2 + st.samperr;
+        st.samperr = 0;
+        angle_diff = -st.angle;
+        st.angle = 0;
+        angle = st.prev_angle + angle_diff;
+        st.prev_angle = angle;
+    } else {                                                                              // acquire.c:120-158
+        for (int i = L.lane; i < NACQ; i += L.n) {
+            int accr = 0, acci = 0;
+            auto at = [&](int pos, int c) -> int {
+                if (pos >= 0) return AM_LDIN(io.iq + 2 * (start + pos) + c);
+                return st.bp_hist[31 + pos][c];
+            };
+            for (int k = 1; k < 16; k++) {
+                accr = (short)(accr + (((at(i - 31 + k, 0) + at(i - 31 + 32 - k, 0)) * tb.bp_tap[k]) >> 15));
+                acci = (short)(acci + (((at(i - 31 + k, 1) + at(i - 31 + 32 - k, 1)) * tb.bp_tap[k]) >> 15));
+            }
+            accr = (short)(accr + ((at(i - 31 + 16, 0) * tb.bp_tap[16]) >> 15));
+            acci = (short)(acci + ((at(i - 31 + 16, 1) * tb.bp_tap[16]) >> 15));
+            w.buf[i] = make_float2((float)accr / 32767.0f, (float)acci / 32767.0f);
+        }
+        AM_SYNC();
+        for (int t = 0; t < 31; t++) {                                                    // every lane: private copy
+            st.bp_hist[t][0] = AM_LDIN(io.iq + 2 * (start + NACQ - 31 + t));
+            st.bp_hist[t][1] = AM_LDIN(io.iq + 2 * (start + NACQ - 31 + t) + 1);
+        }
+        for (int i = L.lane; i < SYM; i += L.n) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int j = 0; j < BLK; ++j) acc = cadd(acc, cmul(w.buf[i + j * SYM], cconj(w.buf[i + j * SYM + FFT])));
+            w.sums[i] = acc;
+        }
+        AM_SYNC();
+        float max_mag = -1.0f;
+        float2 max_v = make_float2(0.f, 0.f);
+        for (int i = 0; i < SYM; ++i) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int j = 0; j < CP; ++j) {
+                const float2 sv = w.sums[(i + j) % SYM];
+                v.x += (sv.x * tb.shape[j]) * tb.shape[j + FFT];
+                v.y += (sv.y * tb.shape[j]) * tb.shape[j + FFT];
+            }
+            const float mag = v.x * v.x + v.y * v.y;
+            if (mag > max_mag) {
+                max_mag = mag;
+                max_v = v;
+                samperr = (i + SYM - 15) % SYM;
+            }
+        }
+        angle_diff = carg(cmul(max_v, cexpj(-st.prev_angle)));
+        const float factor = (st.prev_angle != 0.0f) ? 0.25f : 1.0f;
+        angle = st.prev_angle + (angle_diff * factor);
+        st.prev_angle = angle;
+        set_state(st, io, L, ST_COARSE);
+    }
+    AM_SYNC();
+    for (int i = L.lane; i < NACQ; i += L.n) w.buf[i] = input_at(io, start + i);          // acquire.c:160-161
+    AM_SYNC();
+
+    angle = (float)((double)angle - 2 * PI * st.cfo);                                     // acquire.c:164-168
+    st.phase = cmul(st.phase, cexpj((float)(-(SYM / 2 - samperr)) * angle / (float)FFT));
+    float2 phase_increment = cexpj(angle / (float)FFT);
+
+    {   // AM only (acquire.c:170-235): carrier phase slope over the block, strongest bin while acquiring
+        float y = 0, sum_y = 0, sum_xy = 0, sum_x2 = 0;
+        float2 last_carrier = make_float2(0.f, 0.f);
+        float2 temp_phase = st.phase;
+        float mag_sums[2 * PIDS_OUTER + 1];
+        for (int j = 0; j < 2 * PIDS_OUTER + 1; j++) mag_sums[j] = 0;
+        for (int i = 0; i < BLK; ++i) {
+            symbol_fft(w, tb, L, i, samperr, temp_phase, phase_increment);
+            const float x = SYM * (i - (float)(BLK - 1) / 2);
+            if (i == 0) y = carg(w.spec[CENTER]);
+            else y += carg(cdiv(w.spec[CENTER], last_carrier));
+            last_carrier = w.spec[CENTER];
+            sum_y += y;
+            sum_xy += x * y;
+            sum_x2 += x * x;
+            if (st.state != ST_FINE)
+                for (int j = 0; j < 2 * PIDS_OUTER + 1; j++) mag_sums[j] += cabs2(w.spec[CENTER - PIDS_OUTER + j]);
+            AM_SYNC();
+        }
+        if (st.state != ST_FINE) {
+            float mm = -1.0f;
+            int max_index = -1;
+            for (int j = 0; j < 2 * PIDS_OUTER + 1; j++)
+                if (mag_sums[j] > mm) {
+                    mm = mag_sums[j];
+                    max_index = CENTER - PIDS_OUTER + j;
+                }
+            st.cfo += max_index - CENTER;
+        }
+        phase_increment = cmul(phase_increment, cexpj(-sum_xy / sum_x2));
+        st.phase = cmul(st.phase, cexpj((float)((double)(-sum_y / BLK + (sum_xy / sum_x2) * (BLK) * SYM / 2) - 0.06)));
+    }
+
+    for (int i = 0; i < BLK; ++i) {                                                       // acquire.c:237-257
+        symbol_fft(w, tb, L, i, samperr, st.phase, phase_increment);
+        for (int b = CENTER - MAX_IDX + L.lane; b <= CENTER + MAX_IDX; b += L.n) w.bins[b][i] = w.spec[b];   // sync_push
+        AM_SYNC();
+    }
+    sync_block(st, w, tb, io, L, fix_header);
+
+    const int keep = SYM + (SYM / 2 - samperr) + st.keep_extra;                           // acquire.c:259-262
+    st.keep_extra = 0;
+    st.start += NACQ - keep;
+    st.blocks_done++;
+}
+
+}  // namespace nbam

@@ -20,6 +20,8 @@
 #include "viterbi_chunk.cuh"
 #include "viterbi64.cuh"
 #include "front.cuh"
+#include "am.cuh"
+#include "am_tables.h"
 
 namespace nb {
 
@@ -363,6 +365,51 @@ __global__ void k_viterbi_test(const int8_t *in, uint8_t *out, uint2 *dec, int l
     }
 }
 
+// ===========================================================================
+// AM (hybrid MA1): one warp per stream runs the chain of am.cuh over every complete 33-symbol window
+// ===========================================================================
+struct AmFixHeader {
+    __host__ __device__ int operator()(uint8_t *pdu) const
+    {
+#if defined(__CUDA_ARCH__)
+        uint8_t blk[255];
+        return fix_header_96(pdu, blk);
+#else
+        (void)pdu;
+        return 1;
+#endif
+    }
+};
+
+__global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmState *ast, nbam::AmWork *aw,
+                                           const nbam::AmTables *tb, int max_blocks)
+{
+    const int s = blockIdx.x;
+    const nbam::Lanes L = { (int)threadIdx.x, 32 };
+    StreamState &fs = p.st[s];
+    nbam::AmState st = ast[s];
+    st.log_len = fs.log_len;                               // the host rewinds the log when it drains it
+    const nbam::AmIo io = { reinterpret_cast<const int16_t *>(p.iq + (size_t)s * d.in_stride), p.log + (size_t)s * d.log_cap,
+                            (unsigned)d.log_cap };
+    int nb_done = 0;
+    for (; nb_done < max_blocks; nb_done++) {
+        const long long avail = *reinterpret_cast<volatile long long *>(&fs.in_avail) / 2;    // cs16 complex samples
+        if (avail < st.start + nbam::NACQ) break;
+        nbam::process_window(st, aw[s], *tb, io, L, AmFixHeader());
+        __syncwarp();
+    }
+    __syncwarp();
+    if (L.lane == 0) {
+        ast[s] = st;
+        fs.log_len = st.log_len;
+        if (st.log_overflow) fs.log_overflow = 1;
+        fs.blocks_done = st.blocks_done;
+        fs.start = st.start;
+        fs.state = st.state;
+        if (nb_done) atomicAdd(&g_progress, (unsigned long long)nb_done);
+    }
+}
+
 __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -412,6 +459,9 @@ struct nrsc5b_engine {
     unsigned long long last_progress;
     std::vector<void *> allocs;
     int v64_ch;                        // chunk length of the fast P1 Viterbi (chosen from the stream count)
+    nbam::AmState *am_st;              // AM mode: per-stream state, work arrays, tables
+    nbam::AmWork *am_work;
+    nbam::AmTables *am_tb;
     int profiling;
     cudaEvent_t pev[5];
     double kernel_ms[4];
@@ -504,7 +554,8 @@ extern "C" const char *nrsc5b_version(void) { return "nrsc5_b200 0.1 (sm_100a)";
 
 extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
 {
-    if (!out || !cfg || cfg->nstreams <= 0 || cfg->mode != NRSC5B_MODE_FM) return NRSC5B_EINVAL;
+    if (!out || !cfg || cfg->nstreams <= 0 || (cfg->mode != NRSC5B_MODE_FM && cfg->mode != NRSC5B_MODE_AM)) return NRSC5B_EINVAL;
+    if (cfg->mode == NRSC5B_MODE_AM && !cfg->input_cs16) return NRSC5B_EINVAL;      // AM takes cs16 at 46 511.72 S/s
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) {
         fprintf(stderr, "nrsc5_b200: no usable CUDA device (the engine has no CPU path)\n");
@@ -518,6 +569,9 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->copy_stream = nullptr;
     e->iq_owned = nullptr;
     e->trim_scratch = nullptr;
+    e->am_st = nullptr;
+    e->am_work = nullptr;
+    e->am_tb = nullptr;
     e->avail_rows = nullptr;
     e->avail_rows_pos = 0;
     for (int i = 0; i < 64; i++) e->fence[i] = nullptr;
@@ -604,6 +658,16 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         DA(p3_flags, int, F * 4);
     }
     DA(log, uint8_t, (size_t)S * e->dims.log_cap);
+    if (cfg->mode == NRSC5B_MODE_AM) {
+        rc = dev_alloc(e, &e->am_st, (size_t)S);
+        if (!rc) rc = dev_alloc(e, &e->am_work, (size_t)S);
+        if (!rc) rc = dev_alloc(e, &e->am_tb, 1);
+        if (rc) { nrsc5b_destroy(e); return rc; }
+        nbam::AmTables *tb = new nbam::AmTables;
+        nbam::am_fill_tables(*tb);
+        cudaMemcpy(e->am_tb, tb, sizeof(*tb), cudaMemcpyHostToDevice);
+        delete tb;
+    }
     {
         // tables
         std::vector<float> shape(NSYM);
@@ -749,6 +813,17 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
     CK(cudaEventRecord(e->reset_done, e->stream));
     CK(cudaStreamWaitEvent(e->copy_stream, e->reset_done, 0));
     e->stats.kernel_launches += 1;
+    if (e->am_st) {
+        nbam::AmState z;
+        memset(&z, 0, sizeof(z));
+        nbam::am_reset_state(z);
+        for (int s = 0; s < S; s++) {
+            if (stream >= 0 && s != stream) continue;
+            CK(cudaMemcpyAsync(e->am_st + s, &z, sizeof(z), cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemsetAsync(e->am_work + s, 0, sizeof(nbam::AmWork), e->stream));
+        }
+        CK(cudaStreamSynchronize(e->stream));              // `z` lives on this stack frame
+    }
     for (int s = 0; s < S; s++) {
         if (stream >= 0 && s != stream) continue;
         e->pushed[s] = 0;
@@ -780,10 +855,11 @@ static int publish_avail(nrsc5b_engine *e, int s, cudaStream_t on)
     return 0;
 }
 
-__global__ void k_trim_state(DevPtrs p, int s, long long drop)
+__global__ void k_trim_state(DevPtrs p, int s, long long drop, nbam::AmState *ast)
 {
     p.st[s].start -= drop;
     p.st[s].in_avail -= 2 * drop;
+    if (ast) ast[s].start -= drop;
 }
 
 // Discards the samples a stream's window has moved past (everything more than 64 decimated samples before
@@ -809,7 +885,7 @@ static int trim_stream(nrsc5b_engine *e, int s)
     }
     CK(cudaMemcpyAsync(e->trim_scratch, base + off, rem, cudaMemcpyDeviceToDevice, e->stream));
     CK(cudaMemcpyAsync(base, e->trim_scratch, rem, cudaMemcpyDeviceToDevice, e->stream));
-    k_trim_state<<<1, 1, 0, e->stream>>>(e->dp, s, drop);
+    k_trim_state<<<1, 1, 0, e->stream>>>(e->dp, s, drop, e->am_st);
     e->pushed[s] -= 2 * drop;
     CK(cudaStreamSynchronize(e->stream));
     return 0;
@@ -959,6 +1035,11 @@ constexpr int BLOCKS_PER_PASS = 16;
 
 static int launch_pass(nrsc5b_engine *e)
 {
+    if (e->am_st) {                                        // AM: one kernel does the whole chain, window after window
+        k_am<<<e->dims.nstreams, 32, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, 1 << 20);
+        e->stats.kernel_launches += 1;
+        return 0;
+    }
     const bool prof = e->profiling != 0;
     if (prof) cudaEventRecord(e->pev[0], e->stream);
     k_stream<<<e->dims.nstreams, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS);

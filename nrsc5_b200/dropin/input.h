@@ -34,6 +34,7 @@ typedef struct input_t
 
     struct nrsc5b_engine *engine;       /* one stream on one GPU */
     int engine_cs16;                    /* the format that engine was built for */
+    int engine_am;                      /* ... and the mode */
     uint8_t *records;                   /* drained record stream of the last push */
     size_t records_cap;
     uint8_t *bits;                      /* one bit per byte, as frame_push()/pids_frame_push() take them */

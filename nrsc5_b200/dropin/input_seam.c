@@ -122,7 +122,14 @@ static void replay(input_t *st, const uint8_t *rec, size_t n)
 
 static void engine_open(input_t *st, int cs16)
 {
-    if (st->engine && st->engine_cs16 == cs16)
+    const int am = st->radio->mode == NRSC5_MODE_AM;
+    if (am && !cs16)
+    {
+        /* AM from cu8 needs the five-stage /32 decimator of src/input.c:71-89, which is not on the GPU yet */
+        fprintf(stderr, "libnrsc5 (B200): AM takes cs16 samples at 46511.72 S/s (nrsc5_pipe_samples_cs16)\n");
+        abort();
+    }
+    if (st->engine && st->engine_cs16 == cs16 && st->engine_am == am)
         return;
     /* the reference accepts cu8 and cs16 pushes on one handle; the engine is built for one format, so a
      * change of format starts a new engine (= input_reset) */
@@ -133,13 +140,14 @@ static void engine_open(input_t *st, int cs16)
     const char *dev = getenv("NRSC5_B200_DEVICE");
     cfg.device = dev ? atoi(dev) : 0;
     cfg.nstreams = 1;
-    cfg.mode = NRSC5B_MODE_FM;
+    cfg.mode = am ? NRSC5B_MODE_AM : NRSC5B_MODE_FM;
     cfg.input_capacity = INPUT_CAPACITY;
     cfg.log_capacity = RECORDS_CAPACITY;
     cfg.input_cs16 = cs16;
     int rc = nrsc5b_create(&st->engine, &cfg);
     if (rc) fail("nrsc5b_create", rc);
     st->engine_cs16 = cs16;
+    st->engine_am = am;
 }
 
 static void run_and_replay(input_t *st)
@@ -175,11 +183,6 @@ void input_push_cs16(input_t *st, const int16_t *buf, const uint32_t len)
 {
     /* input.c:119-124: FM samples that are already at 744 187.5 S/s; len counts int16 values */
     assert(len % 2 == 0);
-    if (st->radio->mode != NRSC5_MODE_FM)
-    {
-        fprintf(stderr, "libnrsc5 (B200): AM is not on the accelerated path yet\n");
-        abort();
-    }
     engine_open(st, 1);
     uint32_t done = 0;
     while (done < len)
@@ -224,11 +227,8 @@ void input_init(input_t *st, nrsc5_t *radio, output_t *output)
 
 void input_set_mode(input_t *st)
 {
-    if (st->radio->mode != NRSC5_MODE_FM)
-    {
-        fprintf(stderr, "libnrsc5 (B200): AM is not on the accelerated path yet\n");
-        abort();
-    }
+    /* acquire_set_mode + input_reset (input.c:159-163): AM and FM use different engines */
+    engine_open(st, st->radio->mode == NRSC5_MODE_AM ? 1 : st->engine_cs16);
     input_reset(st);
 }
 

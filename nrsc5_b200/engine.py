@@ -139,10 +139,13 @@ class Engine:
     """
 
     def __init__(self, nstreams: int, input_capacity: int, device: int = 0, log_capacity: int = 1 << 20,
-                 emit_soft: bool = False, input_cs16: bool = False):
+                 emit_soft: bool = False, input_cs16: bool = False, mode: str = "fm"):
         self._L = load_library()
         self._h = ctypes.c_void_p()
-        cfg = _Config(device, nstreams, 0, input_capacity, log_capacity, int(emit_soft), int(input_cs16))
+        if mode not in ("fm", "am"):
+            raise EngineError("mode must be 'fm' or 'am'")
+        am = mode == "am"                        # AM: hybrid MA1, cs16 at 46 511.72 S/s
+        cfg = _Config(device, nstreams, int(am), input_capacity, log_capacity, int(emit_soft), int(input_cs16 or am))
         _check(self._L.nrsc5b_create(ctypes.byref(self._h), ctypes.byref(cfg)), "nrsc5b_create")
         self.nstreams = nstreams
         self._log_cap = log_capacity + 64
