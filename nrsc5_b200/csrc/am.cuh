@@ -21,6 +21,8 @@
 
 #if defined(__CUDA_ARCH__)
 #define AM_SYNC() __syncwarp()
+#elif defined(AM_HOST_SYNC)
+#define AM_SYNC() AM_HOST_SYNC()          // tests/am_host.cu: lanes emulated by host threads meet at a barrier
 #else
 #define AM_SYNC() ((void)0)
 #endif
