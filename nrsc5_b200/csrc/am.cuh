@@ -160,11 +160,11 @@ AM_HD inline void set_state(AmState &st, const AmIo &io, Lanes L, int ns)       
     if (st.state == ST_FINE) log_reserve(st, io, L, REC_LOST_SYNC, 0);
     if (ns == ST_FINE) {
         float fo = (float)(((double)st.prev_angle - 2 * PI * st.cfo) * 46511.71875 / (2 * PI * FFT));
-        uint8_t *w = log_reserve(st, io, L, REC_SYNC, 8);
+        uint8_t *w = log_reserve(st, io, L, REC_SYNC, 24);
         if (w && L.lane == 0) {
             memcpy(w, &fo, 4);
-            int32_t psmi = st.psmi;
-            memcpy(w + 4, &psmi, 4);
+            const int32_t v[5] = { st.psmi, st.pli, st.hppi, st.aabi, st.rdbi };    // nrsc5_report_sync, input.c:184
+            memcpy(w + 4, v, 20);
         }
     }
     st.state = ns;

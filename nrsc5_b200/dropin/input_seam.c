@@ -68,13 +68,14 @@ static void replay(input_t *st, const uint8_t *rec, size_t n)
         case NRSC5B_REC_SYNC:                        /* sync.c:403-409, input.c:180-186 */
         {
             float freq_offset;
-            int psmi;
+            int psmi, flags[4] = { -1, -1, -1, -1 };     /* pli, hppi, aabi, rdbi: AM only (sync.c:230-236) */
             memcpy(&freq_offset, pay, 4);
             memcpy(&psmi, pay + 4, 4);
+            if (plen >= 24) memcpy(flags, pay + 8, 16);
             if (st->sync_state == SYNC_STATE_FINE)
                 nrsc5_report_lost_sync(st->radio);
             st->sync_state = SYNC_STATE_FINE;
-            nrsc5_report_sync(st->radio, freq_offset, psmi, -1, -1, -1, -1);
+            nrsc5_report_sync(st->radio, freq_offset, psmi, flags[0], flags[1], flags[2], flags[3]);
             pids_init(&st->pids, st);                /* decode_reset, decode.c:556-565 */
             frame_reset(&st->frame);
             break;

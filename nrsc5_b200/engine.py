@@ -108,8 +108,9 @@ def parse_records(raw: bytes):
         elif ty == REC_PIDS:
             rec = {"bits": bytes(pay[:10])}
         elif ty == REC_SYNC:
-            f, psmi = struct.unpack("<fi", pay)
-            rec = {"freq_offset": f, "psmi": psmi}
+            f, psmi = struct.unpack_from("<fi", pay)
+            flags = struct.unpack_from("<4i", pay, 8) if len(pay) >= 24 else (-1, -1, -1, -1)   # AM: pli, hppi, aabi, rdbi
+            rec = {"freq_offset": f, "psmi": psmi, "flags": list(flags)}
         elif ty == REC_LOST_SYNC:
             rec = {}
         elif ty == REC_MER:

@@ -488,7 +488,7 @@ static void set_state(orc_t *o, int ns)
         olog_put(&o->log, ORC_REC_LOST_SYNC, NULL, 0, NULL, 0);
     if (ns == ST_FINE) {
         float fo = (o->prev_angle - 2 * M_PI * o->cfo) * 744187.5 / (2 * M_PI * NFFT);
-        struct { float f; int32_t psmi; } p = { fo, o->psmi };
+        struct { float f; int32_t v[5]; } p = { fo, { o->psmi, -1, -1, -1, -1 } };   /* FM leaves pli..rdbi at sync_reset's -1, sync.c:821-824 */
         olog_put(&o->log, ORC_REC_SYNC, &p, sizeof(p), NULL, 0);
     }
     o->state = ns;

@@ -24,7 +24,7 @@ extern "C" {
 enum {
     ORC_REC_FRAME = 1,     /* u32 lc, u32 nbits, bits packed MSB-first  */
     ORC_REC_PIDS = 2,      /* 10 bytes                                  */
-    ORC_REC_SYNC = 3,      /* f32 freq_offset, i32 psmi                 */
+    ORC_REC_SYNC = 3,      /* f32 freq_offset, i32 psmi, pli, hppi, aabi, rdbi */
     ORC_REC_LOST_SYNC = 4,
     ORC_REC_MER = 5,       /* f32 lower, f32 upper                      */
     ORC_REC_BER = 6,       /* f32 cber                                  */

@@ -137,7 +137,7 @@ static void set_state(orc_am_t *o, int ns)            /* input.c:172-188 */
         alog_put(&o->log, ORC_REC_LOST_SYNC, NULL, 0, NULL, 0);
     if (ns == ST_FINE) {
         float fo = (o->prev_angle - 2 * M_PI * o->cfo) * 46511.71875 / (2 * M_PI * FFT_AM);
-        struct { float f; int32_t psmi; } p = { fo, o->psmi };
+        struct { float f; int32_t v[5]; } p = { fo, { o->psmi, o->pli, o->hppi, o->aabi, o->rdbi } };
         alog_put(&o->log, ORC_REC_SYNC, &p, sizeof(p), NULL, 0);
     }
     o->state = ns;

@@ -27,7 +27,7 @@
 enum {
     REC_FRAME = 1,     /* payload: u32 lc, u32 nbits, bits packed MSB-first       */
     REC_PIDS = 2,      /* payload: 10 bytes (80 bits packed MSB-first)            */
-    REC_SYNC = 3,      /* payload: f32 freq_offset, i32 psmi                      */
+    REC_SYNC = 3,      /* payload: f32 freq_offset, i32 psmi, pli, hppi, aabi, rdbi */
     REC_LOST_SYNC = 4, /* payload: none                                           */
     REC_MER = 5,       /* payload: f32 lower, f32 upper                           */
     REC_BER = 6,       /* payload: f32 cber                                       */
@@ -115,7 +115,8 @@ static void on_event(const nrsc5_event_t *evt, void *opaque)
     (void)opaque;
     switch (evt->event) {
     case NRSC5_EVENT_SYNC: {
-        struct { float f; int32_t psmi; } p = { evt->sync.freq_offset, evt->sync.psmi };
+        struct { float f; int32_t v[5]; } p = { evt->sync.freq_offset,
+            { evt->sync.psmi, evt->sync.pli, evt->sync.hppi, evt->sync.aabi, evt->sync.rdbi } };
         log_put(REC_SYNC, &p, sizeof(p), NULL, 0);
         break;
     }

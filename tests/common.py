@@ -64,7 +64,8 @@ def summarize(log):
         elif ty == reftap.REC_PIDS:
             seq.append(["P", fnv1a32(p["bits"])])
         elif ty == reftap.REC_SYNC:
-            seq.append(["S", round(p["freq_offset"], 3), p["psmi"]])
+            flags = p.get("flags", [-1] * 4)
+            seq.append(["S", round(p["freq_offset"], 3), p["psmi"]] + ([] if flags == [-1] * 4 else list(flags)))
         elif ty == reftap.REC_LOST_SYNC:
             seq.append(["L"])
         elif ty == reftap.REC_MER:

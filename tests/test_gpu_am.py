@@ -39,7 +39,7 @@ def digest(recs):
         elif t == eng.REC_PIDS:
             out.append(("P", r["bits"]))
         elif t == eng.REC_SYNC:
-            out.append(("S", r["psmi"]))
+            out.append(("S", r["psmi"], tuple(r["flags"])))
         elif t == eng.REC_LOST_SYNC:
             out.append(("L",))
         elif t == eng.REC_BER:
@@ -55,7 +55,7 @@ def oracle_digest(log):
         elif t == reftap.REC_PIDS:
             out.append(("P", p["bits"]))
         elif t == reftap.REC_SYNC:
-            out.append(("S", p["psmi"]))
+            out.append(("S", p["psmi"], tuple(p["flags"])))
         elif t == reftap.REC_LOST_SYNC:
             out.append(("L",))
         elif t == reftap.REC_BER:
