@@ -1,4 +1,4 @@
-"""Synthetic NRSC-5 AM (hybrid MA1) captures, cs16 I/Q at 46 511.72 S/s, with known L1 PDUs.
+"""Synthetic NRSC-5 AM (hybrid MA1, all-digital MA3) captures, cs16 I/Q at 46 511.72 S/s, with known L1 PDUs.
 
 The reference ships no modulator; like synth.py for FM this inverts the receive chain stage by stage
 (recipe: SURVEY.md §8(d) "AM MA1 recipe", every step derived from the decoder):
@@ -12,6 +12,10 @@ The reference ships no modulator; like synth.py for FM this inverts the receive 
   -> constellations of sync.c:37-88, training symbols of sync.c:673-710, reference carrier of sync.c:208-236,
   complementary lower sideband (sync.c:616-633) -> 256-point OFDM with 14-sample prefix and the receiver's
   pulse shape, circularly advanced by 121 samples (acquire.c:239-248), on top of a strong carrier.
+
+MA3 (make_am_ma3): the primary sidebands move to the inner partitions, P3 (30 000 bit, E1, punctured like P1)
+is split like P1 into backup/main sets carried by 64-QAM secondary (upper) and tertiary (lower) partitions, the
+PIDS carriers sit at -27/+27 and nothing is complementary (sync.c:624,670-671,694-696; decode.c:117-141).
 
 Test infrastructure for the AM rows of the scope table; pure numpy.
 """
@@ -33,6 +37,7 @@ BLOCKS_PER_FRAME = 8
 CENTER = 128
 P1_BITS = 3750
 P3_BITS = 24000
+P3_BITS_MA3 = 30000
 PIDS_BITS = 80
 GENS_E1 = (0o561, 0o657, 0o711)
 GENS_E2 = (0o561, 0o753, 0o711)     # also E3 (PIDS)
@@ -68,6 +73,11 @@ def _ma1_index_sets():
         "el": table(12000, lambda n: (3 * n + n // 3000) % 8, lambda n: (n + n // 6000) % 750, lambda n: n % 2),
         "eu": table(24000, lambda n: (3 * n + n // 3000 + 2 * (n // 12000)) % 8, lambda n: (n + n // 6000) % 750,
                     lambda n: n % 4),
+        # MA3 (decode.c:117-141): P3's backup/main sets in the tertiary (ebl, eml) and secondary (ebu, emu) matrices
+        "ebl": table(18000, lambda n: (3 * n + 3) % 8, lambda n: (n + n // 3000 + 3) % 750, lambda n: n % 3),
+        "eml": table(18000, lambda n: (3 * n + 3) % 8, lambda n: (n + n // 3000 + 3) % 750, lambda n: 3 + n % 3),
+        "ebu": table(18000, lambda n: (3 * n) % 8, lambda n: (n + n // 3000 + 2) % 750, lambda n: n % 3),
+        "emu": table(18000, lambda n: (3 * n) % 8, lambda n: (n + n // 3000 + 2) % 750, lambda n: 3 + n % 3),
     }
 
 
@@ -112,12 +122,15 @@ def _encode(bits, gens, keep):
     return coded[mask]
 
 
-def ref_bits_am(bc: int, psmi: int = 1) -> np.ndarray:
+def ref_bits_am(bc: int, psmi: int = 1, pli: int = 0, hppi: int = 0, aabi: int = 0, rdbi: int = 0) -> np.ndarray:
     """32 bits of the AM reference subcarrier for block `bc` (find_block_am, reference src/sync.c:208-236):
     fixed pattern, even-parity groups, block count at 17..19, service mode at 26..30."""
     d = np.zeros(32, dtype=np.uint8)
     for i in (1, 2, 5, 9, 21, 22):
         d[i] = 1
+    d[7], d[11], d[12], d[15] = pli, hppi, aabi, rdbi
+    d[8] = d[7]
+    d[13] = d[10] ^ d[11] ^ d[12]
     d[17], d[18], d[19] = (bc >> 2) & 1, (bc >> 1) & 1, bc & 1
     d[20] = d[15] ^ d[16] ^ d[17] ^ d[18] ^ d[19]
     for k, sh in zip(range(26, 31), (4, 3, 2, 1, 0)):
@@ -134,25 +147,42 @@ class AmCapture:
     pids_frames: list = field(default_factory=list)      # uint8[80] per transmitted block
 
 
+def make_am_ma3(**kw) -> AmCapture:
+    """AM all-digital MA3 capture (see make_am_ma1 for the arguments)."""
+    return make_am_ma1(psmi=2, **kw)
+
+
 def make_am_ma1(nframes: int = 10, seed: int = 1234, lead_in: int = 500, carrier: float = 10000.0, unit: float = 50.0,
-                noise_lsb: float = 0.0, noise_seed: int = 5, cfo_hz: float = 0.0) -> AmCapture:
-    """AM hybrid MA1 capture of `nframes` transmitted L1 frames (8 blocks each).  The receiver needs the 0x5670
+                noise_lsb: float = 0.0, noise_seed: int = 5, cfo_hz: float = 0.0, psmi: int = 1,
+                flags: tuple = (0, 0, 0, 0)) -> AmCapture:
+    """AM hybrid MA1 (psmi 1) or all-digital MA3 (psmi 2) capture of `nframes` transmitted L1 frames (8 blocks each).  The receiver needs the 0x5670
     block-count run to lock, then four frames before it decodes (decode.c:512,569), and the main bits of a
     frame travel three frames ahead of its backup bits: frame F comes out when frames F-3 .. F+1 were received."""
     rng = np.random.default_rng(seed)
     idx = _ma1_index_sets()
     cap = AmCapture(cs16=None)
     nlog = nframes + 3
+    frng = np.random.default_rng(seed + 77)                          # MA3 outer-partition filler
     p1 = [[_frame_bits(rng, P1_BITS, 22, 120, 160) for _ in range(8)] for _ in range(nlog)]
-    p3 = [_frame_bits(rng, P3_BITS, 24, 120, 992) for _ in range(nlog)]
+    ma3 = psmi == 2
+    assert psmi in (1, 2)
+    if ma3:
+        p3 = [_frame_bits(rng, P3_BITS_MA3, 24, 120, 1240) for _ in range(nlog)]     # frame.c:676-680
+    else:
+        p3 = [_frame_bits(rng, P3_BITS, 24, 120, 992) for _ in range(nlog)]
     keep_e1 = (1, 0, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1)
     sets = []
     for f in range(nlog):
         c1 = np.concatenate([_encode(b, GENS_E1, keep_e1) for b in p1[f]])          # 72000
-        c3 = _encode(p3[f], GENS_E2, (1, 0, 1, 1, 0, 0))                             # 36000
         bl, ml, bu, mu = _split_p1(c1)
-        el, eu = _split_p3(c3)
-        sets.append(dict(bl=bl, ml=ml, bu=bu, mu=mu, el=el, eu=eu))
+        if ma3:
+            c3 = _encode(p3[f], GENS_E1, keep_e1)                                    # 72000 (decode.c:214-229)
+            ebl, eml, ebu, emu = _split_p1(c3)
+            sets.append(dict(bl=bl, ml=ml, bu=bu, mu=mu, ebl=ebl, eml=eml, ebu=ebu, emu=emu))
+        else:
+            c3 = _encode(p3[f], GENS_E2, (1, 0, 1, 1, 0, 0))                         # 36000
+            el, eu = _split_p3(c3)
+            sets.append(dict(bl=bl, ml=ml, bu=bu, mu=mu, el=el, eu=eu))
         cap.p1_frames[f] = p1[f]
         cap.p3_frames[f] = p3[f]
 
@@ -174,8 +204,12 @@ def make_am_ma1(nframes: int = 10, seed: int = 1234, lead_in: int = 500, carrier
             return m
         pl = fill([("bl", x), ("ml", x + 3)], (8, 32, 25))
         pu = fill([("bu", x), ("mu", x + 3)], (8, 32, 25))
-        tt = fill([("el", x)], (8, 32, 25))
-        ss = fill([("eu", x)], (8, 32, 25))
+        if ma3:
+            tt = fill([("ebl", x), ("eml", x + 3)], (8, 32, 25))
+            ss = fill([("ebu", x), ("emu", x + 3)], (8, 32, 25))
+        else:
+            tt = fill([("el", x)], (8, 32, 25))
+            ss = fill([("eu", x)], (8, 32, 25))
         for bc in range(8):
             # PIDS (decode.c:474-500)
             pb = rng.integers(0, 2, PIDS_BITS, dtype=np.uint8)
@@ -195,29 +229,54 @@ def make_am_ma1(nframes: int = 10, seed: int = 1234, lead_in: int = 500, carrier
             q16 = lambda c: lev16[c & 3] + 1j * lev16[c >> 2]
             qpsk = lambda c: ((c & 1) - 0.5) + 1j * ((c >> 1) - 0.5)
             up = np.zeros((BLKSZ, 82), dtype=np.complex128)            # wanted value of upper carrier CENTER + i
-            lo = np.zeros((BLKSZ, 82), dtype=np.complex128)            # wanted (mirrored) value of CENTER - i, primary only
-            d = ref_bits_am(bc)
+            lo = np.zeros((BLKSZ, 82), dtype=np.complex128)            # wanted (mirrored) value of CENTER - i
+            d = ref_bits_am(bc, psmi, *flags)
             up[:, 1] = 1.5j * (2.0 * d - 1.0)
-            up[:, 27] = q16(sb[:, 0])
-            up[:, 53] = q16(sb[:, 1])
-            up[[8, 24], 27] = 1.5 - 0.5j                                # PIDS training (sync.c:673-674)
-            up[[8, 24], 53] = 1.5 - 0.5j
             cols = np.arange(25)
-            up[:, 57:82] = q64(pu[bc])
-            lo[:, 57:82] = q64(pl[bc])
-            up[:, 28:53] = q16(ss[bc])
-            up[:, 2:27] = qpsk(tt[bc])
-            for col in cols:                                            # training rows (sync.c:699-710)
-                for tr in ((5 + 11 * col) % 32, (21 + 11 * col) % 32):
-                    up[tr, 57 + col] = 2.5 - 2.5j
-                    lo[tr, 57 + col] = 2.5 - 2.5j
-                    up[tr, 28 + col] = 1.5 - 0.5j
-                    up[tr, 2 + col] = -0.5 + 0.5j
             i = np.arange(1, 82)
-            S[:, CENTER + i] = up[:, 1:]
-            # lower sideband: the receiver takes -conj of it and, up to index 53, adds it to the upper one
-            S[:, CENTER - i[:53]] = -np.conj(up[:, 1:54])
-            S[:, CENTER - i[56:]] = -np.conj(lo[:, 57:])
+            if not ma3:
+                up[:, 27] = q16(sb[:, 0])
+                up[:, 53] = q16(sb[:, 1])
+                up[[8, 24], 27] = 1.5 - 0.5j                            # PIDS training (sync.c:673-674)
+                up[[8, 24], 53] = 1.5 - 0.5j
+                up[:, 57:82] = q64(pu[bc])
+                lo[:, 57:82] = q64(pl[bc])
+                up[:, 28:53] = q16(ss[bc])
+                up[:, 2:27] = qpsk(tt[bc])
+                for col in cols:                                        # training rows (sync.c:699-710)
+                    for tr in ((5 + 11 * col) % 32, (21 + 11 * col) % 32):
+                        up[tr, 57 + col] = 2.5 - 2.5j
+                        lo[tr, 57 + col] = 2.5 - 2.5j
+                        up[tr, 28 + col] = 1.5 - 0.5j
+                        up[tr, 2 + col] = -0.5 + 0.5j
+                S[:, CENTER + i] = up[:, 1:]
+                # lower sideband: the receiver takes -conj of it and, up to index 53, adds it to the upper one
+                S[:, CENTER - i[:53]] = -np.conj(up[:, 1:54])
+                S[:, CENTER - i[56:]] = -np.conj(lo[:, 57:])
+            else:
+                # MA3: PIDS at -27 / +27, primary at the inner partitions, secondary = upper middle, tertiary =
+                # lower middle, all 64-QAM with 2.5-2.5j training; the outer partitions are not received
+                lo[:, 27] = q16(sb[:, 0])
+                up[:, 27] = q16(sb[:, 1])
+                lo[[8, 24], 27] = 1.5 - 0.5j
+                up[[8, 24], 27] = 1.5 - 0.5j
+                up[:, 2:27] = q64(pu[bc])
+                lo[:, 2:27] = q64(pl[bc])
+                up[:, 28:53] = q64(ss[bc])
+                lo[:, 28:53] = q64(tt[bc])
+                for col in cols:
+                    for tr in ((5 + 11 * col) % 32, (21 + 11 * col) % 32):
+                        for a in (up, lo):
+                            a[tr, 2 + col] = 2.5 - 2.5j
+                            a[tr, 28 + col] = 2.5 - 2.5j
+                lo[:, 1] = up[:, 1]                                     # until the mode is known the receiver adds the sidebands
+                # the receiver's coarse timing search listens only at |index| 56..85 (band-pass of acquire.c:63-96,
+                # made for the hybrid primary sidebands) and never demodulates those carriers in MA3: unrelated
+                # 64-QAM filler there lets it lock as quickly as on a hybrid signal
+                up[:, 57:82] = q64(frng.integers(0, 64, (BLKSZ, 25)))
+                lo[:, 57:82] = q64(frng.integers(0, 64, (BLKSZ, 25)))
+                S[:, CENTER + i] = up[:, 1:]
+                S[:, CENTER - i] = -np.conj(lo[:, 1:])
             X = np.zeros((BLKSZ, FFT), dtype=np.complex128)
             X[:, k_of_bin % FFT] = S * adv[None, :]
             y = np.fft.ifft(X, axis=1) * FFT * unit

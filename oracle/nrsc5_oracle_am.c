@@ -1,12 +1,12 @@
-/* nrsc5_oracle_am — plain-C CPU restatement of the NRSC-5 AM (hybrid MA1) physical-layer receive chain of
+/* nrsc5_oracle_am — plain-C CPU restatement of the NRSC-5 AM (hybrid MA1, all-digital MA3) physical-layer receive chain of
  * theori-io/nrsc5 (reference @ a5c0972), cs16 input at 46 511.72 S/s.
  *
  * TEST INFRASTRUCTURE ONLY (see nrsc5_oracle.h): the checker for the AM rows of the scope table (SURVEY §8
  * a21).  Pinned by tests/test_oracle_am.py against the UNMODIFIED reference in oracle/_ref/libnrsc5_ref.so
- * (PDUs, events and BER bit-identical on the synthetic MA1 captures of nrsc5_b200/synth_am.py).
+ * (PDUs, events and BER bit-identical on the synthetic MA1 and MA3 captures of nrsc5_b200/synth_am.py).
  *
- * Each stage cites the reference file:line it follows.  Service mode MA3 (all digital) is not restated:
- * a stream that announces it is decoded as MA1 would be, which is wrong - the tests only use MA1.
+ * Each stage cites the reference file:line it follows.  As in the reference every service mode other than
+ * MA3 (psmi 2) is decoded as MA1.
  */
 #include <complex.h>
 #include <math.h>
@@ -36,6 +36,8 @@ typedef float complex cf;
 #define PW_AM 25
 #define P1_LEN_AM 3750
 #define P3_LEN_MA1 24000
+#define P3_LEN_MA3 30000
+#define MODE_MA3 2                              /* SERVICE_MODE_MA3, reference src/defines.h:39 */
 #define PIDS_LEN 80
 #define DIVERSITY (18000 * 3)
 #define ST_NONE 0
@@ -88,9 +90,10 @@ struct orc_am {
     /* decode (reference src/decode.h:19-62) */
     uint8_t buffer_pl[PW_AM * BLK * 8], buffer_pu[PW_AM * BLK * 8], buffer_s[PW_AM * BLK * 8], buffer_t[PW_AM * BLK * 8];
     uint8_t bl[18000], bu[18000], ml[DIVERSITY + 18000], mu[DIVERSITY + 18000], el[12000], eu[24000];
-    uint8_t p1_am[8 * 9000], p3_am[36000];
-    int8_t vit_p1[8 * P1_LEN_AM * 3], vit_p3[P3_LEN_MA1 * 3], vit_pids[PIDS_LEN * 3];
-    uint8_t out_p1[P1_LEN_AM + 8], out_p3[P3_LEN_MA1 + 8], out_pids[PIDS_LEN + 8];
+    uint8_t ebl[18000], ebu[18000], eml[DIVERSITY + 18000], emu[DIVERSITY + 18000];      /* MA3, decode.h:49-52 */
+    uint8_t p1_am[8 * 9000], p3_am[72000];
+    int8_t vit_p1[8 * P1_LEN_AM * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
+    uint8_t out_p1[P1_LEN_AM + 8], out_p3[P3_LEN_MA3 + 8], out_pids[PIDS_LEN + 8];
     int am_errors, am_diversity_wait;
 };
 
@@ -153,8 +156,9 @@ static int bit_map(const uint8_t *matrix, int b, int k, int p)            /* dec
     return (matrix[PW_AM * (b * BLK + row) + col] >> p) & 1;
 }
 
-static void interleaver_ma1(orc_am_t *o)                                  /* decode.c:74-231, MA1 branch */
+static void interleaver_ma1(orc_am_t *o)                                  /* decode.c:74-231 */
 {
+    const int ma3 = o->psmi == MODE_MA3;
     static const int bl_delay[] = { 2, 1, 5 }, ml_delay[] = { 11, 6, 7 }, bu_delay[] = { 10, 8, 9 }, mu_delay[] = { 4, 3, 0 };
     static const int el_delay[] = { 0, 1 }, eu_delay[] = { 2, 3, 5, 4 };
     for (int n = 0; n < 18000; n++) {
@@ -163,10 +167,19 @@ static void interleaver_ma1(orc_am_t *o)                                  /* dec
         o->bu[n] = (uint8_t)bit_map(o->buffer_pu, n / 2250, (n + n / 750) % 750, n % 3);
         o->mu[DIVERSITY + n] = (uint8_t)bit_map(o->buffer_pu, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
     }
-    for (int n = 0; n < 12000; n++)
-        o->el[n] = (uint8_t)bit_map(o->buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2);
-    for (int n = 0; n < 24000; n++)
-        o->eu[n] = (uint8_t)bit_map(o->buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4);
+    if (!ma3) {
+        for (int n = 0; n < 12000; n++)
+            o->el[n] = (uint8_t)bit_map(o->buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2);
+        for (int n = 0; n < 24000; n++)
+            o->eu[n] = (uint8_t)bit_map(o->buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4);
+    } else {
+        for (int n = 0; n < 18000; n++) {                                  /* decode.c:119-140 */
+            o->ebl[n] = (uint8_t)bit_map(o->buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, n % 3);
+            o->eml[DIVERSITY + n] = (uint8_t)bit_map(o->buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
+            o->ebu[n] = (uint8_t)bit_map(o->buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, n % 3);
+            o->emu[DIVERSITY + n] = (uint8_t)bit_map(o->buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
+        }
+    }
     for (int i = 0; i < 6000; i++) {
         for (int j = 0; j < 3; j++) {
             o->p1_am[i * 12 + bl_delay[j]] = o->bl[i * 3 + j];
@@ -174,20 +187,40 @@ static void interleaver_ma1(orc_am_t *o)                                  /* dec
             o->p1_am[i * 12 + bu_delay[j]] = o->bu[i * 3 + j];
             o->p1_am[i * 12 + mu_delay[j]] = o->mu[i * 3 + j];
         }
-        for (int j = 0; j < 2; j++) o->p3_am[i * 6 + el_delay[j]] = o->el[i * 2 + j];
-        for (int j = 0; j < 4; j++) o->p3_am[i * 6 + eu_delay[j]] = o->eu[i * 4 + j];
+        if (!ma3) {
+            for (int j = 0; j < 2; j++) o->p3_am[i * 6 + el_delay[j]] = o->el[i * 2 + j];
+            for (int j = 0; j < 4; j++) o->p3_am[i * 6 + eu_delay[j]] = o->eu[i * 4 + j];
+        } else {
+            for (int j = 0; j < 3; j++) {                                  /* decode.c:163-170 */
+                o->p3_am[i * 12 + bl_delay[j]] = o->ebl[i * 3 + j];
+                o->p3_am[i * 12 + ml_delay[j]] = o->eml[i * 3 + j];
+                o->p3_am[i * 12 + bu_delay[j]] = o->ebu[i * 3 + j];
+                o->p3_am[i * 12 + mu_delay[j]] = o->emu[i * 3 + j];
+            }
+        }
     }
     memmove(o->ml, o->ml + 18000, DIVERSITY);
     memmove(o->mu, o->mu + 18000, DIVERSITY);
+    if (ma3) {
+        memmove(o->eml, o->eml + 18000, DIVERSITY);
+        memmove(o->emu, o->emu + 18000, DIVERSITY);
+    }
     int off = 0;
     for (int i = 0; i < 8 * P1_LEN_AM * 3; i++) {
         const int r = i % 15;
         o->vit_p1[i] = (r == 1 || r == 4 || r == 7) ? 0 : (o->p1_am[off++] ? 1 : -1);
     }
     off = 0;
-    for (int i = 0; i < P3_LEN_MA1 * 3; i++) {
-        const int r = i % 6;
-        o->vit_p3[i] = (r == 1 || r == 4 || r == 5) ? 0 : (o->p3_am[off++] ? 1 : -1);
+    if (!ma3) {
+        for (int i = 0; i < P3_LEN_MA1 * 3; i++) {
+            const int r = i % 6;
+            o->vit_p3[i] = (r == 1 || r == 4 || r == 5) ? 0 : (o->p3_am[off++] ? 1 : -1);
+        }
+    } else {
+        for (int i = 0; i < P3_LEN_MA3 * 3; i++) {                         /* decode.c:214-229 */
+            const int r = i % 15;
+            o->vit_p3[i] = (r == 1 || r == 4 || r == 7) ? 0 : (o->p3_am[off++] ? 1 : -1);
+        }
     }
 }
 
@@ -279,11 +312,19 @@ static void process_p1_p3(orc_am_t *o, unsigned bc)                        /* de
         if (bc == 7) {
             unsigned total = 8 * 9000;
             if (!o->rdbi) {
-                total += 36000;
-                orc_viterbi(o->vit_p3, o->out_p3, 9, P3_LEN_MA1, GENS_E2[0], GENS_E2[1], GENS_E2[2]);
-                o->am_errors += bit_errors(o->vit_p3, o->out_p3, 9, P3_LEN_MA1, GENS_E2, punct_e2, 6);
-                orc_descramble(o->out_p3, P3_LEN_MA1);
-                emit_frame(o, o->out_p3, P3_LEN_MA1, 1);
+                if (o->psmi != MODE_MA3) {
+                    total += 36000;
+                    orc_viterbi(o->vit_p3, o->out_p3, 9, P3_LEN_MA1, GENS_E2[0], GENS_E2[1], GENS_E2[2]);
+                    o->am_errors += bit_errors(o->vit_p3, o->out_p3, 9, P3_LEN_MA1, GENS_E2, punct_e2, 6);
+                    orc_descramble(o->out_p3, P3_LEN_MA1);
+                    emit_frame(o, o->out_p3, P3_LEN_MA1, 1);
+                } else {                                                   /* decode.c:533-539 */
+                    total += 72000;
+                    orc_viterbi(o->vit_p3, o->out_p3, 9, P3_LEN_MA3, GENS_E1[0], GENS_E1[1], GENS_E1[2]);
+                    o->am_errors += bit_errors(o->vit_p3, o->out_p3, 9, P3_LEN_MA3, GENS_E1, punct_e1, 15);
+                    orc_descramble(o->out_p3, P3_LEN_MA3);
+                    emit_frame(o, o->out_p3, P3_LEN_MA3, 1);
+                }
             }
             float cber = (float)o->am_errors / (float)total;
             alog_put(&o->log, ORC_REC_BER, &cber, sizeof(cber), NULL, 0);
@@ -361,14 +402,15 @@ static int find_ref_am(orc_am_t *o, unsigned ref)                          /* sy
     return fuzzy_match(needle_am, 23, data, BLK);
 }
 
-static void sync_block_am(orc_am_t *o)                                     /* sync.c:612-767, MA1 branches */
+static void sync_block_am(orc_am_t *o)                                     /* sync.c:612-767 */
 {
     for (int i = REF_IDX; i <= MAX_IDX; i++)
         for (int n = 0; n < BLK; n++)
             o->bins[CENTER - i][n] = -conjf(o->bins[CENTER - i][n]);
-    for (int i = REF_IDX; i <= PIDS_OUTER; i++)
-        for (int n = 0; n < BLK; n++)
-            o->bins[CENTER + i][n] += o->bins[CENTER - i][n];
+    if (o->psmi != MODE_MA3)                                               /* the mode known when the block starts */
+        for (int i = REF_IDX; i <= PIDS_OUTER; i++)
+            for (int n = 0; n < BLK; n++)
+                o->bins[CENTER + i][n] += o->bins[CENTER - i][n];
 
     if (o->state == ST_COARSE && o->cfo_wait == 0) {
         int offset = find_ref_am(o, CENTER + REF_IDX);
@@ -394,26 +436,38 @@ static void sync_block_am(orc_am_t *o)                                     /* sy
 
     if (o->state != ST_FINE) return;
 
-    const cf pids1_mult = 2 * CMPLXF(1.5, -0.5) / (o->bins[CENTER + PIDS_INNER][8] + o->bins[CENTER + PIDS_INNER][24]);
-    const cf pids2_mult = 2 * CMPLXF(1.5, -0.5) / (o->bins[CENTER + PIDS_OUTER][8] + o->bins[CENTER + PIDS_OUTER][24]);
+    const int ma3 = o->psmi == MODE_MA3;
+    const int pids1_index = !ma3 ? PIDS_INNER : -PIDS_INNER, pids2_index = !ma3 ? PIDS_OUTER : PIDS_INNER;   /* sync.c:670-671 */
+    const cf pids1_mult = 2 * CMPLXF(1.5, -0.5) / (o->bins[CENTER + pids1_index][8] + o->bins[CENTER + pids1_index][24]);
+    const cf pids2_mult = 2 * CMPLXF(1.5, -0.5) / (o->bins[CENTER + pids2_index][8] + o->bins[CENTER + pids2_index][24]);
     uint8_t pids[2 * BLK];
     int pids_out = 0;
     for (int n = 0; n < BLK; n++) {
-        o->bins[CENTER + PIDS_INNER][n] *= pids1_mult;
-        pids[pids_out++] = qam16(o->bins[CENTER + PIDS_INNER][n]);
-        o->bins[CENTER + PIDS_OUTER][n] *= pids2_mult;
-        pids[pids_out++] = qam16(o->bins[CENTER + PIDS_OUTER][n]);
+        o->bins[CENTER + pids1_index][n] *= pids1_mult;
+        pids[pids_out++] = qam16(o->bins[CENTER + pids1_index][n]);
+        o->bins[CENTER + pids2_index][n] *= pids2_mult;
+        pids[pids_out++] = qam16(o->bins[CENTER + pids2_index][n]);
     }
     process_pids(o, pids);
 
+    /* sync.c:694-696: carrier index of column 0 and direction of each partition */
+    const int primary = !ma3 ? OUTER_START : INNER_START, secondary = MIDDLE_START;
+    const int tertiary = !ma3 ? INNER_START : MIDDLE_START, tdir = !ma3 ? 1 : -1;
     cf pl_mult[PW_AM], pu_mult[PW_AM], s_mult[PW_AM], t_mult[PW_AM];
     float samperr = 0;
     for (int col = 0; col < PW_AM; col++) {
         int train1 = (5 + 11 * col) % 32, train2 = (21 + 11 * col) % 32;
-        pl_mult[col] = 2 * CMPLXF(2.5, -2.5) / (o->bins[CENTER - OUTER_START - col][train1] + o->bins[CENTER - OUTER_START - col][train2]);
-        pu_mult[col] = 2 * CMPLXF(2.5, -2.5) / (o->bins[CENTER + OUTER_START + col][train1] + o->bins[CENTER + OUTER_START + col][train2]);
-        s_mult[col] = 2 * CMPLXF(1.5, -0.5) / (o->bins[CENTER + MIDDLE_START + col][train1] + o->bins[CENTER + MIDDLE_START + col][train2]);
-        t_mult[col] = 2 * CMPLXF(-0.5, 0.5) / (o->bins[CENTER + INNER_START + col][train1] + o->bins[CENTER + INNER_START + col][train2]);
+        const int ipl = CENTER - primary - col, ipu = CENTER + primary + col, is = CENTER + secondary + col,
+                  it = CENTER + tdir * (tertiary + col);
+        pl_mult[col] = 2 * CMPLXF(2.5, -2.5) / (o->bins[ipl][train1] + o->bins[ipl][train2]);
+        pu_mult[col] = 2 * CMPLXF(2.5, -2.5) / (o->bins[ipu][train1] + o->bins[ipu][train2]);
+        if (!ma3) {
+            s_mult[col] = 2 * CMPLXF(1.5, -0.5) / (o->bins[is][train1] + o->bins[is][train2]);
+            t_mult[col] = 2 * CMPLXF(-0.5, 0.5) / (o->bins[it][train1] + o->bins[it][train2]);
+        } else {
+            s_mult[col] = 2 * CMPLXF(2.5, -2.5) / (o->bins[is][train1] + o->bins[is][train2]);
+            t_mult[col] = 2 * CMPLXF(2.5, -2.5) / (o->bins[it][train1] + o->bins[it][train2]);
+        }
         if (col > 0) {
             samperr += phase_diff(cargf(pl_mult[col]), cargf(pl_mult[col - 1]));
             samperr += phase_diff(cargf(pu_mult[col]), cargf(pu_mult[col - 1]));
@@ -425,14 +479,16 @@ static void sync_block_am(orc_am_t *o)                                     /* sy
     uint8_t pl[BLK * PW_AM], pu[BLK * PW_AM], s[BLK * PW_AM], t[BLK * PW_AM];
     for (int n = 0; n < BLK; n++)
         for (int col = 0; col < PW_AM; col++) {
-            o->bins[CENTER - OUTER_START - col][n] *= pl_mult[col];
-            o->bins[CENTER + OUTER_START + col][n] *= pu_mult[col];
-            o->bins[CENTER + MIDDLE_START + col][n] *= s_mult[col];
-            o->bins[CENTER + INNER_START + col][n] *= t_mult[col];
-            pl[n * PW_AM + col] = qam64(o->bins[CENTER - OUTER_START - col][n]);
-            pu[n * PW_AM + col] = qam64(o->bins[CENTER + OUTER_START + col][n]);
-            s[n * PW_AM + col] = qam16(o->bins[CENTER + MIDDLE_START + col][n]);
-            t[n * PW_AM + col] = qpsk(o->bins[CENTER + INNER_START + col][n]);
+            const int ipl = CENTER - primary - col, ipu = CENTER + primary + col, is = CENTER + secondary + col,
+                      it = CENTER + tdir * (tertiary + col);
+            o->bins[ipl][n] *= pl_mult[col];
+            o->bins[ipu][n] *= pu_mult[col];
+            o->bins[is][n] *= s_mult[col];
+            o->bins[it][n] *= t_mult[col];
+            pl[n * PW_AM + col] = qam64(o->bins[ipl][n]);
+            pu[n * PW_AM + col] = qam64(o->bins[ipu][n]);
+            s[n * PW_AM + col] = !ma3 ? qam16(o->bins[is][n]) : qam64(o->bins[is][n]);
+            t[n * PW_AM + col] = !ma3 ? qpsk(o->bins[it][n]) : qam64(o->bins[it][n]);
         }
     /* decode_push_pl_pu_s_t (decode.c:439-449) */
     memcpy(o->buffer_pl + o->bc * BLK * PW_AM, pl, BLK * PW_AM);

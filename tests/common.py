@@ -47,10 +47,14 @@ SYNTH_CASES = {
 MP3_CASE = dict(nframes=4, seed=11, lead_in=300, tail_blocks=2)
 
 
-# AM hybrid MA1, cs16 (the reference is the only decoder of these so far; CUDA rows: SURVEY §8 a21)
+# AM hybrid MA1 (psmi 1) and all-digital MA3 (psmi 2), cs16; the *_noisy cases have a channel
+# BER of about 1e-3 so that the K=9 Viterbi decoders correct real errors
 AM_CASES = {
     "ma1_clean": dict(nframes=10, seed=3, lead_in=500),
     "ma1_cfo_awgn": dict(nframes=10, seed=4, lead_in=777, cfo_hz=1.5, noise_lsb=8.0),
+    "ma1_noisy": dict(nframes=10, seed=8, lead_in=333, cfo_hz=-1.0, noise_lsb=120.0),
+    "ma3_clean": dict(nframes=10, seed=5, lead_in=640, psmi=2),
+    "ma3_noisy": dict(nframes=10, seed=6, lead_in=901, cfo_hz=-2.0, noise_lsb=120.0, psmi=2),
 }
 
 

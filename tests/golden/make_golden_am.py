@@ -1,4 +1,4 @@
-"""Regenerates tests/golden/synth_am.json: the synthetic AM MA1 capture (common.AM_CASE, cs16 at 46 511.72 S/s)
+"""Regenerates tests/golden/synth_am.json: the synthetic AM MA1 / MA3 captures (common.AM_CASES, cs16 at 46 511.72 S/s)
 decoded by the UNMODIFIED reference (oracle/_ref/libnrsc5_ref.so, AM mode).  Build container only; the JSON is
 committed.  It is the known answer the AM rows of the scope table will be held to.
 

@@ -1,5 +1,5 @@
 """CPU tests pinning the AM restatement (oracle/nrsc5_oracle_am.c) against the UNMODIFIED reference
-(oracle/_ref/libnrsc5_ref.so, AM mode) and the committed golden file, on the synthetic MA1 captures."""
+(oracle/_ref/libnrsc5_ref.so, AM mode) and the committed golden file, on the synthetic MA1 and MA3 captures."""
 import pytest
 
 import common
@@ -23,8 +23,9 @@ def test_am_port_matches_golden(name):
 
 
 @pytest.mark.skipif(not reftap.available(), reason="reference oracle not built")
-def test_am_port_matches_reference_and_is_chunking_invariant():
-    cap = synth_am.make_am_ma1(nframes=9, seed=9, lead_in=1234, cfo_hz=-0.8, noise_lsb=5.0)
+@pytest.mark.parametrize("psmi", [1, 2])
+def test_am_port_matches_reference_and_is_chunking_invariant(psmi):
+    cap = synth_am.make_am_ma1(nframes=9, seed=9, lead_in=1234, cfo_hz=-0.8, noise_lsb=5.0, psmi=psmi)
     ref = reftap.decode(cap.cs16, mode=reftap.MODE_AM)
     a = port.decode_am(cap.cs16)
     b = port.decode_am(cap.cs16, chunk=16384)
