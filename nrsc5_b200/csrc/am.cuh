@@ -1,4 +1,4 @@
-// AM (hybrid MA1) receive chain: first CUDA path.  One WARP per stream runs the whole chain block after block
+// AM (hybrid MA1, all-digital MA3) receive chain: first CUDA path.  One WARP per stream runs the whole chain block after block
 // (k_am): coarse acquisition, carrier-phase tracking, 256-point OFDM demodulation, reference-carrier search,
 // training-symbol equalisation, QAM/QPSK slicing, PIDS, interleaver MA1 with the diversity delay, K=9
 // tail-biting Viterbi (E1/E2/E3), descramble, L1 PDUs.
@@ -39,9 +39,10 @@ namespace nbam {
 constexpr int FFT = 256, CP = 14, SYM = FFT + CP, BLK = 32, NACQ = SYM * (BLK + 1);
 constexpr int CENTER = 128, REF_IDX = 1, PIDS_INNER = 27, PIDS_OUTER = 53, INNER_START = 2, MIDDLE_START = 28,
               OUTER_START = 57, MAX_IDX = 81, PW = 25;
-constexpr int P1_LEN = 3750, P3_LEN = 24000, PIDS_LEN = 80, DIVERSITY = 18000 * 3;
+constexpr int P1_LEN = 3750, P3_LEN = 24000, P3_LEN_MA3 = 30000, PIDS_LEN = 80, DIVERSITY = 18000 * 3;
+constexpr int MODE_MA3 = 2;                     // SERVICE_MODE_MA3, defines.h:39; every other psmi is decoded as MA1
 constexpr int ST_NONE = 0, ST_COARSE = 1, ST_FINE = 2;
-constexpr int VIT_MAX_STEPS = P3_LEN + 64;
+constexpr int VIT_MAX_STEPS = P3_LEN_MA3 + 64;
 constexpr uint32_t REC_FRAME = 1, REC_PIDS = 2, REC_SYNC = 3, REC_LOST_SYNC = 4, REC_BER = 6;
 constexpr double PI = 3.14159265358979323846;
 
@@ -101,9 +102,10 @@ struct AmWork {
     float2 bins[FFT][BLK];
     uint8_t buffer_pl[PW * BLK * 8], buffer_pu[PW * BLK * 8], buffer_s[PW * BLK * 8], buffer_t[PW * BLK * 8];
     uint8_t bl[18000], bu[18000], ml[DIVERSITY + 18000], mu[DIVERSITY + 18000], el[12000], eu[24000];
-    uint8_t p1_am[8 * 9000], p3_am[36000];
-    int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN * 3], vit_pids[PIDS_LEN * 3];
-    uint8_t out[P3_LEN + 8];
+    uint8_t ebl[18000], ebu[18000], eml[DIVERSITY + 18000], emu[DIVERSITY + 18000];     // MA3 (decode.h:49-52)
+    uint8_t p1_am[8 * 9000], p3_am[72000];
+    int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
+    uint8_t out[P3_LEN_MA3 + 8];
     short pm[2][256];
     uint8_t dec[(size_t)VIT_MAX_STEPS * 32];   // survivor bits, see viterbi_k9
     float2 mult[4][PW];
@@ -115,7 +117,7 @@ struct AmTables {
     float2 tw[FFT / 2];        // exp(-2*pi*i*k/256)
     short bp_tap[32];          // coarse band-pass taps, reversed and truncated like src/firdecim_q15.c:37-41
     uint8_t brev[FFT];         // bit reversal of 8 bits
-    uint8_t pn[P3_LEN + 8];    // descrambler sequence
+    uint8_t pn[P3_LEN_MA3 + 8];    // descrambler sequence
 };
 
 struct AmIo {
@@ -265,7 +267,7 @@ AM_HD inline int bit_map(const uint8_t *matrix, int b, int k, int p)            
     return (matrix[PW * (b * BLK + row) + col] >> p) & 1;
 }
 
-AM_HD inline void interleaver_ma1(AmWork &w, Lanes L)                                  // decode.c:74-231 (MA1)
+AM_HD inline void interleaver_ma1(AmWork &w, Lanes L, bool ma3)                        // decode.c:74-231
 {
     const int bl_delay[3] = { 2, 1, 5 }, ml_delay[3] = { 11, 6, 7 }, bu_delay[3] = { 10, 8, 9 }, mu_delay[3] = { 4, 3, 0 };
     const int el_delay[2] = { 0, 1 }, eu_delay[4] = { 2, 3, 5, 4 };
@@ -275,10 +277,19 @@ AM_HD inline void interleaver_ma1(AmWork &w, Lanes L)                           
         w.bu[n] = (uint8_t)bit_map(w.buffer_pu, n / 2250, (n + n / 750) % 750, n % 3);
         w.mu[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_pu, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
     }
-    for (int n = L.lane; n < 12000; n += L.n)
-        w.el[n] = (uint8_t)bit_map(w.buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2);
-    for (int n = L.lane; n < 24000; n += L.n)
-        w.eu[n] = (uint8_t)bit_map(w.buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4);
+    if (!ma3) {
+        for (int n = L.lane; n < 12000; n += L.n)
+            w.el[n] = (uint8_t)bit_map(w.buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2);
+        for (int n = L.lane; n < 24000; n += L.n)
+            w.eu[n] = (uint8_t)bit_map(w.buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4);
+    } else {
+        for (int n = L.lane; n < 18000; n += L.n) {                                      // decode.c:119-140
+            w.ebl[n] = (uint8_t)bit_map(w.buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, n % 3);
+            w.eml[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
+            w.ebu[n] = (uint8_t)bit_map(w.buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, n % 3);
+            w.emu[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
+        }
+    }
     AM_SYNC();
     for (int i = L.lane; i < 6000; i += L.n) {
         for (int j = 0; j < 3; j++) {
@@ -287,8 +298,17 @@ AM_HD inline void interleaver_ma1(AmWork &w, Lanes L)                           
             w.p1_am[i * 12 + bu_delay[j]] = w.bu[i * 3 + j];
             w.p1_am[i * 12 + mu_delay[j]] = w.mu[i * 3 + j];
         }
-        for (int j = 0; j < 2; j++) w.p3_am[i * 6 + el_delay[j]] = w.el[i * 2 + j];
-        for (int j = 0; j < 4; j++) w.p3_am[i * 6 + eu_delay[j]] = w.eu[i * 4 + j];
+        if (!ma3) {
+            for (int j = 0; j < 2; j++) w.p3_am[i * 6 + el_delay[j]] = w.el[i * 2 + j];
+            for (int j = 0; j < 4; j++) w.p3_am[i * 6 + eu_delay[j]] = w.eu[i * 4 + j];
+        } else {
+            for (int j = 0; j < 3; j++) {                                                // decode.c:163-170
+                w.p3_am[i * 12 + bl_delay[j]] = w.ebl[i * 3 + j];
+                w.p3_am[i * 12 + ml_delay[j]] = w.eml[i * 3 + j];
+                w.p3_am[i * 12 + bu_delay[j]] = w.ebu[i * 3 + j];
+                w.p3_am[i * 12 + mu_delay[j]] = w.emu[i * 3 + j];
+            }
+        }
     }
     AM_SYNC();
     // the main bits move three frames towards the front (memmove of 54000 entries, in three non-overlapping steps)
@@ -296,6 +316,10 @@ AM_HD inline void interleaver_ma1(AmWork &w, Lanes L)                           
         for (int i = L.lane; i < 18000; i += L.n) {
             w.ml[step * 18000 + i] = w.ml[(step + 1) * 18000 + i];
             w.mu[step * 18000 + i] = w.mu[(step + 1) * 18000 + i];
+            if (ma3) {                                                                    // decode.c:176-180
+                w.eml[step * 18000 + i] = w.eml[(step + 1) * 18000 + i];
+                w.emu[step * 18000 + i] = w.emu[(step + 1) * 18000 + i];
+            }
         }
         AM_SYNC();
     }
@@ -305,10 +329,18 @@ AM_HD inline void interleaver_ma1(AmWork &w, Lanes L)                           
         const int before = r - (r > 1) - (r > 4) - (r > 7);
         w.vit_p1[i] = (r == 1 || r == 4 || r == 7) ? 0 : (w.p1_am[base + before] ? 1 : -1);
     }
-    for (int i = L.lane; i < P3_LEN * 3; i += L.n) {
-        const int r = i % 6, base = (i / 6) * 3;
-        const int before = r - (r > 1);
-        w.vit_p3[i] = (r == 1 || r == 4 || r == 5) ? 0 : (w.p3_am[base + before] ? 1 : -1);
+    if (!ma3) {
+        for (int i = L.lane; i < P3_LEN * 3; i += L.n) {
+            const int r = i % 6, base = (i / 6) * 3;
+            const int before = r - (r > 1);
+            w.vit_p3[i] = (r == 1 || r == 4 || r == 5) ? 0 : (w.p3_am[base + before] ? 1 : -1);
+        }
+    } else {
+        for (int i = L.lane; i < P3_LEN_MA3 * 3; i += L.n) {                             // decode.c:214-229
+            const int r = i % 15, base = (i / 15) * 12;
+            const int before = r - (r > 1) - (r > 4) - (r > 7);
+            w.vit_p3[i] = (r == 1 || r == 4 || r == 7) ? 0 : (w.p3_am[base + before] ? 1 : -1);
+        }
     }
     AM_SYNC();
 }
@@ -394,12 +426,21 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
         if (bc == 7) {
             unsigned total = 8 * 9000;
             if (!st.rdbi) {
-                total += 36000;
-                viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711);
-                st.am_errors += bit_errors(w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711, punct_e2, 6);
-                AM_SYNC();
-                descramble(tb, L, w.out, P3_LEN);
-                emit_frame(st, io, L, w.out, P3_LEN, 1);
+                if (st.psmi != MODE_MA3) {
+                    total += 36000;
+                    viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711);
+                    st.am_errors += bit_errors(w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711, punct_e2, 6);
+                    AM_SYNC();
+                    descramble(tb, L, w.out, P3_LEN);
+                    emit_frame(st, io, L, w.out, P3_LEN, 1);
+                } else {                                                                  // decode.c:533-539
+                    total += 72000;
+                    viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711);
+                    st.am_errors += bit_errors(w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711, punct_e1, 15);
+                    AM_SYNC();
+                    descramble(tb, L, w.out, P3_LEN_MA3);
+                    emit_frame(st, io, L, w.out, P3_LEN_MA3, 1);
+                }
                 AM_SYNC();
             }
             const float cber = (float)st.am_errors / (float)total;
@@ -408,7 +449,7 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
         }
     }
     if (bc == 7) {
-        interleaver_ma1(w, L);
+        interleaver_ma1(w, L, st.psmi == MODE_MA3);
         if (st.am_diversity_wait > 0) st.am_diversity_wait--;
     }
 }
@@ -485,8 +526,9 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
             w.bins[CENTER - i][n] = make_float2(-v.x, v.y);                              // -conj
         }
     AM_SYNC();
-    for (int i = REF_IDX + L.lane; i <= PIDS_OUTER; i += L.n)
-        for (int n = 0; n < BLK; n++) w.bins[CENTER + i][n] = cadd(w.bins[CENTER + i][n], w.bins[CENTER - i][n]);
+    if (st.psmi != MODE_MA3)                                                             // the mode known when the block starts
+        for (int i = REF_IDX + L.lane; i <= PIDS_OUTER; i += L.n)
+            for (int n = 0; n < BLK; n++) w.bins[CENTER + i][n] = cadd(w.bins[CENTER + i][n], w.bins[CENTER - i][n]);
     AM_SYNC();
 
     if (st.state == ST_COARSE && st.cfo_wait == 0) {                                     // sync.c:635-647
@@ -512,29 +554,37 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
     }
     if (st.state != ST_FINE) return;
 
+    const bool ma3 = st.psmi == MODE_MA3;
     // PIDS carriers (sync.c:668-685): equalise with the training symbols of rows 8 and 24, slice
     {
+        const int b1 = CENTER + (!ma3 ? PIDS_INNER : -PIDS_INNER), b2 = CENTER + (!ma3 ? PIDS_OUTER : PIDS_INNER);
         const float2 tr = make_float2(2 * 1.5f, 2 * -0.5f);
-        const float2 m1 = cdiv(tr, cadd(w.bins[CENTER + PIDS_INNER][8], w.bins[CENTER + PIDS_INNER][24]));
-        const float2 m2 = cdiv(tr, cadd(w.bins[CENTER + PIDS_OUTER][8], w.bins[CENTER + PIDS_OUTER][24]));
+        const float2 m1 = cdiv(tr, cadd(w.bins[b1][8], w.bins[b1][24]));
+        const float2 m2 = cdiv(tr, cadd(w.bins[b2][8], w.bins[b2][24]));
         AM_SYNC();
         for (int n = L.lane; n < BLK; n += L.n) {
-            w.bins[CENTER + PIDS_INNER][n] = cmul(w.bins[CENTER + PIDS_INNER][n], m1);
-            w.sym_pids[2 * n] = qam16(w.bins[CENTER + PIDS_INNER][n]);
-            w.bins[CENTER + PIDS_OUTER][n] = cmul(w.bins[CENTER + PIDS_OUTER][n], m2);
-            w.sym_pids[2 * n + 1] = qam16(w.bins[CENTER + PIDS_OUTER][n]);
+            w.bins[b1][n] = cmul(w.bins[b1][n], m1);
+            w.sym_pids[2 * n] = qam16(w.bins[b1][n]);
+            w.bins[b2][n] = cmul(w.bins[b2][n], m2);
+            w.sym_pids[2 * n + 1] = qam16(w.bins[b2][n]);
         }
         AM_SYNC();
     }
     process_pids(st, w, tb, io, L);
 
-    // partitions (sync.c:687-717): per column the two training rows give the equaliser tap
+    // partitions (sync.c:687-717): per column the two training rows give the equaliser tap.  Column 0 of the
+    // primary partitions sits at -/+ `primary`, of the secondary at +28, of the tertiary at +2 (MA1) / -28 (MA3)
+    const int primary = !ma3 ? OUTER_START : INNER_START, tertiary = !ma3 ? INNER_START : MIDDLE_START, tdir = !ma3 ? 1 : -1;
+    const float2 tr_p = make_float2(2 * 2.5f, 2 * -2.5f);
+    const float2 tr_s = !ma3 ? make_float2(2 * 1.5f, 2 * -0.5f) : tr_p, tr_t = !ma3 ? make_float2(2 * -0.5f, 2 * 0.5f) : tr_p;
     for (int col = L.lane; col < PW; col += L.n) {
         const int t1 = (5 + 11 * col) % 32, t2 = (21 + 11 * col) % 32;
-        w.mult[0][col] = cdiv(make_float2(2 * 2.5f, 2 * -2.5f), cadd(w.bins[CENTER - OUTER_START - col][t1], w.bins[CENTER - OUTER_START - col][t2]));
-        w.mult[1][col] = cdiv(make_float2(2 * 2.5f, 2 * -2.5f), cadd(w.bins[CENTER + OUTER_START + col][t1], w.bins[CENTER + OUTER_START + col][t2]));
-        w.mult[2][col] = cdiv(make_float2(2 * 1.5f, 2 * -0.5f), cadd(w.bins[CENTER + MIDDLE_START + col][t1], w.bins[CENTER + MIDDLE_START + col][t2]));
-        w.mult[3][col] = cdiv(make_float2(2 * -0.5f, 2 * 0.5f), cadd(w.bins[CENTER + INNER_START + col][t1], w.bins[CENTER + INNER_START + col][t2]));
+        const int ipl = CENTER - primary - col, ipu = CENTER + primary + col, is = CENTER + MIDDLE_START + col,
+                  it = CENTER + tdir * (tertiary + col);
+        w.mult[0][col] = cdiv(tr_p, cadd(w.bins[ipl][t1], w.bins[ipl][t2]));
+        w.mult[1][col] = cdiv(tr_p, cadd(w.bins[ipu][t1], w.bins[ipu][t2]));
+        w.mult[2][col] = cdiv(tr_s, cadd(w.bins[is][t1], w.bins[is][t2]));
+        w.mult[3][col] = cdiv(tr_t, cadd(w.bins[it][t1], w.bins[it][t2]));
     }
     AM_SYNC();
     {
@@ -548,19 +598,21 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
     }
     for (int idx = L.lane; idx < BLK * PW; idx += L.n) {                                 // sync.c:725-754
         const int n = idx / PW, col = idx - n * PW;
+        const int ipl = CENTER - primary - col, ipu = CENTER + primary + col, is = CENTER + MIDDLE_START + col,
+                  it = CENTER + tdir * (tertiary + col);
         float2 v;
-        v = cmul(w.bins[CENTER - OUTER_START - col][n], w.mult[0][col]);
-        w.bins[CENTER - OUTER_START - col][n] = v;
+        v = cmul(w.bins[ipl][n], w.mult[0][col]);
+        w.bins[ipl][n] = v;
         w.sym_pl[idx] = qam64(v);
-        v = cmul(w.bins[CENTER + OUTER_START + col][n], w.mult[1][col]);
-        w.bins[CENTER + OUTER_START + col][n] = v;
+        v = cmul(w.bins[ipu][n], w.mult[1][col]);
+        w.bins[ipu][n] = v;
         w.sym_pu[idx] = qam64(v);
-        v = cmul(w.bins[CENTER + MIDDLE_START + col][n], w.mult[2][col]);
-        w.bins[CENTER + MIDDLE_START + col][n] = v;
-        w.sym_s[idx] = qam16(v);
-        v = cmul(w.bins[CENTER + INNER_START + col][n], w.mult[3][col]);
-        w.bins[CENTER + INNER_START + col][n] = v;
-        w.sym_t[idx] = qpsk(v);
+        v = cmul(w.bins[is][n], w.mult[2][col]);
+        w.bins[is][n] = v;
+        w.sym_s[idx] = !ma3 ? qam16(v) : qam64(v);
+        v = cmul(w.bins[it][n], w.mult[3][col]);
+        w.bins[it][n] = v;
+        w.sym_t[idx] = !ma3 ? qpsk(v) : qam64(v);
     }
     AM_SYNC();
     for (int i = L.lane; i < BLK * PW; i += L.n) {                                        // decode_push_pl_pu_s_t, decode.c:439-449

@@ -36,7 +36,7 @@ inline void am_fill_tables(AmTables &tb)
         tb.brev[i] = (uint8_t)r;
     }
     unsigned reg = 0x3ff;                                   // reference src/decode.c:279-294
-    for (int i = 0; i < P3_LEN + 8; i++) {
+    for (int i = 0; i < P3_LEN_MA3 + 8; i++) {
         const unsigned b = ((reg >> 9) ^ reg) & 1;
         reg |= b << 11;
         reg >>= 1;

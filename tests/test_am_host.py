@@ -1,5 +1,6 @@
 """The AM engine's code (nrsc5_b200/csrc/am.cuh, AM_HD functions) compiled for the CPU and run with one lane
-(tests/am_host.cu) against the oracle and the golden vectors: the same source the GPU runs with 32 lanes."""
+(tests/am_host.cu) against the oracle and the golden vectors, and with the 32 lanes of the GPU warp emulated by fibres:
+the same source the GPU runs."""
 import ctypes
 import os
 import subprocess
@@ -56,11 +57,10 @@ def test_am_engine_code_on_host_matches_oracle(name):
     assert common.summarize(got) == common.summarize(ref)
 
 
-@pytest.mark.parametrize("order", [1, -1])
-def test_am_engine_code_with_32_emulated_lanes(order):
+@pytest.mark.parametrize("name,order", [("ma1_noisy", 1), ("ma1_noisy", -1), ("ma3_noisy", 1), ("ma3_noisy", -1)])
+def test_am_engine_code_with_32_emulated_lanes(name, order):
     """k_am's warp emulated by 32 fibres (tests/am_host.cu): the lane-strided work split and the placement of the
     AM_SYNC() barriers, with the lanes scheduled in ascending and in descending order."""
-    name = next(iter(common.AM_CASES))
     cap = synth_am.make_am_ma1(**common.AM_CASES[name])
     got = host_decode(cap.cs16, lanes=32, order=order)
     ref = port.decode_am(cap.cs16)

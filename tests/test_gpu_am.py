@@ -1,4 +1,4 @@
-"""GPU parity of the AM (hybrid MA1) path through the C ABI: cs16 in, P1 / P3 / PIDS PDUs and events out, against
+"""GPU parity of the AM (hybrid MA1, all-digital MA3) path through the C ABI: cs16 in, P1 / P3 / PIDS PDUs and events out, against
 the oracle (oracle/nrsc5_oracle_am.c, itself pinned to the unmodified reference) and the golden vectors."""
 import numpy as np
 import pytest
@@ -76,7 +76,8 @@ def test_am_pdus_bit_exact(name):
 
 
 def test_am_streams_independent_and_chunked():
-    caps = [synth_am.make_am_ma1(nframes=8, seed=40 + i, lead_in=100 + 333 * i, cfo_hz=0.4 * i) for i in range(3)]
+    caps = [synth_am.make_am_ma1(nframes=8, seed=40 + i, lead_in=100 + 333 * i, cfo_hz=0.4 * i, psmi=2 if i == 2 else 1)
+            for i in range(3)]
     whole = run_am([c.cs16 for c in caps])
     parts = run_am([c.cs16 for c in caps], chunk=1 << 15)
     for c, a, b in zip(caps, whole, parts):
