@@ -59,7 +59,8 @@ extern "C" {
 #endif
 
 #define NRSC5B_MODE_FM 0
-#define NRSC5B_MODE_AM 1      /* hybrid MA1, cs16 input at 46 511.72 S/s only (input_cs16 = 1); first, unoptimised path */
+#define NRSC5B_MODE_AM 1      /* MA1 / MA3; cs16 at 46 511.72 S/s (input_cs16 = 1) or cu8 at 1 488 375 S/s (input_cs16 = 0,
+                               * decimated by 32 on the device); first, unoptimised path */
 
 enum {
     NRSC5B_OK = 0,

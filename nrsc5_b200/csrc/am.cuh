@@ -26,6 +26,14 @@
 #else
 #define AM_SYNC() ((void)0)
 #endif
+// barrier of the cu8 front end's thread block (k_am_decim); the host harness uses the same fibre barrier
+#if defined(__CUDA_ARCH__)
+#define AM_BLOCK_SYNC() __syncthreads()
+#elif defined(AM_HOST_SYNC)
+#define AM_BLOCK_SYNC() AM_HOST_SYNC()
+#else
+#define AM_BLOCK_SYNC() ((void)0)
+#endif
 #define AM_HD __host__ __device__
 // input samples may land (asynchronous pushes) while a kernel runs: on the device they are read through L2 only
 #if defined(__CUDA_ARCH__)
@@ -806,6 +814,78 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
     st.keep_extra = 0;
     st.start += NACQ - keep;
     st.blocks_done++;
+}
+
+// ---- cu8 input (reference src/input.c:52-117 in AM mode, src/firdecim_q15.c:137-165) ----
+// (u8 - 127) * 64 >> 4, then five cascaded halfband decimators: 1 488 375 S/s cu8 -> 46 511.72 S/s cs16.  Every
+// stage is y[m] = x[2m-7] + sum_i ((x[2m-14+2i] + x[2m-2i]) * tap[i]) >> 15 in wrapping int16 arithmetic, the
+// output taken when the even sample of a pair has gone in.  The cascade is feed-forward, so output k is a pure
+// function of the raw samples 32k-434 .. 32k (zeros before the stream's first sample: the reference's filter
+// windows start cleared): a tile of DEC_T outputs recomputes its 434 samples of history instead of carrying
+// filter state, and tiles are independent.
+//
+//   algorithmic bytes per cs16 output: 64 read (32 cu8 samples) + 4 written
+//
+// The raw samples live in a per-stream ring of `ring_bytes` (a power of two); `raw_avail` counts the raw complex
+// samples written so far (absolute index).
+constexpr int DEC_T = 64;                      // cs16 outputs per tile
+constexpr int DEC_NX = 32 * (DEC_T - 1) + 435, DEC_N0 = 16 * (DEC_T - 1) + 211, DEC_N1 = 8 * (DEC_T - 1) + 99,
+              DEC_N2 = 4 * (DEC_T - 1) + 43, DEC_N3 = 2 * (DEC_T - 1) + 15;
+constexpr int DEC_RAW_HISTORY = 434;           // raw samples before 32k that output k depends on
+
+struct DecimScratch {
+    short2 x[DEC_NX], s0[DEC_N0], s1[DEC_N1], s2[DEC_N2], s3[DEC_N3];
+};
+
+AM_HD inline short2 halfband_q15(const short2 *w, int c)      // c: index of the newest (even) sample, c >= 14
+{
+    // taps of src/input.c:33-38 reversed and truncated to int16 (src/firdecim_q15.c:37-41)
+    const int t0 = -134, t1 = 1078, t2 = -4417, t3 = 19864;
+    int re = w[c - 7].x, im = w[c - 7].y;
+    re += ((w[c - 14].x + w[c].x) * t0) >> 15;
+    im += ((w[c - 14].y + w[c].y) * t0) >> 15;
+    re += ((w[c - 12].x + w[c - 2].x) * t1) >> 15;
+    im += ((w[c - 12].y + w[c - 2].y) * t1) >> 15;
+    re += ((w[c - 10].x + w[c - 4].x) * t2) >> 15;
+    im += ((w[c - 10].y + w[c - 4].y) * t2) >> 15;
+    re += ((w[c - 8].x + w[c - 6].x) * t3) >> 15;
+    im += ((w[c - 8].y + w[c - 6].y) * t3) >> 15;
+    short2 y;
+    y.x = (short)re;                               // the reference accumulates in int16: wraps modulo 2^16
+    y.y = (short)im;
+    return y;
+}
+
+// Outputs k0 .. k0+nout-1 (nout <= DEC_T) of one stream into out[0..nout-1].  Every raw sample they need
+// (up to 32*(k0+nout-1)) must have been written: raw_avail >= 32*(k0+nout).
+AM_HD inline void decim_tile(const uint8_t *ring, unsigned ring_bytes, long long raw_avail, long long k0, int nout,
+                             short2 *out, DecimScratch &sc, Lanes L)
+{
+    const long long base = 32 * k0 - DEC_RAW_HISTORY;
+    const unsigned mask = ring_bytes - 1;
+    for (int i = L.lane; i < DEC_NX; i += L.n) {
+        const long long a = base + i;
+        short2 v;
+        v.x = 0;
+        v.y = 0;
+        if (a >= 0 && a < raw_avail) {
+            const unsigned o = (unsigned)((2 * a) & mask);      // rings hold whole samples: 2a and 2a+1 are adjacent
+            v.x = (short)((((int)AM_LDIN(ring + o) - 127) * 64) >> 4);
+            v.y = (short)((((int)AM_LDIN(ring + o + 1) - 127) * 64) >> 4);
+        }
+        sc.x[i] = v;
+    }
+    AM_BLOCK_SYNC();
+    for (int m = L.lane; m < DEC_N0; m += L.n) sc.s0[m] = halfband_q15(sc.x, 14 + 2 * m);
+    AM_BLOCK_SYNC();
+    for (int m = L.lane; m < DEC_N1; m += L.n) sc.s1[m] = halfband_q15(sc.s0, 14 + 2 * m);
+    AM_BLOCK_SYNC();
+    for (int m = L.lane; m < DEC_N2; m += L.n) sc.s2[m] = halfband_q15(sc.s1, 14 + 2 * m);
+    AM_BLOCK_SYNC();
+    for (int m = L.lane; m < DEC_N3; m += L.n) sc.s3[m] = halfband_q15(sc.s2, 14 + 2 * m);
+    AM_BLOCK_SYNC();
+    for (int m = L.lane; m < nout; m += L.n) out[m] = halfband_q15(sc.s3, 14 + 2 * m);
+    AM_BLOCK_SYNC();
 }
 
 }  // namespace nbam

@@ -410,6 +410,18 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
     }
 }
 
+// AM cu8 input (input_push_cu8 in AM mode, reference src/input.c:52-117): one tile of nbam::DEC_T cs16 outputs per
+// CTA, computed from the stream's raw cu8 ring (am.cuh: decim_tile).  Launched on the copy stream behind the
+// copy that delivered the raw samples; the new sample count is published after it.
+__global__ void __launch_bounds__(256) k_am_decim(const uint8_t *ring, unsigned ring_bytes, long long raw_avail, long long k0,
+                                                  int nout, short2 *out)
+{
+    __shared__ nbam::DecimScratch sc;
+    const int first = (int)blockIdx.x * nbam::DEC_T;
+    const int n = min(nbam::DEC_T, nout - first);
+    nbam::decim_tile(ring, ring_bytes, raw_avail, k0 + first, n, out + first, sc, nbam::Lanes{ (int)threadIdx.x, (int)blockDim.x });
+}
+
 __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -462,6 +474,9 @@ struct nrsc5b_engine {
     nbam::AmState *am_st;              // AM mode: per-stream state, work arrays, tables
     nbam::AmWork *am_work;
     nbam::AmTables *am_tb;
+    uint8_t *am_ring;                  // AM with cu8 input: per-stream ring of raw samples ahead of the /32 decimator
+    unsigned am_ring_bytes;            // bytes per stream, a power of two
+    std::vector<long long> am_raw_bytes, am_dec_out;   // raw bytes received / cs16 samples produced per stream
     int profiling;
     cudaEvent_t pev[5];
     double kernel_ms[4];
@@ -555,7 +570,6 @@ extern "C" const char *nrsc5b_version(void) { return "nrsc5_b200 0.1 (sm_100a)";
 extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
 {
     if (!out || !cfg || cfg->nstreams <= 0 || (cfg->mode != NRSC5B_MODE_FM && cfg->mode != NRSC5B_MODE_AM)) return NRSC5B_EINVAL;
-    if (cfg->mode == NRSC5B_MODE_AM && !cfg->input_cs16) return NRSC5B_EINVAL;      // AM takes cs16 at 46 511.72 S/s
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) {
         fprintf(stderr, "nrsc5_b200: no usable CUDA device (the engine has no CPU path)\n");
@@ -572,6 +586,8 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->am_st = nullptr;
     e->am_work = nullptr;
     e->am_tb = nullptr;
+    e->am_ring = nullptr;
+    e->am_ring_bytes = 0;
     e->avail_rows = nullptr;
     e->avail_rows_pos = 0;
     for (int i = 0; i < 64; i++) e->fence[i] = nullptr;
@@ -664,6 +680,12 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         if (!rc) rc = dev_alloc(e, &e->am_tb, 1);
         if (rc) { nrsc5b_destroy(e); return rc; }
         nbam::AmTables *tb = new nbam::AmTables;
+        if (!rc && !cfg->input_cs16) {                      // cu8 at 1 488 375 S/s: decimated by 32 on arrival
+            e->am_ring_bytes = 1u << 20;
+            rc = dev_alloc(e, &e->am_ring, (size_t)S * e->am_ring_bytes);
+            e->am_raw_bytes.assign(S, 0);
+            e->am_dec_out.assign(S, 0);
+        }
         nbam::am_fill_tables(*tb);
         cudaMemcpy(e->am_tb, tb, sizeof(*tb), cudaMemcpyHostToDevice);
         delete tb;
@@ -828,6 +850,7 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
         if (stream >= 0 && s != stream) continue;
         e->pushed[s] = 0;
         e->drained[s] = 0;
+        if (e->am_ring) e->am_raw_bytes[s] = e->am_dec_out[s] = 0;
     }
     CK(cudaGetLastError());
     return NRSC5B_OK;
@@ -892,11 +915,79 @@ static int trim_stream(nrsc5b_engine *e, int s)
 }
 
 static int push_bytes(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
+static int push_am_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
 
 extern "C" int nrsc5b_push_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes)
 {
     if (!e || e->dims.cs16) return NRSC5B_EINVAL;
+    if (e->am_ring) return push_am_cu8(e, stream, buf, nbytes);
     return push_bytes(e, stream, buf, nbytes);
+}
+
+// host -> device copy of input on the copy stream: page-locked caller memory is DMA'd directly, pageable memory
+// goes through the engine's pinned staging buffer
+static int copy_in(nrsc5b_engine_t *e, uint8_t *dst, const uint8_t *buf, size_t nbytes)
+{
+    cudaPointerAttributes attr;
+    bool pinned_src = cudaPointerGetAttributes(&attr, buf) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned_src) {
+        CK(cudaMemcpyAsync(dst, buf, nbytes, cudaMemcpyHostToDevice, e->copy_stream));
+    } else {
+        size_t done = 0;
+        while (done < nbytes) {
+            size_t n = nbytes - done < e->pinned_cap ? nbytes - done : e->pinned_cap;
+            CK(cudaEventSynchronize(e->pinned_free));
+            memcpy(e->pinned, buf + done, n);
+            CK(cudaMemcpyAsync(dst + done, e->pinned, n, cudaMemcpyHostToDevice, e->copy_stream));
+            CK(cudaEventRecord(e->pinned_free, e->copy_stream));
+            done += n;
+        }
+    }
+    return NRSC5B_OK;
+}
+
+/* AM, cu8 at 1 488 375 S/s (input_push_cu8 in AM mode, reference src/input.c:96-117): the raw samples go into the
+ * stream's ring, k_am_decim turns every complete group of 32 into one cs16 sample appended to the stream's
+ * sample buffer, and only that count is published to the receive chain (k_am reads cs16 either way). */
+static int push_am_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes)
+{
+    if (stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned) return NRSC5B_EINVAL;
+    const unsigned R = e->am_ring_bytes;
+    uint8_t *ring = e->am_ring + (size_t)stream * R;
+    while (nbytes) {
+        const size_t n = nbytes < (size_t)R - 4096 ? nbytes : (size_t)R - 4096;     // keeps the 434 samples of history intact
+        const long long raw_after = e->am_raw_bytes[stream] + (long long)n;
+        const long long can = raw_after / 64;
+        const int nout = (int)(can - e->am_dec_out[stream]);
+        size_t off = (size_t)e->pushed[stream] * 2;
+        if (off + 4 * (size_t)nout > e->dims.in_stride) {
+            int rc = trim_stream(e, stream);
+            if (rc) return rc;
+            off = (size_t)e->pushed[stream] * 2;
+            if (off + 4 * (size_t)nout > e->dims.in_stride) return NRSC5B_EFULL;
+        }
+        const size_t pos = (size_t)(e->am_raw_bytes[stream] & (long long)(R - 1));
+        const size_t first = n < R - pos ? n : R - pos;
+        int rc = copy_in(e, ring + pos, buf, first);
+        if (!rc && n > first) rc = copy_in(e, ring, buf + first, n - first);
+        if (rc) return rc;
+        e->am_raw_bytes[stream] = raw_after;
+        if (nout > 0) {
+            short2 *out = reinterpret_cast<short2 *>(e->iq_owned + (size_t)stream * e->dims.in_stride + off);
+            k_am_decim<<<(nout + nbam::DEC_T - 1) / nbam::DEC_T, 256, 0, e->copy_stream>>>(ring, R, raw_after / 2, e->am_dec_out[stream],
+                                                                                          nout, out);
+            e->stats.kernel_launches += 1;
+            e->am_dec_out[stream] = can;
+            e->pushed[stream] += 2LL * nout;
+            rc = publish_avail(e, stream, e->copy_stream);
+            if (rc) return rc;
+        }
+        buf += n;
+        nbytes -= n;
+    }
+    CK(cudaGetLastError());
+    return NRSC5B_OK;
 }
 
 /* cs16: 4 bytes per (already decimated) complex sample; the engine counts input in 2-byte units either way, so
@@ -918,22 +1009,9 @@ static int push_bytes(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t
     }
     if (off + nbytes > e->dims.in_stride) return NRSC5B_EFULL;
     uint8_t *dst = e->iq_owned + (size_t)stream * e->dims.in_stride + off;
-    // page-locked caller memory is DMA'd directly; pageable memory goes through the engine's pinned staging buffer
-    cudaPointerAttributes attr;
-    bool pinned_src = cudaPointerGetAttributes(&attr, buf) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned_src) {
-        CK(cudaMemcpyAsync(dst, buf, nbytes, cudaMemcpyHostToDevice, e->copy_stream));
-    } else {
-        size_t done = 0;
-        while (done < nbytes) {
-            size_t n = nbytes - done < e->pinned_cap ? nbytes - done : e->pinned_cap;
-            CK(cudaEventSynchronize(e->pinned_free));
-            memcpy(e->pinned, buf + done, n);
-            CK(cudaMemcpyAsync(dst + done, e->pinned, n, cudaMemcpyHostToDevice, e->copy_stream));
-            CK(cudaEventRecord(e->pinned_free, e->copy_stream));
-            done += n;
-        }
+    {
+        int rc = copy_in(e, dst, buf, nbytes);
+        if (rc) return rc;
     }
     e->pushed[stream] += (long long)(nbytes / 2);
     // published on the copy stream, i.e. after the samples themselves have landed
@@ -944,7 +1022,7 @@ static int push_bytes(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t
  * a single strided copy and a single publication of the new sample counts instead of one pair per stream. */
 extern "C" int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size_t host_stride, size_t nbytes)
 {
-    if (!e || !host || (nbytes & 3) || !e->iq_owned || nbytes > host_stride) return NRSC5B_EINVAL;
+    if (!e || !host || (nbytes & 3) || !e->iq_owned || nbytes > host_stride || e->am_ring) return NRSC5B_EINVAL;
     const int S = e->dims.nstreams;
     for (int s = 1; s < S; s++)
         if (e->pushed[s] != e->pushed[0]) return NRSC5B_EINVAL;          // streams must be in step
@@ -965,7 +1043,7 @@ extern "C" int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size
 
 extern "C" int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void *dev_buf, size_t nbytes)
 {
-    if (!e || stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned) return NRSC5B_EINVAL;
+    if (!e || stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned || e->am_ring) return NRSC5B_EINVAL;
     size_t off = (size_t)e->pushed[stream] * 2;
     if (off + nbytes > e->dims.in_stride) return NRSC5B_EFULL;
     CK(cudaMemcpyAsync(e->iq_owned + (size_t)stream * e->dims.in_stride + off, dev_buf, nbytes,
@@ -976,7 +1054,7 @@ extern "C" int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void
 
 extern "C" int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_buf, size_t stride, size_t nbytes)
 {
-    if (!e || !dev_buf || (nbytes & 3) || nbytes > stride) return NRSC5B_EINVAL;
+    if (!e || !dev_buf || (nbytes & 3) || nbytes > stride || e->am_ring) return NRSC5B_EINVAL;   // AM cu8 is decimated on arrival
     e->dp.iq = reinterpret_cast<const uint8_t *>(dev_buf);
     e->dims.in_stride = stride;
     for (int s = 0; s < e->dims.nstreams; s++) {

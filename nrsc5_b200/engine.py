@@ -140,13 +140,19 @@ class Engine:
     """
 
     def __init__(self, nstreams: int, input_capacity: int, device: int = 0, log_capacity: int = 1 << 20,
-                 emit_soft: bool = False, input_cs16: bool = False, mode: str = "fm"):
+                 emit_soft: bool = False, input_cs16=None, mode: str = "fm"):
         self._L = load_library()
         self._h = ctypes.c_void_p()
         if mode not in ("fm", "am"):
             raise EngineError("mode must be 'fm' or 'am'")
-        am = mode == "am"                        # AM: hybrid MA1, cs16 at 46 511.72 S/s
-        cfg = _Config(device, nstreams, int(am), input_capacity, log_capacity, int(emit_soft), int(input_cs16 or am))
+        am = mode == "am"
+        # input format: FM defaults to cu8 at 1 488 375 S/s (input_cs16=True: cs16 at 744 187.5 S/s); AM defaults to
+        # cs16 at 46 511.72 S/s (input_cs16=False: cu8 at 1 488 375 S/s, decimated by 32 on the device).
+        # input_capacity is in bytes of what the receive chain keeps per stream: cu8 bytes (FM), cs16 bytes (FM cs16
+        # and AM, whatever AM's input format)
+        if input_cs16 is None:
+            input_cs16 = am
+        cfg = _Config(device, nstreams, int(am), input_capacity, log_capacity, int(emit_soft), int(bool(input_cs16)))
         _check(self._L.nrsc5b_create(ctypes.byref(self._h), ctypes.byref(cfg)), "nrsc5b_create")
         self.nstreams = nstreams
         self._log_cap = log_capacity + 64

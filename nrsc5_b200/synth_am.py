@@ -300,3 +300,16 @@ def make_am_ma1(nframes: int = 10, seed: int = 1234, lead_in: int = 500, carrier
     q[0::2][z] = 1
     cap.cs16 = q
     return cap
+
+
+def am_to_cu8(cs16: np.ndarray, gain: float = 1.0) -> np.ndarray:
+    """cs16 at 46 511.72 S/s -> cu8 at 1 488 375 S/s, the other input format of the AM receiver
+    (input_push_cu8 -> decimate_samples, reference src/input.c:52-117: (u8 - 127) * 4, then five halfband
+    decimators of gain 2 each, so one cu8 LSB is worth 128 cs16 LSB).  Polyphase interpolation by 32."""
+    from scipy.signal import resample_poly
+    z = cs16[0::2].astype(np.float64) + 1j * cs16[1::2].astype(np.float64)
+    up = resample_poly(z, 32, 1) * (gain / 128.0)
+    out = np.empty(2 * up.size, dtype=np.float64)
+    out[0::2] = up.real
+    out[1::2] = up.imag
+    return np.clip(np.rint(out + 127.0), 0, 255).astype(np.uint8)

@@ -52,6 +52,10 @@ orc_am_t *orc_am_new(void);
 void orc_am_free(orc_am_t *o);
 /* mirrors input_push_cs16 in AM mode (reference src/input.c:119); nvalues % 2 == 0 */
 void orc_am_push_cs16(orc_am_t *o, const int16_t *buf, size_t nvalues);
+/* cu8 at 1 488 375 S/s (input_push_cu8 in AM mode: /32 through five halfband stages); nbytes % 4 == 0 */
+void orc_am_push_cu8(orc_am_t *o, const uint8_t *buf, size_t nbytes);
+/* that decimator alone, from a zero state: returns the number of cs16 complex samples written (nbytes / 64) */
+size_t orc_am_decimate(const uint8_t *cu8, size_t nbytes, int16_t *out);
 size_t orc_am_log_size(const orc_am_t *o);
 const uint8_t *orc_am_log_data(const orc_am_t *o);
 

@@ -87,6 +87,10 @@ struct orc_am {
     int psmi, pli, hppi, aabi, rdbi, cfo_wait, samperr;
     unsigned bc, offset_history;
     float angle;
+    /* cu8 input: five cascaded halfband decimators (reference src/input.h:21-25, src/input.c:52-94) */
+    int16_t hb_r[5][15], hb_i[5][15], hb_tap[4];
+    int16_t stage_r[4][2], stage_i[4][2];
+    unsigned offset;
     /* decode (reference src/decode.h:19-62) */
     uint8_t buffer_pl[PW_AM * BLK * 8], buffer_pu[PW_AM * BLK * 8], buffer_s[PW_AM * BLK * 8], buffer_t[PW_AM * BLK * 8];
     uint8_t bl[18000], bu[18000], ml[DIVERSITY + 18000], mu[DIVERSITY + 18000], el[12000], eu[24000];
@@ -638,6 +642,11 @@ orc_am_t *orc_am_new(void)
     o->fin = fftwf_alloc_complex(FFT_AM);
     o->fout = fftwf_alloc_complex(FFT_AM);
     o->plan = fftwf_plan_dft_1d(FFT_AM, o->fin, o->fout, FFTW_FORWARD, FFTW_ESTIMATE);
+    {
+        /* reference src/input.c:33-38, reversed and truncated to int16 as in src/firdecim_q15.c:37-41 */
+        static const float t[4] = { 0.6062333583831787f, -0.13481467962265015f, 0.032919470220804214f, -0.00410953676328063f };
+        for (int i = 0; i < 4; i++) o->hb_tap[i] = (int16_t)(t[3 - i] * 32767.0f);
+    }
     o->phase = 1;
     o->psmi = 1;
     o->pli = o->hppi = o->aabi = o->rdbi = -1;
@@ -665,6 +674,96 @@ void orc_am_push_cs16(orc_am_t *o, const int16_t *buf, size_t nvalues)
         if (++o->fill == NACQ_AM)
             process_window(o);
     }
+}
+
+/* halfband decimator by 2 (reference src/firdecim_q15.c:137-165): w[0..14], w[14] newest; the output is taken
+ * after the even sample of a pair went in, the odd one follows */
+static inline int16_t hb_axis(const int16_t *w, const int16_t *tap)
+{
+    int16_t acc = 0;
+    for (int i = 0; i < 4; i++)
+        acc = (int16_t)(acc + (((w[2 * i] + w[14 - 2 * i]) * tap[i]) >> 15));
+    return (int16_t)(acc + w[7]);
+}
+
+static inline void hb_shift(int16_t *w, int16_t v)
+{
+    memmove(w, w + 1, 14 * sizeof(int16_t));
+    w[14] = v;
+}
+
+static void hb_execute(orc_am_t *o, int stage, const int16_t xr[2], const int16_t xi[2], int16_t *yr, int16_t *yi)
+{
+    hb_shift(o->hb_r[stage], xr[0]);
+    hb_shift(o->hb_i[stage], xi[0]);
+    *yr = hb_axis(o->hb_r[stage], o->hb_tap);
+    *yi = hb_axis(o->hb_i[stage], o->hb_tap);
+    hb_shift(o->hb_r[stage], xr[1]);
+    hb_shift(o->hb_i[stage], xi[1]);
+}
+
+/* mirrors input_push_cu8 in AM mode (reference src/input.c:52-117): (u8 - 127) * 64 >> 4, then /32 through five
+ * halfband stages with ping-pong pair buffers; nbytes counts uint8 values and is a multiple of 4 */
+void orc_am_push_cu8(orc_am_t *o, const uint8_t *buf, size_t nbytes)
+{
+    for (size_t n = 0; n + 3 < nbytes; n += 4) {
+        int16_t xr[2], xi[2], yr, yi;
+        xr[0] = (int16_t)((((int16_t)buf[n + 0] - 127) * 64) >> 4);
+        xi[0] = (int16_t)((((int16_t)buf[n + 1] - 127) * 64) >> 4);
+        xr[1] = (int16_t)((((int16_t)buf[n + 2] - 127) * 64) >> 4);
+        xi[1] = (int16_t)((((int16_t)buf[n + 3] - 127) * 64) >> 4);
+        const unsigned off = o->offset++;
+        hb_execute(o, 0, xr, xi, &o->stage_r[0][off & 1], &o->stage_i[0][off & 1]);
+        int produced = 0;
+        for (int st = 1; st < 5; st++) {
+            const unsigned mask = (1u << st) - 1;
+            if ((off & mask) != mask) break;
+            if (st < 4)
+                hb_execute(o, st, o->stage_r[st - 1], o->stage_i[st - 1], &o->stage_r[st][(off >> st) & 1], &o->stage_i[st][(off >> st) & 1]);
+            else {
+                hb_execute(o, 4, o->stage_r[3], o->stage_i[3], &yr, &yi);
+                produced = 1;
+            }
+        }
+        if (produced) {
+            o->win_r[o->fill] = yr;
+            o->win_i[o->fill] = yi;
+            if (++o->fill == NACQ_AM)
+                process_window(o);
+        }
+    }
+}
+
+/* the decimator alone (kernel-level tests): npairs*... cu8 complex samples -> nbytes/64 cs16 samples */
+size_t orc_am_decimate(const uint8_t *cu8, size_t nbytes, int16_t *out)
+{
+    orc_am_t *o = (orc_am_t *)calloc(1, sizeof(*o));
+    static const float t[4] = { 0.6062333583831787f, -0.13481467962265015f, 0.032919470220804214f, -0.00410953676328063f };
+    for (int i = 0; i < 4; i++) o->hb_tap[i] = (int16_t)(t[3 - i] * 32767.0f);
+    size_t nout = 0;
+    for (size_t n = 0; n + 3 < nbytes; n += 4) {
+        int16_t xr[2], xi[2], yr = 0, yi = 0;
+        xr[0] = (int16_t)((((int16_t)cu8[n + 0] - 127) * 64) >> 4);
+        xi[0] = (int16_t)((((int16_t)cu8[n + 1] - 127) * 64) >> 4);
+        xr[1] = (int16_t)((((int16_t)cu8[n + 2] - 127) * 64) >> 4);
+        xi[1] = (int16_t)((((int16_t)cu8[n + 3] - 127) * 64) >> 4);
+        const unsigned off = o->offset++;
+        hb_execute(o, 0, xr, xi, &o->stage_r[0][off & 1], &o->stage_i[0][off & 1]);
+        for (int st = 1; st < 5; st++) {
+            const unsigned mask = (1u << st) - 1;
+            if ((off & mask) != mask) break;
+            if (st < 4)
+                hb_execute(o, st, o->stage_r[st - 1], o->stage_i[st - 1], &o->stage_r[st][(off >> st) & 1], &o->stage_i[st][(off >> st) & 1]);
+            else {
+                hb_execute(o, 4, o->stage_r[3], o->stage_i[3], &yr, &yi);
+                out[2 * nout] = yr;
+                out[2 * nout + 1] = yi;
+                nout++;
+            }
+        }
+    }
+    free(o);
+    return nout;
 }
 
 size_t orc_am_log_size(const orc_am_t *o) { return o->log.len; }

@@ -35,6 +35,7 @@ def lib():
         L.orc_am_new.restype = ctypes.c_void_p
         L.orc_am_free.argtypes = [ctypes.c_void_p]
         L.orc_am_push_cs16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.orc_am_push_cu8.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.orc_am_log_size.restype = ctypes.c_size_t
         L.orc_am_log_size.argtypes = [ctypes.c_void_p]
         L.orc_am_log_data.restype = ctypes.c_void_p
@@ -77,23 +78,39 @@ def decode(cu8: np.ndarray, chunk: int = 0, want_soft=False, want_blocks=False) 
     return _parse(raw)
 
 
-def decode_am(cs16: np.ndarray, chunk: int = 0) -> RefLog:
-    """AM hybrid MA1 capture (int16 I/Q at 46 511.72 S/s) through oracle/nrsc5_oracle_am.c."""
+def decode_am(samples: np.ndarray, chunk: int = 0) -> RefLog:
+    """AM (MA1 / MA3) capture through oracle/nrsc5_oracle_am.c: int16 = cs16 at 46 511.72 S/s, uint8 = cu8 at
+    1 488 375 S/s (decimated by 32 first, like input_push_cu8 in AM mode)."""
     L = lib()
-    a = np.ascontiguousarray(cs16, dtype=np.int16)
-    n = a.size & ~1
+    a = np.ascontiguousarray(samples)
+    is_cs16 = a.dtype == np.int16
+    assert is_cs16 or a.dtype == np.uint8
+    n = a.size & (~1 if is_cs16 else ~3)
+    push = L.orc_am_push_cs16 if is_cs16 else L.orc_am_push_cu8
     o = L.orc_am_new()
     try:
         if chunk <= 0:
-            L.orc_am_push_cs16(o, a.ctypes.data, n)
+            push(o, a.ctypes.data, n)
         else:
-            chunk &= ~1
+            chunk &= ~1 if is_cs16 else ~3
             for off in range(0, n, chunk):
-                L.orc_am_push_cs16(o, a.ctypes.data + 2 * off, min(chunk, n - off))
+                push(o, a.ctypes.data + a.itemsize * off, min(chunk, n - off))
         raw = ctypes.string_at(L.orc_am_log_data(o), L.orc_am_log_size(o))
     finally:
         L.orc_am_free(o)
     return _parse(raw)
+
+
+def decimate_am(cu8: np.ndarray) -> np.ndarray:
+    """The AM cu8 front end alone (five halfband stages, /32) from a zero state: int16 I/Q interleaved."""
+    a = np.ascontiguousarray(cu8, dtype=np.uint8)
+    n = a.size & ~3
+    out = np.empty(2 * (n // 64), dtype=np.int16)
+    L = lib()
+    L.orc_am_decimate.restype = ctypes.c_size_t
+    got = L.orc_am_decimate(ctypes.c_void_p(a.ctypes.data), ctypes.c_size_t(n), ctypes.c_void_p(out.ctypes.data))
+    assert got == n // 64
+    return out
 
 
 def halfband_fm(cu8: np.ndarray) -> np.ndarray:

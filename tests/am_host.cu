@@ -127,3 +127,96 @@ extern "C" long am_host_decode_lanes(const int16_t *cs16, size_t nvalues, uint8_
     delete tb;
     return n;
 }
+
+// ---- the cu8 front end (decim_tile) under the same fibre emulation, with the engine's ring + tiling arithmetic ----
+namespace {
+struct DecimJob {
+    const uint8_t *ring;
+    unsigned ring_bytes;
+    long long raw_avail, k0;
+    int nout;
+    short2 *out;
+    nbam::DecimScratch *sc;
+    int nlanes;
+};
+DecimJob g_dj;
+bool g_dj_done[1024];
+
+void decim_lane_main()
+{
+    const int l = g_cur_lane;
+    nbam::decim_tile(g_dj.ring, g_dj.ring_bytes, g_dj.raw_avail, g_dj.k0, g_dj.nout, g_dj.out, *g_dj.sc, nbam::Lanes{ l, g_dj.nlanes });
+    g_dj_done[l] = true;
+    g_sync_site = -2;
+    swapcontext(&g_lane_ctx[l], &g_sched_ctx);
+}
+
+// one tile on nlanes fibres (nlanes == 1: plain call); returns false when lanes met at different barriers
+bool run_decim_tile(int nlanes, int order)
+{
+    if (nlanes == 1) {
+        nbam::decim_tile(g_dj.ring, g_dj.ring_bytes, g_dj.raw_avail, g_dj.k0, g_dj.nout, g_dj.out, *g_dj.sc, nbam::Lanes{ 0, 1 });
+        return true;
+    }
+    static std::vector<ucontext_t> ctx;
+    static std::vector<std::vector<char>> stacks;
+    if ((int)ctx.size() < nlanes) {
+        ctx.resize(nlanes);
+        stacks.assign(nlanes, std::vector<char>(256 << 10));
+    }
+    for (int l = 0; l < nlanes; l++) {
+        g_dj_done[l] = false;
+        getcontext(&ctx[l]);
+        ctx[l].uc_stack.ss_sp = stacks[l].data();
+        ctx[l].uc_stack.ss_size = stacks[l].size();
+        ctx[l].uc_link = &g_sched_ctx;
+        makecontext(&ctx[l], decim_lane_main, 0);
+    }
+    g_lane_ctx = ctx.data();
+    bool ok = true;
+    for (;;) {
+        int site = 0, alive = 0;
+        for (int k = 0; k < nlanes; k++) {
+            const int l = order > 0 ? k : nlanes - 1 - k;
+            if (g_dj_done[l]) continue;
+            g_cur_lane = l;
+            swapcontext(&g_sched_ctx, &ctx[l]);
+            if (alive++ == 0) site = g_sync_site;
+            else if (site != g_sync_site) ok = false;
+        }
+        if (!alive || !ok) break;
+    }
+    g_lane_ctx = nullptr;
+    return ok;
+}
+}   // namespace
+
+// cu8 -> cs16 the way the engine does it: pushes of `chunk` bytes land in a ring of `ring_bytes`, every push
+// is followed by the tiles of the outputs that became computable (nrsc5b_push_cu8 in AM mode, engine.cu).
+// Returns the number of cs16 complex samples written, or -3 on barrier divergence.
+extern "C" long am_host_decimate(const uint8_t *cu8, size_t nbytes, int16_t *out, unsigned ring_bytes, size_t chunk, int nlanes,
+                                 int order)
+{
+    using namespace nbam;
+    std::vector<uint8_t> ring(ring_bytes);
+    DecimScratch *sc = new DecimScratch;
+    long long raw_bytes = 0, done = 0;
+    nbytes &= ~(size_t)3;
+    for (size_t off = 0; off < nbytes; off += chunk) {
+        const size_t n = nbytes - off < chunk ? nbytes - off : chunk;
+        for (size_t i = 0; i < n; i++) ring[(raw_bytes + (long long)i) & (ring_bytes - 1)] = cu8[off + i];
+        raw_bytes += (long long)n;
+        const long long raw_avail = raw_bytes / 2, can = raw_avail / 32;
+        for (long long k0 = done; k0 < can; k0 += DEC_T) {
+            const int nout = (int)(can - k0 < DEC_T ? can - k0 : DEC_T);
+            g_dj = DecimJob{ ring.data(), ring_bytes, raw_avail, k0, nout, reinterpret_cast<short2 *>(out) + k0, sc, nlanes };
+            if (!run_decim_tile(nlanes, order)) {
+                delete sc;
+                return -3;
+            }
+        }
+        done = can;
+    }
+    delete sc;
+    return (long)done;
+}

@@ -24,10 +24,11 @@ def fnv1a32(b: bytes) -> int:
     return h
 
 
-def run(lib_path: str, cu8: bytes, chunk: int = 32768, cs16: bool = False):
+def run(lib_path: str, cu8: bytes, chunk: int = 32768, cs16: bool = False, am: bool = False):
     """Decode `cu8` through the public API in `chunk`-byte pushes (main.c:1097-1119 uses 32768);
     returns the event digest list, IQ events left out.  With cs16=True the bytes are int16 I/Q at the
-    decimated rate and go through nrsc5_pipe_samples_cs16 (whose length counts int16 values)."""
+    decimated rate and go through nrsc5_pipe_samples_cs16 (whose length counts int16 values).  am=True selects
+    NRSC5_MODE_AM (nrsc5_set_mode, nrsc5.h:84-85) before the first push."""
     L = ctypes.CDLL(lib_path)
     L.nrsc5_open_pipe.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
     L.nrsc5_set_callback.argtypes = [ctypes.c_void_p, CALLBACK, ctypes.c_void_p]
@@ -62,6 +63,9 @@ def run(lib_path: str, cu8: bytes, chunk: int = 32768, cs16: bool = False):
     rc = L.nrsc5_open_pipe(ctypes.byref(h))
     assert rc == 0, "nrsc5_open_pipe failed"
     L.nrsc5_set_callback(h, cb, None)
+    if am:
+        L.nrsc5_set_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        assert L.nrsc5_set_mode(h, 1) == 0
     buf = ctypes.create_string_buffer(bytes(cu8), len(cu8))
     base = ctypes.addressof(buf)
     for off in range(0, len(cu8), chunk):

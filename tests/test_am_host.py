@@ -33,7 +33,19 @@ def _lib():
     L.am_host_decode_lanes.restype = ctypes.c_long
     L.am_host_decode_lanes.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                        ctypes.c_int]
+    L.am_host_decimate.restype = ctypes.c_long
+    L.am_host_decimate.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_int]
     return L
+
+
+def host_decimate(cu8, ring_bytes=1 << 16, chunk=1 << 15, lanes=1, order=1):
+    a = np.ascontiguousarray(cu8, dtype=np.uint8)
+    out = np.zeros(2 * (a.size // 64), dtype=np.int16)
+    n = _lib().am_host_decimate(a.ctypes.data, a.size, out.ctypes.data, ring_bytes, chunk, lanes, order)
+    assert n != -3, "lanes met at different barriers"
+    assert n == a.size // 64
+    return out
 
 
 def host_decode(cs16, lanes=1, order=1):
@@ -65,3 +77,18 @@ def test_am_engine_code_with_32_emulated_lanes(name, order):
     got = host_decode(cap.cs16, lanes=32, order=order)
     ref = port.decode_am(cap.cs16)
     assert common.summarize(got) == common.summarize(ref)
+
+
+@pytest.mark.parametrize("lanes,order,chunk", [(1, 1, 1 << 15), (256, 1, 40004), (256, -1, 4), (96, 1, 60000)])
+def test_am_cu8_front_end_on_host(lanes, order, chunk):
+    """decim_tile (five cascaded halfband stages, cu8 -> cs16 / 32) with the engine's ring and tiling arithmetic
+    against the oracle's restatement of input_push_cu8 (reference src/input.c:52-117), on random bytes - which
+    drive the int16 accumulators into wrap-around - and on a real AM capture."""
+    rng = np.random.default_rng(21)
+    noise = rng.integers(0, 256, 64 * 3000 + 36, dtype=np.uint8)
+    cap = synth_am.make_am_ma1(nframes=1, seed=2, lead_in=100, carrier=8000.0, unit=40.0)
+    sig = synth_am.am_to_cu8(cap.cs16[: 2 * 4000])
+    for x in (noise, sig):
+        want = port.decimate_am(x)
+        got = host_decimate(x, ring_bytes=1 << 16, chunk=chunk, lanes=lanes, order=order)
+        assert np.array_equal(got, want[: got.size]) and got.size == want.size

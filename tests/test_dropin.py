@@ -67,3 +67,31 @@ def test_dropin_cs16_pipe_matches_reference_events():
     want = common.golden("api_sample_xz.json")["events"]
     assert [e[0] for e in got] == [e[0] for e in want]
     assert [e for e in got if e[0] == "HDC"] == [e for e in want if e[0] == "HDC"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cs16"), (1, "cu8"), (2, "cu8")])
+def test_dropin_am_matches_reference_events(psmi, fmt):
+    """AM through the public API (nrsc5_set_mode(NRSC5_MODE_AM), nrsc5_pipe_samples_cs16 / _cu8): the drop-in and
+    the unmodified reference library deliver the same events on a synthetic MA1 / MA3 capture."""
+    import reftap
+    from nrsc5_b200 import synth_am
+    if not os.path.exists(DROPIN) or not reftap.available():
+        pytest.skip("drop-in or reference library not built")
+    cap = synth_am.make_am_ma1(nframes=8, seed=30 + psmi, lead_in=222, carrier=8000.0, unit=40.0, cfo_hz=0.5, psmi=psmi,
+                               flags=(1, 0, 1, 0))
+    if fmt == "cs16":
+        data, kw = cap.cs16.tobytes(), dict(chunk=32768, cs16=True)
+    else:
+        data, kw = synth_am.am_to_cu8(cap.cs16).tobytes(), dict(chunk=32768)
+    want = nrsc5_api.run(reftap.REF_SO, data, am=True, **kw)
+    got = nrsc5_api.run(DROPIN, data, am=True, **kw)
+    assert [e[0] for e in want].count("SYNC") == 1 and [e[0] for e in want].count("BER") >= 2
+    assert [e[0] for e in got] == [e[0] for e in want]
+    for a, b in zip(got, want):
+        if a[0] == "SYNC":
+            assert a[2:] == b[2:] and abs(a[1] - b[1]) < 0.05           # psmi, pli, hppi, aabi, rdbi
+        elif a[0] == "BER":
+            assert abs(a[1] - b[1]) < 1e-6
+        else:
+            assert a == b

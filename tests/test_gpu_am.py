@@ -13,10 +13,20 @@ from nrsc5_b200 import synth_am
 pytestmark = pytest.mark.gpu
 
 
-def run_am(captures, chunk=None):
-    cap = max(2 * c.size for c in captures) + 4096
-    with nrsc5_b200.Engine(nstreams=len(captures), input_capacity=cap, log_capacity=4 << 20, mode="am") as e:
-        if chunk is None:
+def run_am(captures, chunk=None, cu8=False):
+    """captures: int16 cs16 arrays, or (cu8=True) uint8 arrays at 1 488 375 S/s that the engine decimates by 32."""
+    cap = max(2 * c.size for c in captures) // (16 if cu8 else 1) + 4096
+    with nrsc5_b200.Engine(nstreams=len(captures), input_capacity=cap, log_capacity=4 << 20, mode="am", input_cs16=not cu8) as e:
+        if cu8:
+            n = max(c.size for c in captures)
+            step = chunk or (1 << 22)
+            for off in range(0, n, step):
+                for s, c in enumerate(captures):
+                    piece = c[off: off + step]
+                    if piece.size:
+                        e.push_cu8(s, piece[: piece.size & ~3])
+                e.process()
+        elif chunk is None:
             for s, c in enumerate(captures):
                 e.push_cs16(s, c[: c.size & ~1])
             e.process()
@@ -84,3 +94,15 @@ def test_am_streams_independent_and_chunked():
         want = oracle_digest(port.decode_am(c.cs16))
         assert digest(a) == want
         assert digest(b) == want
+
+
+@pytest.mark.parametrize("psmi", [1, 2])
+def test_am_cu8_input_bit_exact(psmi):
+    """cu8 at 1 488 375 S/s (input_push_cu8 in AM mode): five halfband stages on the device, then the same chain.
+    Pushed in odd-sized pieces so that groups of 32 raw samples straddle pushes and the raw ring wraps."""
+    cap = synth_am.make_am_ma1(nframes=8, seed=50 + psmi, lead_in=555, carrier=8000.0, unit=40.0, cfo_hz=-0.6, psmi=psmi)
+    cu8 = synth_am.am_to_cu8(cap.cs16)
+    want = oracle_digest(port.decode_am(cu8))
+    assert sum(1 for e in want if e[0] == "F" and e[1] == 0) >= 16
+    assert digest(run_am([cu8], cu8=True)[0]) == want
+    assert digest(run_am([cu8], chunk=300004, cu8=True)[0]) == want
