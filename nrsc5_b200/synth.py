@@ -224,7 +224,8 @@ class FmCapture:
     cu8: np.ndarray                      # uint8 [2 * nsamples], I/Q interleaved
     p1_frames: list = field(default_factory=list)    # list of uint8[146176] frame bits
     pids_frames: list = field(default_factory=list)  # list of uint8[80], block order
-    p3_frames: list = field(default_factory=list)    # MP3: list of uint8[4608] the receiver will output
+    p3_frames: list = field(default_factory=list)    # MP2/MP3/MP11: list of uint8[2304 or 4608] the receiver will output
+    p4_frames: list = field(default_factory=list)    # MP11: list of uint8[4608] (PX2)
     psmi: int = 1
     lead_in: int = 0
 
@@ -238,15 +239,19 @@ IV_N = 147456                         # interleaver IV span: 16 P3 frames = 32 b
 
 
 @lru_cache(maxsize=None)
-def interleaver_iv_delay() -> np.ndarray:
-    """D[m]: the deinterleaver's output m (mod IV_N) is the input it received D[m] positions earlier,
-    1 <= D <= IV_N (reference src/decode.c:344-376 for MP3/MP11: J=4, B=32, C=36, M=2): it reads
-    internal[A(m)] before it stores input m at internal[m]."""
-    J, B, C, M = 4, 32, 36, 2
+def interleaver_iv_delay(frame_len: int = P3_BITS) -> np.ndarray:
+    """D[m]: the deinterleaver's output m (mod N) is the input it received D[m] positions earlier, 1 <= D <= N
+    (reference src/decode.c:344-376; MP3/MP11: J=4, M=2, N=147456; MP2, frame_len 2304: J=2, M=4, N=73728):
+    it reads internal[A(m)] before it stores input m at internal[m]."""
+    if frame_len == P3_BITS:
+        J, M, N = 4, 2, IV_N
+    else:
+        J, M, N = 2, 4, IV_N // 2
+    B, C = 32, 36
     bk_bits, bk_adj = 32 * C, 32 * C - 1
-    m = np.arange(IV_N, dtype=np.int64)
-    part = (m // M) % J
-    pti = np.empty(IV_N, dtype=np.int64)
+    m = np.arange(N, dtype=np.int64)
+    part = ((m + 2 * (M // 4)) // M) % J
+    pti = np.empty(N, dtype=np.int64)
     for pp in range(J):
         sel = part == pp
         pti[sel] = np.arange(int(sel.sum()))
@@ -254,25 +259,52 @@ def interleaver_iv_delay() -> np.ndarray:
     row = ((11 * pti) % bk_bits) // C
     col = (pti * 11) % C
     A = (block * 32 + row) * (J * C) + part * C + col
-    return np.where(A < m, m - A, m - A + IV_N)
+    return np.where(A < m, m - A, m - A + N)
 
 
-def build_p3_frame_bits(rng) -> np.ndarray:
-    """4608 descrambled P3 frame bits as handed to frame_push() (frame.c:658-662: PCI at logical bits
-    120 + 184 h); PCI says fixed data only and the last byte rules out a fixed-data sync (frame.c:448-456)."""
-    logical = np.zeros(P3_BITS, dtype=np.uint8)
-    pci_pos = 120 + 184 * np.arange(24)
-    is_pci = np.zeros(P3_BITS, dtype=bool)
+def build_p3_frame_bits(rng, nbits: int = P3_BITS) -> np.ndarray:
+    """4608 (MP2: 2304) descrambled P3 / P4 frame bits as handed to frame_push() (frame.c:658-668: PCI at logical
+    bits 120 + 184 h, MP2: 120 + 88 h); PCI says fixed data only and the last byte rules out a fixed-data sync
+    (frame.c:448-456)."""
+    step = 184 if nbits == P3_BITS else 88
+    logical = np.zeros(nbits, dtype=np.uint8)
+    pci_pos = 120 + step * np.arange(24)
+    is_pci = np.zeros(nbits, dtype=bool)
     is_pci[pci_pos] = True
     logical[pci_pos] = [(PCI_FIXED >> (23 - h)) & 1 for h in range(24)]
-    pdu = rng.integers(0, 256, (P3_BITS - 24) // 8, dtype=np.uint8)
+    pdu = rng.integers(0, 256, (nbits - 24) // 8, dtype=np.uint8)
     pdu[-1] = 0x12
     logical[~is_pci] = np.unpackbits(pdu)
-    i = np.arange(P3_BITS)
+    i = np.arange(nbits)
     phys = (i & ~7) + 7 - (i & 7)
-    bits = np.zeros(P3_BITS, dtype=np.uint8)
+    bits = np.zeros(nbits, dtype=np.uint8)
     bits[phys] = logical
     return bits
+
+
+def _px_stream(prng, nblocks: int, first_even: int, frame_len: int):
+    """The bit stream of one extended-partition group (PX1 or PX2) over `nblocks` blocks of `frame_len` soft bits
+    each, and the frames a receiver hands out: the deinterleaver starts with the first even block it sees and
+    returns frame c (inputs of blocks 2c, 2c+1 counted from there) once 16 frames have gone in; transmit stream
+    position j carries the punctured coded bit of output position k = j + D[k mod N]."""
+    ncalls = (nblocks - first_even) // 2
+    D = interleaver_iv_delay(frame_len)
+    N = D.size
+    px = prng.integers(0, 2, nblocks * frame_len, dtype=np.uint8)
+    tx = px[first_even * frame_len:]
+    pn = pn_sequence(frame_len)
+    keep3 = np.tile(np.array([1, 0, 1, 1, 0, 1], dtype=bool), frame_len * 3 // 6)
+    frames = []
+    for c in range(ncalls):
+        fb = build_p3_frame_bits(prng, frame_len)
+        u = conv_encode_tb(fb ^ pn).reshape(-1)[keep3]                 # 2 * frame_len transmitted bits
+        k = c * 2 * frame_len + np.arange(2 * frame_len, dtype=np.int64)
+        j = k - D[k % N]
+        ok = j >= 0
+        tx[j[ok]] = u[ok]
+        if c >= N // (2 * frame_len):
+            frames.append(fb)
+    return px, frames
 
 
 @lru_cache(maxsize=None)
@@ -304,6 +336,11 @@ def make_fm_mp1(**kw) -> FmCapture:
     return make_fm(psmi=1, **kw)
 
 
+def compat_mode(psmi: int) -> int:
+    """compatibility_mode[psmi] of the reference (src/sync.c:30-35)."""
+    return (0, 1, 2, 3, 1, 5, 6, 5, 6, 1, 2, 11, 1, 5, 6, 5)[psmi & 15] if psmi & 15 else (0 if psmi == 0 else 6)
+
+
 def make_fm_mp3(**kw) -> FmCapture:
     """FM extended hybrid MP3 (PSMI 3): 13 reference subcarriers and 12 partitions per sideband, P3 on the
     two PX1 partitions per sideband.  P3 frames only come out after the interleaver has filled
@@ -315,12 +352,17 @@ def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 10
             noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
             tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
             start_bc: int = 0) -> FmCapture:
-    """FM capture (PSMI 1 or 3) holding `nframes` complete L1 frames
+    """FM capture (PSMI 1, 2, 3, 5, 6 or 11) holding `nframes` complete L1 frames
     followed by `tail_blocks` further blocks so the last frame flushes
-    (the reference has no flush call)."""
-    assert psmi in (1, 3)
+    (the reference has no flush call).
+
+    What the reference does with the service modes (src/sync.c:343-357,537-595): MP2 = one more partition per
+    sideband carrying P3 frames of 2304 bits (PX1); MP3 = two more, P3 frames of 4608 bits; MP11 = four more,
+    PX1 as in MP3 plus PX2 with P4 frames of 4608 bits; MP5 / MP6 = fourteen partitions per sideband tracked,
+    equalised and counted in the MER, only the twenty main ones decoded (filled with unrelated QPSK here)."""
+    assert psmi in (1, 2, 3, 5, 6, 11)
     rng = np.random.default_rng(seed)
-    nref = 11 if psmi == 1 else 13
+    nref = {1: 11, 2: 12, 3: 13, 5: 15, 6: 15, 11: 15}[psmi]
     nblocks = nframes * BLOCKS_PER_FRAME + tail_blocks
     idx_i = interleaver_i_index()
     idx_ii = interleaver_ii_index()
@@ -347,29 +389,28 @@ def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 10
             pids_this.append(pb)
         mats.append((bits, pids_this, mat.reshape(16, 32, 20, 36)))
 
-    # P3 (MP3): the deinterleaver starts with the first even block it sees and hands out frame c (inputs of
-    # blocks 2c, 2c+1 counted from there) once 16 frames have gone in; transmit stream position j carries the
-    # punctured coded bit of output position k = j + D[k mod N]
-    px1 = None
+    # extended partitions: (first bin of the 18 data carriers, ...) per group in the receiver's demap order
+    # (sync.c:537-595) and the bits they carry, [block][symbol][group][carrier][re, im]
+    first_even = start_bc % 2                         # PX blocks before the first even block are read by nobody
+    ext = []                                          # (bases, bits)
     if psmi == 3:
-        first_even = start_bc % 2                     # blocks before it carry PX1 bits nobody reads
-        ncalls = (nblocks - first_even) // 2
-        D = interleaver_iv_delay()
-        prng = np.random.default_rng(seed + 7919)
-        px1 = prng.integers(0, 2, nblocks * PX1_BLOCK, dtype=np.uint8)
-        tx = px1[first_even * PX1_BLOCK:]
-        pn_p3 = pn_sequence(P3_BITS)
-        keep3 = np.tile(np.array([1, 0, 1, 1, 0, 1], dtype=bool), P3_BITS * 3 // 6)
-        for c in range(ncalls):
-            fb = build_p3_frame_bits(prng)
-            u = conv_encode_tb(fb ^ pn_p3).reshape(-1)[keep3]          # 9216 transmitted bits
-            k = c * 2 * PX1_BLOCK + np.arange(2 * PX1_BLOCK, dtype=np.int64)
-            j = k - D[k % IV_N]
-            ok = j >= 0
-            tx[j[ok]] = u[ok]
-            if c >= IV_N // (2 * PX1_BLOCK):
-                cap.p3_frames.append(fb)
-        px1 = px1.reshape(nblocks, BLKSZ, 4, 18, 2)   # [block][symbol][lower q0, lower q1, upper q0, upper q1][carrier][re, im]
+        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK)
+        ext.append(((LB_START + 190 + 1, LB_START + 209 + 1, UB_END - 228 + 1, UB_END - 209 + 1),
+                    px1.reshape(nblocks, BLKSZ, 4, 18, 2)))
+    elif psmi == 2:
+        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK // 2)
+        ext.append(((LB_START + 190 + 1, UB_END - 209 + 1), px1.reshape(nblocks, BLKSZ, 2, 18, 2)))
+    elif psmi == 11:
+        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK)
+        px2, cap.p4_frames = _px_stream(np.random.default_rng(seed + 7920), nblocks, first_even, PX1_BLOCK)
+        ext.append(((LB_START + 190 + 1, LB_START + 209 + 1, UB_END - 228 + 1, UB_END - 209 + 1),
+                    px1.reshape(nblocks, BLKSZ, 4, 18, 2)))
+        ext.append(((LB_START + 228 + 1, LB_START + 247 + 1, UB_END - 266 + 1, UB_END - 247 + 1),
+                    px2.reshape(nblocks, BLKSZ, 4, 18, 2)))
+    elif psmi in (5, 6):
+        fill = np.random.default_rng(seed + 7921).integers(0, 2, (nblocks, BLKSZ, 8, 18, 2), dtype=np.uint8)
+        ext.append((tuple(LB_START + 19 * q + 1 for q in range(10, 14)) + tuple(UB_END - 19 * (q + 1) + 1 for q in range(13, 9, -1)),
+                    fill))
 
     sh = _shape2x()
     sig = np.zeros(nblocks * BLKSZ * 2 * FFTCP, dtype=np.complex128)
@@ -384,10 +425,10 @@ def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 10
             refs[LB_START + 19 * i] = raw
             refs[UB_END - 19 * i] = raw
         S = _block_matrix_to_bins(mat[bc], refs)
-        if px1 is not None:                           # PX1 partitions (sync.c:552-573)
-            symx = 2.0 * px1[blk].astype(np.float64) - 1.0
-            iqx = symx[..., 0] + 1j * symx[..., 1]    # [32, 4, 18]
-            for q, base in enumerate((LB_START + 190 + 1, LB_START + 209 + 1, UB_END - 228 + 1, UB_END - 209 + 1)):
+        for bases, bits_x in ext:                     # PX1 / PX2 / filler partitions (sync.c:537-595)
+            symx = 2.0 * bits_x[blk].astype(np.float64) - 1.0
+            iqx = symx[..., 0] + 1j * symx[..., 1]    # [32, groups, 18]
+            for q, base in enumerate(bases):
                 S[:, base:base + 18] = iqx[:, q, :]
         # receiver computes fftshift(FFT(conj(x)));  build y = conj(x) at 2x rate
         S2 = np.zeros((BLKSZ, 2 * FFT), dtype=np.complex128)

@@ -47,6 +47,16 @@ SYNTH_CASES = {
 MP3_CASE = dict(nframes=4, seed=11, lead_in=300, tail_blocks=2)
 
 
+# the other FM service modes the reference tells apart (src/sync.c:343-357,537-595): MP2 (11 partitions per sideband,
+# 2304-bit P3), MP5 / MP6 (14 partitions tracked and counted in the MER), MP11 (14 partitions, P3 on PX1, P4 on PX2)
+FM_MODE_CASES = {
+    "mp2": dict(psmi=2, nframes=4, seed=22, lead_in=300, tail_blocks=2, cfo_hz=50.0, noise_lsb=4.0),
+    "mp5": dict(psmi=5, nframes=3, seed=25, lead_in=411, tail_blocks=2, cfo_hz=-80.0, noise_lsb=6.0),
+    "mp6": dict(psmi=6, nframes=3, seed=26, lead_in=97, tail_blocks=2, noise_lsb=14.0),
+    "mp11": dict(psmi=11, nframes=4, seed=31, lead_in=300, tail_blocks=2, cfo_hz=50.0, noise_lsb=4.0),
+}
+
+
 # AM hybrid MA1 (psmi 1) and all-digital MA3 (psmi 2), cs16; the *_noisy cases have a channel
 # BER of about 1e-3 so that the K=9 Viterbi decoders correct real errors
 AM_CASES = {

@@ -48,6 +48,38 @@ def test_port_matches_golden_mp3():
     assert len(p3) >= 8 and set(p3) <= set(g["generated_p3_fnv"])     # round trip: only generated frames come out
 
 
+@pytest.mark.parametrize("name", list(common.FM_MODE_CASES))
+def test_port_matches_golden_service_modes(name):
+    """MP2 (2304-bit P3 through interleaver IV with J=2, M=4), MP5 / MP6 (14 partitions per sideband in the Costas
+    loops, the equaliser and the MER), MP11 (PX1 -> P3, PX2 -> P4 with the lower sideband's scale on both halves,
+    sync.c:591-592): events, PDUs and soft bits identical to what the unmodified reference put into the golden file,
+    and every P1 / P3 / P4 frame that comes out is one the generator put in."""
+    g = common.golden("synth_fm_modes.json")[name]
+    cap = synth.make_fm(**common.FM_MODE_CASES[name])
+    if common.fnv1a32(cap.cu8[:1 << 20].tobytes()) != g["input_fnv"]:
+        pytest.skip("numpy generator stream differs from the one the golden file was made with")
+    log = port.decode(cap.cu8, want_soft=True)
+    assert common.summarize(log) == g["events"]
+    assert _soft_fnv(log) == g["soft_fnv"]
+    for lc, key, least in ((0, "generated_p1_fnv", 2), (1, "generated_p3_fnv", 8 if g["generated_p3_fnv"] else 0),
+                           (2, "generated_p4_fnv", 8 if g["generated_p4_fnv"] else 0)):
+        got = [common.fnv1a32(p["bits"]) for t, p in log.records if t == reftap.REC_FRAME and p["lc"] == lc]
+        assert len(got) >= least and set(got) <= set(g[key])
+
+
+@pytest.mark.skipif(not reftap.available(), reason="reference oracle not built")
+@pytest.mark.parametrize("psmi", [2, 5, 11])
+def test_port_matches_reference_live_service_modes(psmi):
+    """The restatement against the unmodified reference on a capture that is not in the golden file (other seed,
+    start block and noise), so that the pin does not rest on four inputs only."""
+    cap = synth.make_fm(psmi=psmi, nframes=3, seed=100 + psmi, lead_in=1234, tail_blocks=2, cfo_hz=-150.0, noise_lsb=10.0,
+                        start_bc=5)
+    ref = reftap.decode(cap.cu8, want_soft=True)
+    log = port.decode(cap.cu8, want_soft=True)
+    assert common.summarize(log) == common.summarize(ref)
+    assert _soft_fnv(log) == _soft_fnv(ref)
+
+
 def test_port_matches_golden_sample():
     raw = common.load_sample()
     if raw is None:
