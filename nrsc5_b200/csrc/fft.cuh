@@ -18,7 +18,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 __device__ __forceinline__ void bar_sync(int id)
 {
     if (id == 0) __syncthreads();
+#if defined(NB_EMU)                      // tests/emu: the CPU emulator has no PTX
+    else emu_bar_sync(id, 128);
+#else
     else asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory");
+#endif
 }
 __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }   // * (-j)
 

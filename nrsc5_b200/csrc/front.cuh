@@ -1069,7 +1069,11 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDims d, int max_blocks)
 {
+#if defined(NB_EMU)
+    unsigned char *front_smem_raw = emu::dyn_smem();
+#else
     extern __shared__ __align__(16) unsigned char front_smem_raw[];
+#endif
     FrontSmem &sm = *reinterpret_cast<FrontSmem *>(front_smem_raw);
     const int t = threadIdx.x, team = t >> 7, tl = t & 127;
     const int s = blockIdx.x;

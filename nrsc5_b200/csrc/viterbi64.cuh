@@ -61,19 +61,31 @@ struct V64Args {
 __device__ __forceinline__ unsigned v64_umax(unsigned a, unsigned b)
 {
     unsigned r;
+#if defined(NB_EMU)
+    r = emu_max_u16x2(a, b);
+#else
     asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
     return r;
 }
 __device__ __forceinline__ unsigned v64_umin(unsigned a, unsigned b)
 {
     unsigned r;
+#if defined(NB_EMU)
+    r = emu_min_u16x2(a, b);
+#else
     asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
     return r;
 }
 __device__ __forceinline__ unsigned v64_prmt(unsigned a, unsigned b, unsigned sel)
 {
     unsigned r;
+#if defined(NB_EMU)
+    r = emu_prmt(a, b, sel);
+#else
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+#endif
     return r;
 }
 
@@ -284,7 +296,11 @@ __device__ __forceinline__ int v64_pad(int q) { return q + (q >> 5); }
 
 __global__ void __launch_bounds__(V64_EMIT_WARPS * 32) k_v64_emit(V64Args a)
 {
+#if defined(NB_EMU)
+    unsigned char *v64_smem = emu::dyn_smem();
+#else
     extern __shared__ __align__(16) unsigned char v64_smem[];
+#endif
     const int f = blockIdx.y;
     if (!a.ready[(size_t)f * a.stride]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

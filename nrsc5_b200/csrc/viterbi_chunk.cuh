@@ -203,7 +203,11 @@ constexpr int VITC_EMIT_STEPS = CH_LEN + VITC_HEAD;    // staged decisions per c
 // downwards; a wrong guess is repaired by re-walking that segment.
 __global__ void __launch_bounds__(VITC_EMIT_WARPS * 32) k_vitc_emit(VitcArgs a)
 {
+#if defined(NB_EMU)
+    unsigned char *vitc_smem = emu::dyn_smem();
+#else
     extern __shared__ __align__(16) unsigned char vitc_smem[];
+#endif
     const int f = blockIdx.y;
     if (!a.ready[(size_t)f * a.ready_stride]) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;

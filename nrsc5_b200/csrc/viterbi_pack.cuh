@@ -30,19 +30,31 @@ constexpr int VITC_HEAD_STEPS = 128;
 __device__ __forceinline__ unsigned vadd16(unsigned a, unsigned b)
 {
     unsigned r;
+#if defined(NB_EMU)
+    r = emu_add_s16x2(a, b);
+#else
     asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
     return r;
 }
 __device__ __forceinline__ unsigned vmax16(unsigned a, unsigned b)
 {
     unsigned r;
+#if defined(NB_EMU)
+    r = emu_max_s16x2(a, b);
+#else
     asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
     return r;
 }
 __device__ __forceinline__ unsigned vmin16(unsigned a, unsigned b)
 {
     unsigned r;
+#if defined(NB_EMU)
+    r = emu_min_s16x2(a, b);
+#else
     asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+#endif
     return r;
 }
 __device__ __forceinline__ unsigned vneg16(unsigned a) { return vadd16(~a, 0x00010001u); }

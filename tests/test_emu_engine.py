@@ -1,0 +1,63 @@
+"""The GPU parity tests run on a box WITHOUT a GPU: the engine's CUDA sources, unmodified, are compiled with g++
+against a CPU emulation of the CUDA execution model (tests/emu: one fibre per CUDA thread, real barriers, shared
+memory, shuffles) into tests/_build/libnrsc5_b200_emu.so, and the very test functions of tests/test_gpu_*.py are
+run against that library.
+
+What this proves and what it does not: the kernels' logic - indexing, work split, barrier placement (a missing or
+divergent barrier deadlocks the emulator, which reports it instead of hanging a device), the host side of the C
+ABI - is exercised bit for bit against the oracle on the CPU tier.  It says nothing about speed, and floating
+point can differ from the GPU's in the last place (glibc's sincosf/atan2f, exact instead of approximate division),
+so the `-m gpu` run of the same tests on a B200 remains the parity gate.  The emulator is test infrastructure: the
+product library (nrsc5_b200/build.py, nvcc) has no CPU path.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import common
+import port
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+pytestmark = pytest.mark.skipif(not port.available(), reason="oracle/_ref/liboracle.so not built")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulated_engine():
+    import build_emu
+    from nrsc5_b200 import engine as eng
+    so = build_emu.build()
+    saved = (eng.lib_path, eng._lib)
+    eng.lib_path = lambda: so
+    eng._lib = None
+    yield
+    eng.lib_path, eng._lib = saved
+
+
+import test_gpu_am as _am            # noqa: E402
+import test_gpu_chain as _chain      # noqa: E402
+import test_gpu_stages as _stages    # noqa: E402
+
+# kernel-level
+test_halfband_bit_exact = _stages.test_halfband_bit_exact
+test_fft2048_matches_fp64 = _stages.test_fft2048_matches_fp64
+test_viterbi_random_soft_bit_exact = _stages.test_viterbi_random_soft_bit_exact
+test_viterbi_saturating_and_noisy = _stages.test_viterbi_saturating_and_noisy
+test_viterbi_fast_path_and_fallback_agree = _stages.test_viterbi_fast_path_and_fallback_agree
+test_viterbi_p1_length_bit_exact = _stages.test_viterbi_p1_length_bit_exact
+test_rs_decode_bit_exact = _stages.test_rs_decode_bit_exact
+# whole chain, FM
+test_synth_pdus_bit_exact = _chain.test_synth_pdus_bit_exact
+test_mp3_p1_pids_p3_bit_exact = _chain.test_mp3_p1_pids_p3_bit_exact
+test_chunked_push_matches_single_push = _chain.test_chunked_push_matches_single_push
+test_drain_all_equals_per_stream_drain = _chain.test_drain_all_equals_per_stream_drain
+test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_is_trimmed_to_the_input_buffer
+test_cs16_input_equals_cu8_input = _chain.test_cs16_input_equals_cu8_input
+test_multi_stream_independent = _chain.test_multi_stream_independent
+# whole chain, AM
+test_am_pdus_bit_exact = _am.test_am_pdus_bit_exact
+test_am_streams_independent_and_chunked = _am.test_am_streams_independent_and_chunked
+test_am_cu8_input_bit_exact = _am.test_am_cu8_input_bit_exact
