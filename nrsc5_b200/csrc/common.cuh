@@ -88,6 +88,14 @@ struct StreamState {
     int p3_pending;            // P3 frames waiting for the decode kernels that follow k_stream
     long long p3_k0[8];        // interleaver position of each frame's first soft bit
     unsigned p3_rec[8];        // log offset of each frame's reserved FRAME record
+    // the other extended-partition channels, decoded by kernel groups the host only launches once a stream has
+    // asked for them (g_px_need): [0] = MP2's 2304-bit P3 frames (PX1 ring, one partition per sideband),
+    // [1] = MP11's P4 frames (PX2 ring)
+    long long px2_total;       // PX2 soft bits taken in since the interleaver (re)started
+    int px2_started;
+    int xq_pending[2];
+    long long xq_k0[2][8];
+    unsigned xq_rec[2][8];
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
     // output log cursor
     unsigned log_len;
@@ -112,7 +120,22 @@ struct EngineDims {
     size_t log_cap;            // bytes of log per stream
     int emit_soft;
     int cs16;                  // input is cs16 at the decimated rate: 4 bytes per sample, no halfband
+    int px_enabled;            // extra decode groups the host launches after k_stream: bit 0 = MP2's P3, bit 1 = MP11's P4
 };
+
+// buffers of one extra extended-partition decode group (same roles as the p3_* arrays)
+struct PxBufs {
+    int8_t *vin;
+    uint2 *dec;
+    uint32_t *spec, *end;
+    int *endstate;
+    uint2 *fspec, *fend;
+    int *fhstate, *ftbend;
+    uint32_t *bits;
+    int *flags;
+};
+constexpr int PX_NEED_SHORT = 1, PX_NEED_PX2 = 2;
+constexpr int P3S_LEN = 2304, IV_NS = IV_N / 2;    // MP2: P3 frame bits, interleaver IV span (decode.c:346-350)
 
 // Pointers to all device arrays, passed by value to kernels.
 struct DevPtrs {
@@ -142,6 +165,9 @@ struct DevPtrs {
     int *p3_fhstate, *p3_ftbend;    // [S][8][5]
     uint32_t *p3_bits;         // [S][8][144] decoded (still scrambled) bits
     int *p3_flags;             // [S][8][4] ready, slow, retry, -
+    int8_t *px2_ring;          // [S][2 * IV_N] PX2 soft bits (MP11)
+    const uint32_t *iv_delay_s;     // [IV_NS] interleaver IV of MP2 (J=2, M=4)
+    PxBufs xb[2];              // extra groups (null until the host enables them)
     uint8_t *log;              // [S][log_cap]
     const float *shape;        // [2160]
     const float2 *twid;        // [FFT_TW] twiddle tables of fft2048_block (fft.cuh)

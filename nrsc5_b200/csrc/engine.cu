@@ -321,6 +321,97 @@ __host__ __device__ inline VitcArgs p3_vitc_args(const DevPtrs &dp)
     return a;
 }
 
+// ---- the extra extended-partition groups: MP2's 2304-bit P3 frames (which = 0: PX1 ring, interleaver IV with J=2,
+// M=4, span 73728) and MP11's P4 frames (which = 1: PX2 ring, the MP3 interleaver).  Same steps as the P3 group
+// above; the host adds them to a pass only after a stream has asked for them (g_px_need), so the hybrid modes pay
+// nothing for them.
+__global__ void __launch_bounds__(256) k_px_gather(DevPtrs p, EngineDims d, int which)
+{
+    const int s = blockIdx.y, slot = blockIdx.x, t = threadIdx.x;
+    const StreamState &st = p.st[s];
+    const PxBufs &xb = p.xb[which];
+    int *fl = xb.flags + ((size_t)s * P3_SLOTS + slot) * 4;
+    const bool on = slot < st.xq_pending[which];
+    if (t == 0) { fl[0] = on; fl[1] = 0; fl[2] = 0; }
+    if (!on) return;
+    const long long k0 = st.xq_k0[which][slot];
+    const int len = which == 0 ? P3S_LEN : P3_LEN, span = which == 0 ? IV_NS : IV_N;
+    const uint32_t *delay = which == 0 ? p.iv_delay_s : p.iv_delay;
+    const int8_t *ring = (which == 0 ? p.px_ring : p.px2_ring) + (size_t)s * PX_RING;
+    uint32_t *vout = reinterpret_cast<uint32_t *>(xb.vin + ((size_t)s * P3_SLOTS + slot) * (3 * len));
+    for (int g = t; g < 3 * len / 12; g += 256) {           // depuncture 1,0,1,1,0,1 as in k_p3_gather
+        int8_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const long long k = k0 + 8 * g + i;
+            const long long j = k - (long long)__ldg(&delay[k % span]);
+            v[i] = ring[j % PX_RING];
+        }
+        auto b = [&](int i) { return (uint32_t)(uint8_t)v[i]; };
+        vout[3 * g + 0] = b(0) | (b(1) << 16) | (b(2) << 24);
+        vout[3 * g + 1] = (b(3) << 8) | (b(4) << 16);
+        vout[3 * g + 2] = b(5) | (b(6) << 8) | (b(7) << 24);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_px_fin(DevPtrs p, EngineDims d, int which)
+{
+    const int s = blockIdx.y, slot = blockIdx.x, t = threadIdx.x;
+    const StreamState &st = p.st[s];
+    if (slot >= st.xq_pending[which]) return;
+    const unsigned rec = st.xq_rec[which][slot];
+    if (rec == 0xffffffffu) return;
+    const int len = which == 0 ? P3S_LEN : P3_LEN;
+    uint8_t *frame = p.log + (size_t)s * d.log_cap + rec + 8;          // past lc, nbits
+    const uint32_t *bw = p.xb[which].bits + ((size_t)s * P3_SLOTS + slot) * (len / 32);
+    for (int w = t; w < len / 32; w += 128) {
+        const uint32_t x = bw[w] ^ p.pnw[w];                            // the descrambler restarts with every frame
+        reinterpret_cast<uint32_t *>(frame)[w] = __brev(__byte_perm(x, 0, 0x0123));
+    }
+}
+
+__host__ __device__ inline V64Args px_v64_args(const DevPtrs &dp, int which)
+{
+    const PxBufs &xb = dp.xb[which];
+    const int len = which == 0 ? P3S_LEN : P3_LEN;
+    V64Args a;
+    a.vin = xb.vin;
+    a.dec = xb.dec;
+    a.vspec = xb.spec;
+    a.vend = xb.end;
+    a.endstate = xb.endstate;
+    a.bitsw = xb.bits;
+    a.ready = xb.flags;
+    a.retry = xb.flags + 2;
+    a.stride = 4;
+    a.len = len;
+    a.ch = 256;
+    a.nch = (len + 64 + 255) / 256;
+    a.dec_stride = P3_DEC_STRIDE;
+    return a;
+}
+
+__host__ __device__ inline VitcArgs px_vitc_args(const DevPtrs &dp, int which)
+{
+    const PxBufs &xb = dp.xb[which];
+    const int len = which == 0 ? P3S_LEN : P3_LEN;
+    VitcArgs a;
+    a.vin = xb.vin;
+    a.dec = xb.dec;
+    a.vspec = xb.fspec;
+    a.vend = xb.fend;
+    a.hstate = xb.fhstate;
+    a.tbend = xb.ftbend;
+    a.bitsw = xb.bits;
+    a.ready = xb.flags + 2;
+    a.slow = xb.flags + 1;
+    a.ready_stride = 4;
+    a.len = len;
+    a.nch = (len + 64 + CH_LEN - 1) / CH_LEN;
+    a.dec_stride = P3_DEC_STRIDE;
+    return a;
+}
+
 constexpr size_t VITC_EMIT_SMEM = (size_t)VITC_EMIT_WARPS * VITC_EMIT_STEPS * sizeof(uint2);
 
 // input_reset for a range of streams (reference src/input.c:126-138)
@@ -604,6 +695,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->dims.log_cap = cfg->log_capacity ? ((cfg->log_capacity + 15) & ~(size_t)15) : (1u << 20);
     e->dims.emit_soft = cfg->emit_soft;
     e->dims.cs16 = cfg->input_cs16 ? 1 : 0;
+    e->dims.px_enabled = 0;
     e->pushed.assign(S, 0);
     e->drained.assign(S, 0);
     int rc = upload_tables(cfg->device);
@@ -661,6 +753,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     {
         const size_t F = (size_t)S * P3_SLOTS;
         DA(px_ring, int8_t, (size_t)S * PX_RING);
+        DA(px2_ring, int8_t, (size_t)S * PX_RING);
         DA(p3_vin, int8_t, F * P3_VIT);
         DA(p3_dec, uint2, F * P3_DEC_STRIDE);
         DA(p3_spec, uint32_t, F * 19 * 32);
@@ -743,6 +836,21 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
             if (rc) { nrsc5b_destroy(e); return rc; }
             cudaMemcpy(ddl, dl.data(), dl.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
             dp.iv_delay = ddl;
+            // MP2 (frame length 2304): J=2, M=4, span 73728, partition = ((m + 2) / 4) % 2
+            std::vector<uint32_t> ds(IV_NS);
+            unsigned pts[2] = { 0, 0 };
+            for (unsigned m = 0; m < (unsigned)IV_NS; m++) {
+                const unsigned part = ((m + 2) / 4) % 2, pti = pts[part]++;
+                const unsigned block = (pti + part * 7 - 1151 * (pti / 1152)) % 32;
+                const unsigned row = ((11 * pti) % 1152) / 36, col = (pti * 11) % 36;
+                const unsigned A = (block * 32 + row) * 72 + part * 36 + col;
+                ds[m] = A < m ? m - A : m - A + IV_NS;
+            }
+            uint32_t *dds = nullptr;
+            rc = dev_alloc(e, &dds, IV_NS);
+            if (rc) { nrsc5b_destroy(e); return rc; }
+            cudaMemcpy(dds, ds.data(), ds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+            dp.iv_delay_s = dds;
         }
         uint32_t *dlut = nullptr;
         rc = dev_alloc(e, &dlut, P1_ENC);
@@ -1105,6 +1213,40 @@ static void launch_p1(nrsc5b_engine *e)
     launch_vitc(p3_vitc_args(e->dp), S * P3_SLOTS, e->stream);
     k_p3_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims);
     e->stats.kernel_launches += 8;
+    // MP2's short P3 frames / MP11's P4 frames: only once a stream has asked for the group (enable_px_groups)
+    for (int which = 0; which < 2; which++) {
+        if (!(e->dims.px_enabled & (1 << which))) continue;
+        k_px_gather<<<dim3(P3_SLOTS, S), 256, 0, e->stream>>>(e->dp, e->dims, which);
+        launch_v64(px_v64_args(e->dp, which), S * P3_SLOTS, e->stream);
+        launch_vitc(px_vitc_args(e->dp, which), S * P3_SLOTS, e->stream);
+        k_px_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims, which);
+        e->stats.kernel_launches += 8;
+    }
+}
+
+// Allocates the buffers of the extra decode groups named in `need` (PX_NEED_* bits) and adds them to the passes.
+static int enable_px_groups(nrsc5b_engine *e, unsigned need)
+{
+    const size_t F = (size_t)e->dims.nstreams * P3_SLOTS;
+    for (int which = 0; which < 2; which++) {
+        if (!(need & (1u << which)) || (e->dims.px_enabled & (1 << which))) continue;
+        const int len = which == 0 ? P3S_LEN : P3_LEN;
+        PxBufs &xb = e->dp.xb[which];
+        int rc = dev_alloc(e, &xb.vin, F * 3 * len);
+        if (!rc) rc = dev_alloc(e, &xb.dec, F * P3_DEC_STRIDE);
+        if (!rc) rc = dev_alloc(e, &xb.spec, F * 19 * 32);
+        if (!rc) rc = dev_alloc(e, &xb.end, F * 19 * 32);
+        if (!rc) rc = dev_alloc(e, &xb.endstate, F);
+        if (!rc) rc = dev_alloc(e, &xb.fspec, F * 5 * 16);
+        if (!rc) rc = dev_alloc(e, &xb.fend, F * 5 * 16);
+        if (!rc) rc = dev_alloc(e, &xb.fhstate, F * 5);
+        if (!rc) rc = dev_alloc(e, &xb.ftbend, F * 5);
+        if (!rc) rc = dev_alloc(e, &xb.bits, F * (len / 32));
+        if (!rc) rc = dev_alloc(e, &xb.flags, F * 4);
+        if (rc) return rc;
+        e->dims.px_enabled |= 1 << which;
+    }
+    return NRSC5B_OK;
 }
 
 // One pass: every stream runs its front end up to its next frame boundary (at most BLOCKS_PER_PASS blocks,
@@ -1203,11 +1345,19 @@ static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
             if (rc) return rc;
         }
         unsigned long long prog = 0;
+        unsigned px_need = 0;
         CK(cudaMemcpyFromSymbolAsync(&prog, g_progress, sizeof(prog), 0, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyFromSymbolAsync(&px_need, g_px_need, sizeof(px_need), 0, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
         const unsigned long long delta = prog - e->last_progress;
         e->last_progress = prog;
+        if (px_need & ~(unsigned)e->dims.px_enabled) {
+            // a stream in MP2 / MP11 waits at a block boundary for its decode group: add it and go on
+            int rc = enable_px_groups(e, px_need);
+            if (rc) return rc;
+            continue;
+        }
         if (delta == 0) {
             // samples pushed asynchronously may still have been in flight: wait for them once, then retry
             if (!wait_for_copies || cudaStreamQuery(e->copy_stream) == cudaSuccess) break;

@@ -30,6 +30,7 @@ constexpr int ACQ_TILE = 4096;                     // decimated samples per acqu
 
 __device__ int g_dbg;                              // experiment switches (nrsc5b_debug_set), 0 in production
 __device__ unsigned long long g_progress;          // bumped by every stream that processed a block
+__device__ unsigned g_px_need;                     // PX_NEED_* bits: a stream waits for a decode group the host has not enabled
 
 __constant__ int c_compat_mode[64];
 __constant__ unsigned c_pn80[3];                   // first 80 bits of the descrambler sequence (bit i of word i/32)
@@ -97,7 +98,8 @@ struct PidsSmem {
 };
 constexpr int ZS = 32;                              // row stride of the per-reference arrays (>= 2 * MAXREF)
 constexpr int EQ_LD = BLK + 1;                      // padded row of the equalisation buffer (bank-conflict free)
-constexpr int EQ_MAXPART = 12;                      // partitions per sideband the equaliser stages (MP1..MP3, MP11 excluded)
+constexpr int EQ_MAXPART = 12;                      // partitions per sideband the equaliser stages in shared memory (MP1..MP3);
+                                                    // the two more of MP5/MP6/MP11 are equalised in place in global memory
 constexpr int EQ_ROWS = 2 * EQ_MAXPART * (PW - 1);  // data carriers of both sidebands
 struct SyncSmem {
     // reference carriers after their Costas loop and the loop's phase, [symbol][reference slot]: the threads
@@ -241,7 +243,17 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
         }
         // in_avail is advanced by asynchronous copies while this kernel runs
         const long long avail = *reinterpret_cast<volatile long long *>(&st.in_avail);
-        const int act = avail >= 2 * (st.start + NACQ);
+        int act = avail >= 2 * (st.start + NACQ);
+        if (act && st.state == ST_FINE) {
+            // MP2's short P3 frames and MP11's P4 frames are decoded by kernel groups the host adds to the pass
+            // only when a stream asks: wait at the block boundary until it has (nrsc5b_process looks at the flag)
+            const int cm = c_compat_mode[st.psmi & 63];
+            const int need = cm == 2 ? PX_NEED_SHORT : cm == 11 ? PX_NEED_PX2 : 0;
+            if (need & ~d.px_enabled) {
+                atomicOr(&g_px_need, (unsigned)need);
+                act = 0;
+            }
+        }
         st.active = act;
         sh_active = act;
         if (act) atomicAdd(&g_progress, 1ull);
@@ -713,6 +725,8 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     st.started_pm = 0;                   // decode_reset (decode.c:556-565)
                     st.px_total = 0;
                     st.px_started = 0;
+                    st.px2_total = 0;
+                    st.px2_started = 0;
                 }
             } else if (st.cfo_wait == 0) {
                 sm.do_search = 1;
@@ -878,7 +892,6 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         }
         const int bc = st.bc;
         int8_t *pm = p.pm + ((size_t)s * 16 + bc) * PM_BLOCK;
-        // (service modes with 14 partitions per sideband are equalised on their outer 12 only: not supported)
         const int rows = min(ppb, EQ_MAXPART) * (PW - 1), rows2 = 2 * rows;
         sylap(2);
         if (!pre_staged) stage_eq(t, FRONT_THREADS);
@@ -896,6 +909,30 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         sylap(3);
         // equalise (adjust_data, sync.c:263-282) and squared error to the nearest QPSK point (sync.c:465-488)
         float e_lb = 0.f, e_ub = 0.f;
+        if (ppb > EQ_MAXPART) {
+            // MP5 / MP6 / MP11 (14 partitions per sideband): partitions 12 and 13 do not fit the shared-memory
+            // stage; they are equalised where they lie (2 x 2 x 18 carriers x 32 symbols) - they count in the MER
+            // and MP11's PX2 demap reads them back from there
+            const int xrows = (ppb - EQ_MAXPART) * (PW - 1);
+            for (int idx = t; idx < 2 * xrows * BLK; idx += FRONT_THREADS) {
+                const int r = idx >> 5, n = idx & (BLK - 1);
+                const int sb = r >= xrows, rr = sb ? r - xrows : r;
+                const int i = EQ_MAXPART + rr / (PW - 1), k = rr % (PW - 1) + 1;
+                const int ci = sb == 0 ? PW * i + k : (NBINS - 1 - PW) - PW * i + k;
+                const int slot_lo = sb == 0 ? i : MAXREF + i + 1, slot_hi = sb == 0 ? i + 1 : MAXREF + i;
+                const float fa = (float)k * sm.smag[slot_hi], fb = (float)(PW - k) * sm.smag[slot_lo];
+                const float2 up = sm.eph[slot_hi][n], lp = sm.eph[slot_lo][n];
+                const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
+                const float rden = __fdividef(19.0f, c * c + dd * dd);
+                const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
+                const float2 v = cmulf(bins[(size_t)n * NBINS + ci], C);
+                bins[(size_t)n * NBINS + ci] = v;
+                const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
+                const float e = dx * dx + dy * dy;
+                if (sb) e_ub += e;
+                else e_lb += e;
+            }
+        }
         for (int idx = t; idx < rows2 * BLK; idx += FRONT_THREADS) {
             const int r = idx >> 5, n = idx & (BLK - 1);
             const float4 rc = sm.rowc[r];
@@ -952,19 +989,23 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                                ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
             *reinterpret_cast<uint32_t *>(pm + n * 720 + part * 36 + 4 * c4) = w;
         }
-        // PX1 (sync.c:552-573; MP3/MP11): two more partitions per sideband go to the convolutional interleaver's
-        // store in arrival order.  The mode is looked up afresh here, so the block that reaches FINE sync demaps
-        // them although it did not equalise them (its partition count was fixed at entry).
+        // Extended partitions (sync.c:537-595): MP2 = one more partition per sideband (PX1, 2304 soft bits per
+        // block), MP3 / MP11 = two more (PX1, 4608), MP11 = another two (PX2, 4608, both sidebands scaled with the
+        // LOWER sideband's factor, sync.c:591-592).  They go to the convolutional interleaver's store in arrival
+        // order.  The mode is looked up afresh here, so the block that reaches FINE sync demaps them although it
+        // did not equalise them (its partition count was fixed at entry): partitions the equaliser staged come
+        // from shared memory, the others from global memory (equalised in place above, or raw).
         const int cm = c_compat_mode[st.psmi & 63];
-        const bool has_px1 = cm == 3 || cm == 11;
-        if (has_px1 && (st.px_started || (bc & 1) == 0)) {       // decode_push_px1, decode.c:393-399
-            int8_t *ring = p.px_ring + (size_t)s * PX_RING;
-            const long long T = st.px_total;
-            const int eqparts = rows / (PW - 1);
-            for (int item = t; item < BLK * 36; item += FRONT_THREADS) {
-                const int n = item / 36, rem = item - n * 36;
-                const int q = rem / 9, c4 = rem - q * 9;         // q: lower 10, lower 11, upper 11, upper 10 (from the band edge)
-                const int sb = q >= 2, i = (q == 0 || q == 3) ? 10 : 11;
+        const bool has_px1 = cm == 2 || cm == 3 || cm == 11;
+        const int eqparts = rows / (PW - 1);
+        auto px_demap = [&](int8_t *ring, long long T, int nq, int base, bool lower_scale_only) {
+            const int per_sym = nq * 36;
+            for (int item = t; item < BLK * nq * 9; item += FRONT_THREADS) {
+                const int n = item / (nq * 9), rem = item - n * (nq * 9);
+                const int q = rem / 9, c4 = rem - q * 9;
+                // nq == 4: lower base, lower base+1, upper base+1, upper base (counted from the band edge); nq == 2: lower, upper
+                const int sb = q >= nq / 2;
+                const int i = nq == 2 ? base : ((q == 0 || q == 3) ? base : base + 1);
                 float2 a, b;
                 if (i < eqparts) {
                     const int r = (sb ? rows : 0) + i * (PW - 1) + 2 * c4;
@@ -975,13 +1016,17 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     a = bins[(size_t)n * NBINS + ci];
                     b = bins[(size_t)n * NBINS + ci + 1];
                 }
-                const float mult = sm.mult[sb];
+                const float mult = sm.mult[lower_scale_only ? 0 : sb];
                 const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
                                    ((unsigned)(uint8_t)soft_demap(b.x, mult) << 16) | ((unsigned)(uint8_t)soft_demap(b.y, mult) << 24);
-                const long long pos = (T + n * 144 + q * 36 + 4 * c4) % PX_RING;
+                const long long pos = (T + n * per_sym + q * 36 + 4 * c4) % PX_RING;
                 *reinterpret_cast<uint32_t *>(ring + pos) = w;
             }
-        }
+        };
+        if (has_px1 && (st.px_started || (bc & 1) == 0))         // decode_push_px1, decode.c:393-399
+            px_demap(p.px_ring + (size_t)s * PX_RING, st.px_total, cm == 2 ? 2 : 4, 10, false);
+        if (cm == 11 && (st.px2_started || (bc & 1) == 0))       // decode_push_px2, decode.c:416-422
+            px_demap(p.px2_ring + (size_t)s * PX_RING, st.px2_total, 4, 12, true);
         __syncthreads();
         if (t == 0) {
             st.err_lb += e_sb[0];
@@ -1031,14 +1076,16 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 }
                 st.p1_ready = 1;
             }
-            // P3 bookkeeping (decode_push_px1, decode.c:393-414): every second block closes a 9216-bit span of
-            // the interleaver; once a whole span of 147456 bits has gone through it yields a frame
+            // P3 / P4 bookkeeping (decode_push_px1 / _px2, decode.c:393-437): every second block closes a span of the
+            // interleaver (9216 soft bits; MP2: 4608); once a whole cycle (147456; MP2: 73728) has gone through, it
+            // yields a frame.  The records are reserved now: P3 before P4, like the reference's calls.
             if (has_px1) {
+                const int blk_len = cm == 2 ? PX1_BLOCK / 2 : PX1_BLOCK;
                 if ((bc & 1) == 0) st.px_started = 1;
                 if (st.px_started) {
-                    st.px_total += PX1_BLOCK;
-                    const long long k0 = st.px_total - 2 * PX1_BLOCK;
-                    if ((bc & 1) && k0 >= IV_N && st.p3_pending < P3_SLOTS) {
+                    st.px_total += blk_len;
+                    const long long k0 = st.px_total - 2 * blk_len;
+                    if ((bc & 1) && cm != 2 && k0 >= IV_N && st.p3_pending < P3_SLOTS) {
                         uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P3_LEN / 8);
                         const int e3 = st.p3_pending;
                         st.p3_k0[e3] = k0;
@@ -1048,6 +1095,35 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                             reinterpret_cast<uint32_t *>(fw)[1] = P3_LEN;
                         }
                         st.p3_pending = e3 + 1;
+                    }
+                    if ((bc & 1) && cm == 2 && k0 >= IV_NS && st.xq_pending[0] < P3_SLOTS) {
+                        uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P3S_LEN / 8);
+                        const int e3 = st.xq_pending[0];
+                        st.xq_k0[0][e3] = k0;
+                        st.xq_rec[0][e3] = fw ? (unsigned)(fw - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+                        if (fw) {
+                            reinterpret_cast<uint32_t *>(fw)[0] = 1;        // P3 logical channel
+                            reinterpret_cast<uint32_t *>(fw)[1] = P3S_LEN;
+                        }
+                        st.xq_pending[0] = e3 + 1;
+                    }
+                }
+            }
+            if (cm == 11) {
+                if ((bc & 1) == 0) st.px2_started = 1;
+                if (st.px2_started) {
+                    st.px2_total += PX1_BLOCK;
+                    const long long k0 = st.px2_total - 2 * PX1_BLOCK;
+                    if ((bc & 1) && k0 >= IV_N && st.xq_pending[1] < P3_SLOTS) {
+                        uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P3_LEN / 8);
+                        const int e4 = st.xq_pending[1];
+                        st.xq_k0[1][e4] = k0;
+                        st.xq_rec[1][e4] = fw ? (unsigned)(fw - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+                        if (fw) {
+                            reinterpret_cast<uint32_t *>(fw)[0] = 2;        // P4 logical channel
+                            reinterpret_cast<uint32_t *>(fw)[1] = P3_LEN;
+                        }
+                        st.xq_pending[1] = e4 + 1;
                     }
                 }
             }
@@ -1082,7 +1158,11 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
     __syncthreads();
 
     if (max_blocks > 16) max_blocks = 16;             // the PIDS queue (and its interleaver matrix rows) hold 16 blocks
-    if (t == 0) st.p3_pending = 0;                    // decoded by the kernels that followed the previous pass
+    if (t == 0) {                                     // decoded by the kernels that followed the previous pass
+        st.p3_pending = 0;
+        st.xq_pending[0] = 0;
+        st.xq_pending[1] = 0;
+    }
     __syncthreads();
     for (int nb = 0; nb < max_blocks; nb++) {
         // a completed interleaver matrix is decoded (and its header checked) before the next block

@@ -149,6 +149,9 @@ void sync_named(int id, int nthreads) { wait_on(g_named_bars[id], (unsigned)nthr
 
 void run_grid(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *arg)
 {
+    // EMU_ORDER=reverse schedules the threads of a block (and the blocks of a grid) from the last to the first: a
+    // result that depends on the order in which threads reach a barrier-free stretch of code is a race on the GPU
+    static const bool g_reverse = getenv("EMU_ORDER") && !strcmp(getenv("EMU_ORDER"), "reverse");
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads <= 0 || nthreads > MAX_THREADS || smem > sizeof(g_dyn_smem)) {
         fprintf(stderr, "cuda_emu: invalid launch configuration (%d threads, %zu bytes of shared memory)\n", nthreads, smem);
@@ -170,9 +173,10 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *ar
     g_grid_dim = Idx{ grid.x, grid.y, grid.z };
     g_block_dim = Idx{ block.x, block.y, block.z };
     g_nthreads = nthreads;
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    for (unsigned long long bi = 0; bi < nblocks; bi++) {
+                const unsigned long long b = g_reverse ? nblocks - 1 - bi : bi;
+                const unsigned bx = (unsigned)(b % grid.x), by = (unsigned)((b / grid.x) % grid.y), bz = (unsigned)(b / ((unsigned long long)grid.x * grid.y));
                 g_block_idx = Idx{ bx, by, bz };
                 g_block_bar = Barrier();
                 g_warp_bars.clear();
@@ -193,7 +197,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *ar
                 }
                 while (g_alive > 0) {
                     const unsigned long long before = g_progress;
-                    for (int t = 0; t < nthreads; t++) {
+                    for (int k = 0; k < nthreads; k++) {
+                        const int t = g_reverse ? nthreads - 1 - k : k;
                         if (g_fibres[t].done) continue;
                         g_cur = t;
                         emu_switch(&g_sched_sp, g_fibres[t].sp);

@@ -52,6 +52,8 @@ test_rs_decode_bit_exact = _stages.test_rs_decode_bit_exact
 # whole chain, FM
 test_synth_pdus_bit_exact = _chain.test_synth_pdus_bit_exact
 test_mp3_p1_pids_p3_bit_exact = _chain.test_mp3_p1_pids_p3_bit_exact
+test_service_modes_bit_exact = _chain.test_service_modes_bit_exact
+test_mixed_service_modes_in_one_engine = _chain.test_mixed_service_modes_in_one_engine
 test_chunked_push_matches_single_push = _chain.test_chunked_push_matches_single_push
 test_drain_all_equals_per_stream_drain = _chain.test_drain_all_equals_per_stream_drain
 test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_is_trimmed_to_the_input_buffer
@@ -61,3 +63,16 @@ test_multi_stream_independent = _chain.test_multi_stream_independent
 test_am_pdus_bit_exact = _am.test_am_pdus_bit_exact
 test_am_streams_independent_and_chunked = _am.test_am_streams_independent_and_chunked
 test_am_cu8_input_bit_exact = _am.test_am_cu8_input_bit_exact
+
+
+def test_reverse_thread_order_gives_the_same_results():
+    """The same library with EMU_ORDER=reverse: threads of a block and blocks of a grid are scheduled from the last
+    to the first.  A result that depended on the order in which threads run between two barriers would be a race
+    on the GPU; a subset of the parity tests must pass unchanged.  (The order is fixed per process, hence the
+    subprocess.)"""
+    env = dict(os.environ, EMU_ORDER="reverse")
+    sel = "mp1_cfo-300_awgn12 or service_modes_bit_exact or ma3_noisy or am_cu8_input_bit_exact or viterbi_fast_path"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
