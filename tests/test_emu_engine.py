@@ -39,6 +39,7 @@ def emulated_engine():
 
 import test_gpu_am as _am            # noqa: E402
 import test_gpu_chain as _chain      # noqa: E402
+import test_gpu_modes as _modes      # noqa: E402
 import test_gpu_stages as _stages    # noqa: E402
 
 # kernel-level
@@ -52,8 +53,8 @@ test_rs_decode_bit_exact = _stages.test_rs_decode_bit_exact
 # whole chain, FM
 test_synth_pdus_bit_exact = _chain.test_synth_pdus_bit_exact
 test_mp3_p1_pids_p3_bit_exact = _chain.test_mp3_p1_pids_p3_bit_exact
-test_service_modes_bit_exact = _chain.test_service_modes_bit_exact
-test_mixed_service_modes_in_one_engine = _chain.test_mixed_service_modes_in_one_engine
+test_service_modes_bit_exact = _modes.test_service_modes_bit_exact
+test_mixed_service_modes_in_one_engine = _modes.test_mixed_service_modes_in_one_engine
 test_chunked_push_matches_single_push = _chain.test_chunked_push_matches_single_push
 test_drain_all_equals_per_stream_drain = _chain.test_drain_all_equals_per_stream_drain
 test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_is_trimmed_to_the_input_buffer
