@@ -77,3 +77,33 @@ def test_reverse_thread_order_gives_the_same_results():
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+# ---- the drop-in libnrsc5.so on the emulated engine: the reference's unmodified host side + our input seam, linked
+# ---- against the emulator build of the engine instead of the CUDA one (same objects, other -l) ----
+@pytest.fixture(scope="module")
+def emulated_dropin(emulated_engine):
+    import build_emu
+    import test_dropin
+    objdir = os.path.join(common.ROOT, "nrsc5_b200", "dropin", "_build", "obj")
+    if not os.path.isdir(objdir):
+        pytest.skip("drop-in objects not built (needs the reference tree at build time)")
+    objs = sorted(os.path.join(objdir, f) for f in os.listdir(objdir) if f.endswith(".o"))
+    so = os.path.join(HERE, "_build", "libnrsc5_emu.so")
+    emu = build_emu.build()
+    subprocess.run(["gcc", "-shared", "-o", so, *objs, emu, "-Wl,-rpath," + os.path.dirname(emu), "-lm", "-lpthread"], check=True)
+    saved = test_dropin.DROPIN
+    test_dropin.DROPIN = so
+    yield so
+    test_dropin.DROPIN = saved
+
+
+def test_dropin_events_match_reference_on_sample_xz(emulated_dropin):
+    import test_dropin
+    test_dropin.test_dropin_events_match_reference_on_sample_xz()
+
+
+@pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cu8")])
+def test_dropin_am_matches_reference_events(emulated_dropin, psmi, fmt):
+    import test_dropin
+    test_dropin.test_dropin_am_matches_reference_events(psmi, fmt)
