@@ -39,6 +39,7 @@ def emulated_engine():
 
 import test_gpu_am as _am            # noqa: E402
 import test_gpu_chain as _chain      # noqa: E402
+import test_gpu_edge as _edge        # noqa: E402
 import test_gpu_modes as _modes      # noqa: E402
 import test_gpu_stages as _stages    # noqa: E402
 
@@ -60,6 +61,11 @@ test_drain_all_equals_per_stream_drain = _chain.test_drain_all_equals_per_stream
 test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_is_trimmed_to_the_input_buffer
 test_cs16_input_equals_cu8_input = _chain.test_cs16_input_equals_cu8_input
 test_multi_stream_independent = _chain.test_multi_stream_independent
+# awkward inputs
+test_dropout_and_reacquisition = _edge.test_dropout_and_reacquisition
+test_stream_starting_mid_frame_mp3 = _edge.test_stream_starting_mid_frame_mp3
+test_noise_only_and_short_inputs = _edge.test_noise_only_and_short_inputs
+test_push_misuse_is_refused = _edge.test_push_misuse_is_refused
 # whole chain, AM
 test_am_pdus_bit_exact = _am.test_am_pdus_bit_exact
 test_am_streams_independent_and_chunked = _am.test_am_streams_independent_and_chunked
