@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "nrsc5_b200", "csrc")
 OUTDIR = os.path.join(ROOT, "tests", "_build")
-OUT = os.path.join(OUTDIR, "libnrsc5_b200_emu.so")
+OUT = os.path.join(OUTDIR, "libnrsc5_b200_emu_asan.so" if os.environ.get("EMU_ASAN") else "libnrsc5_b200_emu.so")
 UNITS = ["engine.cu", "frontend.cu"]
 
 
@@ -91,8 +91,10 @@ def build(verbose=False):
     cxx = os.environ.get("CXX", "g++")
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-I" + HERE, "-I" + CSRC,
              "-I" + os.path.join(ROOT, "include")]
+    if os.environ.get("EMU_ASAN"):          # EMU_ASAN=1: AddressSanitizer build (run python with LD_PRELOAD=libasan.so)
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     for u in UNITS:
-        gen = os.path.join(OUTDIR, "emu_" + u.replace(".cu", ".cpp"))
+        gen = os.path.join(OUTDIR, ("asan_" if os.environ.get("EMU_ASAN") else "") + "emu_" + u.replace(".cu", ".cpp"))
         text = open(os.path.join(CSRC, u)).read()
         with open(gen, "w") as f:
             f.write('#line 1 "%s"\n' % os.path.join(CSRC, u))
@@ -103,9 +105,9 @@ def build(verbose=False):
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    obj = os.path.join(OUTDIR, "cuda_emu.o")
+    obj = os.path.join(OUTDIR, ("asan_" if os.environ.get("EMU_ASAN") else "") + "cuda_emu.o")
     subprocess.run([cxx, *flags, "-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", obj], check=True)
-    subprocess.run([cxx, "-shared", "-o", OUT, *objs, obj, "-lm"], check=True)
+    subprocess.run([cxx, "-shared", "-o", OUT, *objs, obj, "-lm"] + (["-fsanitize=address"] if os.environ.get("EMU_ASAN") else []), check=True)
     return OUT
 
 
