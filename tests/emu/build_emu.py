@@ -92,7 +92,8 @@ def build(verbose=False):
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-I" + HERE, "-I" + CSRC,
              "-I" + os.path.join(ROOT, "include")]
     if os.environ.get("EMU_ASAN"):          # EMU_ASAN=1: AddressSanitizer build (run python with LD_PRELOAD=libasan.so)
-        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+        # + alignment checks: a misaligned short2 / float2 / uint4 access is fatal on the GPU and silent on x86
+        flags += ["-fsanitize=address,alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer"]
     for u in UNITS:
         gen = os.path.join(OUTDIR, ("asan_" if os.environ.get("EMU_ASAN") else "") + "emu_" + u.replace(".cu", ".cpp"))
         text = open(os.path.join(CSRC, u)).read()
@@ -107,7 +108,7 @@ def build(verbose=False):
         objs.append(obj)
     obj = os.path.join(OUTDIR, ("asan_" if os.environ.get("EMU_ASAN") else "") + "cuda_emu.o")
     subprocess.run([cxx, *flags, "-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", obj], check=True)
-    subprocess.run([cxx, "-shared", "-o", OUT, *objs, obj, "-lm"] + (["-fsanitize=address"] if os.environ.get("EMU_ASAN") else []), check=True)
+    subprocess.run([cxx, "-shared", "-o", OUT, *objs, obj, "-lm"] + (["-fsanitize=address,alignment"] if os.environ.get("EMU_ASAN") else []), check=True)
     return OUT
 
 

@@ -69,7 +69,7 @@ def test_dropin_cs16_pipe_matches_reference_events():
     assert [e for e in got if e[0] == "HDC"] == [e for e in want if e[0] == "HDC"]
 
 
-@pytest.mark.gpu_new
+@pytest.mark.gpu
 @pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cs16"), (1, "cu8"), (2, "cu8")])
 def test_dropin_am_matches_reference_events(psmi, fmt):
     """AM through the public API (nrsc5_set_mode(NRSC5_MODE_AM), nrsc5_pipe_samples_cs16 / _cu8): the drop-in and

@@ -1,8 +1,8 @@
 """GPU parity of the AM (hybrid MA1, all-digital MA3) path through the C ABI: cs16 in, P1 / P3 / PIDS PDUs and events out, against
 the oracle (oracle/nrsc5_oracle_am.c, itself pinned to the unmodified reference) and the golden vectors.
 
-Marker `gpu_new`: these tests pass on the CPU emulation of the kernels (tests/test_emu_engine.py) but have not yet
-run on a B200; they join the `gpu` set once they have.  Run them on a GPU box with  -m "gpu or gpu_new"."""
+First B200 run: round 1, all green (they ran as `gpu_new` until then; their CPU twins on the emulated kernels
+are in tests/test_emu_engine.py)."""
 import numpy as np
 import pytest
 
@@ -13,7 +13,7 @@ import nrsc5_b200
 from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth_am
 
-pytestmark = pytest.mark.gpu_new
+pytestmark = pytest.mark.gpu
 
 
 def run_am(captures, chunk=None, cu8=False):

@@ -1,8 +1,8 @@
 """GPU parity of the FM service modes beyond MP1 / MP3 through the C ABI: MP2, MP5, MP6, MP11 against the oracle and
 the golden vectors of the unmodified reference (tests/golden/synth_fm_modes.json).
 
-Marker `gpu_new`: these tests pass on the CPU emulation of the kernels (tests/test_emu_engine.py) but have not yet
-run on a B200; they join the `gpu` set once they have.  Run them on a GPU box with  -m "gpu or gpu_new"."""
+First B200 run: round 1, all green (they ran as `gpu_new` until then; their CPU twins on the emulated kernels
+are in tests/test_emu_engine.py)."""
 import numpy as np
 import pytest
 
@@ -13,7 +13,7 @@ from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth
 from test_gpu_chain import kinds, oracle_kinds, pdus, run_engine
 
-pytestmark = pytest.mark.gpu_new
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", list(common.FM_MODE_CASES))
