@@ -69,7 +69,7 @@ def test_am_engine_code_on_host_matches_oracle(name):
     assert common.summarize(got) == common.summarize(ref)
 
 
-@pytest.mark.parametrize("name,order", [("ma1_noisy", 1), ("ma1_noisy", -1), ("ma3_noisy", 1), ("ma3_noisy", -1)])
+@pytest.mark.parametrize("name,order", [("ma1_noisy", 1), ("ma3_noisy", -1)])
 def test_am_engine_code_with_32_emulated_lanes(name, order):
     """k_am's warp emulated by 32 fibres (tests/am_host.cu): the lane-strided work split and the placement of the
     AM_SYNC() barriers, with the lanes scheduled in ascending and in descending order."""

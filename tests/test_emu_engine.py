@@ -78,7 +78,7 @@ def test_reverse_thread_order_gives_the_same_results():
     on the GPU; a subset of the parity tests must pass unchanged.  (The order is fixed per process, hence the
     subprocess.)"""
     env = dict(os.environ, EMU_ORDER="reverse")
-    sel = "mp1_cfo-300_awgn12 or service_modes_bit_exact or ma3_noisy or am_cu8_input_bit_exact or viterbi_fast_path"
+    sel = "mp1_cfo-300_awgn12 or mp11 or ma3_noisy or viterbi_fast_path or (am_cu8_input_bit_exact and 2)"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
