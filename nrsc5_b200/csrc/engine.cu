@@ -696,6 +696,12 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->dims.emit_soft = cfg->emit_soft;
     e->dims.cs16 = cfg->input_cs16 ? 1 : 0;
     e->dims.px_enabled = 0;
+    {
+        // the request flag for the extra decode groups is per process: every new engine starts from a clean one (a
+        // stream of another engine that is waiting raises it again at its next pass)
+        const unsigned zero = 0;
+        cudaMemcpyToSymbol(g_px_need, &zero, sizeof(zero));
+    }
     e->pushed.assign(S, 0);
     e->drained.assign(S, 0);
     int rc = upload_tables(cfg->device);
