@@ -73,7 +73,7 @@ enum {
 
 enum {
     NRSC5B_REC_FRAME = 1,     /* u32 lc, u32 nbits, packed bits            */
-    NRSC5B_REC_PIDS = 2,      /* 10 bytes                                  */
+    NRSC5B_REC_PIDS = 2,      /* 10 bytes (80 bits, MSB first) + u8: 1 if the frame passes the CRC-12 of pids.c:52-86 */
     NRSC5B_REC_SYNC = 3,      /* f32 freq_offset, i32 psmi [AM: + i32 pli, hppi, aabi, rdbi; FM: those stay -1] */
     NRSC5B_REC_LOST_SYNC = 4,
     NRSC5B_REC_MER = 5,       /* f32 lower, f32 upper                      */

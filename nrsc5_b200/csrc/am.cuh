@@ -19,6 +19,8 @@
 
 #include <cuda_runtime.h>
 
+#include "pids_crc.cuh"
+
 #if defined(__CUDA_ARCH__)
 #define AM_SYNC() __syncwarp()
 #elif defined(AM_HOST_SYNC)
@@ -373,9 +375,11 @@ AM_HD inline void process_pids(AmState &st, AmWork &w, const AmTables &tb, const
     AM_SYNC();
     viterbi_k9(w, L, w.vit_pids, w.out, PIDS_LEN, 0561, 0753, 0711);
     descramble(tb, L, w.out, PIDS_LEN);
-    uint8_t *rec = log_reserve(st, io, L, REC_PIDS, 10);
-    if (rec && L.lane == 0)
+    uint8_t *rec = log_reserve(st, io, L, REC_PIDS, 11);                                  // 80 bits + CRC verdict
+    if (rec && L.lane == 0) {
         for (int i = 0; i < PIDS_LEN; i++) rec[i >> 3] |= (uint8_t)(w.out[i] << (7 - (i & 7)));
+        rec[10] = (uint8_t)pids_crc12_ok(rec);                                            // pids.c:1042
+    }
     AM_SYNC();
 }
 

@@ -15,6 +15,7 @@
 // This translation unit is compiled with -fmad=false: float expressions keep the reference's
 // evaluation order wherever a discrete decision depends on them.
 #pragma once
+#include "pids_crc.cuh"
 #include "common.cuh"
 #include "fft.cuh"
 #include "viterbi_pack.cuh"
@@ -193,6 +194,7 @@ __device__ void pids_decode_warp(const DevPtrs &p, const EngineDims &d, int s, i
         if (st.pids_rec[e] != 0xffffffffu) {
             uint8_t *w = p.log + (size_t)s * d.log_cap + st.pids_rec[e];
             for (int i = 0; i < 10; i++) w[i] = pk[i];
+            w[10] = (uint8_t)pids_crc12_ok(pk);          // pids.c:1042: what pids_frame_push will find
         }
     }
 }
@@ -1058,7 +1060,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         // PIDS (decode.c:463-471): the frames of a pass are decoded together when k_stream exits; the record
         // slot is reserved here to keep the stream's record order
         if (t == 0) {
-            uint8_t *w = log_reserve(p, d, s, REC_PIDS, 10);
+            uint8_t *w = log_reserve(p, d, s, REC_PIDS, 11);             // 80 bits + CRC verdict
             const int e = st.pids_pending;
             st.pids_rec[e] = w ? (unsigned)(w - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
             st.pids_bc[e] = bc;

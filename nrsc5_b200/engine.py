@@ -106,7 +106,7 @@ def parse_records(raw: bytes):
             lc, nbits = struct.unpack_from("<II", pay, 0)
             rec = {"lc": lc, "nbits": nbits, "bits": bytes(pay[8:])}
         elif ty == REC_PIDS:
-            rec = {"bits": bytes(pay[:10])}
+            rec = {"bits": bytes(pay[:10]), "crc_ok": (pay[10] if len(pay) > 10 else None)}   # CRC-12 verdict (pids.c:52-86)
         elif ty == REC_SYNC:
             f, psmi = struct.unpack_from("<fi", pay)
             flags = struct.unpack_from("<4i", pay, 8) if len(pay) >= 24 else (-1, -1, -1, -1)   # AM: pli, hppi, aabi, rdbi

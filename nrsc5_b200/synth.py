@@ -195,6 +195,35 @@ def build_p1_frame_bits(rng, pci: int = PCI_AUDIO, valid_header: bool = True) ->
     return bits
 
 
+def pids_crc12(pids: np.ndarray) -> int:
+    """CRC-12 over bits 0..67 of a PIDS frame in pids_frame_push's bit order (reference src/pids.c:52-72)."""
+    reg = 0
+    for i in range(67, -1, -1):
+        low = reg & 1
+        reg = (reg >> 1) ^ (int(pids[i]) << 15)
+        if low:
+            reg ^= 0xD010
+    for _ in range(16):
+        low = reg & 1
+        reg >>= 1
+        if low:
+            reg ^= 0xD010
+    return (reg ^ 0x955) & 0xFFF
+
+
+def pids_with_crc(frame_bits: np.ndarray) -> np.ndarray:
+    """The same 80 frame bits with bits 68..79 (in pids_frame_push's per-byte reversed order, src/pids.c:1036-1040)
+    replaced by the CRC-12 of the first 68, so that the reference's L2 accepts the frame."""
+    i = np.arange(80)
+    order = ((i >> 3) << 3) + 7 - (i & 7)            # pids[i] = frame_bits[order[i]]
+    pids = frame_bits[order].copy()
+    crc = pids_crc12(pids)
+    pids[68:80] = [(crc >> (11 - k)) & 1 for k in range(12)]
+    out = frame_bits.copy()
+    out[order] = pids
+    return out
+
+
 # ----------------------------------------------------------------------------
 # reference subcarriers
 # ----------------------------------------------------------------------------
@@ -351,7 +380,7 @@ def make_fm_mp3(**kw) -> FmCapture:
 def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz: float = 0.0,
             noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
             tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
-            start_bc: int = 0) -> FmCapture:
+            start_bc: int = 0, pids_crc: bool = False) -> FmCapture:
     """FM capture (PSMI 1, 2, 3, 5, 6 or 11) holding `nframes` complete L1 frames
     followed by `tail_blocks` further blocks so the last frame flushes
     (the reference has no flush call).
@@ -382,6 +411,8 @@ def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 10
         pids_this = []
         for bc in range(16):
             pb = rng.integers(0, 2, PIDS_BITS, dtype=np.uint8)
+            if pids_crc:
+                pb = pids_with_crc(pb)
             pc = conv_encode_tb(pb ^ pn_pids).reshape(-1)         # 240
             k2 = np.ones(pc.size, dtype=bool)
             k2[5::6] = False

@@ -494,6 +494,33 @@ static void set_state(orc_t *o, int ns)
     o->state = ns;
 }
 
+/* CRC-12 of a PIDS frame, restated from reference src/pids.c:52-86 with the per-byte bit reversal of
+ * pids_frame_push (src/pids.c:1036-1040); pk = 80 frame bits packed MSB-first */
+int orc_pids_crc12_ok(const uint8_t *pk)
+{
+    uint8_t bits[80];
+    for (int i = 0; i < 80; i++) {
+        const int src = ((i >> 3) << 3) + 7 - (i & 7);              /* frame bit index read by pids_frame_push */
+        bits[i] = (pk[src >> 3] >> (7 - (src & 7))) & 1;
+    }
+    uint16_t poly = 0xD010, reg = 0;
+    for (int i = 67; i >= 0; i--) {
+        int lowbit = reg & 1;
+        reg >>= 1;
+        reg ^= (uint16_t)(bits[i] << 15);
+        if (lowbit) reg ^= poly;
+    }
+    for (int i = 0; i < 16; i++) {
+        int lowbit = reg & 1;
+        reg >>= 1;
+        if (lowbit) reg ^= poly;
+    }
+    reg ^= 0x955;
+    uint16_t expected = 0;
+    for (int i = 68; i < 80; i++) expected = (uint16_t)((expected << 1) | bits[i]);
+    return expected == (reg & 0xfff);
+}
+
 static void decode_reset(orc_t *o)
 {
     o->started_pm = 0;
@@ -529,7 +556,8 @@ static void push_pm(orc_t *o, const int8_t *soft, unsigned bc)
     orc_descramble(bp, PIDS_LEN);
     uint8_t pk[10] = { 0 };
     for (int i = 0; i < PIDS_LEN; i++) pk[i >> 3] |= (uint8_t)(bp[i] << (7 - (i & 7)));
-    olog_put(&o->log, ORC_REC_PIDS, pk, 10, NULL, 0);
+    const uint8_t crc_ok = (uint8_t)orc_pids_crc12_ok(pk);
+    olog_put(&o->log, ORC_REC_PIDS, pk, 10, &crc_ok, 1);
 
     if (bc == 0) o->started_pm = 1;
     if (o->started_pm && bc == 15) {

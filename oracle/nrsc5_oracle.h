@@ -23,7 +23,7 @@ extern "C" {
 /* log record types: identical to oracle/reftap.c so one parser serves both */
 enum {
     ORC_REC_FRAME = 1,     /* u32 lc, u32 nbits, bits packed MSB-first  */
-    ORC_REC_PIDS = 2,      /* 10 bytes                                  */
+    ORC_REC_PIDS = 2,      /* 10 bytes + u8 CRC-12 verdict (pids.c:52-86) */
     ORC_REC_SYNC = 3,      /* f32 freq_offset, i32 psmi, pli, hppi, aabi, rdbi */
     ORC_REC_LOST_SYNC = 4,
     ORC_REC_MER = 5,       /* f32 lower, f32 upper                      */
@@ -47,6 +47,9 @@ const uint8_t *orc_log_data(const orc_t *o);
 void orc_log_clear(orc_t *o);
 
 /* ---- AM (hybrid MA1), oracle/nrsc5_oracle_am.c: cs16 at 46 511.72 S/s in, same record stream out ---- */
+/* CRC-12 verdict of a PIDS frame (80 bits packed MSB-first), reference src/pids.c:52-86,1032-1050 */
+int orc_pids_crc12_ok(const uint8_t *pk);
+
 typedef struct orc_am orc_am_t;
 orc_am_t *orc_am_new(void);
 void orc_am_free(orc_am_t *o);

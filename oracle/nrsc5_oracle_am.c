@@ -270,7 +270,8 @@ static void process_pids(orc_am_t *o, const uint8_t *sbit)                 /* de
     orc_descramble(o->out_pids, PIDS_LEN);
     uint8_t pk[10] = { 0 };
     for (int i = 0; i < PIDS_LEN; i++) pk[i >> 3] |= (uint8_t)(o->out_pids[i] << (7 - (i & 7)));
-    alog_put(&o->log, ORC_REC_PIDS, pk, 10, NULL, 0);
+    const uint8_t crc_ok = (uint8_t)orc_pids_crc12_ok(pk);
+    alog_put(&o->log, ORC_REC_PIDS, pk, 10, &crc_ok, 1);
 }
 
 /* frame.c:645-714 (PCI), :146-156, :527-541: an AM P1 PDU that announces audio but whose first header fails RS

@@ -61,6 +61,7 @@ test_drain_all_equals_per_stream_drain = _chain.test_drain_all_equals_per_stream
 test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_is_trimmed_to_the_input_buffer
 test_cs16_input_equals_cu8_input = _chain.test_cs16_input_equals_cu8_input
 test_multi_stream_independent = _chain.test_multi_stream_independent
+test_pids_crc_verdicts_on_valid_frames = _chain.test_pids_crc_verdicts_on_valid_frames
 # awkward inputs
 test_dropout_and_reacquisition = _edge.test_dropout_and_reacquisition
 test_stream_starting_mid_frame_mp3 = _edge.test_stream_starting_mid_frame_mp3

@@ -50,7 +50,7 @@ def digest(recs):
         if t == eng.REC_FRAME:
             out.append(("F", r["lc"], r["nbits"], r["bits"]))
         elif t == eng.REC_PIDS:
-            out.append(("P", r["bits"]))
+            out.append(("P", r["bits"], r["crc_ok"]))
         elif t == eng.REC_SYNC:
             out.append(("S", r["psmi"], tuple(r["flags"])))
         elif t == eng.REC_LOST_SYNC:
@@ -66,7 +66,7 @@ def oracle_digest(log):
         if t == reftap.REC_FRAME:
             out.append(("F", p["lc"], p["nbits"], p["bits"]))
         elif t == reftap.REC_PIDS:
-            out.append(("P", p["bits"]))
+            out.append(("P", p["bits"], p["crc_ok"]))
         elif t == reftap.REC_SYNC:
             out.append(("S", p["psmi"], tuple(p["flags"])))
         elif t == reftap.REC_LOST_SYNC:

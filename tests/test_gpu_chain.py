@@ -35,6 +35,10 @@ def run_engine(cu8_list, chunk=None, emit_soft=False, log_capacity=8 << 20):
         return outs
 
 
+def pids_verdicts(recs):
+    return [r["crc_ok"] for t, r in recs if t == eng.REC_PIDS]
+
+
 def pdus(recs):
     p1 = [r["bits"] for t, r in recs if t == eng.REC_FRAME and r["lc"] == 0]
     pids = [r["bits"] for t, r in recs if t == eng.REC_PIDS]
@@ -58,6 +62,7 @@ def test_synth_pdus_bit_exact(name):
     p1, pids = pdus(recs)
     assert p1 == ref.p1_frames                   # L1 P1 PDUs, bit-exact
     assert pids == ref.pids_frames               # PIDS PDUs, bit-exact
+    assert pids_verdicts(recs) == [p["crc_ok"] for p in ref.of(reftap.REC_PIDS)]    # and their CRC-12 verdicts
     assert kinds(recs) == oracle_kinds(ref)      # same events in the same order
     # events carrying floats: tolerance (FFT arithmetic differs from the reference's FFT)
     for (a, b) in zip([r for t, r in recs if t == eng.REC_SYNC], ref.of(reftap.REC_SYNC)):
@@ -175,6 +180,32 @@ def test_sample_xz_bit_exact():
     assert [common.fnv1a32(b) for b in p1] == gold_p1
     assert [common.fnv1a32(b) for b in pids] == gold_pids
     assert kinds(recs) == [e[0] for e in g["events"]]
+    # 143 of the capture's 172 PIDS frames pass the CRC-12 the reference's L2 applies (pids.c:52-86): the verdict the
+    # engine appends to the record, checked against a restatement in numpy
+    v = pids_verdicts(recs)
+    assert v == [int(synth.pids_crc12(_pids_order(b)) == _pids_field(b)) for b in pids] and sum(v) == 143
+
+
+def _pids_order(packed):
+    fb = np.unpackbits(np.frombuffer(packed, dtype=np.uint8))
+    i = np.arange(80)
+    return fb[((i >> 3) << 3) + 7 - (i & 7)]
+
+
+def _pids_field(packed):
+    p = _pids_order(packed)
+    return int("".join(str(int(x)) for x in p[68:80]), 2)
+
+
+def test_pids_crc_verdicts_on_valid_frames():
+    """Every PIDS frame of this capture carries a valid CRC-12: all verdicts 1, as in the oracle."""
+    cap = synth.make_fm_mp1(nframes=1, seed=31, lead_in=200, pids_crc=True)
+    ref = port.decode(cap.cu8)
+    recs = run_engine([cap.cu8])[0]
+    assert pdus(recs)[1] == ref.pids_frames
+    v = pids_verdicts(recs)
+    assert v == [p["crc_ok"] for p in ref.of(reftap.REC_PIDS)]
+    assert len(v) >= 15 and all(x == 1 for x in v[1:])        # (the first frame may predate a clean lock)
 
 
 def test_no_gpu_error_is_loud(monkeypatch):
