@@ -21,6 +21,8 @@
  *                                                   reference src/input.c:41-50,
  *                                                   src/acquire.c:98-263, src/sync.c:339-610,
  *                                                   src/decode.c:378-471, src/conv_dec.c:429-463
+ *       All service modes the reference tells apart are decoded: FM MP1, MP2, MP3, MP5, MP6, MP11
+ *       (src/sync.c:30-35,343-357,537-595); AM MA1 and MA3 (src/sync.c:612-767).
  *   nrsc5b_drain
  *       the downstream calls of the path, as records in call order:
  *         REC_FRAME      frame_push(frame_t*, bits, len, lc)   reference src/frame.h:53
@@ -72,7 +74,8 @@ enum {
 };
 
 enum {
-    NRSC5B_REC_FRAME = 1,     /* u32 lc, u32 nbits, packed bits            */
+    NRSC5B_REC_FRAME = 1,     /* u32 lc (0 = P1, 1 = P3, 2 = P4: logical_channel_t, reference src/frame.h), u32 nbits
+                               * (FM: 146176 P1; 4608 P3/P4, 2304 P3 in MP2.  AM: 3750 P1; 24000 / 30000 P3), packed bits */
     NRSC5B_REC_PIDS = 2,      /* 10 bytes (80 bits, MSB first) + u8: 1 if the frame passes the CRC-12 of pids.c:52-86 */
     NRSC5B_REC_SYNC = 3,      /* f32 freq_offset, i32 psmi [AM: + i32 pli, hppi, aabi, rdbi; FM: those stay -1] */
     NRSC5B_REC_LOST_SYNC = 4,
