@@ -120,7 +120,7 @@ struct EngineDims {
     size_t log_cap;            // bytes of log per stream
     int emit_soft;
     int cs16;                  // input is cs16 at the decimated rate: 4 bytes per sample, no halfband
-    int px_enabled;            // extra decode groups the host launches after k_stream: bit 0 = MP2's P3, bit 1 = MP11's P4
+    int px_enabled;            // PX_NEED_* bits: the extended-partition decode groups the host launches after k_stream
 };
 
 // buffers of one extra extended-partition decode group (same roles as the p3_* arrays)
@@ -134,7 +134,7 @@ struct PxBufs {
     uint32_t *bits;
     int *flags;
 };
-constexpr int PX_NEED_SHORT = 1, PX_NEED_PX2 = 2;
+constexpr int PX_NEED_SHORT = 1, PX_NEED_PX2 = 2, PX_NEED_P3 = 4;   // MP2 | MP11 (P4) | MP3 and MP11 (4608-bit P3)
 constexpr int P3S_LEN = 2304, IV_NS = IV_N / 2;    // MP2: P3 frame bits, interleaver IV span (decode.c:346-350)
 
 // Pointers to all device arrays, passed by value to kernels.

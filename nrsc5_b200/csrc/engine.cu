@@ -1213,13 +1213,15 @@ static void launch_p1(nrsc5b_engine *e)
     launch_vitc(p1_vitc_args(e->dp), S, e->stream);               // ... exact fallback for the frames it flagged
     k_p1_fin<<<dim3(FIN_CTAS, S), P1_THREADS, 0, e->stream>>>(e->dp, e->dims);
     e->stats.kernel_launches += 8;
-    // P3 frames (streams in MP3/MP11 queue up to 8 per pass; the kernels find nothing to do otherwise)
-    k_p3_gather<<<dim3(P3_SLOTS, S), 256, 0, e->stream>>>(e->dp, e->dims);
-    launch_v64(p3_v64_args(e->dp), S * P3_SLOTS, e->stream);
-    launch_vitc(p3_vitc_args(e->dp), S * P3_SLOTS, e->stream);
-    k_p3_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims);
-    e->stats.kernel_launches += 8;
-    // MP2's short P3 frames / MP11's P4 frames: only once a stream has asked for the group (enable_px_groups)
+    // P3 / P4 frames: every group only once a stream has asked for it (enable_px_groups).  MP3 / MP11's 4608-bit P3:
+    if (e->dims.px_enabled & PX_NEED_P3) {
+        k_p3_gather<<<dim3(P3_SLOTS, S), 256, 0, e->stream>>>(e->dp, e->dims);
+        launch_v64(p3_v64_args(e->dp), S * P3_SLOTS, e->stream);
+        launch_vitc(p3_vitc_args(e->dp), S * P3_SLOTS, e->stream);
+        k_p3_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims);
+        e->stats.kernel_launches += 8;
+    }
+    // MP2's short P3 frames / MP11's P4 frames
     for (int which = 0; which < 2; which++) {
         if (!(e->dims.px_enabled & (1 << which))) continue;
         k_px_gather<<<dim3(P3_SLOTS, S), 256, 0, e->stream>>>(e->dp, e->dims, which);
@@ -1234,6 +1236,7 @@ static void launch_p1(nrsc5b_engine *e)
 static int enable_px_groups(nrsc5b_engine *e, unsigned need)
 {
     const size_t F = (size_t)e->dims.nstreams * P3_SLOTS;
+    e->dims.px_enabled |= (int)(need & PX_NEED_P3);          // (its buffers exist from the start)
     for (int which = 0; which < 2; which++) {
         if (!(need & (1u << which)) || (e->dims.px_enabled & (1 << which))) continue;
         const int len = which == 0 ? P3S_LEN : P3_LEN;

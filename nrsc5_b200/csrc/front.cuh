@@ -247,10 +247,11 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
         const long long avail = *reinterpret_cast<volatile long long *>(&st.in_avail);
         int act = avail >= 2 * (st.start + NACQ);
         if (act && st.state == ST_FINE) {
-            // MP2's short P3 frames and MP11's P4 frames are decoded by kernel groups the host adds to the pass
-            // only when a stream asks: wait at the block boundary until it has (nrsc5b_process looks at the flag)
+            // P3 / P4 frames (MP2, MP3, MP11) are decoded by kernel groups the host adds to the pass only when a
+            // stream asks: wait at the block boundary until it has (nrsc5b_process looks at the flag).  Streams
+            // in MP1 / MP5 / MP6 never pay for those launches.
             const int cm = c_compat_mode[st.psmi & 63];
-            const int need = cm == 2 ? PX_NEED_SHORT : cm == 11 ? PX_NEED_PX2 : 0;
+            const int need = cm == 2 ? PX_NEED_SHORT : cm == 3 ? PX_NEED_P3 : cm == 11 ? (PX_NEED_P3 | PX_NEED_PX2) : 0;
             if (need & ~d.px_enabled) {
                 atomicOr(&g_px_need, (unsigned)need);
                 act = 0;
