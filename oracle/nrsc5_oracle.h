@@ -32,6 +32,14 @@ enum {
     ORC_REC_BLOCK = 9,     /* i32 state_in, i32 samperr, f32 angle, f32 ph_re, f32 ph_im, i32 cfo, i64 start */
 };
 
+/* the L2 -> L3 calls of frame.c, same layout as oracle/reftap_l2.c */
+enum {
+    ORC_REC_L2_SERVICE = 16,   /* i32 x8: program, access, type, codec_mode, blend_control, gain, common_delay, latency */
+    ORC_REC_L2_ALIGN = 17,     /* u32 program, stream_id, offset                                                        */
+    ORC_REC_L2_AAS = 18,       /* the bytes handed to output_aas_push                                                   */
+    ORC_REC_L2_PACKET = 19,    /* u32 program, stream_id, seq, shape, flags, size; then the packet bytes                */
+};
+
 typedef struct orc orc_t;
 
 orc_t *orc_new(void);
@@ -45,6 +53,19 @@ void orc_push_cs16(orc_t *o, const int16_t *buf, size_t nvalues);
 size_t orc_log_size(const orc_t *o);
 const uint8_t *orc_log_data(const orc_t *o);
 void orc_log_clear(orc_t *o);
+
+/* ---- L2 framing (oracle/nrsc5_oracle_l2.c): frame_push / frame_process, reference src/frame.c:130-714 ---- */
+typedef struct orc_l2 orc_l2_t;
+orc_l2_t *orc_l2_new(void);
+void orc_l2_free(orc_l2_t *o);
+void orc_l2_reset(orc_l2_t *o);                                   /* frame_reset */
+void orc_l2_push(orc_l2_t *o, const uint8_t *packed, unsigned nbits, unsigned lc);   /* frame_push */
+/* {u32 lc, u32 nbits, packed bits padded to 4} back to back; nbits == 0 = frame_reset */
+int orc_l2_frames(orc_l2_t *o, const uint8_t *frames, size_t nbytes);
+size_t orc_l2_log_size(const orc_l2_t *o);
+const uint8_t *orc_l2_log_data(const orc_l2_t *o);
+void orc_l2_log_clear(orc_l2_t *o);
+unsigned orc_l2_lost(const orc_l2_t *o);                          /* sync-loss predicate count (frame.c:535-540) */
 
 /* ---- AM (hybrid MA1), oracle/nrsc5_oracle_am.c: cs16 at 46 511.72 S/s in, same record stream out ---- */
 /* CRC-12 verdict of a PIDS frame (80 bits packed MSB-first), reference src/pids.c:52-86,1032-1050 */

@@ -1,0 +1,415 @@
+/* nrsc5_oracle_l2 — plain-C CPU restatement of the reference's L2 framing
+ * (SURVEY §8 f1): frame_push / frame_process of theori-io/nrsc5
+ * (reference src/frame.c:130-714), i.e. PCI extraction, RS-protected audio
+ * PDU headers, packet locations, header expansion fields, CRC-8 per packet,
+ * PSD over HDLC with FCS-16, and the fixed-data (CCC / subchannel) path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see nrsc5_oracle.h): the checker for
+ * nrsc5_b200/csrc/l2.cuh.  The product never links or calls it.
+ *
+ * Parity pin: tests/test_oracle_l2.py compares the record stream written
+ * here, byte for byte, with the one oracle/reftap_l2.c taps from the
+ * UNMODIFIED reference (output_align / output_push / output_aas_push /
+ * nrsc5_report_audio_service in call order) on the P1 frames of
+ * support/sample.xz and on generated PDUs (nrsc5_b200/synth_l2.py) that
+ * cover header errors, HEF, both location widths, PSD, fixed data and the
+ * truncation / early-return branches.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nrsc5_oracle.h"
+
+enum { BUF_LEN = 18269, AAS_MAX = 8212, NPROG = 8, NLC = 3, RING = 64 };   /* frame.h:5, defines.h:63-71 */
+
+typedef struct {
+    unsigned mode, length, fill;          /* fill: bytes held in blk[]                      */
+    uint8_t blk[259];
+    int idx;
+    uint8_t data[AAS_MAX];
+} l2_sub_t;
+
+typedef struct {
+    unsigned width, count;
+    uint8_t ccc[32];
+    int ccc_idx;
+    l2_sub_t sub[4];
+    int ready;
+} l2_ccc_t;
+
+struct orc_l2 {
+    uint8_t buf[BUF_LEN];                 /* PDU bytes; persists from frame to frame like frame_t::buffer */
+    int svc[NPROG][7];                    /* access, type, codec_mode, blend_control, gain, common_delay, latency */
+    uint32_t pci;
+    uint8_t psd[NPROG][AAS_MAX];
+    int psd_idx[NPROG];
+    l2_ccc_t ccc[NLC];
+    uint8_t *log;
+    size_t len, cap;
+    unsigned lost;                        /* times the sync-loss predicate fired (frame.c:535-540) */
+};
+
+static void put(orc_l2_t *o, uint32_t type, const void *a, size_t alen, const void *b, size_t blen)
+{
+    size_t plen = alen + blen, need = 8 + ((plen + 3) & ~(size_t)3);
+    if (o->len + need > o->cap) {
+        size_t nc = o->cap ? o->cap * 2 : (1u << 18);
+        while (nc < o->len + need) nc *= 2;
+        o->log = (uint8_t *)realloc(o->log, nc);
+        o->cap = nc;
+    }
+    uint32_t hdr[2] = { type, (uint32_t)plen };
+    memcpy(o->log + o->len, hdr, 8);
+    if (alen) memcpy(o->log + o->len + 8, a, alen);
+    if (blen) memcpy(o->log + o->len + 8 + alen, b, blen);
+    memset(o->log + o->len + 8 + plen, 0, need - 8 - plen);
+    o->len += need;
+}
+
+/* CRC-8, polynomial 0x31, initial value 0xFF (frame.c:60-93,130-136: the table is that of x^8+x^5+x^4+1) */
+static unsigned crc8_bytes(const uint8_t *p, unsigned n)
+{
+    unsigned c = 0xFF;
+    for (unsigned i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c & 0x80) ? ((c << 1) ^ 0x31) & 0xFF : (c << 1) & 0xFF;
+    }
+    return c;
+}
+
+/* FCS-16 of RFC 1662 (reflected 0x8408), frame.c:95-144; a good frame leaves 0xF0B8 */
+static unsigned fcs16_bytes(const uint8_t *p, int n)
+{
+    unsigned c = 0xFFFF;
+    while (n-- > 0) {
+        c ^= *p++;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x8408 : c >> 1;
+    }
+    return c;
+}
+
+void orc_l2_reset(orc_l2_t *o)                                       /* frame.c:716-742 */
+{
+    for (int p = 0; p < NPROG; p++) {
+        for (int k = 0; k < 7; k++) o->svc[p][k] = -1;
+        o->psd_idx[p] = -1;
+    }
+    o->pci = 0;
+    for (int c = 0; c < NLC; c++) {
+        o->ccc[c].ready = 0;
+        o->ccc[c].width = 0;
+        o->ccc[c].count = 0;
+        o->ccc[c].ccc_idx = -1;
+    }
+}
+
+orc_l2_t *orc_l2_new(void)
+{
+    orc_l2_t *o = (orc_l2_t *)calloc(1, sizeof(*o));
+    orc_l2_reset(o);
+    return o;
+}
+
+void orc_l2_free(orc_l2_t *o)
+{
+    if (!o) return;
+    free(o->log);
+    free(o);
+}
+
+size_t orc_l2_log_size(const orc_l2_t *o) { return o->len; }
+const uint8_t *orc_l2_log_data(const orc_l2_t *o) { return o->log; }
+void orc_l2_log_clear(orc_l2_t *o) { o->len = 0; }
+unsigned orc_l2_lost(const orc_l2_t *o) { return o->lost; }
+
+/* frame.c:328-341; a trailing 0x7D takes the byte after the frame, as the reference does */
+static int hdlc_unescape(uint8_t *d, int n)
+{
+    int w = 0;
+    for (int i = 0; i < n; i++) {
+        if (d[i] == 0x7D) d[w++] = d[++i] | 0x20;
+        else d[w++] = d[i];
+    }
+    return w;
+}
+
+/* one complete HDLC frame of PSD / AAS data (frame.c:343-367) */
+static void aas_frame(orc_l2_t *o, uint8_t *d, int n)
+{
+    n = hdlc_unescape(d, n);
+    if (n == 0) return;
+    if (fcs16_bytes(d, n) != 0xF0B8) return;
+    if (d[0] != 0x21) return;
+    put(o, ORC_REC_L2_AAS, d + 1, (size_t)(unsigned)(n - 3), NULL, 0);
+}
+
+/* one complete HDLC frame on the channel-configuration channel (frame.c:393-438) */
+static void ccc_frame(l2_ccc_t *c, uint8_t *d, int n0)
+{
+    unsigned n = (unsigned)hdlc_unescape(d, n0);
+    if (n == 0 || c->ready) return;
+    if (fcs16_bytes(d, (int)n) != 0xF0B8) return;
+    for (unsigned i = 0; i < 4; i++) {
+        l2_sub_t *s = &c->sub[i];
+        s->mode = 0;
+        s->length = 0;
+        if (5 + 4 * i <= n) {
+            unsigned mode = d[1 + 4 * i] | (d[2 + 4 * i] << 8), len = d[3 + 4 * i] | (d[4 + 4 * i] << 8);
+            if (mode == 0) {
+                s->length = len;
+                s->fill = 0;
+                s->idx = -1;
+            }
+        }
+    }
+    c->ready = 1;
+}
+
+/* HDLC byte scanner shared by PSD, CCC and the subchannels (frame.c:369-391).  kind: 0 = AAS, 1 = CCC */
+static void hdlc_scan(orc_l2_t *o, int kind, l2_ccc_t *c, uint8_t *acc, int *idx, int cap, const uint8_t *in, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        uint8_t b = in[i];
+        if (b == 0x7E) {
+            if (*idx >= 0) {
+                if (kind) ccc_frame(c, acc, *idx);
+                else aas_frame(o, acc, *idx);
+            }
+            *idx = 0;
+        } else if (*idx >= 0) {
+            if (*idx == cap) {
+                *idx = -1;
+                continue;
+            }
+            acc[(*idx)++] = b;
+        }
+    }
+}
+
+/* fixed-data tail of a PDU (frame.c:448-514); returns where the audio part ends */
+static unsigned fixed_tail(orc_l2_t *o, unsigned length, unsigned lc)
+{
+    static const uint8_t marker[4] = { 0x7D, 0x3A, 0xE2, 0x42 };
+    l2_ccc_t *c = &o->ccc[lc];
+    unsigned pos = length - 1;
+    if (c->count < 2) {
+        uint8_t b = o->buf[pos];
+        unsigned w = b == 0 ? 1 : ((b >> 4) == (b & 15) ? (b & 15) * 2u : 0);
+        c->count = (w > 0 && c->width == w) ? c->count + 1 : 0;
+        c->width = w;
+        if (c->count < 2) return pos;
+    }
+    pos -= c->width;
+    hdlc_scan(o, 1, c, c->ccc, &c->ccc_idx, 32, o->buf + pos, c->width);
+    if (!c->ready) return pos;
+    for (int i = 3; i >= 0; i--) {
+        l2_sub_t *s = &c->sub[i];
+        if (s->length == 0) continue;
+        pos -= s->length;
+        for (unsigned j = 0; j < s->length; j++) {
+            s->blk[s->fill++] = o->buf[pos + j];
+            if (s->fill == 4 && memcmp(s->blk, marker, 4) != 0) {
+                memmove(s->blk, s->blk + 1, 3);
+                s->fill--;
+            }
+            if (s->fill == 259) {
+                hdlc_scan(o, 0, NULL, s->data, &s->idx, AAS_MAX, s->blk + 4, 255);
+                s->fill = 0;
+            }
+        }
+    }
+    return pos;
+}
+
+typedef struct { unsigned prog, pdu_len, type, access, services, marker; } l2_hef_t;
+
+/* header expansion fields (frame.c:198-265); returns the bytes consumed (all of them when truncated) */
+static unsigned hef_walk(const uint8_t *b, unsigned n, l2_hef_t *h)
+{
+    unsigned i = 0;
+    for (;;) {
+        if (i >= n) return n;
+        uint8_t v = b[i];
+        switch ((v >> 4) & 7) {
+        case 0:
+            break;
+        case 1:
+            h->prog = (v >> 1) & 7;
+            if (v & 1) {
+                if (i + 2 >= n) return n;
+                h->pdu_len = ((b[i + 1] & 0x7Fu) << 7) | (b[i + 2] & 0x7F);
+                i += 2;
+            }
+            break;
+        case 2:
+            if (i + 1 >= n) return n;
+            h->access = (v >> 3) & 1;
+            h->type = ((v & 1u) << 7) | (b[i + 1] & 0x7F);
+            i += 1;
+            break;
+        case 3: {
+            unsigned skip = (v & 8) ? 4 : 3;
+            if (i + skip >= n) return n;
+            i += skip;
+            break;
+        }
+        case 4:
+            if (v & 8) {
+                if (i + 3 >= n) return n;
+                h->services = v & 7;
+                h->marker = ((b[i + 1] & 0x7Fu) << 14) | ((b[i + 2] & 0x7Fu) << 7) | (b[i + 3] & 0x7F);
+                i += 3;
+            } else {
+                if (i + 1 >= n) return n;
+                i += 1;
+            }
+            break;
+        default:
+            break;
+        }
+        if (!(b[i++] & 0x80)) return i;
+    }
+}
+
+static unsigned loc_bits_of(unsigned codec, unsigned stream)                 /* frame.c:267-287 */
+{
+    if (codec >= 1 && codec <= 3) return stream == 0 ? 12 : 16;
+    if (codec == 10 || codec == 13) return 12;
+    return 16;
+}
+
+static unsigned avg_packets_of(unsigned codec, unsigned stream)              /* frame.c:289-313 */
+{
+    if (codec >= 1 && codec <= 3) return stream == 0 ? 4 : 32;
+    if (codec == 10) return stream == 0 ? 32 : 4;
+    if (codec == 13) return 4;
+    return 32;
+}
+
+static unsigned location_at(const uint8_t *b, unsigned bits, unsigned j)     /* frame.c:315-326 */
+{
+    if (bits == 16) return b[2 * j] | (b[2 * j + 1] << 8);
+    const uint8_t *q = b + (j / 2) * 3;
+    return (j & 1) ? (q[2] << 4) | (q[1] >> 4) : ((q[1] & 15u) << 8) | q[0];
+}
+
+/* the audio PDUs of one L1 PDU (frame.c:516-643); p1_len: this PDU length makes a bad first header drop sync */
+static void walk_pdus(orc_l2_t *o, unsigned length, unsigned lc)
+{
+    unsigned end = length, off = 0;
+    const uint32_t k = o->pci & 0xFFFFFC;
+    const int fixed = k == (0xE3634C & 0xFFFFFC) || k == (0x8D8D33 & 0xFFFFFC) || k == (0x3634CE & 0xFFFFFC);
+    if (fixed) end = fixed_tail(o, length, lc);
+    if (k == (0x3634CE & 0xFFFFFC)) return;
+    while (off < end - 96u) {                                             /* unsigned, as in the reference */
+        const unsigned start = off;
+        uint8_t *h = o->buf + off;
+        if (!orc_fix_header(h)) {
+            if ((length == 18269 || length == 466) && off == 0) o->lost++;
+            return;
+        }
+        const unsigned codec = h[8] & 15, stream = (h[8] >> 4) & 3, pdu_seq = (h[8] >> 6) | ((h[9] & 1u) << 2);
+        const unsigned blend = (h[9] >> 1) & 3, psd_delay = h[9] >> 3, common = h[10] & 0x3F;
+        const unsigned latency = (h[10] >> 6) | ((h[11] & 1u) << 2), pfirst = (h[11] >> 1) & 1, plast = (h[11] >> 2) & 1;
+        const unsigned seq0 = (h[11] >> 3) | ((h[12] & 1u) << 5), nop = (h[12] >> 1) & 0x3F, has_hef = h[12] >> 7;
+        const unsigned la = h[13];
+        off += 14;
+        const unsigned lbits = loc_bits_of(codec, stream), lbytes = (lbits * nop + 4) / 8;
+        if (start + la + 1 < off + lbytes || start + la >= end) return;
+        unsigned loc[64];
+        for (unsigned j = 0; j < nop; j++) {
+            loc[j] = location_at(o->buf + off, lbits, j);
+            if (j == 0 ? loc[j] <= la : loc[j] <= loc[j - 1]) return;
+            if (start + loc[j] >= end) return;
+        }
+        off += lbytes;
+        if (stream >= 2) {
+            off = start + loc[nop - 1] + 1;
+            continue;
+        }
+        l2_hef_t hef = { 0, 0, 0, 0, 0, 0 };
+        if (has_hef) off += hef_walk(o->buf + off, end - off, &hef);
+        const unsigned prog = hef.prog;
+        int *sv = o->svc[prog];
+        const int now[7] = { (int)hef.access, (int)hef.type, (int)codec, (int)blend, (int)psd_delay, (int)common, (int)latency };
+        if (stream == 0 && memcmp(sv, now, sizeof(now)) != 0) {
+            memcpy(sv, now, sizeof(now));
+            int32_t r[8] = { (int32_t)prog, sv[0], sv[1], sv[2], sv[3], sv[4] < 16 ? sv[4] : sv[4] - 32, sv[5] * 4, sv[6] * 2 };
+            put(o, ORC_REC_L2_SERVICE, r, sizeof(r), NULL, 0);
+        }
+        const unsigned avg = avg_packets_of(codec, stream);
+        unsigned seq = (RING + seq0 - pfirst) % RING;
+        unsigned out_off = (RING + pdu_seq * avg - latency * 2) % RING;
+        if ((RING + seq - out_off) % RING >= RING / 2) out_off = (out_off + RING / 2) % RING;
+        uint32_t al[3] = { prog, stream, out_off };
+        put(o, ORC_REC_L2_ALIGN, al, sizeof(al), NULL, 0);
+        hdlc_scan(o, 0, NULL, o->psd[prog], &o->psd_idx[prog], AAS_MAX, o->buf + off, (size_t)(start + la + 1 - off));
+        off = start + la + 1;
+        for (unsigned j = 0; j < nop; j++) {
+            const unsigned cnt = start + loc[j] - off;
+            uint32_t pk[6] = { prog, stream, seq, 0, crc8_bytes(o->buf + off, cnt + 1) ? 1u : 0u, cnt };
+            pk[3] = (j == 0 && pfirst) ? 3 : (j == nop - 1 && plast) ? 2 : 1;      /* output.h:28-31: FULL 1, HALF_FRONT 2, HALF_BACK 3 */
+            put(o, ORC_REC_L2_PACKET, pk, sizeof(pk), o->buf + off, cnt);
+            off += cnt + 1;
+            seq = (seq + 1) % RING;
+        }
+    }
+}
+
+/* frame_push (frame.c:645-714): bits packed MSB-first as in the REC_FRAME records */
+void orc_l2_push(orc_l2_t *o, const uint8_t *packed, unsigned nbits, unsigned lc)
+{
+    unsigned first, step, npci;
+    switch (nbits) {
+    case 146176: first = 146176 - 30000; step = 1248; npci = 24; break;
+    case 4608: first = 120; step = 184; npci = 24; break;
+    case 2304: first = 120; step = 88; npci = 24; break;
+    case 3750: first = 120; step = 160; npci = 22; break;
+    case 24000: first = 120; step = 992; npci = 24; break;
+    case 30000: first = 120; step = 1240; npci = 24; break;
+    default: return;
+    }
+    uint32_t fh[2] = { lc, nbits };
+    put(o, ORC_REC_FRAME, fh, sizeof(fh), packed, (nbits + 7) / 8);
+    uint32_t pci = 0;
+    unsigned got = 0, nout = 0, acc = 0, fill = 0;
+    for (unsigned i = 0; i < nbits; i++) {
+        const unsigned base = i & ~7u, span = nbits - base < 8 ? nbits - base : 8;
+        const unsigned src = base + span - 1 - (i & 7);
+        const unsigned bit = (packed[src >> 3] >> (7 - (src & 7))) & 1;
+        if (i >= first && (i - first) % step == 0 && got < npci) {
+            pci |= bit << (23 - got);
+            got++;
+        } else {
+            acc = (acc << 1) | bit;
+            if (++fill == 8) {
+                o->buf[nout++] = (uint8_t)acc;
+                acc = 0;
+                fill = 0;
+            }
+        }
+    }
+    o->pci = pci;
+    walk_pdus(o, nout, lc);
+}
+
+/* frames: {u32 lc, u32 nbits, packed bits padded to 4 bytes} back to back; nbits == 0 = frame_reset() */
+int orc_l2_frames(orc_l2_t *o, const uint8_t *frames, size_t nbytes)
+{
+    size_t off = 0;
+    while (off + 8 <= nbytes) {
+        uint32_t hdr[2];
+        memcpy(hdr, frames + off, 8);
+        off += 8;
+        if (hdr[1] == 0) {
+            orc_l2_reset(o);
+            continue;
+        }
+        size_t nb = (hdr[1] + 7) / 8;
+        if (off + nb > nbytes) return -1;
+        orc_l2_push(o, frames + off, hdr[1], hdr[0]);
+        off += (nb + 3) & ~(size_t)3;
+    }
+    return 0;
+}

@@ -50,6 +50,15 @@ def lib():
         L.orc_rs_decode.argtypes = [ctypes.c_void_p]
         L.orc_fix_header.argtypes = [ctypes.c_void_p]
         L.orc_p1_sync_lost.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_l2_new.restype = ctypes.c_void_p
+        L.orc_l2_free.argtypes = [ctypes.c_void_p]
+        L.orc_l2_frames.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_l2_log_size.restype = ctypes.c_size_t
+        L.orc_l2_log_size.argtypes = [ctypes.c_void_p]
+        L.orc_l2_log_data.restype = ctypes.c_void_p
+        L.orc_l2_log_data.argtypes = [ctypes.c_void_p]
+        L.orc_l2_lost.restype = ctypes.c_uint
+        L.orc_l2_lost.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -166,3 +175,33 @@ def p1_sync_lost(bits: np.ndarray):
     pci = ctypes.c_uint32(0)
     lost = lib().orc_p1_sync_lost(b.ctypes.data, ctypes.byref(pci))
     return bool(lost), pci.value
+
+
+def l2_frames(frames, raw=False):
+    """L2 framing (oracle/nrsc5_oracle_l2.c) over a sequence of L1 PDUs: (lc, nbits, packed bits) or None
+    (= frame_reset).  Returns the record stream (every frame followed by the L2 -> L3 calls it causes) and the
+    number of times the sync-loss predicate fired."""
+    from reftap import pack_frames
+    L = lib()
+    o = L.orc_l2_new()
+    try:
+        blob = pack_frames(frames)
+        rc = L.orc_l2_frames(o, blob, len(blob))
+        assert rc == 0
+        rawlog = ctypes.string_at(L.orc_l2_log_data(o), L.orc_l2_log_size(o))
+        lost = L.orc_l2_lost(o)
+    finally:
+        L.orc_l2_free(o)
+    return (rawlog if raw else _parse(rawlog)), lost
+
+
+def l1_to_l2_input(records):
+    """The L1 record stream of a decode -> the frame list L2 sees: frame_reset where fine sync was entered
+    (REC_SYNC, reference src/sync.c:405-409), then every REC_FRAME in order."""
+    out = []
+    for ty, r in records:
+        if ty == 3:
+            out.append(None)
+        elif ty == 1:
+            out.append((r["lc"], r["nbits"], r["bits"]))
+    return out

@@ -61,6 +61,10 @@ static void log_put(uint32_t type, const void *a, size_t alen, const void *b, si
     g_len += need;
 }
 
+/* for reftap_l2.c (the L2 -> L3 taps share this log) */
+void reftap_log_put(uint32_t type, const void *a, size_t alen, const void *b, size_t blen) { log_put(type, a, alen, b, blen); }
+void reftap_set_logging(int on) { tls_logging = on; }
+
 /* ---- link-time taps (-Wl,--wrap=...) ---- */
 struct frame_t;
 struct pids_t;

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libnrsc5_ref.so")
 
 REC_FRAME, REC_PIDS, REC_SYNC, REC_LOST_SYNC, REC_MER, REC_BER, REC_HDC, REC_SOFT_PM, REC_BLOCK = range(1, 10)
+REC_L2_SERVICE, REC_L2_ALIGN, REC_L2_AAS, REC_L2_PACKET = 16, 17, 18, 19   # the L2 -> L3 calls (reftap_l2.c)
 MODE_FM, MODE_AM = 0, 1
 
 _lib = None
@@ -30,6 +31,7 @@ def lib():
         L.reftap_log_size.restype = ctypes.c_size_t
         L.reftap_log_data.restype = ctypes.c_void_p
         L.reftap_decode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+        L.reftap_l2_frames.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
         L.reftap_bench.restype = ctypes.c_double
         L.reftap_bench.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _lib = L
@@ -89,10 +91,55 @@ def _parse(raw: bytes) -> RefLog:
         elif ty == REC_BLOCK:
             st, se, ang, pr, pi, cfo, start = struct.unpack("<iifffiq", pay[:32])
             rec = {"state": st, "samperr": se, "angle": ang, "phase": complex(pr, pi), "cfo": cfo, "start": start}
+        elif ty in (REC_L2_SERVICE, REC_L2_ALIGN, REC_L2_AAS, REC_L2_PACKET):
+            rec = parse_l2(ty, pay)
         else:
             raise ValueError(f"bad record type {ty}")
         out.records.append((ty, rec))
     return out
+
+
+def parse_l2(ty, pay):
+    """Payload of one L2 -> L3 call record (same layout in the reference tap, the oracle and the engine)."""
+    if ty == REC_L2_SERVICE:
+        k = ("program", "access", "type", "codec_mode", "blend_control", "gain", "common_delay", "latency")
+        return dict(zip(k, struct.unpack("<8i", pay[:32])))
+    if ty == REC_L2_ALIGN:
+        return dict(zip(("program", "stream_id", "offset"), struct.unpack("<3I", pay[:12])))
+    if ty == REC_L2_AAS:
+        return {"data": bytes(pay)}
+    k = ("program", "stream_id", "seq", "shape", "flags", "size")
+    rec = dict(zip(k, struct.unpack("<6I", pay[:24])))
+    rec["data"] = bytes(pay[24:24 + rec["size"]])
+    return rec
+
+
+def pack_frames(frames) -> bytes:
+    """frames: iterable of (lc, nbits, packed bits) or None (= frame_reset) -> the byte layout reftap_l2_frames,
+    the oracle's L2 entry and nrsc5b_l2_frames take."""
+    out = bytearray()
+    for f in frames:
+        if f is None:
+            out += struct.pack("<II", 0, 0)
+            continue
+        lc, nbits, bits = f
+        nb = (nbits + 7) // 8
+        assert len(bits) >= nb
+        out += struct.pack("<II", lc, nbits) + bytes(bits[:nb]) + bytes((-nb) % 4)
+    return bytes(out)
+
+
+def l2_frames(frames, mode=MODE_FM) -> RefLog:
+    """Feed L1 PDUs straight into the reference's frame_push() on a fresh handle; the log holds every frame
+    followed by the L2 -> L3 calls it caused."""
+    L = lib()
+    raw_in = pack_frames(frames)
+    L.reftap_reset()
+    rc = L.reftap_l2_frames(raw_in, len(raw_in), mode)
+    assert rc == 0
+    raw = ctypes.string_at(L.reftap_log_data(), L.reftap_log_size())
+    L.reftap_reset()
+    return _parse(raw)
 
 
 def decode(samples: np.ndarray, mode=MODE_FM, chunk=0, want_soft=False) -> RefLog:
