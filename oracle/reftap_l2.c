@@ -51,10 +51,16 @@ void __wrap_output_push(output_t *st, const packet_ref_t *ref)
     __real_output_push(st, ref);
 }
 
+/* reftap_l2_frames() feeds generated PDUs whose AAS payloads are random bytes; the L3 parsers behind
+ * output_aas_push (ID3, SIG, LOT: outside the L2 row) are not meant to see those, so the call is recorded there
+ * and not forwarded.  Captures decoded through the public API (reftap_decode) are forwarded as always. */
+static int g_isolate_l3;
+
 void __wrap_output_aas_push(output_t *st, uint8_t *psd, unsigned int len)
 {
     reftap_log_put(REC_L2_AAS, psd, len, NULL, 0);
-    __real_output_aas_push(st, psd, len);
+    if (!g_isolate_l3)
+        __real_output_aas_push(st, psd, len);
 }
 
 void __wrap_nrsc5_report_audio_service(nrsc5_t *st, unsigned int program, unsigned int access, unsigned int type,
@@ -78,6 +84,7 @@ int reftap_l2_frames(const uint8_t *frames, size_t nbytes, int mode)
         return -1;
     nrsc5_set_mode(st, mode);
     reftap_set_logging(1);
+    g_isolate_l3 = 1;
     size_t off = 0;
     uint8_t *bits = (uint8_t *)malloc(P1_FRAME_LEN_FM);
     while (off + 8 <= nbytes) {
@@ -95,6 +102,7 @@ int reftap_l2_frames(const uint8_t *frames, size_t nbytes, int mode)
         __wrap_frame_push(&st->input.frame, bits, hdr[1], (logical_channel_t)hdr[0]);
     }
     free(bits);
+    g_isolate_l3 = 0;
     reftap_set_logging(0);
     nrsc5_close(st);
     return 0;
