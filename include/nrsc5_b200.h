@@ -39,6 +39,9 @@
  *       The engine evaluates the same predicate on the GPU (RS(255,247) header
  *       check, reference src/frame.c:158-179 + src/rs_decode.c) so batch use
  *       needs no host round trip; a host L2 may still force the state.
+ *   nrsc5b_enable_l2 / nrsc5b_l2_frames
+ *       frame_push / frame_process / frame_reset (L2 framing: PCI, audio PDU headers, packet locations, HEF, CRC-8,
+ *       PSD over HDLC, fixed data)                  reference src/frame.h:53-54, src/frame.c:516-742
  *   nrsc5b_rs_decode
  *       decode_rs_char(rs, data, NULL, 0) for the (255,247) code set up at
  *                                                   reference src/frame.c:747, src/rs_decode.c:16
@@ -83,6 +86,18 @@ enum {
     NRSC5B_REC_BER = 6,       /* f32 cber                                  */
     NRSC5B_REC_SOFT_PM = 8,   /* u32 bc, 23040 int8 (only when enabled)    */
     NRSC5B_REC_BLOCK = 9,     /* i32 state_in, i32 samperr, f32 angle, f32 ph_re, f32 ph_im, i32 cfo, i64 start */
+    NRSC5B_REC_L2 = 20,       /* what frame_process() made of one frame (nrsc5b_enable_l2): u32 frame_off (log offset of the
+                               * frame's packed bits in this drain; nrsc5b_l2_frames: index of the frame), u32 lc, u32 nbits,
+                               * u32 pci, u32 flags (1: the sync-loss predicate of frame.c:535-540 fired, 2: event staging
+                               * overflowed), u32 pdu_len, u32 ev_len, u32 frame ordinal; then ev_len bytes of events, then
+                               * the PDU bytes (PCI removed, headers corrected; padded to 4).  Events, in the order of the
+                               * reference's L2 -> L3 calls, each {u32 type, u32 len, payload padded to 4}:
+                               *   16 nrsc5_report_audio_service (frame.c:590): i32 program, access, type, codec_mode,
+                               *      blend_control, digital_audio_gain, common_delay, latency
+                               *   17 output_align (frame.c:606): u32 program, stream_id, offset
+                               *   18 output_aas_push (frame.c:365): the bytes (protocol and FCS removed)
+                               *   19 output_push (frame.c:635): u32 program, stream_id, seq, shape, flags, size, and the
+                               *      packet's offset in the PDU bytes */
 };
 
 typedef struct nrsc5b_engine nrsc5b_engine_t;
@@ -168,6 +183,12 @@ int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12, unsig
 /* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops); 0 = default. */
 int nrsc5b_debug_set(int flags);
 
+/* L2 framing on the device for every frame an FM engine decodes from now on: after each REC_FRAME's pass
+ * the log also holds a REC_L2 record with what frame_push / frame_process (reference src/frame.c:516-714) would have
+ * handed on: audio service changes, elastic-buffer alignment, PSD / AAS messages and the HDC packets with their CRC
+ * verdicts.  The per-stream L2 state (service table, PSD and fixed-data assembly) lives on the GPU. */
+int nrsc5b_enable_l2(nrsc5b_engine_t *e, int on);
+
 /* ---- single-stage entry points (kernel-level parity tests, host buffers) ---- */
 /* cu8 -> Q15 -> halfband /2 from zero history: out[2*npairs] int16 (reference src/firdecim_q15.c:137-165) */
 int nrsc5b_halfband_fm(int device, const uint8_t *cu8, size_t npairs, int16_t *out_ri);
@@ -177,6 +198,10 @@ int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int len, int n
 int nrsc5b_viterbi_k7_ex(int device, const int8_t *in, uint8_t *out, int len, int nframes, int *fallbacks);
 /* batch RS(255,247) decode in place; rc[n] = corrections or -1 (reference src/rs_decode.c:16) */
 int nrsc5b_rs_decode(int device, uint8_t *blocks255, int *rc, int nblocks);
+/* L2 alone on one stream: frames = {u32 lc, u32 nbits, packed bits padded to 4 bytes} back to back, nbits == 0 standing
+ * for frame_reset (frame.c:716); all six frame lengths of frame.c:651-690.  Writes one REC_L2 record per frame
+ * (frame_off = the frame's index in the list) and returns the bytes written, or NRSC5B_EFULL. */
+long nrsc5b_l2_frames(int device, const uint8_t *frames, size_t nbytes, uint8_t *out, size_t cap, size_t *needed);
 /* 2048-point forward complex FFT of nffts rows (float2 interleaved), natural order, for numerics tests */
 int nrsc5b_fft2048(int device, const float *in, float *out, int nffts);
 

@@ -47,6 +47,8 @@ __host__ __device__ inline int compact_of_bin(int b)   // b in fftshift-ed coord
     return -1;
 }
 
+constexpr int L2_QUEUE = 40;                // frames + resets one pass can hand to L2 (16 blocks: 1 P1, 8 P3, 8 P4)
+
 // Per-stream persistent state.  One instance per stream in device memory.
 struct StreamState {
     // input cursor
@@ -97,6 +99,10 @@ struct StreamState {
     long long xq_k0[2][8];
     unsigned xq_rec[2][8];
     int force_state;           // host override (nrsc5b_set_sync_state), -1 = none
+    // L2 on the device (l2.cuh): what the pass handed to L2 so far, in the reference's call order - frames by the log
+    // offset of their packed bits (0xffffffff: the log was full), nbits == 0 for a frame_reset (entering fine sync)
+    int l2_n;
+    unsigned l2_off[L2_QUEUE], l2_lc[L2_QUEUE], l2_nbits[L2_QUEUE];
     // output log cursor
     unsigned log_len;
     unsigned log_overflow;
@@ -121,6 +127,7 @@ struct EngineDims {
     int emit_soft;
     int cs16;                  // input is cs16 at the decimated rate: 4 bytes per sample, no halfband
     int px_enabled;            // PX_NEED_* bits: the extended-partition decode groups the host launches after k_stream
+    int l2;                    // frames also go through L2 on the device (nrsc5b_enable_l2)
 };
 
 // buffers of one extra extended-partition decode group (same roles as the p3_* arrays)
@@ -190,6 +197,17 @@ __device__ inline uint8_t *log_reserve(const DevPtrs &p, const EngineDims &d, in
     reinterpret_cast<uint32_t *>(w)[1] = plen;
     st.log_len += need;
     return w + 8;
+}
+
+// hands a frame (or, with nbits == 0, a frame_reset) to the L2 kernel that ends the pass
+__device__ inline void l2_enqueue(StreamState &st, const EngineDims &d, const DevPtrs &p, int s, const uint8_t *bits,
+                                  unsigned lc, unsigned nbits)
+{
+    if (!d.l2 || st.l2_n >= L2_QUEUE) return;
+    const int e = st.l2_n++;
+    st.l2_off[e] = bits ? (unsigned)(bits - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+    st.l2_lc[e] = lc;
+    st.l2_nbits[e] = nbits;
 }
 
 // cu8 byte of absolute input sample n (component c); before the stream start

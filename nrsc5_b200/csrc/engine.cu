@@ -22,6 +22,7 @@
 #include "front.cuh"
 #include "am.cuh"
 #include "am_tables.h"
+#include "l2.cuh"
 
 namespace nb {
 
@@ -519,6 +520,60 @@ __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
     if (i < n) rc[i] = rs_decode_255_247(blocks + (size_t)i * 255);
 }
 
+// ===========================================================================
+// L2 framing (l2.cuh): the last kernel of a pass.  One CTA per stream walks the frames (and frame_resets) k_stream
+// queued, in the reference's call order, and appends one REC_L2 record per frame to the stream's log.
+// ===========================================================================
+__global__ void __launch_bounds__(nbl2::L2_THREADS) k_l2(DevPtrs p, EngineDims d, nbl2::L2State *l2)
+{
+    const int s = blockIdx.x;
+    StreamState &st = p.st[s];
+    const int n = st.l2_n;
+    if (n == 0) return;
+    uint8_t *base = p.log + (size_t)s * d.log_cap;
+    const nbl2::L2Sink sink = { base, d.log_cap, &st.log_len, &st.log_overflow };
+    for (int e = 0; e < n; e++) {
+        const unsigned off = st.l2_off[e], nbits = st.l2_nbits[e];
+        if (nbits == 0) {
+            if (threadIdx.x == 0) nbl2::l2_reset(l2[s]);
+            __syncthreads();
+        } else if (off != 0xffffffffu) {
+            nbl2::l2_frame(l2[s], base + off, nbits, st.l2_lc[e], off, sink);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st.l2_n = 0;
+}
+
+// state of a stream's L2 as the reference has it after calloc + frame_init (frame.c:744-749)
+__global__ void k_l2_init(nbl2::L2State *l2, int only)
+{
+    const int s = blockIdx.x;
+    if (only >= 0 && s != only) return;
+    uint32_t *w = reinterpret_cast<uint32_t *>(l2 + s);
+    static_assert(sizeof(nbl2::L2State) % 4 == 0, "word-wise clear");
+    for (size_t i = threadIdx.x; i < sizeof(nbl2::L2State) / 4; i += blockDim.x) w[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) nbl2::l2_reset(l2[s]);
+}
+
+// stage entry point: a list of frames (desc: offset into `frames`, lc, nbits; nbits == 0 = frame_reset) through one
+// stream's L2, records into out[cap]
+__global__ void __launch_bounds__(nbl2::L2_THREADS) k_l2_test(nbl2::L2State *l2, const uint8_t *frames, const uint32_t *desc,
+                                                               int ndesc, uint8_t *out, size_t cap, unsigned *len_ovf)
+{
+    const nbl2::L2Sink sink = { out, cap, len_ovf, len_ovf + 1 };
+    for (int e = 0; e < ndesc; e++) {
+        const unsigned off = desc[3 * e], lc = desc[3 * e + 1], nbits = desc[3 * e + 2];
+        if (nbits == 0) {
+            if (threadIdx.x == 0) nbl2::l2_reset(*l2);
+            __syncthreads();
+        } else {
+            nbl2::l2_frame(*l2, frames + off, nbits, lc, (unsigned)e, sink);
+        }
+    }
+}
+
 }  // namespace nb
 
 // ===========================================================================
@@ -568,6 +623,7 @@ struct nrsc5b_engine {
     uint8_t *am_ring;                  // AM with cu8 input: per-stream ring of raw samples ahead of the /32 decimator
     unsigned am_ring_bytes;            // bytes per stream, a power of two
     std::vector<long long> am_raw_bytes, am_dec_out;   // raw bytes received / cs16 samples produced per stream
+    nbl2::L2State *l2;                 // L2 on the device (nrsc5b_enable_l2): per-stream state, null until enabled
     int profiling;
     cudaEvent_t pev[5];
     double kernel_ms[4];
@@ -946,6 +1002,7 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
     const int S = e->dims.nstreams;
     CK(cudaStreamSynchronize(e->copy_stream));       // no input copy of the old contents may still be in flight
     k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream);
+    if (e->l2) k_l2_init<<<S, 256, 0, e->stream>>>(e->l2, stream < 0 ? -1 : stream);
     CK(cudaEventRecord(e->reset_done, e->stream));
     CK(cudaStreamWaitEvent(e->copy_stream, e->reset_done, 0));
     e->stats.kernel_launches += 1;
@@ -975,6 +1032,7 @@ extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
 {
     if (!e) return NRSC5B_EINVAL;
     k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2);
+    if (e->l2) k_l2_init<<<e->dims.nstreams, 256, 0, e->stream>>>(e->l2, -1);
     e->stats.kernel_launches += 1;
     for (int s = 0; s < e->dims.nstreams; s++) e->drained[s] = 0;
     CK(cudaGetLastError());
@@ -1229,6 +1287,11 @@ static void launch_p1(nrsc5b_engine *e)
         launch_vitc(px_vitc_args(e->dp, which), S * P3_SLOTS, e->stream);
         k_px_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims, which);
         e->stats.kernel_launches += 8;
+    }
+    // L2 framing of everything the pass decoded (only when enabled)
+    if (e->l2) {
+        k_l2<<<S, nbl2::L2_THREADS, 0, e->stream>>>(e->dp, e->dims, e->l2);
+        e->stats.kernel_launches += 1;
     }
 }
 
@@ -1620,6 +1683,68 @@ extern "C" int nrsc5b_rs_decode(int device, uint8_t *blocks, int *rcs, int n)
     cudaFree(db);
     cudaFree(dr);
     return NRSC5B_OK;
+}
+
+/* L2 framing on the device for every frame the engine decodes from now on (FM engines). */
+extern "C" int nrsc5b_enable_l2(nrsc5b_engine_t *e, int on)
+{
+    if (!e) return NRSC5B_EINVAL;
+    if (e->am_st) return NRSC5B_EINVAL;                    // AM frames leave k_am as REC_FRAME only (nrsc5b_l2_frames takes them)
+    CK(cudaStreamSynchronize(e->stream));
+    if (on && !e->l2) {
+        int rc = dev_alloc(e, &e->l2, (size_t)e->dims.nstreams, false);
+        if (rc) return rc;
+        k_l2_init<<<e->dims.nstreams, 256, 0, e->stream>>>(e->l2, -1);
+        CK(cudaGetLastError());
+    }
+    e->dims.l2 = on ? 1 : 0;
+    return NRSC5B_OK;
+}
+
+/* L2 alone: frames = {u32 lc, u32 nbits, packed bits padded to 4 bytes} back to back, nbits == 0 = frame_reset
+ * (reference src/frame.c:645 frame_push, :716 frame_reset); one REC_L2 record per frame into out. */
+extern "C" long nrsc5b_l2_frames(int device, const uint8_t *frames, size_t nbytes, uint8_t *out, size_t cap, size_t *needed)
+{
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (!frames || !out) return NRSC5B_EINVAL;
+    std::vector<uint32_t> desc;
+    size_t off = 0;
+    while (off + 8 <= nbytes) {
+        uint32_t h[2];
+        memcpy(h, frames + off, 8);
+        off += 8;
+        desc.push_back((uint32_t)off);
+        desc.push_back(h[0]);
+        desc.push_back(h[1]);
+        if (h[1] == 0) continue;
+        const size_t nb = (h[1] + 7) / 8;
+        if (off + nb > nbytes) return NRSC5B_EINVAL;
+        off += (nb + 3) & ~(size_t)3;
+    }
+    const int nd = (int)(desc.size() / 3);
+    if (nd == 0) { if (needed) *needed = 0; return 0; }
+    nbl2::L2State *st = nullptr;
+    uint8_t *df = nullptr, *dout = nullptr;
+    uint32_t *dd = nullptr;
+    unsigned *dlen = nullptr;
+    CK(cudaMalloc(&st, sizeof(nbl2::L2State)));
+    CK(cudaMalloc(&df, nbytes + 16));
+    CK(cudaMalloc(&dd, desc.size() * sizeof(uint32_t)));
+    CK(cudaMalloc(&dout, cap));
+    CK(cudaMalloc(&dlen, 2 * sizeof(unsigned)));
+    CK(cudaMemset(dlen, 0, 2 * sizeof(unsigned)));
+    CK(cudaMemcpy(df, frames, nbytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dd, desc.data(), desc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    k_l2_init<<<1, 256>>>(st, -1);
+    k_l2_test<<<1, nbl2::L2_THREADS>>>(st, df, dd, nd, dout, cap, dlen);
+    CK(cudaGetLastError());
+    unsigned lo[2] = { 0, 0 };
+    CK(cudaMemcpy(lo, dlen, sizeof(lo), cudaMemcpyDeviceToHost));
+    if (lo[0]) CK(cudaMemcpy(out, dout, lo[0], cudaMemcpyDeviceToHost));
+    cudaFree(st); cudaFree(df); cudaFree(dd); cudaFree(dout); cudaFree(dlen);
+    if (needed) *needed = lo[0];
+    return lo[1] ? (long)NRSC5B_EFULL : (long)lo[0];
 }
 
 extern "C" int nrsc5b_fft2048(int device, const float *in, float *out, int nffts)

@@ -1,0 +1,462 @@
+// L2 framing on the device: what the reference's frame_push / frame_process do with every L1
+// PDU (reference src/frame.c:645-714, 516-643) - PCI extraction, the RS(255,247)-protected audio PDU headers
+// (:158-196), packet locations (:315-326), header expansion fields (:198-265), PSD carried as HDLC frames with an
+// FCS-16 (:328-391, :138-144), CRC-8 of every packet (:130-136, :617-620), and the fixed-data tail with its CCC and
+// subchannel blocks (:393-514) - so that a frame's HDC packets, PSD messages and service changes leave the GPU as
+// one REC_L2 record and the host has no L2 work left.
+//
+// One CTA per stream takes the frames of a pass in the order the reference would see them:
+//   all threads : bit order swap + PCI removal -> PDU bytes in shared memory        (frame.c:692-710)
+//   thread 0    : the sequential part - fixed-data tail, header RS decode, location / HEF parsing, service
+//                 comparison, HDLC scanning - appending events to the stream's staging area and packets to a table
+//   all threads : CRC-8 of the packets (one packet per thread), then the copy of events + PDU bytes into the log
+// Per-stream state that outlives a frame (frame_t in the reference: service table, PSD assembly buffers, CCC and
+// subchannel state) lives in L2State in device memory.
+#pragma once
+#include "common.cuh"
+#include "rs.cuh"
+
+namespace nbl2 {
+
+constexpr int L2_THREADS = 128;
+constexpr int L2_PDU_MAX = 18269;            // (146176 - 24) / 8, reference src/defines.h:63
+constexpr int L2_AAS_MAX = 8212;             // reference src/frame.h:5
+constexpr int L2_EV_CAP = 96 * 1024;         // staging for one frame's events
+constexpr int L2_PK_MAX = 1024;              // packets whose CRC-8 the CTA computes in parallel (more: thread 0 does them)
+constexpr int L2_RING = 64;                  // ELASTIC_BUFFER_LEN, reference src/defines.h:71
+constexpr uint32_t REC_L2 = 20;              // include/nrsc5_b200.h
+constexpr uint32_t EV_SERVICE = 16, EV_ALIGN = 17, EV_AAS = 18, EV_PACKET = 19;
+constexpr uint32_t L2F_LOST = 1, L2F_EV_OVERFLOW = 2;
+
+struct L2Sub {                               // fixed_subchannel_t, reference src/frame.h:19-28
+    unsigned length, fill;
+    int idx;
+    uint8_t blk[260];
+    uint8_t data[L2_AAS_MAX];
+};
+
+struct L2Ccc {                               // ccc_data_t, reference src/frame.h:30-38
+    unsigned width, count;
+    int ccc_idx, ready;
+    uint8_t ccc[32];
+    L2Sub sub[4];
+};
+
+struct L2State {
+    int svc[8][7];                           // access, type, codec mode, blend control, gain, common delay, latency
+    int psd_idx[8];
+    unsigned frames;                         // frames taken since the stream was (re)created
+    L2Ccc ccc[3];
+    uint8_t psd[8][L2_AAS_MAX];
+    uint8_t ev[L2_EV_CAP];
+};
+
+// where the records go: a stream's log in the engine, a plain buffer in the stage entry point
+struct L2Sink {
+    uint8_t *base;
+    size_t cap;
+    unsigned *len;
+    unsigned *overflow;
+};
+
+__device__ inline void l2_reset(L2State &z)                        // frame_reset, reference src/frame.c:716-742
+{
+    for (int p = 0; p < 8; p++) {
+        for (int k = 0; k < 7; k++) z.svc[p][k] = -1;
+        z.psd_idx[p] = -1;
+    }
+    for (int c = 0; c < 3; c++) {
+        z.ccc[c].ready = 0;
+        z.ccc[c].width = 0;
+        z.ccc[c].count = 0;
+        z.ccc[c].ccc_idx = -1;
+    }
+}
+
+struct EvWriter {
+    uint8_t *base;
+    unsigned len, overflow;
+};
+
+// appends {type, plen, a, b} and returns the payload position (nullptr when the staging area is full)
+__device__ inline uint8_t *ev_put(EvWriter &w, uint32_t type, const void *a, unsigned alen, const uint8_t *b, unsigned blen)
+{
+    const unsigned plen = alen + blen, need = 8 + ((plen + 3) & ~3u);
+    if (w.len + need > (unsigned)L2_EV_CAP) {
+        w.overflow = 1;
+        return nullptr;
+    }
+    uint8_t *q = w.base + w.len;
+    reinterpret_cast<uint32_t *>(q)[0] = type;
+    reinterpret_cast<uint32_t *>(q)[1] = plen;
+    const uint8_t *ab = static_cast<const uint8_t *>(a);
+    for (unsigned i = 0; i < alen; i++) q[8 + i] = ab[i];
+    for (unsigned i = 0; i < blen; i++) q[8 + alen + i] = b[i];
+    for (unsigned i = plen; i < need - 8; i++) q[8 + i] = 0;
+    w.len += need;
+    return q + 8;
+}
+
+__device__ inline unsigned fcs16_of(const uint8_t *p, int n)        // RFC 1662 FCS, reference src/frame.c:95-144
+{
+    unsigned c = 0xFFFF;
+    for (int i = 0; i < n; i++) {
+        c ^= p[i];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0x8408u : 0u);
+    }
+    return c;
+}
+
+__device__ inline unsigned crc8_step(unsigned c, unsigned byte)     // x^8 + x^5 + x^4 + 1, reference src/frame.c:60-93
+{
+    c ^= byte;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c = ((c << 1) ^ ((c & 0x80) ? 0x31u : 0u)) & 0xFFu;
+    return c;
+}
+
+__device__ inline int hdlc_unescape(uint8_t *d, int n)              // reference src/frame.c:328-341
+{
+    int w = 0;
+    for (int i = 0; i < n; i++) {
+        if (d[i] == 0x7D) d[w++] = d[++i] | 0x20;
+        else d[w++] = d[i];
+    }
+    return w;
+}
+
+// a complete HDLC frame of PSD / AAS data: aas_push, reference src/frame.c:343-367
+__device__ inline void aas_frame(EvWriter &w, uint8_t *d, int n)
+{
+    n = hdlc_unescape(d, n);
+    if (n == 0) return;
+    if (fcs16_of(d, n) != 0xF0B8u) return;
+    if (d[0] != 0x21) return;
+    ev_put(w, EV_AAS, nullptr, 0, d + 1, (unsigned)(n - 3));
+}
+
+// a complete HDLC frame of the channel-configuration channel: process_fixed_ccc, reference src/frame.c:393-438
+__device__ inline void ccc_frame(L2Ccc &c, uint8_t *d, int n0)
+{
+    const unsigned n = (unsigned)hdlc_unescape(d, n0);
+    if (n == 0 || c.ready) return;
+    if (fcs16_of(d, (int)n) != 0xF0B8u) return;
+    for (unsigned i = 0; i < 4; i++) {
+        L2Sub &s = c.sub[i];
+        s.length = 0;
+        if (5 + 4 * i <= n) {
+            const unsigned mode = d[1 + 4 * i] | (d[2 + 4 * i] << 8), len = d[3 + 4 * i] | (d[4 + 4 * i] << 8);
+            if (mode == 0) {
+                s.length = len;
+                s.fill = 0;
+                s.idx = -1;
+            }
+        }
+    }
+    c.ready = 1;
+}
+
+// parse_hdlc, reference src/frame.c:369-391.  ccc != nullptr: frames go to ccc_frame, else to aas_frame
+__device__ inline void hdlc_scan(EvWriter &w, L2Ccc *ccc, uint8_t *acc, int *idx, int cap, const uint8_t *in, unsigned n)
+{
+    int k = *idx;
+    for (unsigned i = 0; i < n; i++) {
+        const uint8_t b = in[i];
+        if (b == 0x7E) {
+            if (k >= 0) {
+                if (ccc) ccc_frame(*ccc, acc, k);
+                else aas_frame(w, acc, k);
+            }
+            k = 0;
+        } else if (k >= 0) {
+            if (k == cap) k = -1;
+            else acc[k++] = b;
+        }
+    }
+    *idx = k;
+}
+
+// process_fixed_data, reference src/frame.c:448-514: returns where the audio part of the PDU ends
+__device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const uint8_t *pdu, unsigned length, unsigned lc)
+{
+    L2Ccc &c = z.ccc[lc];
+    unsigned pos = length - 1;
+    if (c.count < 2) {
+        const unsigned b = pdu[pos];
+        const unsigned wd = b == 0 ? 1u : ((b >> 4) == (b & 15u) ? (b & 15u) * 2u : 0u);
+        c.count = (wd > 0 && c.width == wd) ? c.count + 1 : 0;
+        c.width = wd;
+        if (c.count < 2) return pos;
+    }
+    pos -= c.width;
+    hdlc_scan(w, &c, c.ccc, &c.ccc_idx, 32, pdu + pos, c.width);
+    if (!c.ready) return pos;
+    for (int i = 3; i >= 0; i--) {
+        L2Sub &s = c.sub[i];
+        if (s.length == 0) continue;
+        pos -= s.length;
+        for (unsigned j = 0; j < s.length; j++) {
+            s.blk[s.fill++] = pdu[pos + j];
+            if (s.fill == 4 && !(s.blk[0] == 0x7D && s.blk[1] == 0x3A && s.blk[2] == 0xE2 && s.blk[3] == 0x42)) {
+                s.blk[0] = s.blk[1];                                  // not on a block boundary yet: slide by one byte
+                s.blk[1] = s.blk[2];
+                s.blk[2] = s.blk[3];
+                s.fill = 3;
+            }
+            if (s.fill == 259) {
+                hdlc_scan(w, nullptr, s.data, &s.idx, L2_AAS_MAX, s.blk + 4, 255);
+                s.fill = 0;
+            }
+        }
+    }
+    return pos;
+}
+
+struct Hef {
+    unsigned prog, access, type;
+};
+
+// parse_hef, reference src/frame.c:198-265: bytes consumed (all n of them when the field list is cut short)
+__device__ inline unsigned hef_walk(const uint8_t *b, unsigned n, Hef &h)
+{
+    unsigned i = 0;
+    for (;;) {
+        if (i >= n) return n;
+        const unsigned v = b[i];
+        switch ((v >> 4) & 7u) {
+        case 1:
+            h.prog = (v >> 1) & 7u;
+            if (v & 1u) {
+                if (i + 2 >= n) return n;
+                i += 2;                                               // PDU length: not used downstream
+            }
+            break;
+        case 2:
+            if (i + 1 >= n) return n;
+            h.access = (v >> 3) & 1u;
+            h.type = ((v & 1u) << 7) | (b[i + 1] & 0x7Fu);
+            i += 1;
+            break;
+        case 3: {
+            const unsigned skip = (v & 8u) ? 4 : 3;
+            if (i + skip >= n) return n;
+            i += skip;
+            break;
+        }
+        case 4: {
+            const unsigned skip = (v & 8u) ? 3 : 1;                   // applied services + PDU marker: not used downstream
+            if (i + skip >= n) return n;
+            i += skip;
+            break;
+        }
+        default:
+            break;
+        }
+        if (!(b[i++] & 0x80u)) return i;
+    }
+}
+
+struct PkEntry {
+    unsigned start, cnt, ev;                 // first byte, payload bytes, staging offset of the packet's flags word
+};
+
+// the sequential walk over one PDU (thread 0): frame_process, reference src/frame.c:516-643
+__device__ inline void l2_walk(L2State &z, EvWriter &w, uint8_t *pdu, unsigned length, unsigned lc, uint32_t pci,
+                               PkEntry *pk, unsigned &npk, unsigned &flags, uint8_t *rs_scratch)
+{
+    const uint32_t k = pci & 0xFFFFFCu;
+    const bool fixed = k == (0xE3634Cu & 0xFFFFFCu) || k == (0x8D8D33u & 0xFFFFFCu) || k == (0x3634CEu & 0xFFFFFCu);
+    unsigned end = length, off = 0;
+    if (fixed) end = fixed_tail(z, w, pdu, length, lc);
+    if (k == (0x3634CEu & 0xFFFFFCu)) return;                         // fixed data only: no audio
+    while (off < end - 96u) {                                         // unsigned on purpose, as frame.c:527
+        const unsigned start = off;
+        uint8_t *h = pdu + off;
+        if (!nb::fix_header_96(h, rs_scratch)) {
+            if ((length == 18269u || length == 466u) && off == 0) flags |= L2F_LOST;     // frame.c:535-540
+            return;
+        }
+        const unsigned codec = h[8] & 15u, stream = (h[8] >> 4) & 3u, pdu_seq = (h[8] >> 6) | ((h[9] & 1u) << 2);
+        const unsigned blend = (h[9] >> 1) & 3u, gain = h[9] >> 3, common = h[10] & 0x3Fu;
+        const unsigned latency = (h[10] >> 6) | ((h[11] & 1u) << 2), pfirst = (h[11] >> 1) & 1u, plast = (h[11] >> 2) & 1u;
+        const unsigned seq0 = (h[11] >> 3) | ((h[12] & 1u) << 5), nop = (h[12] >> 1) & 0x3Fu, has_hef = h[12] >> 7;
+        const unsigned la = h[13];
+        off += 14;
+        const bool narrow = (codec >= 1 && codec <= 3) ? stream == 0 : (codec == 10 || codec == 13);   // calc_lc_bits
+        const unsigned lbits = narrow ? 12u : 16u, lbytes = (lbits * nop + 4) / 8;
+        if (start + la + 1 < off + lbytes || start + la >= end) return;
+        unsigned loc[64];
+        for (unsigned j = 0; j < nop; j++) {
+            const uint8_t *q = pdu + off;
+            unsigned v;
+            if (!narrow) v = q[2 * j] | (q[2 * j + 1] << 8);
+            else {
+                const uint8_t *r = q + (j >> 1) * 3;
+                v = (j & 1u) ? ((unsigned)r[2] << 4) | (r[1] >> 4) : ((r[1] & 15u) << 8) | r[0];
+            }
+            loc[j] = v;
+            if (j == 0 ? v <= la : v <= loc[j - 1]) return;
+            if (start + v >= end) return;
+        }
+        off += lbytes;
+        if (stream >= 2) {                                            // MAX_STREAMS: skip this PDU
+            off = start + loc[nop - 1] + 1;
+            continue;
+        }
+        Hef hef = { 0, 0, 0 };
+        if (has_hef) off += hef_walk(pdu + off, end - off, hef);
+        const unsigned prog = hef.prog;
+        int *sv = z.svc[prog];
+        const int now[7] = { (int)hef.access, (int)hef.type, (int)codec, (int)blend, (int)gain, (int)common, (int)latency };
+        bool changed = false;
+        for (int i = 0; i < 7; i++) changed |= sv[i] != now[i];
+        if (stream == 0 && changed) {
+            for (int i = 0; i < 7; i++) sv[i] = now[i];
+            const int32_t r[8] = { (int32_t)prog, now[0], now[1], now[2], now[3], now[4] < 16 ? now[4] : now[4] - 32,
+                                   now[5] * 4, now[6] * 2 };
+            ev_put(w, EV_SERVICE, r, sizeof(r), nullptr, 0);
+        }
+        unsigned avg;                                                 // calc_avg_packets, frame.c:289-313
+        if (codec >= 1 && codec <= 3) avg = stream == 0 ? 4 : 32;
+        else if (codec == 10) avg = stream == 0 ? 32 : 4;
+        else avg = codec == 13 ? 4 : 32;
+        unsigned seq = (L2_RING + seq0 - pfirst) % L2_RING;
+        unsigned out_off = (L2_RING + pdu_seq * avg - latency * 2) % L2_RING;
+        if ((L2_RING + seq - out_off) % L2_RING >= L2_RING / 2) out_off = (out_off + L2_RING / 2) % L2_RING;
+        const uint32_t al[3] = { prog, stream, out_off };
+        ev_put(w, EV_ALIGN, al, sizeof(al), nullptr, 0);
+        hdlc_scan(w, nullptr, z.psd[prog], &z.psd_idx[prog], L2_AAS_MAX, pdu + off, start + la + 1 - off);
+        off = start + la + 1;
+        for (unsigned j = 0; j < nop; j++) {
+            const unsigned cnt = start + loc[j] - off;
+            const unsigned shape = (j == 0 && pfirst) ? 3u : (j == nop - 1 && plast) ? 2u : 1u;      // output.h:28-31
+            uint32_t r[7] = { prog, stream, seq, shape, 0u, cnt, off };
+            if (npk >= (unsigned)L2_PK_MAX) {                         // table full: this thread checks the CRC itself
+                unsigned c = 0xFF;
+                for (unsigned i = 0; i <= cnt; i++) c = crc8_step(c, pdu[off + i]);
+                r[4] = c ? 1u : 0u;
+            }
+            uint8_t *q = ev_put(w, EV_PACKET, r, sizeof(r), nullptr, 0);
+            if (q && npk < (unsigned)L2_PK_MAX) {
+                pk[npk].start = off;
+                pk[npk].cnt = cnt;
+                pk[npk].ev = (unsigned)(q - w.base) + 16;
+                npk++;
+            }
+            off += cnt + 1;
+            seq = (seq + 1) % L2_RING;
+        }
+    }
+}
+
+// frame geometry of frame_push, reference src/frame.c:651-690
+__device__ inline bool l2_geometry(unsigned nbits, unsigned &first, unsigned &step, unsigned &npci)
+{
+    switch (nbits) {
+    case 146176: first = 146176 - 30000; step = 1248; npci = 24; return true;
+    case 4608: first = 120; step = 184; npci = 24; return true;
+    case 2304: first = 120; step = 88; npci = 24; return true;
+    case 3750: first = 120; step = 160; npci = 22; return true;
+    case 24000: first = 120; step = 992; npci = 24; return true;
+    case 30000: first = 120; step = 1240; npci = 24; return true;
+    default: return false;
+    }
+}
+
+// bit i of the frame after the per-byte order swap (frame.c:694-697); packed = the REC_FRAME bytes, MSB first
+__device__ __forceinline__ unsigned swapped_bit(const uint8_t *packed, unsigned nbits, unsigned i)
+{
+    const unsigned base = i & ~7u, span = min(8u, nbits - base), src = base + span - 1 - (i & 7u);
+    return (packed[src >> 3] >> (7 - (src & 7u))) & 1u;
+}
+
+// One L1 PDU through L2, by the whole CTA.  frame_off: what the REC_L2 record names as its frame (the engine passes
+// the log offset of the frame's packed bits).
+__device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbits, unsigned lc, unsigned frame_off,
+                                const L2Sink &sink)
+{
+    __shared__ __align__(16) uint8_t pdu[(L2_PDU_MAX + 15) & ~15];
+    __shared__ PkEntry pk[L2_PK_MAX];
+    __shared__ uint8_t rs_scratch[256];
+    __shared__ unsigned sh_pci, sh_npk, sh_flags, sh_evlen;
+    __shared__ uint8_t *sh_out;
+    const unsigned t = threadIdx.x, nt = blockDim.x;
+    unsigned first, step, npci;
+    if (!l2_geometry(nbits, first, step, npci)) return;
+    const unsigned nout = (nbits - npci) / 8;
+    if (t == 0) sh_pci = 0;
+    __syncthreads();
+    if (t < npci) atomicOr(&sh_pci, swapped_bit(packed, nbits, first + step * t) << (23 - t));
+    // PDU byte n = frame bits (after the swap) 8n .. 8n+7, counted without the PCI bits
+    for (unsigned n = t; n < nout; n += nt) {
+        const unsigned o0 = 8 * n, o7 = o0 + 7;
+        const unsigned i0 = o0 + (o0 < first ? 0u : min(npci, (o0 - first) / (step - 1) + 1));
+        const unsigned i7 = o7 + (o7 < first ? 0u : min(npci, (o7 - first) / (step - 1) + 1));
+        unsigned v;
+        if (i7 - i0 == 7 && i7 + 8 < (nbits & ~7u)) {                 // no PCI bit inside, whole source bytes
+            const unsigned b = i0 >> 3, sft = i0 & 7u;
+            const unsigned two = ((__brev((unsigned)packed[b]) >> 24) << 8) | (__brev((unsigned)packed[b + 1]) >> 24);
+            v = (two >> (8 - sft)) & 0xFFu;
+        } else {
+            v = 0;
+            for (unsigned o = o0; o <= o7; o++) {
+                const unsigned i = o + (o < first ? 0u : min(npci, (o - first) / (step - 1) + 1));
+                v = (v << 1) | swapped_bit(packed, nbits, i);
+            }
+        }
+        pdu[n] = (uint8_t)v;
+    }
+    __syncthreads();
+    if (t == 0) {
+        EvWriter w = { z.ev, 0u, 0u };
+        unsigned npk = 0, flags = 0;
+        l2_walk(z, w, pdu, nout, lc, sh_pci, pk, npk, flags, rs_scratch);
+        if (w.overflow) flags |= L2F_EV_OVERFLOW;
+        sh_npk = npk;
+        sh_flags = flags;
+        sh_evlen = w.len;
+        z.frames++;
+    }
+    __syncthreads();
+    for (unsigned j = t; j < sh_npk; j += nt) {                       // CRC-8 over payload + check byte: 0 when intact
+        unsigned c = 0xFF;
+        const uint8_t *q = pdu + pk[j].start;
+        for (unsigned i = 0; i <= pk[j].cnt; i++) c = crc8_step(c, q[i]);
+        *reinterpret_cast<uint32_t *>(z.ev + pk[j].ev) = c ? 1u : 0u;
+    }
+    __syncthreads();
+    const unsigned evlen = sh_evlen, body = 32 + evlen + ((nout + 3) & ~3u);
+    if (t == 0) {
+        uint8_t *out = nullptr;
+        const unsigned need = 8 + body;
+        if ((size_t)*sink.len + need > sink.cap) *sink.overflow = 1;
+        else {
+            out = sink.base + *sink.len;
+            uint32_t *h = reinterpret_cast<uint32_t *>(out);
+            h[0] = REC_L2; h[1] = body;
+            h[2] = frame_off; h[3] = lc; h[4] = nbits; h[5] = sh_pci; h[6] = sh_flags; h[7] = nout; h[8] = evlen;
+            h[9] = z.frames - 1;
+            *sink.len += need;
+        }
+        sh_out = out;
+    }
+    __syncthreads();
+    uint8_t *out = sh_out;
+    if (!out) return;
+    out += 40;
+    for (unsigned i = t; i < evlen / 4; i += nt)
+        reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(z.ev)[i];
+    out += evlen;
+    for (unsigned i = t; i < (nout + 3) / 4; i += nt) {
+        const unsigned b = 4 * i;
+        uint32_t v = pdu[b];
+        if (b + 1 < nout) v |= (uint32_t)pdu[b + 1] << 8;
+        if (b + 2 < nout) v |= (uint32_t)pdu[b + 2] << 16;
+        if (b + 3 < nout) v |= (uint32_t)pdu[b + 3] << 24;
+        reinterpret_cast<uint32_t *>(out)[i] = v;
+    }
+    __syncthreads();
+}
+
+}  // namespace nbl2

@@ -4,6 +4,12 @@
  * reference's: input_push_cu8() pushes the samples to the GPU, runs what they complete, and replays the
  * engine's records - in the reference's call order - into frame_push() / pids_frame_push() /
  * nrsc5_report_*() / output_advance() on the calling thread before it returns.
+ *
+ * FM: L2 framing runs on the GPU as well (nrsc5b_enable_l2, csrc/l2.cuh).  The engine's REC_L2 record of a frame
+ * holds what the reference's frame_process() (src/frame.c:516-643) would have called, in order; replay() makes
+ * those calls - nrsc5_report_audio_service / output_align / output_aas_push / output_push - instead of
+ * frame_push(), so the host does no L2 parsing.  NRSC5_B200_HOST_L2=1 keeps the reference's own frame.c on the
+ * path (A/B checks); AM frames always take it.
  */
 #include "config.h"
 
@@ -48,6 +54,80 @@ static void unpack_bits(const uint8_t *packed, size_t nbits, uint8_t *bits)
 {
     for (size_t i = 0; i < nbits; i++)
         bits[i] = (packed[i >> 3] >> (7 - (i & 7))) & 1;
+}
+
+/* the L2 -> L3 calls the device made of one frame (REC_L2 payload, include/nrsc5_b200.h), in call order */
+static void replay_l2(input_t *st, const uint8_t *pay)
+{
+    uint32_t h[8];
+    memcpy(h, pay, sizeof(h));
+    const uint32_t flags = h[4], ev_len = h[6];
+    const uint8_t *ev = pay + 32, *pdu = pay + 32 + ev_len;
+    uint32_t off = 0;
+    while (off + 8 <= ev_len)
+    {
+        uint32_t type, plen, v[8];
+        memcpy(&type, ev + off, 4);
+        memcpy(&plen, ev + off + 4, 4);
+        const uint8_t *p = ev + off + 8;
+        off += 8 + ((plen + 3) & ~3u);
+        switch (type)
+        {
+        case 16:                                     /* frame.c:590 */
+            memcpy(v, p, 32);
+            nrsc5_report_audio_service(st->radio, v[0], v[1], v[2], v[3], v[4], (int)v[5], v[6], v[7]);
+            break;
+        case 17:                                     /* frame.c:606 */
+            memcpy(v, p, 12);
+            output_align(st->output, v[0], v[1], v[2]);
+            break;
+        case 18:                                     /* frame.c:365 */
+            output_aas_push(st->output, (uint8_t *)p, plen);
+            break;
+        case 19:                                     /* frame.c:619-635 */
+        {
+            packet_ref_t ref;
+            memcpy(v, p, 28);
+            ref.program = v[0];
+            ref.stream_id = v[1];
+            ref.seq = v[2];
+            ref.shape = v[3];
+            ref.flags = v[4];
+            ref.size = v[5];
+            ref.data = (uint8_t *)pdu + v[6];
+            output_push(st->output, &ref);
+            break;
+        }
+        default:
+            break;
+        }
+    }
+    if (flags & 1)                                   /* frame.c:535-540: the first audio header of a P1 frame failed */
+    {
+        st->in_frame_push = 1;
+        input_set_sync_state(st, SYNC_STATE_NONE);
+        st->in_frame_push = 0;
+    }
+}
+
+/* the REC_L2 record whose frame_off names the frame bits at `bits_off` of this drain */
+static const uint8_t *find_l2(const uint8_t *rec, size_t n, size_t from, uint32_t bits_off)
+{
+    size_t off = from;
+    while (off + 8 <= n)
+    {
+        uint32_t type, plen, frame_off;
+        memcpy(&type, rec + off, 4);
+        memcpy(&plen, rec + off + 4, 4);
+        if (type == NRSC5B_REC_L2)
+        {
+            memcpy(&frame_off, rec + off + 8, 4);
+            if (frame_off == bits_off)
+                return rec + off + 8;
+        }
+        off += 8 + ((plen + 3) & ~3u);
+    }
+    return NULL;
 }
 
 static void replay(input_t *st, const uint8_t *rec, size_t n)
@@ -109,6 +189,14 @@ static void replay(input_t *st, const uint8_t *rec, size_t n)
             uint32_t lc, nbits;
             memcpy(&lc, pay, 4);
             memcpy(&nbits, pay + 4, 4);
+            if (st->device_l2)
+            {
+                /* L2 ran on the GPU at the end of the frame's pass: make its calls here, where frame_push() stood */
+                const uint8_t *l2 = find_l2(rec, n, off, (uint32_t)(pay + 8 - rec));
+                if (!l2) fail("REC_L2 of a frame", -1);
+                replay_l2(st, l2);
+                break;
+            }
             unpack_bits(pay + 8, nbits, st->bits);
             st->in_frame_push = 1;
             frame_push(&st->frame, st->bits, nbits, (logical_channel_t)lc);
@@ -145,6 +233,13 @@ static void engine_open(input_t *st, int cs16)
     if (rc) fail("nrsc5b_create", rc);
     st->engine_cs16 = cs16;
     st->engine_am = am;
+    const char *host_l2 = getenv("NRSC5_B200_HOST_L2");
+    st->device_l2 = !am && !(host_l2 && atoi(host_l2));
+    if (st->device_l2)
+    {
+        rc = nrsc5b_enable_l2(st->engine, 1);
+        if (rc) fail("nrsc5b_enable_l2", rc);
+    }
 }
 
 static void run_and_replay(input_t *st)

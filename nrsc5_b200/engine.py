@@ -16,6 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 REC_FRAME, REC_PIDS, REC_SYNC, REC_LOST_SYNC, REC_MER, REC_BER = 1, 2, 3, 4, 5, 6
 REC_SOFT_PM, REC_BLOCK = 8, 9
+REC_L2 = 20                                                   # L2 framing of one frame (include/nrsc5_b200.h)
+EV_SERVICE, EV_ALIGN, EV_AAS, EV_PACKET = 16, 17, 18, 19      # its events: the reference's L2 -> L3 calls
+L2F_LOST, L2F_EV_OVERFLOW = 1, 2
 
 
 class EngineError(RuntimeError):
@@ -78,6 +81,9 @@ def load_library():
     L.nrsc5b_drain_all.argtypes = [vp, vp, sz, vp]
     L.nrsc5b_set_sync_state.argtypes = [vp, ci, ci]
     L.nrsc5b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.nrsc5b_enable_l2.argtypes = [vp, ci]
+    L.nrsc5b_l2_frames.argtypes = [ci, ctypes.c_char_p, sz, vp, sz, ctypes.POINTER(sz)]
+    L.nrsc5b_l2_frames.restype = ctypes.c_long
     L.nrsc5b_halfband_fm.argtypes = [ci, vp, sz, vp]
     L.nrsc5b_viterbi_k7.argtypes = [ci, vp, vp, ci, ci]
     L.nrsc5b_viterbi_k7_ex.argtypes = [ci, vp, vp, ci, ci, ctypes.POINTER(ci)]
@@ -94,12 +100,59 @@ def _check(rc, what):
     return rc
 
 
-def parse_records(raw: bytes):
-    """Decode the engine's record stream into (type, dict) tuples."""
+def parse_l2(pay: bytes) -> dict:
+    """Payload of a REC_L2 record -> its header fields, the PDU bytes and the events in call order.  A packet
+    event's `data` is cut out of the PDU bytes, so that events compare directly with the oracle's L2 records."""
+    frame_off, lc, nbits, pci, flags, pdu_len, ev_len, ordinal = struct.unpack_from("<8I", pay, 0)
+    ev = pay[32:32 + ev_len]
+    pdu = bytes(pay[32 + ev_len:32 + ev_len + pdu_len])
+    events, off = [], 0
+    while off < len(ev):
+        ty, plen = struct.unpack_from("<II", ev, off)
+        p = ev[off + 8: off + 8 + plen]
+        off += 8 + ((plen + 3) & ~3)
+        if ty == EV_SERVICE:
+            k = ("program", "access", "type", "codec_mode", "blend_control", "gain", "common_delay", "latency")
+            r = dict(zip(k, struct.unpack("<8i", p[:32])))
+        elif ty == EV_ALIGN:
+            r = dict(zip(("program", "stream_id", "offset"), struct.unpack("<3I", p[:12])))
+        elif ty == EV_AAS:
+            r = {"data": bytes(p)}
+        elif ty == EV_PACKET:
+            prog, sid, seq, shape, fl, size, at = struct.unpack("<7I", p[:28])
+            r = {"program": prog, "stream_id": sid, "seq": seq, "shape": shape, "flags": fl, "size": size,
+                 "data": pdu[at:at + size]}
+        else:
+            raise EngineError(f"corrupt L2 event stream (type {ty})")
+        events.append((ty, r))
+    return {"frame_off": frame_off, "lc": lc, "nbits": nbits, "pci": pci, "flags": flags, "ordinal": ordinal,
+            "pdu": pdu, "events": events}
+
+
+def with_l2_in_call_order(raw: bytes):
+    """A drained record stream with every REC_L2 moved right behind the REC_FRAME it belongs to and expanded into
+    its events - the order in which the reference makes the calls (frame_push -> frame_process)."""
+    offs = []
+    records = parse_records(raw, offs)
+    l2_of = {r["frame_rec_off"]: r for ty, r in records if ty == REC_L2}
+    out = []
+    for (ty, r), at in zip(records, offs):
+        if ty == REC_L2:
+            continue
+        out.append((ty, r))
+        if ty == REC_FRAME and at in l2_of:
+            out.extend(l2_of[at]["events"])
+    return out
+
+
+def parse_records(raw: bytes, offsets: list = None):
+    """Decode the engine's record stream into (type, dict) tuples (offsets: gets each record's byte offset)."""
     out = []
     off, n = 0, len(raw)
     while off < n:
         ty, plen = struct.unpack_from("<II", raw, off)
+        if offsets is not None:
+            offsets.append(off)
         pay = raw[off + 8: off + 8 + plen]
         off += 8 + ((plen + 3) & ~3)
         if ty == REC_FRAME:
@@ -123,6 +176,9 @@ def parse_records(raw: bytes):
         elif ty == REC_BLOCK:
             st, se, ang, pr, pi, cfo, start = struct.unpack("<iifffiq", pay[:32])
             rec = {"state": st, "samperr": se, "angle": ang, "phase": complex(pr, pi), "cfo": cfo, "start": start}
+        elif ty == REC_L2:
+            rec = parse_l2(pay)
+            rec["frame_rec_off"] = rec["frame_off"] - 16      # where that frame's record starts in this drain
         elif ty in (10, 11):
             rec = {"dbg": struct.unpack("<%di" % (plen // 4), pay)}
         else:
@@ -265,6 +321,10 @@ class Engine:
     def drain_all(self):
         return [parse_records(r.tobytes()) for r in self.drain_all_raw()]
 
+    def enable_l2(self, on: bool = True):
+        """L2 framing on the device: every frame's REC_FRAME is followed (at the end of its pass) by a REC_L2."""
+        _check(self._L.nrsc5b_enable_l2(self._h, int(on)), "nrsc5b_enable_l2")
+
     def set_sync_state(self, stream: int, state: int):
         _check(self._L.nrsc5b_set_sync_state(self._h, stream, state), "nrsc5b_set_sync_state")
 
@@ -294,6 +354,23 @@ def viterbi_k7(soft: np.ndarray, length: int, device: int = 0, want_fallbacks: b
            "nrsc5b_viterbi_k7_ex")
     out = out.reshape(nframes, length)
     return (out, fb.value) if want_fallbacks else out
+
+
+def l2_frames(frames, device: int = 0, cap: int = 64 << 20):
+    """L2 alone: frames = [(lc, nbits, packed bits) | None (= frame_reset)] -> the REC_L2 records, one per frame."""
+    blob = bytearray()
+    for f in frames:
+        if f is None:
+            blob += struct.pack("<II", 0, 0)
+        else:
+            lc, nbits, bits = f
+            nb = (nbits + 7) // 8
+            blob += struct.pack("<II", lc, nbits) + bytes(bits[:nb]) + bytes((-nb) % 4)
+    out = ctypes.create_string_buffer(cap)
+    need = ctypes.c_size_t(0)
+    n = load_library().nrsc5b_l2_frames(device, bytes(blob), len(blob), out, cap, ctypes.byref(need))
+    _check(n, "nrsc5b_l2_frames")
+    return [r for t, r in parse_records(out.raw[:n]) if t == REC_L2]
 
 
 def rs_decode(blocks: np.ndarray, device: int = 0):

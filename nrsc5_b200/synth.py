@@ -380,7 +380,7 @@ def make_fm_mp3(**kw) -> FmCapture:
 def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz: float = 0.0,
             noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
             tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
-            start_bc: int = 0, pids_crc: bool = False) -> FmCapture:
+            start_bc: int = 0, pids_crc: bool = False, p1_frames=None) -> FmCapture:
     """FM capture (PSMI 1, 2, 3, 5, 6 or 11) holding `nframes` complete L1 frames
     followed by `tail_blocks` further blocks so the last frame flushes
     (the reference has no flush call).
@@ -402,7 +402,10 @@ def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 10
     nfr_total = (nblocks + start_bc + BLOCKS_PER_FRAME - 1) // BLOCKS_PER_FRAME
     mats = []
     for f in range(nfr_total):
-        bits = build_p1_frame_bits(rng, pci=pci, valid_header=valid_header)
+        if p1_frames is not None and f < len(p1_frames) and p1_frames[f] is not None:   # caller's P1 PDUs (packed, synth_l2.py)
+            bits = np.unpackbits(np.frombuffer(p1_frames[f], dtype=np.uint8))[:P1_BITS]
+        else:
+            bits = build_p1_frame_bits(rng, pci=pci, valid_header=valid_header)
         coded = conv_encode_tb(bits ^ pn_p1).reshape(-1)          # 438528
         keep = np.ones(coded.size, dtype=bool)
         keep[5::6] = False

@@ -31,9 +31,14 @@ def test_dropin_exports_the_public_api():
 
 
 @pytest.mark.gpu
-def test_dropin_events_match_reference_on_sample_xz():
+@pytest.mark.parametrize("host_l2", [0, 1])
+def test_dropin_events_match_reference_on_sample_xz(host_l2=0, monkeypatch=None):
+    """host_l2 = 0: L2 framing on the GPU (REC_L2 replayed by the seam, the default); 1: the reference's own frame.c
+    on the host (NRSC5_B200_HOST_L2=1).  Both must deliver the reference's events."""
     if not os.path.exists(DROPIN):
         pytest.skip("drop-in not built")
+    if monkeypatch is not None:
+        monkeypatch.setenv("NRSC5_B200_HOST_L2", str(host_l2))
     raw = common.load_sample()
     if raw is None:
         pytest.skip("sample.xz not available on this box")

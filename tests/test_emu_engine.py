@@ -40,6 +40,7 @@ def emulated_engine():
 import test_gpu_am as _am            # noqa: E402
 import test_gpu_chain as _chain      # noqa: E402
 import test_gpu_edge as _edge        # noqa: E402
+import test_gpu_l2 as _l2            # noqa: E402
 import test_gpu_modes as _modes      # noqa: E402
 import test_gpu_stages as _stages    # noqa: E402
 
@@ -62,6 +63,11 @@ test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_
 test_cs16_input_equals_cu8_input = _chain.test_cs16_input_equals_cu8_input
 test_multi_stream_independent = _chain.test_multi_stream_independent
 test_pids_crc_verdicts_on_valid_frames = _chain.test_pids_crc_verdicts_on_valid_frames
+# L2 framing on the device
+test_l2_frames_equal_oracle = _l2.test_l2_frames_equal_oracle
+test_l2_frames_of_sample_xz = _l2.test_l2_frames_of_sample_xz
+test_chain_with_l2_on_device = _l2.test_chain_with_l2_on_device
+test_mp3_chain_l2_records_follow_their_frames = _l2.test_mp3_chain_l2_records_follow_their_frames
 # awkward inputs
 test_dropout_and_reacquisition = _edge.test_dropout_and_reacquisition
 test_stream_starting_mid_frame_mp3 = _edge.test_stream_starting_mid_frame_mp3
@@ -79,7 +85,8 @@ def test_reverse_thread_order_gives_the_same_results():
     on the GPU; a subset of the parity tests must pass unchanged.  (The order is fixed per process, hence the
     subprocess.)"""
     env = dict(os.environ, EMU_ORDER="reverse")
-    sel = "mp1_cfo-300_awgn12 or mp11 or ma3_noisy or viterbi_fast_path or (am_cu8_input_bit_exact and 2)"
+    sel = ("mp1_cfo-300_awgn12 or mp11 or ma3_noisy or viterbi_fast_path or (am_cu8_input_bit_exact and 2) or "
+           "(l2_frames_equal_oracle and p1_fm_fixed_b) or chain_with_l2")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -105,9 +112,10 @@ def emulated_dropin(emulated_engine):
     test_dropin.DROPIN = saved
 
 
-def test_dropin_events_match_reference_on_sample_xz(emulated_dropin):
+@pytest.mark.parametrize("host_l2", [0, 1])
+def test_dropin_events_match_reference_on_sample_xz(emulated_dropin, host_l2, monkeypatch):
     import test_dropin
-    test_dropin.test_dropin_events_match_reference_on_sample_xz()
+    test_dropin.test_dropin_events_match_reference_on_sample_xz(host_l2, monkeypatch)
 
 
 @pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cu8")])
