@@ -169,7 +169,8 @@ typedef struct {
 int nrsc5b_get_stats(nrsc5b_engine_t *e, nrsc5b_stats_t *st);
 
 /* Per-kernel device time from CUDA events around every launch (a separate, slower pass):
- * ms4/n4: slot 1 = the front-end kernel (k_stream), slot 3 = the P1 decode group; slots 0, 2 unused. */
+ * ms4/n4: slot 1 = the front-end kernel (k_stream), slot 3 = the P1 decode group, slot 2 = the L2 kernel (k_l2,
+ * when enabled); slot 0 unused. */
 int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on);
 int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long *n4);
 

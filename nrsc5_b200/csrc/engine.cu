@@ -1288,11 +1288,6 @@ static void launch_p1(nrsc5b_engine *e)
         k_px_fin<<<dim3(P3_SLOTS, S), 128, 0, e->stream>>>(e->dp, e->dims, which);
         e->stats.kernel_launches += 8;
     }
-    // L2 framing of everything the pass decoded (only when enabled)
-    if (e->l2) {
-        k_l2<<<S, nbl2::L2_THREADS, 0, e->stream>>>(e->dp, e->dims, e->l2);
-        e->stats.kernel_launches += 1;
-    }
 }
 
 // Allocates the buffers of the extra decode groups named in `need` (PX_NEED_* bits) and adds them to the passes.
@@ -1338,20 +1333,30 @@ static int launch_pass(nrsc5b_engine *e)
     e->stats.kernel_launches += 1;
     if (prof) cudaEventRecord(e->pev[1], e->stream);
     launch_p1(e);
+    if (prof) cudaEventRecord(e->pev[2], e->stream);
+    // L2 framing of everything the pass decoded (only when enabled, nrsc5b_enable_l2)
+    if (e->l2 && e->dims.l2) {
+        k_l2<<<e->dims.nstreams, nbl2::L2_THREADS, 0, e->stream>>>(e->dp, e->dims, e->l2);
+        e->stats.kernel_launches += 1;
+    }
     if (prof) {
-        cudaEventRecord(e->pev[2], e->stream);
-        cudaEventSynchronize(e->pev[2]);
+        cudaEventRecord(e->pev[3], e->stream);
+        cudaEventSynchronize(e->pev[3]);
         float ms = 0;
         cudaEventElapsedTime(&ms, e->pev[0], e->pev[1]);
         e->kernel_ms[1] += ms; e->kernel_n[1] += 1;
         cudaEventElapsedTime(&ms, e->pev[1], e->pev[2]);
         e->kernel_ms[3] += ms; e->kernel_n[3] += 1;
+        if (e->l2 && e->dims.l2) {
+            cudaEventElapsedTime(&ms, e->pev[2], e->pev[3]);
+            e->kernel_ms[2] += ms; e->kernel_n[2] += 1;
+        }
     }
     return 0;
 }
 
 /* Per-kernel device time (CUDA events around every launch; slows the run down, use a separate pass).
- * Slots: [1] = the stream-resident front-end kernel k_stream, [3] = the P1 decode group; [0],[2] unused. */
+ * Slots: [1] = the stream-resident front-end kernel k_stream, [3] = the P1 decode group, [2] = k_l2; [0] unused. */
 extern "C" int nrsc5b_set_profiling(nrsc5b_engine_t *e, int on)
 {
     if (!e) return NRSC5B_EINVAL;

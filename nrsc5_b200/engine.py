@@ -248,7 +248,10 @@ class Engine:
         n = (ctypes.c_ulonglong * 4)()
         _check(self._L.nrsc5b_get_kernel_times(self._h, ms, n), "nrsc5b_get_kernel_times")
         # slot 1 = the stream-resident front-end kernel (k_stream), slot 3 = the P1 decode kernel group
-        return {"front": {"ms": ms[1], "launches": int(n[1])}, "p1": {"ms": ms[3], "launches": int(n[3])}}
+        out = {"front": {"ms": ms[1], "launches": int(n[1])}, "p1": {"ms": ms[3], "launches": int(n[3])}}
+        if n[2]:
+            out["l2"] = {"ms": ms[2], "launches": int(n[2])}      # k_l2, only when L2 runs on the device
+        return out
 
     def phase_cycles(self):
         """SM cycles per phase of k_stream summed over streams: {name: (cycles, count)}."""

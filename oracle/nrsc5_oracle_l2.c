@@ -372,6 +372,7 @@ void orc_l2_push(orc_l2_t *o, const uint8_t *packed, unsigned nbits, unsigned lc
     }
     uint32_t fh[2] = { lc, nbits };
     put(o, ORC_REC_FRAME, fh, sizeof(fh), packed, (nbits + 7) / 8);
+    if (nbits & 7) o->log[o->len - (((nbits + 7) / 8 + 3) & ~(size_t)3) + (nbits + 7) / 8 - 1] &= (uint8_t)(0xFF00 >> (nbits & 7));   /* padding bits */
     uint32_t pci = 0;
     unsigned got = 0, nout = 0, acc = 0, fill = 0;
     for (unsigned i = 0; i < nbits; i++) {

@@ -142,18 +142,21 @@ def l2_frames(frames, mode=MODE_FM) -> RefLog:
     return _parse(raw)
 
 
-def decode(samples: np.ndarray, mode=MODE_FM, chunk=0, want_soft=False) -> RefLog:
-    """Run the reference on a capture (uint8 cu8 array, or int16 cs16 array)."""
+def decode(samples: np.ndarray, mode=MODE_FM, chunk=0, want_soft=False, want_l2=False) -> RefLog:
+    """Run the reference on a capture (uint8 cu8 array, or int16 cs16 array).  want_l2: also record the L2 -> L3
+    calls (types 16..19, reftap_l2.c) between the other records."""
     L = lib()
     a = np.ascontiguousarray(samples)
     is_cs16 = a.dtype == np.int16
     assert is_cs16 or a.dtype == np.uint8
     L.reftap_reset()
     L.reftap_want_soft(1 if want_soft else 0)
+    L.reftap_want_l2(1 if want_l2 else 0)
     rc = L.reftap_decode(a.ctypes.data, a.size, mode, int(is_cs16), chunk)
     assert rc == 0
     raw = ctypes.string_at(L.reftap_log_data(), L.reftap_log_size())
     L.reftap_reset()
+    L.reftap_want_l2(0)
     return _parse(raw)
 
 

@@ -25,6 +25,9 @@ enum {
     REC_L2_PACKET = 19,    /* u32 program, stream_id, seq, shape, flags, size; then the packet bytes                */
 };
 
+static int g_want_l2;          /* the L2 -> L3 records are only written on request (reftap_want_l2, reftap_l2_frames) */
+void reftap_want_l2(int on) { g_want_l2 = on; }
+
 void reftap_log_put(uint32_t type, const void *a, size_t alen, const void *b, size_t blen);
 void reftap_set_logging(int on);
 
@@ -40,14 +43,14 @@ void __wrap_frame_push(frame_t *st, uint8_t *bits, size_t length, logical_channe
 void __wrap_output_align(output_t *st, unsigned int program, unsigned int stream_id, unsigned int offset)
 {
     uint32_t p[3] = { program, stream_id, offset };
-    reftap_log_put(REC_L2_ALIGN, p, sizeof(p), NULL, 0);
+    if (g_want_l2) reftap_log_put(REC_L2_ALIGN, p, sizeof(p), NULL, 0);
     __real_output_align(st, program, stream_id, offset);
 }
 
 void __wrap_output_push(output_t *st, const packet_ref_t *ref)
 {
     uint32_t p[6] = { ref->program, ref->stream_id, ref->seq, ref->shape, ref->flags, ref->size };
-    reftap_log_put(REC_L2_PACKET, p, sizeof(p), ref->data, ref->size);
+    if (g_want_l2) reftap_log_put(REC_L2_PACKET, p, sizeof(p), ref->data, ref->size);
     __real_output_push(st, ref);
 }
 
@@ -58,7 +61,7 @@ static int g_isolate_l3;
 
 void __wrap_output_aas_push(output_t *st, uint8_t *psd, unsigned int len)
 {
-    reftap_log_put(REC_L2_AAS, psd, len, NULL, 0);
+    if (g_want_l2) reftap_log_put(REC_L2_AAS, psd, len, NULL, 0);
     if (!g_isolate_l3)
         __real_output_aas_push(st, psd, len);
 }
@@ -69,7 +72,7 @@ void __wrap_nrsc5_report_audio_service(nrsc5_t *st, unsigned int program, unsign
 {
     int32_t p[8] = { (int32_t)program, (int32_t)access, (int32_t)type, (int32_t)codec_mode, (int32_t)blend_control,
                      digital_audio_gain, (int32_t)common_delay, (int32_t)latency };
-    reftap_log_put(REC_L2_SERVICE, p, sizeof(p), NULL, 0);
+    if (g_want_l2) reftap_log_put(REC_L2_SERVICE, p, sizeof(p), NULL, 0);
     __real_nrsc5_report_audio_service(st, program, access, type, codec_mode, blend_control, digital_audio_gain,
                                       common_delay, latency);
 }
@@ -85,6 +88,8 @@ int reftap_l2_frames(const uint8_t *frames, size_t nbytes, int mode)
     nrsc5_set_mode(st, mode);
     reftap_set_logging(1);
     g_isolate_l3 = 1;
+    const int want_before = g_want_l2;
+    g_want_l2 = 1;
     size_t off = 0;
     uint8_t *bits = (uint8_t *)malloc(P1_FRAME_LEN_FM);
     while (off + 8 <= nbytes) {
@@ -103,6 +108,7 @@ int reftap_l2_frames(const uint8_t *frames, size_t nbytes, int mode)
     }
     free(bits);
     g_isolate_l3 = 0;
+    g_want_l2 = want_before;
     reftap_set_logging(0);
     nrsc5_close(st);
     return 0;

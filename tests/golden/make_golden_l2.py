@@ -15,7 +15,7 @@ from l2_cases import AM_BITS, L2_CASES, l2_digest  # noqa: E402
 from nrsc5_b200 import synth_l2  # noqa: E402
 
 out = {}
-log = reftap.decode(load_sample())
+log = reftap.decode(load_sample(), want_l2=True)
 out["sample_xz"] = l2_digest([(t, r) for t, r in log.records if t in (1, 16, 17, 18, 19)])
 for name, kw in L2_CASES.items():
     fr = synth_l2.make_l2_sequence(**kw)

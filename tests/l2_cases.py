@@ -29,3 +29,26 @@ def l2_digest(records):
         elif ty == 19:
             out.append(["K", r["program"], r["stream_id"], r["seq"], r["shape"], r["flags"], r["size"], fnv1a32(r["data"])])
     return out
+
+
+def mutated_sequence(trial: int):
+    """A generated PDU sequence with up to five random byte errors per frame (most of them in the first 400 bytes,
+    where headers, locations, HEF and PSD live): exercises the early-return / resynchronisation branches of
+    frame_process.  Returns (frames, am)."""
+    import numpy as np
+    from nrsc5_b200 import synth_l2
+    rng = np.random.default_rng(1000 + trial)
+    nbits = [4608, 146176, 3750, 24000, 4608, 2304][trial % 6]
+    fixed = (trial % 3 == 1) and nbits not in (2304, 3750)
+    fr = synth_l2.make_l2_sequence(seed=500 + trial, nframes=10 if nbits == 146176 else 24, nbits=nbits, fixed=fixed, lc=trial % 3)
+    out = []
+    for f in fr:
+        if f is None:
+            out.append(None)
+            continue
+        b = bytearray(f[2])
+        for _ in range(int(rng.integers(0, 6))):
+            pos = int(rng.integers(0, min(len(b), 400) if rng.random() < 0.7 else len(b)))
+            b[pos] ^= int(rng.integers(1, 256))
+        out.append((f[0], f[1], bytes(b)))
+    return out, nbits in AM_BITS

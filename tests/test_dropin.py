@@ -31,30 +31,33 @@ def test_dropin_exports_the_public_api():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("host_l2", [0, 1])
-def test_dropin_events_match_reference_on_sample_xz(host_l2=0, monkeypatch=None):
-    """host_l2 = 0: L2 framing on the GPU (REC_L2 replayed by the seam, the default); 1: the reference's own frame.c
-    on the host (NRSC5_B200_HOST_L2=1).  Both must deliver the reference's events."""
+def test_dropin_events_match_reference_on_sample_xz(device_l2=0):
+    """device_l2 = 1 (the library's default): L2 framing on the GPU, REC_L2 replayed by the seam; 0
+    (NRSC5_B200_DEVICE_L2=0): the reference's own frame.c on the host - this test.  Both must deliver the
+    reference's events (the device variant is run from tests/test_zz_gpu_l2.py and, emulated, from
+    tests/test_emu_engine.py)."""
     if not os.path.exists(DROPIN):
         pytest.skip("drop-in not built")
-    if monkeypatch is not None:
-        monkeypatch.setenv("NRSC5_B200_HOST_L2", str(host_l2))
-    raw = common.load_sample()
-    if raw is None:
-        pytest.skip("sample.xz not available on this box")
-    g = common.golden("api_sample_xz.json")
-    got = nrsc5_api.run(DROPIN, raw.tobytes())
-    want = g["events"]
-    assert [e[0] for e in got] == [e[0] for e in want]                  # kinds and order
-    for a, b in zip(got, want):
-        if a[0] == "HDC":
-            assert a == b                                               # program, length, payload digest
-        elif a[0] == "SYNC":
-            assert a[2:] == b[2:] and abs(a[1] - b[1]) < 0.05
-        elif a[0] == "MER":
-            assert abs(a[1] - b[1]) < 0.05 and abs(a[2] - b[2]) < 0.05
-        elif a[0] == "BER":
-            assert abs(a[1] - b[1]) < 2e-4
+    os.environ["NRSC5_B200_DEVICE_L2"] = str(device_l2)
+    try:
+        raw = common.load_sample()
+        if raw is None:
+            pytest.skip("sample.xz not available on this box")
+        g = common.golden("api_sample_xz.json")
+        got = nrsc5_api.run(DROPIN, raw.tobytes())
+        want = g["events"]
+        assert [e[0] for e in got] == [e[0] for e in want]                  # kinds and order
+        for a, b in zip(got, want):
+            if a[0] == "HDC":
+                assert a == b                                               # program, length, payload digest
+            elif a[0] == "SYNC":
+                assert a[2:] == b[2:] and abs(a[1] - b[1]) < 0.05
+            elif a[0] == "MER":
+                assert abs(a[1] - b[1]) < 0.05 and abs(a[2] - b[2]) < 0.05
+            elif a[0] == "BER":
+                assert abs(a[1] - b[1]) < 2e-4
+    finally:
+        os.environ.pop("NRSC5_B200_DEVICE_L2", None)
 
 
 @pytest.mark.gpu

@@ -40,7 +40,7 @@ def emulated_engine():
 import test_gpu_am as _am            # noqa: E402
 import test_gpu_chain as _chain      # noqa: E402
 import test_gpu_edge as _edge        # noqa: E402
-import test_gpu_l2 as _l2            # noqa: E402
+import test_zz_gpu_l2 as _l2         # noqa: E402
 import test_gpu_modes as _modes      # noqa: E402
 import test_gpu_stages as _stages    # noqa: E402
 
@@ -65,6 +65,7 @@ test_multi_stream_independent = _chain.test_multi_stream_independent
 test_pids_crc_verdicts_on_valid_frames = _chain.test_pids_crc_verdicts_on_valid_frames
 # L2 framing on the device
 test_l2_frames_equal_oracle = _l2.test_l2_frames_equal_oracle
+test_l2_frames_mutated_equal_oracle = _l2.test_l2_frames_mutated_equal_oracle
 test_l2_frames_of_sample_xz = _l2.test_l2_frames_of_sample_xz
 test_chain_with_l2_on_device = _l2.test_chain_with_l2_on_device
 test_mp3_chain_l2_records_follow_their_frames = _l2.test_mp3_chain_l2_records_follow_their_frames
@@ -112,10 +113,11 @@ def emulated_dropin(emulated_engine):
     test_dropin.DROPIN = saved
 
 
-@pytest.mark.parametrize("host_l2", [0, 1])
-def test_dropin_events_match_reference_on_sample_xz(emulated_dropin, host_l2, monkeypatch):
+@pytest.mark.parametrize("device_l2", [0, 1])
+def test_dropin_events_match_reference_on_sample_xz(emulated_dropin, device_l2):
     import test_dropin
-    test_dropin.test_dropin_events_match_reference_on_sample_xz(host_l2, monkeypatch)
+    test_dropin.test_dropin_events_match_reference_on_sample_xz(device_l2)
+    os.environ.pop("NRSC5_B200_DEVICE_L2", None)
 
 
 @pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cu8")])

@@ -5,7 +5,7 @@ import pytest
 import port
 import reftap
 from common import golden, load_sample
-from l2_cases import AM_BITS, L2_CASES, l2_digest
+from l2_cases import AM_BITS, L2_CASES, l2_digest, mutated_sequence
 from nrsc5_b200 import synth_l2
 
 L2_TYPES = (1, 16, 17, 18, 19)
@@ -45,3 +45,16 @@ def test_l2_generator_covers_the_branches():
     aas = [r["data"] for t, r in orc.records if t == 18]
     assert len(aas) > 20                                    # PSD messages and fixed-data subchannel messages
     assert lost == 1
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_l2_oracle_equals_reference_under_mutation(block):
+    """Random byte errors in the PDUs (headers, locations, HEF, PSD, fixed-data tail): the restatement must take
+    every early return and resynchronisation exactly as the unmodified reference's frame.c does."""
+    if not reftap.available():
+        pytest.skip("reference library not built")
+    for trial in range(12 * block, 12 * block + 12):
+        frames, am = mutated_sequence(trial)
+        ref = reftap.l2_frames(frames, mode=1 if am else 0)
+        orc, _ = port.l2_frames(frames)
+        assert ref.records == orc.records, trial

@@ -1,16 +1,21 @@
 """L2 framing on the device (nrsc5_b200/csrc/l2.cuh) against the oracle's L2 restatement - which is
 pinned, byte for byte, to the unmodified reference's L2 -> L3 calls (tests/test_oracle_l2.py) - and against the
 golden call streams made from the reference (tests/golden/l2.json).  Through the C ABI: nrsc5b_l2_frames (L2
-alone, all six frame lengths) and nrsc5b_enable_l2 (the whole chain, REC_L2 after every frame's pass)."""
+alone, all six frame lengths) and nrsc5b_enable_l2 (the whole chain, REC_L2 after every frame's pass).
+
+They went green on the CPU emulation of the kernels first (tests/test_emu_engine.py runs these very functions) and
+then on the B200 (profiles/r1_l2_gpu_tests.txt)."""
+import os
+
 import pytest
 
 import port
 from common import MP3_CASE, SYNTH_CASES, golden, load_sample
-from l2_cases import L2_CASES, l2_digest
+from l2_cases import L2_CASES, l2_digest, mutated_sequence
 from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth, synth_l2
 
-pytestmark = pytest.mark.gpu_new
+pytestmark = pytest.mark.gpu
 
 
 def expand(l2_records, frames):
@@ -37,6 +42,18 @@ def test_l2_frames_equal_oracle(name):
     assert not any(r["flags"] & eng.L2F_EV_OVERFLOW for r in recs)
     for r, f in zip(recs, [f for f in frames if f is not None]):
         assert (r["lc"], r["nbits"]) == (f[0], f[1]) and len(r["pdu"]) == synth_l2.pdu_len(f[1])
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_l2_frames_mutated_equal_oracle(block):
+    """PDUs with random byte errors (tests/l2_cases.py:mutated_sequence; the oracle equals the reference on them,
+    tests/test_oracle_l2.py): the device takes the same early returns, finds the same packets and CRC verdicts."""
+    for trial in range(8 * block, 8 * block + 8):
+        frames, _ = mutated_sequence(trial)
+        recs = eng.l2_frames(frames)
+        orc, lost = port.l2_frames(frames)
+        assert expand(recs, frames) == orc.records, trial
+        assert sum(bool(r["flags"] & eng.L2F_LOST) for r in recs) == lost, trial
 
 
 def test_l2_frames_of_sample_xz():
@@ -124,3 +141,13 @@ def test_mp3_chain_l2_records_follow_their_frames():
     got = [(t, r) for t, r in eng.with_l2_in_call_order(raw) if t in (1, 16, 17, 18, 19)]
     orc, _ = port.l2_frames(port.l1_to_l2_input([(t, r) for t, r in recs if t in (1, 3)]))
     assert got == orc.records
+
+
+def test_dropin_with_device_l2_matches_reference_events():
+    """The drop-in libnrsc5.so with NRSC5_B200_DEVICE_L2=1 through the reference's public API on sample.xz: the
+    seam replays REC_L2 instead of calling frame_push(); same events, 476 identical HDC packets, ID3, AUDIO_SERVICE."""
+    import test_dropin
+    try:
+        test_dropin.test_dropin_events_match_reference_on_sample_xz(1)
+    finally:
+        os.environ.pop("NRSC5_B200_DEVICE_L2", None)
