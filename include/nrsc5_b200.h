@@ -184,7 +184,7 @@ int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12, unsig
 /* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops); 0 = default. */
 int nrsc5b_debug_set(int flags);
 
-/* L2 framing on the device for every frame an FM engine decodes from now on: after each REC_FRAME's pass
+/* L2 framing on the device for every frame the engine (FM or AM) decodes from now on: after each REC_FRAME's pass
  * the log also holds a REC_L2 record with what frame_push / frame_process (reference src/frame.c:516-714) would have
  * handed on: audio service changes, elastic-buffer alignment, PSD / AAS messages and the HDC packets with their CRC
  * verdicts.  The per-stream L2 state (service table, PSD and fixed-data assembly) lives on the GPU. */

@@ -87,6 +87,9 @@ AM_HD inline float2 cdiv(float2 a, float2 b)
     return make_float2(((a.y * ratio) + a.x) / denom, (a.y - (a.x * ratio)) / denom);
 }
 
+constexpr int AM_L2_QUEUE = 40;            // = nb::L2_QUEUE: a launch with L2 on takes at most 16 blocks (1 P1 + 1 P3 each)
+constexpr int AM_L2_BLOCKS = 16;
+
 // Per-stream scalars (reference src/acquire.h, src/sync.h, src/decode.h).
 struct AmState {
     long long in_avail;        // cs16 complex samples available from absolute index 0 (advanced by the host)
@@ -101,7 +104,20 @@ struct AmState {
     unsigned log_len, log_overflow;
     unsigned long long blocks_done;
     short bp_hist[31][2];      // the coarse band-pass filter's last 31 inputs
+    // L2 on the device (l2.cuh): the frames (log offset of their packed bits) and frame_resets (nbits == 0) this
+    // launch handed to the L2 kernel that follows it, in the reference's call order
+    int l2_on, l2_n;
+    unsigned l2_off[AM_L2_QUEUE], l2_lc[AM_L2_QUEUE], l2_nbits[AM_L2_QUEUE];
 };
+
+AM_HD inline void l2_enqueue(AmState &st, unsigned off, unsigned lc, unsigned nbits)
+{
+    if (!st.l2_on || st.l2_n >= AM_L2_QUEUE) return;
+    st.l2_off[st.l2_n] = off;
+    st.l2_lc[st.l2_n] = lc;
+    st.l2_nbits[st.l2_n] = nbits;
+    st.l2_n++;
+}
 
 // Per-stream arrays.
 struct AmWork {
@@ -164,6 +180,7 @@ AM_HD inline void emit_frame(AmState &st, const AmIo &io, Lanes L, const uint8_t
         memcpy(w, hdr, 8);
         for (unsigned i = 0; i < len; i++) w[8 + (i >> 3)] |= (uint8_t)((bits[i] & 1) << (7 - (i & 7)));
     }
+    l2_enqueue(st, w ? (unsigned)(w + 8 - io.log) : 0xffffffffu, lc, len);            // frame_push -> frame_process
 }
 
 AM_HD inline void set_state(AmState &st, const AmIo &io, Lanes L, int ns)       // input.c:172-188
@@ -559,6 +576,7 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
         if ((st.offset_history & 0xffff) == 0x5670) {
             st.bc = 0;
             set_state(st, io, L, ST_FINE);
+            l2_enqueue(st, 0, 0, 0);                                                     // frame_reset, sync.c:662-663
             st.am_errors = 0;                                                            // decode_reset, decode.c:556-565
             st.am_diversity_wait = 4;
             st.offset_history = 0;

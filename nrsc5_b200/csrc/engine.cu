@@ -481,6 +481,9 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
     StreamState &fs = p.st[s];
     nbam::AmState st = ast[s];
     st.log_len = fs.log_len;                               // the host rewinds the log when it drains it
+    st.l2_on = d.l2;
+    st.l2_n = 0;
+    static_assert(nbam::AM_L2_QUEUE <= L2_QUEUE, "the L2 kernel reads the queue from StreamState");
     const nbam::AmIo io = { reinterpret_cast<const int16_t *>(p.iq + (size_t)s * d.in_stride), p.log + (size_t)s * d.log_cap,
                             (unsigned)d.log_cap };
     int nb_done = 0;
@@ -498,6 +501,12 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
         fs.blocks_done = st.blocks_done;
         fs.start = st.start;
         fs.state = st.state;
+        fs.l2_n = st.l2_n;                                 // k_l2 follows this launch (launch_pass)
+        for (int i = 0; i < st.l2_n; i++) {
+            fs.l2_off[i] = st.l2_off[i];
+            fs.l2_lc[i] = st.l2_lc[i];
+            fs.l2_nbits[i] = st.l2_nbits[i];
+        }
         if (nb_done) atomicAdd(&g_progress, (unsigned long long)nb_done);
     }
 }
@@ -1323,8 +1332,13 @@ constexpr int BLOCKS_PER_PASS = 16;
 static int launch_pass(nrsc5b_engine *e)
 {
     if (e->am_st) {                                        // AM: one kernel does the whole chain, window after window
-        k_am<<<e->dims.nstreams, 32, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, 1 << 20);
+        const bool l2 = e->l2 && e->dims.l2;              // with L2 on, a launch stops after 16 blocks: its frames fit the queue
+        k_am<<<e->dims.nstreams, 32, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20);
         e->stats.kernel_launches += 1;
+        if (l2) {
+            k_l2<<<e->dims.nstreams, nbl2::L2_THREADS, 0, e->stream>>>(e->dp, e->dims, e->l2);
+            e->stats.kernel_launches += 1;
+        }
         return 0;
     }
     const bool prof = e->profiling != 0;
@@ -1690,11 +1704,10 @@ extern "C" int nrsc5b_rs_decode(int device, uint8_t *blocks, int *rcs, int n)
     return NRSC5B_OK;
 }
 
-/* L2 framing on the device for every frame the engine decodes from now on (FM engines). */
+/* L2 framing on the device for every frame the engine decodes from now on (FM and AM engines). */
 extern "C" int nrsc5b_enable_l2(nrsc5b_engine_t *e, int on)
 {
     if (!e) return NRSC5B_EINVAL;
-    if (e->am_st) return NRSC5B_EINVAL;                    // AM frames leave k_am as REC_FRAME only (nrsc5b_l2_frames takes them)
     CK(cudaStreamSynchronize(e->stream));
     if (on && !e->l2) {
         int rc = dev_alloc(e, &e->l2, (size_t)e->dims.nstreams, false);

@@ -5,11 +5,11 @@
  * engine's records - in the reference's call order - into frame_push() / pids_frame_push() /
  * nrsc5_report_*() / output_advance() on the calling thread before it returns.
  *
- * FM: L2 framing runs on the GPU as well (nrsc5b_enable_l2, csrc/l2.cuh).  The engine's REC_L2 record of a frame
+ * L2 framing runs on the GPU as well (nrsc5b_enable_l2, csrc/l2.cuh).  The engine's REC_L2 record of a frame
  * holds what the reference's frame_process() (src/frame.c:516-643) would have called, in order; replay() makes
  * those calls - nrsc5_report_audio_service / output_align / output_aas_push / output_push - instead of
  * frame_push(), so the host does no L2 parsing.  NRSC5_B200_DEVICE_L2=0 puts the reference's own frame.c back on
- * the path (A/B checks); AM frames always take it.
+ * the path (A/B checks).
  */
 #include "config.h"
 
@@ -234,7 +234,7 @@ static void engine_open(input_t *st, int cs16)
     st->engine_cs16 = cs16;
     st->engine_am = am;
     const char *dev_l2 = getenv("NRSC5_B200_DEVICE_L2");
-    st->device_l2 = !am && !(dev_l2 && !atoi(dev_l2));
+    st->device_l2 = !(dev_l2 && !atoi(dev_l2));
     if (st->device_l2)
     {
         rc = nrsc5b_enable_l2(st->engine, 1);

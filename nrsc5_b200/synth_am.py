@@ -154,7 +154,7 @@ def make_am_ma3(**kw) -> AmCapture:
 
 def make_am_ma1(nframes: int = 10, seed: int = 1234, lead_in: int = 500, carrier: float = 10000.0, unit: float = 50.0,
                 noise_lsb: float = 0.0, noise_seed: int = 5, cfo_hz: float = 0.0, psmi: int = 1,
-                flags: tuple = (0, 0, 0, 0)) -> AmCapture:
+                flags: tuple = (0, 0, 0, 0), p1_frames=None) -> AmCapture:
     """AM hybrid MA1 (psmi 1) or all-digital MA3 (psmi 2) capture of `nframes` transmitted L1 frames (8 blocks each).  The receiver needs the 0x5670
     block-count run to lock, then four frames before it decodes (decode.c:512,569), and the main bits of a
     frame travel three frames ahead of its backup bits: frame F comes out when frames F-3 .. F+1 were received."""
@@ -164,6 +164,13 @@ def make_am_ma1(nframes: int = 10, seed: int = 1234, lead_in: int = 500, carrier
     nlog = nframes + 3
     frng = np.random.default_rng(seed + 77)                          # MA3 outer-partition filler
     p1 = [[_frame_bits(rng, P1_BITS, 22, 120, 160) for _ in range(8)] for _ in range(nlog)]
+    if p1_frames is not None:               # caller's P1 PDUs (packed MSB first, 3750 bits each: synth_l2.py), in order
+        src = iter(p1_frames)
+        for f in range(nlog):
+            for k in range(8):
+                pk = next(src, None)
+                if pk is not None:
+                    p1[f][k] = np.unpackbits(np.frombuffer(pk, dtype=np.uint8))[:P1_BITS]
     ma3 = psmi == 2
     assert psmi in (1, 2)
     if ma3:

@@ -151,3 +151,25 @@ def test_dropin_with_device_l2_matches_reference_events():
         test_dropin.test_dropin_events_match_reference_on_sample_xz(1)
     finally:
         os.environ.pop("NRSC5_B200_DEVICE_L2", None)
+
+
+def test_am_chain_with_l2_on_device():
+    """AM (MA1): the 3750-bit P1 frames carry real audio PDUs; with nrsc5b_enable_l2 an AM engine hands every frame
+    k_am decodes to k_l2 (launches of at most 16 blocks each), and the records equal the oracle's L1 stream with the
+    oracle's L2 calls behind every frame."""
+    from nrsc5_b200 import synth_am
+    src = [f for f in synth_l2.make_l2_sequence(seed=33, nframes=13 * 8, nbits=3750) if f is not None]
+    # frames the generator made uncorrectable on purpose would drop sync in AM (frame.c:538): keep the decodable ones
+    good = [f[2] for i, f in enumerate(src) if i % 12 != 5]
+    cap = synth_am.make_am_ma1(nframes=10, seed=3, lead_in=500, p1_frames=good)
+    with eng.Engine(nstreams=1, input_capacity=4 * cap.cs16.size + 4096, log_capacity=1 << 20, mode="am") as e:
+        e.enable_l2()
+        e.push_cs16(0, cap.cs16)
+        e.process()
+        raw = e.drain_raw(0)
+    l1 = port.decode_am(cap.cs16)
+    orc, lost = port.l2_frames(port.l1_to_l2_input(l1.records))
+    got = [(t, r) for t, r in eng.with_l2_in_call_order(raw) if t in (1, 16, 17, 18, 19)]
+    assert got == orc.records
+    assert sum(1 for t, _ in got if t == 19) > 60 and lost == 0
+    assert [t for t, _ in eng.parse_records(raw) if t != eng.REC_L2] == [t for t, _ in l1.records]
