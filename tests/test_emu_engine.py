@@ -121,7 +121,12 @@ def test_dropin_events_match_reference_on_sample_xz(emulated_dropin, device_l2):
     os.environ.pop("NRSC5_B200_DEVICE_L2", None)
 
 
+@pytest.mark.parametrize("device_l2", [0, 1])
 @pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cu8")])
-def test_dropin_am_matches_reference_events(emulated_dropin, psmi, fmt):
+def test_dropin_am_matches_reference_events(emulated_dropin, psmi, fmt, device_l2):
     import test_dropin
-    test_dropin.test_dropin_am_matches_reference_events(psmi, fmt)
+    os.environ["NRSC5_B200_DEVICE_L2"] = str(device_l2)
+    try:
+        test_dropin.test_dropin_am_matches_reference_events(psmi, fmt)
+    finally:
+        os.environ.pop("NRSC5_B200_DEVICE_L2", None)

@@ -173,3 +173,14 @@ def test_am_chain_with_l2_on_device():
     assert got == orc.records
     assert sum(1 for t, _ in got if t == 19) > 60 and lost == 0
     assert [t for t, _ in eng.parse_records(raw) if t != eng.REC_L2] == [t for t, _ in l1.records]
+
+
+@pytest.mark.parametrize("psmi,fmt", [(1, "cs16"), (2, "cu8")])
+def test_dropin_am_with_device_l2_matches_reference_events(psmi, fmt):
+    """AM through the drop-in's public API with NRSC5_B200_DEVICE_L2=1 (AM frames through k_l2 as well)."""
+    import test_dropin
+    os.environ["NRSC5_B200_DEVICE_L2"] = "1"
+    try:
+        test_dropin.test_dropin_am_matches_reference_events(psmi, fmt)
+    finally:
+        os.environ.pop("NRSC5_B200_DEVICE_L2", None)
