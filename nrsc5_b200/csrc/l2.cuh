@@ -97,14 +97,18 @@ __device__ inline uint8_t *ev_put(EvWriter &w, uint32_t type, const void *a, uns
     return q + 8;
 }
 
-__device__ inline unsigned fcs16_of(const uint8_t *p, int n)        // RFC 1662 FCS, reference src/frame.c:95-144
+// CRC tables of the frame being processed, in shared memory (built by the CTA at the start of l2_frame):
+// fcs[x] = x pushed through 8 steps of the reflected polynomial 0x8408 (RFC 1662, reference src/frame.c:95-128),
+// crc8[x] = x through 8 steps of x^8 + x^5 + x^4 + 1 (reference src/frame.c:60-93)
+struct CrcTabs {
+    uint16_t fcs[256];
+    uint8_t crc8[256];
+};
+
+__device__ inline unsigned fcs16_of(const CrcTabs &tb, const uint8_t *p, int n)        // reference src/frame.c:138-144
 {
     unsigned c = 0xFFFF;
-    for (int i = 0; i < n; i++) {
-        c ^= p[i];
-#pragma unroll
-        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0x8408u : 0u);
-    }
+    for (int i = 0; i < n; i++) c = (c >> 8) ^ tb.fcs[(c ^ p[i]) & 0xFFu];
     return c;
 }
 
@@ -127,21 +131,21 @@ __device__ inline int hdlc_unescape(uint8_t *d, int n)              // reference
 }
 
 // a complete HDLC frame of PSD / AAS data: aas_push, reference src/frame.c:343-367
-__device__ inline void aas_frame(EvWriter &w, uint8_t *d, int n)
+__device__ inline void aas_frame(EvWriter &w, const CrcTabs &tb, uint8_t *d, int n)
 {
     n = hdlc_unescape(d, n);
     if (n == 0) return;
-    if (fcs16_of(d, n) != 0xF0B8u) return;
+    if (fcs16_of(tb, d, n) != 0xF0B8u) return;
     if (d[0] != 0x21) return;
     ev_put(w, EV_AAS, nullptr, 0, d + 1, (unsigned)(n - 3));
 }
 
 // a complete HDLC frame of the channel-configuration channel: process_fixed_ccc, reference src/frame.c:393-438
-__device__ inline void ccc_frame(L2Ccc &c, uint8_t *d, int n0)
+__device__ inline void ccc_frame(L2Ccc &c, const CrcTabs &tb, uint8_t *d, int n0)
 {
     const unsigned n = (unsigned)hdlc_unescape(d, n0);
     if (n == 0 || c.ready) return;
-    if (fcs16_of(d, (int)n) != 0xF0B8u) return;
+    if (fcs16_of(tb, d, (int)n) != 0xF0B8u) return;
     for (unsigned i = 0; i < 4; i++) {
         L2Sub &s = c.sub[i];
         s.length = 0;
@@ -158,15 +162,16 @@ __device__ inline void ccc_frame(L2Ccc &c, uint8_t *d, int n0)
 }
 
 // parse_hdlc, reference src/frame.c:369-391.  ccc != nullptr: frames go to ccc_frame, else to aas_frame
-__device__ inline void hdlc_scan(EvWriter &w, L2Ccc *ccc, uint8_t *acc, int *idx, int cap, const uint8_t *in, unsigned n)
+__device__ inline void hdlc_scan(EvWriter &w, const CrcTabs &tb, L2Ccc *ccc, uint8_t *acc, int *idx, int cap, const uint8_t *in,
+                                 unsigned n)
 {
     int k = *idx;
     for (unsigned i = 0; i < n; i++) {
         const uint8_t b = in[i];
         if (b == 0x7E) {
             if (k >= 0) {
-                if (ccc) ccc_frame(*ccc, acc, k);
-                else aas_frame(w, acc, k);
+                if (ccc) ccc_frame(*ccc, tb, acc, k);
+                else aas_frame(w, tb, acc, k);
             }
             k = 0;
         } else if (k >= 0) {
@@ -178,7 +183,7 @@ __device__ inline void hdlc_scan(EvWriter &w, L2Ccc *ccc, uint8_t *acc, int *idx
 }
 
 // process_fixed_data, reference src/frame.c:448-514: returns where the audio part of the PDU ends
-__device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const uint8_t *pdu, unsigned length, unsigned lc)
+__device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const CrcTabs &tb, const uint8_t *pdu, unsigned length, unsigned lc)
 {
     L2Ccc &c = z.ccc[lc];
     unsigned pos = length - 1;
@@ -190,7 +195,7 @@ __device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const uint8_t *pd
         if (c.count < 2) return pos;
     }
     pos -= c.width;
-    hdlc_scan(w, &c, c.ccc, &c.ccc_idx, 32, pdu + pos, c.width);
+    hdlc_scan(w, tb, &c, c.ccc, &c.ccc_idx, 32, pdu + pos, c.width);
     if (!c.ready) return pos;
     for (int i = 3; i >= 0; i--) {
         L2Sub &s = c.sub[i];
@@ -205,7 +210,7 @@ __device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const uint8_t *pd
                 s.fill = 3;
             }
             if (s.fill == 259) {
-                hdlc_scan(w, nullptr, s.data, &s.idx, L2_AAS_MAX, s.blk + 4, 255);
+                hdlc_scan(w, tb, nullptr, s.data, &s.idx, L2_AAS_MAX, s.blk + 4, 255);
                 s.fill = 0;
             }
         }
@@ -262,13 +267,13 @@ struct PkEntry {
 };
 
 // the sequential walk over one PDU (thread 0): frame_process, reference src/frame.c:516-643
-__device__ inline void l2_walk(L2State &z, EvWriter &w, uint8_t *pdu, unsigned length, unsigned lc, uint32_t pci,
+__device__ inline void l2_walk(L2State &z, EvWriter &w, const CrcTabs &tb, uint8_t *pdu, unsigned length, unsigned lc, uint32_t pci,
                                PkEntry *pk, unsigned &npk, unsigned &flags, uint8_t *rs_scratch)
 {
     const uint32_t k = pci & 0xFFFFFCu;
     const bool fixed = k == (0xE3634Cu & 0xFFFFFCu) || k == (0x8D8D33u & 0xFFFFFCu) || k == (0x3634CEu & 0xFFFFFCu);
     unsigned end = length, off = 0;
-    if (fixed) end = fixed_tail(z, w, pdu, length, lc);
+    if (fixed) end = fixed_tail(z, w, tb, pdu, length, lc);
     if (k == (0x3634CEu & 0xFFFFFCu)) return;                         // fixed data only: no audio
     while (off < end - 96u) {                                         // unsigned on purpose, as frame.c:527
         const unsigned start = off;
@@ -326,7 +331,7 @@ __device__ inline void l2_walk(L2State &z, EvWriter &w, uint8_t *pdu, unsigned l
         if ((L2_RING + seq - out_off) % L2_RING >= L2_RING / 2) out_off = (out_off + L2_RING / 2) % L2_RING;
         const uint32_t al[3] = { prog, stream, out_off };
         ev_put(w, EV_ALIGN, al, sizeof(al), nullptr, 0);
-        hdlc_scan(w, nullptr, z.psd[prog], &z.psd_idx[prog], L2_AAS_MAX, pdu + off, start + la + 1 - off);
+        hdlc_scan(w, tb, nullptr, z.psd[prog], &z.psd_idx[prog], L2_AAS_MAX, pdu + off, start + la + 1 - off);
         off = start + la + 1;
         for (unsigned j = 0; j < nop; j++) {
             const unsigned cnt = start + loc[j] - off;
@@ -334,7 +339,7 @@ __device__ inline void l2_walk(L2State &z, EvWriter &w, uint8_t *pdu, unsigned l
             uint32_t r[7] = { prog, stream, seq, shape, 0u, cnt, off };
             if (npk >= (unsigned)L2_PK_MAX) {                         // table full: this thread checks the CRC itself
                 unsigned c = 0xFF;
-                for (unsigned i = 0; i <= cnt; i++) c = crc8_step(c, pdu[off + i]);
+                for (unsigned i = 0; i <= cnt; i++) c = tb.crc8[c ^ pdu[off + i]];
                 r[4] = c ? 1u : 0u;
             }
             uint8_t *q = ev_put(w, EV_PACKET, r, sizeof(r), nullptr, 0);
@@ -379,6 +384,7 @@ __device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbit
     __shared__ __align__(16) uint8_t pdu[(L2_PDU_MAX + 15) & ~15];
     __shared__ PkEntry pk[L2_PK_MAX];
     __shared__ uint8_t rs_scratch[256];
+    __shared__ CrcTabs tb;
     __shared__ unsigned sh_pci, sh_npk, sh_flags, sh_evlen;
     __shared__ uint8_t *sh_out;
     const unsigned t = threadIdx.x, nt = blockDim.x;
@@ -386,6 +392,13 @@ __device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbit
     if (!l2_geometry(nbits, first, step, npci)) return;
     const unsigned nout = (nbits - npci) / 8;
     if (t == 0) sh_pci = 0;
+    for (unsigned x = t; x < 256; x += nt) {
+        unsigned f = x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) f = (f >> 1) ^ ((f & 1u) ? 0x8408u : 0u);
+        tb.fcs[x] = (uint16_t)f;
+        tb.crc8[x] = (uint8_t)crc8_step(0, x);
+    }
     __syncthreads();
     if (t < npci) atomicOr(&sh_pci, swapped_bit(packed, nbits, first + step * t) << (23 - t));
     // PDU byte n = frame bits (after the swap) 8n .. 8n+7, counted without the PCI bits
@@ -411,7 +424,7 @@ __device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbit
     if (t == 0) {
         EvWriter w = { z.ev, 0u, 0u };
         unsigned npk = 0, flags = 0;
-        l2_walk(z, w, pdu, nout, lc, sh_pci, pk, npk, flags, rs_scratch);
+        l2_walk(z, w, tb, pdu, nout, lc, sh_pci, pk, npk, flags, rs_scratch);
         if (w.overflow) flags |= L2F_EV_OVERFLOW;
         sh_npk = npk;
         sh_flags = flags;
@@ -422,7 +435,7 @@ __device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbit
     for (unsigned j = t; j < sh_npk; j += nt) {                       // CRC-8 over payload + check byte: 0 when intact
         unsigned c = 0xFF;
         const uint8_t *q = pdu + pk[j].start;
-        for (unsigned i = 0; i <= pk[j].cnt; i++) c = crc8_step(c, q[i]);
+        for (unsigned i = 0; i <= pk[j].cnt; i++) c = tb.crc8[c ^ q[i]];
         *reinterpret_cast<uint32_t *>(z.ev + pk[j].ev) = c ? 1u : 0u;
     }
     __syncthreads();

@@ -17,13 +17,15 @@ __device__ __forceinline__ unsigned mod255(unsigned x)
     return x;
 }
 
-// data[255] in place; returns number of corrected symbols or -1
-__device__ inline int rs_decode_255_247(uint8_t *data)
+// data[255] in place; returns number of corrected symbols or -1.  lead_zeros: the caller knows data[0 .. lead_zeros)
+// to be zero (the shortened code of the 96-byte header: 159); the syndromes' Horner evaluation over that prefix
+// leaves zeros, so it starts behind it.
+__device__ inline int rs_decode_255_247(uint8_t *data, int lead_zeros = 0)
 {
     constexpr int R = 8, NN = 255, A0 = 255;
     uint8_t s[R], lambda[R + 1], b[R + 1], t[R + 1], omega[R + 1], reg[R + 1], root[R], loc[R];
-    for (int i = 0; i < R; i++) s[i] = data[0];
-    for (int j = 1; j < NN; j++) {
+    for (int i = 0; i < R; i++) s[i] = data[lead_zeros];
+    for (int j = lead_zeros + 1; j < NN; j++) {
         const uint8_t dj = data[j];
         for (int i = 0; i < R; i++)
             s[i] = s[i] == 0 ? dj : (uint8_t)(dj ^ c_gf_exp[mod255(c_gf_log[s[i]] + 1 + i)]);
@@ -112,7 +114,7 @@ __device__ inline int fix_header_96(uint8_t *buf, uint8_t *blk /* 255 bytes scra
 {
     for (int i = 0; i < 159; i++) blk[i] = 0;
     for (int i = 0; i < 96; i++) blk[254 - i] = buf[i];
-    if (rs_decode_255_247(blk) == -1) return 0;
+    if (rs_decode_255_247(blk, 159) == -1) return 0;
     for (int i = 0; i < 159; i++)
         if (blk[i] != 0) return 0;
     for (int i = 0; i < 96; i++) buf[i] = blk[254 - i];

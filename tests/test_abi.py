@@ -43,6 +43,8 @@ def test_no_cpu_fallback_without_gpu():
     import numpy as np
     with pytest.raises(nrsc5_b200.EngineError):
         eng.halfband_fm(np.zeros(64, dtype=np.uint8))
+    with pytest.raises(nrsc5_b200.EngineError):
+        eng.l2_frames([(1, 4608, bytes(576))])              # L2 alone: no host path either
 
 
 def test_record_parser_roundtrip():
@@ -55,3 +57,19 @@ def test_record_parser_roundtrip():
     recs = eng.parse_records(raw)
     assert [t for t, _ in recs] == [eng.REC_SYNC, eng.REC_PIDS, eng.REC_FRAME, eng.REC_LOST_SYNC]
     assert recs[0][1]["psmi"] == 1 and recs[2][1]["bits"] == b"\x01\x02\x03"
+
+
+def test_l2_record_parser():
+    """REC_L2 (include/nrsc5_b200.h): header, events in call order, PDU bytes; packet data is cut out of the PDU."""
+    import struct
+    pdu = bytes(range(40))
+    ev = b""
+    ev += struct.pack("<II", eng.EV_ALIGN, 12) + struct.pack("<3I", 1, 0, 24)
+    ev += struct.pack("<II", eng.EV_AAS, 5) + b"hello" + b"\0\0\0"
+    ev += struct.pack("<II", eng.EV_PACKET, 28) + struct.pack("<7I", 1, 0, 9, 1, 0, 6, 30)
+    body = struct.pack("<8I", 4096, 1, 4608, 0x38D8D3, 0, len(pdu), len(ev), 7) + ev + pdu
+    raw = struct.pack("<II", eng.REC_L2, len(body)) + body
+    (ty, r), = eng.parse_records(raw)
+    assert ty == eng.REC_L2 and (r["lc"], r["nbits"], r["pci"], r["ordinal"], r["frame_rec_off"]) == (1, 4608, 0x38D8D3, 7, 4080)
+    assert [t for t, _ in r["events"]] == [eng.EV_ALIGN, eng.EV_AAS, eng.EV_PACKET]
+    assert r["events"][1][1]["data"] == b"hello" and r["events"][2][1]["data"] == pdu[30:36] and r["pdu"] == pdu

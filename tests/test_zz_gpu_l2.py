@@ -10,7 +10,7 @@ import os
 import pytest
 
 import port
-from common import MP3_CASE, SYNTH_CASES, golden, load_sample
+from common import FM_MODE_CASES, MP3_CASE, SYNTH_CASES, golden, load_sample
 from l2_cases import L2_CASES, l2_digest, mutated_sequence
 from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth, synth_l2
@@ -184,3 +184,26 @@ def test_dropin_am_with_device_l2_matches_reference_events(psmi, fmt):
         test_dropin.test_dropin_am_matches_reference_events(psmi, fmt)
     finally:
         os.environ.pop("NRSC5_B200_DEVICE_L2", None)
+
+
+@pytest.mark.parametrize("mode", ["mp2", "mp11"])
+def test_service_mode_chain_l2_call_order(mode):
+    """MP2 (2304-bit P3 frames) and MP11 (P3 and P4 frames, decode groups added to the passes on demand): every
+    frame of every logical channel gets its REC_L2, taken in the reference's call order (P1 before the P3 / P4 frames
+    of block 15, P3 before P4), and the calls equal the oracle's L2 over the same frames."""
+    cap = synth.make_fm(**FM_MODE_CASES[mode])
+    cu8 = cap.cu8[:cap.cu8.size & ~3]
+    with eng.Engine(nstreams=1, input_capacity=cu8.size + 4096, log_capacity=4 << 20) as e:
+        e.enable_l2()
+        e.push_cu8(0, cu8)
+        e.process()
+        raw = e.drain_raw(0)
+    offs = []
+    recs = eng.parse_records(raw, offs)
+    frames = {at: r for (t, r), at in zip(recs, offs) if t == eng.REC_FRAME}
+    l2s = [r for t, r in recs if t == eng.REC_L2]
+    assert [r["frame_rec_off"] for r in l2s] == sorted(frames) and len(l2s) >= 10
+    assert {r["lc"] for r in l2s} == ({0, 1} if mode == "mp2" else {0, 1, 2})
+    got = [(t, r) for t, r in eng.with_l2_in_call_order(raw) if t in (1, 16, 17, 18, 19)]
+    orc, _ = port.l2_frames(port.l1_to_l2_input([(t, r) for t, r in recs if t in (1, 3)]))
+    assert got == orc.records
