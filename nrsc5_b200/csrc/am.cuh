@@ -112,7 +112,11 @@ struct AmState {
 
 AM_HD inline void l2_enqueue(AmState &st, unsigned off, unsigned lc, unsigned nbits)
 {
-    if (!st.l2_on || st.l2_n >= AM_L2_QUEUE) return;
+    if (!st.l2_on) return;
+    if (st.l2_n >= AM_L2_QUEUE) {               // cannot happen with AM_L2_BLOCKS blocks per launch
+        st.log_overflow = 1;
+        return;
+    }
     st.l2_off[st.l2_n] = off;
     st.l2_lc[st.l2_n] = lc;
     st.l2_nbits[st.l2_n] = nbits;

@@ -203,7 +203,11 @@ __device__ inline uint8_t *log_reserve(const DevPtrs &p, const EngineDims &d, in
 __device__ inline void l2_enqueue(StreamState &st, const EngineDims &d, const DevPtrs &p, int s, const uint8_t *bits,
                                   unsigned lc, unsigned nbits)
 {
-    if (!d.l2 || st.l2_n >= L2_QUEUE) return;
+    if (!d.l2) return;
+    if (st.l2_n >= L2_QUEUE) {                 // cannot happen with 16 blocks per pass; the host is told if it does
+        st.log_overflow = 1;
+        return;
+    }
     const int e = st.l2_n++;
     st.l2_off[e] = bits ? (unsigned)(bits - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
     st.l2_lc[e] = lc;

@@ -200,6 +200,9 @@ __device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const CrcTabs &tb
     for (int i = 3; i >= 0; i--) {
         L2Sub &s = c.sub[i];
         if (s.length == 0) continue;
+        // a CCC that announces more subchannel bytes than the PDU holds (noise that passed the FCS-16) would make
+        // the reference read in front of its buffer (frame.c:493-496); here the frame has no audio part instead
+        if (s.length > pos) return 0;
         pos -= s.length;
         for (unsigned j = 0; j < s.length; j++) {
             s.blk[s.fill++] = pdu[pos + j];
@@ -331,7 +334,10 @@ __device__ inline void l2_walk(L2State &z, EvWriter &w, const CrcTabs &tb, uint8
         if ((L2_RING + seq - out_off) % L2_RING >= L2_RING / 2) out_off = (out_off + L2_RING / 2) % L2_RING;
         const uint32_t al[3] = { prog, stream, out_off };
         ev_put(w, EV_ALIGN, al, sizeof(al), nullptr, 0);
-        hdlc_scan(w, tb, nullptr, z.psd[prog], &z.psd_idx[prog], L2_AAS_MAX, pdu + off, start + la + 1 - off);
+        // header expansion fields that run past la_location make the reference's byte count wrap (frame.c:608: it
+        // would scan 4 GB); nothing is scanned here
+        const unsigned psd_bytes = start + la + 1 >= off ? start + la + 1 - off : 0u;
+        hdlc_scan(w, tb, nullptr, z.psd[prog], &z.psd_idx[prog], L2_AAS_MAX, pdu + off, psd_bytes);
         off = start + la + 1;
         for (unsigned j = 0; j < nop; j++) {
             const unsigned cnt = start + loc[j] - off;

@@ -188,7 +188,9 @@ class FixedDataSource:
         self.width = width
         self.lengths = list(lengths)
         ccc = bytes([0x00]) + b"".join(bytes([0, 0, l & 0xFF, l >> 8]) for l in self.lengths)
-        self.ccc_stream = bytearray(hdlc_frame(ccc) + b"\x7e")
+        # the receiver only scans the CCC bytes once it has seen the same sync width three times in a row
+        # (frame.c:466-477) and forgets everything at a frame_reset: idle flags first, and the CCC keeps repeating
+        self.ccc_stream = bytearray((b"\x7e" * (3 * width) + hdlc_frame(ccc) + b"\x7e") * 64)
         self.ccc_pos = 0
         self.sent = []
         self.sub_streams = []
@@ -205,8 +207,9 @@ class FixedDataSource:
             while len(hd) % 255:
                 hd += b"\x7e"
             blocks = bytearray(rng.integers(0, 256, misalign, dtype=np.uint8).tobytes())
-            for k in range(0, len(hd), 255):
-                blocks += bytes([0x7D, 0x3A, 0xE2, 0x42]) + hd[k:k + 255]
+            for _ in range(6):                 # the receiver joins mid-stream (after the CCC): the messages keep coming
+                for k in range(0, len(hd), 255):
+                    blocks += bytes([0x7D, 0x3A, 0xE2, 0x42]) + hd[k:k + 255]
             self.sub_streams.append(blocks)
             self.sent.append(msgs)
         self.sub_pos = [0] * len(self.lengths)

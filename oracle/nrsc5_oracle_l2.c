@@ -206,6 +206,7 @@ static unsigned fixed_tail(orc_l2_t *o, unsigned length, unsigned lc)
     for (int i = 3; i >= 0; i--) {
         l2_sub_t *s = &c->sub[i];
         if (s->length == 0) continue;
+        if (s->length > pos) return 0;      /* the reference would read in front of its buffer here (frame.c:493-496) */
         pos -= s->length;
         for (unsigned j = 0; j < s->length; j++) {
             s->blk[s->fill++] = o->buf[pos + j];
@@ -344,7 +345,9 @@ static void walk_pdus(orc_l2_t *o, unsigned length, unsigned lc)
         if ((RING + seq - out_off) % RING >= RING / 2) out_off = (out_off + RING / 2) % RING;
         uint32_t al[3] = { prog, stream, out_off };
         put(o, ORC_REC_L2_ALIGN, al, sizeof(al), NULL, 0);
-        hdlc_scan(o, 0, NULL, o->psd[prog], &o->psd_idx[prog], AAS_MAX, o->buf + off, (size_t)(start + la + 1 - off));
+        /* HEF past la_location: the reference's unsigned byte count wraps and it scans 4 GB (frame.c:608) */
+        hdlc_scan(o, 0, NULL, o->psd[prog], &o->psd_idx[prog], AAS_MAX, o->buf + off,
+                  start + la + 1 >= off ? (size_t)(start + la + 1 - off) : 0);
         off = start + la + 1;
         for (unsigned j = 0; j < nop; j++) {
             const unsigned cnt = start + loc[j] - off;

@@ -2,7 +2,7 @@
 L2_CASES = {
     "p1_fm": dict(),
     "p1_fm_fixed": dict(fixed=True, nframes=40),
-    "p1_fm_fixed_b": dict(fixed=True, nframes=20, seed=11),
+    "p1_fm_fixed_b": dict(fixed=True, nframes=36, seed=11),
     "p3_mp3": dict(nbits=4608, lc=1),
     "p4_mp11_fixed": dict(nbits=4608, lc=2, fixed=True, nframes=60, seed=3),
     "p3_mp2": dict(nbits=2304, lc=1),
@@ -52,3 +52,33 @@ def mutated_sequence(trial: int):
             b[pos] ^= int(rng.integers(1, 256))
         out.append((f[0], f[1], bytes(b)))
     return out, nbits in AM_BITS
+
+
+def malformed_sequences():
+    """Two PDU sequences on which the reference's frame.c leaves its buffers (so it is not run on them): a CCC that
+    passes its FCS-16 but announces more subchannel bytes than a PDU holds (frame.c:493-496 would read in front of
+    the buffer), and header expansion fields that run past la_location (frame.c:608: the byte count wraps).  The
+    engine and the oracle define the same safe outcome for both."""
+    import numpy as np
+    from nrsc5_b200 import synth_l2 as g
+    rng = np.random.default_rng(99)
+    n = g.pdu_len(4608)
+    # (a) CCC with a 60 000-byte subchannel
+    src = g.FixedDataSource(rng, 4, [])
+    src.ccc_stream = bytearray(b"\x7e" * 12 + g.hdlc_frame(bytes([0, 0, 0, 0x60, 0xEA])) + b"\x7e")
+    a = [None]
+    for f in range(12):
+        part = g.audio_pdu(rng, [40, 41, 42], seq=f, psd=g.hdlc_frame(bytes([0x21, f]) + bytes(20)))
+        a.append((1, 4608, g.frame_from_pdu(g.fill_pdu(rng, [part], n, src.tail()), 4608, g.PCI_AUDIO_FIXED)))
+    # (b) la_location inside the header expansion fields
+    b = [None]
+    for f in range(6):
+        hef = g.hef_fields(1, ptype=22, pdu_len_field=300, with_loc=True)
+        pdu = bytearray(g.audio_pdu(rng, [50, 60, 70], codec=0, stream=0, seq=f, hef=hef, psd=g.hdlc_frame(bytes([0x21]) + bytes(30))))
+        if f % 2:
+            pdu[13] = 14 + 6 + 2                       # 3 locations of 16 bit = 6 bytes; la points into the HEF
+            head = bytearray(pdu[:96])
+            g.protect_header(head)
+            pdu[:96] = head
+        b.append((1, 4608, g.frame_from_pdu(g.fill_pdu(rng, [bytes(pdu)], n), 4608, g.PCI_AUDIO)))
+    return {"ccc_overlong": a, "hef_past_la": b}

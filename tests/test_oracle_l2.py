@@ -44,6 +44,10 @@ def test_l2_generator_covers_the_branches():
     assert {r["program"] for r in pk} >= {0, 1} and {r["stream_id"] for r in pk} == {0, 1}
     aas = [r["data"] for t, r in orc.records if t == 18]
     assert len(aas) > 20                                    # PSD messages and fixed-data subchannel messages
+    # the subchannel messages (40 + 37 m + 11 s bytes, m-th message of subchannel s; FixedDataSource) got through the
+    # CCC / block-marker / HDLC path, the one with the bad FCS (m = 1, s = 0) did not
+    lens = {len(a) for a in aas}
+    assert {40, 114, 51, 88, 125, 162} <= lens and 77 not in lens
     assert lost == 1
 
 

@@ -11,7 +11,7 @@ import pytest
 
 import port
 from common import FM_MODE_CASES, MP3_CASE, SYNTH_CASES, golden, load_sample
-from l2_cases import L2_CASES, l2_digest, mutated_sequence
+from l2_cases import L2_CASES, l2_digest, malformed_sequences, mutated_sequence
 from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth, synth_l2
 
@@ -207,3 +207,18 @@ def test_service_mode_chain_l2_call_order(mode):
     got = [(t, r) for t, r in eng.with_l2_in_call_order(raw) if t in (1, 16, 17, 18, 19)]
     orc, _ = port.l2_frames(port.l1_to_l2_input([(t, r) for t, r in recs if t in (1, 3)]))
     assert got == orc.records
+
+
+@pytest.mark.parametrize("name", ["ccc_overlong", "hef_past_la"])
+def test_l2_malformed_pdus_stay_in_bounds(name):
+    """PDUs on which the reference's frame.c leaves its buffers (tests/l2_cases.py:malformed_sequences): the kernel
+    must neither fault nor differ from the oracle's defined outcome, and must carry on with the next frames."""
+    frames = malformed_sequences()[name]
+    recs = eng.l2_frames(frames)
+    orc, _ = port.l2_frames(frames)
+    assert expand(recs, frames) == orc.records
+    assert len(recs) == len(frames) - 1
+    if name == "ccc_overlong":
+        assert sum(len(r["events"]) for r in recs[:3]) > 0 and all(not r["events"] for r in recs[-4:])
+    else:
+        assert all(any(t == eng.EV_PACKET for t, _ in r["events"]) for r in recs)
