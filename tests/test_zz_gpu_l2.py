@@ -78,14 +78,19 @@ def test_chain_with_l2_on_device():
     cap = synth.make_fm_mp1(nframes=4, seed=1234, lead_in=1777, p1_frames=[None] + [f[2] for f in frames])
     cu8 = cap.cu8[:cap.cu8.size & ~3]
     half = (cu8.size // 2) & ~3
-    with eng.Engine(nstreams=2, input_capacity=cu8.size + 4096, log_capacity=1 << 20) as e:
+    # a third channel with other PDUs (and a carrier offset): the per-stream L2 state must not mix
+    frames_c = [f for f in synth_l2.make_l2_sequence(seed=22, nframes=3) if f is not None]
+    cap_c = synth.make_fm_mp1(nframes=4, seed=77, lead_in=333, cfo_hz=120.0, p1_frames=[None] + [f[2] for f in frames_c])
+    cu8_c = cap_c.cu8[:cap_c.cu8.size & ~3]
+    with eng.Engine(nstreams=3, input_capacity=max(cu8.size, cu8_c.size) + 4096, log_capacity=1 << 20) as e:
         e.enable_l2()
         e.push_cu8(0, cu8)
         e.push_cu8(1, cu8[:half])
+        e.push_cu8(2, cu8_c)
         e.process()
         e.push_cu8(1, cu8[half:])
         e.process()
-        raws = [e.drain_raw(0), e.drain_raw(1)]
+        raws = [e.drain_raw(0), e.drain_raw(1), e.drain_raw(2)]
     l1 = port.decode(cu8)
     want = []
     l2in, l2 = port.l1_to_l2_input(l1.records), None
@@ -114,6 +119,12 @@ def test_chain_with_l2_on_device():
     a = [(t, r) for t, r in eng.with_l2_in_call_order(raws[0]) if t in (16, 17, 18, 19)]
     b = [(t, r) for t, r in eng.with_l2_in_call_order(raws[1]) if t in (16, 17, 18, 19)]
     assert a == b and len(a) > 50
+    # the third channel: its own frames, its own calls
+    l1c = [(t, r) for t, r in eng.parse_records(raws[2]) if t in (1, 3)]
+    orc_c, _ = port.l2_frames(port.l1_to_l2_input(l1c))
+    c = [(t, r) for t, r in eng.with_l2_in_call_order(raws[2]) if t in (1, 16, 17, 18, 19)]
+    assert c == orc_c.records and [r for t, r in c if t != 1] != [r for t, r in a]
+    assert [r["bits"] for t, r in c if t == 1][1:] == [f[2] for f in frames_c]
 
 
 def test_mp3_chain_l2_records_follow_their_frames():
