@@ -311,7 +311,7 @@ def build_p3_frame_bits(rng, nbits: int = P3_BITS) -> np.ndarray:
     return bits
 
 
-def _px_stream(prng, nblocks: int, first_even: int, frame_len: int):
+def _px_stream(prng, nblocks: int, first_even: int, frame_len: int, supplied=None):
     """The bit stream of one extended-partition group (PX1 or PX2) over `nblocks` blocks of `frame_len` soft bits
     each, and the frames a receiver hands out: the deinterleaver starts with the first even block it sees and
     returns frame c (inputs of blocks 2c, 2c+1 counted from there) once 16 frames have gone in; transmit stream
@@ -326,6 +326,8 @@ def _px_stream(prng, nblocks: int, first_even: int, frame_len: int):
     frames = []
     for c in range(ncalls):
         fb = build_p3_frame_bits(prng, frame_len)
+        if supplied is not None and c < len(supplied) and supplied[c] is not None:      # caller's PDUs (packed, synth_l2.py)
+            fb = np.unpackbits(np.frombuffer(supplied[c], dtype=np.uint8))[:frame_len]
         u = conv_encode_tb(fb ^ pn).reshape(-1)[keep3]                 # 2 * frame_len transmitted bits
         k = c * 2 * frame_len + np.arange(2 * frame_len, dtype=np.int64)
         j = k - D[k % N]
@@ -380,7 +382,7 @@ def make_fm_mp3(**kw) -> FmCapture:
 def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 1000, cfo_hz: float = 0.0,
             noise_lsb: float = 0.0, noise_seed: int = 5, rms_lsb: float = 20.0,
             tail_blocks: int = 2, valid_header: bool = True, pci: int = PCI_AUDIO,
-            start_bc: int = 0, pids_crc: bool = False, p1_frames=None) -> FmCapture:
+            start_bc: int = 0, pids_crc: bool = False, p1_frames=None, p3_frames=None) -> FmCapture:
     """FM capture (PSMI 1, 2, 3, 5, 6 or 11) holding `nframes` complete L1 frames
     followed by `tail_blocks` further blocks so the last frame flushes
     (the reference has no flush call).
@@ -428,14 +430,14 @@ def make_fm(psmi: int = 1, nframes: int = 2, seed: int = 1234, lead_in: int = 10
     first_even = start_bc % 2                         # PX blocks before the first even block are read by nobody
     ext = []                                          # (bases, bits)
     if psmi == 3:
-        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK)
+        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK, p3_frames)
         ext.append(((LB_START + 190 + 1, LB_START + 209 + 1, UB_END - 228 + 1, UB_END - 209 + 1),
                     px1.reshape(nblocks, BLKSZ, 4, 18, 2)))
     elif psmi == 2:
         px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK // 2)
         ext.append(((LB_START + 190 + 1, UB_END - 209 + 1), px1.reshape(nblocks, BLKSZ, 2, 18, 2)))
     elif psmi == 11:
-        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK)
+        px1, cap.p3_frames = _px_stream(np.random.default_rng(seed + 7919), nblocks, first_even, PX1_BLOCK, p3_frames)
         px2, cap.p4_frames = _px_stream(np.random.default_rng(seed + 7920), nblocks, first_even, PX1_BLOCK)
         ext.append(((LB_START + 190 + 1, LB_START + 209 + 1, UB_END - 228 + 1, UB_END - 209 + 1),
                     px1.reshape(nblocks, BLKSZ, 4, 18, 2)))

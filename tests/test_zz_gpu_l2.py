@@ -233,3 +233,24 @@ def test_l2_malformed_pdus_stay_in_bounds(name):
         assert sum(len(r["events"]) for r in recs[:3]) > 0 and all(not r["events"] for r in recs[-4:])
     else:
         assert all(any(t == eng.EV_PACKET for t, _ in r["events"]) for r in recs)
+
+
+def test_mp3_chain_with_l2_content_in_p3_frames():
+    """MP3 with real audio PDUs in the P3 frames (and plain ones in P1): both logical channels feed the same service
+    table and PSD buffers, so the interleaving of the P1 and P3 frames' calls - P3 frames of the odd blocks, the P1
+    frame ahead of block 15's P3 frame - shows in the events; they must equal the oracle's L2 over the same frames."""
+    src = [f for f in synth_l2.make_l2_sequence(seed=44, nframes=34, nbits=4608, lc=1) if f is not None]
+    cap = synth.make_fm_mp3(**MP3_CASE, p3_frames=[f[2] for f in src])
+    cu8 = cap.cu8[:cap.cu8.size & ~3]
+    with eng.Engine(nstreams=1, input_capacity=cu8.size + 4096, log_capacity=4 << 20) as e:
+        e.enable_l2()
+        e.push_cu8(0, cu8)
+        e.process()
+        raw = e.drain_raw(0)
+    recs = eng.parse_records(raw)
+    got = [(t, r) for t, r in eng.with_l2_in_call_order(raw) if t in (1, 16, 17, 18, 19)]
+    orc, _ = port.l2_frames(port.l1_to_l2_input([(t, r) for t, r in recs if t in (1, 3)]))
+    assert got == orc.records
+    p3 = [r["bits"] for t, r in recs if t == 1 and r["lc"] == 1]
+    assert len(p3) >= 12 and all(b in {f[2] for f in src} for b in p3)      # decoded P3 frames = generated ones
+    assert sum(1 for t, _ in got if t == 19) > 30 and sum(1 for t, _ in got if t == 16) >= 4
