@@ -234,9 +234,7 @@ static void engine_open(input_t *st, int cs16)
     st->engine_cs16 = cs16;
     st->engine_am = am;
     const char *dev_l2 = getenv("NRSC5_B200_DEVICE_L2");
-    /* unset: FM on the device (verified on the B200), AM through the reference's frame.c until its first B200 run;
-     * 1: both on the device; 0: both through frame.c */
-    st->device_l2 = dev_l2 ? atoi(dev_l2) != 0 : !am;
+    st->device_l2 = !(dev_l2 && !atoi(dev_l2));      /* default: on the device, FM and AM; 0: the reference's frame.c */
     if (st->device_l2)
     {
         rc = nrsc5b_enable_l2(st->engine, 1);
