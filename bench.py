@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--dbg", type=int, default=0, help="kernel experiment switches (nrsc5b_debug_set)")
     ap.add_argument("--no-l2", action="store_true", help="skip the L2-on-device leg (SURVEY 8 f1)")
     ap.add_argument("--l2-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-am", action="store_true", help="skip the AM leg (BASELINE config 4)")
+    ap.add_argument("--am-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--am-streams", type=int, default=256)
+    ap.add_argument("--am-frames", type=int, default=12)
     return ap.parse_args()
 
 
@@ -163,6 +167,58 @@ def l2_leg(args):
            "packets_per_frame": len(pk) / max(1, len(l2) - 1), "steps": steps,
            "workload": f"{S} synthetic FM MP1 channels x {args.frames} L1 frames, P1 PDUs with real audio PDUs "
                        "(synth_l2.py), cu8 resident in HBM, L2 framing on the device (REC_L2 per frame)"}
+    print(json.dumps(out), flush=True)
+    e.close()
+
+
+def am_leg(args, engine_factory=None):
+    """BASELINE config 4: `--am-streams` synthetic AM MA1 channels (cs16 at 46 511.72 S/s, `--am-frames` L1 frames
+    each) on one GPU, decoded from reset to L1 PDUs by the AM engine (one warp per stream, first unoptimised path).
+    A step = reset, push every channel's samples from host memory (nrsc5b_push_cs16), process, drain: the whole
+    thing is timed on the host clock around synchronous calls (the engine waits for its own kernels), and the
+    process() part alone is reported next to it.  Run by the main bench in a subprocess (rank 0, N=1); prints one
+    JSON object."""
+    import nrsc5_b200
+    from nrsc5_b200 import engine as eng, synth_am
+    S, F = args.am_streams, args.am_frames
+    caps = [synth_am.make_am_ma1(nframes=F, seed=3 + i, lead_in=500 + 64 * i, cfo_hz=(0.0, 1.5)[i % 2]).cs16 for i in range(2)]
+    n = min(c.size for c in caps) - 2 * 512
+    views = [np.ascontiguousarray(caps[s % 2][2 * ((37 * (s // 2)) % 256):][:n]) for s in range(S)]
+    make = engine_factory or (lambda **kw: nrsc5_b200.Engine(**kw))
+    e = make(nstreams=S, input_capacity=2 * n + 4096, log_capacity=512 << 10, mode="am")
+
+    def step():
+        t0 = time.perf_counter()
+        e.reset()
+        for s in range(S):
+            e.push_cs16(s, views[s])
+        t1 = time.perf_counter()
+        e.process()
+        t2 = time.perf_counter()
+        recs = e.drain_all()
+        t3 = time.perf_counter()
+        return t3 - t0, t2 - t1, recs
+
+    _, _, recs = step()                                   # warm-up + gate
+    p1 = [r for t, r in recs[0] if t == eng.REC_FRAME and r["lc"] == 0]
+    assert len(p1) >= 8 * (F - 8), f"{len(p1)} AM P1 frames decoded from {F} transmitted L1 frames"
+    assert all(sum(1 for t, _ in r if t == eng.REC_FRAME) == sum(1 for t, _ in recs[s % 2] if t == eng.REC_FRAME)
+               for s, r in enumerate(recs)), "channels that carry the same capture decoded different frame counts"
+    steps = max(2, min(args.steps, 5))
+    tot = proc = 0.0
+    for _ in range(steps):
+        a, b, _ = step()
+        tot += a
+        proc += b
+    samples = S * (n // 2)
+    out = {"value": samples * steps / tot / 1e6, "unit": "Msamples/s (cs16 complex, 46 511.72 S/s per channel)",
+           "x_realtime": samples * steps / tot / 46511.71875, "ms_per_step": 1e3 * tot / steps,
+           "process_only": {"value": samples * steps / proc / 1e6, "ms_per_step": 1e3 * proc / steps,
+                            "x_realtime": samples * steps / proc / 46511.71875},
+           "h2d_bytes_per_step": int(S * n * 2), "steps": steps, "timing": "host clock around synchronous calls",
+           "p1_frames_per_channel": len(p1),
+           "workload": f"{S} synthetic AM MA1 channels x {F} L1 frames (cs16), reset -> push -> process -> drain; "
+                       "k_am: one warp per stream (first, unoptimised AM path)"}
     print(json.dumps(out), flush=True)
     e.close()
 
@@ -310,6 +366,9 @@ def main():
         return
     if args.l2_leg:
         l2_leg(args)
+        return
+    if args.am_leg:
+        am_leg(args)
         return
 
     import torch
@@ -523,6 +582,19 @@ def main():
         except Exception as ex:                                    # noqa: BLE001 - the leg must not take the headline down
             l2 = {"error": repr(ex)[:400]}
 
+    # ---- AM, BASELINE config 4 (separate process, rank 0, N=1 only) ----
+    am = None
+    if rank == 0 and world == 1 and not args.no_am:
+        import subprocess
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--am-leg", "--am-streams", str(args.am_streams),
+                                "--am-frames", str(args.am_frames), "--steps", str(args.steps)],
+                               capture_output=True, text=True, timeout=420)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            am = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as ex:                                    # noqa: BLE001
+            am = {"error": repr(ex)[:400]}
+
     if rank == 0:
         line = {
             "metric": "cu8 I/Q Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -537,6 +609,8 @@ def main():
             line["cpu_baseline"] = cpu
         if l2:
             line["l2_on_device"] = l2
+        if am:
+            line["am_config4"] = am
         print(json.dumps(line), flush=True)
     e.close()
     if use_dist:

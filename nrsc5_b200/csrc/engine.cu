@@ -1746,21 +1746,26 @@ extern "C" long nrsc5b_l2_frames(int device, const uint8_t *frames, size_t nbyte
     uint8_t *df = nullptr, *dout = nullptr;
     uint32_t *dd = nullptr;
     unsigned *dlen = nullptr;
-    CK(cudaMalloc(&st, sizeof(nbl2::L2State)));
-    CK(cudaMalloc(&df, nbytes + 16));
-    CK(cudaMalloc(&dd, desc.size() * sizeof(uint32_t)));
-    CK(cudaMalloc(&dout, cap));
-    CK(cudaMalloc(&dlen, 2 * sizeof(unsigned)));
-    CK(cudaMemset(dlen, 0, 2 * sizeof(unsigned)));
-    CK(cudaMemcpy(df, frames, nbytes, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dd, desc.data(), desc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    k_l2_init<<<1, 256>>>(st, -1);
-    k_l2_test<<<1, nbl2::L2_THREADS>>>(st, df, dd, nd, dout, cap, dlen);
-    CK(cudaGetLastError());
     unsigned lo[2] = { 0, 0 };
-    CK(cudaMemcpy(lo, dlen, sizeof(lo), cudaMemcpyDeviceToHost));
-    if (lo[0]) CK(cudaMemcpy(out, dout, lo[0], cudaMemcpyDeviceToHost));
-    cudaFree(st); cudaFree(df); cudaFree(dd); cudaFree(dout); cudaFree(dlen);
+    auto run = [&]() -> int {
+        CK(cudaMalloc(&st, sizeof(nbl2::L2State)));
+        CK(cudaMalloc(&df, nbytes + 16));
+        CK(cudaMalloc(&dd, desc.size() * sizeof(uint32_t)));
+        CK(cudaMalloc(&dout, cap));
+        CK(cudaMalloc(&dlen, 2 * sizeof(unsigned)));
+        CK(cudaMemset(dlen, 0, 2 * sizeof(unsigned)));
+        CK(cudaMemcpy(df, frames, nbytes, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dd, desc.data(), desc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        k_l2_init<<<1, 256>>>(st, -1);
+        k_l2_test<<<1, nbl2::L2_THREADS>>>(st, df, dd, nd, dout, cap, dlen);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(lo, dlen, sizeof(lo), cudaMemcpyDeviceToHost));
+        if (lo[0]) CK(cudaMemcpy(out, dout, lo[0], cudaMemcpyDeviceToHost));
+        return NRSC5B_OK;
+    };
+    rc = run();
+    cudaFree(st); cudaFree(df); cudaFree(dd); cudaFree(dout); cudaFree(dlen);      // also on the error paths
+    if (rc) return rc;
     if (needed) *needed = lo[0];
     return lo[1] ? (long)NRSC5B_EFULL : (long)lo[0];
 }
