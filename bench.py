@@ -573,7 +573,6 @@ def main():
     # ---- L2 framing on the device: separate leg, separate process (rank 0, N=1 only) ----
     l2 = None
     if rank == 0 and world == 1 and not args.no_l2:
-        import subprocess
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--l2-leg", "--streams", str(S), "--frames", str(args.frames),
                                 "--steps", str(args.steps)], capture_output=True, text=True, timeout=600)
@@ -585,7 +584,6 @@ def main():
     # ---- AM, BASELINE config 4 (separate process, rank 0, N=1 only) ----
     am = None
     if rank == 0 and world == 1 and not args.no_am:
-        import subprocess
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--am-leg", "--am-streams", str(args.am_streams),
                                 "--am-frames", str(args.am_frames), "--steps", str(args.steps)],
