@@ -116,7 +116,8 @@ typedef struct {
 int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg);
 void nrsc5b_destroy(nrsc5b_engine_t *e);
 int nrsc5b_reset(nrsc5b_engine_t *e, int stream);          /* stream < 0: all */
-/* Restart every stream from sample 0 of the input it already holds (benchmark loops). */
+/* Restart every stream (FM or AM; receiver and L2 state start over) from sample 0 of the input it already holds
+ * (benchmark loops). */
 int nrsc5b_rewind(nrsc5b_engine_t *e);
 
 /* Use this CUDA stream (a cudaStream_t cast to void*) for all engine work; NULL = legacy default. */

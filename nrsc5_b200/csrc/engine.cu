@@ -1043,6 +1043,16 @@ extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
     k_reset<<<e->dims.nstreams, 256, 0, e->stream>>>(e->dp, e->dims, -2);
     if (e->l2) k_l2_init<<<e->dims.nstreams, 256, 0, e->stream>>>(e->l2, -1);
     e->stats.kernel_launches += 1;
+    if (e->am_st) {                                        // AM: the receiver state lives in AmState / AmWork
+        nbam::AmState z;
+        memset(&z, 0, sizeof(z));
+        nbam::am_reset_state(z);
+        for (int s = 0; s < e->dims.nstreams; s++) {
+            CK(cudaMemcpyAsync(e->am_st + s, &z, sizeof(z), cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemsetAsync(e->am_work + s, 0, sizeof(nbam::AmWork), e->stream));
+        }
+        CK(cudaStreamSynchronize(e->stream));              // `z` lives on this stack frame
+    }
     for (int s = 0; s < e->dims.nstreams; s++) e->drained[s] = 0;
     CK(cudaGetLastError());
     return NRSC5B_OK;

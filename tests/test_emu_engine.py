@@ -71,6 +71,7 @@ test_l2_frames_of_sample_xz = _l2.test_l2_frames_of_sample_xz
 test_chain_with_l2_on_device = _l2.test_chain_with_l2_on_device
 test_mp3_chain_l2_records_follow_their_frames = _l2.test_mp3_chain_l2_records_follow_their_frames
 test_am_chain_with_l2_on_device = _l2.test_am_chain_with_l2_on_device
+test_am_rewind_repeats_the_decode = _l2.test_am_rewind_repeats_the_decode
 test_mp3_chain_with_l2_content_in_p3_frames = _l2.test_mp3_chain_with_l2_content_in_p3_frames
 test_service_mode_chain_l2_call_order = _l2.test_service_mode_chain_l2_call_order
 # awkward inputs

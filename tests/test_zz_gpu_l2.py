@@ -254,3 +254,21 @@ def test_mp3_chain_with_l2_content_in_p3_frames():
     p3 = [r["bits"] for t, r in recs if t == 1 and r["lc"] == 1]
     assert len(p3) >= 12 and all(b in {f[2] for f in src} for b in p3)      # decoded P3 frames = generated ones
     assert sum(1 for t, _ in got if t == 19) > 30 and sum(1 for t, _ in got if t == 16) >= 4
+
+
+def test_am_rewind_repeats_the_decode():
+    """nrsc5b_rewind on an AM engine: the receiver state (AmState / AmWork, and the L2 state) starts over on the
+    samples the engine already holds; the second pass writes the same records as the first."""
+    from nrsc5_b200 import synth_am
+    cap = synth_am.make_am_ma1(nframes=9, seed=3, lead_in=500)
+    with eng.Engine(nstreams=2, input_capacity=4 * cap.cs16.size + 4096, log_capacity=1 << 20, mode="am") as e:
+        e.enable_l2()
+        e.push_cs16(0, cap.cs16)
+        e.push_cs16(1, cap.cs16[:cap.cs16.size // 2 & ~1])
+        e.process()
+        first = [e.drain_raw(0), e.drain_raw(1)]
+        e.rewind()
+        e.process()
+        second = [e.drain_raw(0), e.drain_raw(1)]
+    assert first == second and len(first[0]) > len(first[1]) > 0
+    assert sum(1 for t, _ in eng.parse_records(first[0]) if t == eng.REC_L2) >= 8
