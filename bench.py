@@ -59,6 +59,10 @@ def parse_args():
     ap.add_argument("--l2-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-am", action="store_true", help="skip the AM leg (BASELINE config 4)")
     ap.add_argument("--am-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-mp3", action="store_true", help="skip the MP3 leg (BASELINE config 3)")
+    ap.add_argument("--mp3-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--mp3-streams", type=int, default=64)
+    ap.add_argument("--mp3-frames", type=int, default=6)
     ap.add_argument("--am-streams", type=int, default=256)
     ap.add_argument("--am-frames", type=int, default=12)
     return ap.parse_args()
@@ -171,6 +175,56 @@ def l2_leg(args):
     e.close()
 
 
+def mp3_leg(args):
+    """BASELINE config 3: `--mp3-streams` synthetic FM MP3 (extended hybrid) channels, `--mp3-frames` L1 frames each,
+    batched on one GPU: P1, PIDS and the P3 frames of the PX1 partitions (interleaver IV) decoded from reset.
+    `value`: samples resident in HBM (nrsc5b_rewind -> process); `e2e`: reset -> push -> process -> drain.  Host
+    clock around synchronous calls.  Run by the main bench in a subprocess (rank 0, N=1); prints one JSON object."""
+    import nrsc5_b200
+    from nrsc5_b200 import engine as eng, synth
+    S, F = args.mp3_streams, args.mp3_frames
+    caps = [synth.make_fm_mp3(nframes=F, seed=11 + i, lead_in=0, tail_blocks=2, cfo_hz=(0.0, 80.0)[i % 2]).cu8 for i in range(2)]
+    views, nbytes = stream_views(caps, S, 0)
+    views = [np.ascontiguousarray(v) for v in views]
+    log_cap = (F + 1) * (18272 + 64) + 8 * F * (576 + 32) + 128 * 1024
+    e = nrsc5_b200.Engine(nstreams=S, input_capacity=nbytes + 4096, log_capacity=log_cap)
+
+    def step():
+        t0 = time.perf_counter()
+        e.reset()
+        for s in range(S):
+            e.push_cu8(s, views[s])
+        e.process()
+        recs = e.drain_all()
+        return time.perf_counter() - t0, recs
+
+    _, recs = step()
+    nf = [(sum(1 for t, r in rr if t == eng.REC_FRAME and r["lc"] == 0), sum(1 for t, r in rr if t == eng.REC_FRAME and r["lc"] == 1))
+          for rr in recs]
+    assert nf[0][0] >= F - 1 and nf[0][1] >= 8 * (F - 2) - 2, nf[0]         # P3 output starts after two frames of interleaver fill
+    assert all(x == nf[i % 2] for i, x in enumerate(nf)), "channels that carry the same capture decoded different frame counts"
+    steps = max(2, min(args.steps, 3))
+    tot = sum(step()[0] for _ in range(steps))
+    res = 0.0
+    for _ in range(steps):
+        e.rewind()
+        t0 = time.perf_counter()
+        e.process()
+        res += time.perf_counter() - t0
+    again = e.drain_all()
+    assert [sum(1 for t, _ in r if t == eng.REC_FRAME) for r in again] == [a + b for a, b in nf]
+    samples = S * (nbytes // 2)
+    out = {"value": samples * steps / res / 1e6, "unit": "Msamples/s", "x_realtime": samples * steps / res / SAMPLE_RATE,
+           "ms_per_step": 1e3 * res / steps,
+           "e2e": {"value": samples * steps / tot / 1e6, "ms_per_step": 1e3 * tot / steps, "x_realtime": samples * steps / tot / SAMPLE_RATE,
+                   "h2d_bytes_per_step": int(S * nbytes), "what": "reset -> nrsc5b_push_cu8 per channel from host memory -> process -> drain_all"},
+           "steps": steps, "timing": "host clock around synchronous calls (the engine waits for its kernels)",
+           "p1_frames_per_channel": nf[0][0], "p3_frames_per_channel": nf[0][1],
+           "workload": f"{S} synthetic FM MP3 channels x {F} L1 frames (+2 blocks), cu8, full chain to P1 / PIDS / P3 PDUs"}
+    print(json.dumps(out), flush=True)
+    e.close()
+
+
 def am_leg(args, engine_factory=None):
     """BASELINE config 4: `--am-streams` synthetic AM MA1 channels (cs16 at 46 511.72 S/s, `--am-frames` L1 frames
     each) on one GPU, decoded from reset to L1 PDUs by the AM engine (one warp per stream, first unoptimised path).
@@ -204,7 +258,7 @@ def am_leg(args, engine_factory=None):
     assert len(p1) >= 8 * (F - 8), f"{len(p1)} AM P1 frames decoded from {F} transmitted L1 frames"
     assert all(sum(1 for t, _ in r if t == eng.REC_FRAME) == sum(1 for t, _ in recs[s % 2] if t == eng.REC_FRAME)
                for s, r in enumerate(recs)), "channels that carry the same capture decoded different frame counts"
-    steps = max(2, min(args.steps, 5))
+    steps = max(2, min(args.steps, 3))
     tot = proc = 0.0
     for _ in range(steps):
         a, b, _ = step()
@@ -379,6 +433,9 @@ def main():
         return
     if args.am_leg:
         am_leg(args)
+        return
+    if args.mp3_leg:
+        mp3_leg(args)
         return
 
     import torch
@@ -603,6 +660,18 @@ def main():
         except Exception as ex:                                    # noqa: BLE001
             am = {"error": repr(ex)[:400]}
 
+    # ---- FM MP3, BASELINE config 3 (separate process, rank 0, N=1 only) ----
+    mp3 = None
+    if rank == 0 and world == 1 and not args.no_mp3:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--mp3-leg", "--mp3-streams", str(args.mp3_streams),
+                                "--mp3-frames", str(args.mp3_frames), "--steps", str(args.steps)],
+                               capture_output=True, text=True, timeout=420)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            mp3 = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as ex:                                    # noqa: BLE001
+            mp3 = {"error": repr(ex)[:400]}
+
     if rank == 0:
         line = {
             "metric": "cu8 I/Q Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -619,6 +688,8 @@ def main():
             line["l2_on_device"] = l2
         if am:
             line["am_config4"] = am
+        if mp3:
+            line["mp3_config3"] = mp3
         print(json.dumps(line), flush=True)
     e.close()
     if use_dist:
