@@ -199,17 +199,17 @@ __device__ inline uint8_t *log_reserve(const DevPtrs &p, const EngineDims &d, in
     return w + 8;
 }
 
-// hands a frame (or, with nbits == 0, a frame_reset) to the L2 kernel that ends the pass
-__device__ inline void l2_enqueue(StreamState &st, const EngineDims &d, const DevPtrs &p, int s, const uint8_t *bits,
-                                  unsigned lc, unsigned nbits)
+// hands a frame (off = log offset of its packed bits, 0xffffffff when the log was full) or, with nbits == 0, a
+// frame_reset to the L2 kernel that ends the pass
+__device__ __forceinline__ void l2_enqueue(StreamState &st, int l2_on, unsigned off, unsigned lc, unsigned nbits)
 {
-    if (!d.l2) return;
+    if (!l2_on) return;
     if (st.l2_n >= L2_QUEUE) {                 // cannot happen with 16 blocks per pass; the host is told if it does
         st.log_overflow = 1;
         return;
     }
     const int e = st.l2_n++;
-    st.l2_off[e] = bits ? (unsigned)(bits - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
+    st.l2_off[e] = off;
     st.l2_lc[e] = lc;
     st.l2_nbits[e] = nbits;
 }

@@ -725,7 +725,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     st.bc = mbc;
                     st.psmi = mps;
                     set_state(p, d, s, ST_FINE);
-                    l2_enqueue(st, d, p, s, nullptr, 0, 0);   // frame_reset (sync.c:405-409)
+                    l2_enqueue(st, d.l2, 0u, 0, 0);            // frame_reset (sync.c:405-409)
                     st.started_pm = 0;                   // decode_reset (decode.c:556-565)
                     st.px_total = 0;
                     st.px_started = 0;
@@ -1078,7 +1078,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     reinterpret_cast<uint32_t *>(fw)[0] = 0;            // P1 logical channel
                     reinterpret_cast<uint32_t *>(fw)[1] = P1_LEN;
                 }
-                l2_enqueue(st, d, p, s, fw ? fw + 8 : nullptr, 0, P1_LEN);
+                l2_enqueue(st, d.l2, st.p1_rec != 0xffffffffu ? st.p1_rec + 4 + 8 + 8 : 0xffffffffu, 0, P1_LEN);   // BER payload | FRAME header | lc, nbits | bits
                 st.p1_ready = 1;
             }
             // P3 / P4 bookkeeping (decode_push_px1 / _px2, decode.c:393-437): every second block closes a span of the
@@ -1099,7 +1099,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                             reinterpret_cast<uint32_t *>(fw)[0] = 1;        // P3 logical channel
                             reinterpret_cast<uint32_t *>(fw)[1] = P3_LEN;
                         }
-                        l2_enqueue(st, d, p, s, fw ? fw + 8 : nullptr, 1, P3_LEN);
+                        l2_enqueue(st, d.l2, fw ? st.p3_rec[e3] + 8 : 0xffffffffu, 1, P3_LEN);
                         st.p3_pending = e3 + 1;
                     }
                     if ((bc & 1) && cm == 2 && k0 >= IV_NS && st.xq_pending[0] < P3_SLOTS) {
@@ -1111,7 +1111,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                             reinterpret_cast<uint32_t *>(fw)[0] = 1;        // P3 logical channel
                             reinterpret_cast<uint32_t *>(fw)[1] = P3S_LEN;
                         }
-                        l2_enqueue(st, d, p, s, fw ? fw + 8 : nullptr, 1, P3S_LEN);
+                        l2_enqueue(st, d.l2, fw ? st.xq_rec[0][e3] + 8 : 0xffffffffu, 1, P3S_LEN);
                         st.xq_pending[0] = e3 + 1;
                     }
                 }
@@ -1130,7 +1130,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                             reinterpret_cast<uint32_t *>(fw)[0] = 2;        // P4 logical channel
                             reinterpret_cast<uint32_t *>(fw)[1] = P3_LEN;
                         }
-                        l2_enqueue(st, d, p, s, fw ? fw + 8 : nullptr, 2, P3_LEN);
+                        l2_enqueue(st, d.l2, fw ? st.xq_rec[1][e4] + 8 : 0xffffffffu, 2, P3_LEN);
                         st.xq_pending[1] = e4 + 1;
                     }
                 }
