@@ -82,7 +82,7 @@ struct EvWriter {
 __device__ inline uint8_t *ev_put(EvWriter &w, uint32_t type, const void *a, unsigned alen, const uint8_t *b, unsigned blen)
 {
     const unsigned plen = alen + blen, need = 8 + ((plen + 3) & ~3u);
-    if (w.len + need > (unsigned)L2_EV_CAP) {
+    if (w.overflow || w.len + need > (unsigned)L2_EV_CAP) {          // once full, stay full: the record keeps a prefix of the calls
         w.overflow = 1;
         return nullptr;
     }

@@ -82,3 +82,32 @@ def malformed_sequences():
             pdu[:96] = head
         b.append((1, 4608, g.frame_from_pdu(g.fill_pdu(rng, [bytes(pdu)], n), 4608, g.PCI_AUDIO)))
     return {"ccc_overlong": a, "hef_past_la": b}
+
+
+def stress_sequences():
+    """PDU sequences that reach the rarely taken branches of the L2 kernel (the reference handles all of them, so the
+    oracle stays pinned to it): more packets in one frame than the kernel's shared-memory packet table holds (1024;
+    thread 0 then checks the CRC-8 itself), a PSD byte stream that overruns the 8212-byte HDLC buffer before the next
+    flag (frame.c:381-386), and - `ev_overflow` - more events than the kernel's per-frame staging area holds."""
+    import numpy as np
+    from nrsc5_b200 import synth_l2 as g
+    n = g.pdu_len(146176)
+
+    def frame(rng, npdus, psd_of, npk=63):
+        parts = [g.audio_pdu(rng, [1] * npk, codec=0, stream=0, seq=k & 63, psd=psd_of(k)) for k in range(npdus)]
+        return (0, 146176, g.frame_from_pdu(g.fill_pdu(rng, parts, n), 146176, g.PCI_AUDIO))
+
+    out = {}
+    rng = np.random.default_rng(5)
+    out["many_packets"] = [None] + [frame(rng, 36, lambda k: b"") for _ in range(2)]
+    rng = np.random.default_rng(6)
+    filler = bytes(b for b in rng.integers(0, 256, 260, dtype=np.uint8).tobytes() if b != 0x7E)[:210]
+    msg = g.hdlc_frame(bytes([0x21]) + bytes(range(40)))
+    # frame 0: a flag, then 60 PDUs x 210 flag-free PSD bytes = 12 600 > 8212: the buffer overruns and the scanner
+    # waits for the next flag; frame 1: messages again
+    out["hdlc_overrun"] = [None,
+                           frame(rng, 60, lambda k: (b"\x7e" if k == 0 else b"") + filler, npk=10),
+                           frame(rng, 40, lambda k: msg, npk=10)]
+    rng = np.random.default_rng(7)
+    out["ev_overflow"] = [None, frame(rng, 60, lambda k: b"")]
+    return out

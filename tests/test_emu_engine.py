@@ -67,6 +67,7 @@ test_pids_crc_verdicts_on_valid_frames = _chain.test_pids_crc_verdicts_on_valid_
 test_l2_frames_equal_oracle = _l2.test_l2_frames_equal_oracle
 test_l2_frames_mutated_equal_oracle = _l2.test_l2_frames_mutated_equal_oracle
 test_l2_malformed_pdus_stay_in_bounds = _l2.test_l2_malformed_pdus_stay_in_bounds
+test_l2_rare_branches = _l2.test_l2_rare_branches
 test_l2_frames_of_sample_xz = _l2.test_l2_frames_of_sample_xz
 test_chain_with_l2_on_device = _l2.test_chain_with_l2_on_device
 test_mp3_chain_l2_records_follow_their_frames = _l2.test_mp3_chain_l2_records_follow_their_frames

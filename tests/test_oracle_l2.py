@@ -5,7 +5,7 @@ import pytest
 import port
 import reftap
 from common import golden, load_sample
-from l2_cases import AM_BITS, L2_CASES, l2_digest, mutated_sequence
+from l2_cases import AM_BITS, L2_CASES, l2_digest, mutated_sequence, stress_sequences
 from nrsc5_b200 import synth_l2
 
 L2_TYPES = (1, 16, 17, 18, 19)
@@ -62,3 +62,14 @@ def test_l2_oracle_equals_reference_under_mutation(block):
         ref = reftap.l2_frames(frames, mode=1 if am else 0)
         orc, _ = port.l2_frames(frames)
         assert ref.records == orc.records, trial
+
+
+@pytest.mark.parametrize("name", ["many_packets", "hdlc_overrun", "ev_overflow"])
+def test_l2_oracle_equals_reference_on_stress_sequences(name):
+    """Thousands of one-byte packets per frame; a PSD stream that overruns the 8212-byte HDLC buffer (frame.c:381-386)."""
+    if not reftap.available():
+        pytest.skip("reference library not built")
+    frames = stress_sequences()[name]
+    ref = reftap.l2_frames(frames)
+    orc, _ = port.l2_frames(frames)
+    assert ref.records == orc.records and sum(1 for t, _ in orc.records if t == 19) >= 1000

@@ -11,7 +11,7 @@ import pytest
 
 import port
 from common import FM_MODE_CASES, MP3_CASE, SYNTH_CASES, golden, load_sample
-from l2_cases import L2_CASES, l2_digest, malformed_sequences, mutated_sequence
+from l2_cases import L2_CASES, l2_digest, malformed_sequences, mutated_sequence, stress_sequences
 from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth, synth_l2
 
@@ -272,3 +272,20 @@ def test_am_rewind_repeats_the_decode():
         second = [e.drain_raw(0), e.drain_raw(1)]
     assert first == second and len(first[0]) > len(first[1]) > 0
     assert sum(1 for t, _ in eng.parse_records(first[0]) if t == eng.REC_L2) >= 8
+
+
+@pytest.mark.parametrize("name", ["many_packets", "hdlc_overrun", "ev_overflow"])
+def test_l2_rare_branches(name):
+    """More packets per frame (2268) than the kernel's packet table holds (thread 0 checks those CRCs itself), an HDLC
+    buffer overrun, and more events than the per-frame staging area holds: the first two equal the oracle (which
+    equals the reference on them); the third sets L2F_EV_OVERFLOW and keeps a prefix of the calls."""
+    frames = stress_sequences()[name]
+    recs = eng.l2_frames(frames)
+    orc, _ = port.l2_frames(frames)
+    got = expand(recs, frames)
+    if name != "ev_overflow":
+        assert got == orc.records and not any(r["flags"] & eng.L2F_EV_OVERFLOW for r in recs)
+        assert max(sum(1 for t, _ in r["events"] if t == eng.EV_PACKET) for r in recs) >= (2268 if name == "many_packets" else 400)
+    else:
+        assert recs[0]["flags"] & eng.L2F_EV_OVERFLOW
+        assert 2000 < len(got) < len(orc.records) and got == orc.records[:len(got)]
