@@ -199,10 +199,11 @@ def mp3_leg(args):
         return time.perf_counter() - t0, recs
 
     _, recs = step()
+    gate = parity_gate(views, recs, what="mp3_config3")           # every channel: P1 / PIDS / P3 PDUs in order == oracle
     nf = [(sum(1 for t, r in rr if t == eng.REC_FRAME and r["lc"] == 0), sum(1 for t, r in rr if t == eng.REC_FRAME and r["lc"] == 1))
           for rr in recs]
     assert nf[0][0] >= F - 1 and nf[0][1] >= 8 * (F - 2) - 2, nf[0]         # P3 output starts after two frames of interleaver fill
-    assert all(x == nf[i % 2] for i, x in enumerate(nf)), "channels that carry the same capture decoded different frame counts"
+    first = [record_digest(r) for r in recs]
     steps = max(2, min(args.steps, 3))
     tot = sum(step()[0] for _ in range(steps))
     res = 0.0
@@ -212,14 +213,14 @@ def mp3_leg(args):
         e.process()
         res += time.perf_counter() - t0
     again = e.drain_all()
-    assert [sum(1 for t, _ in r if t == eng.REC_FRAME) for r in again] == [a + b for a, b in nf]
+    assert [record_digest(r) for r in again] == first, "rewind -> process gave other records than reset -> push -> process"
     samples = S * (nbytes // 2)
     out = {"value": samples * steps / res / 1e6, "unit": "Msamples/s", "x_realtime": samples * steps / res / SAMPLE_RATE,
            "ms_per_step": 1e3 * res / steps,
            "e2e": {"value": samples * steps / tot / 1e6, "ms_per_step": 1e3 * tot / steps, "x_realtime": samples * steps / tot / SAMPLE_RATE,
                    "h2d_bytes_per_step": int(S * nbytes), "what": "reset -> nrsc5b_push_cu8 per channel from host memory -> process -> drain_all"},
            "steps": steps, "timing": "host clock around synchronous calls (the engine waits for its kernels)",
-           "p1_frames_per_channel": nf[0][0], "p3_frames_per_channel": nf[0][1],
+           "p1_frames_per_channel": nf[0][0], "p3_frames_per_channel": nf[0][1], "parity_gate": gate,
            "workload": f"{S} synthetic FM MP3 channels x {F} L1 frames (+2 blocks), cu8, full chain to P1 / PIDS / P3 PDUs"}
     print(json.dumps(out), flush=True)
     e.close()
@@ -256,8 +257,8 @@ def am_leg(args, engine_factory=None):
     _, _, recs = step()                                   # warm-up + gate
     p1 = [r for t, r in recs[0] if t == eng.REC_FRAME and r["lc"] == 0]
     assert len(p1) >= 8 * (F - 8), f"{len(p1)} AM P1 frames decoded from {F} transmitted L1 frames"
-    assert all(sum(1 for t, _ in r if t == eng.REC_FRAME) == sum(1 for t, _ in recs[s % 2] if t == eng.REC_FRAME)
-               for s, r in enumerate(recs)), "channels that carry the same capture decoded different frame counts"
+    gate = parity_gate(views, recs, am=True, what="am_config4")   # every channel: P1 / P3 / PIDS PDUs in order == oracle
+    first = [record_digest(r) for r in recs]
     steps = max(2, min(args.steps, 3))
     tot = proc = 0.0
     for _ in range(steps):
@@ -272,7 +273,7 @@ def am_leg(args, engine_factory=None):
         e.process()
         res += time.perf_counter() - t0
     again = e.drain_all()
-    assert [sum(1 for t, _ in r if t == eng.REC_FRAME) for r in again] == [sum(1 for t, _ in r if t == eng.REC_FRAME) for r in recs]
+    assert [record_digest(r) for r in again] == first, "rewind -> process gave other records than reset -> push -> process"
     samples = S * (n // 2)
     out = {"value": samples * steps / res / 1e6, "unit": "Msamples/s (cs16 complex, 46 511.72 S/s per channel)",
            "x_realtime": samples * steps / res / 46511.71875, "ms_per_step": 1e3 * res / steps,
@@ -280,7 +281,7 @@ def am_leg(args, engine_factory=None):
                    "process_ms_per_step": 1e3 * proc / steps, "h2d_bytes_per_step": int(S * n * 2),
                    "what": "reset -> nrsc5b_push_cs16 per channel from host memory -> process -> drain_all"},
            "steps": steps, "timing": "host clock around synchronous calls (the engine waits for its kernels)",
-           "p1_frames_per_channel": len(p1),
+           "p1_frames_per_channel": len(p1), "parity_gate": gate,
            "workload": f"{S} synthetic AM MA1 channels x {F} L1 frames (cs16), value: samples resident in HBM "
                        "(rewind -> process); k_am: one warp per stream (first, unoptimised AM path)"}
     print(json.dumps(out), flush=True)
@@ -299,6 +300,60 @@ def stream_views(caps, nstreams: int, rank: int):
         off = 4 * ((37 * (g // D)) % 1080)
         views.append(caps[g % D][off: off + n])
     return views, n
+
+
+# ---------------------------------------------------------------------------
+# parity gate: every stream of a timed workload against the CPU oracle (checker only - never timed, never shipped)
+# ---------------------------------------------------------------------------
+def record_digest(recs):
+    """Order-preserving digest of a parsed record stream: (kind, lc, nbits, crc32 of the packed bits) for every L1 PDU."""
+    import zlib
+    out = []
+    for t, r in recs:
+        if t == 1:                                    # REC_FRAME (P1 / P3 / P4)
+            out.append(("F", r["lc"], r["nbits"], zlib.crc32(r["bits"])))
+        elif t == 2:                                  # REC_PIDS
+            out.append(("P", 0, 80, zlib.crc32(r["bits"])))
+        elif t == 3:
+            out.append(("S", r["psmi"], 0, 0))
+        elif t == 4:
+            out.append(("L", 0, 0, 0))
+    return out
+
+
+def oracle_digests(views, am=False, workers=None):
+    """The same digests from the CPU oracle for every view (the unmodified reference when oracle/_ref holds it, else
+    the restatement), one decode per DISTINCT view, on a thread pool (the C code releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import port
+    # oracle/nrsc5_oracle*.c (one decoder object per call, so the calls can run on threads); it is pinned record for
+    # record to the unmodified reference by tests/test_oracle*.py
+    dec = port.decode_am if am else port.decode
+    keys, distinct = [], {}
+    for v in views:
+        k = (v.__array_interface__["data"][0], v.size)
+        keys.append(k)
+        distinct.setdefault(k, v)
+    items = list(distinct.items())
+    with ThreadPoolExecutor(max_workers=workers or min(64, os.cpu_count() or 1)) as ex:
+        res = list(ex.map(lambda kv: record_digest(dec(np.ascontiguousarray(kv[1])).records), items))
+    by_key = {k: r for (k, _), r in zip(items, res)}
+    return [by_key[k] for k in keys], "port (oracle/nrsc5_oracle*.c, pinned to the unmodified reference)", len(items)
+
+
+def parity_gate(views, recs_per_stream, am=False, what=""):
+    """Asserts that every stream's L1 PDUs (P1 / P3 / P4 / PIDS, in order, with the sync events) are the oracle's."""
+    want, kind, ndistinct = oracle_digests(views, am=am)
+    npdu = 0
+    for s, (recs, w) in enumerate(zip(recs_per_stream, want)):
+        got = record_digest(recs)
+        if got != w:
+            k = next((i for i, (a, b) in enumerate(zip(got, w)) if a != b), min(len(got), len(w)))
+            raise AssertionError(f"{what}: stream {s} differs from the {kind} oracle at record {k}: "
+                                 f"engine {got[k:k + 2]} ({len(got)} records) vs oracle {w[k:k + 2]} ({len(w)})")
+        npdu += sum(1 for g in got if g[0] in "FP")
+    return {"ok": True, "streams_checked": len(views), "distinct_views": ndistinct, "pdus_compared": npdu, "oracle": kind}
 
 
 class ClockSampler:
@@ -537,11 +592,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), l1 - l0, clocks, out
 
-    # ---- correctness gate: PDUs of stream 0 must match what the generator put in ----
+    # ---- correctness gate: EVERY stream's L1 PDUs (P1 + PIDS, in order, with the sync events) must be the CPU
+    # ---- oracle's decode of the same view (rank 0: all streams; other ranks: their first 8, to bound host time)
     step_resident()
-    recs0 = e.drain(0)
-    n_p1 = sum(1 for t, _ in recs0 if t == eng.REC_FRAME)
-    assert n_p1 >= 1, "no P1 frame decoded in the bench workload"
+    recs_all = e.drain_all()
+    ncheck = S if rank == 0 else min(S, 8)
+    gate = parity_gate(views[:ncheck], recs_all[:ncheck], what="resident step")
+    resident_digests = [record_digest(r) for r in recs_all]
+    assert all(any(g[0] == "F" for g in d) for d in resident_digests), "a stream decoded no P1 frame"
 
     # ---- value: device-resident ----
     ms, launches, clocks, _ = timed(step_resident, args.steps, max(args.warmup, 3))
@@ -598,6 +656,10 @@ def main():
     if not args.no_e2e:
         ms2, _, _, out = timed(step_e2e, args.steps, max(args.warmup, 3))
         d2h = out[0] if out else 0
+        # the records of the last timed e2e step (host buffers, chunked pushes) must be the resident step's, stream by stream
+        e2e_digests = [record_digest(eng.parse_records(f.tobytes())) for f in out[1]]
+        assert e2e_digests == resident_digests, "e2e records differ from the device-resident step's"
+        gate["e2e_equals_resident"] = True
         e2e_val = total_samples / (ms2 * 1e-3) / 1e6
         # the PCIe floor of this box: the same bytes as one pinned host->device copy, nothing else
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -678,7 +740,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int16/f32", "data": "synthetic", "config": workload_config(args, nbytes),
             "x_realtime": value * 1e6 / SAMPLE_RATE, "x_realtime_per_gpu": value * 1e6 / SAMPLE_RATE / world,
-            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "parity_gate": gate,
         }
         if e2e:
             line["e2e"] = e2e

@@ -74,6 +74,7 @@ enum {
     NRSC5B_ENOMEM = -3,
     NRSC5B_ECUDA = -4,
     NRSC5B_EFULL = -5,    /* input buffer of that stream cannot take the push */
+    NRSC5B_EOVERFLOW = -6, /* nrsc5b_drain_all: delivered, but at least one stream's log had overflowed (see nrsc5b_take_overflow) */
 };
 
 enum {
@@ -155,6 +156,10 @@ long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_t cap, size
 /* nrsc5b_drain for every stream in one call: stream s's records land at out + s*out_stride, sizes[s] bytes.
  * Returns NRSC5B_EFULL (and drains nothing) if a stream's records exceed out_stride. */
 int nrsc5b_drain_all(nrsc5b_engine_t *e, uint8_t *out, size_t out_stride, size_t *sizes);
+/* 1 if a drain of `stream` since the last call found its log truncated (log_capacity too small for what the stream
+ * produced between two drains: the records handed out are a prefix), else 0.  Reading clears it.  Draining rewinds
+ * the log and clears the device-side flag, so every truncated drain is reported exactly once. */
+int nrsc5b_take_overflow(nrsc5b_engine_t *e, int stream);
 /* Wait for the GPU without draining. */
 int nrsc5b_synchronize(nrsc5b_engine_t *e);
 
@@ -166,6 +171,7 @@ typedef struct {
     uint64_t p1_frames;       /* P1 frames decoded                              */
     uint64_t kernel_launches; /* kernels launched by the engine                 */
     uint64_t p1_fallbacks;    /* P1 frames the fast Viterbi handed to the exact fallback kernels */
+    uint64_t log_overflows;   /* drains that found a stream's record log truncated */
 } nrsc5b_stats_t;
 int nrsc5b_get_stats(nrsc5b_engine_t *e, nrsc5b_stats_t *st);
 

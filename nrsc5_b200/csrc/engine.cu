@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     __shared__ int red[P1_THREADS];
     __shared__ int sh_last;
     __shared__ uint8_t hdr[96];
-    __shared__ uint8_t blk[255];
+    __shared__ GfTab gf;
     __shared__ uint32_t spread[256];
     spread[t] = c_spread3[t];
     __syncthreads();
@@ -170,28 +170,32 @@ __global__ void __launch_bounds__(P1_THREADS) k_p1_fin(DevPtrs p, EngineDims d)
     // last CTA of this stream: BER record, and the L2 feedback predicate
     // (frame.c:645-714 PCI, :146-156 has_audio, :527-541 header RS check)
     __threadfence();
+    gf_tab_load(gf, t, P1_THREADS);
     if (t < 96) {
         // PDU byte n of frame_push() is the bit-reversed packed byte n (the reference swaps the bit order per byte)
         unsigned v = frame ? __ldcg(frame + t) : 0;
         hdr[t] = (uint8_t)(__brev(v) >> 24);
     }
     __syncthreads();
-    if (t == 0) {
-        if (rec) *reinterpret_cast<float *>(rec) = (float)atomicAdd(&st.p1_errs, 0) / (float)P1_ENC;
-        unsigned pci = 0;
-        for (int h = 0; h < 24; h++) {
-            const unsigned i = 116176u + 1248u * h;
+    if (t < 32) {                                        // warp 0: the 24 PCI bits a lane each, the header by the warp's RS decoder
+        unsigned bit = 0;
+        if (t < 24) {
+            const unsigned i = 116176u + 1248u * t;
             const unsigned phys = (i & ~7u) + 7 - (i & 7);
-            const unsigned bit = (p1_bit(bw, (int)phys) ^ (p.pnw[phys >> 5] >> (phys & 31))) & 1u;
-            pci |= bit << (23 - h);
+            bit = ((p1_bit(bw, (int)phys) ^ (p.pnw[phys >> 5] >> (phys & 31))) & 1u) << (23 - t);
         }
+        const unsigned pci = warp_xor(bit);
         const bool has_audio = (pci & 0xFFFFFC) != (0x3634CE & 0xFFFFFC);
-        if (has_audio && !fix_header_96(hdr, blk)) set_state(p, d, s, ST_NONE);
-        if (st.p1_retry) st.p1_fallbacks++;
-        st.p1_ready = 0;
-        st.p1_slow = 0;
-        st.p1_retry = 0;
-        st.frames_done++;
+        const int ok = has_audio ? rs8_fix_header_warp(gf, hdr, t) : 1;
+        if (t == 0) {
+            if (rec) *reinterpret_cast<float *>(rec) = (float)atomicAdd(&st.p1_errs, 0) / (float)P1_ENC;
+            if (!ok) set_state(p, d, s, ST_NONE);
+            if (st.p1_retry) st.p1_fallbacks++;
+            st.p1_ready = 0;
+            st.p1_slow = 0;
+            st.p1_retry = 0;
+            st.frames_done++;
+        }
     }
 }
 
@@ -460,12 +464,13 @@ __global__ void k_viterbi_test(const int8_t *in, uint8_t *out, uint2 *dec, int l
 // ===========================================================================
 // AM (hybrid MA1): one warp per stream runs the chain of am.cuh over every complete 33-symbol window
 // ===========================================================================
+// every lane of k_am's warp holds the same 96 header bytes (am.cuh computes them redundantly) and all call this together
 struct AmFixHeader {
+    const GfTab *gf;
     __host__ __device__ int operator()(uint8_t *pdu) const
     {
-#if defined(__CUDA_ARCH__)
-        uint8_t blk[255];
-        return fix_header_96(pdu, blk);
+#if defined(__CUDA_ARCH__) || defined(NB_EMU)
+        return rs8_fix_header_warp(*gf, pdu, (int)(threadIdx.x & 31));
 #else
         (void)pdu;
         return 1;
@@ -478,9 +483,13 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
 {
     const int s = blockIdx.x;
     const nbam::Lanes L = { (int)threadIdx.x, 32 };
+    __shared__ GfTab gf;
+    gf_tab_load(gf, (int)threadIdx.x, 32);
+    __syncwarp();
     StreamState &fs = p.st[s];
     nbam::AmState st = ast[s];
-    st.log_len = fs.log_len;                               // the host rewinds the log when it drains it
+    st.log_len = fs.log_len;                               // the host rewinds the log when it drains it ...
+    st.log_overflow = fs.log_overflow;                     // ... and takes the overflow flag with it
     st.l2_on = d.l2;
     st.l2_n = 0;
     static_assert(nbam::AM_L2_QUEUE <= L2_QUEUE, "the L2 kernel reads the queue from StreamState");
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
     for (; nb_done < max_blocks; nb_done++) {
         const long long avail = *reinterpret_cast<volatile long long *>(&fs.in_avail) / 2;    // cs16 complex samples
         if (avail < st.start + nbam::NACQ) break;
-        nbam::process_window(st, aw[s], *tb, io, L, AmFixHeader());
+        nbam::process_window(st, aw[s], *tb, io, L, AmFixHeader{ &gf });
         __syncwarp();
     }
     __syncwarp();
@@ -523,10 +532,15 @@ __global__ void __launch_bounds__(256) k_am_decim(const uint8_t *ring, unsigned 
     nbam::decim_tile(ring, ring_bytes, raw_avail, k0 + first, n, out + first, sc, nbam::Lanes{ (int)threadIdx.x, (int)blockDim.x });
 }
 
-__global__ void k_rs_test(uint8_t *blocks, int *rc, int n)
+__global__ void k_rs_test(uint8_t *blocks, int *rc, int n)        // one warp per codeword
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) rc[i] = rs_decode_255_247(blocks + (size_t)i * 255);
+    __shared__ GfTab gf;
+    gf_tab_load(gf, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int r = rs8_decode_warp(gf, blocks + (size_t)i * 255, lane);
+    if (lane == 0) rc[i] = r;
 }
 
 // ===========================================================================
@@ -610,6 +624,7 @@ struct nrsc5b_engine {
     uint8_t *iq_owned;                 // engine-owned cu8 buffer (null when attached)
     std::vector<long long> pushed;     // complex cu8 samples pushed per stream
     std::vector<unsigned> drained;     // log bytes already handed out per stream
+    std::vector<uint8_t> overflowed;   // a drain found this stream's log truncated (until nrsc5b_take_overflow)
     uint8_t *trim_scratch;             // bounce buffer of trim_stream (allocated on first use)
     uint8_t *pinned;                   // staging for pushes
     size_t pinned_cap;
@@ -769,6 +784,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     }
     e->pushed.assign(S, 0);
     e->drained.assign(S, 0);
+    e->overflowed.assign(S, 0);
     int rc = upload_tables(cfg->device);
     if (rc) { delete e; return rc; }
 
@@ -847,6 +863,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         if (!rc && !cfg->input_cs16) {                      // cu8 at 1 488 375 S/s: decimated by 32 on arrival
             e->am_ring_bytes = 1u << 20;
             rc = dev_alloc(e, &e->am_ring, (size_t)S * e->am_ring_bytes);
+            if (rc) { delete tb; nrsc5b_destroy(e); return rc; }
             e->am_raw_bytes.assign(S, 0);
             e->am_dec_out.assign(S, 0);
         }
@@ -1511,12 +1528,19 @@ extern "C" long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_
         CK(cudaMemcpy(out, e->dp.log + (size_t)stream * e->dims.log_cap + e->drained[stream], avail,
                       cudaMemcpyDeviceToHost));
     }
-    // the log is rewound once fully drained
-    unsigned zero = 0;
-    CK(cudaMemcpy(reinterpret_cast<uint8_t *>(e->dp.st + stream) + offsetof(StreamState, log_len), &zero, sizeof(zero),
+    // the log is rewound once fully drained, and the overflow flag goes with it (log_len, log_overflow are adjacent)
+    static_assert(offsetof(StreamState, log_overflow) == offsetof(StreamState, log_len) + sizeof(unsigned), "cleared together");
+    const unsigned zero[2] = { 0, 0 };
+    CK(cudaMemcpy(reinterpret_cast<uint8_t *>(e->dp.st + stream) + offsetof(StreamState, log_len), zero, sizeof(zero),
                   cudaMemcpyHostToDevice));
     e->drained[stream] = 0;
-    if (st.log_overflow) fprintf(stderr, "nrsc5_b200: stream %d output log overflowed (raise log_capacity)\n", stream);
+    if (st.log_overflow) {
+        // the records handed out are a prefix of what the stream produced: told to the caller (nrsc5b_take_overflow,
+        // stats.log_overflows), once per truncated drain
+        e->overflowed[stream] = 1;
+        e->stats.log_overflows++;
+        fprintf(stderr, "nrsc5_b200: stream %d output log overflowed (raise log_capacity)\n", stream);
+    }
     return (long)avail;
 }
 
@@ -1536,16 +1560,32 @@ extern "C" int nrsc5b_drain_all(nrsc5b_engine_t *e, uint8_t *out, size_t out_str
         if (avail)
             CK(cudaMemcpyAsync(out + (size_t)s * out_stride, e->dp.log + (size_t)s * e->dims.log_cap + e->drained[s], avail,
                                cudaMemcpyDeviceToHost, e->stream));
-        if (e->h_state[s].log_overflow) fprintf(stderr, "nrsc5_b200: stream %d output log overflowed (raise log_capacity)\n", s);
     }
+    bool truncated = false;
     if (rc == NRSC5B_OK) {
-        // rewind every log (strided 4-byte writes of zero into the states)
+        // rewind every log and clear its overflow flag (strided 8-byte writes of zero into the states)
         CK(cudaMemset2DAsync(reinterpret_cast<uint8_t *>(e->dp.st) + offsetof(StreamState, log_len), sizeof(StreamState), 0,
-                             sizeof(unsigned), S, e->stream));
-        for (int s = 0; s < S; s++) e->drained[s] = 0;
+                             2 * sizeof(unsigned), S, e->stream));
+        for (int s = 0; s < S; s++) {
+            e->drained[s] = 0;
+            if (e->h_state[s].log_overflow) {
+                e->overflowed[s] = 1;
+                e->stats.log_overflows++;
+                truncated = true;
+                fprintf(stderr, "nrsc5_b200: stream %d output log overflowed (raise log_capacity)\n", s);
+            }
+        }
     }
     CK(cudaStreamSynchronize(e->stream));
-    return rc;
+    return rc ? rc : (truncated ? NRSC5B_EOVERFLOW : NRSC5B_OK);
+}
+
+extern "C" int nrsc5b_take_overflow(nrsc5b_engine_t *e, int stream)
+{
+    if (!e || stream < 0 || stream >= e->dims.nstreams) return NRSC5B_EINVAL;
+    const int v = e->overflowed[stream];
+    e->overflowed[stream] = 0;
+    return v;
 }
 
 extern "C" int nrsc5b_set_sync_state(nrsc5b_engine_t *e, int stream, int state)
@@ -1706,7 +1746,7 @@ extern "C" int nrsc5b_rs_decode(int device, uint8_t *blocks, int *rcs, int n)
     CK(cudaMalloc(&db, (size_t)n * 255));
     CK(cudaMalloc(&dr, (size_t)n * sizeof(int)));
     CK(cudaMemcpy(db, blocks, (size_t)n * 255, cudaMemcpyHostToDevice));
-    k_rs_test<<<(n + 63) / 64, 64>>>(db, dr, n);
+    k_rs_test<<<(n + 3) / 4, 128>>>(db, dr, n);
     CK(cudaMemcpy(blocks, db, (size_t)n * 255, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(rcs, dr, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(db);
@@ -1746,6 +1786,7 @@ extern "C" long nrsc5b_l2_frames(int device, const uint8_t *frames, size_t nbyte
         desc.push_back(h[0]);
         desc.push_back(h[1]);
         if (h[1] == 0) continue;
+        if (h[0] > 2) return NRSC5B_EINVAL;                       // logical channel: P1, P3, P4 (L2State::ccc[3])
         const size_t nb = (h[1] + 7) / 8;
         if (off + nb > nbytes) return NRSC5B_EINVAL;
         off += (nb + 3) & ~(size_t)3;

@@ -1071,8 +1071,11 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             // their place in the stream's record order (decode.c:458-460)
             if (bc == 0) st.started_pm = 1;
             if (st.started_pm && bc == 15) {
+                // both or neither: a BER record whose frame did not fit is taken back (its payload would never be filled)
+                const unsigned len0 = st.log_len;
                 uint8_t *bw = log_reserve(p, d, s, REC_BER, 4);
-                uint8_t *fw = log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8);
+                uint8_t *fw = bw ? log_reserve(p, d, s, REC_FRAME, 8 + P1_LEN / 8) : nullptr;
+                if (!fw) { st.log_len = len0; bw = nullptr; }
                 st.p1_rec = (bw && fw) ? (unsigned)(bw - (p.log + (size_t)s * d.log_cap)) : 0xffffffffu;
                 if (fw) {
                     reinterpret_cast<uint32_t *>(fw)[0] = 0;            // P1 logical channel

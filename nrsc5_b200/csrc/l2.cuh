@@ -7,8 +7,12 @@
 //
 // One CTA per stream takes the frames of a pass in the order the reference would see them:
 //   all threads : bit order swap + PCI removal -> PDU bytes in shared memory        (frame.c:692-710)
-//   thread 0    : the sequential part - fixed-data tail, header RS decode, location / HEF parsing, service
-//                 comparison, HDLC scanning - appending events to the stream's staging area and packets to a table
+//   warp 0      : the walk over the PDU (frame_process).  Only the position of the next audio PDU is sequential;
+//                 inside one, the 32 lanes share the work: RS(255,247) header decode (rs.cuh: syndromes over the
+//                 lanes, all-zero early out), packet locations and their ordering checks by ballot, the PSD bytes'
+//                 HDLC flag scan by ballot with whole segments appended at once, a closed HDLC frame pulled into
+//                 shared memory before it is unescaped and checked, events written a word per lane.  The rare
+//                 fixed-data tail (CCC, subchannel blocks) stays a byte-serial state machine on lane 0.
 //   all threads : CRC-8 of the packets (one packet per thread), then the copy of events + PDU bytes into the log
 // Per-stream state that outlives a frame (frame_t in the reference: service table, PSD assembly buffers, CCC and
 // subchannel state) lives in L2State in device memory.
@@ -27,6 +31,7 @@ constexpr int L2_RING = 64;                  // ELASTIC_BUFFER_LEN, reference sr
 constexpr uint32_t REC_L2 = 20;              // include/nrsc5_b200.h
 constexpr uint32_t EV_SERVICE = 16, EV_ALIGN = 17, EV_AAS = 18, EV_PACKET = 19;
 constexpr uint32_t L2F_LOST = 1, L2F_EV_OVERFLOW = 2;
+constexpr unsigned L2_NO_AUDIO = 0xffffffffu;    // fixed_tail: the frame is dropped (its CCC announces more than it holds)
 
 struct L2Sub {                               // fixed_subchannel_t, reference src/frame.h:19-28
     unsigned length, fill;
@@ -95,6 +100,45 @@ __device__ inline uint8_t *ev_put(EvWriter &w, uint32_t type, const void *a, uns
     for (unsigned i = plen; i < need - 8; i++) q[8 + i] = 0;
     w.len += need;
     return q + 8;
+}
+
+// warp versions (all 32 lanes call them with the same arguments; `w` lives in shared memory): a record of `nw`
+// payload words held by every lane, and a record whose payload is `n` bytes of shared memory
+__device__ inline uint8_t *ev_put_words(EvWriter &w, uint32_t type, const uint32_t *words, unsigned nw, int lane)
+{
+    const unsigned need = 8 + 4 * nw, at = w.len;
+    const bool full = w.overflow || at + need > (unsigned)L2_EV_CAP;
+    __syncwarp();
+    if (full) {
+        if (lane == 0) w.overflow = 1;
+        __syncwarp();
+        return nullptr;
+    }
+    uint32_t *q = reinterpret_cast<uint32_t *>(w.base + at);
+    if (lane == 0) { q[0] = type; q[1] = 4 * nw; w.len = at + need; }
+    if ((unsigned)lane < nw) q[2 + lane] = words[lane];
+    __syncwarp();
+    return w.base + at + 8;
+}
+
+__device__ inline void ev_put_bytes(EvWriter &w, uint32_t type, const uint8_t *src, unsigned n, int lane)
+{
+    const unsigned need = 8 + ((n + 3) & ~3u), at = w.len;
+    const bool full = w.overflow || at + need > (unsigned)L2_EV_CAP;
+    __syncwarp();
+    if (full) {
+        if (lane == 0) w.overflow = 1;
+        __syncwarp();
+        return;
+    }
+    uint8_t *q = w.base + at;
+    if (lane == 0) {
+        reinterpret_cast<uint32_t *>(q)[0] = type;
+        reinterpret_cast<uint32_t *>(q)[1] = n;
+        w.len = at + need;
+    }
+    for (unsigned i = lane; i < need - 8; i += 32) q[8 + i] = i < n ? src[i] : (uint8_t)0;
+    __syncwarp();
 }
 
 // CRC tables of the frame being processed, in shared memory (built by the CTA at the start of l2_frame):
@@ -197,12 +241,17 @@ __device__ inline unsigned fixed_tail(L2State &z, EvWriter &w, const CrcTabs &tb
     pos -= c.width;
     hdlc_scan(w, tb, &c, c.ccc, &c.ccc_idx, 32, pdu + pos, c.width);
     if (!c.ready) return pos;
+    // a CCC that announces more subchannel bytes than the PDU holds (noise that passed the FCS-16) would make the
+    // reference read in front of its buffer (frame.c:493-496); here such a frame is dropped whole - nothing is
+    // consumed, no subchannel state changes, and it has no audio part (L2_NO_AUDIO: l2_walk returns at once)
+    {
+        unsigned total = 0;
+        for (int i = 0; i < 4; i++) total += c.sub[i].length;
+        if (total > pos) return L2_NO_AUDIO;
+    }
     for (int i = 3; i >= 0; i--) {
         L2Sub &s = c.sub[i];
         if (s.length == 0) continue;
-        // a CCC that announces more subchannel bytes than the PDU holds (noise that passed the FCS-16) would make
-        // the reference read in front of its buffer (frame.c:493-496); here the frame has no audio part instead
-        if (s.length > pos) return 0;
         pos -= s.length;
         for (unsigned j = 0; j < s.length; j++) {
             s.blk[s.fill++] = pdu[pos + j];
@@ -269,19 +318,84 @@ struct PkEntry {
     unsigned start, cnt, ev;                 // first byte, payload bytes, staging offset of the packet's flags word
 };
 
-// the sequential walk over one PDU (thread 0): frame_process, reference src/frame.c:516-643
-__device__ inline void l2_walk(L2State &z, EvWriter &w, const CrcTabs &tb, uint8_t *pdu, unsigned length, unsigned lc, uint32_t pci,
-                               PkEntry *pk, unsigned &npk, unsigned &flags, uint8_t *rs_scratch)
+// a complete HDLC frame of PSD data (aas_push, reference src/frame.c:343-367), by one warp: the n accumulated bytes
+// are pulled into shared memory in one sweep (plus the byte behind them, which a trailing escape reads), unescaped and
+// checked there, and - like the reference, which unescapes in place - written back
+__device__ inline void aas_frame_warp(EvWriter &w, const CrcTabs &tb, uint8_t *acc, int n, uint8_t *scratch, int lane)
+{
+    if (n == 0) return;
+    for (int i = lane; i <= n; i += 32) scratch[i] = acc[i];           // acc[n] lies inside L2State (see hdlc_unescape)
+    __syncwarp();
+    int m = 0, ok = 0;
+    if (lane == 0) {
+        m = hdlc_unescape(scratch, n);
+        ok = m != 0 && fcs16_of(tb, scratch, m) == 0xF0B8u && scratch[0] == 0x21;
+    }
+    m = __shfl_sync(0xffffffffu, m, 0);
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    for (int i = lane; i < m; i += 32) acc[i] = scratch[i];
+    if (ok) ev_put_bytes(w, EV_AAS, scratch + 1, (unsigned)(m - 3), lane);
+    __syncwarp();
+}
+
+// parse_hdlc (reference src/frame.c:369-391) over the PSD bytes of one audio PDU, by one warp: 32 bytes at a time,
+// the 0x7E flags found by ballot, the bytes between two flags appended to the accumulator in one step
+__device__ inline void hdlc_scan_psd_warp(EvWriter &w, const CrcTabs &tb, uint8_t *acc, int *idx, const uint8_t *in, unsigned n,
+                                          uint8_t *scratch, int lane)
+{
+    int k = *idx;
+    __syncwarp();
+    for (unsigned base = 0; base < n; base += 32) {
+        const unsigned i = base + (unsigned)lane;
+        const bool valid = i < n;
+        const unsigned b = valid ? in[i] : 0u;
+        unsigned rem = __ballot_sync(0xffffffffu, valid && b == 0x7Eu);
+        const int lim = (int)min(32u, n - base);
+        int seg = 0;
+        for (;;) {
+            const int f = rem ? __ffs((int)rem) - 1 : lim;               // end of this run of data bytes (exclusive)
+            const int cnt = f - seg;
+            if (k >= 0 && cnt > 0) {
+                // byte by byte: stored while k < cap; the byte that arrives at k == cap invalidates the frame
+                const int room = L2_AAS_MAX - k;
+                if (lane >= seg && lane < f && lane - seg < room) acc[k + lane - seg] = (uint8_t)b;
+                k = cnt > room ? -1 : k + cnt;
+            }
+            if (!rem) break;
+            if (k >= 0) {
+                __syncwarp();
+                aas_frame_warp(w, tb, acc, k, scratch, lane);
+            }
+            k = 0;
+            rem &= rem - 1;
+            seg = f + 1;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *idx = k;
+    __syncwarp();
+}
+
+// the walk over one PDU (frame_process, reference src/frame.c:516-643) by warp 0: control flow is uniform (every lane
+// reads the same PDU bytes and state), single writes are lane 0's, the pieces named above are shared by the lanes
+__device__ inline void l2_walk(L2State &z, EvWriter &w, const CrcTabs &tb, const nb::GfTab &gf, uint8_t *pdu, unsigned length,
+                               unsigned lc, uint32_t pci, PkEntry *pk, unsigned &npk, unsigned &flags, uint8_t *scratch, int lane)
 {
     const uint32_t k = pci & 0xFFFFFCu;
     const bool fixed = k == (0xE3634Cu & 0xFFFFFCu) || k == (0x8D8D33u & 0xFFFFFCu) || k == (0x3634CEu & 0xFFFFFCu);
     unsigned end = length, off = 0;
-    if (fixed) end = fixed_tail(z, w, tb, pdu, length, lc);
+    if (lc > 2u) return;                                              // L2Ccc[3]: P1, P3, P4 (callers check; never index past it)
+    if (fixed) {
+        // byte-serial state machine over CCC and subchannel blocks: lane 0 (rare; the others wait)
+        if (lane == 0) end = fixed_tail(z, w, tb, pdu, length, lc);
+        end = __shfl_sync(0xffffffffu, end, 0);
+    }
+    if (end == L2_NO_AUDIO) return;
     if (k == (0x3634CEu & 0xFFFFFCu)) return;                         // fixed data only: no audio
     while (off < end - 96u) {                                         // unsigned on purpose, as frame.c:527
         const unsigned start = off;
         uint8_t *h = pdu + off;
-        if (!nb::fix_header_96(h, rs_scratch)) {
+        if (!nb::rs8_fix_header_warp(gf, h, lane)) {
             if ((length == 18269u || length == 466u) && off == 0) flags |= L2F_LOST;     // frame.c:535-540
             return;
         }
@@ -294,22 +408,41 @@ __device__ inline void l2_walk(L2State &z, EvWriter &w, const CrcTabs &tb, uint8
         const bool narrow = (codec >= 1 && codec <= 3) ? stream == 0 : (codec == 10 || codec == 13);   // calc_lc_bits
         const unsigned lbits = narrow ? 12u : 16u, lbytes = (lbits * nop + 4) / 8;
         if (start + la + 1 < off + lbytes || start + la >= end) return;
-        unsigned loc[64];
-        for (unsigned j = 0; j < nop; j++) {
-            const uint8_t *q = pdu + off;
-            unsigned v;
-            if (!narrow) v = q[2 * j] | (q[2 * j + 1] << 8);
-            else {
-                const uint8_t *r = q + (j >> 1) * 3;
-                v = (j & 1u) ? ((unsigned)r[2] << 4) | (r[1] >> 4) : ((r[1] & 15u) << 8) | r[0];
+        // packet locations: lane l holds those of packets l and l + 32 (nop <= 63); the reference gives up at the first
+        // one that is not behind its predecessor or lies outside the audio part - nothing has been emitted by then
+        unsigned loc2[2] = { 0, 0 };
+        bool bad = false;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const unsigned j = (unsigned)lane + 32u * hh;
+            unsigned v = 0;
+            if (j < nop) {
+                const uint8_t *q = pdu + off;
+                if (!narrow) v = q[2 * j] | (q[2 * j + 1] << 8);
+                else {
+                    const uint8_t *r = q + (j >> 1) * 3;
+                    v = (j & 1u) ? ((unsigned)r[2] << 4) | (r[1] >> 4) : ((r[1] & 15u) << 8) | r[0];
+                }
             }
-            loc[j] = v;
-            if (j == 0 ? v <= la : v <= loc[j - 1]) return;
-            if (start + v >= end) return;
+            loc2[hh] = v;
         }
+        const unsigned loc31 = __shfl_sync(0xffffffffu, loc2[0], 31);
+        unsigned prev2[2];
+        prev2[0] = __shfl_up_sync(0xffffffffu, loc2[0], 1);
+        prev2[1] = __shfl_up_sync(0xffffffffu, loc2[1], 1);
+        if (lane == 0) { prev2[0] = la; prev2[1] = loc31; }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const unsigned j = (unsigned)lane + 32u * hh;
+            if (j < nop && (loc2[hh] <= prev2[hh] || start + loc2[hh] >= end)) bad = true;
+        }
+        if (__any_sync(0xffffffffu, bad)) return;
+        const unsigned last_loc = nop ? (nop > 32 ? __shfl_sync(0xffffffffu, loc2[1], (int)(nop - 33)) : __shfl_sync(0xffffffffu, loc2[0], (int)(nop - 1)))
+                                      : 0u;
         off += lbytes;
         if (stream >= 2) {                                            // MAX_STREAMS: skip this PDU
-            off = start + loc[nop - 1] + 1;
+            if (nop == 0) return;                                     // (the reference would index locations[-1] here)
+            off = start + last_loc + 1;
             continue;
         }
         Hef hef = { 0, 0, 0 };
@@ -319,45 +452,69 @@ __device__ inline void l2_walk(L2State &z, EvWriter &w, const CrcTabs &tb, uint8
         const int now[7] = { (int)hef.access, (int)hef.type, (int)codec, (int)blend, (int)gain, (int)common, (int)latency };
         bool changed = false;
         for (int i = 0; i < 7; i++) changed |= sv[i] != now[i];
+        __syncwarp();
         if (stream == 0 && changed) {
-            for (int i = 0; i < 7; i++) sv[i] = now[i];
-            const int32_t r[8] = { (int32_t)prog, now[0], now[1], now[2], now[3], now[4] < 16 ? now[4] : now[4] - 32,
-                                   now[5] * 4, now[6] * 2 };
-            ev_put(w, EV_SERVICE, r, sizeof(r), nullptr, 0);
+            if (lane < 7) sv[lane] = now[lane];
+            const uint32_t r[8] = { prog, (uint32_t)now[0], (uint32_t)now[1], (uint32_t)now[2], (uint32_t)now[3],
+                                    (uint32_t)(now[4] < 16 ? now[4] : now[4] - 32), (uint32_t)(now[5] * 4), (uint32_t)(now[6] * 2) };
+            ev_put_words(w, EV_SERVICE, r, 8, lane);
         }
         unsigned avg;                                                 // calc_avg_packets, frame.c:289-313
         if (codec >= 1 && codec <= 3) avg = stream == 0 ? 4 : 32;
         else if (codec == 10) avg = stream == 0 ? 32 : 4;
         else avg = codec == 13 ? 4 : 32;
-        unsigned seq = (L2_RING + seq0 - pfirst) % L2_RING;
+        const unsigned seq = (L2_RING + seq0 - pfirst) % L2_RING;
         unsigned out_off = (L2_RING + pdu_seq * avg - latency * 2) % L2_RING;
         if ((L2_RING + seq - out_off) % L2_RING >= L2_RING / 2) out_off = (out_off + L2_RING / 2) % L2_RING;
-        const uint32_t al[3] = { prog, stream, out_off };
-        ev_put(w, EV_ALIGN, al, sizeof(al), nullptr, 0);
+        {
+            const uint32_t al[3] = { prog, stream, out_off };
+            ev_put_words(w, EV_ALIGN, al, 3, lane);
+        }
         // header expansion fields that run past la_location make the reference's byte count wrap (frame.c:608: it
         // would scan 4 GB); nothing is scanned here
         const unsigned psd_bytes = start + la + 1 >= off ? start + la + 1 - off : 0u;
-        hdlc_scan(w, tb, nullptr, z.psd[prog], &z.psd_idx[prog], L2_AAS_MAX, pdu + off, psd_bytes);
+        hdlc_scan_psd_warp(w, tb, z.psd[prog], &z.psd_idx[prog], pdu + off, psd_bytes, scratch, lane);
         off = start + la + 1;
-        for (unsigned j = 0; j < nop; j++) {
-            const unsigned cnt = start + loc[j] - off;
-            const unsigned shape = (j == 0 && pfirst) ? 3u : (j == nop - 1 && plast) ? 2u : 1u;      // output.h:28-31
-            uint32_t r[7] = { prog, stream, seq, shape, 0u, cnt, off };
-            if (npk >= (unsigned)L2_PK_MAX) {                         // table full: this thread checks the CRC itself
-                unsigned c = 0xFF;
-                for (unsigned i = 0; i <= cnt; i++) c = tb.crc8[c ^ pdu[off + i]];
-                r[4] = c ? 1u : 0u;
+        // the packets: packet j spans PDU bytes start + prev_j + 1 .. start + loc_j (payload + CRC byte); their
+        // output_push events are equally long, so they are written side by side, a packet per lane
+        {
+            constexpr unsigned EVB = 8 + 28;
+            const unsigned at = w.len;
+            const unsigned fit = w.overflow ? 0u : min(nop, ((unsigned)L2_EV_CAP - at) / EVB);
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const unsigned j = (unsigned)lane + 32u * hh;
+                if (j >= nop) continue;
+                const unsigned p0 = start + prev2[hh] + 1, cnt = loc2[hh] - prev2[hh] - 1;
+                const unsigned shape = (j == 0 && pfirst) ? 3u : (j == nop - 1 && plast) ? 2u : 1u;      // output.h:28-31
+                const bool in_table = npk + j < (unsigned)L2_PK_MAX;
+                unsigned crc_flag = 0;
+                if (!in_table) {                                      // table full: this lane checks the CRC itself
+                    unsigned c = 0xFF;
+                    for (unsigned i = 0; i <= cnt; i++) c = tb.crc8[c ^ pdu[p0 + i]];
+                    crc_flag = c ? 1u : 0u;
+                }
+                if (j < fit) {
+                    uint32_t *q = reinterpret_cast<uint32_t *>(w.base + at + j * EVB);
+                    q[0] = EV_PACKET; q[1] = 28;
+                    q[2] = prog; q[3] = stream; q[4] = (seq + j) % L2_RING; q[5] = shape; q[6] = crc_flag; q[7] = cnt; q[8] = p0;
+                    if (in_table) {
+                        pk[npk + j].start = p0;
+                        pk[npk + j].cnt = cnt;
+                        pk[npk + j].ev = at + j * EVB + 8 + 16;
+                    }
+                }
             }
-            uint8_t *q = ev_put(w, EV_PACKET, r, sizeof(r), nullptr, 0);
-            if (q && npk < (unsigned)L2_PK_MAX) {
-                pk[npk].start = off;
-                pk[npk].cnt = cnt;
-                pk[npk].ev = (unsigned)(q - w.base) + 16;
-                npk++;
+            __syncwarp();
+            if (lane == 0) {
+                w.len = at + fit * EVB;
+                if (fit < nop) w.overflow = 1;
             }
-            off += cnt + 1;
-            seq = (seq + 1) % L2_RING;
+            npk = min((unsigned)L2_PK_MAX, npk + fit);
+            __syncwarp();
         }
+        off = nop ? start + last_loc + 1 : off;
     }
 }
 
@@ -389,15 +546,23 @@ __device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbit
 {
     __shared__ __align__(16) uint8_t pdu[(L2_PDU_MAX + 15) & ~15];
     __shared__ PkEntry pk[L2_PK_MAX];
-    __shared__ uint8_t rs_scratch[256];
+    __shared__ __align__(16) uint8_t scratch[(L2_AAS_MAX + 1 + 15) & ~15];     // one HDLC frame while it is unescaped and checked
     __shared__ CrcTabs tb;
+    __shared__ nb::GfTab gf;
+    __shared__ EvWriter w;
     __shared__ unsigned sh_pci, sh_npk, sh_flags, sh_evlen;
     __shared__ uint8_t *sh_out;
     const unsigned t = threadIdx.x, nt = blockDim.x;
     unsigned first, step, npci;
     if (!l2_geometry(nbits, first, step, npci)) return;
     const unsigned nout = (nbits - npci) / 8;
-    if (t == 0) sh_pci = 0;
+    if (t == 0) {
+        sh_pci = 0;
+        w.base = z.ev;
+        w.len = 0;
+        w.overflow = 0;
+    }
+    nb::gf_tab_load(gf, (int)t, (int)nt);
     for (unsigned x = t; x < 256; x += nt) {
         unsigned f = x;
 #pragma unroll
@@ -427,15 +592,17 @@ __device__ inline void l2_frame(L2State &z, const uint8_t *packed, unsigned nbit
         pdu[n] = (uint8_t)v;
     }
     __syncthreads();
-    if (t == 0) {
-        EvWriter w = { z.ev, 0u, 0u };
+    if (t < 32) {                                                     // warp 0 walks the PDU
         unsigned npk = 0, flags = 0;
-        l2_walk(z, w, tb, pdu, nout, lc, sh_pci, pk, npk, flags, rs_scratch);
-        if (w.overflow) flags |= L2F_EV_OVERFLOW;
-        sh_npk = npk;
-        sh_flags = flags;
-        sh_evlen = w.len;
-        z.frames++;
+        l2_walk(z, w, tb, gf, pdu, nout, lc, sh_pci, pk, npk, flags, scratch, (int)t);
+        __syncwarp();
+        if (t == 0) {
+            if (w.overflow) flags |= L2F_EV_OVERFLOW;
+            sh_npk = npk;
+            sh_flags = flags;
+            sh_evlen = w.len;
+            z.frames++;
+        }
     }
     __syncthreads();
     for (unsigned j = t; j < sh_npk; j += nt) {                       // CRC-8 over payload + check byte: 0 when intact

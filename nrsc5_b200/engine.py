@@ -34,7 +34,7 @@ class _Config(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("blocks", ctypes.c_uint64), ("samples", ctypes.c_uint64),
                 ("p1_frames", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
-                ("p1_fallbacks", ctypes.c_uint64)]
+                ("p1_fallbacks", ctypes.c_uint64), ("log_overflows", ctypes.c_uint64)]
 
 
 def lib_path() -> str:
@@ -80,6 +80,7 @@ def load_library():
     L.nrsc5b_drain.restype = ctypes.c_long
     L.nrsc5b_drain_all.argtypes = [vp, vp, sz, vp]
     L.nrsc5b_set_sync_state.argtypes = [vp, ci, ci]
+    L.nrsc5b_take_overflow.argtypes = [vp, ci]
     L.nrsc5b_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.nrsc5b_enable_l2.argtypes = [vp, ci]
     L.nrsc5b_l2_frames.argtypes = [ci, ctypes.c_char_p, sz, vp, sz, ctypes.POINTER(sz)]
@@ -95,7 +96,8 @@ def load_library():
 
 def _check(rc, what):
     if rc < 0:
-        names = {-1: "ENODEV (no CUDA device; no CPU path exists)", -2: "EINVAL", -3: "ENOMEM", -4: "ECUDA", -5: "EFULL"}
+        names = {-1: "ENODEV (no CUDA device; no CPU path exists)", -2: "EINVAL", -3: "ENOMEM", -4: "ECUDA", -5: "EFULL",
+                 -6: "EOVERFLOW (a stream's record log overflowed: raise log_capacity)"}
         raise EngineError(f"{what} failed: {names.get(rc, rc)}")
     return rc
 
@@ -213,6 +215,7 @@ class Engine:
         self.nstreams = nstreams
         self._log_cap = log_capacity + 64
         self._keep = []
+        self.allow_overflow = False        # True: a truncated record log is not an error (tests of that very case)
 
     def close(self):
         if self._h:
@@ -308,6 +311,8 @@ class Engine:
         buf = ctypes.create_string_buffer(self._log_cap)
         n = self._L.nrsc5b_drain(self._h, stream, buf, self._log_cap, ctypes.byref(need))
         _check(n, "nrsc5b_drain")
+        if self._L.nrsc5b_take_overflow(self._h, stream) and not self.allow_overflow:
+            raise EngineError(f"stream {stream}: record log overflowed (log_capacity too small); the drained records are a prefix")
         return buf.raw[:n]
 
     def drain(self, stream: int):
@@ -318,7 +323,9 @@ class Engine:
         if out is None:
             out = np.empty((self.nstreams, self._log_cap), dtype=np.uint8)
         sizes = (ctypes.c_size_t * self.nstreams)()
-        _check(self._L.nrsc5b_drain_all(self._h, out.ctypes.data, out.strides[0], sizes), "nrsc5b_drain_all")
+        rc = self._L.nrsc5b_drain_all(self._h, out.ctypes.data, out.strides[0], sizes)
+        if not (rc == -6 and self.allow_overflow):
+            _check(rc, "nrsc5b_drain_all")
         return [out[s, :sizes[s]] for s in range(self.nstreams)]
 
     def drain_all(self):

@@ -203,10 +203,16 @@ static unsigned fixed_tail(orc_l2_t *o, unsigned length, unsigned lc)
     pos -= c->width;
     hdlc_scan(o, 1, c, c->ccc, &c->ccc_idx, 32, o->buf + pos, c->width);
     if (!c->ready) return pos;
+    {
+        /* a CCC announcing more subchannel bytes than the PDU holds: the reference would read in front of its buffer
+         * (frame.c:493-496, undefined); defined here (and in csrc/l2.cuh) as: the frame is dropped whole */
+        unsigned total = 0;
+        for (int i = 0; i < 4; i++) total += c->sub[i].length;
+        if (total > pos) return 0xffffffffu;
+    }
     for (int i = 3; i >= 0; i--) {
         l2_sub_t *s = &c->sub[i];
         if (s->length == 0) continue;
-        if (s->length > pos) return 0;      /* the reference would read in front of its buffer here (frame.c:493-496) */
         pos -= s->length;
         for (unsigned j = 0; j < s->length; j++) {
             s->blk[s->fill++] = o->buf[pos + j];
@@ -302,6 +308,7 @@ static void walk_pdus(orc_l2_t *o, unsigned length, unsigned lc)
     const uint32_t k = o->pci & 0xFFFFFC;
     const int fixed = k == (0xE3634C & 0xFFFFFC) || k == (0x8D8D33 & 0xFFFFFC) || k == (0x3634CE & 0xFFFFFC);
     if (fixed) end = fixed_tail(o, length, lc);
+    if (end == 0xffffffffu) return;
     if (k == (0x3634CE & 0xFFFFFC)) return;
     while (off < end - 96u) {                                             /* unsigned, as in the reference */
         const unsigned start = off;

@@ -52,6 +52,13 @@ test_viterbi_saturating_and_noisy = _stages.test_viterbi_saturating_and_noisy
 test_viterbi_fast_path_and_fallback_agree = _stages.test_viterbi_fast_path_and_fallback_agree
 test_viterbi_p1_length_bit_exact = _stages.test_viterbi_p1_length_bit_exact
 test_rs_decode_bit_exact = _stages.test_rs_decode_bit_exact
+
+
+def test_rs_beyond_the_correction_radius_equals_reference():
+    nfail, ncorr = _stages.rs_beyond_radius(6000)         # (120 000 words on the B200)
+    assert nfail > 5000
+
+
 # whole chain, FM
 test_synth_pdus_bit_exact = _chain.test_synth_pdus_bit_exact
 test_mp3_p1_pids_p3_bit_exact = _chain.test_mp3_p1_pids_p3_bit_exact

@@ -1,7 +1,7 @@
 """GPU parity on awkward inputs through the C ABI: dropouts with re-acquisition, streams that start in the middle of
 a frame, inputs shorter than one acquisition window, pure noise, misuse of the push calls.
 
-Marker `gpu_new` (see tests/conftest.py): verified on the CPU emulation of the kernels, first B200 run pending."""
+Their CPU twins run on the emulation of the kernels (tests/test_emu_engine.py)."""
 import numpy as np
 import pytest
 
@@ -13,7 +13,7 @@ from nrsc5_b200 import engine as eng
 from nrsc5_b200 import synth
 from test_gpu_chain import kinds, oracle_kinds, pdus, run_engine
 
-pytestmark = pytest.mark.gpu_new
+pytestmark = pytest.mark.gpu
 
 
 def _same_as_oracle(cu8, chunk=None):

@@ -104,3 +104,39 @@ def test_rs_decode_bit_exact():
     for i in range(blocks.shape[0]):
         rc_ref, ref = port.rs_decode(blocks[i])
         assert rc[i] == rc_ref and np.array_equal(fixed[i], ref), i
+
+def _rs_words(rng, n):
+    """Valid (255,247) codewords - a generated 96-byte header behind 159 zeros, or a random message encoded by the
+    synth encoder where available - hit by 5..8 symbol errors anywhere in the block: beyond the code's radius, where
+    the result (rejected, or "corrected" into another word) depends on what the decoder makes of an ambiguous locator."""
+    out = np.zeros((n, 255), dtype=np.uint8)
+    for i in range(n):
+        hdr = np.frombuffer(synth.audio_pdu_header(rng=rng), dtype=np.uint8)
+        out[i, 254 - np.arange(96)] = hdr
+        ne = 5 + (i & 3)
+        pos = rng.choice(255 if i % 2 else np.arange(159, 255), ne, replace=False)
+        out[i, pos] ^= rng.integers(1, 256, ne).astype(np.uint8)
+    return out
+
+
+def rs_beyond_radius(n):
+    rng = np.random.default_rng(2024)
+    blocks = _rs_words(rng, n)
+    rc, fixed = eng.rs_decode(blocks)
+    nfail = ncorr = 0
+    for i in range(n):
+        rc_ref, ref = port.rs_decode(blocks[i])
+        assert rc[i] == rc_ref and np.array_equal(fixed[i], ref), (i, rc[i], rc_ref)
+        nfail += rc_ref < 0
+        ncorr += rc_ref > 0
+    return nfail, ncorr
+
+
+def test_rs_beyond_the_correction_radius_equals_reference():
+    """120 000 words with 5..8 symbol errors: the warp decoder (inversion-free Berlekamp-Massey across lanes) must do
+    exactly what decode_rs_char does with them - reject most, mis-correct the ones whose locator happens to split -
+    byte for byte and count for count (the oracle's decoder is pinned to the unmodified reference's decode_rs_char
+    on the same kind of words in tests/test_oracle.py)."""
+    nfail, ncorr = rs_beyond_radius(120000)
+    assert nfail > 100000 and ncorr > 50          # both outcomes occur
+

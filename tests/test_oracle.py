@@ -196,6 +196,24 @@ class TestAgainstReference:
             rc, got = port.rs_decode(blk)
             assert rc == rc_ref and np.array_equal(ref, got)
 
+    def test_rs_decode_beyond_the_radius(self):
+        """The words of tests/test_gpu_stages.py::test_rs_beyond_the_correction_radius_equals_reference (5..8 symbol
+        errors): the oracle's decoder = the unmodified reference's decode_rs_char, including every mis-correction."""
+        import test_gpu_stages
+        L = reftap.lib()
+        L.init_rs_char.restype = ctypes.c_void_p
+        L.decode_rs_char.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        rs = L.init_rs_char(8, 0x11D, 1, 1, 8)
+        blocks = test_gpu_stages._rs_words(np.random.default_rng(2024), 120000)
+        ncorr = 0
+        for blk in blocks:
+            ref = blk.copy()
+            rc_ref = L.decode_rs_char(rs, ref.ctypes.data_as(ctypes.c_void_p), None, 0)
+            rc, got = port.rs_decode(blk)
+            assert rc == rc_ref and np.array_equal(ref, got)
+            ncorr += rc_ref > 0
+        assert ncorr > 50
+
 
 def test_rs_roundtrip_without_reference():
     rng = np.random.default_rng(11)
