@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--am-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-mp3", action="store_true", help="skip the MP3 leg (BASELINE config 3)")
     ap.add_argument("--mp3-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-dropin", action="store_true", help="skip the single-stream drop-in leg (BASELINE configs 1, 2)")
+    ap.add_argument("--dropin-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--mp3-streams", type=int, default=64)
     ap.add_argument("--mp3-frames", type=int, default=6)
     ap.add_argument("--am-streams", type=int, default=256)
@@ -288,6 +290,56 @@ def am_leg(args, engine_factory=None):
     e.close()
 
 
+def dropin_leg(args):
+    """BASELINE configs 1 and 2: ONE stream through the drop-in libnrsc5.so's public API, fed exactly as the reference
+    CLI feeds a file (src/main.c:1097-1119: 32 768-byte nrsc5_pipe_samples_cu8 calls, then stop / close), by the C
+    driver nrsc5_b200/dropin/bench_pipe.c; the same binary then runs the unmodified reference library (one CPU core)
+    on the same bytes.  Config 1 = support/sample.xz, config 2 = a synthetic FM MP1 capture of 8 L1 frames.  The HDC
+    packet digest of the two runs must agree.  Prints one JSON object."""
+    import lzma
+    import tempfile
+    exe = os.path.join(ROOT, "nrsc5_b200", "dropin", "_build", "bench_pipe")
+    dropin = os.path.join(ROOT, "nrsc5_b200", "dropin", "_build", "libnrsc5.so")
+    ref = os.path.join(ROOT, "oracle", "_ref", "libnrsc5_ref.so")
+    if not (os.path.exists(exe) and os.path.exists(dropin)):
+        print(json.dumps({"error": "drop-in not built (needs the reference tree at build time)"}))
+        return
+    out = {"what": "nrsc5_open_pipe -> nrsc5_pipe_samples_cu8 in 32768-byte pushes -> nrsc5_stop -> nrsc5_close on one stream; "
+                   "wall clock of the push loop + stop + close, best of 3 after one warm-up pass, input in memory",
+           "driver": "nrsc5_b200/dropin/bench_pipe.c (the reference CLI's push loop around a dlopen'ed library)"}
+    with tempfile.TemporaryDirectory() as td:
+        cases = {}
+        sample = os.path.join(ROOT, "oracle", "_ref", "sample.xz")
+        if os.path.exists(sample):
+            path = os.path.join(td, "sample.cu8")
+            with open(path, "wb") as f:
+                f.write(lzma.open(sample).read())
+            cases["config1_sample_xz"] = path
+        from nrsc5_b200 import synth
+        cap = synth.make_fm_mp1(nframes=8, seed=1234, lead_in=1777, tail_blocks=2)
+        path = os.path.join(td, "mp1.cu8")
+        cap.cu8[: cap.cu8.size & ~3].tofile(path)
+        cases["config2_synthetic_mp1_8_frames"] = path
+        for name, path in cases.items():
+            res = {}
+            for which, lib in (("dropin_b200", dropin), ("reference_cpu_1core", ref)):
+                if not os.path.exists(lib):
+                    continue
+                r = subprocess.run([exe, lib, path, "--reps", "3"], capture_output=True, text=True, timeout=600)
+                if r.returncode != 0:
+                    res[which] = {"error": (r.stderr or r.stdout)[-300:]}
+                    continue
+                res[which] = json.loads(r.stdout.strip().splitlines()[-1])
+            a, b = res.get("dropin_b200", {}), res.get("reference_cpu_1core", {})
+            if "hdc_fnv" in a and "hdc_fnv" in b:
+                same = all(a[k] == b[k] for k in ("hdc", "hdc_bytes", "hdc_fnv", "sync", "lost_sync", "mer", "ber", "id3", "audio_service"))
+                res["events_identical_to_reference"] = same
+                assert same, (name, a, b)
+                res["speedup_vs_reference_1core"] = a["x_realtime"] and b["x_realtime"] and a["x_realtime"] / b["x_realtime"]
+            out[name] = res
+    print(json.dumps(out), flush=True)
+
+
 def stream_views(caps, nstreams: int, rank: int):
     """Stream s of this rank = capture (g % D) with the first 4*(37*(g // D) % 1080) bytes dropped,
     g = global stream index: distinct alignments, so distinct acquisition paths."""
@@ -491,6 +543,9 @@ def main():
         return
     if args.mp3_leg:
         mp3_leg(args)
+        return
+    if args.dropin_leg:
+        dropin_leg(args)
         return
 
     import torch
@@ -734,6 +789,16 @@ def main():
         except Exception as ex:                                    # noqa: BLE001
             mp3 = {"error": repr(ex)[:400]}
 
+    # ---- one stream through the drop-in's public API, BASELINE configs 1 and 2 (separate process, rank 0, N=1 only) ----
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_dropin:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--dropin-leg"], capture_output=True, text=True, timeout=600)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            dropin = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as ex:                                    # noqa: BLE001
+            dropin = {"error": repr(ex)[:400]}
+
     if rank == 0:
         line = {
             "metric": "cu8 I/Q Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -752,6 +817,8 @@ def main():
             line["am_config4"] = am
         if mp3:
             line["mp3_config3"] = mp3
+        if dropin:
+            line["single_stream_dropin"] = dropin
         print(json.dumps(line), flush=True)
     e.close()
     if use_dist:

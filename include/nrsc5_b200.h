@@ -150,6 +150,25 @@ int nrsc5b_process_available(nrsc5b_engine_t *e);
  * nrsc5b_process_fence(token) processes exactly that as soon as it has landed, while later pushes keep copying. */
 int nrsc5b_push_fence(nrsc5b_engine_t *e);
 int nrsc5b_process_fence(nrsc5b_engine_t *e, int token);
+/* ---- asynchronous use: nothing below waits for the GPU unless asked to ----
+ * nrsc5b_stage_cu8 / _cs16: input_push_cu8 / input_push_cs16 (reference src/input.c:96-124) without a CUDA call - the
+ *     samples are copied into page-locked staging memory and travel to the device, one copy per stream, with the next
+ *     batch (or when the 4 MiB staging area is full, or at nrsc5b_process).
+ * nrsc5b_submit: enqueue the passes the buffered samples can need (sized on the host from the sample counts and the
+ *     streams' last known window positions: a caller that pushes less than a block at a time launches nothing on most
+ *     calls) followed by the export of all records to page-locked host memory.  1 = enqueued, 0 = nothing to do or a
+ *     batch is still in flight.  flush != 0 also sends staged input that completes no block yet.
+ * nrsc5b_poll: 1 = the batch has finished (wait != 0: block until it has), its records can be read with
+ *     nrsc5b_batch_records until the next submit; 0 = none in flight / still running.
+ * One batch is in flight at a time; nrsc5b_process / nrsc5b_drain must not be mixed in while one is.  This is what the
+ * drop-in libnrsc5.so runs on: pushes return at once, callbacks are made - in the reference's order - from a later
+ * push (or from nrsc5_close) as batches complete. */
+int nrsc5b_stage_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
+int nrsc5b_stage_cs16(nrsc5b_engine_t *e, int stream, const int16_t *buf, size_t nvalues);
+int nrsc5b_submit(nrsc5b_engine_t *e, int flush);
+int nrsc5b_poll(nrsc5b_engine_t *e, int wait);
+const uint8_t *nrsc5b_batch_records(nrsc5b_engine_t *e, int stream, size_t *nbytes);
+
 /* Wait for the GPU and copy the records of `stream` produced since the last drain.
  * Returns the number of bytes written (>= 0) or a negative error; *needed gets the full size. */
 long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_t cap, size_t *needed);

@@ -144,8 +144,23 @@ struct PxBufs {
 constexpr int PX_NEED_SHORT = 1, PX_NEED_PX2 = 2, PX_NEED_P3 = 4;   // MP2 | MP11 (P4) | MP3 and MP11 (4608-bit P3)
 constexpr int P3S_LEN = 2304, IV_NS = IV_N / 2;    // MP2: P3 frame bits, interleaver IV span (decode.c:346-350)
 
+// Per-engine control words in device memory (one engine = one instance: engines on one device share nothing).
+struct EngineCtl {
+    unsigned long long progress;   // bumped by every stream that processed a block
+    unsigned px_need;              // PX_NEED_* bits: a stream waits for a decode group the host has not enabled
+    unsigned more;                 // streams that could go on after the last pass of a batch (a full window is buffered)
+};
+
+// What the host needs to know about a stream to plan the next batch of passes (written when k_stream / k_am exit).
+struct StreamBrief {
+    long long start;               // decimated index of the window's first sample
+    int state, bc, p1_ready, pad_;
+};
+
 // Pointers to all device arrays, passed by value to kernels.
 struct DevPtrs {
+    EngineCtl *ctl;            // [1]
+    StreamBrief *brief;        // [S]
     const uint8_t *iq;         // [S][in_stride] cu8
     StreamState *st;           // [S]
     float *cfreq;              // [S][2048]

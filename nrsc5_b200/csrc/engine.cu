@@ -479,7 +479,7 @@ struct AmFixHeader {
 };
 
 __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmState *ast, nbam::AmWork *aw,
-                                           const nbam::AmTables *tb, int max_blocks)
+                                           const nbam::AmTables *tb, int max_blocks, int last_pass)
 {
     const int s = blockIdx.x;
     const nbam::Lanes L = { (int)threadIdx.x, 32 };
@@ -516,7 +516,16 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
             fs.l2_lc[i] = st.l2_lc[i];
             fs.l2_nbits[i] = st.l2_nbits[i];
         }
-        if (nb_done) atomicAdd(&g_progress, (unsigned long long)nb_done);
+        if (nb_done) atomicAdd(&p.ctl->progress, (unsigned long long)nb_done);
+        StreamBrief b;
+        b.start = st.start;
+        b.state = st.state;
+        b.bc = 0;
+        b.p1_ready = 0;
+        b.pad_ = 0;
+        p.brief[s] = b;
+        const long long avail = *reinterpret_cast<volatile long long *>(&fs.in_avail) / 2;
+        if (last_pass && avail >= st.start + nbam::NACQ) atomicAdd(&p.ctl->more, 1u);
     }
 }
 
@@ -580,6 +589,33 @@ __global__ void k_l2_init(nbl2::L2State *l2, int only)
     if (threadIdx.x == 0) nbl2::l2_reset(l2[s]);
 }
 
+// End of an asynchronous batch (nrsc5b_submit): every stream's records go to page-locked host memory the device
+// writes directly (16 bytes per store), with a header saying how many; the device log is rewound.  The host reads
+// them when the batch's event has fired - no sized device->host copy, no round trip for the sizes.
+struct ExportHdr {
+    unsigned log_len, log_overflow;
+};
+
+__global__ void __launch_bounds__(256) k_export(DevPtrs p, EngineDims d, uint8_t *host_log, size_t host_stride, ExportHdr *hdr)
+{
+    const int s = blockIdx.x, t = threadIdx.x;
+    StreamState &st = p.st[s];
+    const unsigned n = st.log_len;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.log + (size_t)s * d.log_cap);
+    uint4 *dst = reinterpret_cast<uint4 *>(host_log + (size_t)s * host_stride);
+    for (unsigned i = t; i < (n + 15) / 16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (t == 0) {
+        hdr[s].log_len = n;
+        // (a frame whose record is reserved but not decoded yet would leave as a hole: the host plans a decode group
+        // into every pass that can complete a frame, so this cannot happen - if it does, say so instead of shipping it)
+        hdr[s].log_overflow = st.log_overflow | (st.p1_ready ? 2u : 0u);
+        st.log_len = 0;
+        st.log_overflow = 0;
+        __threadfence_system();
+    }
+}
+
 // stage entry point: a list of frames (desc: offset into `frames`, lc, nbits; nbits == 0 = frame_reset) through one
 // stream's L2, records into out[cap]
 __global__ void __launch_bounds__(nbl2::L2_THREADS) k_l2_test(nbl2::L2State *l2, const uint8_t *frames, const uint32_t *desc,
@@ -639,6 +675,25 @@ struct nrsc5b_engine {
     StreamState *h_state;              // pinned mirror for read-back
     nrsc5b_stats_t stats;
     unsigned long long last_progress;
+    // host-side planning of the passes (plan_passes): the device's control words and per-stream briefs, read back
+    // into page-locked memory behind every batch
+    EngineCtl *h_ctl;
+    StreamBrief *h_brief;
+    // asynchronous batches (nrsc5b_submit / nrsc5b_poll): records exported into page-locked host memory
+    uint8_t *xlog;                     // [S][xlog_stride], page-locked, written by k_export
+    size_t xlog_stride;
+    ExportHdr *xhdr;                   // [S], page-locked
+    cudaEvent_t batch_done;
+    bool in_flight, batch_decoded;
+    // staged input (nrsc5b_stage_cu8 / _cs16): pushes land in page-locked memory and go to the device in one copy
+    // per stream when a batch is submitted
+    struct Staged { int stream; size_t off, n; };
+    uint8_t *stage[2];
+    size_t stage_cap, stage_fill;
+    int stage_cur;
+    cudaEvent_t stage_free[2];
+    std::vector<Staged> staged;
+    std::vector<long long> staged_units;   // per stream: staged 2-byte units not yet counted in `pushed`
     std::vector<void *> allocs;
     int v64_ch;                        // chunk length of the fast P1 Viterbi (chosen from the stream count)
     nbam::AmState *am_st;              // AM mode: per-stream state, work arrays, tables
@@ -765,6 +820,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->fence_next = 0;
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
+    e->h_ctl = nullptr; e->h_brief = nullptr;
+    e->xlog = nullptr; e->xlog_stride = 0; e->xhdr = nullptr; e->batch_done = nullptr; e->in_flight = false; e->batch_decoded = false;
+    e->stage[0] = e->stage[1] = nullptr; e->stage_cap = 0; e->stage_fill = 0; e->stage_cur = 0;
+    e->stage_free[0] = e->stage_free[1] = nullptr;
     e->profiling = 0;
     for (int i = 0; i < 5; i++) e->pev[i] = nullptr;
     for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
@@ -776,13 +835,8 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->dims.emit_soft = cfg->emit_soft;
     e->dims.cs16 = cfg->input_cs16 ? 1 : 0;
     e->dims.px_enabled = 0;
-    {
-        // the request flag for the extra decode groups is per process: every new engine starts from a clean one (a
-        // stream of another engine that is waiting raises it again at its next pass)
-        const unsigned zero = 0;
-        cudaMemcpyToSymbol(g_px_need, &zero, sizeof(zero));
-    }
     e->pushed.assign(S, 0);
+    e->staged_units.assign(S, 0);
     e->drained.assign(S, 0);
     e->overflowed.assign(S, 0);
     int rc = upload_tables(cfg->device);
@@ -805,6 +859,8 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         e->iq_owned = tmp;
         dp.iq = tmp;
     }
+    DA(ctl, EngineCtl, 1);
+    DA(brief, StreamBrief, S);
     DA(st, StreamState, S);
     DA(cfreq, float, (size_t)S * NFFT);
     DA(cphase, float, (size_t)S * NFFT);
@@ -980,6 +1036,9 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     if (cudaMallocHost((void **)&e->pinned, e->pinned_cap) != cudaSuccess ||
         cudaMallocHost((void **)&e->h_state, sizeof(StreamState) * S) != cudaSuccess ||
         cudaMallocHost((void **)&e->avail_ring, sizeof(long long) * 4096) != cudaSuccess ||
+        cudaMallocHost((void **)&e->h_ctl, sizeof(EngineCtl)) != cudaSuccess ||
+        cudaMallocHost((void **)&e->h_brief, sizeof(StreamBrief) * S) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->batch_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->reset_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->pinned_free, cudaEventDisableTiming) != cudaSuccess) {
         nrsc5b_destroy(e);
@@ -1007,6 +1066,15 @@ extern "C" void nrsc5b_destroy(nrsc5b_engine_t *e)
     if (e->h_state) cudaFreeHost(e->h_state);
     if (e->avail_ring) cudaFreeHost(e->avail_ring);
     if (e->avail_rows) cudaFreeHost(e->avail_rows);
+    if (e->h_ctl) cudaFreeHost(e->h_ctl);
+    if (e->h_brief) cudaFreeHost(e->h_brief);
+    if (e->xlog) cudaFreeHost(e->xlog);
+    if (e->xhdr) cudaFreeHost(e->xhdr);
+    if (e->batch_done) cudaEventDestroy(e->batch_done);
+    for (int i = 0; i < 2; i++) {
+        if (e->stage[i]) cudaFreeHost(e->stage[i]);
+        if (e->stage_free[i]) cudaEventDestroy(e->stage_free[i]);
+    }
     if (e->reset_done) cudaEventDestroy(e->reset_done);
     for (int i = 0; i < 64; i++) if (e->fence[i]) cudaEventDestroy(e->fence[i]);
     if (e->pinned_free) cudaEventDestroy(e->pinned_free);
@@ -1027,6 +1095,16 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
     if (!e || stream >= e->dims.nstreams) return NRSC5B_EINVAL;
     const int S = e->dims.nstreams;
     CK(cudaStreamSynchronize(e->copy_stream));       // no input copy of the old contents may still be in flight
+    if (e->in_flight) {                              // an asynchronous batch: let it finish; its records are void
+        CK(cudaEventSynchronize(e->batch_done));
+        e->in_flight = false;
+    }
+    {
+        std::vector<nrsc5b_engine::Staged> keep;
+        for (const auto &g : e->staged)
+            if (stream >= 0 && g.stream != stream) keep.push_back(g);
+        e->staged.swap(keep);
+    }
     k_reset<<<S, 256, 0, e->stream>>>(e->dp, e->dims, stream < 0 ? -1 : stream);
     if (e->l2) k_l2_init<<<S, 256, 0, e->stream>>>(e->l2, stream < 0 ? -1 : stream);
     CK(cudaEventRecord(e->reset_done, e->stream));
@@ -1046,6 +1124,8 @@ extern "C" int nrsc5b_reset(nrsc5b_engine_t *e, int stream)
     for (int s = 0; s < S; s++) {
         if (stream >= 0 && s != stream) continue;
         e->pushed[s] = 0;
+        e->staged_units[s] = 0;
+        e->h_brief[s] = StreamBrief{ 0, ST_NONE, 0, 0, 0 };
         e->drained[s] = 0;
         if (e->am_ring) e->am_raw_bytes[s] = e->am_dec_out[s] = 0;
     }
@@ -1070,7 +1150,10 @@ extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
         }
         CK(cudaStreamSynchronize(e->stream));              // `z` lives on this stack frame
     }
-    for (int s = 0; s < e->dims.nstreams; s++) e->drained[s] = 0;
+    for (int s = 0; s < e->dims.nstreams; s++) {
+        e->drained[s] = 0;
+        e->h_brief[s] = StreamBrief{ 0, ST_NONE, 0, 0, 0 };
+    }
     CK(cudaGetLastError());
     return NRSC5B_OK;
 }
@@ -1118,6 +1201,7 @@ static int trim_stream(nrsc5b_engine *e, int s)
     CK(cudaMemcpyAsync(base, e->trim_scratch, rem, cudaMemcpyDeviceToDevice, e->stream));
     k_trim_state<<<1, 1, 0, e->stream>>>(e->dp, s, drop, e->am_st);
     e->pushed[s] -= 2 * drop;
+    e->h_brief[s].start = st.start - drop;
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -1354,13 +1438,18 @@ static int enable_px_groups(nrsc5b_engine *e, unsigned need)
 
 // One pass: every stream runs its front end up to its next frame boundary (at most BLOCKS_PER_PASS blocks,
 // one persistent CTA per stream), then the P1 decode of the streams that completed an interleaver matrix.
+// last_pass: the batch ends here - streams that could go on at once say so in EngineCtl::more.
+// with_decode = false: the host knows that no stream can complete a frame in this pass (plan_passes), the decode
+// groups and k_l2 would find nothing.
 constexpr int BLOCKS_PER_PASS = 16;
 
-static int launch_pass(nrsc5b_engine *e)
+static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true)
 {
+    if (last_pass) cudaMemsetAsync(reinterpret_cast<uint8_t *>(e->dp.ctl) + offsetof(EngineCtl, more), 0, sizeof(unsigned), e->stream);
     if (e->am_st) {                                        // AM: one kernel does the whole chain, window after window
         const bool l2 = e->l2 && e->dims.l2;              // with L2 on, a launch stops after 16 blocks: its frames fit the queue
-        k_am<<<e->dims.nstreams, 32, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20);
+        k_am<<<e->dims.nstreams, 32, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20,
+                                                     last_pass ? 1 : 0);
         e->stats.kernel_launches += 1;
         if (l2) {
             k_l2<<<e->dims.nstreams, nbl2::L2_THREADS, 0, e->stream>>>(e->dp, e->dims, e->l2);
@@ -1370,13 +1459,14 @@ static int launch_pass(nrsc5b_engine *e)
     }
     const bool prof = e->profiling != 0;
     if (prof) cudaEventRecord(e->pev[0], e->stream);
-    k_stream<<<e->dims.nstreams, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS);
+    k_stream<<<e->dims.nstreams, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS, last_pass ? 1 : 0);
     e->stats.kernel_launches += 1;
     if (prof) cudaEventRecord(e->pev[1], e->stream);
-    launch_p1(e);
+    if (with_decode) launch_p1(e);
     if (prof) cudaEventRecord(e->pev[2], e->stream);
-    // L2 framing of everything the pass decoded (only when enabled, nrsc5b_enable_l2)
-    if (e->l2 && e->dims.l2) {
+    // L2 framing of everything the pass decoded (only when enabled, nrsc5b_enable_l2); a pass without decode groups
+    // can still have queued a frame_reset (fine sync entered), which the next k_l2 takes
+    if (with_decode && e->l2 && e->dims.l2) {
         k_l2<<<e->dims.nstreams, nbl2::L2_THREADS, 0, e->stream>>>(e->dp, e->dims, e->l2);
         e->stats.kernel_launches += 1;
     }
@@ -1393,6 +1483,49 @@ static int launch_pass(nrsc5b_engine *e)
             e->kernel_ms[2] += ms; e->kernel_n[2] += 1;
         }
     }
+    return 0;
+}
+
+// How many passes the samples buffered on the host's count can need, from what the host knows of every stream
+// (StreamBrief: window position, sync state, block count - read back behind every batch): a block needs a whole
+// 33-symbol window and moves it on by 32 symbols +- the timing correction; a pass ends at a frame boundary.  The
+// count errs on the high side (a surplus pass finds nothing to do); 0 = no stream can complete a block, nothing is
+// launched at all.  *first_needs_decode: whether a stream can complete a frame in the first pass.
+static int plan_passes(const nrsc5b_engine *e, bool count_staged, bool *first_needs_decode)
+{
+    const bool am = e->am_st != nullptr;
+    const long long win = am ? nbam::NACQ : NACQ, adv = am ? nbam::SYM * nbam::BLK : NSYM * BLK;
+    const long long slack = am ? 40 : 160;                 // the window can advance by less than `adv` (timing correction)
+    int passes = 0;
+    bool decode = am || e->dims.px_enabled != 0;           // (extended-partition frames complete every second block)
+    for (int s = 0; s < e->dims.nstreams; s++) {
+        const StreamBrief &b = e->h_brief[s];
+        if (b.p1_ready) decode = true;
+        const long long have = (e->pushed[s] + (count_staged ? e->staged_units[s] : 0)) / 2;
+        if (have < b.start + win) { if (b.p1_ready && passes < 1) passes = 1; continue; }
+        const long long blocks = 1 + (have - b.start - win) / (adv - slack);
+        long long segs;
+        if (am) {
+            segs = (e->l2 && e->dims.l2) ? (blocks + nbam::AM_L2_BLOCKS - 1) / nbam::AM_L2_BLOCKS : 1;
+        } else if (b.state == ST_FINE) {
+            const long long first = BLOCKS_PER_PASS - b.bc;         // blocks up to and including the frame's last one
+            segs = blocks <= first ? 1 : 1 + (blocks - first + BLOCKS_PER_PASS - 1) / BLOCKS_PER_PASS;
+            if (blocks >= first) decode = true;
+        } else {
+            segs = (blocks + BLOCKS_PER_PASS - 1) / BLOCKS_PER_PASS + 1;   // acquisition re-aligns the frame boundaries
+            decode = true;
+        }
+        if (segs > passes) passes = (int)(segs > 12 ? 12 : segs);
+    }
+    if (first_needs_decode) *first_needs_decode = decode;
+    return passes;
+}
+
+// Reads the control words and briefs of the batch just enqueued into page-locked memory (asynchronously).
+static int enqueue_readback(nrsc5b_engine *e)
+{
+    CK(cudaMemcpyAsync(e->h_ctl, e->dp.ctl, sizeof(EngineCtl), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_brief, e->dp.brief, sizeof(StreamBrief) * e->dims.nstreams, cudaMemcpyDeviceToHost, e->stream));
     return 0;
 }
 
@@ -1437,47 +1570,51 @@ extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned
     return NRSC5B_OK;
 }
 
+static int flush_staged(nrsc5b_engine *e);
+
 static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
 {
     if (!e) return NRSC5B_EINVAL;
-    // Each block advances a stream's window by 69120 +- a few decimated samples, and a pass takes a stream
-    // through at most one frame boundary, so the number of passes the buffered samples can need follows
-    // from the host-side sample counts.  Enqueue that many, look at the device-side progress counter, and
-    // stop after a batch (always ending with a pass that also flushes the deferred PIDS decode) made no
-    // progress.  Surplus passes find nothing to do and cost a few microseconds.
-    const int S = e->dims.nstreams;
-    bool first = true;
-    for (;;) {
-        int passes = 1;
-        if (first) {
-            long long most = 0;
-            for (int s = 0; s < S; s++) {
-                const long long n = e->pushed[s] / 2 / (NSYM * BLK - 80) + 1;
-                if (n > most) most = n;
-            }
-            passes = (int)(most / BLOCKS_PER_PASS) + 2;
-            first = false;
-        }
+    if (e->in_flight) return NRSC5B_EINVAL;                // an asynchronous batch is open: nrsc5b_poll first
+    {
+        int rc = flush_staged(e);
+        if (rc) return rc;
+    }
+    if (wait_for_copies) {
+        // everything pushed before this call: the compute stream waits (on the device) for the copy stream
+        const unsigned slot = e->fence_next++ & 63;
+        if (!e->fence[slot]) CK(cudaEventCreateWithFlags(&e->fence[slot], cudaEventDisableTiming));
+        CK(cudaEventRecord(e->fence[slot], e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, e->fence[slot], 0));
+    }
+    // Batches of passes sized by plan_passes() from the host's sample counts and the streams' last known positions;
+    // behind every batch one small read-back (control words + briefs) and one synchronisation.  A caller that pushes
+    // less than a block at a time therefore launches nothing on most calls.
+    for (int guard = 0; guard < 1 << 20; guard++) {
+        bool decode = true;
+        const int passes = plan_passes(e, false, &decode);
+        if (passes == 0) break;
         for (int i = 0; i < passes; i++) {
-            int rc = launch_pass(e);
+            int rc = launch_pass(e, i == passes - 1, i > 0 || decode);
             if (rc) return rc;
         }
-        unsigned long long prog = 0;
-        unsigned px_need = 0;
-        CK(cudaMemcpyFromSymbolAsync(&prog, g_progress, sizeof(prog), 0, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaMemcpyFromSymbolAsync(&px_need, g_px_need, sizeof(px_need), 0, cudaMemcpyDeviceToHost, e->stream));
+        int rc = enqueue_readback(e);
+        if (rc) return rc;
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaGetLastError());
-        const unsigned long long delta = prog - e->last_progress;
-        e->last_progress = prog;
-        if (px_need & ~(unsigned)e->dims.px_enabled) {
-            // a stream in MP2 / MP11 waits at a block boundary for its decode group: add it and go on
-            int rc = enable_px_groups(e, px_need);
+        const unsigned long long delta = e->h_ctl->progress - e->last_progress;
+        e->last_progress = e->h_ctl->progress;
+        if (passes > 1 || decode)                          // (a brief is written before its pass's decode groups run)
+            for (int s = 0; s < e->dims.nstreams; s++) e->h_brief[s].p1_ready = 0;
+        if (e->h_ctl->px_need & ~(unsigned)e->dims.px_enabled) {
+            // a stream in MP2 / MP3 / MP11 waits at a block boundary for its decode group: add it and go on
+            rc = enable_px_groups(e, e->h_ctl->px_need);
             if (rc) return rc;
             continue;
         }
+        if (e->h_ctl->more == 0) break;                    // no stream has another whole window
         if (delta == 0) {
-            // samples pushed asynchronously may still have been in flight: wait for them once, then retry
+            // streams report more input than they could use: samples still in flight on the copy stream
             if (!wait_for_copies || cudaStreamQuery(e->copy_stream) == cudaSuccess) break;
             CK(cudaStreamSynchronize(e->copy_stream));
         }
@@ -1507,6 +1644,168 @@ extern "C" int nrsc5b_process_fence(nrsc5b_engine_t *e, int token)
 
 extern "C" int nrsc5b_process(nrsc5b_engine_t *e) { return process_impl(e, true); }
 extern "C" int nrsc5b_process_available(nrsc5b_engine_t *e) { return process_impl(e, false); }
+
+// ===========================================================================
+// Asynchronous use (one stream or many): staged input, one batch of passes in flight, records exported to host memory
+// ===========================================================================
+static int stage_bytes(nrsc5b_engine *e, int stream, const uint8_t *buf, size_t nbytes)
+{
+    if (stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned || e->am_ring) return NRSC5B_EINVAL;
+    if (!e->stage[0]) {
+        e->stage_cap = 4u << 20;
+        for (int i = 0; i < 2; i++) {
+            if (cudaMallocHost((void **)&e->stage[i], e->stage_cap) != cudaSuccess) return NRSC5B_ENOMEM;
+            CK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
+        }
+    }
+    while (nbytes) {
+        if (e->stage_fill == e->stage_cap) {               // this half is full: send it, go on in the other one
+            int rc = flush_staged(e);
+            if (rc) return rc;
+        }
+        const size_t n = nbytes < e->stage_cap - e->stage_fill ? nbytes : e->stage_cap - e->stage_fill;
+        memcpy(e->stage[e->stage_cur] + e->stage_fill, buf, n);
+        if (!e->staged.empty() && e->staged.back().stream == stream && e->staged.back().off + e->staged.back().n == e->stage_fill)
+            e->staged.back().n += n;                        // the usual case: one stream, contiguous pushes
+        else
+            e->staged.push_back({ stream, e->stage_fill, n });
+        e->stage_fill += n;
+        e->staged_units[stream] += (long long)(n / 2);
+        buf += n;
+        nbytes -= n;
+    }
+    return NRSC5B_OK;
+}
+
+/* input_push_cu8 / input_push_cs16 without a CUDA call: the samples are copied into page-locked memory and reach the
+ * device - one copy per stream - when the next batch is submitted (nrsc5b_submit), when the staging area (4 MiB) is
+ * full, or when nrsc5b_process runs. */
+extern "C" int nrsc5b_stage_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes)
+{
+    if (!e || e->dims.cs16) return NRSC5B_EINVAL;
+    return stage_bytes(e, stream, buf, nbytes);
+}
+
+extern "C" int nrsc5b_stage_cs16(nrsc5b_engine_t *e, int stream, const int16_t *buf, size_t nvalues)
+{
+    if (!e || !e->dims.cs16 || (nvalues & 1)) return NRSC5B_EINVAL;
+    return stage_bytes(e, stream, reinterpret_cast<const uint8_t *>(buf), 2 * nvalues);
+}
+
+static int flush_staged(nrsc5b_engine *e)
+{
+    if (e->staged.empty()) return NRSC5B_OK;
+    const uint8_t *src = e->stage[e->stage_cur];
+    std::vector<uint8_t> touched(e->dims.nstreams, 0);
+    for (const auto &g : e->staged) {
+        size_t off = (size_t)e->pushed[g.stream] * 2;
+        if (off + g.n > e->dims.in_stride) {
+            int rc = trim_stream(e, g.stream);                  // make room: drop what the window has passed
+            if (rc) return rc;
+            off = (size_t)e->pushed[g.stream] * 2;
+            if (off + g.n > e->dims.in_stride) return NRSC5B_EFULL;
+        }
+        CK(cudaMemcpyAsync(e->iq_owned + (size_t)g.stream * e->dims.in_stride + off, src + g.off, g.n, cudaMemcpyHostToDevice,
+                           e->copy_stream));
+        e->pushed[g.stream] += (long long)(g.n / 2);
+        e->staged_units[g.stream] -= (long long)(g.n / 2);
+        touched[g.stream] = 1;
+    }
+    for (int s = 0; s < e->dims.nstreams; s++)
+        if (touched[s]) {
+            int rc = publish_avail(e, s, e->copy_stream);
+            if (rc) return rc;
+        }
+    e->staged.clear();
+    CK(cudaEventRecord(e->stage_free[e->stage_cur], e->copy_stream));
+    e->stage_cur ^= 1;
+    e->stage_fill = 0;
+    CK(cudaEventSynchronize(e->stage_free[e->stage_cur]));      // the other half: its copy was issued a whole half ago
+    return NRSC5B_OK;
+}
+
+/* Enqueues - without waiting for anything - the passes that the samples staged / pushed so far can need, followed by
+ * the export of every stream's records to host memory.  Returns 1 if a batch was enqueued, 0 if there is nothing to
+ * do (no stream has a whole block buffered: nothing is launched, no CUDA call is made) or a batch is still in flight,
+ * < 0 on error.  flush != 0: also send staged input that does not complete a block yet (end of stream). */
+extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
+{
+    if (!e) return NRSC5B_EINVAL;
+    if (e->in_flight) return 0;
+    bool decode = true;
+    const int passes = plan_passes(e, true, &decode);
+    if (passes == 0) {
+        if (flush) { int rc = flush_staged(e); if (rc) return rc; }
+        return 0;
+    }
+    const int S = e->dims.nstreams;
+    if (!e->xlog) {
+        e->xlog_stride = (e->dims.log_cap + 15) & ~(size_t)15;
+        if (cudaMallocHost((void **)&e->xlog, (size_t)S * e->xlog_stride) != cudaSuccess ||
+            cudaMallocHost((void **)&e->xhdr, sizeof(ExportHdr) * S) != cudaSuccess) return NRSC5B_ENOMEM;
+    }
+    int rc = flush_staged(e);
+    if (rc) return rc;
+    {
+        const unsigned slot = e->fence_next++ & 63;
+        if (!e->fence[slot]) CK(cudaEventCreateWithFlags(&e->fence[slot], cudaEventDisableTiming));
+        CK(cudaEventRecord(e->fence[slot], e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, e->fence[slot], 0));
+    }
+    for (int i = 0; i < passes; i++) {
+        rc = launch_pass(e, i == passes - 1, i > 0 || decode);
+        if (rc) return rc;
+    }
+    k_export<<<S, 256, 0, e->stream>>>(e->dp, e->dims, e->xlog, e->xlog_stride, e->xhdr);
+    e->stats.kernel_launches += 1;
+    rc = enqueue_readback(e);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->batch_done, e->stream));
+    CK(cudaGetLastError());
+    e->in_flight = true;
+    e->batch_decoded = passes > 1 || decode;
+    return 1;
+}
+
+/* 1: the batch in flight has finished - its records are in host memory (nrsc5b_batch_records) until the next
+ * nrsc5b_submit; 0: no batch in flight, or (wait == 0) it is still running; < 0 on error. */
+extern "C" int nrsc5b_poll(nrsc5b_engine_t *e, int wait)
+{
+    if (!e) return NRSC5B_EINVAL;
+    if (!e->in_flight) return 0;
+    if (wait) CK(cudaEventSynchronize(e->batch_done));
+    else {
+        const cudaError_t q = cudaEventQuery(e->batch_done);
+        if (q == cudaErrorNotReady) return 0;
+        CK(q);
+    }
+    e->in_flight = false;
+    e->last_progress = e->h_ctl->progress;
+    if (e->batch_decoded)
+        for (int s = 0; s < e->dims.nstreams; s++) e->h_brief[s].p1_ready = 0;
+    for (int s = 0; s < e->dims.nstreams; s++)
+        if (e->xhdr[s].log_overflow) {
+            e->overflowed[s] = 1;
+            e->stats.log_overflows++;
+        }
+    if (e->h_ctl->px_need & ~(unsigned)e->dims.px_enabled) {
+        int rc = enable_px_groups(e, e->h_ctl->px_need);        // the waiting streams go on with the next batch
+        if (rc) return rc;
+    }
+    return 1;
+}
+
+/* Records of `stream` from the batch nrsc5b_poll last reported (same format as nrsc5b_drain); valid until the next
+ * nrsc5b_submit. */
+extern "C" const uint8_t *nrsc5b_batch_records(nrsc5b_engine_t *e, int stream, size_t *nbytes)
+{
+    if (!e || !e->xlog || stream < 0 || stream >= e->dims.nstreams || e->in_flight) {
+        if (nbytes) *nbytes = 0;
+        return nullptr;
+    }
+    if (nbytes) *nbytes = e->xhdr[stream].log_len;
+    return e->xlog + (size_t)stream * e->xlog_stride;
+}
 
 extern "C" int nrsc5b_synchronize(nrsc5b_engine_t *e)
 {

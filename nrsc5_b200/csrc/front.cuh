@@ -30,8 +30,6 @@ constexpr int IN_STRIDE = 8704;
 constexpr int ACQ_TILE = 4096;                     // decimated samples per acquisition tile
 
 __device__ int g_dbg;                              // experiment switches (nrsc5b_debug_set), 0 in production
-__device__ unsigned long long g_progress;          // bumped by every stream that processed a block
-__device__ unsigned g_px_need;                     // PX_NEED_* bits: a stream waits for a decode group the host has not enabled
 
 __constant__ int c_compat_mode[64];
 __constant__ unsigned c_pn80[3];                   // first 80 bits of the descrambler sequence (bit i of word i/32)
@@ -253,13 +251,13 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
             const int cm = c_compat_mode[st.psmi & 63];
             const int need = cm == 2 ? PX_NEED_SHORT : cm == 3 ? PX_NEED_P3 : cm == 11 ? (PX_NEED_P3 | PX_NEED_PX2) : 0;
             if (need & ~d.px_enabled) {
-                atomicOr(&g_px_need, (unsigned)need);
+                atomicOr(&p.ctl->px_need, (unsigned)need);
                 act = 0;
             }
         }
         st.active = act;
         sh_active = act;
-        if (act) atomicAdd(&g_progress, 1ull);
+        if (act) atomicAdd(&p.ctl->progress, 1ull);
     }
     __syncthreads();
     if (!sh_active) return false;
@@ -1154,7 +1152,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
 // ---------------------------------------------------------------------------
 // the stream-resident kernel: grid = streams, one CTA each
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDims d, int max_blocks)
+__global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDims d, int max_blocks, int last_pass)
 {
 #if defined(NB_EMU)
     unsigned char *front_smem_raw = emu::dyn_smem();
@@ -1210,6 +1208,19 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
             st.ph_cyc[0] += (unsigned long long)(clock64() - c0);
             st.ph_n[0]++;
         }
+    }
+    if (t == 0) {
+        // for the host's planning of the next batch: where the stream stands, and - after a batch's last pass -
+        // whether it could go on at once (a frame it just completed is decoded by the kernels that follow this one)
+        StreamBrief b;
+        b.start = st.start;
+        b.state = st.state;
+        b.bc = st.bc;
+        b.p1_ready = st.p1_ready;
+        b.pad_ = 0;
+        p.brief[s] = b;
+        const long long avail = *reinterpret_cast<volatile long long *>(&st.in_avail);
+        if (last_pass && avail >= 2 * (st.start + NACQ)) atomicAdd(&p.ctl->more, 1u);
     }
 }
 

@@ -40,6 +40,7 @@ typedef struct input_t
     uint8_t *bits;                      /* one bit per byte, as frame_push()/pids_frame_push() take them */
     int in_frame_push;
     int device_l2;                      /* L2 framing runs on the GPU (FM): replay REC_L2 instead of calling frame_push() */
+    int pipelined;                      /* pushes stage samples and return; batches complete behind them (default) */
 } input_t;
 
 void input_init(input_t *st, nrsc5_t *radio, output_t *output);

@@ -1,9 +1,17 @@
 /* The seven input_* functions of the reference (src/input.c:96-188, declared src/input.h:37-43) on top of
  * the B200 engine's C ABI (include/nrsc5_b200.h).  Linked with the reference's unmodified host-side
- * sources this gives a libnrsc5.so whose public API, event order and callback threading are the
- * reference's: input_push_cu8() pushes the samples to the GPU, runs what they complete, and replays the
- * engine's records - in the reference's call order - into frame_push() / pids_frame_push() /
- * nrsc5_report_*() / output_advance() on the calling thread before it returns.
+ * sources this gives a libnrsc5.so whose public API and event order are the reference's.
+ *
+ * input_push_cu8() never waits for the GPU: it copies the samples into the engine's page-locked staging area
+ * (nrsc5b_stage_cu8, no CUDA call), replays the records of a batch that has finished meanwhile - in the reference's
+ * call order, into frame_push() / pids_frame_push() / nrsc5_report_*() / output_advance() on the calling thread -
+ * and, if the samples buffered by now complete a block and no batch is in flight, enqueues the next one
+ * (nrsc5b_submit).  A push that completes no block (16 of 17 at the CLI's 32 768-byte pushes) makes no CUDA call at
+ * all.  A source that delivers in real time finds every batch finished by its next push (a block takes the GPU
+ * ~0.1 ms); a file is decoded as fast as the GPU goes, the pushes running ahead.  input_free() (nrsc5_close) and
+ * input_reset() wait for what is in flight and deliver it: nothing is lost at the end of a stream.
+ * NRSC5_B200_SYNC=1 restores the strictly synchronous behaviour (every push returns only after everything it
+ * completed has been delivered), as does NRSC5_B200_DEVICE_L2=0, whose host-side L2 feeds back into the engine.
  *
  * L2 framing runs on the GPU as well (nrsc5b_enable_l2, csrc/l2.cuh).  The engine's REC_L2 record of a frame
  * holds what the reference's frame_process() (src/frame.c:516-643) would have called, in order; replay() makes
@@ -235,6 +243,8 @@ static void engine_open(input_t *st, int cs16)
     st->engine_am = am;
     const char *dev_l2 = getenv("NRSC5_B200_DEVICE_L2");
     st->device_l2 = !(dev_l2 && !atoi(dev_l2));      /* default: on the device, FM and AM; 0: the reference's frame.c */
+    const char *sync = getenv("NRSC5_B200_SYNC");
+    st->pipelined = st->device_l2 && !(sync && atoi(sync));
     if (st->device_l2)
     {
         rc = nrsc5b_enable_l2(st->engine, 1);
@@ -249,7 +259,41 @@ static void run_and_replay(input_t *st)
     size_t need = 0;
     long got = nrsc5b_drain(st->engine, 0, st->records, st->records_cap, &need);
     if (got < 0) fail("nrsc5b_drain", (int)got);
+    if (nrsc5b_take_overflow(st->engine, 0)) fail("record log overflow (RECORDS_CAPACITY)", -1);
     replay(st, st->records, (size_t)got);
+}
+
+/* the records of a finished batch, straight from the page-locked memory the GPU exported them to */
+static void deliver_batch(input_t *st)
+{
+    size_t n = 0;
+    const uint8_t *rec = nrsc5b_batch_records(st->engine, 0, &n);
+    if (nrsc5b_take_overflow(st->engine, 0)) fail("record log overflow (RECORDS_CAPACITY)", -1);
+    if (rec && n) replay(st, rec, n);
+}
+
+/* non-blocking: take what has finished, start what can start */
+static void pump(input_t *st)
+{
+    int rc = nrsc5b_poll(st->engine, 0);
+    if (rc < 0) fail("nrsc5b_poll", rc);
+    if (rc == 1) deliver_batch(st);
+    rc = nrsc5b_submit(st->engine, 0);
+    if (rc < 0) fail("nrsc5b_submit", rc);
+}
+
+/* blocking: everything buffered so far is decoded and delivered */
+static void pump_all(input_t *st)
+{
+    for (;;)
+    {
+        int rc = nrsc5b_poll(st->engine, 1);
+        if (rc < 0) fail("nrsc5b_poll", rc);
+        if (rc == 1) deliver_batch(st);
+        rc = nrsc5b_submit(st->engine, 1);
+        if (rc < 0) fail("nrsc5b_submit", rc);
+        if (rc == 0) break;
+    }
 }
 
 void input_push_cu8(input_t *st, const uint8_t *buf, const uint32_t len)
@@ -257,11 +301,18 @@ void input_push_cu8(input_t *st, const uint8_t *buf, const uint32_t len)
     nrsc5_report_iq(st->radio, buf, len);            /* input.c:101 */
     assert(len % 4 == 0);
     engine_open(st, 0);
+    if (st->pipelined && !st->engine_am)
+    {
+        int rc = nrsc5b_stage_cu8(st->engine, 0, buf, len);
+        if (rc) fail("nrsc5b_stage_cu8", rc);
+        pump(st);
+        return;
+    }
     uint32_t done = 0;
     while (done < len)
     {
-        /* at most a quarter block per round, so that L2's sync-loss verdict (frame.c:538) always lands
-         * before the engine starts the following block, as in the reference */
+        /* synchronous mode (and AM cu8, which is decimated on arrival): at most a quarter block per round, so that a
+         * host-side L2's sync-loss verdict (frame.c:538) always lands before the engine starts the following block */
         uint32_t n = len - done;
         if (n > 65536) n = 65536;
         int rc = nrsc5b_push_cu8(st->engine, 0, buf + done, n);
@@ -276,6 +327,13 @@ void input_push_cs16(input_t *st, const int16_t *buf, const uint32_t len)
     /* input.c:119-124: FM samples that are already at 744 187.5 S/s; len counts int16 values */
     assert(len % 2 == 0);
     engine_open(st, 1);
+    if (st->pipelined)
+    {
+        int rc = nrsc5b_stage_cs16(st->engine, 0, buf, len);
+        if (rc) fail("nrsc5b_stage_cs16", rc);
+        pump(st);
+        return;
+    }
     uint32_t done = 0;
     while (done < len)
     {
@@ -290,7 +348,7 @@ void input_push_cs16(input_t *st, const int16_t *buf, const uint32_t len)
 
 void input_reset(input_t *st)
 {
-    /* input.c:126-138 */
+    /* input.c:126-138 (buffered samples and what they would have decoded to are dropped, as in the reference) */
     if (st->sync_state == SYNC_STATE_FINE)
         nrsc5_report_lost_sync(st->radio);
     st->sync_state = SYNC_STATE_NONE;
@@ -326,6 +384,10 @@ void input_set_mode(input_t *st)
 
 void input_free(input_t *st)
 {
+    /* the reference has no flush and decodes inside the pushes; here the tail of the stream may still be on its way:
+     * deliver it before the handle goes (nrsc5_close -> input_free, nrsc5.c:429) */
+    if (st->engine && st->pipelined)
+        pump_all(st);
     frame_free(&st->frame);
     nrsc5b_destroy(st->engine);
     free(st->records);
