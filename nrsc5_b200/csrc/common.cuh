@@ -72,6 +72,7 @@ struct StreamState {
     int active;                // this step has a full window for the stream
     int blk_samperr;
     int blk_state_in;
+    int blk_go;                // cluster per stream: the owner CTA's word to its helpers - 1 demodulate this block, 0 leave
     float theta;               // NCO step, radians per decimated sample
     float2 phase0;             // NCO phase at the first sample of the block
     // P1 hand-off sync -> p1 kernel
@@ -128,6 +129,7 @@ struct EngineDims {
     int cs16;                  // input is cs16 at the decimated rate: 4 bytes per sample, no halfband
     int px_enabled;            // PX_NEED_* bits: the extended-partition decode groups the host launches after k_stream
     int l2;                    // frames also go through L2 on the device (nrsc5b_enable_l2)
+    int cluster;               // CTAs per stream in k_stream (thread-block cluster): 1, 2 or 4
 };
 
 // buffers of one extra extended-partition decode group (same roles as the p3_* arrays)

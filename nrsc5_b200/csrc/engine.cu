@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -694,6 +695,14 @@ struct nrsc5b_engine {
     cudaEvent_t stage_free[2];
     std::vector<Staged> staged;
     std::vector<long long> staged_units;   // per stream: staged 2-byte units not yet counted in `pushed`
+    std::vector<uint8_t> unpublished;      // per stream: samples copied to the device whose count the kernels have not been told
+    bool direct_push;                      // a push outside the staging area since the last batch (its count is published at once)
+    // NRSC5_B200_TRACE=1: where the host side of the asynchronous path spends its time (printed by nrsc5b_destroy)
+    struct Trace {
+        unsigned long long batches, passes, decode_passes, flushes, trims, polls_ready, submits_idle;
+        double s_flush, s_trim, s_stage_wait, s_submit, s_poll_wait;
+    } tr;
+    bool trace_on;
     std::vector<void *> allocs;
     int v64_ch;                        // chunk length of the fast P1 Viterbi (chosen from the stream count)
     nbam::AmState *am_st;              // AM mode: per-stream state, work arrays, tables
@@ -837,6 +846,10 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->dims.px_enabled = 0;
     e->pushed.assign(S, 0);
     e->staged_units.assign(S, 0);
+    e->unpublished.assign(S, 0);
+    e->direct_push = false;
+    e->tr = {};
+    e->trace_on = getenv("NRSC5_B200_TRACE") != nullptr;
     e->drained.assign(S, 0);
     e->overflowed.assign(S, 0);
     int rc = upload_tables(cfg->device);
@@ -1050,6 +1063,35 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         nrsc5b_destroy(e);
         return NRSC5B_ECUDA;
     }
+    e->dims.cluster = 1;
+#if !defined(NB_EMU)
+    if (cfg->mode == NRSC5B_MODE_FM) {
+        // fewer streams than SMs: a cluster of 4 or 2 CTAs per stream shares the demodulation of every block
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        const char *force = getenv("NRSC5_B200_CLUSTER");
+        for (int c = 4; c >= 2; c >>= 1) {
+            if (force ? atoi(force) != c : S * c > sms) continue;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3((unsigned)(S * c));
+            lc.blockDim = dim3(FRONT_THREADS);
+            lc.dynamicSmemBytes = sizeof(FrontSmem);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)c;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_stream, &lc) == cudaSuccess && (force || nclusters >= S)) {
+                e->dims.cluster = c;
+                break;
+            }
+            cudaGetLastError();
+        }
+    }
+#endif
     *out = e;
     rc = nrsc5b_reset(e, -1);
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = NRSC5B_ECUDA;
@@ -1061,6 +1103,23 @@ extern "C" void nrsc5b_destroy(nrsc5b_engine_t *e)
 {
     if (!e) return;
     cudaDeviceSynchronize();
+    if (e->trace_on && e->h_state) {
+        // SM cycles stream 0's k_stream spent per phase (device clock): what the GPU side of the wall time is made of
+        if (cudaMemcpy(e->h_state, e->dp.st, sizeof(StreamState), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const StreamState &z = e->h_state[0];
+            fprintf(stderr, "nrsc5_b200 trace: stream 0 k_stream Mcycles {pids %.2f, prep_acq %.2f (%llu), prep_fine %.2f (%llu), demod %.2f (%llu), "
+                            "sync_fine %.2f, sync_acq %.2f}, blocks %llu, frames %llu\n",
+                    z.ph_cyc[0] * 1e-6, z.ph_cyc[1] * 1e-6, z.ph_n[1], z.ph_cyc[2] * 1e-6, z.ph_n[2], z.ph_cyc[3] * 1e-6, z.ph_n[3],
+                    z.ph_cyc[4] * 1e-6, z.ph_cyc[5] * 1e-6, z.blocks_done, z.frames_done);
+        }
+    }
+    if (e->trace_on)
+        fprintf(stderr, "nrsc5_b200 trace: {\"batches\": %llu, \"passes\": %llu, \"decode_passes\": %llu, \"launches\": %llu, \"flushes\": %llu, "
+                        "\"trims\": %llu, \"polls_ready\": %llu, \"submits_idle\": %llu, \"s_submit\": %.6f, \"s_flush\": %.6f, \"s_stage_wait\": %.6f, "
+                        "\"s_trim\": %.6f, \"s_poll_wait\": %.6f, \"cluster\": %d}\n",
+                e->tr.batches, e->tr.passes, e->tr.decode_passes, (unsigned long long)e->stats.kernel_launches, e->tr.flushes, e->tr.trims,
+                e->tr.polls_ready, e->tr.submits_idle, e->tr.s_submit, e->tr.s_flush, e->tr.s_stage_wait, e->tr.s_trim, e->tr.s_poll_wait,
+                e->dims.cluster);
     for (void *q : e->allocs) cudaFree(q);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_state) cudaFreeHost(e->h_state);
@@ -1156,6 +1215,27 @@ extern "C" int nrsc5b_rewind(nrsc5b_engine_t *e)
     }
     CK(cudaGetLastError());
     return NRSC5B_OK;
+}
+
+static double wall_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static int publish_avail(nrsc5b_engine *e, int s, cudaStream_t on);
+
+// tells the kernels (on stream `on`) about the staged samples copied since the last time
+static int publish_pending(nrsc5b_engine *e, cudaStream_t on)
+{
+    for (int s = 0; s < e->dims.nstreams; s++)
+        if (e->unpublished[s]) {
+            int rc = publish_avail(e, s, on);
+            if (rc) return rc;
+            e->unpublished[s] = 0;
+        }
+    return 0;
 }
 
 static int publish_avail(nrsc5b_engine *e, int s, cudaStream_t on)
@@ -1272,6 +1352,7 @@ static int push_am_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_
             e->stats.kernel_launches += 1;
             e->am_dec_out[stream] = can;
             e->pushed[stream] += 2LL * nout;
+            e->direct_push = true;
             rc = publish_avail(e, stream, e->copy_stream);
             if (rc) return rc;
         }
@@ -1306,6 +1387,7 @@ static int push_bytes(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t
         if (rc) return rc;
     }
     e->pushed[stream] += (long long)(nbytes / 2);
+    e->direct_push = true;
     // published on the copy stream, i.e. after the samples themselves have landed
     return publish_avail(e, stream, e->copy_stream);
 }
@@ -1330,6 +1412,7 @@ extern "C" int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size
     CK(cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(e->dp.st) + offsetof(StreamState, in_avail), sizeof(StreamState), row,
                          sizeof(long long), sizeof(long long), S, cudaMemcpyHostToDevice, e->copy_stream));
     for (int s = 0; s < S; s++) e->pushed[s] += (long long)(nbytes / 2);
+    e->direct_push = true;
     return NRSC5B_OK;
 }
 
@@ -1341,6 +1424,7 @@ extern "C" int nrsc5b_push_cu8_device(nrsc5b_engine_t *e, int stream, const void
     CK(cudaMemcpyAsync(e->iq_owned + (size_t)stream * e->dims.in_stride + off, dev_buf, nbytes,
                        cudaMemcpyDeviceToDevice, e->stream));
     e->pushed[stream] += (long long)(nbytes / 2);
+    e->direct_push = true;
     return publish_avail(e, stream, e->stream);
 }
 
@@ -1349,6 +1433,7 @@ extern "C" int nrsc5b_attach_device_input(nrsc5b_engine_t *e, const void *dev_bu
     if (!e || !dev_buf || (nbytes & 3) || nbytes > stride || e->am_ring) return NRSC5B_EINVAL;   // AM cu8 is decimated on arrival
     e->dp.iq = reinterpret_cast<const uint8_t *>(dev_buf);
     e->dims.in_stride = stride;
+    e->direct_push = true;
     for (int s = 0; s < e->dims.nstreams; s++) {
         e->pushed[s] = (long long)(nbytes / 2);
         int rc = publish_avail(e, s, e->stream);
@@ -1443,6 +1528,32 @@ static int enable_px_groups(nrsc5b_engine *e, unsigned need)
 // groups and k_l2 would find nothing.
 constexpr int BLOCKS_PER_PASS = 16;
 
+// k_stream with one CTA per stream, or - engines with few streams - a thread-block cluster of dims.cluster CTAs per
+// stream (the cluster dimension is a launch attribute)
+static void launch_k_stream(nrsc5b_engine *e, int last_pass)
+{
+    const int S = e->dims.nstreams, C = e->dims.cluster > 1 ? e->dims.cluster : 1;
+#if !defined(NB_EMU)
+    if (C > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(S * C));
+        cfg.blockDim = dim3(FRONT_THREADS);
+        cfg.dynamicSmemBytes = sizeof(FrontSmem);
+        cfg.stream = e->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)C;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_stream, e->dp, e->dims, (int)BLOCKS_PER_PASS, last_pass);
+        return;
+    }
+#endif
+    k_stream<<<S, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS, last_pass);
+}
+
 static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true)
 {
     if (last_pass) cudaMemsetAsync(reinterpret_cast<uint8_t *>(e->dp.ctl) + offsetof(EngineCtl, more), 0, sizeof(unsigned), e->stream);
@@ -1459,7 +1570,7 @@ static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true
     }
     const bool prof = e->profiling != 0;
     if (prof) cudaEventRecord(e->pev[0], e->stream);
-    k_stream<<<e->dims.nstreams, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS, last_pass ? 1 : 0);
+    launch_k_stream(e, last_pass ? 1 : 0);
     e->stats.kernel_launches += 1;
     if (prof) cudaEventRecord(e->pev[1], e->stream);
     if (with_decode) launch_p1(e);
@@ -1578,6 +1689,7 @@ static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
     if (e->in_flight) return NRSC5B_EINVAL;                // an asynchronous batch is open: nrsc5b_poll first
     {
         int rc = flush_staged(e);
+        if (!rc) rc = publish_pending(e, e->copy_stream);
         if (rc) return rc;
     }
     if (wait_for_copies) {
@@ -1694,13 +1806,17 @@ extern "C" int nrsc5b_stage_cs16(nrsc5b_engine_t *e, int stream, const int16_t *
 
 static int flush_staged(nrsc5b_engine *e)
 {
+    // The samples travel now; the kernels are told about them by the next batch (publish_pending on the compute
+    // stream, nrsc5b_submit) - never in the middle of one: a batch sees exactly the sample counts it was planned with.
     if (e->staged.empty()) return NRSC5B_OK;
+    const double t0 = e->trace_on ? wall_s() : 0;
     const uint8_t *src = e->stage[e->stage_cur];
-    std::vector<uint8_t> touched(e->dims.nstreams, 0);
     for (const auto &g : e->staged) {
         size_t off = (size_t)e->pushed[g.stream] * 2;
         if (off + g.n > e->dims.in_stride) {
+            const double t1 = e->trace_on ? wall_s() : 0;
             int rc = trim_stream(e, g.stream);                  // make room: drop what the window has passed
+            if (e->trace_on) { e->tr.trims++; e->tr.s_trim += wall_s() - t1; }
             if (rc) return rc;
             off = (size_t)e->pushed[g.stream] * 2;
             if (off + g.n > e->dims.in_stride) return NRSC5B_EFULL;
@@ -1709,18 +1825,15 @@ static int flush_staged(nrsc5b_engine *e)
                            e->copy_stream));
         e->pushed[g.stream] += (long long)(g.n / 2);
         e->staged_units[g.stream] -= (long long)(g.n / 2);
-        touched[g.stream] = 1;
+        e->unpublished[g.stream] = 1;
     }
-    for (int s = 0; s < e->dims.nstreams; s++)
-        if (touched[s]) {
-            int rc = publish_avail(e, s, e->copy_stream);
-            if (rc) return rc;
-        }
     e->staged.clear();
     CK(cudaEventRecord(e->stage_free[e->stage_cur], e->copy_stream));
     e->stage_cur ^= 1;
     e->stage_fill = 0;
+    const double t2 = e->trace_on ? wall_s() : 0;
     CK(cudaEventSynchronize(e->stage_free[e->stage_cur]));      // the other half: its copy was issued a whole half ago
+    if (e->trace_on) { e->tr.flushes++; e->tr.s_stage_wait += wall_s() - t2; e->tr.s_flush += wall_s() - t0; }
     return NRSC5B_OK;
 }
 
@@ -1736,8 +1849,12 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
     const int passes = plan_passes(e, true, &decode);
     if (passes == 0) {
         if (flush) { int rc = flush_staged(e); if (rc) return rc; }
+        if (e->trace_on) e->tr.submits_idle++;
         return 0;
     }
+    const double t0 = e->trace_on ? wall_s() : 0;
+    if (e->direct_push) decode = true;                     // counts published outside a batch: plan nothing on them
+    e->direct_push = false;
     const int S = e->dims.nstreams;
     if (!e->xlog) {
         e->xlog_stride = (e->dims.log_cap + 15) & ~(size_t)15;
@@ -1752,10 +1869,13 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
         CK(cudaEventRecord(e->fence[slot], e->copy_stream));
         CK(cudaStreamWaitEvent(e->stream, e->fence[slot], 0));
     }
+    rc = publish_pending(e, e->stream);                    // behind the copies, in front of the passes
+    if (rc) return rc;
     for (int i = 0; i < passes; i++) {
         rc = launch_pass(e, i == passes - 1, i > 0 || decode);
         if (rc) return rc;
     }
+    if (e->trace_on) { e->tr.batches++; e->tr.passes += passes; e->tr.decode_passes += passes - 1 + (decode ? 1 : 0); }
     k_export<<<S, 256, 0, e->stream>>>(e->dp, e->dims, e->xlog, e->xlog_stride, e->xhdr);
     e->stats.kernel_launches += 1;
     rc = enqueue_readback(e);
@@ -1764,6 +1884,7 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
     CK(cudaGetLastError());
     e->in_flight = true;
     e->batch_decoded = passes > 1 || decode;
+    if (e->trace_on) e->tr.s_submit += wall_s() - t0;
     return 1;
 }
 
@@ -1773,13 +1894,17 @@ extern "C" int nrsc5b_poll(nrsc5b_engine_t *e, int wait)
 {
     if (!e) return NRSC5B_EINVAL;
     if (!e->in_flight) return 0;
-    if (wait) CK(cudaEventSynchronize(e->batch_done));
-    else {
+    if (wait) {
+        const double t0 = e->trace_on ? wall_s() : 0;
+        CK(cudaEventSynchronize(e->batch_done));
+        if (e->trace_on) e->tr.s_poll_wait += wall_s() - t0;
+    } else {
         const cudaError_t q = cudaEventQuery(e->batch_done);
         if (q == cudaErrorNotReady) return 0;
         CK(q);
     }
     e->in_flight = false;
+    if (e->trace_on) e->tr.polls_ready++;
     e->last_progress = e->h_ctl->progress;
     if (e->batch_decoded)
         for (int s = 0; s < e->dims.nstreams; s++) e->h_brief[s].p1_ready = 0;

@@ -230,6 +230,19 @@ __device__ __forceinline__ int2 halfband_words(const uint32_t *w)
     return make_int2(ar, ai);
 }
 
+// NCO of a block in closed form, with the pulse shape folded in (acquire.c:243-252): nco[j] = shape[j] * exp(j*theta*j)
+__device__ __forceinline__ void fill_nco(const DevPtrs &p, float2 *nco, float theta, int t)
+{
+    for (int j = t; j < NSYM; j += FRONT_THREADS) {
+        float2 e = cexp_j(theta * (float)j);
+        if (j < NCP || j >= NFFT) {
+            const float w = __ldg(&p.shape[j]);
+            e = make_float2(e.x * w, e.y * w);
+        }
+        nco[j] = e;
+    }
+}
+
 // Returns false (uniformly) when the stream has no complete 33-symbol window buffered.
 __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, float2 *nco, int t)
 {
@@ -412,17 +425,7 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
     __syncthreads();
     // NCO of this block in closed form, with the pulse shape folded in (acquire.c:243-252):
     // nco[j] = shape[j] * exp(j*theta*j); the per-symbol phase is applied to the kept bins
-    {
-        const float theta = sh_theta;
-        for (int j = t; j < NSYM; j += FRONT_THREADS) {
-            float2 e = cexp_j(theta * (float)j);
-            if (j < NCP || j >= NFFT) {
-                const float w = __ldg(&p.shape[j]);
-                e = make_float2(e.x * w, e.y * w);
-            }
-            nco[j] = e;
-        }
-    }
+    fill_nco(p, nco, sh_theta, t);
     __syncthreads();
     return true;
 }
@@ -625,7 +628,9 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
     StreamState &st = p.st[s];
     float *cfreq = p.cfreq + (size_t)s * NFFT;
     float *cphase = p.cphase + (size_t)s * NFFT;
-    float2 *bins = p.bins + (size_t)s * BLK * NBINS;          // [symbol][534]
+    // [symbol][534]; written by the demodulating teams - with a cluster per stream, on other SMs - so every read here
+    // goes to L2 (__ldcg), never to this SM's L1
+    float2 *bins = p.bins + (size_t)s * BLK * NBINS;
     const float loop_bw = 0.05f, damping = 0.70710678f;
     const float denom = 1 + (2 * damping * loop_bw) + (loop_bw * loop_bw);
     const float alpha = (4 * damping * loop_bw) / denom, beta = (4 * loop_bw * loop_bw) / denom;
@@ -650,7 +655,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             const int sb = r >= rows, rr = sb ? r - rows : r;
             const int i = rr / (PW - 1), k = rr - i * (PW - 1) + 1;
             const int ci = sb == 0 ? PW * i + k : (NBINS - 1 - PW) - PW * i + k;
-            sm.eq[r][n] = bins[(size_t)n * NBINS + ci];
+            sm.eq[r][n] = __ldcg(&bins[(size_t)n * NBINS + ci]);
         }
     };
     const bool pre_staged = st.state == ST_FINE && !(g_dbg & 1);   // partitions known: stage while warp 0 runs the Costas loops
@@ -658,7 +663,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
     for (int i = t; i < ZS * BLK; i += FRONT_THREADS) {
         const int slot = i & (ZS - 1), n = i / ZS;
         const int ii = slot < MAXREF ? slot : slot - MAXREF;
-        if (slot < 2 * MAXREF && ii < nref) sm.zref[n][slot] = bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))];
+        if (slot < 2 * MAXREF && ii < nref) sm.zref[n][slot] = __ldcg(&bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))]);
     }
     __syncthreads();
     sylap(0);
@@ -782,7 +787,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     const float2 *src = q ? snap + (size_t)(q - 1) * BLK * NSB + t : nullptr;
                     for (int n = 0; n < BLK; n++)
                         row[(size_t)n * NSB] = q ? src[(size_t)n * NSB]
-                                                 : (ci >= 0 ? bins[(size_t)n * NBINS + ci] : make_float2(0.f, 0.f));
+                                                 : (ci >= 0 ? __ldcg(&bins[(size_t)n * NBINS + ci]) : make_float2(0.f, 0.f));
                     costas_row(row, sphs + t, NSB, f, ph, cfo, alpha, beta);
                     sm.srch.offs[cfo + 2 * PW][2 * i + upper] = ref_find(row, NSB, (unsigned)(30 - i) & 3);
                     for (int n = 0; n < BLK; n++)            // reset_ref (sync.c:132-136)
@@ -927,7 +932,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
                 const float rden = __fdividef(19.0f, c * c + dd * dd);
                 const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
-                const float2 v = cmulf(bins[(size_t)n * NBINS + ci], C);
+                const float2 v = cmulf(__ldcg(&bins[(size_t)n * NBINS + ci]), C);
                 bins[(size_t)n * NBINS + ci] = v;
                 const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
                 const float e = dx * dx + dy * dy;
@@ -1015,8 +1020,8 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     b = sm.eq[r + 1][n];
                 } else {
                     const int ci = (sb == 0 ? PW * i : (NBINS - 1 - PW) - PW * i) + 1 + 2 * c4;
-                    a = bins[(size_t)n * NBINS + ci];
-                    b = bins[(size_t)n * NBINS + ci + 1];
+                    a = __ldcg(&bins[(size_t)n * NBINS + ci]);
+                    b = __ldcg(&bins[(size_t)n * NBINS + ci + 1]);
                 }
                 const float mult = sm.mult[lower_scale_only ? 0 : sb];
                 const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
@@ -1150,8 +1155,22 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
 }
 
 // ---------------------------------------------------------------------------
-// the stream-resident kernel: grid = streams, one CTA each
+// the stream-resident kernel: one CTA per stream - or, when the engine has fewer streams than the GPU has SMs, a
+// thread-block CLUSTER of d.cluster CTAs per stream (engine.cu picks 1, 2 or 4): the cluster's first CTA owns the
+// stream (prep, sync, feedback, bookkeeping), all of them demodulate - 8 teams each, so a block's 32 symbols take
+// 4 / 2 / 1 rounds - and hand the kept bins over through L2.  The hand-offs are two hardware cluster barriers per
+// block (barrier.cluster, release / acquire); the block's parameters travel through the stream's state in global
+// memory, every CTA builds its own copy of the NCO table.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_barrier()
+{
+#if defined(NB_EMU)
+    // (the emulator runs one CTA at a time: engines are created with cluster = 1 there)
+#else
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+
 __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDims d, int max_blocks, int last_pass)
 {
 #if defined(NB_EMU)
@@ -1161,45 +1180,69 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
 #endif
     FrontSmem &sm = *reinterpret_cast<FrontSmem *>(front_smem_raw);
     const int t = threadIdx.x, team = t >> 7, tl = t & 127;
-    const int s = blockIdx.x;
+    const int C = d.cluster > 1 ? d.cluster : 1;
+    const int s = (int)blockIdx.x / C, rank = (int)blockIdx.x % C;
     StreamState &st = p.st[s];
     for (int i = t; i < FFT_TW; i += FRONT_THREADS) sm.tw[i] = __ldg(&p.twid[i]);
     __syncthreads();
 
+    const bool owner = rank == 0;
     if (max_blocks > 16) max_blocks = 16;             // the PIDS queue (and its interleaver matrix rows) hold 16 blocks
-    if (t == 0) {                                     // decoded by the kernels that followed the previous pass
+    if (owner && t == 0) {                            // decoded by the kernels that followed the previous pass
         st.p3_pending = 0;
         st.xq_pending[0] = 0;
         st.xq_pending[1] = 0;
     }
     __syncthreads();
-    for (int nb = 0; nb < max_blocks; nb++) {
-        // a completed interleaver matrix is decoded (and its header checked) before the next block
-        if (st.p1_ready) break;
+    for (int nb = 0;; nb++) {
         long long c0 = clock64();
         auto lap = [&](int ph) {
-            if (t == 0) {
+            if (owner && t == 0) {
                 const long long c1 = clock64();
                 st.ph_cyc[ph] += (unsigned long long)(c1 - c0);
                 st.ph_n[ph]++;
                 c0 = c1;
             }
         };
-        if (!front_prep(p, d, s, sm.u.prep, sm.nco, t)) break;
+        // a completed interleaver matrix is decoded (and its header checked) before the next block
+        bool go = false;
+        if (owner) {
+            go = nb < max_blocks && !st.p1_ready;
+            if (go) go = front_prep(p, d, s, sm.u.prep, sm.nco, t);
+        }
+        if (C > 1) {
+            if (owner && t == 0) {
+                st.blk_go = go ? 1 : 0;
+                __threadfence();
+            }
+            cluster_barrier();                        // the helpers read the block's parameters behind this barrier
+            if (!owner) go = __ldcg(&st.blk_go) != 0;
+        }
+        if (!go) break;
         lap(st.blk_state_in == ST_FINE ? 2 : 1);
-        const long long start = st.start;
-        const int samperr = st.blk_samperr;
-        const float theta = st.theta;
-        const float2 phase0 = st.phase0;
+        const long long start = __ldcg(&st.start);
+        const int samperr = __ldcg(&st.blk_samperr);
+        const float theta = __ldcg(&st.theta);
+        const float2 phase0 = __ldcg(&st.phase0);
+        if (!owner) {                                 // a helper CTA builds its own copy of the block's NCO table
+            fill_nco(p, sm.nco, theta, t);
+            __syncthreads();
+        }
 #pragma unroll 1
-        for (int pass = 0; pass < BLK / TEAMS; pass++)
-            front_demod(p, d, s, pass * TEAMS + team, sm.u.demod, sm.nco, sm.tw, team, tl, start, samperr, theta, phase0);
+        for (int pass = 0; pass < BLK / (TEAMS * C); pass++)
+            front_demod(p, d, s, (pass * C + rank) * TEAMS + team, sm.u.demod, sm.nco, sm.tw, team, tl, start, samperr, theta, phase0);
+        if (C > 1) {
+            __threadfence();
+            cluster_barrier();                        // every CTA's bins are in L2
+        }
+        if (!owner) continue;
         __syncthreads();
         lap(3);
         front_sync(p, d, s, sm.u.sync, t);
         __syncthreads();
         lap(st.blk_state_in == ST_FINE ? 4 : 5);
     }
+    if (!owner) return;
     __syncthreads();
     if (st.pids_pending) {
         const long long c0 = clock64();

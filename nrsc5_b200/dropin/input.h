@@ -41,6 +41,9 @@ typedef struct input_t
     int in_frame_push;
     int device_l2;                      /* L2 framing runs on the GPU (FM): replay REC_L2 instead of calling frame_push() */
     int pipelined;                      /* pushes stage samples and return; batches complete behind them (default) */
+    int trace;                          /* NRSC5_B200_TRACE: time spent delivering records, printed by input_free() */
+    unsigned long trace_batches, trace_bytes;
+    double trace_replay_s;
 } input_t;
 
 void input_init(input_t *st, nrsc5_t *radio, output_t *output);

@@ -25,6 +25,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "defines.h"
 #include "input.h"
@@ -243,6 +244,7 @@ static void engine_open(input_t *st, int cs16)
     st->engine_am = am;
     const char *dev_l2 = getenv("NRSC5_B200_DEVICE_L2");
     st->device_l2 = !(dev_l2 && !atoi(dev_l2));      /* default: on the device, FM and AM; 0: the reference's frame.c */
+    st->trace = getenv("NRSC5_B200_TRACE") != NULL;
     const char *sync = getenv("NRSC5_B200_SYNC");
     st->pipelined = st->device_l2 && !(sync && atoi(sync));
     if (st->device_l2)
@@ -263,13 +265,22 @@ static void run_and_replay(input_t *st)
     replay(st, st->records, (size_t)got);
 }
 
+static double seam_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 /* the records of a finished batch, straight from the page-locked memory the GPU exported them to */
 static void deliver_batch(input_t *st)
 {
     size_t n = 0;
     const uint8_t *rec = nrsc5b_batch_records(st->engine, 0, &n);
-    if (nrsc5b_take_overflow(st->engine, 0)) fail("record log overflow (RECORDS_CAPACITY)", -1);
+    if (nrsc5b_take_overflow(st->engine, 0)) fail("record log overflow (RECORDS_CAPACITY) or a frame exported undecoded", -1);
+    const double t0 = st->trace ? seam_now() : 0;
     if (rec && n) replay(st, rec, n);
+    if (st->trace) { st->trace_replay_s += seam_now() - t0; st->trace_batches++; st->trace_bytes += n; }
 }
 
 /* non-blocking: take what has finished, start what can start */
@@ -388,6 +399,9 @@ void input_free(input_t *st)
      * deliver it before the handle goes (nrsc5_close -> input_free, nrsc5.c:429) */
     if (st->engine && st->pipelined)
         pump_all(st);
+    if (st->trace)
+        fprintf(stderr, "libnrsc5 (B200) trace: %lu batches delivered, %lu record bytes, %.6f s in the replay (callbacks included)\n",
+                st->trace_batches, st->trace_bytes, st->trace_replay_s);
     frame_free(&st->frame);
     nrsc5b_destroy(st->engine);
     free(st->records);

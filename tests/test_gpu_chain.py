@@ -168,6 +168,26 @@ def test_multi_stream_independent():
             assert any(synth.pack_bits(f) in pdus(recs)[0] for f in c.p1_frames)      # round trip
 
 
+@pytest.mark.parametrize("ctas", [1, 2, 4])
+def test_cluster_per_stream_equals_oracle(ctas, monkeypatch):
+    """Engines with fewer streams than the GPU has SMs give every stream a thread-block cluster of 2 or 4 CTAs that
+    share the demodulation of each block (front.cuh: k_stream).  Forced to 1, 2 and 4 CTAs per stream, three streams
+    (MP1 behind a 2 kHz carrier offset in noise - the CFO search -, MP1 with a bad header - sync loss and
+    re-acquisition -, MP3 with P3) must come out as the oracle decodes them, record for record."""
+    monkeypatch.setenv("NRSC5_B200_CLUSTER", str(ctas))
+    caps = [synth.make_fm_mp1(**common.SYNTH_CASES["mp1_cfo2000_awgn20"]).cu8,
+            synth.make_fm_mp1(**common.SYNTH_CASES["mp1_badhdr"]).cu8,
+            synth.make_fm_mp3(**common.MP3_CASE).cu8]
+    outs = run_engine(caps)
+    for cu8, recs in zip(caps, outs):
+        ref = port.decode(cu8)
+        frames = [(r["lc"], r["nbits"], r["bits"]) for t, r in recs if t == eng.REC_FRAME]
+        want = [(p["lc"], p["nbits"], p["bits"]) for t, p in ref.records if t == reftap.REC_FRAME]
+        assert frames == want
+        assert pdus(recs)[1] == ref.pids_frames
+        assert kinds(recs) == oracle_kinds(ref)
+
+
 def test_sample_xz_bit_exact():
     raw = common.load_sample()
     if raw is None:
