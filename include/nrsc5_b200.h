@@ -153,7 +153,9 @@ int nrsc5b_process_fence(nrsc5b_engine_t *e, int token);
 /* ---- asynchronous use: nothing below waits for the GPU unless asked to ----
  * nrsc5b_stage_cu8 / _cs16: input_push_cu8 / input_push_cs16 (reference src/input.c:96-124) without a CUDA call - the
  *     samples are copied into page-locked staging memory and travel to the device, one copy per stream, with the next
- *     batch (or when the 4 MiB staging area is full, or at nrsc5b_process).
+ *     batch (or when the 4 MiB staging area is full, or at nrsc5b_process).  NRSC5B_EFULL: the device buffer is full of
+ *     samples the receiver has not used yet; the engine keeps the rest of the call's samples - wait for the batch in
+ *     flight (nrsc5b_poll), submit the next, and call again with (NULL, 0) until it returns 0.
  * nrsc5b_submit: enqueue the passes the buffered samples can need (sized on the host from the sample counts and the
  *     streams' last known window positions: a caller that pushes less than a block at a time launches nothing on most
  *     calls) followed by the export of all records to page-locked host memory.  1 = enqueued, 0 = nothing to do or a

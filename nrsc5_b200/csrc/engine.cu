@@ -686,6 +686,8 @@ struct nrsc5b_engine {
     ExportHdr *xhdr;                   // [S], page-locked
     cudaEvent_t batch_done;
     bool in_flight, batch_decoded;
+    bool stalled;                      // the last batch moved no stream although the host's count said it could: no new
+    long long stalled_units;           // batch until more samples have arrived (guards the caller's flush loop)
     // staged input (nrsc5b_stage_cu8 / _cs16): pushes land in page-locked memory and go to the device in one copy
     // per stream when a batch is submitted
     struct Staged { int stream; size_t off, n; };
@@ -694,6 +696,8 @@ struct nrsc5b_engine {
     int stage_cur;
     cudaEvent_t stage_free[2];
     std::vector<Staged> staged;
+    std::vector<uint8_t> carry;            // samples of a staging call that found the device buffer full (NRSC5B_EFULL)
+    int carry_stream;
     std::vector<long long> staged_units;   // per stream: staged 2-byte units not yet counted in `pushed`
     std::vector<uint8_t> unpublished;      // per stream: samples copied to the device whose count the kernels have not been told
     bool direct_push;                      // a push outside the staging area since the last batch (its count is published at once)
@@ -800,6 +804,8 @@ static void init_state_host(StreamState &st)
     st.force_state = -1;
 }
 
+static void launch_k_stream(nrsc5b_engine *e, int last_pass);
+
 extern "C" const char *nrsc5b_version(void) { return "nrsc5_b200 0.1 (sm_100a)"; }
 
 extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
@@ -830,7 +836,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     e->stats = nrsc5b_stats_t{};
     e->last_progress = 0;
     e->h_ctl = nullptr; e->h_brief = nullptr;
-    e->xlog = nullptr; e->xlog_stride = 0; e->xhdr = nullptr; e->batch_done = nullptr; e->in_flight = false; e->batch_decoded = false;
+    e->xlog = nullptr; e->xlog_stride = 0; e->xhdr = nullptr; e->batch_done = nullptr; e->in_flight = false; e->batch_decoded = false; e->stalled = false; e->stalled_units = 0;
     e->stage[0] = e->stage[1] = nullptr; e->stage_cap = 0; e->stage_fill = 0; e->stage_cur = 0;
     e->stage_free[0] = e->stage_free[1] = nullptr;
     e->profiling = 0;
@@ -1057,7 +1063,8 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
         nrsc5b_destroy(e);
         return NRSC5B_ENOMEM;
     }
-    if (cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(k_v64_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V64_EMIT_SMEM) != cudaSuccess) {
         nrsc5b_destroy(e);
@@ -1084,7 +1091,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
             lc.attrs = at;
             lc.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, k_stream, &lc) == cudaSuccess && (force || nclusters >= S)) {
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_stream<true>, &lc) == cudaSuccess && (force || nclusters >= S)) {
                 e->dims.cluster = c;
                 break;
             }
@@ -1095,6 +1102,18 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     *out = e;
     rc = nrsc5b_reset(e, -1);
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = NRSC5B_ECUDA;
+#if !defined(NB_EMU)
+    if (rc == 0 && e->dims.cluster > 1) {
+        // trial launch (no input yet: every stream returns at once): a cluster shape the device refuses falls back to
+        // one CTA per stream instead of failing later
+        launch_k_stream(e, 0);
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            cudaGetLastError();
+            fprintf(stderr, "nrsc5_b200: clusters of %d CTAs per stream not available here, using one CTA per stream\n", e->dims.cluster);
+            e->dims.cluster = 1;
+        }
+    }
+#endif
     if (rc) { nrsc5b_destroy(e); *out = nullptr; return rc; }
     return NRSC5B_OK;
 }
@@ -1547,11 +1566,14 @@ static void launch_k_stream(nrsc5b_engine *e, int last_pass)
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_stream, e->dp, e->dims, (int)BLOCKS_PER_PASS, last_pass);
+        if (cudaLaunchKernelEx(&cfg, k_stream<true>, e->dp, e->dims, (int)BLOCKS_PER_PASS, last_pass) != cudaSuccess) {
+            // (checked once at creation with a trial launch; a failure here is reported by the caller's cudaGetLastError)
+            fprintf(stderr, "nrsc5_b200: cluster launch of k_stream failed: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
+        }
         return;
     }
 #endif
-    k_stream<<<S, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS, last_pass);
+    k_stream<false><<<S, FRONT_THREADS, sizeof(FrontSmem), e->stream>>>(e->dp, e->dims, BLOCKS_PER_PASS, last_pass);
 }
 
 static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true)
@@ -1770,9 +1792,27 @@ static int stage_bytes(nrsc5b_engine *e, int stream, const uint8_t *buf, size_t 
             CK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
         }
     }
+    // a call that came back with NRSC5B_EFULL left the rest of its samples here (the caller's buffer may be gone by
+    // the time it retries): they go first; the retry passes (NULL, 0)
+    if (!e->carry.empty()) {
+        std::vector<uint8_t> rest;
+        rest.swap(e->carry);
+        const int cs = e->carry_stream;
+        int rc = stage_bytes(e, cs, rest.data(), rest.size());
+        if (rc) {
+            if (rc == NRSC5B_EFULL && nbytes) {                 // still no room: the new samples queue up behind
+                e->carry.insert(e->carry.end(), buf, buf + nbytes);
+            }
+            return rc;
+        }
+    }
     while (nbytes) {
         if (e->stage_fill == e->stage_cap) {               // this half is full: send it, go on in the other one
             int rc = flush_staged(e);
+            if (rc == NRSC5B_EFULL) {
+                e->carry.assign(buf, buf + nbytes);
+                e->carry_stream = stream;
+            }
             if (rc) return rc;
         }
         const size_t n = nbytes < e->stage_cap - e->stage_fill ? nbytes : e->stage_cap - e->stage_fill;
@@ -1811,7 +1851,8 @@ static int flush_staged(nrsc5b_engine *e)
     if (e->staged.empty()) return NRSC5B_OK;
     const double t0 = e->trace_on ? wall_s() : 0;
     const uint8_t *src = e->stage[e->stage_cur];
-    for (const auto &g : e->staged) {
+    while (!e->staged.empty()) {
+        const nrsc5b_engine::Staged g = e->staged.front();
         size_t off = (size_t)e->pushed[g.stream] * 2;
         if (off + g.n > e->dims.in_stride) {
             const double t1 = e->trace_on ? wall_s() : 0;
@@ -1819,15 +1860,15 @@ static int flush_staged(nrsc5b_engine *e)
             if (e->trace_on) { e->tr.trims++; e->tr.s_trim += wall_s() - t1; }
             if (rc) return rc;
             off = (size_t)e->pushed[g.stream] * 2;
-            if (off + g.n > e->dims.in_stride) return NRSC5B_EFULL;
+            if (off + g.n > e->dims.in_stride) return NRSC5B_EFULL;   // (what was copied so far is off the list)
         }
         CK(cudaMemcpyAsync(e->iq_owned + (size_t)g.stream * e->dims.in_stride + off, src + g.off, g.n, cudaMemcpyHostToDevice,
                            e->copy_stream));
         e->pushed[g.stream] += (long long)(g.n / 2);
         e->staged_units[g.stream] -= (long long)(g.n / 2);
         e->unpublished[g.stream] = 1;
+        e->staged.erase(e->staged.begin());
     }
-    e->staged.clear();
     CK(cudaEventRecord(e->stage_free[e->stage_cur], e->copy_stream));
     e->stage_cur ^= 1;
     e->stage_fill = 0;
@@ -1846,6 +1887,15 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
     if (!e) return NRSC5B_EINVAL;
     if (e->in_flight) return 0;
     bool decode = true;
+    if (e->stalled) {
+        long long units = 0;
+        for (int s = 0; s < e->dims.nstreams; s++) units += e->pushed[s] + e->staged_units[s];
+        if (units == e->stalled_units) {
+            if (flush) { int rc = flush_staged(e); if (rc) return rc; }
+            return 0;
+        }
+        e->stalled = false;
+    }
     const int passes = plan_passes(e, true, &decode);
     if (passes == 0) {
         if (flush) { int rc = flush_staged(e); if (rc) return rc; }
@@ -1905,6 +1955,11 @@ extern "C" int nrsc5b_poll(nrsc5b_engine_t *e, int wait)
     }
     e->in_flight = false;
     if (e->trace_on) e->tr.polls_ready++;
+    if (e->h_ctl->progress == e->last_progress && !(e->h_ctl->px_need & ~(unsigned)e->dims.px_enabled)) {
+        e->stalled = true;
+        e->stalled_units = 0;
+        for (int s = 0; s < e->dims.nstreams; s++) e->stalled_units += e->pushed[s] + e->staged_units[s];
+    }
     e->last_progress = e->h_ctl->progress;
     if (e->batch_decoded)
         for (int s = 0; s < e->dims.nstreams; s++) e->h_brief[s].p1_ready = 0;

@@ -623,14 +623,16 @@ __device__ __forceinline__ int8_t soft_demap(float x, float mult)      // sync.c
     return (int8_t)r;
 }
 
+template <bool CL>
 __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSmem &sm, int t)
 {
     StreamState &st = p.st[s];
     float *cfreq = p.cfreq + (size_t)s * NFFT;
     float *cphase = p.cphase + (size_t)s * NFFT;
-    // [symbol][534]; written by the demodulating teams - with a cluster per stream, on other SMs - so every read here
+    // [symbol][534]; written by the demodulating teams - with a cluster per stream (CL), on other SMs: every read then
     // goes to L2 (__ldcg), never to this SM's L1
     float2 *bins = p.bins + (size_t)s * BLK * NBINS;
+    auto ldbin = [](const float2 *q) -> float2 { return CL ? __ldcg(q) : *q; };
     const float loop_bw = 0.05f, damping = 0.70710678f;
     const float denom = 1 + (2 * damping * loop_bw) + (loop_bw * loop_bw);
     const float alpha = (4 * damping * loop_bw) / denom, beta = (4 * loop_bw * loop_bw) / denom;
@@ -655,7 +657,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
             const int sb = r >= rows, rr = sb ? r - rows : r;
             const int i = rr / (PW - 1), k = rr - i * (PW - 1) + 1;
             const int ci = sb == 0 ? PW * i + k : (NBINS - 1 - PW) - PW * i + k;
-            sm.eq[r][n] = __ldcg(&bins[(size_t)n * NBINS + ci]);
+            sm.eq[r][n] = ldbin(&bins[(size_t)n * NBINS + ci]);
         }
     };
     const bool pre_staged = st.state == ST_FINE && !(g_dbg & 1);   // partitions known: stage while warp 0 runs the Costas loops
@@ -663,7 +665,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
     for (int i = t; i < ZS * BLK; i += FRONT_THREADS) {
         const int slot = i & (ZS - 1), n = i / ZS;
         const int ii = slot < MAXREF ? slot : slot - MAXREF;
-        if (slot < 2 * MAXREF && ii < nref) sm.zref[n][slot] = __ldcg(&bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))]);
+        if (slot < 2 * MAXREF && ii < nref) sm.zref[n][slot] = ldbin(&bins[(size_t)n * NBINS + compact_of_bin(ref_bin(slot))]);
     }
     __syncthreads();
     sylap(0);
@@ -787,7 +789,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     const float2 *src = q ? snap + (size_t)(q - 1) * BLK * NSB + t : nullptr;
                     for (int n = 0; n < BLK; n++)
                         row[(size_t)n * NSB] = q ? src[(size_t)n * NSB]
-                                                 : (ci >= 0 ? __ldcg(&bins[(size_t)n * NBINS + ci]) : make_float2(0.f, 0.f));
+                                                 : (ci >= 0 ? ldbin(&bins[(size_t)n * NBINS + ci]) : make_float2(0.f, 0.f));
                     costas_row(row, sphs + t, NSB, f, ph, cfo, alpha, beta);
                     sm.srch.offs[cfo + 2 * PW][2 * i + upper] = ref_find(row, NSB, (unsigned)(30 - i) & 3);
                     for (int n = 0; n < BLK; n++)            // reset_ref (sync.c:132-136)
@@ -932,7 +934,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                 const float c = fa * up.x + fb * lp.x, dd = fa * up.y + fb * lp.y;
                 const float rden = __fdividef(19.0f, c * c + dd * dd);
                 const float2 C = make_float2((c + dd) * rden, (c - dd) * rden);
-                const float2 v = cmulf(__ldcg(&bins[(size_t)n * NBINS + ci]), C);
+                const float2 v = cmulf(ldbin(&bins[(size_t)n * NBINS + ci]), C);
                 bins[(size_t)n * NBINS + ci] = v;
                 const float dx = (v.x >= 0 ? 1.0f : -1.0f) - v.x, dy = (v.y >= 0 ? 1.0f : -1.0f) - v.y;
                 const float e = dx * dx + dy * dy;
@@ -1020,8 +1022,8 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     b = sm.eq[r + 1][n];
                 } else {
                     const int ci = (sb == 0 ? PW * i : (NBINS - 1 - PW) - PW * i) + 1 + 2 * c4;
-                    a = __ldcg(&bins[(size_t)n * NBINS + ci]);
-                    b = __ldcg(&bins[(size_t)n * NBINS + ci + 1]);
+                    a = ldbin(&bins[(size_t)n * NBINS + ci]);
+                    b = ldbin(&bins[(size_t)n * NBINS + ci + 1]);
                 }
                 const float mult = sm.mult[lower_scale_only ? 0 : sb];
                 const unsigned w = (unsigned)(uint8_t)soft_demap(a.x, mult) | ((unsigned)(uint8_t)soft_demap(a.y, mult) << 8) |
@@ -1171,6 +1173,7 @@ __device__ __forceinline__ void cluster_barrier()
 #endif
 }
 
+template <bool CL>
 __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDims d, int max_blocks, int last_pass)
 {
 #if defined(NB_EMU)
@@ -1180,13 +1183,13 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
 #endif
     FrontSmem &sm = *reinterpret_cast<FrontSmem *>(front_smem_raw);
     const int t = threadIdx.x, team = t >> 7, tl = t & 127;
-    const int C = d.cluster > 1 ? d.cluster : 1;
+    const int C = CL ? d.cluster : 1;                 // (CL: launched as clusters of d.cluster = 2 or 4 CTAs)
     const int s = (int)blockIdx.x / C, rank = (int)blockIdx.x % C;
     StreamState &st = p.st[s];
     for (int i = t; i < FFT_TW; i += FRONT_THREADS) sm.tw[i] = __ldg(&p.twid[i]);
     __syncthreads();
 
-    const bool owner = rank == 0;
+    const bool owner = !CL || rank == 0;
     if (max_blocks > 16) max_blocks = 16;             // the PIDS queue (and its interleaver matrix rows) hold 16 blocks
     if (owner && t == 0) {                            // decoded by the kernels that followed the previous pass
         st.p3_pending = 0;
@@ -1210,7 +1213,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
             go = nb < max_blocks && !st.p1_ready;
             if (go) go = front_prep(p, d, s, sm.u.prep, sm.nco, t);
         }
-        if (C > 1) {
+        if (CL) {
             if (owner && t == 0) {
                 st.blk_go = go ? 1 : 0;
                 __threadfence();
@@ -1220,29 +1223,29 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
         }
         if (!go) break;
         lap(st.blk_state_in == ST_FINE ? 2 : 1);
-        const long long start = __ldcg(&st.start);
-        const int samperr = __ldcg(&st.blk_samperr);
-        const float theta = __ldcg(&st.theta);
-        const float2 phase0 = __ldcg(&st.phase0);
-        if (!owner) {                                 // a helper CTA builds its own copy of the block's NCO table
+        const long long start = CL ? __ldcg(&st.start) : st.start;
+        const int samperr = CL ? __ldcg(&st.blk_samperr) : st.blk_samperr;
+        const float theta = CL ? __ldcg(&st.theta) : st.theta;
+        const float2 phase0 = CL ? __ldcg(&st.phase0) : st.phase0;
+        if (CL && !owner) {                                 // a helper CTA builds its own copy of the block's NCO table
             fill_nco(p, sm.nco, theta, t);
             __syncthreads();
         }
 #pragma unroll 1
         for (int pass = 0; pass < BLK / (TEAMS * C); pass++)
             front_demod(p, d, s, (pass * C + rank) * TEAMS + team, sm.u.demod, sm.nco, sm.tw, team, tl, start, samperr, theta, phase0);
-        if (C > 1) {
+        if (CL) {
             __threadfence();
             cluster_barrier();                        // every CTA's bins are in L2
         }
-        if (!owner) continue;
+        if (CL && !owner) continue;
         __syncthreads();
         lap(3);
-        front_sync(p, d, s, sm.u.sync, t);
+        front_sync<CL>(p, d, s, sm.u.sync, t);
         __syncthreads();
         lap(st.blk_state_in == ST_FINE ? 4 : 5);
     }
-    if (!owner) return;
+    if (CL && !owner) return;
     __syncthreads();
     if (st.pids_pending) {
         const long long c0 = clock64();

@@ -33,7 +33,11 @@
 
 #include "nrsc5_b200.h"
 
-#define INPUT_CAPACITY (8u << 20)       /* cu8 bytes buffered on the GPU (one 33-symbol window is 285 KB) */
+/* Samples buffered on the GPU.  A file is pushed faster than it is decoded, so the buffer holds the part of the stream
+ * the pushes are ahead by; when it is full the engine drops what the receiver's window has passed (a synchronous
+ * step, once per buffer) and, if that frees nothing, the push waits for the batch in flight.  HBM is not scarce:
+ * 256 MiB = 58 L1 frames of cu8.  (A real-time source never gets ahead by more than a block.) */
+#define INPUT_CAPACITY (256u << 20)
 #define RECORDS_CAPACITY (4u << 20)
 
 static void fail(const char *what, int rc)
@@ -293,6 +297,18 @@ static void pump(input_t *st)
     if (rc < 0) fail("nrsc5b_submit", rc);
 }
 
+/* the device buffer is full of samples the GPU has not used yet: deliver the batch in flight and start the next */
+static void wait_for_room(input_t *st)
+{
+    int rc = nrsc5b_poll(st->engine, 1);
+    if (rc < 0) fail("nrsc5b_poll", rc);
+    if (rc == 1) deliver_batch(st);
+    rc = nrsc5b_submit(st->engine, 0);
+    if (rc < 0) fail("nrsc5b_submit", rc);
+    if (rc == 0 && nrsc5b_poll(st->engine, 0) == 0)
+        fail("input buffer full although the GPU is idle (INPUT_CAPACITY)", NRSC5B_EFULL);
+}
+
 /* blocking: everything buffered so far is decoded and delivered */
 static void pump_all(input_t *st)
 {
@@ -315,6 +331,11 @@ void input_push_cu8(input_t *st, const uint8_t *buf, const uint32_t len)
     if (st->pipelined && !st->engine_am)
     {
         int rc = nrsc5b_stage_cu8(st->engine, 0, buf, len);
+        while (rc == NRSC5B_EFULL)                   /* the GPU is a whole buffer behind: let it catch up */
+        {
+            wait_for_room(st);
+            rc = nrsc5b_stage_cu8(st->engine, 0, NULL, 0);
+        }
         if (rc) fail("nrsc5b_stage_cu8", rc);
         pump(st);
         return;
@@ -341,6 +362,11 @@ void input_push_cs16(input_t *st, const int16_t *buf, const uint32_t len)
     if (st->pipelined)
     {
         int rc = nrsc5b_stage_cs16(st->engine, 0, buf, len);
+        while (rc == NRSC5B_EFULL)
+        {
+            wait_for_room(st);
+            rc = nrsc5b_stage_cs16(st->engine, 0, NULL, 0);
+        }
         if (rc) fail("nrsc5b_stage_cs16", rc);
         pump(st);
         return;

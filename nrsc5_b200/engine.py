@@ -76,6 +76,12 @@ def load_library():
     L.nrsc5b_push_fence.argtypes = [vp]
     L.nrsc5b_process_fence.argtypes = [vp, ci]
     L.nrsc5b_synchronize.argtypes = [vp]
+    L.nrsc5b_stage_cu8.argtypes = [vp, ci, vp, sz]
+    L.nrsc5b_stage_cs16.argtypes = [vp, ci, vp, sz]
+    L.nrsc5b_submit.argtypes = [vp, ci]
+    L.nrsc5b_poll.argtypes = [vp, ci]
+    L.nrsc5b_batch_records.argtypes = [vp, ci, ctypes.POINTER(sz)]
+    L.nrsc5b_batch_records.restype = vp
     L.nrsc5b_drain.argtypes = [vp, ci, vp, sz, ctypes.POINTER(sz)]
     L.nrsc5b_drain.restype = ctypes.c_long
     L.nrsc5b_drain_all.argtypes = [vp, vp, sz, vp]
@@ -302,6 +308,30 @@ class Engine:
 
     def process_fence(self, token: int):
         _check(self._L.nrsc5b_process_fence(self._h, token), "nrsc5b_process_fence")
+
+    # ---- asynchronous use (include/nrsc5_b200.h): staged input, one batch in flight, records exported to host memory
+    def stage_cu8(self, stream: int, samples) -> int:
+        """Returns 0, or -5 (EFULL: the device buffer is full of unused samples; the engine kept the rest - poll /
+        submit and call stage_cu8(stream, b"") until it returns 0)."""
+        a = np.ascontiguousarray(np.frombuffer(samples, dtype=np.uint8) if isinstance(samples, (bytes, bytearray)) else samples,
+                                 dtype=np.uint8)
+        rc = self._L.nrsc5b_stage_cu8(self._h, stream, a.ctypes.data if a.size else None, a.size)
+        if rc != -5:
+            _check(rc, "nrsc5b_stage_cu8")
+        return rc
+
+    def submit(self, flush: bool = False) -> int:
+        return _check(self._L.nrsc5b_submit(self._h, int(flush)), "nrsc5b_submit")
+
+    def poll(self, wait: bool = False) -> int:
+        return _check(self._L.nrsc5b_poll(self._h, int(wait)), "nrsc5b_poll")
+
+    def batch_records(self, stream: int):
+        n = ctypes.c_size_t(0)
+        ptr = self._L.nrsc5b_batch_records(self._h, stream, ctypes.byref(n))
+        if self._L.nrsc5b_take_overflow(self._h, stream) and not self.allow_overflow:
+            raise EngineError(f"stream {stream}: record log overflowed (log_capacity too small)")
+        return parse_records(ctypes.string_at(ptr, n.value)) if ptr and n.value else []
 
     def synchronize(self):
         _check(self._L.nrsc5b_synchronize(self._h), "nrsc5b_synchronize")

@@ -69,6 +69,7 @@ test_drain_all_equals_per_stream_drain = _chain.test_drain_all_equals_per_stream
 test_endless_stream_is_trimmed_to_the_input_buffer = _chain.test_endless_stream_is_trimmed_to_the_input_buffer
 test_cs16_input_equals_cu8_input = _chain.test_cs16_input_equals_cu8_input
 test_multi_stream_independent = _chain.test_multi_stream_independent
+test_pipelined_use_equals_synchronous_decode = _chain.test_pipelined_use_equals_synchronous_decode
 test_pids_crc_verdicts_on_valid_frames = _chain.test_pids_crc_verdicts_on_valid_frames
 # L2 framing on the device
 test_l2_frames_equal_oracle = _l2.test_l2_frames_equal_oracle

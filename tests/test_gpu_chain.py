@@ -188,6 +188,46 @@ def test_cluster_per_stream_equals_oracle(ctas, monkeypatch):
         assert kinds(recs) == oracle_kinds(ref)
 
 
+def test_pipelined_use_equals_synchronous_decode():
+    """The asynchronous path the drop-in runs on (stage / submit / poll, records exported by the GPU): two streams fed in
+    32 768-byte pieces, one batch in flight, into a device buffer far smaller than the captures - so the engine has
+    to drop consumed samples and, when the pushes get a whole buffer ahead, tell the caller to wait (EFULL) - must
+    deliver, batch after batch, exactly the records of a one-shot decode."""
+    caps = [synth.make_fm_mp1(nframes=2, seed=61, lead_in=123, cfo_hz=40.0).cu8, synth.make_fm_mp3(**common.MP3_CASE).cu8]
+    caps = [c[: c.size & ~3] for c in caps]
+    whole = run_engine(caps)
+    got = [[], []]
+    with nrsc5_b200.Engine(nstreams=2, input_capacity=3 << 20, log_capacity=4 << 20) as e:
+        def take():
+            for s in range(2):
+                got[s] += e.batch_records(s)
+        n = max(c.size for c in caps)
+        waits = 0
+        for off in range(0, n, 32768):
+            for s, c in enumerate(caps):
+                piece = c[off: off + 32768]
+                if not piece.size:
+                    continue
+                rc = e.stage_cu8(s, piece)
+                while rc == -5:
+                    waits += 1
+                    if e.poll(True) == 1:
+                        take()
+                    e.submit()
+                    rc = e.stage_cu8(s, b"")
+            if e.poll(False) == 1:
+                take()
+            e.submit()
+        while True:                                   # end of the streams: flush
+            if e.poll(True) == 1:
+                take()
+            if e.submit(True) != 1:
+                break
+    for s in range(2):
+        assert [(t, r.get("bits")) for t, r in got[s] if t != eng.REC_BLOCK] == [(t, r.get("bits")) for t, r in whole[s] if t != eng.REC_BLOCK]
+        assert kinds(got[s]) == kinds(whole[s])
+
+
 def test_sample_xz_bit_exact():
     raw = common.load_sample()
     if raw is None:
