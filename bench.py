@@ -277,7 +277,31 @@ def am_leg(args, engine_factory=None):
     again = e.drain_all()
     assert [record_digest(r) for r in again] == first, "rewind -> process gave other records than reset -> push -> process"
     samples = S * (n // 2)
+    # the unmodified reference on this host's cores: one process per channel (cs16, AM mode), 3 passes each
+    cpu = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import reftap
+        if reftap.available():
+            v, nproc, info = cpu_reference_numbers(views, 2 * n, 3, am=True)     # (2 * n bytes // 2 = n int16 = n / 2 samples x 2)
+            # cpu_reference_numbers counts nbytes // 2 units per pass: for cs16 that is int16 values; complex samples = half
+            cpu = dict({"value": v / 2, "unit": "Msamples/s (cs16 complex)", "cores": nproc, "kind": "reference",
+                        "sample": f"{nproc} processes x 3 passes over one {n // 2}-sample AM channel each"}, **info)
+            cpu["single_core_value"] /= 2
+            cpu["all_cores_value"] /= 2
+    except Exception as ex:                                   # noqa: BLE001
+        cpu = {"error": repr(ex)[:300]}
+    peak, peak_src = measured_peak()
+    blocks = int(e.stats().blocks)
+    alg = 35640.0 * (samples / (8640.0))                      # 35 640 B of cs16 in per AM block (8 910 samples window, 8 640 new)
+    ms = 1e3 * res / steps
     out = {"value": samples * steps / res / 1e6, "unit": "Msamples/s (cs16 complex, 46 511.72 S/s per channel)",
+           "roofline": {"bound": "hbm", "kernel": "k_am (whole AM chain, one CTA per stream)", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                        "note": "latency-bound by construction: the NCO phase chain (17 280 dependent complex multiplications per block) "
+                                "and the K=9 add-compare-select (one barrier per trellis step) are sequential per stream; 256 streams "
+                                "put at most two CTAs on an SM", "blocks_total": blocks},
+           "cpu_baseline": cpu,
            "x_realtime": samples * steps / res / 46511.71875, "ms_per_step": 1e3 * res / steps,
            "e2e": {"value": samples * steps / tot / 1e6, "ms_per_step": 1e3 * tot / steps, "x_realtime": samples * steps / tot / 46511.71875,
                    "process_ms_per_step": 1e3 * proc / steps, "h2d_bytes_per_step": int(S * n * 2),
@@ -475,17 +499,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_numbers(bufs, nbytes, reps):
+def cpu_reference_numbers(bufs, nbytes, reps, am=False):
     """The unmodified reference (oracle/_ref/libnrsc5_ref.so) on this host: one PROCESS per channel, each pinned to its
     own physical core (oracle/refproc.py), 1 core and all physical cores.  Returns (aggregate
     Msamples/s, cores used, dict of details)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refproc
+    import reftap
+    mode = reftap.MODE_AM if am else reftap.MODE_FM
     cpus = refproc.physical_cores()
     n = min(len(cpus), len(bufs))
-    refproc.bench_processes(bufs[:1], reps=1, cpus=cpus[:1])                     # warm-up (page cache, library load)
-    t1, _ = refproc.bench_processes(bufs[:1], reps=reps, cpus=cpus[:1])
-    tn, n = refproc.bench_processes(bufs[:n], reps=reps, cpus=cpus[:n])
+    refproc.bench_processes(bufs[:1], mode=mode, reps=1, cpus=cpus[:1])          # warm-up (page cache, library load)
+    t1, _ = refproc.bench_processes(bufs[:1], mode=mode, reps=reps, cpus=cpus[:1])
+    tn, n = refproc.bench_processes(bufs[:n], mode=mode, reps=reps, cpus=cpus[:n])
     per = reps * (nbytes // 2)
     info = {"single_core_value": per / t1 / 1e6, "all_cores_value": n * per / tn / 1e6, "processes": n,
             "physical_cores_available": len(cpus), "logical_cpus": os.cpu_count(), "cpu_model": refproc.cpu_model(),

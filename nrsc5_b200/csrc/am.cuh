@@ -1,17 +1,29 @@
-// AM (hybrid MA1, all-digital MA3) receive chain: first CUDA path.  One WARP per stream runs the whole chain block after block
-// (k_am): coarse acquisition, carrier-phase tracking, 256-point OFDM demodulation, reference-carrier search,
-// training-symbol equalisation, QAM/QPSK slicing, PIDS, interleaver MA1 with the diversity delay, K=9
-// tail-biting Viterbi (E1/E2/E3), descramble, L1 PDUs.
+// AM (hybrid MA1, all-digital MA3) receive chain.  One CTA of AM_THREADS threads per stream (k_am, engine.cu) runs the
+// whole chain block after block: coarse acquisition, carrier-phase tracking, 256-point OFDM demodulation, reference-
+// carrier search, training-symbol equalisation, QAM/QPSK slicing, PIDS, interleaver MA1 with the diversity delay,
+// K=9 tail-biting Viterbi (E1/E2/E3), descramble, L1 PDUs.
 //
 //   reference: src/acquire.c:98-263 (AM branches), src/sync.c:37-88,208-252,612-767, src/decode.c:67-231,
 //              234-277,474-554, src/conv_dec.c (K=9), src/frame.c:645-714,527-541 (sync-loss predicate)
 //
-// The code is written so that it also compiles for the host with ONE lane (AM_HD functions, lane-strided
-// loops with AM_SYNC() between dependent phases): tests/am_host.cu runs exactly these functions on the CPU
-// against the oracle before the GPU ever sees them.  AM rates are tiny (46.5 kS/s per stream), so this first
-// version favours a line-by-line correspondence with the reference's order of operations over speed; the
-// K=9 add-compare-select and the FFT butterflies are spread over the lanes, everything sequential in the
-// reference (phase recurrences, arg-max scans, reductions) is computed redundantly by every lane.
+// AM decides on HARD symbols (QAM-64 / 16 / QPSK slicing, sync.c:37-88), so a float that differs in its last bits can
+// flip a sliced bit and with it the channel-BER figure the reference reports: the float arithmetic here keeps the
+// reference's order of operations throughout - including the per-sample NCO recurrence and the radix-2 butterfly
+// order of the test oracle's FFT.  What is re-designed is where the work runs and what it waits for:
+//   * the working set of a block lives in shared memory (AmSmem): the symbol being demodulated and its FFT, the K=9
+//     path metrics, a tile of survivor decisions - nothing on a dependent path goes to global memory;
+//   * the NCO phase chain (8 640 dependent complex multiplications per pass - sequential by definition) is run by ONE
+//     warp, a symbol ahead of the three warps that window, fold and transform the previous symbol (demod_pass);
+//   * the K=9 add-compare-select gives every thread one butterfly (128 butterflies = the CTA), path metrics packed
+//     two to a shared-memory word, survivor bits collected by warp ballot into 256-step tiles that go to global
+//     memory in one coalesced sweep; traceback pulls the tiles back, newest first (viterbi_k9);
+//   * channel-BER re-encoding and the bit packing of the PDUs are spread over the CTA.
+// Scalar receiver state (AmState) is held redundantly by every thread - each follows the same control flow on the
+// same values - and written back by thread 0.
+//
+// The generic (host) branches of the functions below are the same algorithms in plain loops: tests/am_host.cu runs
+// them on the CPU against the oracle; the device branches run under the CUDA emulator (tests/test_emu_engine.py)
+// and on the GPU against the same oracle.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -22,7 +34,7 @@
 #include "pids_crc.cuh"
 
 #if defined(__CUDA_ARCH__)
-#define AM_SYNC() __syncwarp()
+#define AM_SYNC() __syncthreads()         // the lanes of a stream are the threads of its CTA
 #elif defined(AM_HOST_SYNC)
 #define AM_SYNC() AM_HOST_SYNC()          // tests/am_host.cu: lanes emulated by host threads meet at a barrier
 #else
@@ -56,8 +68,11 @@ constexpr int VIT_MAX_STEPS = P3_LEN_MA3 + 64;
 constexpr uint32_t REC_FRAME = 1, REC_PIDS = 2, REC_SYNC = 3, REC_LOST_SYNC = 4, REC_BER = 6;
 constexpr double PI = 3.14159265358979323846;
 
+constexpr int AM_THREADS = 128;                 // k_am: threads per stream (one K=9 butterfly each)
+
 struct Lanes {
     int lane, n;
+    void *smem;                                 // device: the CTA's AmSmem
 };
 
 // ---- complex helpers in the reference's (gcc, no FMA) evaluation order ----
@@ -103,28 +118,15 @@ struct AmState {
     int am_errors, am_diversity_wait;
     unsigned log_len, log_overflow;
     unsigned long long blocks_done;
-    short bp_hist[31][2];      // the coarse band-pass filter's last 31 inputs
-    // L2 on the device (l2.cuh): the frames (log offset of their packed bits) and frame_resets (nbits == 0) this
-    // launch handed to the L2 kernel that follows it, in the reference's call order
-    int l2_on, l2_n;
-    unsigned l2_off[AM_L2_QUEUE], l2_lc[AM_L2_QUEUE], l2_nbits[AM_L2_QUEUE];
+    int l2_on, l2_n;           // L2 on the device (l2.cuh): entries in AmWork::l2_* this launch handed to the L2 kernel
 };
-
-AM_HD inline void l2_enqueue(AmState &st, unsigned off, unsigned lc, unsigned nbits)
-{
-    if (!st.l2_on) return;
-    if (st.l2_n >= AM_L2_QUEUE) {               // cannot happen with AM_L2_BLOCKS blocks per launch
-        st.log_overflow = 1;
-        return;
-    }
-    st.l2_off[st.l2_n] = off;
-    st.l2_lc[st.l2_n] = lc;
-    st.l2_nbits[st.l2_n] = nbits;
-    st.l2_n++;
-}
 
 // Per-stream arrays.
 struct AmWork {
+    short bp_hist[31][2];      // the coarse band-pass filter's last 31 inputs
+    // L2 on the device: the frames (log offset of their packed bits) and frame_resets (nbits == 0) this launch handed
+    // to the L2 kernel that follows it, in the reference's call order
+    unsigned l2_off[AM_L2_QUEUE], l2_lc[AM_L2_QUEUE], l2_nbits[AM_L2_QUEUE];
     float2 buf[NACQ];
     float2 sums[SYM];
     float2 fft[FFT];
@@ -137,7 +139,7 @@ struct AmWork {
     int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
     uint8_t out[P3_LEN_MA3 + 8];
     short pm[2][256];
-    uint8_t dec[(size_t)VIT_MAX_STEPS * 32];   // survivor bits, see viterbi_k9
+    alignas(16) uint8_t dec[(size_t)VIT_MAX_STEPS * 32];   // survivor bits, 256 per trellis step (eight 32-bit words), see viterbi_k9
     float2 mult[4][PW];
     uint8_t sym_pl[BLK * PW], sym_pu[BLK * PW], sym_s[BLK * PW], sym_t[BLK * PW], sym_pids[2 * BLK];
 };
@@ -149,6 +151,22 @@ struct AmTables {
     uint8_t brev[FFT];         // bit reversal of 8 bits
     uint8_t pn[P3_LEN_MA3 + 8];    // descrambler sequence
 };
+
+// every lane calls this with identical arguments; lane 0 writes the entry
+AM_HD inline void l2_enqueue(AmState &st, AmWork &w, Lanes L, unsigned off, unsigned lc, unsigned nbits)
+{
+    if (!st.l2_on) return;
+    if (st.l2_n >= AM_L2_QUEUE) {               // cannot happen with AM_L2_BLOCKS blocks per launch
+        st.log_overflow = 1;
+        return;
+    }
+    if (L.lane == 0) {
+        w.l2_off[st.l2_n] = off;
+        w.l2_lc[st.l2_n] = lc;
+        w.l2_nbits[st.l2_n] = nbits;
+    }
+    st.l2_n++;
+}
 
 struct AmIo {
     const int16_t *iq;         // this stream's cs16 samples, I/Q interleaved
@@ -175,16 +193,23 @@ AM_HD inline uint8_t *log_reserve(AmState &st, const AmIo &io, Lanes L, uint32_t
     return w + 8;
 }
 
-// All lanes call this with identical arguments; lane 0 writes.  `st` is every lane's private copy.
-AM_HD inline void emit_frame(AmState &st, const AmIo &io, Lanes L, const uint8_t *bits, unsigned len, unsigned lc)
+// All lanes call this with identical arguments.  `st` is every lane's private copy.
+AM_HD inline void emit_frame(AmState &st, AmWork &w, const AmIo &io, Lanes L, const uint8_t *bits, unsigned len, unsigned lc)
 {
-    uint8_t *w = log_reserve(st, io, L, REC_FRAME, 8 + (len + 7) / 8);
-    if (w && L.lane == 0) {
-        uint32_t hdr[2] = { lc, len };
-        memcpy(w, hdr, 8);
-        for (unsigned i = 0; i < len; i++) w[8 + (i >> 3)] |= (uint8_t)((bits[i] & 1) << (7 - (i & 7)));
+    uint8_t *rec = log_reserve(st, io, L, REC_FRAME, 8 + (len + 7) / 8);
+    AM_SYNC();                                                      // (lane 0 cleared the payload)
+    if (rec) {
+        if (L.lane == 0) {
+            uint32_t hdr[2] = { lc, len };
+            memcpy(rec, hdr, 8);
+        }
+        for (unsigned by = L.lane; by < (len + 7) / 8; by += L.n) {     // MSB first, a byte per lane
+            unsigned v = 0;
+            for (unsigned k = 0; k < 8 && 8 * by + k < len; k++) v |= (unsigned)(bits[8 * by + k] & 1) << (7 - k);
+            rec[8 + by] = (uint8_t)v;
+        }
     }
-    l2_enqueue(st, w ? (unsigned)(w + 8 - io.log) : 0xffffffffu, lc, len);            // frame_push -> frame_process
+    l2_enqueue(st, w, L, rec ? (unsigned)(rec + 8 - io.log) : 0xffffffffu, lc, len);     // frame_push -> frame_process
 }
 
 AM_HD inline void set_state(AmState &st, const AmIo &io, Lanes L, int ns)       // input.c:172-188
@@ -218,9 +243,130 @@ AM_HD inline int parity9(unsigned v)
 }
 AM_HD inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
 
+// ---- shared memory of a stream's CTA (device) ----
+constexpr int VT = 256;                          // trellis steps per tile of survivor decisions
+struct AmSmem {
+    union {
+        struct {                                 // viterbi_k9
+            uint32_t pmw[2][128];                // path metrics, int16 x 2 per word: word b = old states 2b (low), 2b+1 (high)
+            uint32_t tile[VT][8];                // survivor bit of new state s at a step: bit s & 31 of word s >> 5
+            int8_t q[3 * VT];                    // the tile's soft inputs
+            int wred[AM_THREADS / 32];
+            int wmax[AM_THREADS / 32], widx[AM_THREADS / 32];
+            unsigned state;
+        } vit;
+        struct {                                 // demod_pass
+            float2 ph[2][SYM];                   // NCO phase per sample of a symbol, double-buffered (producer warp runs ahead)
+            float2 phase_end[2];                 // the phase after the symbol, renormalised
+            float2 fft[FFT];                     // one symbol: windowed, folded, shifted; transformed in place
+            float2 carrier[BLK];                 // first pass: the carrier bin of every symbol
+            float mag[2 * PIDS_OUTER + 1];       // first pass while acquiring: summed magnitudes around the carrier
+        } dem;
+    };
+    int red[AM_THREADS / 32];                    // CTA-wide sums (bit_errors)
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ int am_warp_min(int v)
+{
+#if defined(NB_EMU)
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+#else
+    return __reduce_min_sync(0xffffffffu, v);
+#endif
+}
+#endif
+
 AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out, int len, unsigned g0, unsigned g1, unsigned g2)
 {
     const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
+#if defined(__CUDA_ARCH__)
+    // One butterfly per thread: thread b reads old states 2b, 2b+1 (one shared-memory word) and produces new states b
+    // and b + 128.  Decisions: 1 = the odd predecessor survived (it does unless the even one is strictly better).
+    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    const int b = L.lane, warp = b >> 5;
+    const unsigned reg = (unsigned)b << 1;
+    const int s0 = parity9(reg & g0) ? 1 : -1, s1 = parity9(reg & g1) ? 1 : -1, s2 = parity9(reg & g2) ? 1 : -1;
+    uint32_t *decw = reinterpret_cast<uint32_t *>(w.dec);                   // [step][8]
+    sm.vit.pmw[0][b] = 0;
+    int cur = 0;
+    for (int base = 0; base < steps; base += VT) {
+        const int nst = min(VT, steps - base);
+        for (int i = b; i < 3 * nst; i += AM_THREADS) {
+            const int st_i = base + i / 3;
+            int j = len - 32 + st_i;                                        // the input index wraps (tail biting)
+            while (j >= len) j -= len;
+            sm.vit.q[i] = in[3 * j + (i - 3 * (i / 3))];
+        }
+        __syncthreads();
+        for (int k = 0; k < nst; k++) {
+            const int m = (int)sm.vit.q[3 * k] * s0 + (int)sm.vit.q[3 * k + 1] * s1 + (int)sm.vit.q[3 * k + 2] * s2;
+            const uint32_t pw = sm.vit.pmw[cur][b];
+            const int p0 = (short)(pw & 0xffffu), p1 = (short)(pw >> 16);
+            const int a0 = sat16(p0 + m), a1 = sat16(p1 - m), c0 = sat16(p0 - m), c1 = sat16(p1 + m);
+            const int d0 = !(a0 > a1), d1 = !(c0 > c1);
+            int n0 = d0 ? a1 : a0, n1 = d1 ? c1 : c0;
+            short *nxt = reinterpret_cast<short *>(sm.vit.pmw[cur ^ 1]);
+            const unsigned w0 = __ballot_sync(0xffffffffu, d0), w1 = __ballot_sync(0xffffffffu, d1);
+            if ((b & 31) == 0) {
+                sm.vit.tile[k][warp] = w0;
+                sm.vit.tile[k][4 + warp] = w1;
+            }
+            if ((base + k) % interval == 0) {                               // subtract the minimum (conv_dec.c:417-421)
+                const int wm = am_warp_min(min(n0, n1));
+                if ((b & 31) == 0) sm.vit.wred[warp] = wm;
+                __syncthreads();
+                const int mn = min(min(sm.vit.wred[0], sm.vit.wred[1]), min(sm.vit.wred[2], sm.vit.wred[3]));
+                n0 = sat16(n0 - mn);
+                n1 = sat16(n1 - mn);
+            }
+            nxt[b] = (short)n0;
+            nxt[b + 128] = (short)n1;
+            __syncthreads();
+            cur ^= 1;
+        }
+        // the tile's decisions: one coalesced sweep to global memory
+        for (int i = b; i < nst * 8; i += AM_THREADS) decw[(size_t)base * 8 + i] = (&sm.vit.tile[0][0])[i];
+        __syncthreads();
+    }
+    // first maximum in state order (conv_dec.c:310-317)
+    {
+        const short *pmv = reinterpret_cast<const short *>(sm.vit.pmw[cur]);
+        int v = pmv[2 * b], idx = 2 * b;
+        if (pmv[2 * b + 1] > v) { v = pmv[2 * b + 1]; idx = 2 * b + 1; }
+        for (int o = 16; o; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, v, o), oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if ((b & 31) == 0) { sm.vit.wmax[warp] = v; sm.vit.widx[warp] = idx; }
+        __syncthreads();
+        if (b == 0) {
+            int bv = sm.vit.wmax[0], bi = sm.vit.widx[0];
+            for (int q = 1; q < AM_THREADS / 32; q++)
+                if (sm.vit.wmax[q] > bv || (sm.vit.wmax[q] == bv && sm.vit.widx[q] < bi)) { bv = sm.vit.wmax[q]; bi = sm.vit.widx[q]; }
+            sm.vit.state = (unsigned)bi;
+        }
+        __syncthreads();
+    }
+    // traceback, newest tile first: the CTA pulls a tile into shared memory, one thread walks it
+    for (int base = ((steps - 1) / VT) * VT; base >= 0; base -= VT) {
+        const int nst = min(VT, steps - base);
+        for (int i = b; i < nst * 8; i += AM_THREADS) (&sm.vit.tile[0][0])[i] = decw[(size_t)base * 8 + i];
+        __syncthreads();
+        if (b == 0) {
+            unsigned state = sm.vit.state;
+            for (int k = nst - 1; k >= 0; k--) {
+                const int st_i = base + k;
+                const unsigned bit = (sm.vit.tile[k][state >> 5] >> (state & 31u)) & 1u;
+                if (st_i >= 32 && st_i < 32 + len) out[st_i - 32] = (uint8_t)((state >> 7) & 1u);
+                state = ((state << 1) & 254u) | bit;
+            }
+            sm.vit.state = state;
+        }
+        __syncthreads();
+    }
+#else
     for (int i = L.lane; i < 256; i += L.n) w.pm[0][i] = 0;
     AM_SYNC();
     int cur = 0;
@@ -268,6 +414,7 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
         state = ((state << 1) & 254u) | bit;
     }
     AM_SYNC();
+#endif
 }
 
 AM_HD inline void descramble(const AmTables &tb, Lanes L, uint8_t *bits, int len)     // decode.c:279-294
@@ -276,10 +423,34 @@ AM_HD inline void descramble(const AmTables &tb, Lanes L, uint8_t *bits, int len
     AM_SYNC();
 }
 
-AM_HD inline int bit_errors(const int8_t *coded, const uint8_t *decoded, unsigned len, unsigned g0, unsigned g1, unsigned g2,
+// Every lane gets the total.  Device: the positions are spread over the CTA - the encoder register at bit i is just
+// the nine decoded bits i-8 .. i (tail-biting), no running state - and the counts summed (integers: any order).
+AM_HD inline int bit_errors(Lanes L, const int8_t *coded, const uint8_t *decoded, unsigned len, unsigned g0, unsigned g1, unsigned g2,
                             const uint8_t *punct, int plen)                             // decode.c:234-259
 {
     const unsigned k = 9, gens[3] = { g0, g1, g2 };
+#if defined(__CUDA_ARCH__)
+    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    int errors = 0;
+    for (unsigned i = L.lane; i < len; i += L.n) {
+        unsigned r = 0;
+        for (unsigned q = 0; q < k; q++) {
+            const unsigned src = i >= q ? i - q : i + len - q;
+            r |= (unsigned)decoded[src] << (k - 1 - q);
+        }
+        const unsigned j = 3 * i;
+        for (unsigned g = 0; g < 3; g++)
+            if (punct[(j + g) % plen] && ((coded[j + g] > 0) != parity9(r & gens[g]))) errors++;
+    }
+    for (int o = 16; o; o >>= 1) errors += __shfl_xor_sync(0xffffffffu, errors, o);
+    __syncthreads();
+    if ((L.lane & 31) == 0) sm.red[L.lane >> 5] = errors;
+    __syncthreads();
+    int total = 0;
+    for (int q = 0; q < AM_THREADS / 32; q++) total += sm.red[q];
+    return total;
+#else
+    (void)L;
     unsigned r = 0, errors = 0;
     for (unsigned i = 0; i < k - 1; i++) r = ((r >> 1) | ((unsigned)decoded[len - (k - 1) + i] << (k - 1))) & 0xffffu;
     for (unsigned i = 0, j = 0; i < len; i++, j += 3) {
@@ -288,6 +459,7 @@ AM_HD inline int bit_errors(const int8_t *coded, const uint8_t *decoded, unsigne
             if (punct[(j + g) % plen] && ((coded[j + g] > 0) != parity9(r & gens[g]))) errors++;
     }
     return (int)errors;
+#endif
 }
 
 // ---- decode (reference src/decode.c) ----
@@ -450,10 +622,10 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
     if (st.am_diversity_wait == 0) {
         const int8_t *v = w.vit_p1 + bc * P1_LEN * 3;
         viterbi_k9(w, L, v, w.out, P1_LEN, 0561, 0657, 0711);
-        st.am_errors += bit_errors(v, w.out, P1_LEN, 0561, 0657, 0711, punct_e1, 15);
+        st.am_errors += bit_errors(L, v, w.out, P1_LEN, 0561, 0657, 0711, punct_e1, 15);
         AM_SYNC();
         descramble(tb, L, w.out, P1_LEN);
-        emit_frame(st, io, L, w.out, P1_LEN, 0);
+        emit_frame(st, w, io, L, w.out, P1_LEN, 0);
         if (p1_sync_lost(w.out, fix_header)) set_state(st, io, L, ST_NONE);              // inside frame_push, frame.c:538
         AM_SYNC();
         if (bc == 7) {
@@ -462,17 +634,17 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
                 if (st.psmi != MODE_MA3) {
                     total += 36000;
                     viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711);
-                    st.am_errors += bit_errors(w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711, punct_e2, 6);
+                    st.am_errors += bit_errors(L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711, punct_e2, 6);
                     AM_SYNC();
                     descramble(tb, L, w.out, P3_LEN);
-                    emit_frame(st, io, L, w.out, P3_LEN, 1);
+                    emit_frame(st, w, io, L, w.out, P3_LEN, 1);
                 } else {                                                                  // decode.c:533-539
                     total += 72000;
                     viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711);
-                    st.am_errors += bit_errors(w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711, punct_e1, 15);
+                    st.am_errors += bit_errors(L, w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711, punct_e1, 15);
                     AM_SYNC();
                     descramble(tb, L, w.out, P3_LEN_MA3);
-                    emit_frame(st, io, L, w.out, P3_LEN_MA3, 1);
+                    emit_frame(st, w, io, L, w.out, P3_LEN_MA3, 1);
                 }
                 AM_SYNC();
             }
@@ -580,7 +752,7 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
         if ((st.offset_history & 0xffff) == 0x5670) {
             st.bc = 0;
             set_state(st, io, L, ST_FINE);
-            l2_enqueue(st, 0, 0, 0);                                                     // frame_reset, sync.c:662-663
+            l2_enqueue(st, w, L, 0, 0, 0);                                               // frame_reset, sync.c:662-663
             st.am_errors = 0;                                                            // decode_reset, decode.c:556-565
             st.am_diversity_wait = 4;
             st.offset_history = 0;
@@ -726,6 +898,104 @@ AM_HD inline void symbol_fft(AmWork &w, const AmTables &tb, Lanes L, int sym, in
     AM_SYNC();
 }
 
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void am_bar_consumers()
+{
+#if defined(NB_EMU)
+    emu_bar_sync(1, AM_THREADS - 32);
+#else
+    asm volatile("bar.sync 1, %0;" ::"n"(AM_THREADS - 32) : "memory");
+#endif
+}
+
+// One pass over the 32 symbols of a block (acquire.c:178-195 first pass, :237-256 second pass), as a two-stage pipeline:
+// warp 0 runs the NCO phase chain of symbol i - 270 dependent complex multiplications and the renormalisation,
+// exactly the reference's recurrence - while warps 1..3 window, fold, shift and transform symbol i-1 (the radix-2
+// butterfly order of symbol_fft / fft256 above) in shared memory and hand its bins on:
+//   first pass  (bins == nullptr): the carrier bin of every symbol -> sm.dem.carrier, and - while acquiring - the
+//               magnitudes of the 107 bins around it, summed over the symbols in order -> sm.dem.mag
+//   second pass: bins CENTER-81 .. CENTER+81 -> bins[b][symbol]                               (sync_push)
+// `phase` is every thread's copy of the running NCO phase; all of them get the value after the last symbol.
+__device__ inline void demod_pass(AmWork &w, const AmTables &tb, Lanes L, int samperr, float2 &phase, float2 inc,
+                                  float2 (*bins)[BLK], bool want_mag)
+{
+    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    constexpr int NC = AM_THREADS - 32;
+    const int t = L.lane, c = t - 32;
+    const int offset = (FFT - CP) / 2;
+    float2 ph = phase;
+    float mag = 0, mag2 = 0;                                   // consumer c: bins CENTER - PIDS_OUTER + c and ... + c + NC (107 in all)
+    for (int i = 0; i <= BLK; i++) {
+        if (t < 32) {
+            if (i < BLK) {
+                float2 *out = sm.dem.ph[i & 1];
+                for (int j = 0; j < SYM; ++j) {
+                    if (t == 0) out[j] = ph;
+                    ph = cmul(ph, inc);
+                }
+                const float a = cabs2(ph);
+                ph = make_float2(ph.x / a, ph.y / a);
+            }
+        } else if (i > 0) {
+            const int sym = i - 1;
+            const float2 *pv = sm.dem.ph[sym & 1];
+            for (int j = c; j < FFT; j += NC) {
+                const float2 sample = cmul(pv[j], w.buf[sym * SYM + j + samperr]);
+                sm.dem.fft[(j + offset) % FFT] = j < CP ? cscale(sample, tb.shape[j]) : sample;
+            }
+            am_bar_consumers();
+            for (int j = FFT + c; j < SYM; j += NC) {
+                const float2 sample = cmul(pv[j], w.buf[sym * SYM + j + samperr]);
+                const int idx = (j + offset) % FFT;
+                sm.dem.fft[idx] = cadd(sm.dem.fft[idx], cscale(sample, tb.shape[j]));
+            }
+            am_bar_consumers();
+            for (int k = c; k < FFT; k += NC) {               // bit reversal
+                const int r = tb.brev[k];
+                if (r > k) {
+                    const float2 tmp = sm.dem.fft[k];
+                    sm.dem.fft[k] = sm.dem.fft[r];
+                    sm.dem.fft[r] = tmp;
+                }
+            }
+            am_bar_consumers();
+            for (int half = 1; half < FFT; half <<= 1) {
+                const int tstep = FFT / (2 * half);
+                for (int bf = c; bf < FFT / 2; bf += NC) {
+                    const int grp = bf / half, k = bf - grp * half;
+                    const int i0 = grp * 2 * half + k, i1 = i0 + half;
+                    const float2 tt = cmul(sm.dem.fft[i1], tb.tw[k * tstep]);
+                    const float2 u = sm.dem.fft[i0];
+                    sm.dem.fft[i0] = cadd(u, tt);
+                    sm.dem.fft[i1] = make_float2(u.x - tt.x, u.y - tt.y);
+                }
+                am_bar_consumers();
+            }
+            // spec[k] = fft[(k + 128) % 256] (fftshift, defines.h:123-138)
+            if (bins) {
+                for (int b = CENTER - MAX_IDX + c; b <= CENTER + MAX_IDX; b += NC) bins[b][sym] = sm.dem.fft[(b + FFT / 2) % FFT];
+            } else {
+                if (c == 0) sm.dem.carrier[sym] = sm.dem.fft[(CENTER + FFT / 2) % FFT];
+                if (want_mag) {
+                    mag += cabs2(sm.dem.fft[(CENTER - PIDS_OUTER + c + FFT / 2) % FFT]);
+                    if (c + NC < 2 * PIDS_OUTER + 1) mag2 += cabs2(sm.dem.fft[(CENTER - PIDS_OUTER + c + NC + FFT / 2) % FFT]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!bins && want_mag && c >= 0) {
+        sm.dem.mag[c] = mag;
+        if (c + NC < 2 * PIDS_OUTER + 1) sm.dem.mag[c + NC] = mag2;
+    }
+    static_assert(2 * NC >= 2 * PIDS_OUTER + 1 && NC <= 2 * PIDS_OUTER + 1, "two bins per consumer cover the 107");
+    if (t == 0) sm.dem.phase_end[0] = ph;
+    __syncthreads();
+    phase = sm.dem.phase_end[0];
+    __syncthreads();
+}
+#endif
+
 template <typename FixHeader>
 AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, const AmIo &io, Lanes L, FixHeader fix_header)
 {
@@ -745,7 +1015,7 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
             int accr = 0, acci = 0;
             auto at = [&](int pos, int c) -> int {
                 if (pos >= 0) return AM_LDIN(io.iq + 2 * (start + pos) + c);
-                return st.bp_hist[31 + pos][c];
+                return w.bp_hist[31 + pos][c];
             };
             for (int k = 1; k < 16; k++) {
                 accr = (short)(accr + (((at(i - 31 + k, 0) + at(i - 31 + 32 - k, 0)) * tb.bp_tap[k]) >> 15));
@@ -756,9 +1026,9 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
             w.buf[i] = make_float2((float)accr / 32767.0f, (float)acci / 32767.0f);
         }
         AM_SYNC();
-        for (int t = 0; t < 31; t++) {                                                    // every lane: private copy
-            st.bp_hist[t][0] = AM_LDIN(io.iq + 2 * (start + NACQ - 31 + t));
-            st.bp_hist[t][1] = AM_LDIN(io.iq + 2 * (start + NACQ - 31 + t) + 1);
+        for (int t = L.lane; t < 31; t += L.n) {
+            w.bp_hist[t][0] = AM_LDIN(io.iq + 2 * (start + NACQ - 31 + t));
+            w.bp_hist[t][1] = AM_LDIN(io.iq + 2 * (start + NACQ - 31 + t) + 1);
         }
         for (int i = L.lane; i < SYM; i += L.n) {
             float2 acc = make_float2(0.f, 0.f);
@@ -802,6 +1072,23 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
         float2 temp_phase = st.phase;
         float mag_sums[2 * PIDS_OUTER + 1];
         for (int j = 0; j < 2 * PIDS_OUTER + 1; j++) mag_sums[j] = 0;
+#if defined(__CUDA_ARCH__)
+        AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+        demod_pass(w, tb, L, samperr, temp_phase, phase_increment, nullptr, st.state != ST_FINE);
+        for (int i = 0; i < BLK; ++i) {                        // the regression, on the carriers the pass collected
+            const float2 carrier = sm.dem.carrier[i];
+            const float x = SYM * (i - (float)(BLK - 1) / 2);
+            if (i == 0) y = carg(carrier);
+            else y += carg(cdiv(carrier, last_carrier));
+            last_carrier = carrier;
+            sum_y += y;
+            sum_xy += x * y;
+            sum_x2 += x * x;
+        }
+        if (st.state != ST_FINE)
+            for (int j = 0; j < 2 * PIDS_OUTER + 1; j++) mag_sums[j] = sm.dem.mag[j];
+        AM_SYNC();
+#else
         for (int i = 0; i < BLK; ++i) {
             symbol_fft(w, tb, L, i, samperr, temp_phase, phase_increment);
             const float x = SYM * (i - (float)(BLK - 1) / 2);
@@ -815,6 +1102,7 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
                 for (int j = 0; j < 2 * PIDS_OUTER + 1; j++) mag_sums[j] += cabs2(w.spec[CENTER - PIDS_OUTER + j]);
             AM_SYNC();
         }
+#endif
         if (st.state != ST_FINE) {
             float mm = -1.0f;
             int max_index = -1;
@@ -829,11 +1117,15 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
         st.phase = cmul(st.phase, cexpj((float)((double)(-sum_y / BLK + (sum_xy / sum_x2) * (BLK) * SYM / 2) - 0.06)));
     }
 
+#if defined(__CUDA_ARCH__)
+    demod_pass(w, tb, L, samperr, st.phase, phase_increment, w.bins, false);                // acquire.c:237-257, sync_push
+#else
     for (int i = 0; i < BLK; ++i) {                                                       // acquire.c:237-257
         symbol_fft(w, tb, L, i, samperr, st.phase, phase_increment);
         for (int b = CENTER - MAX_IDX + L.lane; b <= CENTER + MAX_IDX; b += L.n) w.bins[b][i] = w.spec[b];   // sync_push
         AM_SYNC();
     }
+#endif
     sync_block(st, w, tb, io, L, fix_header);
 
     const int keep = SYM + (SYM / 2 - samperr) + st.keep_extra;                           // acquire.c:259-262

@@ -479,16 +479,17 @@ struct AmFixHeader {
     }
 };
 
-__global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmState *ast, nbam::AmWork *aw,
-                                           const nbam::AmTables *tb, int max_blocks, int last_pass)
+__global__ void __launch_bounds__(nbam::AM_THREADS) k_am(DevPtrs p, EngineDims d, nbam::AmState *ast, nbam::AmWork *aw,
+                                                         const nbam::AmTables *tb, int max_blocks, int last_pass)
 {
     const int s = blockIdx.x;
-    const nbam::Lanes L = { (int)threadIdx.x, 32 };
+    __shared__ nbam::AmSmem sm;
     __shared__ GfTab gf;
-    gf_tab_load(gf, (int)threadIdx.x, 32);
-    __syncwarp();
+    const nbam::Lanes L = { (int)threadIdx.x, nbam::AM_THREADS, &sm };
+    gf_tab_load(gf, (int)threadIdx.x, nbam::AM_THREADS);
+    __syncthreads();
     StreamState &fs = p.st[s];
-    nbam::AmState st = ast[s];
+    nbam::AmState st = ast[s];                             // every thread's own copy of the receiver's scalars
     st.log_len = fs.log_len;                               // the host rewinds the log when it drains it ...
     st.log_overflow = fs.log_overflow;                     // ... and takes the overflow flag with it
     st.l2_on = d.l2;
@@ -501,9 +502,9 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
         const long long avail = *reinterpret_cast<volatile long long *>(&fs.in_avail) / 2;    // cs16 complex samples
         if (avail < st.start + nbam::NACQ) break;
         nbam::process_window(st, aw[s], *tb, io, L, AmFixHeader{ &gf });
-        __syncwarp();
+        __syncthreads();
     }
-    __syncwarp();
+    __syncthreads();
     if (L.lane == 0) {
         ast[s] = st;
         fs.log_len = st.log_len;
@@ -513,9 +514,9 @@ __global__ void __launch_bounds__(32) k_am(DevPtrs p, EngineDims d, nbam::AmStat
         fs.state = st.state;
         fs.l2_n = st.l2_n;                                 // k_l2 follows this launch (launch_pass)
         for (int i = 0; i < st.l2_n; i++) {
-            fs.l2_off[i] = st.l2_off[i];
-            fs.l2_lc[i] = st.l2_lc[i];
-            fs.l2_nbits[i] = st.l2_nbits[i];
+            fs.l2_off[i] = aw[s].l2_off[i];
+            fs.l2_lc[i] = aw[s].l2_lc[i];
+            fs.l2_nbits[i] = aw[s].l2_nbits[i];
         }
         if (nb_done) atomicAdd(&p.ctl->progress, (unsigned long long)nb_done);
         StreamBrief b;
@@ -1581,7 +1582,7 @@ static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true
     if (last_pass) cudaMemsetAsync(reinterpret_cast<uint8_t *>(e->dp.ctl) + offsetof(EngineCtl, more), 0, sizeof(unsigned), e->stream);
     if (e->am_st) {                                        // AM: one kernel does the whole chain, window after window
         const bool l2 = e->l2 && e->dims.l2;              // with L2 on, a launch stops after 16 blocks: its frames fit the queue
-        k_am<<<e->dims.nstreams, 32, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20,
+        k_am<<<e->dims.nstreams, nbam::AM_THREADS, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20,
                                                      last_pass ? 1 : 0);
         e->stats.kernel_launches += 1;
         if (l2) {
