@@ -209,7 +209,9 @@ int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long 
  * equalise + error sums, demap + bookkeeping}. */
 int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12, unsigned long long *n12);
 
-/* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops); 0 = default. */
+/* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops; bit 1: library
+ * sincosf / atan2f on the Costas loops' dependent chain instead of the short-chain versions); 0 = default.  Also read
+ * from the environment (NRSC5_B200_DBG) when an engine is created. */
 int nrsc5b_debug_set(int flags);
 
 /* L2 framing on the device for every frame the engine (FM or AM) decodes from now on: after each REC_FRAME's pass

@@ -807,6 +807,8 @@ static void init_state_host(StreamState &st)
 
 static void launch_k_stream(nrsc5b_engine *e, int last_pass);
 
+extern "C" int nrsc5b_debug_set(int flags);
+
 extern "C" const char *nrsc5b_version(void) { return "nrsc5_b200 0.1 (sm_100a)"; }
 
 extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
@@ -845,6 +847,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     for (int i = 0; i < 4; i++) { e->kernel_ms[i] = 0; e->kernel_n[i] = 0; }
     e->pinned = nullptr; e->h_state = nullptr; e->pinned_free = nullptr; e->avail_ring = nullptr; e->avail_pos = 0; e->reset_done = nullptr;
     const int S = cfg->nstreams;
+    if (const char *dbg = getenv("NRSC5_B200_DBG")) nrsc5b_debug_set(atoi(dbg));      // kernel experiment switches (A/B runs)
     e->dims.nstreams = S;
     e->dims.in_stride = (cfg->input_capacity + 63) & ~(size_t)63;
     e->dims.log_cap = cfg->log_capacity ? ((cfg->log_capacity + 15) & ~(size_t)15) : (1u << 20);
@@ -1888,20 +1891,21 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
     if (!e) return NRSC5B_EINVAL;
     if (e->in_flight) return 0;
     bool decode = true;
-    if (e->stalled) {
-        long long units = 0;
-        for (int s = 0; s < e->dims.nstreams; s++) units += e->pushed[s] + e->staged_units[s];
-        if (units == e->stalled_units) {
-            if (flush) { int rc = flush_staged(e); if (rc) return rc; }
-            return 0;
-        }
-        e->stalled = false;
-    }
     const int passes = plan_passes(e, true, &decode);
-    if (passes == 0) {
-        if (flush) { int rc = flush_staged(e); if (rc) return rc; }
+    if (passes == 0 && !flush) {
         if (e->trace_on) e->tr.submits_idle++;
-        return 0;
+        return 0;                                              // the usual case of a small push: no CUDA call at all
+    }
+    int rc = flush_staged(e);
+    if (rc == NRSC5B_EFULL) rc = NRSC5B_OK;                // no room yet: the batch runs on what the device holds and frees some
+    if (rc) return rc;
+    if (passes == 0) return 0;
+    if (e->stalled) {
+        // the last batch moved no stream: nothing to gain from another one until the device holds more samples
+        long long units = 0;
+        for (int s = 0; s < e->dims.nstreams; s++) units += e->pushed[s];
+        if (units == e->stalled_units) return 0;
+        e->stalled = false;
     }
     const double t0 = e->trace_on ? wall_s() : 0;
     if (e->direct_push) decode = true;                     // counts published outside a batch: plan nothing on them
@@ -1912,8 +1916,6 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
         if (cudaMallocHost((void **)&e->xlog, (size_t)S * e->xlog_stride) != cudaSuccess ||
             cudaMallocHost((void **)&e->xhdr, sizeof(ExportHdr) * S) != cudaSuccess) return NRSC5B_ENOMEM;
     }
-    int rc = flush_staged(e);
-    if (rc) return rc;
     {
         const unsigned slot = e->fence_next++ & 63;
         if (!e->fence[slot]) CK(cudaEventCreateWithFlags(&e->fence[slot], cudaEventDisableTiming));
@@ -1959,7 +1961,7 @@ extern "C" int nrsc5b_poll(nrsc5b_engine_t *e, int wait)
     if (e->h_ctl->progress == e->last_progress && !(e->h_ctl->px_need & ~(unsigned)e->dims.px_enabled)) {
         e->stalled = true;
         e->stalled_units = 0;
-        for (int s = 0; s < e->dims.nstreams; s++) e->stalled_units += e->pushed[s] + e->staged_units[s];
+        for (int s = 0; s < e->dims.nstreams; s++) e->stalled_units += e->pushed[s];
     }
     e->last_progress = e->h_ctl->progress;
     if (e->batch_decoded)

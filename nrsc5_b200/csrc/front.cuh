@@ -530,8 +530,36 @@ __device__ __forceinline__ int ref_bin(int slot)                // slot < MAXREF
     return slot < MAXREF ? LB0 + PW * slot : UB1 - PW * (slot - MAXREF);
 }
 
+// The Costas loop below is 32 DEPENDENT steps per reference carrier on one warp - its cost is the latency of one
+// step's chain phase -> exp(-j phase) -> rotate -> arg -> filter -> phase.  Two short-chain replacements for the
+// library calls on that chain (selected by FAST): the rotation by the SFU's sin / cos (|phase| <= pi; absolute error
+// 2^-21.4, the size of a float's last bit at 1.0), and the loop error - the argument of u^2, i.e. of a point in the
+// right half plane while the loop tracks - by one reciprocal and a degree-8 polynomial in t^2 (fitted on [0, 1], max
+// error 1.2e-7 rad).  Both errors are of the size by which CUDA's sincosf / atan2f differ from the reference's libm;
+// the parity tests bound the consequence (soft bits within one step, PDUs exact).
+__device__ __forceinline__ float atan2_short(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float z = t * t;
+    float p = 0.0028340641874819994f;
+    p = __fmaf_rn(p, z, -0.016005029901862144f);
+    p = __fmaf_rn(p, z, 0.042587608098983765f);
+    p = __fmaf_rn(p, z, -0.07495445758104324f);
+    p = __fmaf_rn(p, z, 0.10636754333972931f);
+    p = __fmaf_rn(p, z, -0.14202570915222168f);
+    p = __fmaf_rn(p, z, 0.19992484152317047f);
+    p = __fmaf_rn(p, z, -0.3333306610584259f);
+    p = __fmaf_rn(p, z, 1.0f);
+    float r = p * t;
+    if (ay > ax) r = 1.57079637f - r;
+    if (x < 0.f) r = 3.14159274f - r;
+    return copysignf(r, y);
+}
+
 // adjust_ref (sync.c:90-130) on one row of 32 symbols
-__device__ __forceinline__ void costas_row(float2 *z, float *phs, int zs, float &cfreq, float &cphase, int cfo, float alpha, float beta)
+__device__ __forceinline__ void costas_row(float2 *z, float *phs, int zs, float &cfreq, float &cphase, int cfo, float alpha, float beta, bool FAST)
 {
     // sync pattern -1, 1, -1, -1, -1, 1, 1, 0, 1, -1, 0, 0, 0, -1, -1, 0, 0, 0, 0, 0, -1, 1, -1, 0 x8, -1 as bit masks
     const unsigned pat_pos = (1u << 1) | (1u << 5) | (1u << 6) | (1u << 8) | (1u << 21);
@@ -546,8 +574,17 @@ __device__ __forceinline__ void costas_row(float2 *z, float *phs, int zs, float 
     for (int n = 0; n < BLK; n++) {
         const float2 v = z[n * zs];
         // u = v * exp(-j*ph); the loop error arg(v^2 * exp(-2j*ph)) / 2 equals arg(u^2) / 2
-        const float2 u = cmulf(v, cexp_j(-ph));
-        const float error = atan2f((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y) * 0.5f;
+        float2 rot;
+        if (FAST) {
+            float sn, cs;
+            __sincosf(-ph, &sn, &cs);
+            rot = make_float2(cs, sn);
+        } else {
+            rot = cexp_j(-ph);
+        }
+        const float2 u = cmulf(v, rot);
+        const float error = (FAST ? atan2_short((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y)
+                                  : atan2f((u.x * u.y) * 2.0f, u.x * u.x - u.y * u.y)) * 0.5f;
         phs[n * zs] = ph;
         z[n * zs] = u;
         f += beta * error;
@@ -674,7 +711,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
         if (i < nref) {
             const int b = ref_bin(t);
             float f = cfreq[b], ph = cphase[b];
-            costas_row(&sm.zref[0][t], &sm.phs[0][t], ZS, f, ph, 0, alpha, beta);
+            costas_row(&sm.zref[0][t], &sm.phs[0][t], ZS, f, ph, 0, alpha, beta, !(g_dbg & 2));
             cfreq[b] = f;
             cphase[b] = ph;
             sm.cfq[t] = f;
@@ -790,7 +827,7 @@ __device__ void front_sync(const DevPtrs &p, const EngineDims &d, int s, SyncSme
                     for (int n = 0; n < BLK; n++)
                         row[(size_t)n * NSB] = q ? src[(size_t)n * NSB]
                                                  : (ci >= 0 ? ldbin(&bins[(size_t)n * NBINS + ci]) : make_float2(0.f, 0.f));
-                    costas_row(row, sphs + t, NSB, f, ph, cfo, alpha, beta);
+                    costas_row(row, sphs + t, NSB, f, ph, cfo, alpha, beta, false);
                     sm.srch.offs[cfo + 2 * PW][2 * i + upper] = ref_find(row, NSB, (unsigned)(30 - i) & 3);
                     for (int n = 0; n < BLK; n++)            // reset_ref (sync.c:132-136)
                         row[(size_t)n * NSB] = cmulf(row[(size_t)n * NSB], cexp_j(sphs[(size_t)n * NSB + t]));

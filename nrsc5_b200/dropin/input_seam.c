@@ -117,9 +117,10 @@ static void replay_l2(input_t *st, const uint8_t *pay)
     }
     if (flags & 1)                                   /* frame.c:535-540: the first audio header of a P1 frame failed */
     {
-        st->in_frame_push = 1;
+        /* The engine applied this very predicate on the GPU when it decoded the frame and is long past it (batches
+         * run ahead of the replay): only the host's view and the event follow here - forcing the engine's state now
+         * would drop a sync it has regained since. */
         input_set_sync_state(st, SYNC_STATE_NONE);
-        st->in_frame_push = 0;
     }
 }
 
