@@ -165,6 +165,7 @@ int nrsc5b_process_fence(nrsc5b_engine_t *e, int token);
  * One batch is in flight at a time; nrsc5b_process / nrsc5b_drain must not be mixed in while one is.  This is what the
  * drop-in libnrsc5.so runs on: pushes return at once, callbacks are made - in the reference's order - from a later
  * push (or from nrsc5_close) as batches complete. */
+int nrsc5b_prepare_async(nrsc5b_engine_t *e);      /* optional: allocate the page-locked staging / export buffers now */
 int nrsc5b_stage_cu8(nrsc5b_engine_t *e, int stream, const uint8_t *buf, size_t nbytes);
 int nrsc5b_stage_cs16(nrsc5b_engine_t *e, int stream, const int16_t *buf, size_t nvalues);
 int nrsc5b_submit(nrsc5b_engine_t *e, int flush);

@@ -498,8 +498,12 @@ __global__ void __launch_bounds__(nbam::AM_THREADS) k_am(DevPtrs p, EngineDims d
     const nbam::AmIo io = { reinterpret_cast<const int16_t *>(p.iq + (size_t)s * d.in_stride), p.log + (size_t)s * d.log_cap,
                             (unsigned)d.log_cap };
     int nb_done = 0;
+    __shared__ long long sh_avail;
     for (; nb_done < max_blocks; nb_done++) {
-        const long long avail = *reinterpret_cast<volatile long long *>(&fs.in_avail) / 2;    // cs16 complex samples
+        // the sample count can grow while the kernel runs (asynchronous pushes): one thread reads it for the whole CTA
+        if (threadIdx.x == 0) sh_avail = *reinterpret_cast<volatile long long *>(&fs.in_avail) / 2;    // cs16 complex samples
+        __syncthreads();
+        const long long avail = sh_avail;
         if (avail < st.start + nbam::NACQ) break;
         nbam::process_window(st, aw[s], *tb, io, L, AmFixHeader{ &gf });
         __syncthreads();
@@ -1708,6 +1712,7 @@ extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned
 }
 
 static int flush_staged(nrsc5b_engine *e);
+extern "C" int nrsc5b_prepare_async(nrsc5b_engine_t *e);
 
 static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
 {
@@ -1790,11 +1795,8 @@ static int stage_bytes(nrsc5b_engine *e, int stream, const uint8_t *buf, size_t 
 {
     if (stream < 0 || stream >= e->dims.nstreams || (nbytes & 3) || !e->iq_owned || e->am_ring) return NRSC5B_EINVAL;
     if (!e->stage[0]) {
-        e->stage_cap = 4u << 20;
-        for (int i = 0; i < 2; i++) {
-            if (cudaMallocHost((void **)&e->stage[i], e->stage_cap) != cudaSuccess) return NRSC5B_ENOMEM;
-            CK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
-        }
+        int rc = nrsc5b_prepare_async(e);
+        if (rc) return rc;
     }
     // a call that came back with NRSC5B_EFULL left the rest of its samples here (the caller's buffer may be gone by
     // the time it retries): they go first; the retry passes (NULL, 0)
@@ -1856,7 +1858,7 @@ static int flush_staged(nrsc5b_engine *e)
     const double t0 = e->trace_on ? wall_s() : 0;
     const uint8_t *src = e->stage[e->stage_cur];
     while (!e->staged.empty()) {
-        const nrsc5b_engine::Staged g = e->staged.front();
+        nrsc5b_engine::Staged &g = e->staged.front();
         size_t off = (size_t)e->pushed[g.stream] * 2;
         if (off + g.n > e->dims.in_stride) {
             const double t1 = e->trace_on ? wall_s() : 0;
@@ -1864,13 +1866,20 @@ static int flush_staged(nrsc5b_engine *e)
             if (e->trace_on) { e->tr.trims++; e->tr.s_trim += wall_s() - t1; }
             if (rc) return rc;
             off = (size_t)e->pushed[g.stream] * 2;
-            if (off + g.n > e->dims.in_stride) return NRSC5B_EFULL;   // (what was copied so far is off the list)
         }
-        CK(cudaMemcpyAsync(e->iq_owned + (size_t)g.stream * e->dims.in_stride + off, src + g.off, g.n, cudaMemcpyHostToDevice,
-                           e->copy_stream));
-        e->pushed[g.stream] += (long long)(g.n / 2);
-        e->staged_units[g.stream] -= (long long)(g.n / 2);
-        e->unpublished[g.stream] = 1;
+        // as much of the entry as the device buffer takes (an entry can be larger than a small buffer)
+        const size_t room = e->dims.in_stride > off ? (e->dims.in_stride - off) & ~(size_t)3 : 0;
+        const size_t n = g.n < room ? g.n : room;
+        if (n) {
+            CK(cudaMemcpyAsync(e->iq_owned + (size_t)g.stream * e->dims.in_stride + off, src + g.off, n, cudaMemcpyHostToDevice,
+                               e->copy_stream));
+            e->pushed[g.stream] += (long long)(n / 2);
+            e->staged_units[g.stream] -= (long long)(n / 2);
+            e->unpublished[g.stream] = 1;
+            g.off += n;
+            g.n -= n;
+        }
+        if (g.n) return NRSC5B_EFULL;                           // the rest stays on the list (and in this staging half)
         e->staged.erase(e->staged.begin());
     }
     CK(cudaEventRecord(e->stage_free[e->stage_cur], e->copy_stream));
@@ -1879,6 +1888,28 @@ static int flush_staged(nrsc5b_engine *e)
     const double t2 = e->trace_on ? wall_s() : 0;
     CK(cudaEventSynchronize(e->stage_free[e->stage_cur]));      // the other half: its copy was issued a whole half ago
     if (e->trace_on) { e->tr.flushes++; e->tr.s_stage_wait += wall_s() - t2; e->tr.s_flush += wall_s() - t0; }
+    return NRSC5B_OK;
+}
+
+/* Allocates what the asynchronous path needs (page-locked staging halves and export buffers) now instead of at the
+ * first nrsc5b_stage_* / nrsc5b_submit call - a few milliseconds of cudaMallocHost that a caller may not want inside
+ * its first push. */
+extern "C" int nrsc5b_prepare_async(nrsc5b_engine_t *e)
+{
+    if (!e) return NRSC5B_EINVAL;
+    if (!e->stage[0]) {
+        e->stage_cap = 4u << 20;
+        for (int i = 0; i < 2; i++) {
+            if (cudaMallocHost((void **)&e->stage[i], e->stage_cap) != cudaSuccess) return NRSC5B_ENOMEM;
+            CK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
+        }
+    }
+    if (!e->xlog) {
+        const int S = e->dims.nstreams;
+        e->xlog_stride = (e->dims.log_cap + 15) & ~(size_t)15;
+        if (cudaMallocHost((void **)&e->xlog, (size_t)S * e->xlog_stride) != cudaSuccess ||
+            cudaMallocHost((void **)&e->xhdr, sizeof(ExportHdr) * S) != cudaSuccess) return NRSC5B_ENOMEM;
+    }
     return NRSC5B_OK;
 }
 
@@ -1912,9 +1943,8 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
     e->direct_push = false;
     const int S = e->dims.nstreams;
     if (!e->xlog) {
-        e->xlog_stride = (e->dims.log_cap + 15) & ~(size_t)15;
-        if (cudaMallocHost((void **)&e->xlog, (size_t)S * e->xlog_stride) != cudaSuccess ||
-            cudaMallocHost((void **)&e->xhdr, sizeof(ExportHdr) * S) != cudaSuccess) return NRSC5B_ENOMEM;
+        rc = nrsc5b_prepare_async(e);
+        if (rc) return rc;
     }
     {
         const unsigned slot = e->fence_next++ & 63;

@@ -252,6 +252,11 @@ static void engine_open(input_t *st, int cs16)
     st->trace = getenv("NRSC5_B200_TRACE") != NULL;
     const char *sync = getenv("NRSC5_B200_SYNC");
     st->pipelined = st->device_l2 && !(sync && atoi(sync));
+    if (st->pipelined)
+    {
+        rc = nrsc5b_prepare_async(st->engine);       /* page-locked buffers now, not inside the first push */
+        if (rc) fail("nrsc5b_prepare_async", rc);
+    }
     if (st->device_l2)
     {
         rc = nrsc5b_enable_l2(st->engine, 1);

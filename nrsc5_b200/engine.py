@@ -76,6 +76,7 @@ def load_library():
     L.nrsc5b_push_fence.argtypes = [vp]
     L.nrsc5b_process_fence.argtypes = [vp, ci]
     L.nrsc5b_synchronize.argtypes = [vp]
+    L.nrsc5b_prepare_async.argtypes = [vp]
     L.nrsc5b_stage_cu8.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_stage_cs16.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_submit.argtypes = [vp, ci]

@@ -211,6 +211,7 @@ def test_pipelined_use_equals_synchronous_decode():
                 rc = e.stage_cu8(s, piece)
                 while rc == -5:
                     waits += 1
+                    assert waits < 100000, "the engine never made room"
                     if e.poll(True) == 1:
                         take()
                     e.submit()
