@@ -237,6 +237,31 @@ long nrsc5b_l2_frames(int device, const uint8_t *frames, size_t nbytes, uint8_t 
 /* 2048-point forward complex FFT of nffts rows (float2 interleaved), natural order, for numerics tests */
 int nrsc5b_fft2048(int device, const float *in, float *out, int nffts);
 
+/* ---- wideband channeliser (the reference has no counterpart: its ingest is one narrowband device per
+ * handle, reference src/nrsc5.c:130-207) ----
+ * One cu8 capture at 32 x 744 187.5 = 23 814 000 S/s -> `nch` FM channels at 744 187.5 S/s cs16, the format
+ * input_push_cs16 (reference src/input.c:119-124) / nrsc5b_push_cs16 take.  Channel k is centred `offsets_100khz[k]` x
+ * 100 kHz from the capture's centre.  Integer-exact definition (csrc/channelizer.cu header; restated in numpy by
+ * tests/test_channelizer.py):
+ *     acc = sum_{u<256} W_k[u] * (x[32 n + u] - (127 + 127j));   v = (acc + 2^13) >> 14;
+ *     y[k][n] = saturate16((v * conj(P[(1600 m_k n) mod 11907]) + 2^14) >> 15)
+ * with the 16-bit taps W_k and the phasor table P as returned by nrsc5b_chan_tables.  Runs on the tensor cores
+ * (tcgen05.mma.kind::i8, TMA-fed, accumulators in TMEM). */
+typedef struct nrsc5b_channelizer nrsc5b_channelizer_t;
+int nrsc5b_chan_create(nrsc5b_channelizer_t **out, int device, const int *offsets_100khz, int nch);
+void nrsc5b_chan_destroy(nrsc5b_channelizer_t *c);
+/* taps[nch][256][2] (real, imaginary part of W_k[u]) and phasor[11907][2]; either may be NULL */
+int nrsc5b_chan_tables(nrsc5b_channelizer_t *c, int16_t *taps, int16_t *phasor);
+/* the same tables computed on the host without a device (the definition's inputs, for the numpy restatement) */
+int nrsc5b_chan_make_tables(const int *offsets_100khz, int nch, int16_t *taps, int16_t *phasor);
+/* output samples per channel for a capture of nbytes (a multiple of 64): nbytes / 64 - 7 */
+long long nrsc5b_chan_outputs(size_t nbytes);
+/* device capture (64-byte aligned, nbytes % 64 == 0) -> device out[nch][out_stride] (int16 values, I/Q interleaved;
+ * out_stride >= 2 * outputs, even), asynchronous on cuda_stream (a cudaStream_t cast to void*, NULL = default) */
+int nrsc5b_chan_run_device(nrsc5b_channelizer_t *c, const void *d_cu8, size_t nbytes, void *d_out, size_t out_stride, void *cuda_stream);
+/* host capture -> host out[nch][2 * outputs]; synchronous (tests) */
+int nrsc5b_chan_run(nrsc5b_channelizer_t *c, const uint8_t *cu8, size_t nbytes, int16_t *out);
+
 const char *nrsc5b_version(void);
 
 #ifdef __cplusplus

@@ -19,6 +19,7 @@ COMMON = (["-DNB_DEBUG"] if os.environ.get("NB_DEBUG") else []) + ["-O3", "-line
 UNITS = [
     ("frontend.cu", []),
     ("engine.cu", ["-fmad=false"]),
+    ("channelizer.cu", []),
 ]
 
 
