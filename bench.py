@@ -277,6 +277,12 @@ def am_leg(args, engine_factory=None):
     again = e.drain_all()
     assert [record_digest(r) for r in again] == first, "rewind -> process gave other records than reset -> push -> process"
     samples = S * (n // 2)
+    try:
+        pc = e.am_phase_cycles()                          # of the last rewind -> process
+        nblk = max(1, int(e.stats().blocks))
+        am_phases = {k: round(v / nblk / 1965.0, 2) for k, v in pc.items()}    # us per stream-block at 1965 MHz
+    except Exception:                                     # noqa: BLE001
+        am_phases = None
     # the unmodified reference on this host's cores: one process per channel (cs16, AM mode), 3 passes each
     cpu = None
     try:
@@ -301,7 +307,7 @@ def am_leg(args, engine_factory=None):
                         "note": "latency-bound by construction: the NCO phase chain (17 280 dependent complex multiplications per block) "
                                 "and the K=9 add-compare-select (one barrier per trellis step) are sequential per stream; 256 streams "
                                 "put at most two CTAs on an SM", "blocks_total": blocks},
-           "cpu_baseline": cpu,
+           "cpu_baseline": cpu, "phases_us_per_stream_block_at_1965MHz": am_phases,
            "x_realtime": samples * steps / res / 46511.71875, "ms_per_step": 1e3 * res / steps,
            "e2e": {"value": samples * steps / tot / 1e6, "ms_per_step": 1e3 * tot / steps, "x_realtime": samples * steps / tot / 46511.71875,
                    "process_ms_per_step": 1e3 * proc / steps, "h2d_bytes_per_step": int(S * n * 2),

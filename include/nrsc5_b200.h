@@ -210,6 +210,10 @@ int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long 
  * equalise + error sums, demap + bookkeeping}. */
 int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12, unsigned long long *n12);
 
+/* AM engines: SM cycles of k_am per phase summed over streams since the last reset / rewind: {window + coarse acquisition,
+ * first demodulation pass, second pass, sync + slicing, PIDS, P1 + P3 + interleaver, of which P3, of which interleaver}. */
+int nrsc5b_get_am_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc8);
+
 /* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops; bit 1: library
  * sincosf / atan2f on the Costas loops' dependent chain instead of the short-chain versions); 0 = default.  Also read
  * from the environment (NRSC5_B200_DBG) when an engine is created. */

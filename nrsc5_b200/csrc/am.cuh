@@ -139,6 +139,8 @@ struct AmWork {
     int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
     uint8_t out[P3_LEN_MA3 + 8];
     short pm[2][256];
+    unsigned long long ph_cyc[8];              // SM cycles per phase (thread 0): window + acquisition, first pass, second pass, sync +
+                                               // slicing, PIDS, P1 (Viterbi, BER, packing), P3, interleaver
     alignas(16) uint8_t dec[(size_t)VIT_MAX_STEPS * 32];   // survivor bits, 256 per trellis step (eight 32-bit words), see viterbi_k9
     float2 mult[4][PW];
     uint8_t sym_pl[BLK * PW], sym_pu[BLK * PW], sym_s[BLK * PW], sym_t[BLK * PW], sym_pids[2 * BLK];
@@ -173,6 +175,21 @@ struct AmIo {
     uint8_t *log;
     unsigned log_cap;
 };
+
+#if defined(__CUDA_ARCH__)
+#define AM_LAP(w, L, slot, t0)                                   \
+    do {                                                         \
+        if ((L).lane == 0) {                                     \
+            const long long t1_ = clock64();                     \
+            (w).ph_cyc[slot] += (unsigned long long)(t1_ - (t0)); \
+            (t0) = t1_;                                          \
+        }                                                        \
+    } while (0)
+#define AM_T0() clock64()
+#else
+#define AM_LAP(w, L, slot, t0) ((void)0)
+#define AM_T0() 0
+#endif
 
 // ---- records ----
 // Every lane calls this with identical arguments (each keeps its own copy of the cursor); lane 0 writes.
@@ -628,6 +645,8 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
         emit_frame(st, w, io, L, w.out, P1_LEN, 0);
         if (p1_sync_lost(w.out, fix_header)) set_state(st, io, L, ST_NONE);              // inside frame_push, frame.c:538
         AM_SYNC();
+        long long tl3 = AM_T0();
+        (void)tl3;
         if (bc == 7) {
             unsigned total = 8 * 9000;
             if (!st.rdbi) {
@@ -648,13 +667,17 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
                 }
                 AM_SYNC();
             }
+            AM_LAP(w, L, 6, tl3);
             const float cber = (float)st.am_errors / (float)total;
             uint8_t *rec = log_reserve(st, io, L, REC_BER, 4);
             if (rec && L.lane == 0) memcpy(rec, &cber, 4);
         }
     }
     if (bc == 7) {
+        long long tl7 = AM_T0();
+        (void)tl7;
         interleaver_ma1(w, L, st.psmi == MODE_MA3);
+        AM_LAP(w, L, 7, tl7);
         if (st.am_diversity_wait > 0) st.am_diversity_wait--;
     }
 }
@@ -776,7 +799,10 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
         }
         AM_SYNC();
     }
+    long long tlap = AM_T0();
+    (void)tlap;
     process_pids(st, w, tb, io, L);
+    AM_LAP(w, L, 4, tlap);
 
     // partitions (sync.c:687-717): per column the two training rows give the equaliser tap.  Column 0 of the
     // primary partitions sits at -/+ `primary`, of the secondary at +28, of the tertiary at +2 (MA1) / -28 (MA3)
@@ -828,7 +854,9 @@ AM_HD inline void sync_block(AmState &st, AmWork &w, const AmTables &tb, const A
         w.buffer_t[st.bc * BLK * PW + i] = w.sym_t[i];
     }
     AM_SYNC();
+    AM_LAP(w, L, 3, tlap);
     process_p1_p3(st, w, tb, io, L, st.bc, fix_header);
+    AM_LAP(w, L, 5, tlap);                     // (P1 + at the frame's last block P3 and the interleaver; split below)
     st.bc = (st.bc + 1) % 8;
 }
 
@@ -1002,6 +1030,8 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
     int samperr = 0;
     float angle, angle_diff;
     const long long start = st.start;
+    long long tlap = AM_T0();
+    (void)tlap;
 
     if (st.state == ST_FINE) {                                                            // acquire.c:110-119
         samperr = SYM / 2 + st.samperr;
@@ -1062,6 +1092,7 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
     for (int i = L.lane; i < NACQ; i += L.n) w.buf[i] = input_at(io, start + i);          // acquire.c:160-161
     AM_SYNC();
 
+    AM_LAP(w, L, 0, tlap);
     angle = (float)((double)angle - 2 * PI * st.cfo);                                     // acquire.c:164-168
     st.phase = cmul(st.phase, cexpj((float)(-(SYM / 2 - samperr)) * angle / (float)FFT));
     float2 phase_increment = cexpj(angle / (float)FFT);
@@ -1117,6 +1148,7 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
         st.phase = cmul(st.phase, cexpj((float)((double)(-sum_y / BLK + (sum_xy / sum_x2) * (BLK) * SYM / 2) - 0.06)));
     }
 
+    AM_LAP(w, L, 1, tlap);
 #if defined(__CUDA_ARCH__)
     demod_pass(w, tb, L, samperr, st.phase, phase_increment, w.bins, false);                // acquire.c:237-257, sync_push
 #else
@@ -1126,6 +1158,7 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
         AM_SYNC();
     }
 #endif
+    AM_LAP(w, L, 2, tlap);
     sync_block(st, w, tb, io, L, fix_header);
 
     const int keep = SYM + (SYM / 2 - samperr) + st.keep_extra;                           // acquire.c:259-262

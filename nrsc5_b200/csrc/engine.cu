@@ -1704,6 +1704,22 @@ extern "C" int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *c
     return NRSC5B_OK;
 }
 
+/* AM: SM cycles k_am spent per phase, summed over streams since the last reset / rewind (thread 0's clock): window +
+ * coarse acquisition, first demodulation pass (carrier), second pass (bins), sync + slicing, PIDS, P1 group incl. the two
+ * following, P3 Viterbi, interleaver. */
+extern "C" int nrsc5b_get_am_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc8)
+{
+    if (!e || !cyc8 || !e->am_work) return NRSC5B_EINVAL;
+    CK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 8; i++) cyc8[i] = 0;
+    for (int s = 0; s < e->dims.nstreams; s++) {
+        unsigned long long v[8];
+        CK(cudaMemcpy(v, reinterpret_cast<uint8_t *>(e->am_work + s) + offsetof(nbam::AmWork, ph_cyc), sizeof(v), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 8; i++) cyc8[i] += v[i];
+    }
+    return NRSC5B_OK;
+}
+
 extern "C" int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long *n4)
 {
     if (!e || !ms4 || !n4) return NRSC5B_EINVAL;

@@ -64,6 +64,7 @@ def load_library():
     L.nrsc5b_set_profiling.argtypes = [vp, ci]
     L.nrsc5b_get_kernel_times.argtypes = [vp, vp, vp]
     L.nrsc5b_get_phase_cycles.argtypes = [vp, vp, vp]
+    L.nrsc5b_get_am_phase_cycles.argtypes = [vp, vp]
     L.nrsc5b_set_cuda_stream.argtypes = [vp, vp]
     L.nrsc5b_push_cu8.argtypes = [vp, ci, vp, sz]
     L.nrsc5b_push_cs16.argtypes = [vp, ci, vp, sz]
@@ -272,6 +273,12 @@ class Engine:
                  "sync_fine.gather", "sync_fine.costas", "sync_fine.tables_feedback", "sync_fine.stage",
                  "sync_fine.equalise", "sync_fine.demap_tail"]
         return {k: (int(c[i]), int(n[i])) for i, k in enumerate(names)}
+
+    def am_phase_cycles(self):
+        c = (ctypes.c_ulonglong * 8)()
+        _check(self._L.nrsc5b_get_am_phase_cycles(self._h, c), "nrsc5b_get_am_phase_cycles")
+        names = ["window_acquire", "pass1_carrier", "pass2_bins", "sync_slicing", "pids", "p1_p3_interleaver", "of_which_p3", "of_which_interleaver"]
+        return {k: int(c[i]) for i, k in enumerate(names)}
 
     def push_cu8(self, stream: int, samples):
         """samples: uint8 numpy array / bytes (host) — length counts uint8 values, multiple of 4."""
