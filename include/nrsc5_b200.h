@@ -247,7 +247,7 @@ int nrsc5b_fft2048(int device, const float *in, float *out, int nffts);
  * input_push_cs16 (reference src/input.c:119-124) / nrsc5b_push_cs16 take.  Channel k is centred `offsets_100khz[k]` x
  * 100 kHz from the capture's centre.  Integer-exact definition (csrc/channelizer.cu header; restated in numpy by
  * tests/test_channelizer.py):
- *     acc = sum_{u<256} W_k[u] * (x[32 n + u] - (127 + 127j));   v = (acc + 2^13) >> 14;
+ *     acc = sum_{u<256} W_k[u] * (x[32 n + u] - (127 + 127j));   v = (acc + 2^12) >> 13;
  *     y[k][n] = saturate16((v * conj(P[(1600 m_k n) mod 11907]) + 2^14) >> 15)
  * with the 16-bit taps W_k and the phasor table P as returned by nrsc5b_chan_tables.  Runs on the tensor cores
  * (tcgen05.mma.kind::i8, TMA-fed, accumulators in TMEM). */

@@ -138,6 +138,8 @@ struct AmWork {
     uint8_t p1_am[8 * 9000], p3_am[72000];
     int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
     uint8_t out[P3_LEN_MA3 + 8];
+    uint8_t out_p1[P1_LEN + 10];               // P1 bits when P1 and P3 are decoded side by side (a frame's last block)
+    alignas(16) uint8_t dec_p1[(size_t)(P1_LEN + 64) * 32];   // ... and its survivor bits
     short pm[2][256];
     unsigned long long ph_cyc[8];              // SM cycles per phase (thread 0): window + acquisition, first pass, second pass, sync +
                                                // slicing, PIDS, P1 (Viterbi, BER, packing), P3, interleaver
@@ -262,16 +264,14 @@ AM_HD inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 
 
 // ---- shared memory of a stream's CTA (device) ----
 constexpr int VT = 256;                          // trellis steps per tile of survivor decisions
+struct AmVitSlot {                               // one single-warp K=9 decoder (viterbi_k9_warp)
+    alignas(16) uint32_t pmw[2][128];            // path metrics, int16 x 2 per word: word b = old states 2b (low), 2b+1 (high)
+    alignas(16) uint8_t tile[VT][32];            // survivor bits of a step: byte l = new states 4l..4l+3 (bits 0-3), 128+4l.. (bits 4-7)
+    uint32_t q[VT];                              // the tile's soft inputs, three int8 per step in one word
+};
 struct AmSmem {
     union {
-        struct {                                 // viterbi_k9
-            uint32_t pmw[2][128];                // path metrics, int16 x 2 per word: word b = old states 2b (low), 2b+1 (high)
-            uint32_t tile[VT][8];                // survivor bit of new state s at a step: bit s & 31 of word s >> 5
-            int8_t q[3 * VT];                    // the tile's soft inputs
-            int wred[AM_THREADS / 32];
-            int wmax[AM_THREADS / 32], widx[AM_THREADS / 32];
-            unsigned state;
-        } vit;
+        AmVitSlot vit[2];                        // two decodes can run side by side (P1 and P3 at a frame's last block)
         struct {                                 // demod_pass
             float2 ph[2][SYM];                   // NCO phase per sample of a symbol, double-buffered (producer warp runs ahead)
             float2 phase_end[2];                 // the phase after the symbol, renormalised
@@ -295,94 +295,126 @@ __device__ __forceinline__ int am_warp_min(int v)
 }
 #endif
 
-AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out, int len, unsigned g0, unsigned g1, unsigned g2)
+#if defined(__CUDA_ARCH__)
+// One WARP decodes one frame: lane l owns butterflies 4l..4l+3, i.e. reads old states 8l..8l+7 (one 16-byte shared-memory
+// load) and produces new states 4l..4l+3 and 128+4l..128+4l+3 (two 8-byte stores); a step ends with __syncwarp, not a
+// CTA barrier, so several decodes run side by side on the warps of a CTA.  Survivor bits go to a 256-step tile in
+// shared memory that is written to global memory in one sweep; traceback pulls the tiles back, newest first.
+// Semantics as conv_dec.c / conv_gen.h: int16 metrics (they cannot overflow: branch metrics are at most 3 in magnitude
+// and the minimum is subtracted every 77 steps), odd predecessor survives unless the even one is strictly better,
+// first maximum at the end, 32 steps of pre- and post-roll.
+__device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint8_t *dec, int lane, const int8_t *in, uint8_t *out, int len, unsigned g0,
+                                       unsigned g1, unsigned g2)
 {
     const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
-#if defined(__CUDA_ARCH__)
-    // One butterfly per thread: thread b reads old states 2b, 2b+1 (one shared-memory word) and produces new states b
-    // and b + 128.  Decisions: 1 = the odd predecessor survived (it does unless the even one is strictly better).
-    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
-    const int b = L.lane, warp = b >> 5;
-    const unsigned reg = (unsigned)b << 1;
-    const int s0 = parity9(reg & g0) ? 1 : -1, s1 = parity9(reg & g1) ? 1 : -1, s2 = parity9(reg & g2) ? 1 : -1;
-    uint32_t *decw = reinterpret_cast<uint32_t *>(w.dec);                   // [step][8]
-    sm.vit.pmw[0][b] = 0;
+    int sg[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const unsigned reg = (unsigned)(4 * lane + q) << 1;
+        sg[q][0] = parity9(reg & g0) ? 1 : -1;
+        sg[q][1] = parity9(reg & g1) ? 1 : -1;
+        sg[q][2] = parity9(reg & g2) ? 1 : -1;
+    }
+    uint4 *dec16 = reinterpret_cast<uint4 *>(dec);                          // [step][2] x 16 bytes
+    for (int i = lane; i < 128; i += 32) sm.pmw[0][i] = 0;
+    __syncwarp();
     int cur = 0;
     for (int base = 0; base < steps; base += VT) {
         const int nst = min(VT, steps - base);
-        for (int i = b; i < 3 * nst; i += AM_THREADS) {
-            const int st_i = base + i / 3;
-            int j = len - 32 + st_i;                                        // the input index wraps (tail biting)
+        for (int k = lane; k < nst; k += 32) {
+            int j = len - 32 + base + k;                                    // the input index wraps (tail biting)
             while (j >= len) j -= len;
-            sm.vit.q[i] = in[3 * j + (i - 3 * (i / 3))];
+            sm.q[k] = (uint32_t)(uint8_t)in[3 * j] | ((uint32_t)(uint8_t)in[3 * j + 1] << 8) | ((uint32_t)(uint8_t)in[3 * j + 2] << 16);
         }
-        __syncthreads();
+        __syncwarp();
+#pragma unroll 1
         for (int k = 0; k < nst; k++) {
-            const int m = (int)sm.vit.q[3 * k] * s0 + (int)sm.vit.q[3 * k + 1] * s1 + (int)sm.vit.q[3 * k + 2] * s2;
-            const uint32_t pw = sm.vit.pmw[cur][b];
-            const int p0 = (short)(pw & 0xffffu), p1 = (short)(pw >> 16);
-            const int a0 = sat16(p0 + m), a1 = sat16(p1 - m), c0 = sat16(p0 - m), c1 = sat16(p1 + m);
-            const int d0 = !(a0 > a1), d1 = !(c0 > c1);
-            int n0 = d0 ? a1 : a0, n1 = d1 ? c1 : c0;
-            short *nxt = reinterpret_cast<short *>(sm.vit.pmw[cur ^ 1]);
-            const unsigned w0 = __ballot_sync(0xffffffffu, d0), w1 = __ballot_sync(0xffffffffu, d1);
-            if ((b & 31) == 0) {
-                sm.vit.tile[k][warp] = w0;
-                sm.vit.tile[k][4 + warp] = w1;
+            const uint32_t qq = sm.q[k];
+            const int q0 = (int8_t)(qq & 0xff), q1 = (int8_t)((qq >> 8) & 0xff), q2 = (int8_t)((qq >> 16) & 0xff);
+            const uint4 pw = *reinterpret_cast<const uint4 *>(&sm.pmw[cur][4 * lane]);
+            const uint32_t pws[4] = { pw.x, pw.y, pw.z, pw.w };
+            int n0[4], n1[4];
+            unsigned d = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int m = q0 * sg[q][0] + q1 * sg[q][1] + q2 * sg[q][2];
+                const int p0 = (short)(pws[q] & 0xffffu), p1 = (short)(pws[q] >> 16);
+                const int a0 = p0 + m, a1 = p1 - m, c0 = p0 - m, c1 = p1 + m;
+                if (a0 > a1) n0[q] = a0;
+                else { n0[q] = a1; d |= 1u << q; }
+                if (c0 > c1) n1[q] = c0;
+                else { n1[q] = c1; d |= 16u << q; }
             }
             if ((base + k) % interval == 0) {                               // subtract the minimum (conv_dec.c:417-421)
-                const int wm = am_warp_min(min(n0, n1));
-                if ((b & 31) == 0) sm.vit.wred[warp] = wm;
-                __syncthreads();
-                const int mn = min(min(sm.vit.wred[0], sm.vit.wred[1]), min(sm.vit.wred[2], sm.vit.wred[3]));
-                n0 = sat16(n0 - mn);
-                n1 = sat16(n1 - mn);
+                int mn = min(min(min(n0[0], n0[1]), min(n0[2], n0[3])), min(min(n1[0], n1[1]), min(n1[2], n1[3])));
+                mn = am_warp_min(mn);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { n0[q] -= mn; n1[q] -= mn; }
             }
-            nxt[b] = (short)n0;
-            nxt[b + 128] = (short)n1;
-            __syncthreads();
+            short *nxt = reinterpret_cast<short *>(sm.pmw[cur ^ 1]);
+            *reinterpret_cast<uint2 *>(nxt + 4 * lane) =
+                make_uint2((uint32_t)(uint16_t)n0[0] | ((uint32_t)(uint16_t)n0[1] << 16), (uint32_t)(uint16_t)n0[2] | ((uint32_t)(uint16_t)n0[3] << 16));
+            *reinterpret_cast<uint2 *>(nxt + 128 + 4 * lane) =
+                make_uint2((uint32_t)(uint16_t)n1[0] | ((uint32_t)(uint16_t)n1[1] << 16), (uint32_t)(uint16_t)n1[2] | ((uint32_t)(uint16_t)n1[3] << 16));
+            sm.tile[k][lane] = (uint8_t)d;
+            __syncwarp();
             cur ^= 1;
         }
         // the tile's decisions: one coalesced sweep to global memory
-        for (int i = b; i < nst * 8; i += AM_THREADS) decw[(size_t)base * 8 + i] = (&sm.vit.tile[0][0])[i];
-        __syncthreads();
+        for (int i = lane; i < nst * 2; i += 32) dec16[(size_t)base * 2 + i] = reinterpret_cast<const uint4 *>(&sm.tile[0][0])[i];
+        __syncwarp();
     }
     // first maximum in state order (conv_dec.c:310-317)
+    unsigned state;
     {
-        const short *pmv = reinterpret_cast<const short *>(sm.vit.pmw[cur]);
-        int v = pmv[2 * b], idx = 2 * b;
-        if (pmv[2 * b + 1] > v) { v = pmv[2 * b + 1]; idx = 2 * b + 1; }
+        const short *pmv = reinterpret_cast<const short *>(sm.pmw[cur]);
+        int v = pmv[8 * lane], idx = 8 * lane;
+#pragma unroll
+        for (int q = 1; q < 8; q++)
+            if (pmv[8 * lane + q] > v) { v = pmv[8 * lane + q]; idx = 8 * lane + q; }
         for (int o = 16; o; o >>= 1) {
             const int ov = __shfl_xor_sync(0xffffffffu, v, o), oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
-        if ((b & 31) == 0) { sm.vit.wmax[warp] = v; sm.vit.widx[warp] = idx; }
-        __syncthreads();
-        if (b == 0) {
-            int bv = sm.vit.wmax[0], bi = sm.vit.widx[0];
-            for (int q = 1; q < AM_THREADS / 32; q++)
-                if (sm.vit.wmax[q] > bv || (sm.vit.wmax[q] == bv && sm.vit.widx[q] < bi)) { bv = sm.vit.wmax[q]; bi = sm.vit.widx[q]; }
-            sm.vit.state = (unsigned)bi;
-        }
-        __syncthreads();
+        state = (unsigned)idx;
     }
-    // traceback, newest tile first: the CTA pulls a tile into shared memory, one thread walks it
+    // traceback, newest tile first: the warp pulls a tile into shared memory, lane 0 walks it
     for (int base = ((steps - 1) / VT) * VT; base >= 0; base -= VT) {
         const int nst = min(VT, steps - base);
-        for (int i = b; i < nst * 8; i += AM_THREADS) (&sm.vit.tile[0][0])[i] = decw[(size_t)base * 8 + i];
-        __syncthreads();
-        if (b == 0) {
-            unsigned state = sm.vit.state;
+        for (int i = lane; i < nst * 2; i += 32) reinterpret_cast<uint4 *>(&sm.tile[0][0])[i] = dec16[(size_t)base * 2 + i];
+        __syncwarp();
+        if (lane == 0) {
             for (int k = nst - 1; k >= 0; k--) {
                 const int st_i = base + k;
-                const unsigned bit = (sm.vit.tile[k][state >> 5] >> (state & 31u)) & 1u;
+                const unsigned byte = sm.tile[k][(state & 127u) >> 2];
+                const unsigned bit = (byte >> ((state & 3u) + (state >= 128u ? 4u : 0u))) & 1u;
                 if (st_i >= 32 && st_i < 32 + len) out[st_i - 32] = (uint8_t)((state >> 7) & 1u);
                 state = ((state << 1) & 254u) | bit;
             }
-            sm.vit.state = state;
         }
-        __syncthreads();
+        state = __shfl_sync(0xffffffffu, state, 0);
     }
+}
+#endif
+
+// Up to two independent decodes at once (device: one warp each; `dec` = AmWork::dec, split between them).
+struct VitJob {
+    const int8_t *in;
+    uint8_t *out;
+    int len;
+    unsigned g0, g1, g2;
+};
+
+AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out, int len, unsigned g0, unsigned g1, unsigned g2)
+{
+    const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
+#if defined(__CUDA_ARCH__)
+    (void)steps;
+    (void)interval;
+    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    __syncthreads();
+    if ((L.lane >> 5) == 0) viterbi_k9_warp(sm.vit[0], w.dec, L.lane & 31, in, out, len, g0, g1, g2);
+    __syncthreads();
 #else
     for (int i = L.lane; i < 256; i += L.n) w.pm[0][i] = 0;
     AM_SYNC();
@@ -431,6 +463,22 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
         state = ((state << 1) & 254u) | bit;
     }
     AM_SYNC();
+#endif
+}
+
+// P1 and P3 of a frame's last block, decoded at the same time (device: warp 0 and warp 1; host: one after the other)
+AM_HD inline void viterbi_k9_pair(AmWork &w, Lanes L, const VitJob &a, const VitJob &b)
+{
+#if defined(__CUDA_ARCH__)
+    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    __syncthreads();
+    const int warp = L.lane >> 5;
+    if (warp == 0) viterbi_k9_warp(sm.vit[0], w.dec_p1, L.lane & 31, a.in, a.out, a.len, a.g0, a.g1, a.g2);
+    else if (warp == 1) viterbi_k9_warp(sm.vit[1], w.dec, L.lane & 31, b.in, b.out, b.len, b.g0, b.g1, b.g2);
+    __syncthreads();
+#else
+    viterbi_k9(w, L, a.in, a.out, a.len, a.g0, a.g1, a.g2);
+    viterbi_k9(w, L, b.in, b.out, b.len, b.g0, b.g1, b.g2);
 #endif
 }
 
@@ -638,28 +686,36 @@ AM_HD inline void process_p1_p3(AmState &st, AmWork &w, const AmTables &tb, cons
     if (bc == 0) st.am_errors = 0;
     if (st.am_diversity_wait == 0) {
         const int8_t *v = w.vit_p1 + bc * P1_LEN * 3;
-        viterbi_k9(w, L, v, w.out, P1_LEN, 0561, 0657, 0711);
-        st.am_errors += bit_errors(L, v, w.out, P1_LEN, 0561, 0657, 0711, punct_e1, 15);
+        // the frame's last block also decodes P3 (unless the station sends none): both at once, P1 into its own buffer
+        const bool with_p3 = bc == 7 && !st.rdbi;
+        const bool ma3 = st.psmi == MODE_MA3;
+        uint8_t *p1_out = with_p3 ? w.out_p1 : w.out;
+        if (with_p3) {
+            const VitJob ja = { v, w.out_p1, P1_LEN, 0561, 0657, 0711 };
+            const VitJob jb = { w.vit_p3, w.out, ma3 ? P3_LEN_MA3 : P3_LEN, 0561, ma3 ? 0657u : 0753u, 0711 };
+            viterbi_k9_pair(w, L, ja, jb);
+        } else {
+            viterbi_k9(w, L, v, w.out, P1_LEN, 0561, 0657, 0711);
+        }
+        st.am_errors += bit_errors(L, v, p1_out, P1_LEN, 0561, 0657, 0711, punct_e1, 15);
         AM_SYNC();
-        descramble(tb, L, w.out, P1_LEN);
-        emit_frame(st, w, io, L, w.out, P1_LEN, 0);
-        if (p1_sync_lost(w.out, fix_header)) set_state(st, io, L, ST_NONE);              // inside frame_push, frame.c:538
+        descramble(tb, L, p1_out, P1_LEN);
+        emit_frame(st, w, io, L, p1_out, P1_LEN, 0);
+        if (p1_sync_lost(p1_out, fix_header)) set_state(st, io, L, ST_NONE);             // inside frame_push, frame.c:538
         AM_SYNC();
         long long tl3 = AM_T0();
         (void)tl3;
         if (bc == 7) {
             unsigned total = 8 * 9000;
             if (!st.rdbi) {
-                if (st.psmi != MODE_MA3) {
+                if (!ma3) {
                     total += 36000;
-                    viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711);
                     st.am_errors += bit_errors(L, w.vit_p3, w.out, P3_LEN, 0561, 0753, 0711, punct_e2, 6);
                     AM_SYNC();
                     descramble(tb, L, w.out, P3_LEN);
                     emit_frame(st, w, io, L, w.out, P3_LEN, 1);
                 } else {                                                                  // decode.c:533-539
                     total += 72000;
-                    viterbi_k9(w, L, w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711);
                     st.am_errors += bit_errors(L, w.vit_p3, w.out, P3_LEN_MA3, 0561, 0657, 0711, punct_e1, 15);
                     AM_SYNC();
                     descramble(tb, L, w.out, P3_LEN_MA3);
@@ -957,7 +1013,8 @@ __device__ inline void demod_pass(AmWork &w, const AmTables &tb, Lanes L, int sa
         if (t < 32) {
             if (i < BLK) {
                 float2 *out = sm.dem.ph[i & 1];
-                for (int j = 0; j < SYM; ++j) {
+#pragma unroll 10
+                for (int j = 0; j < SYM; ++j) {               // (unrolled: the stores and the loop leave the dependent chain alone)
                     if (t == 0) out[j] = ph;
                     ph = cmul(ph, inc);
                 }
@@ -1089,7 +1146,22 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
         set_state(st, io, L, ST_COARSE);
     }
     AM_SYNC();
+#if defined(__CUDA_ARCH__)
+    {   // acquire.c:160-161; one 4-byte load per sample (I and Q together), four in flight per thread
+        const int *iqw = reinterpret_cast<const int *>(io.iq) + start;
+        int i = L.lane;
+        for (; i + 3 * L.n < NACQ; i += 4 * L.n) {
+            const int v0 = __ldcg(iqw + i), v1 = __ldcg(iqw + i + L.n), v2 = __ldcg(iqw + i + 2 * L.n), v3 = __ldcg(iqw + i + 3 * L.n);
+            w.buf[i] = make_float2((float)(short)(v0 & 0xffff) / 32767.0f, (float)(short)(v0 >> 16) / 32767.0f);
+            w.buf[i + L.n] = make_float2((float)(short)(v1 & 0xffff) / 32767.0f, (float)(short)(v1 >> 16) / 32767.0f);
+            w.buf[i + 2 * L.n] = make_float2((float)(short)(v2 & 0xffff) / 32767.0f, (float)(short)(v2 >> 16) / 32767.0f);
+            w.buf[i + 3 * L.n] = make_float2((float)(short)(v3 & 0xffff) / 32767.0f, (float)(short)(v3 >> 16) / 32767.0f);
+        }
+        for (; i < NACQ; i += L.n) w.buf[i] = input_at(io, start + i);
+    }
+#else
     for (int i = L.lane; i < NACQ; i += L.n) w.buf[i] = input_at(io, start + i);          // acquire.c:160-161
+#endif
     AM_SYNC();
 
     AM_LAP(w, L, 0, tlap);

@@ -6,8 +6,8 @@
 // It is the one dense contraction of the whole system, and the one kernel here that runs on the 5th-generation tensor
 // cores:  for channel k and output sample n
 //
-//     acc[k][n] = sum_{u < 256} W_k[u] * (x[32 n + u] - (127 + 127j))        W_k[u] = round(2^20 h[255-u] e^{-j 2 pi 50 m_k u / 11907})
-//     y[k][n]   = sat16( ((acc + 2^13) >> 14) * conj(P[(1600 m_k n) mod 11907]) + 2^14 >> 15 )
+//     acc[k][n] = sum_{u < 256} W_k[u] * (x[32 n + u] - (127 + 127j))        W_k[u] = round(2^19 h[255-u] e^{-j 2 pi 50 m_k u / 11907})
+//     y[k][n]   = sat16( ((acc + 2^12) >> 13) * conj(P[(1600 m_k n) mod 11907]) + 2^14 >> 15 )
 //
 // (m_k = the channel's offset from the capture centre in units of 100 kHz; 100 kHz / 23.814 MHz = 50 / 11907, so
 // every phasor comes from ONE table P[i] = round(32767 e^{+j 2 pi i / 11907}); all arithmetic is integer, the rounding
@@ -43,7 +43,8 @@ constexpr int CHUNK = 64, NCHUNK = KBYTES / CHUNK;               // K chunks of 
 constexpr int TILE_M = 128;                                       // output samples per tile
 constexpr int GROUP = 32, TILE_N = 4 * GROUP;                    // channels per CTA, rows of B
 constexpr int PERIOD = 11907;                                     // phasor table length (100 kHz / 23.814 MHz = 50 / 11907)
-constexpr int SHIFT1 = 14, TAP_SCALE_LOG2 = 20;                   // unit DC gain -> 64 LSB per input LSB (the cu8 -> Q15 convention)
+constexpr int SHIFT1 = 13, TAP_SCALE_LOG2 = 19;                   // unit DC gain -> 64 LSB per input LSB (the cu8 -> Q15 convention);
+                                                                  // taps stay below 127 * 256 + 127: both bytes of the split are int8
 constexpr int THREADS = 192;
 constexpr uint32_t A_STAGE_BYTES = NCHUNK * TILE_M * CHUNK;      // 65536
 constexpr uint32_t W_BYTES = NCHUNK * TILE_N * CHUNK;            // 65536
@@ -314,7 +315,7 @@ static void make_tables(const int *offsets, int nch, std::vector<short2> &phasor
         long long swr = 0, swi = 0;
         const int g = k / GROUP, cl = k % GROUP;
         for (int u = 0; u < TAPS; u++) {
-            // W_k[u] = 2^20 h[255-u] e^{-j 2 pi 50 m u / 11907}, from the integer phasor table
+            // W_k[u] = 2^19 h[255-u] e^{-j 2 pi 50 m u / 11907}, from the integer phasor table
             const short2 ph = phasor[(size_t)((step * u) % PERIOD)];
             const double g0 = ldexp(h[TAPS - 1 - u], TAP_SCALE_LOG2) / 32767.0;
             const int wr = (int)lrint(g0 * ph.x), wi = (int)lrint(-g0 * ph.y);
@@ -329,6 +330,7 @@ static void make_tables(const int *offsets, int nch, std::vector<short2> &phasor
                 for (int comp = 0; comp < 2; comp++) {
                     const int v = vals[part][comp];
                     const int hi = (v + 128) >> 8, lo = v - 256 * hi;           // v = 256 hi + lo, both in [-128, 127]
+                    if (hi < -128 || hi > 127) { fprintf(stderr, "nrsc5_b200: channeliser tap out of range\n"); abort(); }
                     const int kappa = 2 * u + comp, ck = kappa / CHUNK, b = kappa % CHUNK;
                     const size_t base = ((size_t)(g * NCHUNK + ck) * TILE_N) * CHUNK;
                     (*w)[base + (size_t)(4 * cl + part) * CHUNK + b] = (int8_t)hi;

@@ -25,8 +25,8 @@ def channelize(cu8: np.ndarray, offsets, taps: np.ndarray, phasor: np.ndarray) -
         wi = taps[k, :, 1].astype(np.int64)
         ar = XR @ wr - XI @ wi
         ai = XI @ wr + XR @ wi
-        vr = (ar + (1 << 13)) >> 14
-        vi = (ai + (1 << 13)) >> 14
+        vr = (ar + (1 << 12)) >> 13
+        vi = (ai + (1 << 12)) >> 13
         step = (1600 * int(m)) % PERIOD
         q = (step * (n % PERIOD)) % PERIOD
         pr = phasor[q, 0].astype(np.int64)
