@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--am-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-mp3", action="store_true", help="skip the MP3 leg (BASELINE config 3)")
     ap.add_argument("--mp3-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-chan", action="store_true", help="skip the channeliser leg (SURVEY 8 f3)")
+    ap.add_argument("--chan-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-dropin", action="store_true", help="skip the single-stream drop-in leg (BASELINE configs 1, 2)")
     ap.add_argument("--dropin-leg", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--mp3-streams", type=int, default=64)
@@ -335,7 +337,7 @@ def dropin_leg(args):
         print(json.dumps({"error": "drop-in not built (needs the reference tree at build time)"}))
         return
     out = {"what": "nrsc5_open_pipe -> nrsc5_pipe_samples_cu8 in 32768-byte pushes -> nrsc5_stop -> nrsc5_close on one stream; "
-                   "wall clock of the push loop + stop + close, best of 3 after one warm-up pass, input in memory",
+                   "wall clock of the push loop + stop + close, best of 8 after one warm-up pass, input in memory",
            "driver": "nrsc5_b200/dropin/bench_pipe.c (the reference CLI's push loop around a dlopen'ed library)"}
     with tempfile.TemporaryDirectory() as td:
         cases = {}
@@ -355,7 +357,7 @@ def dropin_leg(args):
             for which, lib in (("dropin_b200", dropin), ("reference_cpu_1core", ref)):
                 if not os.path.exists(lib):
                     continue
-                r = subprocess.run([exe, lib, path, "--reps", "3"], capture_output=True, text=True, timeout=600)
+                r = subprocess.run([exe, lib, path, "--reps", "8"], capture_output=True, text=True, timeout=600)
                 if r.returncode != 0:
                     res[which] = {"error": (r.stderr or r.stdout)[-300:]}
                     continue
@@ -368,6 +370,70 @@ def dropin_leg(args):
                 res["speedup_vs_reference_1core"] = a["x_realtime"] and b["x_realtime"] and a["x_realtime"] / b["x_realtime"]
             out[name] = res
     print(json.dumps(out), flush=True)
+
+
+def chan_leg(args):
+    """SURVEY 8 f3: the wideband channeliser (csrc/channelizer.cu, tcgen05.mma.kind::i8).  One cu8 capture at 23.814 MS/s
+    resident in HBM -> 100 FM channels (the whole 88-108 MHz raster) at 744 187.5 S/s cs16, device to device.  Gate: a
+    slice of the output equals the numpy restatement bit for bit.  Prints one JSON object."""
+    import torch
+    from nrsc5_b200 import channelizer as ch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chan_oracle
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    offs = list(range(-99, 100, 2))                             # 100 channels, 200 kHz apart
+    nbytes = 1 << 27                                            # 67.1 M complex samples = 2.82 s of signal, larger than L2
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    cap = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev, generator=g)
+    nout = ch.outputs(nbytes)
+    stride = 2 * nout
+    out = torch.zeros((len(offs), stride), dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream()
+    with ch.Channelizer(offs) as c:
+        taps, ph = c.tables()
+        run = lambda: c.run_device(cap.data_ptr(), nbytes, out.data_ptr(), stride, stream.cuda_stream)   # noqa: E731
+        run()
+        torch.cuda.synchronize()
+        part = cap[: 64 * 1500].cpu().numpy()
+        want = chan_oracle.channelize(part, offs, taps, ph)
+        got = out[:, : want.shape[1]].cpu().numpy()
+        assert np.array_equal(got, want), "channeliser output differs from the numpy restatement"
+        tail = out[:, 2 * (nout - 64): 2 * nout].cpu().numpy()                   # the end of the capture as well
+        want_t = chan_oracle.channelize(cap[nbytes - 64 * (64 + 7):].cpu().numpy(), offs, taps, ph)
+        assert np.array_equal(tail, want_t), "channeliser output differs from the numpy restatement at the end of the capture"
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        steps = max(5, min(args.steps, 20))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            run()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+    samples = nbytes // 2
+    groups = (len(offs) + 31) // 32
+    macs = nout * groups * 128 * 512                           # int8 multiply-accumulates issued (rows of B incl. padding channels)
+    useful = nout * len(offs) * 4 * 512
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    bf16 = float(peaks.get("bf16_tflops", 1660.8))
+    peak_i8 = 2 * bf16                                          # int8 runs at twice the bf16 rate; no int8 GEMM measurement in MEASURED_PEAKS.json
+    hbm, hbm_src = measured_peak()
+    traffic = nbytes + len(offs) * nout * 4
+    out_j = {"value": samples / (ms * 1e-3) / 1e6, "unit": "Msamples/s (wideband cu8 complex, 23.814 MS/s)", "ms_per_step": ms,
+             "x_realtime": samples / (ms * 1e-3) / 23814000.0, "channels": len(offs), "outputs_per_channel": int(nout), "steps": steps,
+             "channel_msamples_per_s": len(offs) * nout / (ms * 1e-3) / 1e6,
+             "roofline": {"bound": "tensor", "kernel": "k_channelize (tcgen05.mma.kind::i8, M128 N128 K512 per tile)",
+                          "achieved": 2 * macs / (ms * 1e-3) / 1e12, "useful": 2 * useful / (ms * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s",
+                          "frac": 2 * macs / (ms * 1e-3) / 1e12 / peak_i8,
+                          "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 tensor rate; no int8 measurement in that file)",
+                          "hbm_gbs": traffic / (ms * 1e-3) / 1e9, "hbm_frac": traffic / (ms * 1e-3) / 1e9 / hbm, "traffic": None},
+             "parity_gate": {"ok": True, "what": "first 1493 and last 64 output samples of all 100 channels == oracle/chan_oracle.py"},
+             "workload": "one 2^27-byte cu8 capture (uniform random bytes) resident in HBM -> 100 channels x %d cs16 samples, device to device" % nout}
+    print(json.dumps(out_j), flush=True)
 
 
 def stream_views(caps, nstreams: int, rank: int):
@@ -601,6 +667,9 @@ def main():
     if args.dropin_leg:
         dropin_leg(args)
         return
+    if args.chan_leg:
+        chan_leg(args)
+        return
 
     import torch
     import torch.distributed as dist
@@ -746,7 +815,9 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture, scaled to this run's
     # average launch (bytes per stream-block x stream-blocks per launch)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if dom == "front" and os.path.exists(tp):
         tj = json.load(open(tp))
         per_block = (tj["k_stream"]["dram_read_bytes"] + tj["k_stream"]["dram_write_bytes"]) / tj["k_stream"]["stream_blocks"]
@@ -848,6 +919,17 @@ def main():
         except Exception as ex:                                    # noqa: BLE001
             dropin = {"error": repr(ex)[:400]}
 
+    # ---- the wideband channeliser, SURVEY 8 f3 (separate process, rank 0, N=1 only) ----
+    chan = None
+    if rank == 0 and world == 1 and not args.no_chan:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--chan-leg", "--steps", str(args.steps)],
+                               capture_output=True, text=True, timeout=420)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            chan = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as ex:                                    # noqa: BLE001
+            chan = {"error": repr(ex)[:400]}
+
     if rank == 0:
         line = {
             "metric": "cu8 I/Q Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -868,6 +950,8 @@ def main():
             line["mp3_config3"] = mp3
         if dropin:
             line["single_stream_dropin"] = dropin
+        if chan:
+            line["channeliser_f3"] = chan
         print(json.dumps(line), flush=True)
     e.close()
     if use_dist:

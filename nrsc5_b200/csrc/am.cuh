@@ -264,14 +264,17 @@ AM_HD inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 
 
 // ---- shared memory of a stream's CTA (device) ----
 constexpr int VT = 256;                          // trellis steps per tile of survivor decisions
-struct AmVitSlot {                               // one single-warp K=9 decoder (viterbi_k9_warp)
-    alignas(16) uint32_t pmw[2][128];            // path metrics, int16 x 2 per word: word b = old states 2b (low), 2b+1 (high)
-    alignas(16) uint8_t tile[VT][32];            // survivor bits of a step: byte l = new states 4l..4l+3 (bits 0-3), 128+4l.. (bits 4-7)
-    uint32_t q[VT];                              // the tile's soft inputs, three int8 per step in one word
+struct AmVitSlot {                               // one K=9 decoder (viterbi_k9_cta): a butterfly per thread
+    uint32_t pmw[2][128];                        // path metrics, int16 x 2 per word: word b = old states 2b (low), 2b+1 (high)
+    uint32_t tile[VT][8];                        // survivor bit of new state s at a step: bit s & 31 of word s >> 5
+    int8_t q[3 * VT];                            // the tile's soft inputs
+    int wred[AM_THREADS / 32];
+    int wmax[AM_THREADS / 32], widx[AM_THREADS / 32];
+    unsigned state;
 };
 struct AmSmem {
     union {
-        AmVitSlot vit[2];                        // two decodes can run side by side (P1 and P3 at a frame's last block)
+        AmVitSlot vit;
         struct {                                 // demod_pass
             float2 ph[2][SYM];                   // NCO phase per sample of a symbol, double-buffered (producer warp runs ahead)
             float2 phase_end[2];                 // the phase after the symbol, renormalised
@@ -296,108 +299,102 @@ __device__ __forceinline__ int am_warp_min(int v)
 #endif
 
 #if defined(__CUDA_ARCH__)
-// One WARP decodes one frame: lane l owns butterflies 4l..4l+3, i.e. reads old states 8l..8l+7 (one 16-byte shared-memory
-// load) and produces new states 4l..4l+3 and 128+4l..128+4l+3 (two 8-byte stores); a step ends with __syncwarp, not a
-// CTA barrier, so several decodes run side by side on the warps of a CTA.  Survivor bits go to a 256-step tile in
-// shared memory that is written to global memory in one sweep; traceback pulls the tiles back, newest first.
-// Semantics as conv_dec.c / conv_gen.h: int16 metrics (they cannot overflow: branch metrics are at most 3 in magnitude
-// and the minimum is subtracted every 77 steps), odd predecessor survives unless the even one is strictly better,
-// first maximum at the end, 32 steps of pre- and post-roll.
-__device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint8_t *dec, int lane, const int8_t *in, uint8_t *out, int len, unsigned g0,
-                                       unsigned g1, unsigned g2)
+// One butterfly per thread (128 threads): thread b reads old states 2b, 2b+1 (one shared-memory word) and produces new
+// states b and b + 128; the survivor bits of a step are collected by warp ballot into a 256-step tile that goes to global
+// memory in one coalesced sweep; traceback pulls the tiles back, newest first, and one thread walks them in shared
+// memory.  Semantics as conv_dec.c / conv_gen.h: int16 metrics (they cannot overflow: branch metrics are at most 3 in
+// magnitude and the minimum is subtracted every 77 steps), the odd predecessor survives unless the even one is strictly
+// better, first maximum at the end, 32 steps of pre- and post-roll.
+__device__ inline void viterbi_k9_cta(AmVitSlot &sm, uint8_t *dec, int b, const int8_t *in, uint8_t *out, int len, unsigned g0, unsigned g1,
+                                      unsigned g2)
 {
     const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
-    int sg[4][3];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const unsigned reg = (unsigned)(4 * lane + q) << 1;
-        sg[q][0] = parity9(reg & g0) ? 1 : -1;
-        sg[q][1] = parity9(reg & g1) ? 1 : -1;
-        sg[q][2] = parity9(reg & g2) ? 1 : -1;
-    }
-    uint4 *dec16 = reinterpret_cast<uint4 *>(dec);                          // [step][2] x 16 bytes
-    for (int i = lane; i < 128; i += 32) sm.pmw[0][i] = 0;
-    __syncwarp();
+    const int warp = b >> 5;
+    const unsigned reg = (unsigned)b << 1;
+    const int s0 = parity9(reg & g0) ? 1 : -1, s1 = parity9(reg & g1) ? 1 : -1, s2 = parity9(reg & g2) ? 1 : -1;
+    uint32_t *decw = reinterpret_cast<uint32_t *>(dec);                     // [step][8]
+    sm.pmw[0][b] = 0;
     int cur = 0;
     for (int base = 0; base < steps; base += VT) {
         const int nst = min(VT, steps - base);
-        for (int k = lane; k < nst; k += 32) {
-            int j = len - 32 + base + k;                                    // the input index wraps (tail biting)
+        for (int i = b; i < 3 * nst; i += AM_THREADS) {
+            const int st_i = base + i / 3;
+            int j = len - 32 + st_i;                                        // the input index wraps (tail biting)
             while (j >= len) j -= len;
-            sm.q[k] = (uint32_t)(uint8_t)in[3 * j] | ((uint32_t)(uint8_t)in[3 * j + 1] << 8) | ((uint32_t)(uint8_t)in[3 * j + 2] << 16);
+            sm.q[i] = in[3 * j + (i - 3 * (i / 3))];
         }
-        __syncwarp();
+        __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < nst; k++) {
-            const uint32_t qq = sm.q[k];
-            const int q0 = (int8_t)(qq & 0xff), q1 = (int8_t)((qq >> 8) & 0xff), q2 = (int8_t)((qq >> 16) & 0xff);
-            const uint4 pw = *reinterpret_cast<const uint4 *>(&sm.pmw[cur][4 * lane]);
-            const uint32_t pws[4] = { pw.x, pw.y, pw.z, pw.w };
-            int n0[4], n1[4];
-            unsigned d = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int m = q0 * sg[q][0] + q1 * sg[q][1] + q2 * sg[q][2];
-                const int p0 = (short)(pws[q] & 0xffffu), p1 = (short)(pws[q] >> 16);
-                const int a0 = p0 + m, a1 = p1 - m, c0 = p0 - m, c1 = p1 + m;
-                if (a0 > a1) n0[q] = a0;
-                else { n0[q] = a1; d |= 1u << q; }
-                if (c0 > c1) n1[q] = c0;
-                else { n1[q] = c1; d |= 16u << q; }
+            const int m = (int)sm.q[3 * k] * s0 + (int)sm.q[3 * k + 1] * s1 + (int)sm.q[3 * k + 2] * s2;
+            const uint32_t pw = sm.pmw[cur][b];
+            const int p0 = (short)(pw & 0xffffu), p1 = (short)(pw >> 16);
+            const int a0 = p0 + m, a1 = p1 - m, c0 = p0 - m, c1 = p1 + m;
+            const int d0 = !(a0 > a1), d1 = !(c0 > c1);
+            int n0 = d0 ? a1 : a0, n1 = d1 ? c1 : c0;
+            short *nxt = reinterpret_cast<short *>(sm.pmw[cur ^ 1]);
+            const unsigned w0 = __ballot_sync(0xffffffffu, d0), w1 = __ballot_sync(0xffffffffu, d1);
+            if ((b & 31) == 0) {
+                sm.tile[k][warp] = w0;
+                sm.tile[k][4 + warp] = w1;
             }
             if ((base + k) % interval == 0) {                               // subtract the minimum (conv_dec.c:417-421)
-                int mn = min(min(min(n0[0], n0[1]), min(n0[2], n0[3])), min(min(n1[0], n1[1]), min(n1[2], n1[3])));
-                mn = am_warp_min(mn);
-#pragma unroll
-                for (int q = 0; q < 4; q++) { n0[q] -= mn; n1[q] -= mn; }
+                const int wm = am_warp_min(min(n0, n1));
+                if ((b & 31) == 0) sm.wred[warp] = wm;
+                __syncthreads();
+                const int mn = min(min(sm.wred[0], sm.wred[1]), min(sm.wred[2], sm.wred[3]));
+                n0 -= mn;
+                n1 -= mn;
             }
-            short *nxt = reinterpret_cast<short *>(sm.pmw[cur ^ 1]);
-            *reinterpret_cast<uint2 *>(nxt + 4 * lane) =
-                make_uint2((uint32_t)(uint16_t)n0[0] | ((uint32_t)(uint16_t)n0[1] << 16), (uint32_t)(uint16_t)n0[2] | ((uint32_t)(uint16_t)n0[3] << 16));
-            *reinterpret_cast<uint2 *>(nxt + 128 + 4 * lane) =
-                make_uint2((uint32_t)(uint16_t)n1[0] | ((uint32_t)(uint16_t)n1[1] << 16), (uint32_t)(uint16_t)n1[2] | ((uint32_t)(uint16_t)n1[3] << 16));
-            sm.tile[k][lane] = (uint8_t)d;
-            __syncwarp();
+            nxt[b] = (short)n0;
+            nxt[b + 128] = (short)n1;
+            __syncthreads();
             cur ^= 1;
         }
         // the tile's decisions: one coalesced sweep to global memory
-        for (int i = lane; i < nst * 2; i += 32) dec16[(size_t)base * 2 + i] = reinterpret_cast<const uint4 *>(&sm.tile[0][0])[i];
-        __syncwarp();
+        for (int i = b; i < nst * 8; i += AM_THREADS) decw[(size_t)base * 8 + i] = (&sm.tile[0][0])[i];
+        __syncthreads();
     }
     // first maximum in state order (conv_dec.c:310-317)
-    unsigned state;
     {
         const short *pmv = reinterpret_cast<const short *>(sm.pmw[cur]);
-        int v = pmv[8 * lane], idx = 8 * lane;
-#pragma unroll
-        for (int q = 1; q < 8; q++)
-            if (pmv[8 * lane + q] > v) { v = pmv[8 * lane + q]; idx = 8 * lane + q; }
+        int v = pmv[2 * b], idx = 2 * b;
+        if (pmv[2 * b + 1] > v) { v = pmv[2 * b + 1]; idx = 2 * b + 1; }
         for (int o = 16; o; o >>= 1) {
             const int ov = __shfl_xor_sync(0xffffffffu, v, o), oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
-        state = (unsigned)idx;
+        if ((b & 31) == 0) { sm.wmax[warp] = v; sm.widx[warp] = idx; }
+        __syncthreads();
+        if (b == 0) {
+            int bv = sm.wmax[0], bi = sm.widx[0];
+            for (int q = 1; q < AM_THREADS / 32; q++)
+                if (sm.wmax[q] > bv || (sm.wmax[q] == bv && sm.widx[q] < bi)) { bv = sm.wmax[q]; bi = sm.widx[q]; }
+            sm.state = (unsigned)bi;
+        }
+        __syncthreads();
     }
-    // traceback, newest tile first: the warp pulls a tile into shared memory, lane 0 walks it
+    // traceback, newest tile first: the CTA pulls a tile into shared memory, one thread walks it
     for (int base = ((steps - 1) / VT) * VT; base >= 0; base -= VT) {
         const int nst = min(VT, steps - base);
-        for (int i = lane; i < nst * 2; i += 32) reinterpret_cast<uint4 *>(&sm.tile[0][0])[i] = dec16[(size_t)base * 2 + i];
-        __syncwarp();
-        if (lane == 0) {
+        for (int i = b; i < nst * 8; i += AM_THREADS) (&sm.tile[0][0])[i] = decw[(size_t)base * 8 + i];
+        __syncthreads();
+        if (b == 0) {
+            unsigned state = sm.state;
             for (int k = nst - 1; k >= 0; k--) {
                 const int st_i = base + k;
-                const unsigned byte = sm.tile[k][(state & 127u) >> 2];
-                const unsigned bit = (byte >> ((state & 3u) + (state >= 128u ? 4u : 0u))) & 1u;
+                const unsigned bit = (sm.tile[k][state >> 5] >> (state & 31u)) & 1u;
                 if (st_i >= 32 && st_i < 32 + len) out[st_i - 32] = (uint8_t)((state >> 7) & 1u);
                 state = ((state << 1) & 254u) | bit;
             }
+            sm.state = state;
         }
-        state = __shfl_sync(0xffffffffu, state, 0);
+        __syncthreads();
     }
 }
 #endif
 
-// Up to two independent decodes at once (device: one warp each; `dec` = AmWork::dec, split between them).
+// a decode job
 struct VitJob {
     const int8_t *in;
     uint8_t *out;
@@ -413,8 +410,7 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
     (void)interval;
     AmSmem &sm = *static_cast<AmSmem *>(L.smem);
     __syncthreads();
-    if ((L.lane >> 5) == 0) viterbi_k9_warp(sm.vit[0], w.dec, L.lane & 31, in, out, len, g0, g1, g2);
-    __syncthreads();
+    viterbi_k9_cta(sm.vit, w.dec, L.lane, in, out, len, g0, g1, g2);
 #else
     for (int i = L.lane; i < 256; i += L.n) w.pm[0][i] = 0;
     AM_SYNC();
@@ -466,20 +462,11 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
 #endif
 }
 
-// P1 and P3 of a frame's last block, decoded at the same time (device: warp 0 and warp 1; host: one after the other)
+// P1 and P3 of a frame's last block into separate buffers (one after the other: a decode takes the whole CTA)
 AM_HD inline void viterbi_k9_pair(AmWork &w, Lanes L, const VitJob &a, const VitJob &b)
 {
-#if defined(__CUDA_ARCH__)
-    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
-    __syncthreads();
-    const int warp = L.lane >> 5;
-    if (warp == 0) viterbi_k9_warp(sm.vit[0], w.dec_p1, L.lane & 31, a.in, a.out, a.len, a.g0, a.g1, a.g2);
-    else if (warp == 1) viterbi_k9_warp(sm.vit[1], w.dec, L.lane & 31, b.in, b.out, b.len, b.g0, b.g1, b.g2);
-    __syncthreads();
-#else
     viterbi_k9(w, L, a.in, a.out, a.len, a.g0, a.g1, a.g2);
     viterbi_k9(w, L, b.in, b.out, b.len, b.g0, b.g1, b.g2);
-#endif
 }
 
 AM_HD inline void descramble(const AmTables &tb, Lanes L, uint8_t *bits, int len)     // decode.c:279-294

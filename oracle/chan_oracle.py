@@ -1,4 +1,4 @@
-"""The channeliser's definition restated in numpy (test infrastructure): exact integer arithmetic on the tables the
+"""TEST INFRASTRUCTURE ONLY (tests/, bench.py's gates).  The channeliser's definition restated in numpy: exact integer arithmetic on the tables the
 library publishes (nrsc5b_chan_make_tables).  The reference has no channeliser - there is nothing to pin this to but the
 definition itself (include/nrsc5_b200.h) and the end-to-end check that the stations mixed into a wideband capture decode."""
 import numpy as np
