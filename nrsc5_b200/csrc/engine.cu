@@ -657,6 +657,44 @@ static size_t vitc_emit_smem() { return VITC_EMIT_SMEM; }
         }                                                                                          \
     } while (0)
 
+
+// Page-locked host buffers come from a small process-wide pool: cudaMallocHost / cudaFreeHost cost about a millisecond
+// each, and a handle that is opened and closed per capture (the drop-in: nrsc5_open_pipe ... nrsc5_close) would pay for a
+// dozen of them inside its close.  Buffers go back to the pool when an engine is destroyed and are handed to the next
+// engine that asks for the same size.
+#include <map>
+#include <mutex>
+static std::mutex g_pin_mu;
+static std::multimap<size_t, void *> g_pin_free;
+static std::map<void *, size_t> g_pin_size;
+
+static cudaError_t pinned_alloc(void **out, size_t n)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        auto it = g_pin_free.find(n);
+        if (it != g_pin_free.end()) {
+            *out = it->second;
+            g_pin_free.erase(it);
+            return cudaSuccess;
+        }
+    }
+    const cudaError_t rc = cudaMallocHost(out, n);
+    if (rc == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pin_size[*out] = n;
+    }
+    return rc;
+}
+
+static void pinned_release(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_size.find(p);
+    if (it != g_pin_size.end()) g_pin_free.insert({ it->second, p });
+}
+
 struct nrsc5b_engine {
     nrsc5b_config_t cfg;
     EngineDims dims;
@@ -1060,11 +1098,11 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
 #undef DA
     e->pinned_cap = 8u << 20;
     if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { nrsc5b_destroy(e); return NRSC5B_ECUDA; }
-    if (cudaMallocHost((void **)&e->pinned, e->pinned_cap) != cudaSuccess ||
-        cudaMallocHost((void **)&e->h_state, sizeof(StreamState) * S) != cudaSuccess ||
-        cudaMallocHost((void **)&e->avail_ring, sizeof(long long) * 4096) != cudaSuccess ||
-        cudaMallocHost((void **)&e->h_ctl, sizeof(EngineCtl)) != cudaSuccess ||
-        cudaMallocHost((void **)&e->h_brief, sizeof(StreamBrief) * S) != cudaSuccess ||
+    if (pinned_alloc((void **)&e->pinned, e->pinned_cap) != cudaSuccess ||
+        pinned_alloc((void **)&e->h_state, sizeof(StreamState) * S) != cudaSuccess ||
+        pinned_alloc((void **)&e->avail_ring, sizeof(long long) * 4096) != cudaSuccess ||
+        pinned_alloc((void **)&e->h_ctl, sizeof(EngineCtl)) != cudaSuccess ||
+        pinned_alloc((void **)&e->h_brief, sizeof(StreamBrief) * S) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->batch_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->reset_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->pinned_free, cudaEventDisableTiming) != cudaSuccess) {
@@ -1148,17 +1186,17 @@ extern "C" void nrsc5b_destroy(nrsc5b_engine_t *e)
                 e->tr.polls_ready, e->tr.submits_idle, e->tr.s_submit, e->tr.s_flush, e->tr.s_stage_wait, e->tr.s_trim, e->tr.s_poll_wait,
                 e->dims.cluster);
     for (void *q : e->allocs) cudaFree(q);
-    if (e->pinned) cudaFreeHost(e->pinned);
-    if (e->h_state) cudaFreeHost(e->h_state);
-    if (e->avail_ring) cudaFreeHost(e->avail_ring);
-    if (e->avail_rows) cudaFreeHost(e->avail_rows);
-    if (e->h_ctl) cudaFreeHost(e->h_ctl);
-    if (e->h_brief) cudaFreeHost(e->h_brief);
-    if (e->xlog) cudaFreeHost(e->xlog);
-    if (e->xhdr) cudaFreeHost(e->xhdr);
+    if (e->pinned) pinned_release(e->pinned);
+    if (e->h_state) pinned_release(e->h_state);
+    if (e->avail_ring) pinned_release(e->avail_ring);
+    if (e->avail_rows) pinned_release(e->avail_rows);
+    if (e->h_ctl) pinned_release(e->h_ctl);
+    if (e->h_brief) pinned_release(e->h_brief);
+    if (e->xlog) pinned_release(e->xlog);
+    if (e->xhdr) pinned_release(e->xhdr);
     if (e->batch_done) cudaEventDestroy(e->batch_done);
     for (int i = 0; i < 2; i++) {
-        if (e->stage[i]) cudaFreeHost(e->stage[i]);
+        if (e->stage[i]) pinned_release(e->stage[i]);
         if (e->stage_free[i]) cudaEventDestroy(e->stage_free[i]);
     }
     if (e->reset_done) cudaEventDestroy(e->reset_done);
@@ -1432,7 +1470,7 @@ extern "C" int nrsc5b_push_cu8_all(nrsc5b_engine_t *e, const uint8_t *host, size
     CK(cudaMemcpy2DAsync(e->iq_owned + off, e->dims.in_stride, host, host_stride, nbytes, S, cudaMemcpyHostToDevice,
                          e->copy_stream));
     // publish: one strided copy of the new count into every stream's state, after the samples
-    if (!e->avail_rows && cudaMallocHost((void **)&e->avail_rows, sizeof(long long) * 16 * S) != cudaSuccess) return NRSC5B_ENOMEM;
+    if (!e->avail_rows && pinned_alloc((void **)&e->avail_rows, sizeof(long long) * 16 * S) != cudaSuccess) return NRSC5B_ENOMEM;
     if (e->avail_rows_pos && (e->avail_rows_pos & 15) == 0) CK(cudaStreamSynchronize(e->copy_stream));   // rows recycled
     long long *row = e->avail_rows + (size_t)(e->avail_rows_pos++ & 15) * S;
     for (int s = 0; s < S; s++) row[s] = e->pushed[0] + (long long)(nbytes / 2);
@@ -1916,15 +1954,15 @@ extern "C" int nrsc5b_prepare_async(nrsc5b_engine_t *e)
     if (!e->stage[0]) {
         e->stage_cap = 4u << 20;
         for (int i = 0; i < 2; i++) {
-            if (cudaMallocHost((void **)&e->stage[i], e->stage_cap) != cudaSuccess) return NRSC5B_ENOMEM;
+            if (pinned_alloc((void **)&e->stage[i], e->stage_cap) != cudaSuccess) return NRSC5B_ENOMEM;
             CK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
         }
     }
     if (!e->xlog) {
         const int S = e->dims.nstreams;
         e->xlog_stride = (e->dims.log_cap + 15) & ~(size_t)15;
-        if (cudaMallocHost((void **)&e->xlog, (size_t)S * e->xlog_stride) != cudaSuccess ||
-            cudaMallocHost((void **)&e->xhdr, sizeof(ExportHdr) * S) != cudaSuccess) return NRSC5B_ENOMEM;
+        if (pinned_alloc((void **)&e->xlog, (size_t)S * e->xlog_stride) != cudaSuccess ||
+            pinned_alloc((void **)&e->xhdr, sizeof(ExportHdr) * S) != cudaSuccess) return NRSC5B_ENOMEM;
     }
     return NRSC5B_OK;
 }

@@ -429,13 +429,17 @@ void input_free(input_t *st)
 {
     /* the reference has no flush and decodes inside the pushes; here the tail of the stream may still be on its way:
      * deliver it before the handle goes (nrsc5_close -> input_free, nrsc5.c:429) */
+    const double t0 = st->trace ? seam_now() : 0;
     if (st->engine && st->pipelined)
         pump_all(st);
+    const double t1 = st->trace ? seam_now() : 0;
     if (st->trace)
-        fprintf(stderr, "libnrsc5 (B200) trace: %lu batches delivered, %lu record bytes, %.6f s in the replay (callbacks included)\n",
-                st->trace_batches, st->trace_bytes, st->trace_replay_s);
+        fprintf(stderr, "libnrsc5 (B200) trace: %lu batches delivered, %lu record bytes, %.6f s in the replay (callbacks included), "
+                        "%.6f s in the final flush\n", st->trace_batches, st->trace_bytes, st->trace_replay_s, t1 - t0);
     frame_free(&st->frame);
     nrsc5b_destroy(st->engine);
+    if (st->trace)
+        fprintf(stderr, "libnrsc5 (B200) trace: %.6f s in nrsc5b_destroy\n", seam_now() - t1);
     free(st->records);
     free(st->bits);
 }
