@@ -112,3 +112,16 @@ def test_stations_in_a_wideband_capture_decode_bit_exact():
         ref = port.decode(cs16[s])
         assert p1 == ref.p1_frames
         assert [r["bits"] for t_, r in recs[s] if t_ == eng.REC_PIDS] == ref.pids_frames
+    # the same without leaving the GPU: the channeliser writes a device buffer that the engine reads in place
+    import torch
+    d_cu8 = torch.from_numpy(cu8).cuda()
+    nout = ch.outputs(cu8.size)
+    stride = (2 * nout + 64) & ~31                                       # int16 values between channels
+    d_out = torch.zeros((2, stride), dtype=torch.int16, device="cuda")
+    with ch.Channelizer(offs) as c:
+        c.run_device(d_cu8.data_ptr(), cu8.size, d_out.data_ptr(), stride)
+        torch.cuda.synchronize()
+    with nrsc5_b200.Engine(nstreams=2, input_capacity=4096, log_capacity=4 << 20, input_cs16=True) as e:
+        e.attach_device_input(d_out.data_ptr(), 2 * stride, 4 * nout)
+        e.process()
+        assert [e.drain(s) for s in range(2)] == recs
