@@ -401,7 +401,7 @@ def chan_leg(args):
         got = out[:, : want.shape[1]].cpu().numpy()
         assert np.array_equal(got, want), "channeliser output differs from the numpy restatement"
         tail = out[:, 2 * (nout - 64): 2 * nout].cpu().numpy()                   # the end of the capture as well
-        want_t = chan_oracle.channelize(cap[nbytes - 64 * (64 + 7):].cpu().numpy(), offs, taps, ph)
+        want_t = chan_oracle.channelize(cap[nbytes - 64 * (64 + 7):].cpu().numpy(), offs, taps, ph, n0=nout - 64)
         assert np.array_equal(tail, want_t), "channeliser output differs from the numpy restatement at the end of the capture"
         for _ in range(3):
             run()

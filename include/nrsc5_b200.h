@@ -234,6 +234,12 @@ int nrsc5b_viterbi_k7(int device, const int8_t *in, uint8_t *out, int len, int n
 int nrsc5b_viterbi_k7_ex(int device, const int8_t *in, uint8_t *out, int len, int nframes, int *fallbacks);
 /* batch RS(255,247) decode in place; rc[n] = corrections or -1 (reference src/rs_decode.c:16) */
 int nrsc5b_rs_decode(int device, uint8_t *blocks255, int *rc, int nblocks);
+/* The AM chain's K=9 rate-1/3 tail-biting Viterbi decoder (reference src/conv_dec.c + src/conv_gen.h with K = 9 as
+ * src/decode.c:487,515-539 call it): njobs frames of len bits; in = 3 * len hard symbols per frame (-1, 0 = punctured, +1:
+ * the AM chain slices hard, other values are rejected), out = len bits per frame.  warmup <= 0 selects the production
+ * warm-up of the segmented traceback; rounds (optional, [njobs]) receives the repair rounds the traceback needed. */
+int nrsc5b_viterbi_k9(int device, const int8_t *in, uint8_t *out, int len, int njobs, unsigned g0, unsigned g1, unsigned g2,
+                      int warmup, int *rounds);
 /* L2 alone on one stream: frames = {u32 lc, u32 nbits, packed bits padded to 4 bytes} back to back, nbits == 0 standing
  * for frame_reset (frame.c:716); all six frame lengths of frame.c:651-690.  Writes one REC_L2 record per frame
  * (frame_off = the frame's index in the list) and returns the bytes written, or NRSC5B_EFULL. */

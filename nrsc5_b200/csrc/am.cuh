@@ -14,9 +14,11 @@
 //     path metrics, a tile of survivor decisions - nothing on a dependent path goes to global memory;
 //   * the NCO phase chain (8 640 dependent complex multiplications per pass - sequential by definition) is run by ONE
 //     warp, a symbol ahead of the three warps that window, fold and transform the previous symbol (demod_pass);
-//   * the K=9 add-compare-select gives every thread one butterfly (128 butterflies = the CTA), path metrics packed
-//     two to a shared-memory word, survivor bits collected by warp ballot into 256-step tiles that go to global
-//     memory in one coalesced sweep; traceback pulls the tiles back, newest first (viterbi_k9);
+//   * the K=9 recursion is ONE WARP with the 256 path metrics in its registers, three trellis steps between two metric
+//     exchanges and two butterflies per instruction (radix 8 on packed 16-bit pairs, viterbi_k9_warp) - no CTA barrier
+//     in it; P1 and P3 of a frame's last block run side by side, a warp each.  Traceback is cut into 128 segments
+//     walked concurrently from warmed-up start states and repaired until it equals the sequential one
+//     (viterbi_k9_traceback);
 //   * channel-BER re-encoding and the bit packing of the PDUs are spread over the CTA.
 // Scalar receiver state (AmState) is held redundantly by every thread - each follows the same control flow on the
 // same values - and written back by thread 0.
@@ -139,11 +141,11 @@ struct AmWork {
     int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
     uint8_t out[P3_LEN_MA3 + 8];
     uint8_t out_p1[P1_LEN + 10];               // P1 bits when P1 and P3 are decoded side by side (a frame's last block)
-    alignas(16) uint8_t dec_p1[(size_t)(P1_LEN + 64) * 32];   // ... and its survivor bits
+    alignas(16) uint8_t dec_p1[(size_t)((P1_LEN + 64 + 2) / 3) * 128];   // ... and its survivor bits
     short pm[2][256];
     unsigned long long ph_cyc[8];              // SM cycles per phase (thread 0): window + acquisition, first pass, second pass, sync +
                                                // slicing, PIDS, P1 (Viterbi, BER, packing), P3, interleaver
-    alignas(16) uint8_t dec[(size_t)VIT_MAX_STEPS * 32];   // survivor bits, 256 per trellis step (eight 32-bit words), see viterbi_k9
+    alignas(16) uint8_t dec[(size_t)VIT_MAX_STEPS * 48];   // survivor bits: host 32 bytes per trellis step, device 128 per three steps (viterbi_k9)
     float2 mult[4][PW];
     uint8_t sym_pl[BLK * PW], sym_pu[BLK * PW], sym_s[BLK * PW], sym_t[BLK * PW], sym_pids[2 * BLK];
 };
@@ -263,18 +265,18 @@ AM_HD inline int parity9(unsigned v)
 AM_HD inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
 
 // ---- shared memory of a stream's CTA (device) ----
-constexpr int VT = 256;                          // trellis steps per tile of survivor decisions
-struct AmVitSlot {                               // one K=9 decoder (viterbi_k9_cta): a butterfly per thread
-    uint32_t pmw[2][128];                        // path metrics, int16 x 2 per word: word b = old states 2b (low), 2b+1 (high)
-    uint32_t tile[VT][8];                        // survivor bit of new state s at a step: bit s & 31 of word s >> 5
-    int8_t q[3 * VT];                            // the tile's soft inputs
-    int wred[AM_THREADS / 32];
-    int wmax[AM_THREADS / 32], widx[AM_THREADS / 32];
-    unsigned state;
+constexpr int VT = 192;                          // trellis steps per tile of staged inputs (a multiple of three)
+constexpr int VIT_WARMUP = 128;                  // traceback walkers start this many steps late, from any state
+struct AmVitSlot {                               // one K=9 decoder: the recursion by ONE warp (viterbi_k9_warp)
+    alignas(16) unsigned short pm[256];          // path metrics between two groups of three steps (slot order, see below)
+    alignas(16) uint32_t qd[VT][4];              // the tile's soft inputs, (q + 1) in both halves of a word
+    unsigned short ends[AM_THREADS];             // traceback: the state each walker arrived at
+    unsigned state;                              // state after the last step (first maximum)
+    int changed;
 };
 struct AmSmem {
     union {
-        AmVitSlot vit;
+        AmVitSlot vit[2];                        // two decoders side by side (P1 and P3 of a frame's last block)
         struct {                                 // demod_pass
             float2 ph[2][SYM];                   // NCO phase per sample of a symbol, double-buffered (producer warp runs ahead)
             float2 phase_end[2];                 // the phase after the symbol, renormalised
@@ -296,101 +298,234 @@ __device__ __forceinline__ int am_warp_min(int v)
     return __reduce_min_sync(0xffffffffu, v);
 #endif
 }
+__device__ __forceinline__ unsigned am_umax2(unsigned a, unsigned b)       // max.u16x2
+{
+#if defined(NB_EMU)
+    const unsigned lo = max(a & 0xffffu, b & 0xffffu), hi = max(a >> 16, b >> 16);
+    return lo | (hi << 16);
+#else
+    unsigned r;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#endif
+}
+__device__ __forceinline__ unsigned am_umin2(unsigned a, unsigned b)       // min.u16x2
+{
+#if defined(NB_EMU)
+    const unsigned lo = min(a & 0xffffu, b & 0xffffu), hi = min(a >> 16, b >> 16);
+    return lo | (hi << 16);
+#else
+    unsigned r;
+    asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#endif
+}
+__device__ __forceinline__ unsigned am_lo2(unsigned a, unsigned b) { return (a & 0xffffu) | (b << 16); }          // (a.lo, b.lo)
+__device__ __forceinline__ unsigned am_hi2(unsigned a, unsigned b) { return (a >> 16) | (b & 0xffff0000u); }      // (a.hi, b.hi)
 #endif
 
 #if defined(__CUDA_ARCH__)
-// One butterfly per thread (128 threads): thread b reads old states 2b, 2b+1 (one shared-memory word) and produces new
-// states b and b + 128; the survivor bits of a step are collected by warp ballot into a 256-step tile that goes to global
-// memory in one coalesced sweep; traceback pulls the tiles back, newest first, and one thread walks them in shared
-// memory.  Semantics as conv_dec.c / conv_gen.h: int16 metrics (they cannot overflow: branch metrics are at most 3 in
-// magnitude and the minimum is subtracted every 77 steps), the odd predecessor survives unless the even one is strictly
-// better, first maximum at the end, 32 steps of pre- and post-roll.
-__device__ inline void viterbi_k9_cta(AmVitSlot &sm, uint8_t *dec, int b, const int8_t *in, uint8_t *out, int len, unsigned g0, unsigned g1,
-                                      unsigned g2)
+// The K=9 recursion in ONE warp, three trellis steps between two metric exchanges (radix 8), two butterflies per
+// instruction (16-bit metrics packed in pairs).  Lane g takes the eight old states 8g..8g+7 into four registers and
+// runs three add-compare-select stages on them without talking to anybody; the states it holds after stage 1, 2, 3 are
+// {4g+i, 4g+128+i}, {2g+(i&1)+64(i>>1) (+128)}, {g+32j}.  Only then do the metrics go through shared memory (eight
+// 2-byte stores, one 16-byte load, two __syncwarp) - no CTA barrier anywhere in the recursion.
+//   * In every stage butterfly i of a lane reads (unpacked) values 2i, 2i+1 and produces i (input bit 0) and 4+i (input
+//     bit 1).  A packed operation takes E = the even inputs and O = the odd inputs of two butterflies and yields their
+//     two bit-0 outputs in one register and their two bit-1 outputs in another: pairing the butterflies (0,2),(1,3) in
+//     stage 1 makes stage 1's four output registers exactly the E/O operands of stage 2 paired (0,1),(2,3); stage 3
+//     needs four byte permutes.  The exchange buffer is laid out so that the 16-byte load delivers stage 1's operands
+//     as they are: 16-bit slot 8 (s >> 3) + 2 (s & 3) + ((s >> 2) & 1) holds state s.
+//   * Metrics are unsigned with a common drift: every branch adds 3 + m or 3 - m (m = the branch metric, |m| <= 3
+//     because AM slices hard: the inputs are -1, 0, +1 - a precondition of this function), so nothing ever borrows
+//     between the halves of a word; differences between states - all that decisions, the minimum subtraction every 77
+//     steps (conv_dec.c:417-421) and the final "first maximum" look at - are those of the reference's int16 metrics.
+//     3 + m is built per polynomial by a bitwise select between (q + 1) and (1 - q) under the lane's sign masks.
+//   * The decision "odd predecessor unless the even one is strictly better" is bit 15 / 31 of Y + 0x80008000 - X; the 24
+//     decisions of a lane per group go to global memory as one word: bit 4 stage + 2 (input bit) + op + 16 half.
+// Semantics as conv_dec.c / conv_gen.h: survivor = odd predecessor unless the even one is strictly better, first
+// maximum at the end, 32 steps of pre- and post-roll.
+__device__ __forceinline__ int vit_butterfly(int stage, int g, int i)
+{
+    return stage == 0 ? 4 * g + i : stage == 1 ? 2 * g + (i & 1) + 64 * (i >> 1) : g + 32 * i;
+}
+__device__ __forceinline__ int vit_slot(int s) { return 8 * (s >> 3) + 2 * (s & 3) + ((s >> 2) & 1); }
+
+__device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, const int8_t *in, int len, unsigned g0, unsigned g1, unsigned g2)
 {
     const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
-    const int warp = b >> 5;
-    const unsigned reg = (unsigned)b << 1;
-    const int s0 = parity9(reg & g0) ? 1 : -1, s1 = parity9(reg & g1) ? 1 : -1, s2 = parity9(reg & g2) ? 1 : -1;
-    uint32_t *decw = reinterpret_cast<uint32_t *>(dec);                     // [step][8]
-    sm.pmw[0][b] = 0;
-    int cur = 0;
+    // sign masks: mk[stage][op][poly], 0xffff in a half whose butterfly has code bit 1 on its (even state, input 0) branch
+    unsigned mk[3][2][3];
+#pragma unroll
+    for (int sgi = 0; sgi < 3; sgi++)
+#pragma unroll
+        for (int op = 0; op < 2; op++) {
+            const int iA = sgi == 0 ? op : 2 * op, iB = sgi == 0 ? op + 2 : 2 * op + 1;     // pairing (0,2),(1,3) | (0,1),(2,3)
+            const unsigned rA = (unsigned)vit_butterfly(sgi, g, iA) << 1, rB = (unsigned)vit_butterfly(sgi, g, iB) << 1;
+            mk[sgi][op][0] = (parity9(rA & g0) ? 0xffffu : 0u) | (parity9(rB & g0) ? 0xffff0000u : 0u);
+            mk[sgi][op][1] = (parity9(rA & g1) ? 0xffffu : 0u) | (parity9(rB & g1) ? 0xffff0000u : 0u);
+            mk[sgi][op][2] = (parity9(rA & g2) ? 0xffffu : 0u) | (parity9(rB & g2) ? 0xffff0000u : 0u);
+        }
+    const int my_slot = 8 * (g >> 3) + 2 * (g & 3) + ((g >> 2) & 1);        // vit_slot(g + 32 j) = my_slot + 32 j
+    unsigned z0 = 0, z1 = 0, z2 = 0, z3 = 0;                                // (x0|x4), (x1|x5), (x2|x6), (x3|x7), x_i = state 8g+i
+    int next_norm = 0;                                                      // the minimum goes when step % interval == 0
     for (int base = 0; base < steps; base += VT) {
         const int nst = min(VT, steps - base);
-        for (int i = b; i < 3 * nst; i += AM_THREADS) {
-            const int st_i = base + i / 3;
-            int j = len - 32 + st_i;                                        // the input index wraps (tail biting)
+        for (int i = g; i < nst; i += 32) {
+            int j = len - 32 + base + i;                                    // the input index wraps (tail biting)
             while (j >= len) j -= len;
-            sm.q[i] = in[3 * j + (i - 3 * (i / 3))];
+            const unsigned a = (unsigned)(in[3 * j] + 1), b = (unsigned)(in[3 * j + 1] + 1), c = (unsigned)(in[3 * j + 2] + 1);
+            *reinterpret_cast<uint4 *>(sm.qd[i]) = make_uint4(a * 0x00010001u, b * 0x00010001u, c * 0x00010001u, 0u);
         }
-        __syncthreads();
+        __syncwarp();
 #pragma unroll 1
-        for (int k = 0; k < nst; k++) {
-            const int m = (int)sm.q[3 * k] * s0 + (int)sm.q[3 * k + 1] * s1 + (int)sm.q[3 * k + 2] * s2;
-            const uint32_t pw = sm.pmw[cur][b];
-            const int p0 = (short)(pw & 0xffffu), p1 = (short)(pw >> 16);
-            const int a0 = p0 + m, a1 = p1 - m, c0 = p0 - m, c1 = p1 + m;
-            const int d0 = !(a0 > a1), d1 = !(c0 > c1);
-            int n0 = d0 ? a1 : a0, n1 = d1 ? c1 : c0;
-            short *nxt = reinterpret_cast<short *>(sm.pmw[cur ^ 1]);
-            const unsigned w0 = __ballot_sync(0xffffffffu, d0), w1 = __ballot_sync(0xffffffffu, d1);
-            if ((b & 31) == 0) {
-                sm.tile[k][warp] = w0;
-                sm.tile[k][4 + warp] = w1;
+        for (int k = 0; k < nst; k += 3) {
+            const int ns = min(3, nst - k);                                 // (only the very last group can be short)
+            unsigned dword = 0;
+#pragma unroll
+            for (int sgi = 0; sgi < 3; sgi++) {
+                if (sgi < ns) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(sm.qd[k + sgi]);
+                    const unsigned n0 = 0x00020002u - q.x, n1 = 0x00020002u - q.y, n2 = 0x00020002u - q.z;
+                    unsigned e0, o0, e1, o1;                                // operands of the two packed operations
+                    if (sgi == 2) {
+                        e0 = am_lo2(z0, z1); o0 = am_hi2(z0, z1);           // stage 2 left (v0|v1), (v2|v3), (v4|v5), (v6|v7):
+                        e1 = am_lo2(z2, z3); o1 = am_hi2(z2, z3);           // evens (v0|v2), odds (v1|v3); (v4|v6), (v5|v7)
+                    } else {
+                        e0 = z0; o0 = z1; e1 = z2; o1 = z3;
+                    }
+                    unsigned r0, r1, r2, r3, d = 0;
+                    {
+                        const unsigned *m = mk[sgi][0];
+                        const unsigned mp = ((q.x & m[0]) | (n0 & ~m[0])) + ((q.y & m[1]) | (n1 & ~m[1])) + ((q.z & m[2]) | (n2 & ~m[2]));
+                        const unsigned mm = 0x00060006u - mp;
+                        const unsigned x1 = e0 + mp, y1 = o0 + mm, x2 = e0 + mm, y2 = o0 + mp;
+                        r0 = am_umax2(x1, y1);
+                        r1 = am_umax2(x2, y2);
+                        const unsigned t1 = y1 + 0x80008000u - x1, t2 = y2 + 0x80008000u - x2;
+                        d |= ((t1 >> 15) & 0x00010001u) | ((t2 >> 13) & 0x00040004u);
+                    }
+                    {
+                        const unsigned *m = mk[sgi][1];
+                        const unsigned mp = ((q.x & m[0]) | (n0 & ~m[0])) + ((q.y & m[1]) | (n1 & ~m[1])) + ((q.z & m[2]) | (n2 & ~m[2]));
+                        const unsigned mm = 0x00060006u - mp;
+                        const unsigned x1 = e1 + mp, y1 = o1 + mm, x2 = e1 + mm, y2 = o1 + mp;
+                        r2 = am_umax2(x1, y1);
+                        r3 = am_umax2(x2, y2);
+                        const unsigned t1 = y1 + 0x80008000u - x1, t2 = y2 + 0x80008000u - x2;
+                        d |= ((t1 >> 14) & 0x00020002u) | ((t2 >> 12) & 0x00080008u);
+                    }
+                    // stage 1 -> 2: E/O of ops (0,1),(2,3) are (r0, r2) and (r1, r3); stage 2 -> 3 and stage 3 -> exchange
+                    // keep the same order: op 0's bit-0 outputs, op 1's bit-0 outputs, op 0's bit-1 outputs, op 1's
+                    z0 = r0; z1 = r2; z2 = r1; z3 = r3;
+                    if (base + k + sgi == next_norm) {
+                        unsigned mn = am_umin2(am_umin2(z0, z1), am_umin2(z2, z3));
+                        mn = min(mn & 0xffffu, mn >> 16);
+                        mn = (unsigned)am_warp_min((int)mn) * 0x00010001u;
+                        z0 -= mn; z1 -= mn; z2 -= mn; z3 -= mn;
+                        next_norm += interval;
+                    }
+                    dword |= d << (4 * sgi);
+                }
             }
-            if ((base + k) % interval == 0) {                               // subtract the minimum (conv_dec.c:417-421)
-                const int wm = am_warp_min(min(n0, n1));
-                if ((b & 31) == 0) sm.wred[warp] = wm;
-                __syncthreads();
-                const int mn = min(min(sm.wred[0], sm.wred[1]), min(sm.wred[2], sm.wred[3]));
-                n0 -= mn;
-                n1 -= mn;
+            decw[(size_t)((base + k) / 3) * 32 + g] = dword;
+            // back to the exchange buffer.  After a full group: z0 = (u0|u1), z1 = (u2|u3), z2 = (u4|u5), z3 = (u6|u7), u_j = state g + 32 j
+            if (ns == 3) {
+                sm.pm[my_slot] = (unsigned short)z0;        sm.pm[my_slot + 32] = (unsigned short)(z0 >> 16);
+                sm.pm[my_slot + 64] = (unsigned short)z1;   sm.pm[my_slot + 96] = (unsigned short)(z1 >> 16);
+                sm.pm[my_slot + 128] = (unsigned short)z2;  sm.pm[my_slot + 160] = (unsigned short)(z2 >> 16);
+                sm.pm[my_slot + 192] = (unsigned short)z3;  sm.pm[my_slot + 224] = (unsigned short)(z3 >> 16);
+            } else {
+                // a short last group: after stage 1 the registers hold (y0|y2), (y1|y3), (y4|y6), (y5|y7); after stage 2
+                // (z0|z1), (z2|z3), (z4|z5), (z6|z7) - value i of stage sgi is state vit_butterfly(sgi, g, i & 3) + 128 (i >> 2)
+                const unsigned zz[4] = { z0, z1, z2, z3 };
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int ia = ns == 1 ? (r & 1) + 4 * (r >> 1) : 2 * r, ib = ns == 1 ? ia + 2 : ia + 1;
+                    sm.pm[vit_slot(vit_butterfly(ns - 1, g, ia & 3) + 128 * (ia >> 2))] = (unsigned short)zz[r];
+                    sm.pm[vit_slot(vit_butterfly(ns - 1, g, ib & 3) + 128 * (ib >> 2))] = (unsigned short)(zz[r] >> 16);
+                }
             }
-            nxt[b] = (short)n0;
-            nxt[b + 128] = (short)n1;
-            __syncthreads();
-            cur ^= 1;
+            __syncwarp();
+            {
+                const uint4 v = *reinterpret_cast<const uint4 *>(&sm.pm[8 * g]);
+                z0 = v.x; z1 = v.y; z2 = v.z; z3 = v.w;
+            }
+            __syncwarp();
         }
-        // the tile's decisions: one coalesced sweep to global memory
-        for (int i = b; i < nst * 8; i += AM_THREADS) decw[(size_t)base * 8 + i] = (&sm.tile[0][0])[i];
-        __syncthreads();
     }
-    // first maximum in state order (conv_dec.c:310-317)
+    // first maximum in state order (conv_dec.c:310-317): (z0..z3) = (x0|x4), (x1|x5), (x2|x6), (x3|x7)
     {
-        const short *pmv = reinterpret_cast<const short *>(sm.pmw[cur]);
-        int v = pmv[2 * b], idx = 2 * b;
-        if (pmv[2 * b + 1] > v) { v = pmv[2 * b + 1]; idx = 2 * b + 1; }
+        const unsigned xs[8] = { z0 & 0xffffu, z1 & 0xffffu, z2 & 0xffffu, z3 & 0xffffu, z0 >> 16, z1 >> 16, z2 >> 16, z3 >> 16 };
+        int v = (int)xs[0], idx = 8 * g;
+#pragma unroll
+        for (int i = 1; i < 8; i++)
+            if ((int)xs[i] > v) { v = (int)xs[i]; idx = 8 * g + i; }
         for (int o = 16; o; o >>= 1) {
             const int ov = __shfl_xor_sync(0xffffffffu, v, o), oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
-        if ((b & 31) == 0) { sm.wmax[warp] = v; sm.widx[warp] = idx; }
-        __syncthreads();
-        if (b == 0) {
-            int bv = sm.wmax[0], bi = sm.widx[0];
-            for (int q = 1; q < AM_THREADS / 32; q++)
-                if (sm.wmax[q] > bv || (sm.wmax[q] == bv && sm.widx[q] < bi)) { bv = sm.wmax[q]; bi = sm.widx[q]; }
-            sm.state = (unsigned)bi;
-        }
-        __syncthreads();
+        if (g == 0) sm.state = (unsigned)idx;
     }
-    // traceback, newest tile first: the CTA pulls a tile into shared memory, one thread walks it
-    for (int base = ((steps - 1) / VT) * VT; base >= 0; base -= VT) {
-        const int nst = min(VT, steps - base);
-        for (int i = b; i < nst * 8; i += AM_THREADS) (&sm.tile[0][0])[i] = decw[(size_t)base * 8 + i];
-        __syncthreads();
-        if (b == 0) {
-            unsigned state = sm.state;
-            for (int k = nst - 1; k >= 0; k--) {
-                const int st_i = base + k;
-                const unsigned bit = (sm.tile[k][state >> 5] >> (state & 31u)) & 1u;
-                if (st_i >= 32 && st_i < 32 + len) out[st_i - 32] = (uint8_t)((state >> 7) & 1u);
-                state = ((state << 1) & 254u) | bit;
+}
+
+// the survivor bit of new state s after step t, from the decision words of viterbi_k9_warp
+__device__ __forceinline__ unsigned vit_survivor(const uint32_t *decw, int t, unsigned s)
+{
+    const int grp = t / 3, sgi = t - 3 * grp;
+    const unsigned b = s & 127u, hi = s >> 7;
+    const unsigned ln = sgi == 0 ? b >> 2 : sgi == 1 ? (b & 63u) >> 1 : b & 31u;
+    const unsigned i = sgi == 0 ? b & 3u : sgi == 1 ? (b & 1u) + 2u * (b >> 6) : b >> 5;
+    const unsigned op = sgi == 0 ? i & 1u : i >> 1, half = sgi == 0 ? i >> 1 : i & 1u;
+    return (decw[(size_t)grp * 32 + ln] >> (4u * sgi + 2u * hi + op + 16u * half)) & 1u;
+}
+
+// Traceback by the whole CTA: the steps are cut into AM_THREADS segments and every thread walks its own one backwards.
+// The state a walk has to start from is only known once the walk of the following segment has arrived - so a walker
+// starts VIT_WARMUP steps further on, from state 0: survivor paths merge going backwards, and by the time it crosses
+// into its own segment it is (almost always) on the decoder's path.  Every walker then checks the state it started its
+// segment from against the state the following segment's walker really arrived at, and walks again from that one if they
+// differ, until nobody had to: the last segment starts from the true end state, so when the round without changes comes
+// every segment was walked from the state the sequential traceback passes through - the output is that of the
+// sequential traceback, whatever the warm-up did.
+__device__ inline int viterbi_k9_traceback(AmVitSlot &sm, const uint32_t *decw, int w, uint8_t *out, int len, int warmup = VIT_WARMUP)
+{
+    const int steps = len + 64;
+    const int seg = (steps + AM_THREADS - 1) / AM_THREADS;
+    const int lo = w * seg, hi = min(steps, lo + seg);                       // this walker's steps [lo, hi)
+    const bool mine = lo < hi;
+    unsigned start = 0;                                                      // state after step hi - 1
+    if (mine) {
+        const int t0 = min(steps, hi + warmup);
+        unsigned state = t0 == steps ? sm.state : 0u;
+        for (int t = t0 - 1; t >= hi; t--) state = ((state << 1) & 254u) | vit_survivor(decw, t, state);
+        start = state;
+    }
+    bool walk = mine;
+    int round = 0;                                                           // returns the number of repair rounds (0: the warm-up was right)
+    for (; round <= AM_THREADS; round++) {
+        if (walk) {
+            unsigned state = start;
+            for (int t = hi - 1; t >= lo; t--) {
+                if (t >= 32 && t < 32 + len) out[t - 32] = (uint8_t)(state >> 7);
+                state = ((state << 1) & 254u) | vit_survivor(decw, t, state);
             }
-            sm.state = state;
+            sm.ends[w] = (unsigned short)state;                              // state after step lo - 1
         }
+        if (w == 0) sm.changed = 0;
         __syncthreads();
+        walk = false;
+        if (mine) {
+            const unsigned want = hi == steps ? sm.state : (unsigned)sm.ends[w + 1];
+            if (want != start) { start = want; walk = true; }
+        }
+        if (walk) sm.changed = 1;
+        __syncthreads();
+        const int any = sm.changed;
+        __syncthreads();
+        if (!any) break;
     }
+    return round;
 }
 #endif
 
@@ -409,8 +544,12 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
     (void)steps;
     (void)interval;
     AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    uint32_t *decw = reinterpret_cast<uint32_t *>(w.dec);
     __syncthreads();
-    viterbi_k9_cta(sm.vit, w.dec, L.lane, in, out, len, g0, g1, g2);
+    if (L.lane < 32) viterbi_k9_warp(sm.vit[0], decw, L.lane, in, len, g0, g1, g2);
+    __syncthreads();
+    viterbi_k9_traceback(sm.vit[0], decw, L.lane, out, len);
+    __syncthreads();
 #else
     for (int i = L.lane; i < 256; i += L.n) w.pm[0][i] = 0;
     AM_SYNC();
@@ -462,11 +601,23 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
 #endif
 }
 
-// P1 and P3 of a frame's last block into separate buffers (one after the other: a decode takes the whole CTA)
+// P1 and P3 of a frame's last block into separate buffers: on the device the two recursions run side by side, a warp each
 AM_HD inline void viterbi_k9_pair(AmWork &w, Lanes L, const VitJob &a, const VitJob &b)
 {
+#if defined(__CUDA_ARCH__)
+    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
+    uint32_t *da = reinterpret_cast<uint32_t *>(w.dec_p1), *db = reinterpret_cast<uint32_t *>(w.dec);
+    __syncthreads();
+    if (L.lane < 32) viterbi_k9_warp(sm.vit[0], da, L.lane, a.in, a.len, a.g0, a.g1, a.g2);
+    else if (L.lane < 64) viterbi_k9_warp(sm.vit[1], db, L.lane - 32, b.in, b.len, b.g0, b.g1, b.g2);
+    __syncthreads();
+    viterbi_k9_traceback(sm.vit[0], da, L.lane, a.out, a.len);
+    viterbi_k9_traceback(sm.vit[1], db, L.lane, b.out, b.len);
+    __syncthreads();
+#else
     viterbi_k9(w, L, a.in, a.out, a.len, a.g0, a.g1, a.g2);
     viterbi_k9(w, L, b.in, b.out, b.len, b.g0, b.g1, b.g2);
+#endif
 }
 
 AM_HD inline void descramble(const AmTables &tb, Lanes L, uint8_t *bits, int len)     // decode.c:279-294

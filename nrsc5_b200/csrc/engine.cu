@@ -558,6 +558,22 @@ __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)        // one warp pe
     if (lane == 0) rc[i] = r;
 }
 
+// stage entry point: the AM decoder (am.cuh: viterbi_k9_warp + viterbi_k9_traceback) on `njobs` independent tail-biting
+// frames of `len` bits, one CTA each; rounds[j] = repair rounds the segmented traceback needed
+__global__ void __launch_bounds__(nbam::AM_THREADS) k_am_vit_test(const int8_t *in, uint8_t *out, uint32_t *dec, size_t dec_words, int len,
+                                                                  unsigned g0, unsigned g1, unsigned g2, int warmup, int *rounds)
+{
+#if defined(__CUDA_ARCH__)                                                    // (the decoder's device branch does not exist in the host pass)
+    __shared__ nbam::AmVitSlot slot;
+    const int j = blockIdx.x, t = threadIdx.x;
+    uint32_t *decw = dec + (size_t)j * dec_words;
+    if (t < 32) nbam::viterbi_k9_warp(slot, decw, t, in + (size_t)j * 3 * len, len, g0, g1, g2);
+    __syncthreads();
+    const int r = nbam::viterbi_k9_traceback(slot, decw, t, out + (size_t)j * len, len, warmup);
+    if (t == 0) rounds[j] = r;
+#endif
+}
+
 // ===========================================================================
 // L2 framing (l2.cuh): the last kernel of a pass.  One CTA per stream walks the frames (and frame_resets) k_stream
 // queued, in the reference's call order, and appends one REC_L2 record per frame to the stream's log.
@@ -2316,6 +2332,38 @@ extern "C" int nrsc5b_rs_decode(int device, uint8_t *blocks, int *rcs, int n)
     CK(cudaMemcpy(blocks, db, (size_t)n * 255, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(rcs, dr, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(db);
+    cudaFree(dr);
+    return NRSC5B_OK;
+}
+
+/* The AM chain's K=9 rate-1/3 tail-biting decoder alone (reference src/conv_dec.c with K = 9, as decode.c:487,515-539
+ * calls it): njobs frames of len bits, in = 3 * len hard symbols each (-1, 0 = punctured, +1), out = len bits each.
+ * warmup <= 0: the production warm-up of the segmented traceback; rounds (optional, [njobs]) = repair rounds it took. */
+extern "C" int nrsc5b_viterbi_k9(int device, const int8_t *in, uint8_t *out, int len, int njobs, unsigned g0, unsigned g1, unsigned g2,
+                                 int warmup, int *rounds)
+{
+    if (!in || !out || len < 32 || njobs < 1) return NRSC5B_EINVAL;
+    for (size_t i = 0; i < (size_t)njobs * 3 * len; i++)
+        if (in[i] < -1 || in[i] > 1) return NRSC5B_EINVAL;                 // the AM chain slices hard
+    int rc = use_device(device);
+    if (rc) return rc;
+    const size_t dec_words = (size_t)((len + 64 + 2) / 3) * 32;
+    int8_t *di = nullptr;
+    uint8_t *dout = nullptr;
+    uint32_t *dd = nullptr;
+    int *dr = nullptr;
+    CK(cudaMalloc(&di, (size_t)njobs * 3 * len));
+    CK(cudaMalloc(&dout, (size_t)njobs * len));
+    CK(cudaMalloc(&dd, (size_t)njobs * dec_words * 4));
+    CK(cudaMalloc(&dr, (size_t)njobs * sizeof(int)));
+    CK(cudaMemcpy(di, in, (size_t)njobs * 3 * len, cudaMemcpyHostToDevice));
+    k_am_vit_test<<<njobs, nbam::AM_THREADS>>>(di, dout, dd, dec_words, len, g0, g1, g2, warmup > 0 ? warmup : nbam::VIT_WARMUP, dr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, (size_t)njobs * len, cudaMemcpyDeviceToHost));
+    if (rounds) CK(cudaMemcpy(rounds, dr, (size_t)njobs * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(di);
+    cudaFree(dout);
+    cudaFree(dd);
     cudaFree(dr);
     return NRSC5B_OK;
 }

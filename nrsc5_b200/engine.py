@@ -428,6 +428,21 @@ def rs_decode(blocks: np.ndarray, device: int = 0):
     return rc, b
 
 
+def viterbi_k9(sym: np.ndarray, gens=(0o561, 0o657, 0o711), warmup: int = 0, device: int = 0):
+    """The AM chain's K=9 decoder on a batch of frames: sym int8 [njobs, 3 * len] of -1 / 0 / +1; returns (bits uint8
+    [njobs, len], repair rounds of the segmented traceback int32 [njobs])."""
+    a = np.ascontiguousarray(sym, dtype=np.int8)
+    a = a.reshape(1, -1) if a.ndim == 1 else a
+    njobs, n = a.shape[0], a.shape[1] // 3
+    out = np.empty((njobs, n), dtype=np.uint8)
+    rounds = np.empty(njobs, dtype=np.int32)
+    L = load_library()
+    L.nrsc5b_viterbi_k9.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                    ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_void_p]
+    _check(L.nrsc5b_viterbi_k9(device, a.ctypes.data, out.ctypes.data, n, njobs, *gens, warmup, rounds.ctypes.data), "nrsc5b_viterbi_k9")
+    return out, rounds
+
+
 def fft2048(x: np.ndarray, device: int = 0) -> np.ndarray:
     a = np.ascontiguousarray(x, dtype=np.complex64).reshape(-1, 2048)
     out = np.empty_like(a)

@@ -6,8 +6,9 @@ import numpy as np
 TAPS, PERIOD, DECIM = 256, 11907, 32
 
 
-def channelize(cu8: np.ndarray, offsets, taps: np.ndarray, phasor: np.ndarray) -> np.ndarray:
-    """cu8: uint8 I/Q interleaved (length a multiple of 64 is used); returns int16 [nch][2 * nout]."""
+def channelize(cu8: np.ndarray, offsets, taps: np.ndarray, phasor: np.ndarray, n0: int = 0) -> np.ndarray:
+    """cu8: uint8 I/Q interleaved (length a multiple of 64 is used); returns int16 [nch][2 * nout].  n0: index of the
+    first output when cu8 is a slice of a longer capture starting at its sample 32 * n0 (the mixer runs on)."""
     a = np.asarray(cu8, dtype=np.uint8)
     a = a[: a.size & ~63]
     ns = a.size // 2
@@ -19,7 +20,7 @@ def channelize(cu8: np.ndarray, offsets, taps: np.ndarray, phasor: np.ndarray) -
         return out
     idx = (np.arange(nout)[:, None] * DECIM + np.arange(TAPS)[None, :])         # [nout][256] sample indices 32 n + u
     XR, XI = xr[idx], xi[idx]
-    n = np.arange(nout, dtype=np.int64)
+    n = np.arange(nout, dtype=np.int64) + int(n0)
     for k, m in enumerate(offsets):
         wr = taps[k, :, 0].astype(np.int64)
         wi = taps[k, :, 1].astype(np.int64)

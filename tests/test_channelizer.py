@@ -48,7 +48,7 @@ def test_oracle_moves_a_tone_at_the_channel_centre_to_dc():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nch,nbytes", [(3, 64 * 700), (40, 64 * 1031), (33, 64 * 135)])
+@pytest.mark.parametrize("nch,nbytes", [(3, 64 * 700), (40, 64 * 1031), (33, 64 * 135), (5, 64 * 25001)])   # the last: the mixer wraps twice
 def test_kernel_equals_the_restatement_bit_for_bit(nch, nbytes):
     rng = np.random.default_rng(nch)
     offs = list(rng.choice(np.arange(-118, 119), nch, replace=False))

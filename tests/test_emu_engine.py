@@ -52,6 +52,7 @@ test_viterbi_saturating_and_noisy = _stages.test_viterbi_saturating_and_noisy
 test_viterbi_fast_path_and_fallback_agree = _stages.test_viterbi_fast_path_and_fallback_agree
 test_viterbi_p1_length_bit_exact = _stages.test_viterbi_p1_length_bit_exact
 test_rs_decode_bit_exact = _stages.test_rs_decode_bit_exact
+test_viterbi_k9_equals_the_reference_decoder = _stages.test_viterbi_k9_equals_the_reference_decoder
 
 
 def test_rs_beyond_the_correction_radius_equals_reference():

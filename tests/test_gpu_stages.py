@@ -140,3 +140,50 @@ def test_rs_beyond_the_correction_radius_equals_reference():
     nfail, ncorr = rs_beyond_radius(120000)
     assert nfail > 100000 and ncorr > 50          # both outcomes occur
 
+
+
+def _k9_frames(rng, njobs, n, gens, noise):
+    """Tail-biting rate-1/3 K=9 code words of random bits as hard symbols; `noise` = fraction of flipped symbols; every
+    fifth symbol punctured (0), as the AM chain's E1/E2/E3 depuncturing leaves them."""
+    bits = rng.integers(0, 2, (njobs, n), dtype=np.uint8)
+    sym = np.zeros((njobs, 3 * n), dtype=np.int8)
+    for j in range(njobs):
+        b = bits[j].astype(np.int64)
+        reg = np.zeros(n, dtype=np.int64)
+        for q in range(9):
+            reg |= np.roll(b, q) << (8 - q)                                  # register at bit i: bits i-8 .. i, newest on top
+        for k, g in enumerate(gens):
+            v = reg & g
+            par = np.zeros(n, dtype=np.int64)
+            for q in range(9):
+                par ^= (v >> q) & 1
+            sym[j, k::3] = np.where(par == 1, 1, -1)
+    flip = rng.random(sym.shape) < noise
+    sym = np.where(flip, -sym, sym).astype(np.int8)
+    sym[:, 4::5] = 0
+    return bits, sym
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,gens", [(80, (0o561, 0o753, 0o711)), (3750, (0o561, 0o657, 0o711)), (3751, (0o561, 0o657, 0o711)),
+                                    (3752, (0o561, 0o657, 0o711)), (24000, (0o561, 0o753, 0o711))])
+def test_viterbi_k9_equals_the_reference_decoder(n, gens):
+    """The AM decoder alone (radix-8 single-warp recursion + segmented traceback, csrc/am.cuh) against the oracle's
+    conv_dec restatement with K = 9: clean, noisy and pure-noise frames of every length the chain uses (PIDS 80, P1 3750,
+    P3 24000; 3751 / 3752 for the two shapes of a short last group) - bit for bit, ties and all.  Then the same frames
+    with a warm-up of 3 steps, which leaves most traceback walkers on a wrong path: the repair rounds must bring back the
+    sequential traceback's output."""
+    from nrsc5_b200 import engine as eng
+    rng = np.random.default_rng(n)
+    njobs = 6 if n > 4000 else 12
+    _, clean = _k9_frames(rng, njobs // 3, n, gens, 0.0)
+    _, noisy = _k9_frames(rng, njobs // 3, n, gens, 0.08)
+    junk = rng.integers(-1, 2, (njobs - 2 * (njobs // 3), 3 * n)).astype(np.int8)
+    sym = np.concatenate([clean, noisy, junk])
+    want = np.stack([port.viterbi(sym[j], k=9, gens=gens) for j in range(sym.shape[0])])
+    got, rounds = eng.viterbi_k9(sym, gens)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:5]
+    got3, rounds3 = eng.viterbi_k9(sym, gens, warmup=3)
+    assert np.array_equal(got3, want)
+    if n >= 3750:
+        assert rounds3.max() >= 1 and rounds3.max() >= rounds.max()          # the repair loop really ran
