@@ -278,11 +278,12 @@ struct AmSmem {
     union {
         AmVitSlot vit[2];                        // two decoders side by side (P1 and P3 of a frame's last block)
         struct {                                 // demod_pass
-            float2 ph[2][SYM];                   // NCO phase per sample of a symbol, double-buffered (producer warp runs ahead)
-            float2 phase_end[2];                 // the phase after the symbol, renormalised
-            float2 fft[FFT];                     // one symbol: windowed, folded, shifted; transformed in place
+            float2 ph[2][3][SYM];                // NCO phase per sample of three symbols, double-buffered (producer warp runs ahead)
+            float2 phase_end[2];                 // the phase after the block, renormalised
+            float2 fft[3][FFT];                  // a symbol per consumer warp: windowed, folded, shifted; transformed in place
             float2 carrier[BLK];                 // first pass: the carrier bin of every symbol
-            float mag[2 * PIDS_OUTER + 1];       // first pass while acquiring: summed magnitudes around the carrier
+            float magv[2][3][2 * PIDS_OUTER + 1];    // first pass while acquiring: a symbol's magnitudes around the carrier ...
+            float mag[2 * PIDS_OUTER + 1];       // ... and their sums over the symbols, added in symbol order
         } dem;
     };
     int red[AM_THREADS / 32];                    // CTA-wide sums (bit_errors)
@@ -1121,36 +1122,31 @@ AM_HD inline void symbol_fft(AmWork &w, const AmTables &tb, Lanes L, int sym, in
 }
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void am_bar_consumers()
-{
-#if defined(NB_EMU)
-    emu_bar_sync(1, AM_THREADS - 32);
-#else
-    asm volatile("bar.sync 1, %0;" ::"n"(AM_THREADS - 32) : "memory");
-#endif
-}
-
-// One pass over the 32 symbols of a block (acquire.c:178-195 first pass, :237-256 second pass), as a two-stage pipeline:
-// warp 0 runs the NCO phase chain of symbol i - 270 dependent complex multiplications and the renormalisation,
-// exactly the reference's recurrence - while warps 1..3 window, fold, shift and transform symbol i-1 (the radix-2
-// butterfly order of symbol_fft / fft256 above) in shared memory and hand its bins on:
+// One pass over the 32 symbols of a block (acquire.c:178-195 first pass, :237-256 second pass), as a two-stage pipeline
+// in batches of three symbols: warp 0 runs the NCO phase chain of symbols 3i .. 3i+2 - 270 dependent complex
+// multiplications and the renormalisation each, exactly the reference's recurrence, the one thing in this pass that
+// cannot be spread out - while warps 1, 2, 3 take ONE symbol each of batch i-1: window, fold, shift and the radix-2
+// butterflies of symbol_fft / fft256 above in the warp's own shared-memory buffer, with __syncwarp between the stages
+// and no CTA barrier (one per batch hands the phases over), then hand the bins on:
 //   first pass  (bins == nullptr): the carrier bin of every symbol -> sm.dem.carrier, and - while acquiring - the
-//               magnitudes of the 107 bins around it, summed over the symbols in order -> sm.dem.mag
+//               magnitudes of the 107 bins around it, summed over the symbols in symbol order -> sm.dem.mag
 //   second pass: bins CENTER-81 .. CENTER+81 -> bins[b][symbol]                               (sync_push)
 // `phase` is every thread's copy of the running NCO phase; all of them get the value after the last symbol.
 __device__ inline void demod_pass(AmWork &w, const AmTables &tb, Lanes L, int samperr, float2 &phase, float2 inc,
                                   float2 (*bins)[BLK], bool want_mag)
 {
     AmSmem &sm = *static_cast<AmSmem *>(L.smem);
-    constexpr int NC = AM_THREADS - 32;
-    const int t = L.lane, c = t - 32;
+    constexpr int NMAG = 2 * PIDS_OUTER + 1, NBATCH = (BLK + 2) / 3;
+    const int t = L.lane, lane = t & 31, cw = (t >> 5) - 1;    // consumer warp 0..2 (warp 0 of the CTA produces)
     const int offset = (FFT - CP) / 2;
     float2 ph = phase;
-    float mag = 0, mag2 = 0;                                   // consumer c: bins CENTER - PIDS_OUTER + c and ... + c + NC (107 in all)
-    for (int i = 0; i <= BLK; i++) {
+    if (!bins && want_mag)
+        for (int b = t; b < NMAG; b += AM_THREADS) sm.dem.mag[b] = 0.0f;
+    for (int i = 0; i <= NBATCH; i++) {
         if (t < 32) {
-            if (i < BLK) {
-                float2 *out = sm.dem.ph[i & 1];
+            for (int q = 0; q < 3; q++) {
+                if (3 * i + q >= BLK) break;
+                float2 *out = sm.dem.ph[i & 1][q];
 #pragma unroll 10
                 for (int j = 0; j < SYM; ++j) {               // (unrolled: the stores and the loop leave the dependent chain alone)
                     if (t == 0) out[j] = ph;
@@ -1160,58 +1156,73 @@ __device__ inline void demod_pass(AmWork &w, const AmTables &tb, Lanes L, int sa
                 ph = make_float2(ph.x / a, ph.y / a);
             }
         } else if (i > 0) {
-            const int sym = i - 1;
-            const float2 *pv = sm.dem.ph[sym & 1];
-            for (int j = c; j < FFT; j += NC) {
-                const float2 sample = cmul(pv[j], w.buf[sym * SYM + j + samperr]);
-                sm.dem.fft[(j + offset) % FFT] = j < CP ? cscale(sample, tb.shape[j]) : sample;
-            }
-            am_bar_consumers();
-            for (int j = FFT + c; j < SYM; j += NC) {
-                const float2 sample = cmul(pv[j], w.buf[sym * SYM + j + samperr]);
-                const int idx = (j + offset) % FFT;
-                sm.dem.fft[idx] = cadd(sm.dem.fft[idx], cscale(sample, tb.shape[j]));
-            }
-            am_bar_consumers();
-            for (int k = c; k < FFT; k += NC) {               // bit reversal
-                const int r = tb.brev[k];
-                if (r > k) {
-                    const float2 tmp = sm.dem.fft[k];
-                    sm.dem.fft[k] = sm.dem.fft[r];
-                    sm.dem.fft[r] = tmp;
+            // the magnitudes of batch i-2, in symbol order (its three warps finished before the barrier that started this
+            // iteration): consumer warp 0 adds them before it starts on its own symbol
+            if (!bins && want_mag && cw == 0 && i >= 2) {
+                const int nb = min(3, BLK - 3 * (i - 2));
+                for (int b = lane; b < NMAG; b += 32) {
+                    float m = sm.dem.mag[b];
+                    for (int q = 0; q < nb; q++) m += sm.dem.magv[i & 1][q][b];
+                    sm.dem.mag[b] = m;
                 }
             }
-            am_bar_consumers();
-            for (int half = 1; half < FFT; half <<= 1) {
-                const int tstep = FFT / (2 * half);
-                for (int bf = c; bf < FFT / 2; bf += NC) {
-                    const int grp = bf / half, k = bf - grp * half;
-                    const int i0 = grp * 2 * half + k, i1 = i0 + half;
-                    const float2 tt = cmul(sm.dem.fft[i1], tb.tw[k * tstep]);
-                    const float2 u = sm.dem.fft[i0];
-                    sm.dem.fft[i0] = cadd(u, tt);
-                    sm.dem.fft[i1] = make_float2(u.x - tt.x, u.y - tt.y);
+            const int sym = 3 * (i - 1) + cw;
+            if (sym < BLK) {
+                const float2 *pv = sm.dem.ph[(i - 1) & 1][cw];
+                float2 *f = sm.dem.fft[cw];
+                for (int j = lane; j < FFT; j += 32) {
+                    const float2 sample = cmul(pv[j], w.buf[sym * SYM + j + samperr]);
+                    f[(j + offset) % FFT] = j < CP ? cscale(sample, tb.shape[j]) : sample;
                 }
-                am_bar_consumers();
-            }
-            // spec[k] = fft[(k + 128) % 256] (fftshift, defines.h:123-138)
-            if (bins) {
-                for (int b = CENTER - MAX_IDX + c; b <= CENTER + MAX_IDX; b += NC) bins[b][sym] = sm.dem.fft[(b + FFT / 2) % FFT];
-            } else {
-                if (c == 0) sm.dem.carrier[sym] = sm.dem.fft[(CENTER + FFT / 2) % FFT];
-                if (want_mag) {
-                    mag += cabs2(sm.dem.fft[(CENTER - PIDS_OUTER + c + FFT / 2) % FFT]);
-                    if (c + NC < 2 * PIDS_OUTER + 1) mag2 += cabs2(sm.dem.fft[(CENTER - PIDS_OUTER + c + NC + FFT / 2) % FFT]);
+                __syncwarp();
+                for (int j = FFT + lane; j < SYM; j += 32) {
+                    const float2 sample = cmul(pv[j], w.buf[sym * SYM + j + samperr]);
+                    const int idx = (j + offset) % FFT;
+                    f[idx] = cadd(f[idx], cscale(sample, tb.shape[j]));
+                }
+                __syncwarp();
+                for (int k = lane; k < FFT; k += 32) {            // bit reversal
+                    const int r = tb.brev[k];
+                    if (r > k) {
+                        const float2 tmp = f[k];
+                        f[k] = f[r];
+                        f[r] = tmp;
+                    }
+                }
+                __syncwarp();
+                for (int half = 1; half < FFT; half <<= 1) {
+                    const int tstep = FFT / (2 * half);
+#pragma unroll
+                    for (int bf = lane; bf < FFT / 2; bf += 32) {
+                        const int grp = bf / half, k = bf - grp * half;
+                        const int i0 = grp * 2 * half + k, i1 = i0 + half;
+                        const float2 tt = cmul(f[i1], tb.tw[k * tstep]);
+                        const float2 u = f[i0];
+                        f[i0] = cadd(u, tt);
+                        f[i1] = make_float2(u.x - tt.x, u.y - tt.y);
+                    }
+                    __syncwarp();
+                }
+                // spec[k] = fft[(k + 128) % 256] (fftshift, defines.h:123-138)
+                if (bins) {
+                    for (int b = CENTER - MAX_IDX + lane; b <= CENTER + MAX_IDX; b += 32) bins[b][sym] = f[(b + FFT / 2) % FFT];
+                } else {
+                    if (lane == 0) sm.dem.carrier[sym] = f[(CENTER + FFT / 2) % FFT];
+                    if (want_mag)
+                        for (int b = lane; b < NMAG; b += 32) sm.dem.magv[(i - 1) & 1][cw][b] = cabs2(f[(CENTER - PIDS_OUTER + b + FFT / 2) % FFT]);
                 }
             }
         }
         __syncthreads();
     }
-    if (!bins && want_mag && c >= 0) {
-        sm.dem.mag[c] = mag;
-        if (c + NC < 2 * PIDS_OUTER + 1) sm.dem.mag[c + NC] = mag2;
+    if (!bins && want_mag && cw == 0) {                        // the last batch's magnitudes
+        const int nb = BLK - 3 * (NBATCH - 1);
+        for (int b = lane; b < NMAG; b += 32) {
+            float m = sm.dem.mag[b];
+            for (int q = 0; q < nb; q++) m += sm.dem.magv[(NBATCH - 1) & 1][q][b];
+            sm.dem.mag[b] = m;
+        }
     }
-    static_assert(2 * NC >= 2 * PIDS_OUTER + 1 && NC <= 2 * PIDS_OUTER + 1, "two bins per consumer cover the 107");
     if (t == 0) sm.dem.phase_end[0] = ph;
     __syncthreads();
     phase = sm.dem.phase_end[0];
