@@ -210,12 +210,14 @@ int nrsc5b_get_kernel_times(nrsc5b_engine_t *e, double *ms4, unsigned long long 
  * equalise + error sums, demap + bookkeeping}. */
 int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12, unsigned long long *n12);
 
-/* AM engines: SM cycles of k_am per phase summed over streams since the last reset / rewind: {window + coarse acquisition,
- * first demodulation pass, second pass, sync + slicing, PIDS, P1 + P3 + interleaver, of which P3, of which interleaver}. */
-int nrsc5b_get_am_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc8);
+/* AM engines: SM cycles of k_am per phase summed over streams since the last reset / rewind, twelve values: {window + coarse
+ * acquisition, first demodulation pass, second pass, sync + slicing, PIDS, P1 + P3 + interleaver, of which P3's post-processing,
+ * of which interleaver; across all decodes: K=9 recursion, traceback; window load of the blocks in fine sync; spare}. */
+int nrsc5b_get_am_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12);
 
 /* Experiment switches for kernel tuning (bit 0: do not overlap carrier staging with the Costas loops; bit 1: library
- * sincosf / atan2f on the Costas loops' dependent chain instead of the short-chain versions); 0 = default.  Also read
+ * sincosf / atan2f on the Costas loops' dependent chain instead of the short-chain versions; bit 3: nrsc5b_viterbi_k9 prints its
+ * cycle counts per frame); 0 = default.  Also read
  * from the environment (NRSC5_B200_DBG) when an engine is created. */
 int nrsc5b_debug_set(int flags);
 
@@ -236,10 +238,11 @@ int nrsc5b_viterbi_k7_ex(int device, const int8_t *in, uint8_t *out, int len, in
 int nrsc5b_rs_decode(int device, uint8_t *blocks255, int *rc, int nblocks);
 /* The AM chain's K=9 rate-1/3 tail-biting Viterbi decoder (reference src/conv_dec.c + src/conv_gen.h with K = 9 as
  * src/decode.c:487,515-539 call it): njobs frames of len bits; in = 3 * len hard symbols per frame (-1, 0 = punctured, +1:
- * the AM chain slices hard, other values are rejected), out = len bits per frame.  warmup <= 0 selects the production
- * warm-up of the segmented traceback; rounds (optional, [njobs]) receives the repair rounds the traceback needed. */
+ * the AM chain slices hard, other values are rejected), out = len bits per frame.  warmup / chunk_warmup <= 0 select the
+ * production warm-up of the segmented traceback / of the recursion's chunks; rounds (optional, [njobs]) receives the repair
+ * rounds the traceback needed (low 16 bits) and the chunks of the recursion that had to be run again (high 16 bits). */
 int nrsc5b_viterbi_k9(int device, const int8_t *in, uint8_t *out, int len, int njobs, unsigned g0, unsigned g1, unsigned g2,
-                      int warmup, int *rounds);
+                      int warmup, int chunk_warmup, int *rounds);
 /* L2 alone on one stream: frames = {u32 lc, u32 nbits, packed bits padded to 4 bytes} back to back, nbits == 0 standing
  * for frame_reset (frame.c:716); all six frame lengths of frame.c:651-690.  Writes one REC_L2 record per frame
  * (frame_off = the frame's index in the list) and returns the bytes written, or NRSC5B_EFULL. */

@@ -143,8 +143,9 @@ struct AmWork {
     uint8_t out_p1[P1_LEN + 10];               // P1 bits when P1 and P3 are decoded side by side (a frame's last block)
     alignas(16) uint8_t dec_p1[(size_t)((P1_LEN + 64 + 2) / 3) * 128];   // ... and its survivor bits
     short pm[2][256];
-    unsigned long long ph_cyc[8];              // SM cycles per phase (thread 0): window + acquisition, first pass, second pass, sync +
-                                               // slicing, PIDS, P1 (Viterbi, BER, packing), P3, interleaver
+    unsigned long long ph_cyc[16];             // SM cycles per phase (thread 0): window + acquisition, first pass, second pass, sync +
+                                               // slicing, PIDS, P1/P3 group, of it P3's post-processing, interleaver; K=9 recursion,
+                                               // traceback (all decodes), window load of a FINE block, spare
     alignas(16) uint8_t dec[(size_t)VIT_MAX_STEPS * 48];   // survivor bits: host 32 bytes per trellis step, device 128 per three steps (viterbi_k9)
     float2 mult[4][PW];
     uint8_t sym_pl[BLK * PW], sym_pu[BLK * PW], sym_s[BLK * PW], sym_t[BLK * PW], sym_pids[2 * BLK];
@@ -266,17 +267,24 @@ AM_HD inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 
 
 // ---- shared memory of a stream's CTA (device) ----
 constexpr int VT = 192;                          // trellis steps per tile of staged inputs (a multiple of three)
-constexpr int VIT_WARMUP = 128;                  // traceback walkers start this many steps late, from any state
+constexpr int VIT_WARMUP = 96;                   // traceback walkers start this many steps late, from any state
+constexpr int VIT_CHUNK_WARMUP = 192;            // the recursion's chunks start this many steps early (a multiple of three)
+constexpr int VIT_TEST_SLOTS_BYTES = 4 * 5 * 1024;               // >= (AM_THREADS / 32) * sizeof(AmVitSlot), a multiple of 16 (stage test kernel)
+constexpr int VIT_TB_WORDS = 2 * (AM_THREADS / 32) * 8 * 8 * 32;  // sizeof(AmVitRows) / 4 (declared after the decoder)
 struct AmVitSlot {                               // one K=9 decoder: the recursion by ONE warp (viterbi_k9_warp)
     alignas(16) unsigned short pm[256];          // path metrics between two groups of three steps (slot order, see below)
+    alignas(16) unsigned short chk[256];         // a chunk's metrics after its warm-up (viterbi_k9_forward)
     alignas(16) uint32_t qd[VT][4];              // the tile's soft inputs, (q + 1) in both halves of a word
-    unsigned short ends[AM_THREADS];             // traceback: the state each walker arrived at
+    unsigned short ends[AM_THREADS + 1];         // traceback: the state each walker arrived at
     unsigned state;                              // state after the last step (first maximum)
     int changed;
 };
 struct AmSmem {
     union {
-        AmVitSlot vit[2];                        // two decoders side by side (P1 and P3 of a frame's last block)
+        struct {
+            AmVitSlot vit[AM_THREADS / 32];      // the recursion's chunks, one per warp (viterbi_k9_forward)
+            uint32_t tb[VIT_TB_WORDS];           // traceback: rows of decision words per walker (AmVitRows)
+        };
         struct {                                 // demod_pass
             float2 ph[2][3][SYM];                // NCO phase per sample of three symbols, double-buffered (producer warp runs ahead)
             float2 phase_end[2];                 // the phase after the block, renormalised
@@ -352,9 +360,14 @@ __device__ __forceinline__ int vit_butterfly(int stage, int g, int i)
 }
 __device__ __forceinline__ int vit_slot(int s) { return 8 * (s >> 3) + 2 * (s & 3) + ((s >> 2) & 1); }
 
-__device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, const int8_t *in, int len, unsigned g0, unsigned g1, unsigned g2)
+// The groups [g_begin, g_end) of the frame (three steps each; g_end past the last group = to the end).  start_pm: the
+// path metrics to start from, in exchange-buffer order (a previous chunk's sm.pm), or nullptr = all equal (the frame's
+// start, or a chunk's warm-up).  Decisions are stored from group g_store on; the metrics as they stand before that group
+// are copied to sm.chk (chunk verification, viterbi_k9_forward).
+__device__ __noinline__ void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, const int8_t *in, int len, unsigned g0, unsigned g1, unsigned g2,
+                                             int g_begin, int g_store, int g_end, const unsigned short *start_pm)
 {
-    const int steps = len + 64, interval = 32767 / (3 * 127) - 9;
+    const int steps = min(len + 64, 3 * g_end), interval = 32767 / (3 * 127) - 9;
     // sign masks: mk[stage][op][poly], 0xffff in a half whose butterfly has code bit 1 on its (even state, input 0) branch
     unsigned mk[3][2][3];
 #pragma unroll
@@ -369,8 +382,12 @@ __device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, con
         }
     const int my_slot = 8 * (g >> 3) + 2 * (g & 3) + ((g >> 2) & 1);        // vit_slot(g + 32 j) = my_slot + 32 j
     unsigned z0 = 0, z1 = 0, z2 = 0, z3 = 0;                                // (x0|x4), (x1|x5), (x2|x6), (x3|x7), x_i = state 8g+i
-    int next_norm = 0;                                                      // the minimum goes when step % interval == 0
-    for (int base = 0; base < steps; base += VT) {
+    if (start_pm) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(&start_pm[8 * g]);
+        z0 = v.x; z1 = v.y; z2 = v.z; z3 = v.w;
+    }
+    int next_norm = ((3 * g_begin + interval - 1) / interval) * interval;   // the minimum goes when step % interval == 0
+    for (int base = 3 * g_begin; base < steps; base += VT) {
         const int nst = min(VT, steps - base);
         for (int i = g; i < nst; i += 32) {
             int j = len - 32 + base + i;                                    // the input index wraps (tail biting)
@@ -382,6 +399,10 @@ __device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, con
 #pragma unroll 1
         for (int k = 0; k < nst; k += 3) {
             const int ns = min(3, nst - k);                                 // (only the very last group can be short)
+            if (base + k == 3 * g_store && g_store > g_begin) {             // (sm.pm holds what the last exchange left there)
+                *reinterpret_cast<uint4 *>(&sm.chk[8 * g]) = *reinterpret_cast<const uint4 *>(&sm.pm[8 * g]);
+                __syncwarp();                                               // (before any lane's next exchange store)
+            }
             unsigned dword = 0;
 #pragma unroll
             for (int sgi = 0; sgi < 3; sgi++) {
@@ -429,7 +450,7 @@ __device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, con
                     dword |= d << (4 * sgi);
                 }
             }
-            decw[(size_t)((base + k) / 3) * 32 + g] = dword;
+            if (base + k >= 3 * g_store) decw[(size_t)((base + k) / 3) * 32 + g] = dword;
             // back to the exchange buffer.  After a full group: z0 = (u0|u1), z1 = (u2|u3), z2 = (u4|u5), z3 = (u6|u7), u_j = state g + 32 j
             if (ns == 3) {
                 sm.pm[my_slot] = (unsigned short)z0;        sm.pm[my_slot + 32] = (unsigned short)(z0 >> 16);
@@ -470,54 +491,180 @@ __device__ inline void viterbi_k9_warp(AmVitSlot &sm, uint32_t *decw, int g, con
     }
 }
 
-// the survivor bit of new state s after step t, from the decision words of viterbi_k9_warp
-__device__ __forceinline__ unsigned vit_survivor(const uint32_t *decw, int t, unsigned s)
+// The recursion of a whole frame by the CTA.  A short frame (PIDS) is one warp's job.  A long one is cut into a chunk per
+// warp: chunk c > 0 starts VIT_CHUNK_WARMUP steps early from all-equal metrics, keeps no decisions until its own part
+// begins, and notes its metrics at that point.  If they equal - up to one common constant - the metrics the chunk before
+// ended with, every later decision and metric difference of the chunk is what the sequential recursion computes (the
+// recursion only ever looks at differences, and the minimum is subtracted at the same absolute steps), and so by
+// induction from chunk 0 for the whole frame.  The first chunk that fails the comparison, and all after it, are run
+// again one after the other from the true metrics - rare: survivors merge within a few constraint lengths.
+// Leaves the end state (first maximum) in vit[0].state.
+__device__ inline int viterbi_k9_forward(AmVitSlot *vit, uint32_t *decw, int t, const int8_t *in, int len, unsigned g0, unsigned g1, unsigned g2,
+                                         int warmup = VIT_CHUNK_WARMUP)
 {
-    const int grp = t / 3, sgi = t - 3 * grp;
-    const unsigned b = s & 127u, hi = s >> 7;
-    const unsigned ln = sgi == 0 ? b >> 2 : sgi == 1 ? (b & 63u) >> 1 : b & 31u;
-    const unsigned i = sgi == 0 ? b & 3u : sgi == 1 ? (b & 1u) + 2u * (b >> 6) : b >> 5;
-    const unsigned op = sgi == 0 ? i & 1u : i >> 1, half = sgi == 0 ? i >> 1 : i & 1u;
-    return (decw[(size_t)grp * 32 + ln] >> (4u * sgi + 2u * hi + op + 16u * half)) & 1u;
+    constexpr int NW = AM_THREADS / 32;
+    const int steps = len + 64, G = (steps + 2) / 3, wp = t >> 5, lane = t & 31;
+    if (steps < 1024) {
+        if (wp == 0) viterbi_k9_warp(vit[0], decw, lane, in, len, g0, g1, g2, 0, 0, G, nullptr);
+        __syncthreads();
+        return 0;
+    }
+    auto gb = [&](int c) { return (int)((long long)c * G / NW); };
+    {
+        const int b = gb(wp), e = wp == NW - 1 ? G : gb(wp + 1);
+        viterbi_k9_warp(vit[wp], decw, lane, in, len, g0, g1, g2, wp == 0 ? 0 : max(0, b - warmup / 3), b, e, nullptr);
+    }
+    __syncthreads();
+    int bad = NW;
+    for (int c = 1; c < NW && bad == NW; c++) {
+        bool same = true;
+        if (gb(c) - warmup / 3 > 0) {                                        // (a warm-up that reaches the frame's start is the true recursion)
+            const int d0 = (int)vit[c].chk[0] - (int)vit[c - 1].pm[0];
+            for (int i = t; i < 256; i += AM_THREADS) same = same && ((int)vit[c].chk[i] - (int)vit[c - 1].pm[i] == d0);
+        }
+        if (t == 0) vit[0].changed = 0;
+        __syncthreads();
+        if (!same) vit[0].changed = 1;
+        __syncthreads();
+        if (vit[0].changed) bad = c;
+        __syncthreads();
+    }
+    for (int c = bad; c < NW; c++) {
+        if (wp == c) viterbi_k9_warp(vit[c], decw, lane, in, len, g0, g1, g2, gb(c), gb(c), c == NW - 1 ? G : gb(c + 1), vit[c - 1].pm);
+        __syncthreads();
+    }
+    if (t == 0) vit[0].state = vit[NW - 1].state;
+    __syncthreads();
+    return NW - bad;                                                         // chunks that had to be run again
 }
 
-// Traceback by the whole CTA: the steps are cut into AM_THREADS segments and every thread walks its own one backwards.
+// Where viterbi_k9_warp keeps the survivor bit of new state s after a step of stage sgi: lane and bit of the group's word
+__device__ __forceinline__ void vit_where(int sgi, unsigned s, unsigned &ln, unsigned &bit)
+{
+    const unsigned b = s & 127u, hi = s >> 7;
+    ln = sgi == 0 ? b >> 2 : sgi == 1 ? (b & 63u) >> 1 : b & 31u;
+    const unsigned i = sgi == 0 ? b & 3u : sgi == 1 ? (b & 1u) + 2u * (b >> 6) : b >> 5;
+    const unsigned op = sgi == 0 ? i & 1u : i >> 1, half = sgi == 0 ? i >> 1 : i & 1u;
+    bit = 4u * (unsigned)sgi + 2u * hi + op + 16u * half;
+}
+
+// Traceback by the whole CTA: the steps are cut into VIT_WALKERS segments and eight lanes of every warp walk one each,
+// backwards.  A walk is a dependent chain - the survivor bit of the state decides which bit is needed
+// next - but WHICH ROWS of decision words it needs does not depend on the state: the warp brings the next VIT_G groups'
+// rows of each of its walkers into shared memory with coalesced 128-byte asynchronous copies (cp.async, all 32 lanes),
+// one batch of 24 steps ahead of the batch being walked - longer than the memory latency - so the chains read shared
+// memory only and a warp's chains advance in lock-step for the price of one.
 // The state a walk has to start from is only known once the walk of the following segment has arrived - so a walker
 // starts VIT_WARMUP steps further on, from state 0: survivor paths merge going backwards, and by the time it crosses
 // into its own segment it is (almost always) on the decoder's path.  Every walker then checks the state it started its
 // segment from against the state the following segment's walker really arrived at, and walks again from that one if they
 // differ, until nobody had to: the last segment starts from the true end state, so when the round without changes comes
 // every segment was walked from the state the sequential traceback passes through - the output is that of the
-// sequential traceback, whatever the warm-up did.
-__device__ inline int viterbi_k9_traceback(AmVitSlot &sm, const uint32_t *decw, int w, uint8_t *out, int len, int warmup = VIT_WARMUP)
+// sequential traceback, whatever the warm-up did.  Returns the number of repair rounds.
+constexpr int VIT_G = 8, VIT_LW = 8, VIT_WALKERS = VIT_LW * (AM_THREADS / 32);
+struct AmVitRows {
+    uint32_t w[2][AM_THREADS / 32][VIT_LW][VIT_G][32];   // [buffer][warp][walker = lane < VIT_LW][group, newest first][word]
+};
+static_assert((AM_THREADS / 32) * sizeof(AmVitSlot) <= VIT_TEST_SLOTS_BYTES, "stage test kernel's slots");
+static_assert(sizeof(AmVitRows) == 4 * VIT_TB_WORDS, "AmSmem reserves the rows as plain words");
+
+__device__ __forceinline__ void am_copy_async4(uint32_t *smem_dst, const uint32_t *gmem_src)
 {
-    const int steps = len + 64;
-    const int seg = (steps + AM_THREADS - 1) / AM_THREADS;
-    const int lo = w * seg, hi = min(steps, lo + seg);                       // this walker's steps [lo, hi)
-    const bool mine = lo < hi;
-    unsigned start = 0;                                                      // state after step hi - 1
-    if (mine) {
-        const int t0 = min(steps, hi + warmup);
-        unsigned state = t0 == steps ? sm.state : 0u;
-        for (int t = t0 - 1; t >= hi; t--) state = ((state << 1) & 254u) | vit_survivor(decw, t, state);
-        start = state;
-    }
-    bool walk = mine;
-    int round = 0;                                                           // returns the number of repair rounds (0: the warm-up was right)
-    for (; round <= AM_THREADS; round++) {
-        if (walk) {
-            unsigned state = start;
-            for (int t = hi - 1; t >= lo; t--) {
-                if (t >= 32 && t < 32 + len) out[t - 32] = (uint8_t)(state >> 7);
-                state = ((state << 1) & 254u) | vit_survivor(decw, t, state);
-            }
-            sm.ends[w] = (unsigned short)state;                              // state after step lo - 1
+#if defined(NB_EMU)
+    *smem_dst = *gmem_src;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void am_copy_async_commit()
+{
+#if !defined(NB_EMU)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void am_copy_async_wait_but_one()                 // all but the most recent group have landed
+{
+#if !defined(NB_EMU)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+
+// Every lane walks its own steps [from, to) going down, starting in `state` (updated); the decoded bits of the steps
+// below emit_below are written (the others are warm-up).  The 32 lanes of a warp call it together.
+__device__ inline void vit_walk(uint32_t (*rows)[AM_THREADS / 32][VIT_LW][VIT_G][32], int wp, const uint32_t *decw, int lane, int from, int to, int emit_below,
+                                unsigned &state_io, uint8_t *out, int len)
+{
+    const int g_lo = from / 3;
+    int t = to - 1;
+    unsigned state = state_io;
+    // the rows of every lane's groups g_top .. g_top - n + 1 into buffer `buf`
+    auto issue = [&](int buf, int g_top, int n) {
+#pragma unroll 2
+        for (int j = 0; j < VIT_LW; j++) {
+            const int gj = __shfl_sync(0xffffffffu, g_top, j), nj = __shfl_sync(0xffffffffu, n, j);
+#pragma unroll
+            for (int r = 0; r < VIT_G; r++)
+                if (r < nj) am_copy_async4(&rows[buf][wp][j][r][lane], decw + (size_t)(gj - r) * 32 + lane);
         }
+        am_copy_async_commit();
+    };
+    int g_cur = t >= from ? t / 3 : 0, n_cur = t >= from ? min(VIT_G, g_cur - g_lo + 1) : 0;
+    int buf = 0;
+    issue(0, g_cur, n_cur);
+    while (__any_sync(0xffffffffu, n_cur > 0)) {
+        const int g_next = g_cur - n_cur, n_next = (n_cur > 0 && g_next >= g_lo) ? min(VIT_G, g_next - g_lo + 1) : 0;
+        issue(buf ^ 1, g_next, n_next);
+        am_copy_async_wait_but_one();
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < VIT_G; r++) {
+#pragma unroll
+            for (int sgi = 2; sgi >= 0; sgi--) {
+                const int tt = 3 * (g_cur - r) + sgi;
+                const bool on = r < n_cur && tt <= t && tt >= from;
+                unsigned ln, bit;
+                vit_where(sgi, state, ln, bit);
+                const unsigned v = rows[buf][wp][lane & (VIT_LW - 1)][r][ln];
+                const unsigned nxt = ((state << 1) & 254u) | ((v >> bit) & 1u);
+                if (on && tt < emit_below && tt >= 32 && tt < 32 + len) out[tt - 32] = (uint8_t)(state >> 7);
+                state = on ? nxt : state;
+            }
+        }
+        if (n_cur > 0) t = 3 * (g_cur - n_cur + 1) - 1;
+        g_cur = g_next;
+        n_cur = n_next;
+        buf ^= 1;
+        __syncwarp();
+    }
+    state_io = state;
+}
+
+// (not inlined: four call sites in k_am, and the kernel's code should stay within reach of the instruction cache)
+__device__ __noinline__ int viterbi_k9_traceback(AmVitSlot &sm, AmVitRows &rows, const uint32_t *decw, int w, uint8_t *out, int len,
+                                           int warmup = VIT_WARMUP)
+{
+    const int steps = len + 64, lane = w & 31, wp = w >> 5;
+    // walkers: lanes 0 .. VIT_LW-1 of every warp; a short frame (PIDS) is walked by one of them, without any warm-up
+    const int nwalk = steps >= 1024 ? VIT_WALKERS : 1;
+    const int seg = (steps + nwalk - 1) / nwalk;
+    const int id = lane < VIT_LW ? VIT_LW * wp + lane : VIT_WALKERS;         // (other lanes only help loading)
+    const int lo = min(steps, id * seg), hi = min(steps, lo + seg);          // this walker's steps [lo, hi)
+    const bool mine = lo < hi;
+    // warm-up: from `warmup` steps beyond the segment (or from the true end state) down to its upper end
+    const int top = mine ? min(steps, hi + warmup) : hi;
+    unsigned start = top == steps ? sm.state : 0u;
+    vit_walk(rows.w, wp, decw, lane, hi, top, 0, start, out, len);
+    bool walk = mine;
+    int round = 0;                                                           // repair rounds (0: the warm-up was right)
+    for (; round <= VIT_WALKERS; round++) {
+        unsigned st2 = start;
+        vit_walk(rows.w, wp, decw, lane, lo, walk ? hi : lo, steps, st2, out, len);
+        if (walk) sm.ends[id] = (unsigned short)st2;                         // state after step lo - 1
         if (w == 0) sm.changed = 0;
         __syncthreads();
         walk = false;
         if (mine) {
-            const unsigned want = hi == steps ? sm.state : (unsigned)sm.ends[w + 1];
+            const unsigned want = hi == steps ? sm.state : (unsigned)sm.ends[id + 1];
             if (want != start) { start = want; walk = true; }
         }
         if (walk) sm.changed = 1;
@@ -547,10 +694,14 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
     AmSmem &sm = *static_cast<AmSmem *>(L.smem);
     uint32_t *decw = reinterpret_cast<uint32_t *>(w.dec);
     __syncthreads();
-    if (L.lane < 32) viterbi_k9_warp(sm.vit[0], decw, L.lane, in, len, g0, g1, g2);
+    long long tv = AM_T0();
+    const int redone = viterbi_k9_forward(sm.vit, decw, L.lane, in, len, g0, g1, g2);
+    if (L.lane == 0) w.ph_cyc[15] += (unsigned long long)redone;        // chunks of the recursion that had to be run again
+    AM_LAP(w, L, 8, tv);
+    const int rr = viterbi_k9_traceback(sm.vit[0], *reinterpret_cast<AmVitRows *>(sm.tb), decw, L.lane, out, len);
+    if (L.lane == 0) w.ph_cyc[11] += (unsigned long long)rr;             // repair rounds of the segmented traceback, all decodes
     __syncthreads();
-    viterbi_k9_traceback(sm.vit[0], decw, L.lane, out, len);
-    __syncthreads();
+    AM_LAP(w, L, 9, tv);
 #else
     for (int i = L.lane; i < 256; i += L.n) w.pm[0][i] = 0;
     AM_SYNC();
@@ -602,19 +753,12 @@ AM_HD inline void viterbi_k9(AmWork &w, Lanes L, const int8_t *in, uint8_t *out,
 #endif
 }
 
-// P1 and P3 of a frame's last block into separate buffers: on the device the two recursions run side by side, a warp each
+// P1 and P3 of a frame's last block into separate buffers
 AM_HD inline void viterbi_k9_pair(AmWork &w, Lanes L, const VitJob &a, const VitJob &b)
 {
 #if defined(__CUDA_ARCH__)
-    AmSmem &sm = *static_cast<AmSmem *>(L.smem);
-    uint32_t *da = reinterpret_cast<uint32_t *>(w.dec_p1), *db = reinterpret_cast<uint32_t *>(w.dec);
-    __syncthreads();
-    if (L.lane < 32) viterbi_k9_warp(sm.vit[0], da, L.lane, a.in, a.len, a.g0, a.g1, a.g2);
-    else if (L.lane < 64) viterbi_k9_warp(sm.vit[1], db, L.lane - 32, b.in, b.len, b.g0, b.g1, b.g2);
-    __syncthreads();
-    viterbi_k9_traceback(sm.vit[0], da, L.lane, a.out, a.len);
-    viterbi_k9_traceback(sm.vit[1], db, L.lane, b.out, b.len);
-    __syncthreads();
+    viterbi_k9(w, L, a.in, a.out, a.len, a.g0, a.g1, a.g2);              // (each is the whole CTA's job: chunks of the recursion, segments of the traceback)
+    viterbi_k9(w, L, b.in, b.out, b.len, b.g0, b.g1, b.g2);
 #else
     viterbi_k9(w, L, a.in, a.out, a.len, a.g0, a.g1, a.g2);
     viterbi_k9(w, L, b.in, b.out, b.len, b.g0, b.g1, b.g2);
@@ -1313,6 +1457,9 @@ AM_HD inline void process_window(AmState &st, AmWork &w, const AmTables &tb, con
 #endif
     AM_SYNC();
 
+#if defined(__CUDA_ARCH__)
+    if (st.state == ST_FINE && L.lane == 0) w.ph_cyc[10] += (unsigned long long)(clock64() - tlap);
+#endif
     AM_LAP(w, L, 0, tlap);
     angle = (float)((double)angle - 2 * PI * st.cfo);                                     // acquire.c:164-168
     st.phase = cmul(st.phase, cexpj((float)(-(SYM / 2 - samperr)) * angle / (float)FFT));

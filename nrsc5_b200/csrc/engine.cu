@@ -483,7 +483,12 @@ __global__ void __launch_bounds__(nbam::AM_THREADS) k_am(DevPtrs p, EngineDims d
                                                          const nbam::AmTables *tb, int max_blocks, int last_pass)
 {
     const int s = blockIdx.x;
-    __shared__ nbam::AmSmem sm;
+#if defined(NB_EMU)
+    unsigned char *am_smem_raw = emu::dyn_smem();
+#else
+    extern __shared__ __align__(16) unsigned char am_smem_raw[];     // sizeof(nbam::AmSmem) bytes (above the 48 KB a static array may have)
+#endif
+    nbam::AmSmem &sm = *reinterpret_cast<nbam::AmSmem *>(am_smem_raw);
     __shared__ GfTab gf;
     const nbam::Lanes L = { (int)threadIdx.x, nbam::AM_THREADS, &sm };
     gf_tab_load(gf, (int)threadIdx.x, nbam::AM_THREADS);
@@ -561,16 +566,26 @@ __global__ void k_rs_test(uint8_t *blocks, int *rc, int n)        // one warp pe
 // stage entry point: the AM decoder (am.cuh: viterbi_k9_warp + viterbi_k9_traceback) on `njobs` independent tail-biting
 // frames of `len` bits, one CTA each; rounds[j] = repair rounds the segmented traceback needed
 __global__ void __launch_bounds__(nbam::AM_THREADS) k_am_vit_test(const int8_t *in, uint8_t *out, uint32_t *dec, size_t dec_words, int len,
-                                                                  unsigned g0, unsigned g1, unsigned g2, int warmup, int *rounds)
+                                                                  unsigned g0, unsigned g1, unsigned g2, int warmup, int chunk_warmup, int *rounds)
 {
 #if defined(__CUDA_ARCH__)                                                    // (the decoder's device branch does not exist in the host pass)
-    __shared__ nbam::AmVitSlot slot;
+#if defined(NB_EMU)
+    unsigned char *vit_test_smem = emu::dyn_smem();
+#else
+    extern __shared__ __align__(16) unsigned char vit_test_smem[];    // AmVitSlot + AmVitRows
+#endif
+    nbam::AmVitSlot *vit = reinterpret_cast<nbam::AmVitSlot *>(vit_test_smem);
+    nbam::AmVitRows &rows = *reinterpret_cast<nbam::AmVitRows *>(vit_test_smem + nbam::VIT_TEST_SLOTS_BYTES);
     const int j = blockIdx.x, t = threadIdx.x;
     uint32_t *decw = dec + (size_t)j * dec_words;
-    if (t < 32) nbam::viterbi_k9_warp(slot, decw, t, in + (size_t)j * 3 * len, len, g0, g1, g2);
-    __syncthreads();
-    const int r = nbam::viterbi_k9_traceback(slot, decw, t, out + (size_t)j * len, len, warmup);
-    if (t == 0) rounds[j] = r;
+    const long long c0 = clock64();
+    const int redone = nbam::viterbi_k9_forward(vit, decw, t, in + (size_t)j * 3 * len, len, g0, g1, g2, chunk_warmup);
+    const long long c1 = clock64();
+    const int r = nbam::viterbi_k9_traceback(vit[0], rows, decw, t, out + (size_t)j * len, len, warmup);
+    if (t == 0) {
+        rounds[j] = r | (redone << 16);
+        if (g_dbg & 8) printf("k9 job %d: recursion %lld cycles (%d chunks again), traceback %lld cycles, %d repair rounds\n", j, c1 - c0, redone, clock64() - c1, r);
+    }
 #endif
 }
 
@@ -1127,6 +1142,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     }
     if (cudaFuncSetAttribute(k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_am, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nbam::AmSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_vitc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vitc_emit_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(k_v64_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V64_EMIT_SMEM) != cudaSuccess) {
         nrsc5b_destroy(e);
@@ -1643,7 +1659,7 @@ static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true
     if (last_pass) cudaMemsetAsync(reinterpret_cast<uint8_t *>(e->dp.ctl) + offsetof(EngineCtl, more), 0, sizeof(unsigned), e->stream);
     if (e->am_st) {                                        // AM: one kernel does the whole chain, window after window
         const bool l2 = e->l2 && e->dims.l2;              // with L2 on, a launch stops after 16 blocks: its frames fit the queue
-        k_am<<<e->dims.nstreams, nbam::AM_THREADS, 0, e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20,
+        k_am<<<e->dims.nstreams, nbam::AM_THREADS, sizeof(nbam::AmSmem), e->stream>>>(e->dp, e->dims, e->am_st, e->am_work, e->am_tb, l2 ? nbam::AM_L2_BLOCKS : 1 << 20,
                                                      last_pass ? 1 : 0);
         e->stats.kernel_launches += 1;
         if (l2) {
@@ -1759,17 +1775,19 @@ extern "C" int nrsc5b_get_phase_cycles(nrsc5b_engine_t *e, unsigned long long *c
 }
 
 /* AM: SM cycles k_am spent per phase, summed over streams since the last reset / rewind (thread 0's clock): window +
- * coarse acquisition, first demodulation pass (carrier), second pass (bins), sync + slicing, PIDS, P1 group incl. the two
- * following, P3 Viterbi, interleaver. */
-extern "C" int nrsc5b_get_am_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc8)
+ * coarse acquisition, first demodulation pass (carrier), second pass (bins), sync + slicing, PIDS, P1/P3 group incl. the two
+ * following, P3 post-processing, interleaver; then, across all decodes: K=9 recursion, traceback; window load of a block in
+ * fine sync; spare. */
+extern "C" int nrsc5b_get_am_phase_cycles(nrsc5b_engine_t *e, unsigned long long *cyc12)
 {
-    if (!e || !cyc8 || !e->am_work) return NRSC5B_EINVAL;
+    if (!e || !cyc12 || !e->am_work) return NRSC5B_EINVAL;
     CK(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < 8; i++) cyc8[i] = 0;
+    for (int i = 0; i < 12; i++) cyc12[i] = 0;
     for (int s = 0; s < e->dims.nstreams; s++) {
-        unsigned long long v[8];
+        unsigned long long v[16];
         CK(cudaMemcpy(v, reinterpret_cast<uint8_t *>(e->am_work + s) + offsetof(nbam::AmWork, ph_cyc), sizeof(v), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < 8; i++) cyc8[i] += v[i];
+        for (int i = 0; i < 12; i++) cyc12[i] += v[i];
+        if (getenv("NRSC5_B200_TRACE") && s == 0) fprintf(stderr, "nrsc5_b200 trace: AM stream 0 traceback Mcycles {warm-up %.2f, walks %.2f, checks %.2f}, until return %.2f, slot 8 %.2f slot 9 %.2f\n", v[12] * 1e-6, v[13] * 1e-6, v[14] * 1e-6, v[15] * 1e-6, v[8] * 1e-6, v[9] * 1e-6);
     }
     return NRSC5B_OK;
 }
@@ -2340,7 +2358,7 @@ extern "C" int nrsc5b_rs_decode(int device, uint8_t *blocks, int *rcs, int n)
  * calls it): njobs frames of len bits, in = 3 * len hard symbols each (-1, 0 = punctured, +1), out = len bits each.
  * warmup <= 0: the production warm-up of the segmented traceback; rounds (optional, [njobs]) = repair rounds it took. */
 extern "C" int nrsc5b_viterbi_k9(int device, const int8_t *in, uint8_t *out, int len, int njobs, unsigned g0, unsigned g1, unsigned g2,
-                                 int warmup, int *rounds)
+                                 int warmup, int chunk_warmup, int *rounds)
 {
     if (!in || !out || len < 32 || njobs < 1) return NRSC5B_EINVAL;
     for (size_t i = 0; i < (size_t)njobs * 3 * len; i++)
@@ -2357,7 +2375,10 @@ extern "C" int nrsc5b_viterbi_k9(int device, const int8_t *in, uint8_t *out, int
     CK(cudaMalloc(&dd, (size_t)njobs * dec_words * 4));
     CK(cudaMalloc(&dr, (size_t)njobs * sizeof(int)));
     CK(cudaMemcpy(di, in, (size_t)njobs * 3 * len, cudaMemcpyHostToDevice));
-    k_am_vit_test<<<njobs, nbam::AM_THREADS>>>(di, dout, dd, dec_words, len, g0, g1, g2, warmup > 0 ? warmup : nbam::VIT_WARMUP, dr);
+    const size_t smem = nbam::VIT_TEST_SLOTS_BYTES + 4 * (size_t)nbam::VIT_TB_WORDS;
+    CK(cudaFuncSetAttribute(k_am_vit_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_am_vit_test<<<njobs, nbam::AM_THREADS, smem>>>(di, dout, dd, dec_words, len, g0, g1, g2, warmup > 0 ? warmup : nbam::VIT_WARMUP,
+                                                 chunk_warmup > 0 ? chunk_warmup : nbam::VIT_CHUNK_WARMUP, dr);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dout, (size_t)njobs * len, cudaMemcpyDeviceToHost));
     if (rounds) CK(cudaMemcpy(rounds, dr, (size_t)njobs * sizeof(int), cudaMemcpyDeviceToHost));

@@ -275,9 +275,10 @@ class Engine:
         return {k: (int(c[i]), int(n[i])) for i, k in enumerate(names)}
 
     def am_phase_cycles(self):
-        c = (ctypes.c_ulonglong * 8)()
+        c = (ctypes.c_ulonglong * 12)()
         _check(self._L.nrsc5b_get_am_phase_cycles(self._h, c), "nrsc5b_get_am_phase_cycles")
-        names = ["window_acquire", "pass1_carrier", "pass2_bins", "sync_slicing", "pids", "p1_p3_interleaver", "of_which_p3", "of_which_interleaver"]
+        names = ["window_acquire", "pass1_carrier", "pass2_bins", "sync_slicing", "pids", "p1_p3_interleaver", "of_which_p3_post",
+                 "of_which_interleaver", "all_decodes_k9_recursion", "all_decodes_traceback", "window_load_fine_blocks", "traceback_repair_rounds"]
         return {k: int(c[i]) for i, k in enumerate(names)}
 
     def push_cu8(self, stream: int, samples):
@@ -428,9 +429,9 @@ def rs_decode(blocks: np.ndarray, device: int = 0):
     return rc, b
 
 
-def viterbi_k9(sym: np.ndarray, gens=(0o561, 0o657, 0o711), warmup: int = 0, device: int = 0):
+def viterbi_k9(sym: np.ndarray, gens=(0o561, 0o657, 0o711), warmup: int = 0, chunk_warmup: int = 0, device: int = 0):
     """The AM chain's K=9 decoder on a batch of frames: sym int8 [njobs, 3 * len] of -1 / 0 / +1; returns (bits uint8
-    [njobs, len], repair rounds of the segmented traceback int32 [njobs])."""
+    [njobs, len], repair rounds of the segmented traceback int32 [njobs], chunks of the recursion run again int32 [njobs])."""
     a = np.ascontiguousarray(sym, dtype=np.int8)
     a = a.reshape(1, -1) if a.ndim == 1 else a
     njobs, n = a.shape[0], a.shape[1] // 3
@@ -438,9 +439,10 @@ def viterbi_k9(sym: np.ndarray, gens=(0o561, 0o657, 0o711), warmup: int = 0, dev
     rounds = np.empty(njobs, dtype=np.int32)
     L = load_library()
     L.nrsc5b_viterbi_k9.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
-                                    ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_void_p]
-    _check(L.nrsc5b_viterbi_k9(device, a.ctypes.data, out.ctypes.data, n, njobs, *gens, warmup, rounds.ctypes.data), "nrsc5b_viterbi_k9")
-    return out, rounds
+                                    ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    _check(L.nrsc5b_viterbi_k9(device, a.ctypes.data, out.ctypes.data, n, njobs, *gens, warmup, chunk_warmup, rounds.ctypes.data),
+           "nrsc5b_viterbi_k9")
+    return out, rounds & 0xffff, rounds >> 16
 
 
 def fft2048(x: np.ndarray, device: int = 0) -> np.ndarray:

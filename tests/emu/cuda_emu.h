@@ -35,6 +35,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __constant__
 #define __launch_bounds__(...)

@@ -171,8 +171,8 @@ def test_viterbi_k9_equals_the_reference_decoder(n, gens):
     """The AM decoder alone (radix-8 single-warp recursion + segmented traceback, csrc/am.cuh) against the oracle's
     conv_dec restatement with K = 9: clean, noisy and pure-noise frames of every length the chain uses (PIDS 80, P1 3750,
     P3 24000; 3751 / 3752 for the two shapes of a short last group) - bit for bit, ties and all.  Then the same frames
-    with a warm-up of 3 steps, which leaves most traceback walkers on a wrong path: the repair rounds must bring back the
-    sequential traceback's output."""
+    with warm-ups of 3 steps, which leave most traceback walkers on a wrong path and most chunks of the recursion with
+    wrong metrics: the repair rounds / the sequential re-run must bring back the reference decoder's output."""
     from nrsc5_b200 import engine as eng
     rng = np.random.default_rng(n)
     njobs = 6 if n > 4000 else 12
@@ -181,9 +181,10 @@ def test_viterbi_k9_equals_the_reference_decoder(n, gens):
     junk = rng.integers(-1, 2, (njobs - 2 * (njobs // 3), 3 * n)).astype(np.int8)
     sym = np.concatenate([clean, noisy, junk])
     want = np.stack([port.viterbi(sym[j], k=9, gens=gens) for j in range(sym.shape[0])])
-    got, rounds = eng.viterbi_k9(sym, gens)
+    got, rounds, redone = eng.viterbi_k9(sym, gens)
     assert np.array_equal(got, want), np.argwhere(got != want)[:5]
-    got3, rounds3 = eng.viterbi_k9(sym, gens, warmup=3)
+    got3, rounds3, redone3 = eng.viterbi_k9(sym, gens, warmup=3, chunk_warmup=3)
     assert np.array_equal(got3, want)
     if n >= 3750:
-        assert rounds3.max() >= 1 and rounds3.max() >= rounds.max()          # the repair loop really ran
+        assert rounds3.max() >= 1 and rounds3.max() >= rounds.max()          # the traceback's repair loop really ran
+        assert redone3.max() >= 1 and redone[: 2 * (njobs // 3)].max() == 0   # and so did the recursion's; decodable frames never need it
