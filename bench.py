@@ -282,7 +282,8 @@ def am_leg(args, engine_factory=None):
     try:
         pc = e.am_phase_cycles()                          # of the last rewind -> process
         nblk = max(1, int(e.stats().blocks))
-        am_phases = {k: round(v / nblk / 1965.0, 2) for k, v in pc.items()}    # us per stream-block at 1965 MHz
+        am_phases = {k: round(v / nblk / 1965.0, 2) for k, v in pc.items() if k != "traceback_repair_rounds"}    # us per stream-block at 1965 MHz
+        am_phases["traceback_repair_rounds_per_block"] = round(pc.get("traceback_repair_rounds", 0) / nblk, 4)   # (a count, not a time)
     except Exception:                                     # noqa: BLE001
         am_phases = None
     # the unmodified reference on this host's cores: one process per channel (cs16, AM mode), 3 passes each
@@ -306,9 +307,9 @@ def am_leg(args, engine_factory=None):
     out = {"value": samples * steps / res / 1e6, "unit": "Msamples/s (cs16 complex, 46 511.72 S/s per channel)",
            "roofline": {"bound": "hbm", "kernel": "k_am (whole AM chain, one CTA per stream)", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
-                        "note": "latency-bound by construction: the NCO phase chain (17 280 dependent complex multiplications per block) "
-                                "and the K=9 add-compare-select (one barrier per trellis step) are sequential per stream; 256 streams "
-                                "put at most two CTAs on an SM", "blocks_total": blocks},
+                        "note": "latency-bound by construction: per stream the NCO phase chain (17 280 dependent complex multiplications "
+                                "per block, one warp) and the K=9 recursion (a verified chunk per warp, three trellis steps per metric "
+                                "exchange) are dependent chains; 256 streams put at most two CTAs on an SM", "blocks_total": blocks},
            "cpu_baseline": cpu, "phases_us_per_stream_block_at_1965MHz": am_phases,
            "x_realtime": samples * steps / res / 46511.71875, "ms_per_step": 1e3 * res / steps,
            "e2e": {"value": samples * steps / tot / 1e6, "ms_per_step": 1e3 * tot / steps, "x_realtime": samples * steps / tot / 46511.71875,

@@ -75,6 +75,7 @@ constexpr int AM_THREADS = 128;                 // k_am: threads per stream (one
 struct Lanes {
     int lane, n;
     void *smem;                                 // device: the CTA's AmSmem
+    int dbg;                                    // experiment switches (nrsc5b_debug_set), 0 in production
 };
 
 // ---- complex helpers in the reference's (gcc, no FMA) evaluation order ----
@@ -1311,7 +1312,7 @@ __device__ inline void demod_pass(AmWork &w, const AmTables &tb, Lanes L, int sa
                 }
             }
             const int sym = 3 * (i - 1) + cw;
-            if (sym < BLK) {
+            if (sym < BLK && !(L.dbg & 16)) {               // (bit 4: timing experiment, the NCO chain alone - results are wrong)
                 const float2 *pv = sm.dem.ph[(i - 1) & 1][cw];
                 float2 *f = sm.dem.fft[cw];
                 for (int j = lane; j < FFT; j += 32) {

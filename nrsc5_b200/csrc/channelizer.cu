@@ -225,14 +225,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_channelize(const __grid_constant
                 for (int q = 0; q < 8; q++) {
                     const int ch = group * GROUP + c0 + q;
                     if (ch >= p.nch || n >= p.nout) continue;
-                    const long long ar = 256ll * (int)v[4 * q + 0] + (int)v[4 * q + 2] - p.corr[2 * ch + 0];
-                    const long long ai = 256ll * (int)v[4 * q + 1] + (int)v[4 * q + 3] - p.corr[2 * ch + 1];
-                    const long long vr = (ar + (1ll << (SHIFT1 - 1))) >> SHIFT1, vi = (ai + (1ll << (SHIFT1 - 1))) >> SHIFT1;
-                    const int qi = (int)(((long long)p.rot_step[ch] * nmod) % PERIOD);
+                    // 32-bit arithmetic throughout: 256 * hi + lo wraps, the filter output itself is bounded by
+                    // 128 * sum(|Wr| + |Wi|) < 2^28 (checked when the tables are made), so the wrapped sum is the value;
+                    // after the shift a component is below 2^15 and the rotation's two products stay below 2^31
+                    const int ar = (int)(256u * v[4 * q + 0] + v[4 * q + 2] - (uint32_t)p.corr[2 * ch + 0]);
+                    const int ai = (int)(256u * v[4 * q + 1] + v[4 * q + 3] - (uint32_t)p.corr[2 * ch + 1]);
+                    const int vr = (ar + (1 << (SHIFT1 - 1))) >> SHIFT1, vi = (ai + (1 << (SHIFT1 - 1))) >> SHIFT1;
+                    const int qi = (int)(((unsigned)p.rot_step[ch] * (unsigned)nmod) % (unsigned)PERIOD);   // < 11907^2 < 2^32
                     const short2 ph = __ldg(&p.phasor[qi]);
-                    long long zr = vr * ph.x + vi * ph.y, zi = vi * ph.x - vr * ph.y;          // v * conj(P)
-                    zr = (zr + (1ll << 14)) >> 15;
-                    zi = (zi + (1ll << 14)) >> 15;
+                    int zr = vr * ph.x + vi * ph.y, zi = vi * ph.x - vr * ph.y;                // v * conj(P)
+                    zr = (zr + (1 << 14)) >> 15;
+                    zi = (zi + (1 << 14)) >> 15;
                     zr = zr > 32767 ? 32767 : (zr < -32768 ? -32768 : zr);
                     zi = zi > 32767 ? 32767 : (zi < -32768 ? -32768 : zi);
                     const uint32_t packed = (uint32_t)(uint16_t)(int16_t)zr | ((uint32_t)(uint16_t)(int16_t)zi << 16);
@@ -312,7 +315,7 @@ static void make_tables(const int *offsets, int nch, std::vector<short2> &phasor
         const int m = offsets[k];
         const long long step = (((long long)50 * m) % PERIOD + PERIOD) % PERIOD;
         if (rot) (*rot)[k] = (int)((((long long)1600 * m) % PERIOD + PERIOD) % PERIOD);
-        long long swr = 0, swi = 0;
+        long long swr = 0, swi = 0, sabs = 0;
         const int g = k / GROUP, cl = k % GROUP;
         for (int u = 0; u < TAPS; u++) {
             // W_k[u] = 2^19 h[255-u] e^{-j 2 pi 50 m u / 11907}, from the integer phasor table
@@ -323,6 +326,7 @@ static void make_tables(const int *offsets, int nch, std::vector<short2> &phasor
             taps[((size_t)k * TAPS + u) * 2 + 1] = (int16_t)wi;
             swr += wr;
             swi += wi;
+            sabs += (wr < 0 ? -wr : wr) + (wi < 0 ? -wi : wi);
             if (!w) continue;
             // rows of B: real = (Wr, -Wi) against (xr, xi); imaginary = (Wi, Wr); each 16-bit value as signed high and low bytes
             const int vals[2][2] = { { wr, -wi }, { wi, wr } };
@@ -337,6 +341,8 @@ static void make_tables(const int *offsets, int nch, std::vector<short2> &phasor
                     (*w)[base + (size_t)(4 * cl + 2 + part) * CHUNK + b] = (int8_t)lo;
                 }
         }
+        // the kernel's epilogue computes in 32 bits (k_channelize): the filter output must stay below 2^28
+        if (128 * sabs >= (1ll << 28)) { fprintf(stderr, "nrsc5_b200: channeliser taps too large for the 32-bit epilogue\n"); abort(); }
         if (corr) {
             (*corr)[2 * k + 0] = 127ll * (swr - swi);
             (*corr)[2 * k + 1] = 127ll * (swi + swr);

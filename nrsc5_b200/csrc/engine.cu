@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(nbam::AM_THREADS) k_am(DevPtrs p, EngineDims d
 #endif
     nbam::AmSmem &sm = *reinterpret_cast<nbam::AmSmem *>(am_smem_raw);
     __shared__ GfTab gf;
-    const nbam::Lanes L = { (int)threadIdx.x, nbam::AM_THREADS, &sm };
+    const nbam::Lanes L = { (int)threadIdx.x, nbam::AM_THREADS, &sm, g_dbg };
     gf_tab_load(gf, (int)threadIdx.x, nbam::AM_THREADS);
     __syncthreads();
     StreamState &fs = p.st[s];

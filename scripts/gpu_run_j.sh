@@ -17,7 +17,7 @@ san mp3 racecheck 420 python scripts/sanitize_case.py mp3
 san cluster memcheck 300 python scripts/sanitize_case.py mp1 2 1
 san cluster racecheck 420 python scripts/sanitize_case.py mp1 2 1
 san am memcheck 300 python scripts/sanitize_am.py
-san am racecheck 600 python scripts/sanitize_am.py
+san am racecheck 500 python scripts/sanitize_am.py
 san chan memcheck 300 python -m pytest tests/test_channelizer.py -q -m gpu -k "kernel_equals" --timeout 280
 ( time python bench.py ) > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err
 tail -c 1500 gpurun_out/r2j_bench.json
