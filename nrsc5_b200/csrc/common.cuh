@@ -119,6 +119,7 @@ struct StreamState {
     unsigned long long sy_cyc[6];
     // history of the coarse band-pass FIR: the last 31 samples it was fed
     short bp_hist[31][2];
+    short bp_hist_next[31][2];     // ... of the window being acquired (front_acq_tiles), taken over once all its tiles are done
 };
 
 struct EngineDims {
@@ -171,6 +172,7 @@ struct DevPtrs {
     float2 *bins;              // [S][32][534]
     int8_t *pm;                // [S][16][23040]
     short2 *ydec;              // [S][71280]   decimated window (coarse acquisition scratch)
+    float2 *acq_sums;          // [S][2160]    cyclic-prefix correlation per sample offset (coarse acquisition)
     float2 *tbuf;              // [S][71280]   band-passed window (coarse acquisition scratch)
     int8_t *vit_in;            // [S][438528]
     uint2 *vit_dec;            // [S][146240]

@@ -964,6 +964,7 @@ extern "C" int nrsc5b_create(nrsc5b_engine_t **out, const nrsc5b_config_t *cfg)
     DA(bins, float2, (size_t)S * BLK * NBINS);
     DA(pm, int8_t, (size_t)S * 16 * PM_BLOCK);
     DA(ydec, short2, (size_t)S * NACQ);
+    DA(acq_sums, float2, (size_t)S * NSYM);
     DA(tbuf, float2, (size_t)S * NACQ);
     DA(vit_in, int8_t, (size_t)S * P1_VIT);
     DA(vit_dec, uint2, (size_t)S * P1_NCH * CH_LEN);

@@ -244,11 +244,12 @@ __device__ __forceinline__ void fill_nco(const DevPtrs &p, float2 *nco, float th
 }
 
 // Returns false (uniformly) when the stream has no complete 33-symbol window buffered.
-__device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, float2 *nco, int t)
+// prep, first part (the stream's owner CTA): does the stream have a whole window, and in which state does the block start?
+// Returns 0 = nothing to do, 1 = a block in fine sync, 2 = a block that starts with coarse acquisition.
+__device__ int front_prep_begin(const DevPtrs &p, const EngineDims &d, int s, int t)
 {
     StreamState &st = p.st[s];
-    __shared__ int sh_active, sh_samperr;
-    __shared__ float sh_angle, sh_theta;
+    __shared__ int sh_active;
     if (t == 0) {
         if (st.force_state >= 0) {
             set_state(p, d, s, st.force_state);
@@ -269,72 +270,104 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
             }
         }
         st.active = act;
-        sh_active = act;
+        sh_active = act ? (st.state == ST_FINE ? 1 : 2) : 0;
         if (act) atomicAdd(&p.ctl->progress, 1ull);
     }
     __syncthreads();
-    if (!sh_active) return false;
+    const int mode = sh_active;
+    __syncthreads();
+    return mode;
+}
 
+// Coarse acquisition, the part that is spread over the stream's CTAs (one, or the `nranks` of its cluster):
+// the 71280-sample window in tiles - cu8 words -> shared memory (coalesced), halfband /2 (input.c:52-94), 32-tap
+// symmetric Q15 band-pass (acquire.c:120-127, firdecim_q15.c:95-109) -> float window in `tb`; CTA `rank` takes every
+// nranks-th tile.  (The window's last 31 band-pass inputs become the next window's history: parked in bp_hist_next,
+// because the CTA with the first tile may not have read the old history yet.)
+__device__ void front_acq_tiles(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, int t, int rank, int nranks)
+{
+    StreamState &st = p.st[s];
     const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
-    const int state_in = st.state;
-    if (state_in != ST_FINE) {
-        float2 *tb = p.tbuf + (size_t)s * NACQ;
-        const long long start = st.start;
-        const uint32_t *iqw = reinterpret_cast<const uint32_t *>(iq);
-        // the 71280-sample window in tiles: cu8 words -> shared memory (coalesced), halfband /2 (input.c:52-94),
-        // 32-tap symmetric Q15 band-pass (acquire.c:120-127, firdecim_q15.c:95-109) -> float window in `tb`
-        for (int i0 = 0; i0 < NACQ; i0 += ACQ_TILE) {
-            const int L = min(ACQ_TILE, NACQ - i0);
-            const long long w0 = start + i0 - 38;                 // word of halfband output i0-31's first input
-            for (int v = t; v < L + 38; v += FRONT_THREADS) {
-                const long long a = w0 + v;
-                // before the stream starts the decimator sees zeros = byte 127; through L2 only (asynchronous pushes)
-                sm.words[v] = a >= 0 ? __ldcg(iqw + a) : (d.cs16 ? 0u : 0x7f7f7f7fu);
-            }
-            __syncthreads();
-            for (int k = t; k < L + 31; k += FRONT_THREADS) {
-                if (i0 == 0 && k < 31) {                          // history: the last 31 outputs of the previous window
-                    sm.ytile[k] = make_short2(st.bp_hist[k][0], st.bp_hist[k][1]);
-                } else if (d.cs16) {                              // already decimated: the sample itself
-                    const uint32_t w = sm.words[k + 7];
-                    sm.ytile[k] = make_short2((short)(w & 0xffff), (short)(w >> 16));
-                } else {
-                    const int2 h = halfband_words(sm.words + k);
-                    sm.ytile[k] = make_short2((short)h.x, (short)h.y);
-                }
-            }
-            __syncthreads();
-            for (int j = t; j < L; j += FRONT_THREADS) {
-                const short2 *yy = sm.ytile + j;                  // yy[k] = y[i - 31 + k]
-                short accr = 0, acci = 0;
-#pragma unroll 5
-                for (int k = 1; k < 16; k++) {
-                    const short2 a = yy[k], b = yy[32 - k];
-                    accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
-                    acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
-                }
-                const short2 c = yy[16];
-                accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
-                acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
-                tb[i0 + j] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
-            }
-            if (i0 + L == NACQ && t < 31) {                       // keep the window's last 31 outputs as history
-                const short2 v = sm.ytile[L + t];
-                st.bp_hist[t][0] = v.x;
-                st.bp_hist[t][1] = v.y;
-            }
-            __syncthreads();
+    float2 *tb = p.tbuf + (size_t)s * NACQ;
+    const long long start = nranks > 1 ? __ldcg(&st.start) : st.start;
+    const uint32_t *iqw = reinterpret_cast<const uint32_t *>(iq);
+    for (int i0 = rank * ACQ_TILE; i0 < NACQ; i0 += nranks * ACQ_TILE) {
+        const int L = min(ACQ_TILE, NACQ - i0);
+        const long long w0 = start + i0 - 38;                 // word of halfband output i0-31's first input
+        for (int v = t; v < L + 38; v += FRONT_THREADS) {
+            const long long a = w0 + v;
+            // before the stream starts the decimator sees zeros = byte 127; through L2 only (asynchronous pushes)
+            sm.words[v] = a >= 0 ? __ldcg(iqw + a) : (d.cs16 ? 0u : 0x7f7f7f7fu);
         }
-        // cyclic-prefix correlation per sample offset (acquire.c:129-134)
-        for (int i = t; i < NSYM; i += FRONT_THREADS) {
-            float2 acc = make_float2(0.f, 0.f);
-            for (int j = 0; j < BLK; j++) {
-                float2 a = tb[i + j * NSYM], b = tb[i + j * NSYM + NFFT];
-                float2 pr = cmulf(a, make_float2(b.x, -b.y));
-                acc.x += pr.x;
-                acc.y += pr.y;
+        __syncthreads();
+        for (int k = t; k < L + 31; k += FRONT_THREADS) {
+            if (i0 == 0 && k < 31) {                          // history: the last 31 outputs of the previous window
+                sm.ytile[k] = make_short2(st.bp_hist[k][0], st.bp_hist[k][1]);
+            } else if (d.cs16) {                              // already decimated: the sample itself
+                const uint32_t w = sm.words[k + 7];
+                sm.ytile[k] = make_short2((short)(w & 0xffff), (short)(w >> 16));
+            } else {
+                const int2 h = halfband_words(sm.words + k);
+                sm.ytile[k] = make_short2((short)h.x, (short)h.y);
             }
-            sm.sums[i] = acc;
+        }
+        __syncthreads();
+        for (int j = t; j < L; j += FRONT_THREADS) {
+            const short2 *yy = sm.ytile + j;                  // yy[k] = y[i - 31 + k]
+            short accr = 0, acci = 0;
+#pragma unroll 5
+            for (int k = 1; k < 16; k++) {
+                const short2 a = yy[k], b = yy[32 - k];
+                accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
+                acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
+            }
+            const short2 c = yy[16];
+            accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
+            acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
+            tb[i0 + j] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
+        }
+        if (i0 + L == NACQ && t < 31) {                       // the window's last 31 outputs: the next window's history
+            const short2 v = sm.ytile[L + t];
+            st.bp_hist_next[t][0] = v.x;
+            st.bp_hist_next[t][1] = v.y;
+        }
+        __syncthreads();
+    }
+}
+
+// cyclic-prefix correlation per sample offset (acquire.c:129-134): CTA `rank` takes its share of the 2160 offsets (each
+// offset's sum is one thread's, in the reference's order) and leaves them in global memory for the owner
+__device__ void front_acq_corr(const DevPtrs &p, int s, int t, int rank, int nranks)
+{
+    const float2 *tb = p.tbuf + (size_t)s * NACQ;
+    float2 *sums = p.acq_sums + (size_t)s * NSYM;
+    const int lo = rank * NSYM / nranks, hi = (rank + 1) * NSYM / nranks;
+    for (int i = lo + t; i < hi; i += FRONT_THREADS) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int j = 0; j < BLK; j++) {
+            const float2 a = __ldcg(&tb[i + j * NSYM]), b = __ldcg(&tb[i + j * NSYM + NFFT]);   // (written by other SMs too)
+            float2 pr = cmulf(a, make_float2(b.x, -b.y));
+            acc.x += pr.x;
+            acc.y += pr.y;
+        }
+        sums[i] = acc;
+    }
+}
+
+// prep, last part (owner CTA): timing and angle of the block - from the correlation sums when acquiring (mode 2) -,
+// sync_adjust, the block's NCO table and REC_BLOCK record
+__device__ void front_prep_finish(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, float2 *nco, int t, int mode)
+{
+    StreamState &st = p.st[s];
+    __shared__ int sh_samperr;
+    __shared__ float sh_angle, sh_theta;
+    const int state_in = st.state;
+    if (mode == 2) {
+        const float2 *gs = p.acq_sums + (size_t)s * NSYM;
+        for (int i = t; i < NSYM; i += FRONT_THREADS) sm.sums[i] = __ldcg(&gs[i]);
+        if (t < 31) {
+            st.bp_hist[t][0] = __ldcg(&st.bp_hist_next[t][0]);
+            st.bp_hist[t][1] = __ldcg(&st.bp_hist_next[t][1]);
         }
         __syncthreads();
         // pulse-shaped sliding sum and arg-max (acquire.c:136-151)
@@ -427,7 +460,6 @@ __device__ bool front_prep(const DevPtrs &p, const EngineDims &d, int s, PrepSme
     // nco[j] = shape[j] * exp(j*theta*j); the per-symbol phase is applied to the kept bins
     fill_nco(p, nco, sh_theta, t);
     __syncthreads();
-    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -1245,20 +1277,38 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
             }
         };
         // a completed interleaver matrix is decoded (and its header checked) before the next block
-        bool go = false;
+        // blk_go: 0 = the pass is over, 1 = demodulate the block (its parameters are in place), 2 = coarse acquisition
+        // first - which the stream's CTAs share
+        int mode = 0;
         if (owner) {
-            go = nb < max_blocks && !st.p1_ready;
-            if (go) go = front_prep(p, d, s, sm.u.prep, sm.nco, t);
+            if (nb < max_blocks && !st.p1_ready) mode = front_prep_begin(p, d, s, t);
+            if (mode == 1) front_prep_finish(p, d, s, sm.u.prep, sm.nco, t, 1);
         }
         if (CL) {
             if (owner && t == 0) {
-                st.blk_go = go ? 1 : 0;
+                st.blk_go = mode;
                 __threadfence();
             }
             cluster_barrier();                        // the helpers read the block's parameters behind this barrier
-            if (!owner) go = __ldcg(&st.blk_go) != 0;
+            if (!owner) mode = __ldcg(&st.blk_go);
         }
-        if (!go) break;
+        if (mode == 0) break;
+        if (mode == 2) {
+            front_acq_tiles(p, d, s, sm.u.prep, t, rank, C);
+            if (CL) {
+                __threadfence();
+                cluster_barrier();                    // the whole window is in L2
+            }
+            front_acq_corr(p, s, t, rank, C);
+            __threadfence();
+            if (CL) cluster_barrier();
+            else __syncthreads();
+            if (owner) front_prep_finish(p, d, s, sm.u.prep, sm.nco, t, 2);
+            if (CL) {
+                if (owner) __threadfence();
+                cluster_barrier();                    // the block's parameters are in place
+            }
+        }
         lap(st.blk_state_in == ST_FINE ? 2 : 1);
         const long long start = CL ? __ldcg(&st.start) : st.start;
         const int samperr = CL ? __ldcg(&st.blk_samperr) : st.blk_samperr;
