@@ -48,7 +48,9 @@ constexpr int SHIFT1 = 13, TAP_SCALE_LOG2 = 19;                   // unit DC gai
 constexpr int THREADS = 192;
 constexpr uint32_t A_STAGE_BYTES = NCHUNK * TILE_M * CHUNK;      // 65536
 constexpr uint32_t W_BYTES = NCHUNK * TILE_N * CHUNK;            // 65536
-constexpr uint32_t SMEM_BYTES = W_BYTES + 2 * A_STAGE_BYTES + 1024 /* alignment */ + 256 /* barriers */;
+constexpr int HALF = PERIOD / 2 + 1;                              // phasor table entries 0 .. 5953; the rest are their conjugates
+constexpr uint32_t EPI_BYTES = ((HALF * 4 + 15) & ~15) + GROUP * 4 + 2 * GROUP * 4;   // half table, rotation steps, offset corrections
+constexpr uint32_t SMEM_BYTES = W_BYTES + 2 * A_STAGE_BYTES + 1024 /* alignment */ + 256 /* barriers */ + EPI_BYTES;
 
 struct Params {
     int nch;                   // channels
@@ -137,9 +139,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_channelize(const __grid_constant
     uint8_t *smem_w = smem;                                        // [8 chunks][128 rows][64 B]
     uint8_t *smem_a = smem + W_BYTES;                              // [2 stages][8 chunks][128 rows][64 B]
     Barriers &bar = *reinterpret_cast<Barriers *>(smem + W_BYTES + 2 * A_STAGE_BYTES);
+    // the epilogue's tables in shared memory: the first half of the phasor table (P[11907 - i] = conj(P[i]), made so on
+    // the host), and this group's rotation steps and offset corrections
+    short2 *ph_half = reinterpret_cast<short2 *>(smem + W_BYTES + 2 * A_STAGE_BYTES + 256);
+    int *s_rot = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(ph_half) + ((HALF * 4 + 15) & ~15));
+    uint32_t *s_corr = reinterpret_cast<uint32_t *>(s_rot + GROUP);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = (int)blockIdx.x % p.ngroups, slot = (int)blockIdx.x / p.ngroups, nslots = (int)gridDim.x / p.ngroups;
 
+    for (int i = threadIdx.x; i < HALF; i += THREADS) ph_half[i] = p.phasor[i];
+    for (int i = threadIdx.x; i < GROUP; i += THREADS) {
+        const int ch = min(((int)blockIdx.x % p.ngroups) * GROUP + i, p.nch - 1);
+        s_rot[i] = p.rot_step[ch];
+        s_corr[2 * i] = (uint32_t)p.corr[2 * ch];
+        s_corr[2 * i + 1] = (uint32_t)p.corr[2 * ch + 1];
+    }
     if (threadIdx.x == 0) {
         mbar_init(&bar.w_full, 1);
         for (int i = 0; i < 2; i++) {
@@ -221,25 +235,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_channelize(const __grid_constant
                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr + 4u * c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // 32-bit arithmetic throughout: 256 * hi + lo wraps, the filter output itself is bounded by
+                // 128 * sum(|Wr| + |Wi|) < 2^28 (checked when the tables are made), so the wrapped sum is the value; after
+                // the shift a component is below 2^15 and the rotation's two products stay below 2^31.  No branches: the
+                // eight table reads of a load are independent and go out together.
+                short2 ph[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const unsigned qi = ((unsigned)s_rot[c0 + q] * (unsigned)nmod) % (unsigned)PERIOD;   // < 11907^2 < 2^32
+                    const bool up = qi >= (unsigned)HALF;
+                    const short2 v2 = ph_half[up ? (unsigned)PERIOD - qi : qi];
+                    ph[q] = make_short2(v2.x, up ? (short)-v2.y : v2.y);
+                }
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     const int ch = group * GROUP + c0 + q;
-                    if (ch >= p.nch || n >= p.nout) continue;
-                    // 32-bit arithmetic throughout: 256 * hi + lo wraps, the filter output itself is bounded by
-                    // 128 * sum(|Wr| + |Wi|) < 2^28 (checked when the tables are made), so the wrapped sum is the value;
-                    // after the shift a component is below 2^15 and the rotation's two products stay below 2^31
-                    const int ar = (int)(256u * v[4 * q + 0] + v[4 * q + 2] - (uint32_t)p.corr[2 * ch + 0]);
-                    const int ai = (int)(256u * v[4 * q + 1] + v[4 * q + 3] - (uint32_t)p.corr[2 * ch + 1]);
+                    const int ar = (int)(256u * v[4 * q + 0] + v[4 * q + 2] - s_corr[2 * (c0 + q)]);
+                    const int ai = (int)(256u * v[4 * q + 1] + v[4 * q + 3] - s_corr[2 * (c0 + q) + 1]);
                     const int vr = (ar + (1 << (SHIFT1 - 1))) >> SHIFT1, vi = (ai + (1 << (SHIFT1 - 1))) >> SHIFT1;
-                    const int qi = (int)(((unsigned)p.rot_step[ch] * (unsigned)nmod) % (unsigned)PERIOD);   // < 11907^2 < 2^32
-                    const short2 ph = __ldg(&p.phasor[qi]);
-                    int zr = vr * ph.x + vi * ph.y, zi = vi * ph.x - vr * ph.y;                // v * conj(P)
+                    int zr = vr * ph[q].x + vi * ph[q].y, zi = vi * ph[q].x - vr * ph[q].y;    // v * conj(P)
                     zr = (zr + (1 << 14)) >> 15;
                     zi = (zi + (1 << 14)) >> 15;
                     zr = zr > 32767 ? 32767 : (zr < -32768 ? -32768 : zr);
                     zi = zi > 32767 ? 32767 : (zi < -32768 ? -32768 : zi);
                     const uint32_t packed = (uint32_t)(uint16_t)(int16_t)zr | ((uint32_t)(uint16_t)(int16_t)zi << 16);
-                    *reinterpret_cast<uint32_t *>(p.out + (size_t)ch * p.out_stride + 2 * n) = packed;
+                    if (ch < p.nch && n < p.nout) *reinterpret_cast<uint32_t *>(p.out + (size_t)ch * p.out_stride + 2 * n) = packed;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -288,10 +308,12 @@ static void make_tables(const int *offsets, int nch, std::vector<short2> &phasor
                         std::vector<int> *rot, std::vector<long long> *corr)
 {
     phasor.resize(PERIOD);
-    for (int i = 0; i < PERIOD; i++) {
+    for (int i = 0; i <= PERIOD / 2; i++) {
         const double a = 2.0 * M_PI * i / PERIOD;
         phasor[i] = make_short2((short)lrint(32767.0 * cos(a)), (short)lrint(32767.0 * sin(a)));
     }
+    for (int i = PERIOD / 2 + 1; i < PERIOD; i++)                          // exactly conjugate-symmetric: the kernel keeps half of it
+        phasor[i] = make_short2(phasor[PERIOD - i].x, (short)-phasor[PERIOD - i].y);
     // prototype low-pass: Kaiser-windowed sinc, -6 dB at 372 kHz: flat over a hybrid FM channel (+-200 kHz), >= 55 dB down from 544 kHz on (what folds onto the channel after /32), unit DC gain
     std::vector<double> h(TAPS);
     {

@@ -13,6 +13,7 @@ WIDE = ch.WIDE_RATE
 def test_tables_filter_quality_and_symmetry():
     taps, ph = ch.make_tables([0, 9, -37])
     assert np.abs(ph.astype(np.int64)[:, 0] ** 2 + ph.astype(np.int64)[:, 1] ** 2 - 32767 ** 2).max() < 2 * 32767 * 2
+    assert np.array_equal(ph[1:, 0], ph[:0:-1, 0]) and np.array_equal(ph[1:, 1], -ph[:0:-1, 1])   # P[N - i] = conj(P[i])
     h = taps[0, :, 0].astype(np.float64)                                  # channel 0: no mixing, real taps
     assert np.all(taps[0, :, 1] == 0) and abs(h.sum() - 2 ** 19) < 64     # unit DC gain at the 2^19 scale
     H = np.abs(np.fft.fft(h, 1 << 16)) / h.sum()
