@@ -136,8 +136,12 @@ struct AmWork {
     float2 spec[FFT];                          // one demodulated symbol, fftshift-ed
     float2 bins[FFT][BLK];
     uint8_t buffer_pl[PW * BLK * 8], buffer_pu[PW * BLK * 8], buffer_s[PW * BLK * 8], buffer_t[PW * BLK * 8];
-    uint8_t bl[18000], bu[18000], ml[DIVERSITY + 18000], mu[DIVERSITY + 18000], el[12000], eu[24000];
-    uint8_t ebl[18000], ebu[18000], eml[DIVERSITY + 18000], emu[DIVERSITY + 18000];     // MA3 (decode.h:49-52)
+    uint8_t bl[18000], bu[18000], el[12000], eu[24000];
+    alignas(16) uint8_t ml[DIVERSITY + 18000];     // (16-byte aligned: the diversity delay moves them 16 bytes at a time)
+    alignas(16) uint8_t mu[DIVERSITY + 18000];
+    uint8_t ebl[18000], ebu[18000];                // MA3 (decode.h:49-52)
+    alignas(16) uint8_t eml[DIVERSITY + 18000];
+    alignas(16) uint8_t emu[DIVERSITY + 18000];
     uint8_t p1_am[8 * 9000], p3_am[72000];
     int8_t vit_p1[8 * P1_LEN * 3], vit_p3[P3_LEN_MA3 * 3], vit_pids[PIDS_LEN * 3];
     uint8_t out[P3_LEN_MA3 + 8];
@@ -819,80 +823,168 @@ AM_HD inline int bit_map(const uint8_t *matrix, int b, int k, int p)            
     return (matrix[PW * (b * BLK + row) + col] >> p) & 1;
 }
 
+// for (i = lane; i < N; i += n_lanes) st(i, ld(i)), B iterations at a time with all their loads ahead of their stores:
+// the loops below move bytes between arrays of one struct, which the compiler will not reorder on its own, and every
+// iteration would otherwise wait for its own load (the arrays live in global memory)
+template <int B, typename Load, typename Store>
+AM_HD inline void batched(Lanes L, int N, Load ld, Store st)
+{
+    for (int i0 = L.lane; i0 < N; i0 += B * L.n) {
+        decltype(ld(0)) v[B];
+#pragma unroll
+        for (int k = 0; k < B; k++)
+            if (i0 + k * L.n < N) v[k] = ld(i0 + k * L.n);
+#pragma unroll
+        for (int k = 0; k < B; k++)
+            if (i0 + k * L.n < N) st(i0 + k * L.n, v[k]);
+    }
+}
+struct AmBytes4 { uint8_t a, b, c, d; };
+struct AmBytes12 { uint8_t v[12]; };
+struct AmWords4 { uint32_t x, y, z, w; };
+
 AM_HD inline void interleaver_ma1(AmWork &w, Lanes L, bool ma3)                        // decode.c:74-231
 {
     const int bl_delay[3] = { 2, 1, 5 }, ml_delay[3] = { 11, 6, 7 }, bu_delay[3] = { 10, 8, 9 }, mu_delay[3] = { 4, 3, 0 };
     const int el_delay[2] = { 0, 1 }, eu_delay[4] = { 2, 3, 5, 4 };
-    for (int n = L.lane; n < 18000; n += L.n) {
-        w.bl[n] = (uint8_t)bit_map(w.buffer_pl, n / 2250, (n + n / 750 + 1) % 750, n % 3);
-        w.ml[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_pl, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
-        w.bu[n] = (uint8_t)bit_map(w.buffer_pu, n / 2250, (n + n / 750) % 750, n % 3);
-        w.mu[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_pu, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
-    }
+    batched<2>(L, 18000,
+               [&](int n) {
+                   AmBytes4 r;
+                   r.a = (uint8_t)bit_map(w.buffer_pl, n / 2250, (n + n / 750 + 1) % 750, n % 3);
+                   r.b = (uint8_t)bit_map(w.buffer_pl, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
+                   r.c = (uint8_t)bit_map(w.buffer_pu, n / 2250, (n + n / 750) % 750, n % 3);
+                   r.d = (uint8_t)bit_map(w.buffer_pu, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
+                   return r;
+               },
+               [&](int n, const AmBytes4 &r) {
+                   w.bl[n] = r.a;
+                   w.ml[DIVERSITY + n] = r.b;
+                   w.bu[n] = r.c;
+                   w.mu[DIVERSITY + n] = r.d;
+               });
     if (!ma3) {
-        for (int n = L.lane; n < 12000; n += L.n)
-            w.el[n] = (uint8_t)bit_map(w.buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2);
-        for (int n = L.lane; n < 24000; n += L.n)
-            w.eu[n] = (uint8_t)bit_map(w.buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4);
+        batched<2>(L, 12000, [&](int n) { return (uint8_t)bit_map(w.buffer_t, (3 * n + n / 3000) % 8, (n + (n / 6000)) % 750, n % 2); },
+                   [&](int n, uint8_t v) { w.el[n] = v; });
+        batched<2>(L, 24000,
+                   [&](int n) { return (uint8_t)bit_map(w.buffer_s, (3 * n + n / 3000 + 2 * (n / 12000)) % 8, (n + (n / 6000)) % 750, n % 4); },
+                   [&](int n, uint8_t v) { w.eu[n] = v; });
     } else {
-        for (int n = L.lane; n < 18000; n += L.n) {                                      // decode.c:119-140
-            w.ebl[n] = (uint8_t)bit_map(w.buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, n % 3);
-            w.eml[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
-            w.ebu[n] = (uint8_t)bit_map(w.buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, n % 3);
-            w.emu[DIVERSITY + n] = (uint8_t)bit_map(w.buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
-        }
+        batched<2>(L, 18000,                                                             // decode.c:119-140
+                   [&](int n) {
+                       AmBytes4 r;
+                       r.a = (uint8_t)bit_map(w.buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, n % 3);
+                       r.b = (uint8_t)bit_map(w.buffer_t, (3 * n + 3) % 8, (n + n / 3000 + 3) % 750, 3 + (n % 3));
+                       r.c = (uint8_t)bit_map(w.buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, n % 3);
+                       r.d = (uint8_t)bit_map(w.buffer_s, (3 * n) % 8, (n + n / 3000 + 2) % 750, 3 + (n % 3));
+                       return r;
+                   },
+                   [&](int n, const AmBytes4 &r) {
+                       w.ebl[n] = r.a;
+                       w.eml[DIVERSITY + n] = r.b;
+                       w.ebu[n] = r.c;
+                       w.emu[DIVERSITY + n] = r.d;
+                   });
     }
     AM_SYNC();
-    for (int i = L.lane; i < 6000; i += L.n) {
-        for (int j = 0; j < 3; j++) {
-            w.p1_am[i * 12 + bl_delay[j]] = w.bl[i * 3 + j];
-            w.p1_am[i * 12 + ml_delay[j]] = w.ml[i * 3 + j];
-            w.p1_am[i * 12 + bu_delay[j]] = w.bu[i * 3 + j];
-            w.p1_am[i * 12 + mu_delay[j]] = w.mu[i * 3 + j];
-        }
-        if (!ma3) {
-            for (int j = 0; j < 2; j++) w.p3_am[i * 6 + el_delay[j]] = w.el[i * 2 + j];
-            for (int j = 0; j < 4; j++) w.p3_am[i * 6 + eu_delay[j]] = w.eu[i * 4 + j];
-        } else {
-            for (int j = 0; j < 3; j++) {                                                // decode.c:163-170
-                w.p3_am[i * 12 + bl_delay[j]] = w.ebl[i * 3 + j];
-                w.p3_am[i * 12 + ml_delay[j]] = w.eml[i * 3 + j];
-                w.p3_am[i * 12 + bu_delay[j]] = w.ebu[i * 3 + j];
-                w.p3_am[i * 12 + mu_delay[j]] = w.emu[i * 3 + j];
-            }
-        }
-    }
+    batched<2>(L, 6000,
+               [&](int i) {
+                   AmBytes12 r;
+#pragma unroll
+                   for (int j = 0; j < 3; j++) {
+                       r.v[j] = w.bl[i * 3 + j];
+                       r.v[3 + j] = w.ml[i * 3 + j];
+                       r.v[6 + j] = w.bu[i * 3 + j];
+                       r.v[9 + j] = w.mu[i * 3 + j];
+                   }
+                   return r;
+               },
+               [&](int i, const AmBytes12 &r) {
+#pragma unroll
+                   for (int j = 0; j < 3; j++) {
+                       w.p1_am[i * 12 + bl_delay[j]] = r.v[j];
+                       w.p1_am[i * 12 + ml_delay[j]] = r.v[3 + j];
+                       w.p1_am[i * 12 + bu_delay[j]] = r.v[6 + j];
+                       w.p1_am[i * 12 + mu_delay[j]] = r.v[9 + j];
+                   }
+               });
+    batched<2>(L, 6000,
+               [&](int i) {
+                   AmBytes12 r;
+                   if (!ma3) {
+#pragma unroll
+                       for (int j = 0; j < 2; j++) r.v[j] = w.el[i * 2 + j];
+#pragma unroll
+                       for (int j = 0; j < 4; j++) r.v[2 + j] = w.eu[i * 4 + j];
+#pragma unroll
+                       for (int j = 6; j < 12; j++) r.v[j] = 0;
+                   } else {
+#pragma unroll
+                       for (int j = 0; j < 3; j++) {                                     // decode.c:163-170
+                           r.v[j] = w.ebl[i * 3 + j];
+                           r.v[3 + j] = w.eml[i * 3 + j];
+                           r.v[6 + j] = w.ebu[i * 3 + j];
+                           r.v[9 + j] = w.emu[i * 3 + j];
+                       }
+                   }
+                   return r;
+               },
+               [&](int i, const AmBytes12 &r) {
+                   if (!ma3) {
+#pragma unroll
+                       for (int j = 0; j < 2; j++) w.p3_am[i * 6 + el_delay[j]] = r.v[j];
+#pragma unroll
+                       for (int j = 0; j < 4; j++) w.p3_am[i * 6 + eu_delay[j]] = r.v[2 + j];
+                   } else {
+#pragma unroll
+                       for (int j = 0; j < 3; j++) {
+                           w.p3_am[i * 12 + bl_delay[j]] = r.v[j];
+                           w.p3_am[i * 12 + ml_delay[j]] = r.v[3 + j];
+                           w.p3_am[i * 12 + bu_delay[j]] = r.v[6 + j];
+                           w.p3_am[i * 12 + mu_delay[j]] = r.v[9 + j];
+                       }
+                   }
+               });
     AM_SYNC();
-    // the main bits move three frames towards the front (memmove of 54000 entries, in three non-overlapping steps)
+    // the main bits move three frames towards the front (memmove of 54000 entries, in three non-overlapping steps),
+    // sixteen bytes at a time
     for (int step = 0; step < 3; step++) {
-        for (int i = L.lane; i < 18000; i += L.n) {
-            w.ml[step * 18000 + i] = w.ml[(step + 1) * 18000 + i];
-            w.mu[step * 18000 + i] = w.mu[(step + 1) * 18000 + i];
-            if (ma3) {                                                                    // decode.c:176-180
-                w.eml[step * 18000 + i] = w.eml[(step + 1) * 18000 + i];
-                w.emu[step * 18000 + i] = w.emu[(step + 1) * 18000 + i];
-            }
+        auto move16 = [&](uint8_t *arr) {
+            const AmWords4 *src = reinterpret_cast<const AmWords4 *>(arr + (step + 1) * 18000);
+            AmWords4 *dst = reinterpret_cast<AmWords4 *>(arr + step * 18000);
+            batched<2>(L, 18000 / 16, [&](int i) { return src[i]; }, [&](int i, const AmWords4 &v) { dst[i] = v; });
+        };
+        move16(w.ml);
+        move16(w.mu);
+        if (ma3) {                                                                        // decode.c:176-180
+            move16(w.eml);
+            move16(w.emu);
         }
         AM_SYNC();
     }
     // depuncture: kept positions of every 15 (P1) / 6 (P3) code bits (decode.c:186-212)
-    for (int i = L.lane; i < 8 * P1_LEN * 3; i += L.n) {
-        const int r = i % 15, base = (i / 15) * 12;
-        const int before = r - (r > 1) - (r > 4) - (r > 7);
-        w.vit_p1[i] = (r == 1 || r == 4 || r == 7) ? 0 : (w.p1_am[base + before] ? 1 : -1);
-    }
+    batched<2>(L, 8 * P1_LEN * 3,
+               [&](int i) {
+                   const int r = i % 15, base = (i / 15) * 12;
+                   const int before = r - (r > 1) - (r > 4) - (r > 7);
+                   return (int8_t)((r == 1 || r == 4 || r == 7) ? 0 : (w.p1_am[base + before] ? 1 : -1));
+               },
+               [&](int i, int8_t v) { w.vit_p1[i] = v; });
     if (!ma3) {
-        for (int i = L.lane; i < P3_LEN * 3; i += L.n) {
-            const int r = i % 6, base = (i / 6) * 3;
-            const int before = r - (r > 1);
-            w.vit_p3[i] = (r == 1 || r == 4 || r == 5) ? 0 : (w.p3_am[base + before] ? 1 : -1);
-        }
+        batched<2>(L, P3_LEN * 3,
+                   [&](int i) {
+                       const int r = i % 6, base = (i / 6) * 3;
+                       const int before = r - (r > 1);
+                       return (int8_t)((r == 1 || r == 4 || r == 5) ? 0 : (w.p3_am[base + before] ? 1 : -1));
+                   },
+                   [&](int i, int8_t v) { w.vit_p3[i] = v; });
     } else {
-        for (int i = L.lane; i < P3_LEN_MA3 * 3; i += L.n) {                             // decode.c:214-229
-            const int r = i % 15, base = (i / 15) * 12;
-            const int before = r - (r > 1) - (r > 4) - (r > 7);
-            w.vit_p3[i] = (r == 1 || r == 4 || r == 7) ? 0 : (w.p3_am[base + before] ? 1 : -1);
-        }
+        batched<2>(L, P3_LEN_MA3 * 3,                                                    // decode.c:214-229
+                   [&](int i) {
+                       const int r = i % 15, base = (i / 15) * 12;
+                       const int before = r - (r > 1) - (r > 4) - (r > 7);
+                       return (int8_t)((r == 1 || r == 4 || r == 7) ? 0 : (w.p3_am[base + before] ? 1 : -1));
+                   },
+                   [&](int i, int8_t v) { w.vit_p3[i] = v; });
     }
     AM_SYNC();
 }
