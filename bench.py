@@ -424,6 +424,12 @@ def chan_leg(args):
     peak_i8 = 2 * bf16                                          # int8 runs at twice the bf16 rate; no int8 GEMM measurement in MEASURED_PEAKS.json
     hbm, hbm_src = measured_peak()
     traffic = nbytes + len(offs) * nout * 4
+    dram = None
+    try:                                                   # DRAM bytes of one launch from the ncu capture of this very leg
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get("k_channelize")
+        dram = tj and (tj["dram_read_bytes"] + tj["dram_write_bytes"])
+    except Exception:                                      # noqa: BLE001
+        pass
     out_j = {"value": samples / (ms * 1e-3) / 1e6, "unit": "Msamples/s (wideband cu8 complex, 23.814 MS/s)", "ms_per_step": ms,
              "x_realtime": samples / (ms * 1e-3) / 23814000.0, "channels": len(offs), "outputs_per_channel": int(nout), "steps": steps,
              "channel_msamples_per_s": len(offs) * nout / (ms * 1e-3) / 1e6,
@@ -431,7 +437,8 @@ def chan_leg(args):
                           "achieved": 2 * macs / (ms * 1e-3) / 1e12, "useful": 2 * useful / (ms * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s",
                           "frac": 2 * macs / (ms * 1e-3) / 1e12 / peak_i8,
                           "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 tensor rate; no int8 measurement in that file)",
-                          "hbm_gbs": traffic / (ms * 1e-3) / 1e9, "hbm_frac": traffic / (ms * 1e-3) / 1e9 / hbm, "traffic": None},
+                          "hbm_gbs": traffic / (ms * 1e-3) / 1e9, "hbm_frac": traffic / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": traffic,
+                          "traffic": dram, "traffic_source": "profiles/r2_ncu_summary.md (ncu --set full, one launch of this leg)"},
              "parity_gate": {"ok": True, "what": "first 1493 and last 64 output samples of all 100 channels == oracle/chan_oracle.py"},
              "workload": "one 2^27-byte cu8 capture (uniform random bytes) resident in HBM -> 100 channels x %d cs16 samples, device to device" % nout}
     print(json.dumps(out_j), flush=True)
