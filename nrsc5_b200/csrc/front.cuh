@@ -462,6 +462,195 @@ __device__ void front_prep_finish(const DevPtrs &p, const EngineDims &d, int s, 
     __syncthreads();
 }
 
+// prep of a block by ONE CTA (k_stream<false>, a stream per CTA): everything front_prep_begin / front_acq_tiles /
+// front_acq_corr / front_prep_finish do, in one piece - kept as one function because the 128-stream kernel is at its
+// 64-register ceiling and the split version costs it spills
+__device__ bool front_prep_single(const DevPtrs &p, const EngineDims &d, int s, PrepSmem &sm, float2 *nco, int t)
+{
+    StreamState &st = p.st[s];
+    __shared__ int sh_active, sh_samperr;
+    __shared__ float sh_angle, sh_theta;
+    if (t == 0) {
+        if (st.force_state >= 0) {
+            set_state(p, d, s, st.force_state);
+            st.force_state = -1;
+        }
+        // in_avail is advanced by asynchronous copies while this kernel runs
+        const long long avail = *reinterpret_cast<volatile long long *>(&st.in_avail);
+        int act = avail >= 2 * (st.start + NACQ);
+        if (act && st.state == ST_FINE) {
+            // P3 / P4 frames (MP2, MP3, MP11) are decoded by kernel groups the host adds to the pass only when a
+            // stream asks: wait at the block boundary until it has (nrsc5b_process looks at the flag).  Streams
+            // in MP1 / MP5 / MP6 never pay for those launches.
+            const int cm = c_compat_mode[st.psmi & 63];
+            const int need = cm == 2 ? PX_NEED_SHORT : cm == 3 ? PX_NEED_P3 : cm == 11 ? (PX_NEED_P3 | PX_NEED_PX2) : 0;
+            if (need & ~d.px_enabled) {
+                atomicOr(&p.ctl->px_need, (unsigned)need);
+                act = 0;
+            }
+        }
+        st.active = act;
+        sh_active = act;
+        if (act) atomicAdd(&p.ctl->progress, 1ull);
+    }
+    __syncthreads();
+    if (!sh_active) return false;
+
+    const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
+    const int state_in = st.state;
+    if (state_in != ST_FINE) {
+        float2 *tb = p.tbuf + (size_t)s * NACQ;
+        const long long start = st.start;
+        const uint32_t *iqw = reinterpret_cast<const uint32_t *>(iq);
+        // the 71280-sample window in tiles: cu8 words -> shared memory (coalesced), halfband /2 (input.c:52-94),
+        // 32-tap symmetric Q15 band-pass (acquire.c:120-127, firdecim_q15.c:95-109) -> float window in `tb`
+        for (int i0 = 0; i0 < NACQ; i0 += ACQ_TILE) {
+            const int L = min(ACQ_TILE, NACQ - i0);
+            const long long w0 = start + i0 - 38;                 // word of halfband output i0-31's first input
+            for (int v = t; v < L + 38; v += FRONT_THREADS) {
+                const long long a = w0 + v;
+                // before the stream starts the decimator sees zeros = byte 127; through L2 only (asynchronous pushes)
+                sm.words[v] = a >= 0 ? __ldcg(iqw + a) : (d.cs16 ? 0u : 0x7f7f7f7fu);
+            }
+            __syncthreads();
+            for (int k = t; k < L + 31; k += FRONT_THREADS) {
+                if (i0 == 0 && k < 31) {                          // history: the last 31 outputs of the previous window
+                    sm.ytile[k] = make_short2(st.bp_hist[k][0], st.bp_hist[k][1]);
+                } else if (d.cs16) {                              // already decimated: the sample itself
+                    const uint32_t w = sm.words[k + 7];
+                    sm.ytile[k] = make_short2((short)(w & 0xffff), (short)(w >> 16));
+                } else {
+                    const int2 h = halfband_words(sm.words + k);
+                    sm.ytile[k] = make_short2((short)h.x, (short)h.y);
+                }
+            }
+            __syncthreads();
+            for (int j = t; j < L; j += FRONT_THREADS) {
+                const short2 *yy = sm.ytile + j;                  // yy[k] = y[i - 31 + k]
+                short accr = 0, acci = 0;
+#pragma unroll 5
+                for (int k = 1; k < 16; k++) {
+                    const short2 a = yy[k], b = yy[32 - k];
+                    accr = (short)(accr + ((((int)a.x + (int)b.x) * c_bp_tap[k]) >> 15));
+                    acci = (short)(acci + ((((int)a.y + (int)b.y) * c_bp_tap[k]) >> 15));
+                }
+                const short2 c = yy[16];
+                accr = (short)(accr + (((int)c.x * c_bp_tap[16]) >> 15));
+                acci = (short)(acci + (((int)c.y * c_bp_tap[16]) >> 15));
+                tb[i0 + j] = make_float2(__fdiv_rn((float)accr, 32767.0f), __fdiv_rn((float)acci, -32767.0f));
+            }
+            if (i0 + L == NACQ && t < 31) {                       // keep the window's last 31 outputs as history
+                const short2 v = sm.ytile[L + t];
+                st.bp_hist[t][0] = v.x;
+                st.bp_hist[t][1] = v.y;
+            }
+            __syncthreads();
+        }
+        // cyclic-prefix correlation per sample offset (acquire.c:129-134)
+        for (int i = t; i < NSYM; i += FRONT_THREADS) {
+            float2 acc = make_float2(0.f, 0.f);
+            for (int j = 0; j < BLK; j++) {
+                float2 a = tb[i + j * NSYM], b = tb[i + j * NSYM + NFFT];
+                float2 pr = cmulf(a, make_float2(b.x, -b.y));
+                acc.x += pr.x;
+                acc.y += pr.y;
+            }
+            sm.sums[i] = acc;
+        }
+        __syncthreads();
+        // pulse-shaped sliding sum and arg-max (acquire.c:136-151)
+        float best = -1.0f;
+        int besti = 0;
+        float2 bestv = make_float2(0.f, 0.f);
+        for (int i = t; i < NSYM; i += FRONT_THREADS) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int j = 0; j < NCP; j++) {
+                int q = i + j;
+                if (q >= NSYM) q -= NSYM;
+                const float2 sv = sm.sums[q];
+                const float a = __ldg(&p.shape[j]), b = __ldg(&p.shape[j + NFFT]);
+                v.x += (sv.x * a) * b;
+                v.y += (sv.y * a) * b;
+            }
+            const float mag = v.x * v.x + v.y * v.y;
+            if (mag > best) { best = mag; besti = i; bestv = v; }
+        }
+        sm.red_mag[t] = best; sm.red_idx[t] = besti; sm.red_v[t] = bestv;
+        __syncthreads();
+        for (int o = FRONT_THREADS / 2; o; o >>= 1) {
+            if (t < o) {
+                const float m2 = sm.red_mag[t + o];
+                const int i2 = sm.red_idx[t + o];
+                if (m2 > sm.red_mag[t] || (m2 == sm.red_mag[t] && i2 < sm.red_idx[t])) {
+                    sm.red_mag[t] = m2; sm.red_idx[t] = i2; sm.red_v[t] = sm.red_v[t + o];
+                }
+            }
+            __syncthreads();
+        }
+        if (t == 0) {
+            const float2 w = cmulf(sm.red_v[0], cexp_j(-st.prev_angle));
+            const float angle_diff = atan2f(w.y, w.x);
+            const float factor = (st.prev_angle != 0.0f) ? 0.25f : 1.0f;
+            const float angle = st.prev_angle + (angle_diff * factor);
+            st.prev_angle = angle;
+            sh_angle = angle;
+            sh_samperr = (sm.red_idx[0] + NSYM - 15) % NSYM;
+            if (st.state == ST_NONE) st.state = ST_COARSE;
+        }
+    } else if (t == 0) {
+        sh_samperr = NSYM / 2 + st.samperr;
+        st.samperr = 0;
+        const float angle = st.prev_angle + (-st.angle);
+        st.angle = 0;
+        st.prev_angle = angle;
+        sh_angle = angle;
+    }
+    __syncthreads();
+
+    const int samperr = sh_samperr;
+    const int adj = NSYM / 2 - samperr;
+    if (adj != 0) {                                            // sync_adjust, sync.c:769-777
+        float *cp = p.cphase + (size_t)s * NFFT;
+        for (int i = t; i < SIDE; i += FRONT_THREADS) {
+            const int bl = LB0 + i, bu = UB1 - i;
+            cp[bl] = (float)((double)cp[bl] - (double)(adj * (bl - NFFT / 2) * 2) * M_PI / NFFT);
+            cp[bu] = (float)((double)cp[bu] - (double)(adj * (bu - NFFT / 2) * 2) * M_PI / NFFT);
+        }
+    }
+    if (t == 0) {
+        float angle = sh_angle;
+        angle = (float)((double)angle - 2 * M_PI * st.cfo);
+        const float pre = (float)(-adj) * angle / (float)NFFT;
+        const float2 ph = cmulf(st.phase, cexp_j(pre));
+        const float theta = angle / (float)NFFT;
+        st.phase0 = ph;
+        st.theta = theta;
+        sh_theta = theta;
+        st.blk_samperr = samperr;
+        st.blk_state_in = state_in;
+        // NCO phase after the 32 symbols of this block (acquire.c:250-252, closed form)
+        double sn, cs;
+        sincos((double)theta * (double)(NSYM * BLK), &sn, &cs);
+        const float2 pe = cmulf(ph, make_float2((float)cs, (float)sn));
+        const float nrm = sqrtf(pe.x * pe.x + pe.y * pe.y);
+        st.phase = make_float2(pe.x / nrm, pe.y / nrm);
+        uint8_t *w = log_reserve(p, d, s, REC_BLOCK, 32);
+        if (w) {
+            int *wi = reinterpret_cast<int *>(w);
+            float *wf = reinterpret_cast<float *>(w);
+            wi[0] = state_in; wi[1] = samperr; wf[2] = angle; wf[3] = ph.x; wf[4] = ph.y; wi[5] = st.cfo;
+            wi[6] = (int)(unsigned)(st.start & 0xffffffffLL);
+            wi[7] = (int)(st.start >> 32);
+        }
+    }
+    __syncthreads();
+    // NCO of this block in closed form, with the pulse shape folded in (acquire.c:243-252):
+    // nco[j] = shape[j] * exp(j*theta*j); the per-symbol phase is applied to the kept bins
+    fill_nco(p, nco, sh_theta, t);
+    __syncthreads();
+    return true;
+}
+
 // ---------------------------------------------------------------------------
 // demod: one OFDM symbol per 128-thread half of the CTA
 // ---------------------------------------------------------------------------
@@ -1280,32 +1469,32 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_stream(DevPtrs p, EngineDi
         // blk_go: 0 = the pass is over, 1 = demodulate the block (its parameters are in place), 2 = coarse acquisition
         // first - which the stream's CTAs share
         int mode = 0;
-        if (owner) {
-            if (nb < max_blocks && !st.p1_ready) mode = front_prep_begin(p, d, s, t);
-            if (mode == 1) front_prep_finish(p, d, s, sm.u.prep, sm.nco, t, 1);
-        }
-        if (CL) {
+        if (!CL) {
+            if (nb < max_blocks && !st.p1_ready) mode = front_prep_single(p, d, s, sm.u.prep, sm.nco, t) ? 1 : 0;
+            if (mode == 0) break;
+        } else {
+            if (owner) {
+                if (nb < max_blocks && !st.p1_ready) mode = front_prep_begin(p, d, s, t);
+                if (mode == 1) front_prep_finish(p, d, s, sm.u.prep, sm.nco, t, 1);
+            }
             if (owner && t == 0) {
                 st.blk_go = mode;
                 __threadfence();
             }
             cluster_barrier();                        // the helpers read the block's parameters behind this barrier
             if (!owner) mode = __ldcg(&st.blk_go);
-        }
-        if (mode == 0) break;
-        if (mode == 2) {
-            front_acq_tiles(p, d, s, sm.u.prep, t, rank, C);
-            if (CL) {
+            if (mode == 0) break;
+            if (mode == 2) {
+                front_acq_tiles(p, d, s, sm.u.prep, t, rank, C);
                 __threadfence();
                 cluster_barrier();                    // the whole window is in L2
-            }
-            front_acq_corr(p, s, t, rank, C);
-            __threadfence();
-            if (CL) cluster_barrier();
-            else __syncthreads();
-            if (owner) front_prep_finish(p, d, s, sm.u.prep, sm.nco, t, 2);
-            if (CL) {
-                if (owner) __threadfence();
+                front_acq_corr(p, s, t, rank, C);
+                __threadfence();
+                cluster_barrier();
+                if (owner) {
+                    front_prep_finish(p, d, s, sm.u.prep, sm.nco, t, 2);
+                    __threadfence();
+                }
                 cluster_barrier();                    // the block's parameters are in place
             }
         }
