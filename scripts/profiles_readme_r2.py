@@ -6,13 +6,13 @@ import shutil
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "r2r_bench.json")
+src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "r2s_bench.json")
 j = json.loads(open(src).read().strip().splitlines()[-1])
 shutil.copyfile(src, os.path.join(ROOT, "profiles", "r2_bench_final.json"))
-for f in ("r2r_gpu_tests.log", "r2p.log"):
+for f in ("r2s_gpu_tests.log", "r2p.log"):
     p = os.path.join(ROOT, "gpurun_out", f)
     if os.path.exists(p):
-        shutil.copyfile(p, os.path.join(ROOT, "profiles", f.replace("r2r_", "r2_final_").replace("r2p", "r2_cluster_acquisition_check")))
+        shutil.copyfile(p, os.path.join(ROOT, "profiles", f.replace("r2s_", "r2_final_").replace("r2p", "r2_cluster_acquisition_check")))
 
 r, cb, l2, am, mp3, dr, ch = (j["roofline"], j["cpu_baseline"], j["l2_on_device"], j["am_config4"], j["mp3_config3"], j["single_stream_dropin"],
                               j["channeliser_f3"])
@@ -27,7 +27,7 @@ out = f"""# profiles/ — measurements on the B200 (sm_100a, {j['clocks']['sm_mh
 ## Round 2
 
 Everything below the headline table comes from ONE `python bench.py` on a fresh box - the round's last GPU call
-(`scripts/gpu_run_r.sh`), its line kept as `r2_bench_final.json`; the same call ran `pytest -m gpu`
+(`scripts/gpu_run_s.sh`), its line kept as `r2_bench_final.json`; the same call ran `pytest -m gpu`
 (`r2_final_gpu_tests.log`), compute-sanitizer (`r2_sanitizer.md`) and the second ncu pass.  Files: `r2_ncu_summary.md` +
 `launches_r2.csv` + `r2_k_*_raw.csv` (ncu: launch list of the headline step, `--set full` captures of `k_stream`, `k_l2`, `k_am`,
 `k_channelize`; `scripts/profile_r2.sh`, `profile_r2b.sh`, `summarize_r2.py`), `r2_traffic.json` (DRAM bytes of `k_stream` per
