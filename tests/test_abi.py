@@ -45,6 +45,13 @@ def test_no_cpu_fallback_without_gpu():
         eng.halfband_fm(np.zeros(64, dtype=np.uint8))
     with pytest.raises(nrsc5_b200.EngineError):
         eng.l2_frames([(1, 4608, bytes(576))])              # L2 alone: no host path either
+    with pytest.raises(nrsc5_b200.EngineError):
+        eng.viterbi_k9(np.ones((1, 3 * 80), dtype=np.int8))  # the AM decoder alone: device only
+    from nrsc5_b200 import channelizer
+    with pytest.raises(nrsc5_b200.EngineError):
+        channelizer.Channelizer([0, 9])                     # the channeliser needs a device; its tables do not:
+    taps, ph = channelizer.make_tables([0, 9])
+    assert taps.shape == (2, 256, 2) and ph.shape == (11907, 2)
 
 
 def test_record_parser_roundtrip():
