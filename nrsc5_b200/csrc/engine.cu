@@ -16,6 +16,17 @@
 
 #include "../../include/nrsc5_b200.h"
 #include "common.cuh"
+// NVTX ranges around the host-side phases (header-only NVTX 3: no library to link; a no-op unless a tool is attached -
+// `ncu --nvtx`, Nsight Systems): process / submit / poll, and per pass the front end and the decode groups
+#if defined(NB_EMU)
+struct NvtxRange { explicit NvtxRange(const char *) {} };
+#else
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#endif
 #include "rs.cuh"
 #include "viterbi.cuh"
 #include "viterbi_chunk.cuh"
@@ -1568,6 +1579,7 @@ static void launch_v64(const V64Args &a, int nframes, cudaStream_t stream)
 
 static void launch_p1(nrsc5b_engine *e)
 {
+    NvtxRange nvtx_("nrsc5b: P1/P3 decode groups");
     const int S = e->dims.nstreams;
     k_p1_gather<<<dim3(32, S), 256, 0, e->stream>>>(e->dp, e->dims);
     launch_v64(p1_v64_args(e->dp, e->v64_ch), S, e->stream);      // fast path ...
@@ -1657,6 +1669,7 @@ static void launch_k_stream(nrsc5b_engine *e, int last_pass)
 
 static int launch_pass(nrsc5b_engine *e, bool last_pass, bool with_decode = true)
 {
+    NvtxRange nvtx_("nrsc5b: pass");
     if (last_pass) cudaMemsetAsync(reinterpret_cast<uint8_t *>(e->dp.ctl) + offsetof(EngineCtl, more), 0, sizeof(unsigned), e->stream);
     if (e->am_st) {                                        // AM: one kernel does the whole chain, window after window
         const bool l2 = e->l2 && e->dims.l2;              // with L2 on, a launch stops after 16 blocks: its frames fit the queue
@@ -1805,6 +1818,7 @@ extern "C" int nrsc5b_prepare_async(nrsc5b_engine_t *e);
 
 static int process_impl(nrsc5b_engine_t *e, bool wait_for_copies)
 {
+    NvtxRange nvtx_("nrsc5b_process");
     if (!e) return NRSC5B_EINVAL;
     if (e->in_flight) return NRSC5B_EINVAL;                // an asynchronous batch is open: nrsc5b_poll first
     {
@@ -2008,6 +2022,7 @@ extern "C" int nrsc5b_prepare_async(nrsc5b_engine_t *e)
  * < 0 on error.  flush != 0: also send staged input that does not complete a block yet (end of stream). */
 extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
 {
+    NvtxRange nvtx_("nrsc5b_submit");
     if (!e) return NRSC5B_EINVAL;
     if (e->in_flight) return 0;
     bool decode = true;
@@ -2064,6 +2079,7 @@ extern "C" int nrsc5b_submit(nrsc5b_engine_t *e, int flush)
  * nrsc5b_submit; 0: no batch in flight, or (wait == 0) it is still running; < 0 on error. */
 extern "C" int nrsc5b_poll(nrsc5b_engine_t *e, int wait)
 {
+    NvtxRange nvtx_("nrsc5b_poll");
     if (!e) return NRSC5B_EINVAL;
     if (!e->in_flight) return 0;
     if (wait) {
@@ -2149,6 +2165,7 @@ extern "C" long nrsc5b_drain(nrsc5b_engine_t *e, int stream, uint8_t *out, size_
  * device->host copy of the stream states, then one asynchronous copy per stream and a single wait. */
 extern "C" int nrsc5b_drain_all(nrsc5b_engine_t *e, uint8_t *out, size_t out_stride, size_t *sizes)
 {
+    NvtxRange nvtx_("nrsc5b_drain_all");
     if (!e || !out || !sizes) return NRSC5B_EINVAL;
     const int S = e->dims.nstreams;
     CK(cudaMemcpyAsync(e->h_state, e->dp.st, sizeof(StreamState) * S, cudaMemcpyDeviceToHost, e->stream));

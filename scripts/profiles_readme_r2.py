@@ -32,7 +32,9 @@ Everything below the headline table comes from ONE `python bench.py` on a fresh 
 `launches_r2.csv` + `r2_k_*_raw.csv` (ncu: launch list of the headline step, `--set full` captures of `k_stream`, `k_l2`, `k_am`,
 `k_channelize`; `scripts/profile_r2.sh`, `profile_r2b.sh`, `summarize_r2.py`), `r2_traffic.json` (DRAM bytes of `k_stream` per
 launch, read by `bench.py`), `r2_*_sass.txt` (SASS excerpts: tcgen05 / TMA / TMEM in `k_channelize`, the Costas loop's
-short chain, the AM decoder's packed recursion and cp.async traceback), `r2_overlap_probe.txt`, `r2_sanitizer.md`.
+short chain, the AM decoder's packed recursion and cp.async traceback), `r2_overlap_probe.txt`, `r2_sanitizer.md`,
+`r2_nvtx_launches.csv` (`ncu --nvtx` around `smoke()`: every launch with the engine's NVTX ranges - `nrsc5b_process` > `nrsc5b: pass` >
+`nrsc5b: P1/P3 decode groups`; header-only NVTX 3, no library linked).
 
 ### Bench line (20 steps, 3 warm-up; every leg carries an oracle gate)
 
