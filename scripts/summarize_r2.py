@@ -48,7 +48,7 @@ WANT = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "time us"), ("dram
         ("launch__block_size", "block"), ("launch__cluster_size", "cluster"), ("smsp__inst_executed.sum", "warp insts"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem conflicts")]
 traffic = {}
-for tag in ("k_stream", "k_l2", "k_am", "k_channelize"):
+for tag in ("k_stream", "k_l2", "k_am", "k_am_decim", "k_channelize"):
     raw = os.path.join(G, f"prof_r2_{tag}_raw.csv")
     if not os.path.exists(raw) or os.path.getsize(raw) < 100:
         continue
