@@ -28,7 +28,8 @@ out = f"""# profiles/ — measurements on the B200 (sm_100a, {j['clocks']['sm_mh
 
 Everything below the headline table comes from ONE `python bench.py` on a fresh box - the round's last GPU call
 (`scripts/gpu_run_s.sh`), its line kept as `r2_bench_final.json`; the same call ran `pytest -m gpu`
-(`r2_final_gpu_tests.log`), compute-sanitizer (`r2_sanitizer.md`) and the second ncu pass.  Files: `r2_ncu_summary.md` +
+(`r2_final_gpu_tests.log`: 98 passed) and compute-sanitizer on the cluster case; the other sanitizer cases and the ncu passes ran in
+the calls before it on the same kernels (`r2_sanitizer.md` says which).  Files: `r2_ncu_summary.md` +
 `launches_r2.csv` + `r2_k_*_raw.csv` (ncu: launch list of the headline step, `--set full` captures of `k_stream`, `k_l2`, `k_am`, `k_am_decim`,
 `k_channelize`; `scripts/profile_r2.sh`, `profile_r2b.sh`, `summarize_r2.py`), `r2_traffic.json` (DRAM bytes of `k_stream` per
 launch, read by `bench.py`), `r2_*_sass.txt` (SASS excerpts: tcgen05 / TMA / TMEM in `k_channelize`, the Costas loop's
