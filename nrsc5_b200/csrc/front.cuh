@@ -684,14 +684,25 @@ __device__ void front_demod(const DevPtrs &p, const EngineDims &d, int s, int sy
     const uint8_t *iq = p.iq + (size_t)s * d.in_stride;
     bar_sync(bar);                                       // the team has read the previous symbol's FFT buffer
     {
+        // the symbol's cu8 bytes go to shared memory by asynchronous 16-byte copies (cp.async.cg: through L2 only - samples
+        // may have landed after an earlier, partial read of the same line - and past the register file)
         const int nvec = (off + 4 * NSYM + 28 + 15) / 16;
         uint4 *dst = reinterpret_cast<uint4 *>(in);
         for (int v = tl; v < nvec; v += 128) {
             const long long a = b0a + 16LL * v;
-            // through L2 only: samples may have landed after an earlier (partial) read of the same line
-            dst[v] = a >= 0 ? __ldcg(reinterpret_cast<const uint4 *>(iq + a))
-                            : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+            if (a >= 0) {
+#if defined(NB_EMU)
+                dst[v] = *reinterpret_cast<const uint4 *>(iq + a);
+#else
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + v)), "l"(iq + a) : "memory");
+#endif
+            } else {
+                dst[v] = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);      // before the stream's first sample
+            }
         }
+#if !defined(NB_EMU)
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
     }
     if (tl == 0) {
         double sn, cs;
