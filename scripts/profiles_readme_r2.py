@@ -37,6 +37,9 @@ short chain, the AM decoder's packed recursion and cp.async traceback), `r2_over
 `r2_nvtx_launches.csv` (`ncu --nvtx` around `smoke()`: every launch with the engine's NVTX ranges - `nrsc5b_process` > `nrsc5b: pass` >
 `nrsc5b: P1/P3 decode groups`; header-only NVTX 3, no library linked).
 
+One change went in after that call: `k_stream` stages the cu8 symbols with `cp.async` (DESIGN.md §4).  With it the GPU suite was run
+again (98 passed) and the headline twice: 148 780 / 148 831 Msamples/s, 7.84 ms per step, demod 42.35 us per block, gate ok.
+
 ### Bench line (20 steps, 3 warm-up; every leg carries an oracle gate)
 
 | workload (BASELINE config) | value | x real time | ms / step | note |
